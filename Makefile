@@ -1,0 +1,27 @@
+# Builds the B200-native query library, the synthetic-corpus generator and the CPU oracle.
+NVCC ?= /usr/local/cuda/bin/nvcc
+CXX ?= g++
+ARCH := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS := -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC,-Wall,-Wno-unused-function -Iinclude
+CSRC := fugu_b200/csrc
+
+all: fugu_b200/libfugu_gpu.so fugu_b200/synth/libfugu_synth.so oracle/liboracle.so
+
+$(CSRC)/fg_kernels.o: $(CSRC)/fg_kernels.cu $(CSRC)/fg_internal.h
+	$(NVCC) $(NVFLAGS) -Xptxas -v -c $< -o $@
+$(CSRC)/fg_api.o: $(CSRC)/fg_api.cu $(CSRC)/fg_internal.h include/fugu_gpu.h
+	$(NVCC) $(NVFLAGS) -c $< -o $@
+
+fugu_b200/libfugu_gpu.so: $(CSRC)/fg_kernels.o $(CSRC)/fg_api.o
+	$(NVCC) -shared $(ARCH) -o $@ $^ -lpthread
+
+fugu_b200/synth/libfugu_synth.so: fugu_b200/synth/synth.cpp
+	$(CXX) -O3 -march=x86-64-v2 -std=c++17 -shared -fPIC -pthread -o $@ $<
+
+oracle/liboracle.so: oracle/oracle.cpp
+	$(CXX) -O3 -std=c++17 -shared -fPIC -pthread -o $@ $<
+
+clean:
+	rm -f $(CSRC)/*.o fugu_b200/libfugu_gpu.so fugu_b200/synth/libfugu_synth.so oracle/liboracle.so
+
+.PHONY: all clean

@@ -1,0 +1,712 @@
+// Host side of the C ABI (include/fugu_gpu.h): context, index snapshot upload (flat CSR ->
+// block-compressed HBM layout), plan lowering (fg_query_batch -> device plan + work items) and
+// batch execution. No CPU evaluation path exists here: without a CUDA device every compute entry
+// point returns FG_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/fugu_gpu.h"
+#include "fg_internal.h"
+
+using namespace fg;
+
+// ------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static int32_t fail(int32_t code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CU(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return fail(e_ == cudaErrorMemoryAllocation ? FG_ERR_OOM : FG_ERR_CUDA,           \
+                        "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+extern "C" const char* fg_last_error(void) { return g_err; }
+extern "C" const char* fg_version(void) { return "fugu_b200 0.1 (sm_100a)"; }
+
+// ------------------------------------------------------------------------------------------
+// tantivy fieldnorm code (Lucene SmallFloat byte4ToInt) and BM25 weight (A.4)
+// ------------------------------------------------------------------------------------------
+static uint32_t g_fn_table[256];
+static std::once_flag g_fn_once;
+static void fn_init() {
+    for (uint32_t b = 0; b < 256; b++) {
+        if (b < 24) { g_fn_table[b] = b; continue; }
+        uint32_t i = b - 24, bits = i & 7, shift = i >> 3;
+        uint32_t dec = shift == 0 ? bits : ((bits | 8u) << (shift - 1));
+        g_fn_table[b] = 24 + dec;
+    }
+}
+extern "C" uint32_t fg_id_to_fieldnorm(uint8_t id) {
+    std::call_once(g_fn_once, fn_init);
+    return g_fn_table[id];
+}
+extern "C" uint8_t fg_fieldnorm_to_id(uint32_t n) {
+    std::call_once(g_fn_once, fn_init);
+    // largest id with table[id] <= n
+    const uint32_t* p = std::upper_bound(g_fn_table, g_fn_table + 256, n);
+    return (uint8_t)((p - g_fn_table) - 1);
+}
+extern "C" float fg_bm25_idf(uint64_t df, uint64_t n) {
+    float x = ((float)(n - df) + 0.5f) / ((float)df + 0.5f);
+    return logf(1.0f + x);
+}
+static const float K1 = 1.2f, B = 0.75f;
+
+// ------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------
+struct fg_ctx {
+    int device = 0;
+    cudaStream_t own = nullptr;
+    cudaStream_t stream = nullptr;
+    std::mutex mu;
+    int n_sms = 0;
+};
+
+extern "C" int32_t fg_ctx_create(int32_t device, fg_ctx** out) {
+    if (!out) return fail(FG_ERR_INVALID, "fg_ctx_create: out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(FG_ERR_NO_DEVICE, "no CUDA device (%s); the query path has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail(FG_ERR_INVALID, "device %d out of range [0,%d)", device, n);
+    CU(cudaSetDevice(device));
+    cudaDeviceProp pr;
+    CU(cudaGetDeviceProperties(&pr, device));
+    if (pr.major < 10)
+        return fail(FG_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only",
+                    device, pr.major, pr.minor);
+    fg_ctx* c = new fg_ctx();
+    c->device = device;
+    c->n_sms = pr.multiProcessorCount;
+    CU(cudaStreamCreateWithFlags(&c->own, cudaStreamNonBlocking));
+    c->stream = c->own;
+    *out = c;
+    return FG_OK;
+}
+extern "C" void fg_ctx_destroy(fg_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->own) cudaStreamDestroy(c->own);
+    delete c;
+}
+extern "C" int32_t fg_ctx_set_stream(fg_ctx* c, void* s) {
+    if (!c) return fail(FG_ERR_INVALID, "ctx is NULL");
+    std::lock_guard<std::mutex> g(c->mu);
+    c->stream = s ? (cudaStream_t)s : c->own;
+    return FG_OK;
+}
+extern "C" int32_t fg_ctx_synchronize(fg_ctx* c) {
+    if (!c) return fail(FG_ERR_INVALID, "ctx is NULL");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    return FG_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// index snapshot
+// ------------------------------------------------------------------------------------------
+struct TermInfo {
+    uint32_t blk_begin, n_blocks, df_local, df_global;
+    uint64_t bytes;  // packed payload + 16 B skip per block
+};
+struct HostField {
+    uint32_t flags = 0;
+    uint32_t n_terms = 0;
+    uint64_t total_tokens = 0;
+    float cnorm = 0.f;
+    std::vector<TermInfo> terms;
+};
+struct fg_index {
+    fg_ctx* ctx = nullptr;
+    uint32_t n_docs = 0, doc_base = 0;
+    uint64_t global_n_docs = 0;
+    std::vector<HostField> fields;
+    fg_index_info info{};
+    DevIndex dev{};
+    std::vector<void*> allocs;
+};
+
+static int host_threads() {
+    unsigned h = std::thread::hardware_concurrency();
+    const char* e = getenv("FG_HOST_THREADS");
+    if (e) h = (unsigned)atoi(e);
+    return (int)std::max(1u, std::min(h ? h : 4u, 64u));
+}
+static inline uint32_t bits_of(uint32_t v) { return v ? 32 - __builtin_clz(v) : 0; }
+
+template <class F>
+static void parallel_for(uint64_t n, int T, F f) {
+    if (n == 0) return;
+    T = (int)std::min<uint64_t>((uint64_t)T, n);
+    if (T <= 1) { f(0, n, 0); return; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < T; t++) th.emplace_back([=]() { f(n * t / T, n * (t + 1) / T, t); });
+    for (auto& x : th) x.join();
+}
+
+static void pack_stream(uint32_t* words, const uint32_t* vals, uint32_t n, uint32_t b) {
+    // little-endian horizontal stream, value i at bit i*b; caller zeroed `words` (4*b words)
+    if (b == 0) return;
+    for (uint32_t i = 0; i < n; i++) {
+        uint64_t bp = (uint64_t)i * b;
+        uint32_t wi = (uint32_t)(bp >> 5), sh = (uint32_t)(bp & 31);
+        uint64_t v = (uint64_t)vals[i] << sh;
+        words[wi] |= (uint32_t)v;
+        if (sh + b > 32) words[wi + 1] |= (uint32_t)(v >> 32);
+    }
+}
+
+extern "C" void fg_index_release(fg_index* ix) {
+    if (!ix) return;
+    if (ix->ctx) cudaSetDevice(ix->ctx->device);
+    for (void* p : ix->allocs) cudaFree(p);
+    delete ix;
+}
+
+extern "C" int32_t fg_index_upload(fg_ctx* ctx, const fg_index_desc* d, fg_index** out) {
+    if (!ctx || !d || !out) return fail(FG_ERR_INVALID, "fg_index_upload: NULL argument");
+    *out = nullptr;
+    if (d->n_fields == 0 || d->n_fields > (uint32_t)MAX_FIELDS || !d->fields)
+        return fail(FG_ERR_INVALID, "n_fields must be in [1,%d]", MAX_FIELDS);
+    std::call_once(g_fn_once, fn_init);
+    CU(cudaSetDevice(ctx->device));
+    std::unique_ptr<fg_index, void (*)(fg_index*)> ix(new fg_index(), fg_index_release);
+    ix->ctx = ctx;
+    ix->n_docs = d->n_docs;
+    ix->doc_base = d->doc_id_base;
+    ix->global_n_docs = d->global_n_docs ? d->global_n_docs : d->n_docs;
+    ix->fields.resize(d->n_fields);
+    const int T = host_threads();
+
+    // ---- block counts per term ----
+    uint64_t n_blocks = 0, n_postings = 0;
+    for (uint32_t f = 0; f < d->n_fields; f++) {
+        const fg_field_desc& fd = d->fields[f];
+        HostField& hf = ix->fields[f];
+        hf.flags = fd.flags;
+        hf.n_terms = fd.n_terms;
+        hf.total_tokens = fd.total_num_tokens;
+        hf.terms.resize(fd.n_terms);
+        if (fd.n_terms && (!fd.term_offsets || !fd.doc_ids))
+            return fail(FG_ERR_INVALID, "field %u: term_offsets/doc_ids NULL", f);
+        if ((fd.flags & FG_FIELD_HAS_FIELDNORMS) && !fd.fieldnorm_ids && d->n_docs)
+            return fail(FG_ERR_INVALID, "field %u: HAS_FIELDNORMS but fieldnorm_ids NULL", f);
+        for (uint32_t t = 0; t < fd.n_terms; t++) {
+            if (fd.term_offsets[t + 1] < fd.term_offsets[t])
+                return fail(FG_ERR_INVALID, "field %u: term_offsets not monotone at %u", f, t);
+            uint64_t n = fd.term_offsets[t + 1] - fd.term_offsets[t];
+            if (n > d->n_docs) return fail(FG_ERR_INVALID, "field %u term %u: df > n_docs", f, t);
+            TermInfo& ti = hf.terms[t];
+            ti.df_local = (uint32_t)n;
+            ti.df_global = fd.global_doc_freq ? fd.global_doc_freq[t] : (uint32_t)n;
+            if (ti.df_global < ti.df_local)
+                return fail(FG_ERR_INVALID, "field %u term %u: global df < local df", f, t);
+            ti.n_blocks = (uint32_t)((n + BLOCK - 1) / BLOCK);
+            if (n_blocks + ti.n_blocks > 0xFFFFFFF0ull) return fail(FG_ERR_UNSUPPORTED, "too many blocks");
+            ti.blk_begin = (uint32_t)n_blocks;
+            ti.bytes = 0;
+            n_blocks += ti.n_blocks;
+            n_postings += n;
+        }
+    }
+
+    // ---- pass A: per-block bit widths (parallel over terms of each field) ----
+    std::vector<SkipEntry> skip(n_blocks);
+    std::vector<uint8_t> wsum(n_blocks);  // bd + bt (16-byte units of payload)
+    std::vector<int> bad(T, 0);
+    for (uint32_t f = 0; f < d->n_fields; f++) {
+        const fg_field_desc& fd = d->fields[f];
+        HostField& hf = ix->fields[f];
+        const bool freqs = (fd.flags & FG_FIELD_HAS_FREQS) && fd.term_freqs;
+        parallel_for(fd.n_terms, T, [&](uint64_t a, uint64_t b, int tix) {
+            for (uint64_t t = a; t < b; t++) {
+                const TermInfo& ti = hf.terms[t];
+                const uint32_t* docs = fd.doc_ids + fd.term_offsets[t];
+                const uint32_t* tfs = freqs ? fd.term_freqs + fd.term_offsets[t] : nullptr;
+                uint32_t prev_plus1 = 0;  // previous doc + 1
+                for (uint32_t bi = 0; bi < ti.n_blocks; bi++) {
+                    const uint32_t i0 = bi * BLOCK, n = std::min<uint32_t>(BLOCK, ti.df_local - i0);
+                    uint32_t gor = 0, tor = 0, p = prev_plus1;
+                    for (uint32_t i = 0; i < n; i++) {
+                        const uint32_t dd = docs[i0 + i];
+                        if (dd < p || dd >= d->n_docs) { bad[tix] = 1; break; }
+                        gor |= dd - p;
+                        p = dd + 1;
+                        if (tfs) {
+                            if (tfs[i0 + i] == 0) { bad[tix] = 1; break; }
+                            tor |= tfs[i0 + i] - 1;
+                        }
+                    }
+                    const uint32_t bd = bits_of(gor), bt = bits_of(tor);
+                    SkipEntry& e = skip[ti.blk_begin + bi];
+                    e.last_doc = docs[i0 + n - 1];
+                    e.first_base = prev_plus1;
+                    e.off16 = 0;
+                    e.packed = pack_meta(bd, bt, n);
+                    wsum[ti.blk_begin + bi] = (uint8_t)(bd + bt);
+                    prev_plus1 = p;
+                }
+            }
+        });
+    }
+    for (int t = 0; t < T; t++)
+        if (bad[t])
+            return fail(FG_ERR_INVALID, "postings must be strictly ascending, < n_docs, with tf >= 1");
+
+    // ---- offsets ----
+    uint64_t off16 = 0;
+    for (uint64_t b = 0; b < n_blocks; b++) {
+        if (off16 > 0xFFFFFFFFull) return fail(FG_ERR_UNSUPPORTED, "packed payload exceeds 64 GiB");
+        skip[b].off16 = (uint32_t)off16;
+        off16 += wsum[b];
+    }
+    const uint64_t payload = off16 * 16;
+    for (uint32_t f = 0; f < d->n_fields; f++)
+        for (auto& ti : ix->fields[f].terms) {
+            uint64_t by = 0;
+            for (uint32_t bi = 0; bi < ti.n_blocks; bi++) by += (uint64_t)wsum[ti.blk_begin + bi] * 16 + 16;
+            ti.bytes = by;
+        }
+
+    // ---- pass B: pack (parallel) ----
+    std::vector<uint32_t> blk((payload + 64) / 4, 0);
+    for (uint32_t f = 0; f < d->n_fields; f++) {
+        const fg_field_desc& fd = d->fields[f];
+        HostField& hf = ix->fields[f];
+        const bool freqs = (fd.flags & FG_FIELD_HAS_FREQS) && fd.term_freqs;
+        parallel_for(fd.n_terms, T, [&](uint64_t a, uint64_t b, int) {
+            uint32_t gaps[BLOCK], tfm[BLOCK];
+            for (uint64_t t = a; t < b; t++) {
+                const TermInfo& ti = hf.terms[t];
+                const uint32_t* docs = fd.doc_ids + fd.term_offsets[t];
+                const uint32_t* tfs = freqs ? fd.term_freqs + fd.term_offsets[t] : nullptr;
+                for (uint32_t bi = 0; bi < ti.n_blocks; bi++) {
+                    const SkipEntry& e = skip[ti.blk_begin + bi];
+                    const uint32_t bd = e.packed & 63, bt = (e.packed >> 6) & 63;
+                    const uint32_t i0 = bi * BLOCK, n = ((e.packed >> 12) & 127) + 1;
+                    uint32_t p = e.first_base;
+                    for (uint32_t i = 0; i < n; i++) {
+                        gaps[i] = docs[i0 + i] - p;
+                        p = docs[i0 + i] + 1;
+                        tfm[i] = tfs ? tfs[i0 + i] - 1 : 0;
+                    }
+                    uint32_t* w = blk.data() + (size_t)e.off16 * 4;
+                    pack_stream(w, gaps, n, bd);
+                    pack_stream(w + 4 * bd, tfm, n, bt);
+                }
+            }
+        });
+    }
+
+    // ---- BM25 norm caches from GLOBAL statistics ----
+    std::vector<float> cache((size_t)MAX_FIELDS * 256, 0.f);
+    for (uint32_t f = 0; f < d->n_fields; f++) {
+        const float avg = (float)ix->fields[f].total_tokens / (float)ix->global_n_docs;
+        for (int i = 0; i < 256; i++)
+            cache[f * 256 + i] = K1 * (1.0f - B + B * (float)g_fn_table[i] / avg);
+        ix->fields[f].cnorm = cache[f * 256 + fg_fieldnorm_to_id(1)];
+    }
+
+    // ---- upload ----
+    auto dev_copy = [&](const void* src, size_t bytes, const void** dst) -> int32_t {
+        void* p = nullptr;
+        CU(cudaMalloc(&p, std::max<size_t>(bytes, 16)));
+        ix->allocs.push_back(p);
+        if (bytes) CU(cudaMemcpy(p, src, bytes, cudaMemcpyHostToDevice));
+        *dst = p;
+        ix->info.device_bytes += bytes;
+        return FG_OK;
+    };
+    int32_t rc;
+    if ((rc = dev_copy(skip.data(), n_blocks * sizeof(SkipEntry), (const void**)&ix->dev.skip))) return rc;
+    if ((rc = dev_copy(blk.data(), blk.size() * 4, (const void**)&ix->dev.blk))) return rc;
+    if ((rc = dev_copy(cache.data(), cache.size() * 4, (const void**)&ix->dev.cache))) return rc;
+    for (uint32_t f = 0; f < d->n_fields; f++) {
+        ix->dev.fnorm[f] = nullptr;
+        if (d->fields[f].flags & FG_FIELD_HAS_FIELDNORMS)
+            if ((rc = dev_copy(d->fields[f].fieldnorm_ids, d->n_docs, (const void**)&ix->dev.fnorm[f]))) return rc;
+    }
+    ix->dev.alive = nullptr;
+    if (d->alive_bitset)
+        if ((rc = dev_copy(d->alive_bitset, ((size_t)d->n_docs + 31) / 32 * 4, (const void**)&ix->dev.alive))) return rc;
+    ix->dev.n_docs = d->n_docs;
+    ix->dev.doc_base = d->doc_id_base;
+
+    ix->info.n_postings = n_postings;
+    ix->info.n_blocks = n_blocks;
+    ix->info.packed_bytes = payload;
+    ix->info.skip_bytes = n_blocks * 16;
+    ix->info.n_docs = d->n_docs;
+    ix->info.n_fields = d->n_fields;
+    *out = ix.release();
+    return FG_OK;
+}
+
+extern "C" int32_t fg_index_get_info(const fg_index* ix, fg_index_info* out) {
+    if (!ix || !out) return fail(FG_ERR_INVALID, "NULL argument");
+    *out = ix->info;
+    return FG_OK;
+}
+extern "C" int32_t fg_index_term_info(const fg_index* ix, uint32_t field, uint32_t term,
+                                      uint32_t* ldf, uint32_t* gdf, uint32_t* nb, uint64_t* bytes) {
+    if (!ix) return fail(FG_ERR_INVALID, "NULL index");
+    if (field >= ix->fields.size() || term >= ix->fields[field].n_terms)
+        return fail(FG_ERR_INVALID, "field/term out of range");
+    const TermInfo& t = ix->fields[field].terms[term];
+    if (ldf) *ldf = t.df_local;
+    if (gdf) *gdf = t.df_global;
+    if (nb) *nb = t.n_blocks;
+    if (bytes) *bytes = t.bytes;
+    return FG_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// plan lowering
+// ------------------------------------------------------------------------------------------
+struct fg_batch {
+    fg_index* ix = nullptr;
+    uint32_t n_queries = 0, n_items = 0, kcap = 0;
+    int ks = 1;
+    uint64_t sum_k = 0;
+    DevQuery* d_queries = nullptr;
+    DevLeaf* d_leaves = nullptr;
+    DevItem* d_items = nullptr;
+    uint64_t* d_partial = nullptr;
+    uint32_t* d_partial_count = nullptr;
+    unsigned long long* d_stats = nullptr;
+    uint64_t n_launches = 0;
+};
+
+static uint64_t env_u64(const char* name, uint64_t dflt) {
+    const char* e = getenv(name);
+    return e ? strtoull(e, nullptr, 10) : dflt;
+}
+
+extern "C" void fg_batch_release(fg_batch* b) {
+    if (!b) return;
+    if (b->ix && b->ix->ctx) cudaSetDevice(b->ix->ctx->device);
+    cudaFree(b->d_queries); cudaFree(b->d_leaves); cudaFree(b->d_items);
+    cudaFree(b->d_partial); cudaFree(b->d_partial_count); cudaFree(b->d_stats);
+    delete b;
+}
+
+namespace {
+struct LClause {
+    uint32_t occur;
+    uint64_t cost;  // bytes (work estimate)
+    uint64_t df;    // sum of local doc freqs = tantivy's scorer cost (Intersection order)
+    std::vector<DevLeaf> leaves;
+};
+}  // namespace
+
+extern "C" int32_t fg_batch_prepare(fg_index* ix, const fg_query_batch* qb, fg_batch** out) {
+    if (!ix || !qb || !out) return fail(FG_ERR_INVALID, "fg_batch_prepare: NULL argument");
+    *out = nullptr;
+    if (qb->n_queries && (!qb->queries || (qb->n_clauses && !qb->clauses) || (qb->n_leaves && !qb->leaves)))
+        return fail(FG_ERR_INVALID, "fg_batch_prepare: NULL arrays");
+    const uint64_t ITEM_BYTES = env_u64("FG_ITEM_BYTES", 65536);
+    const uint64_t DENSE_MIN = env_u64("FG_DENSE_MIN", 1536);  // insert postings per dense window
+    const uint32_t HASH_MIN_SPAN = 4096;
+
+    std::vector<DevQuery> dq(qb->n_queries);
+    std::vector<DevLeaf> dl;
+    std::vector<DevItem> items;
+    std::vector<uint64_t> item_cost;
+    uint32_t kmax = 1;
+    uint64_t sum_k = 0;
+    const uint64_t N = ix->global_n_docs;
+
+    for (uint32_t qi = 0; qi < qb->n_queries; qi++) {
+        const fg_query& q = qb->queries[qi];
+        if (q.k == 0) return fail(FG_ERR_INVALID, "query %u: k == 0 (TopDocs::with_limit requires limit >= 1)", qi);
+        if (q.k > 128) return fail(FG_ERR_UNSUPPORTED, "query %u: k = %u > 128 not supported yet", qi, q.k);
+        if ((uint64_t)q.clause_begin + q.n_clauses > qb->n_clauses)
+            return fail(FG_ERR_INVALID, "query %u: clause range out of bounds", qi);
+        kmax = std::max(kmax, q.k);
+        sum_k += q.k;
+        std::vector<LClause> must, should, mnot;
+        float const_score = 0.f;
+        bool empty = false;   // a Must clause that can never match
+        bool has_all_only = false;
+        for (uint32_t ci = 0; ci < q.n_clauses; ci++) {
+            const fg_clause& c = qb->clauses[q.clause_begin + ci];
+            if ((uint64_t)c.leaf_begin + c.n_leaves > qb->n_leaves)
+                return fail(FG_ERR_INVALID, "query %u: leaf range out of bounds", qi);
+            if (c.occur > FG_OCCUR_MUST_NOT) return fail(FG_ERR_INVALID, "query %u: bad occur", qi);
+            LClause lc;
+            lc.occur = c.occur;
+            lc.cost = 0;
+            lc.df = 0;
+            bool all = false;
+            float all_boost = 0.f;
+            for (uint32_t li = 0; li < c.n_leaves; li++) {
+                const fg_leaf& lf = qb->leaves[c.leaf_begin + li];
+                if (lf.term_ord == FG_TERM_ALL) { all = true; all_boost += lf.boost; continue; }
+                if (lf.term_ord == FG_TERM_MISSING) continue;
+                if (lf.field >= ix->fields.size()) return fail(FG_ERR_INVALID, "query %u: field %u out of range", qi, lf.field);
+                const HostField& hf = ix->fields[lf.field];
+                if (lf.term_ord >= hf.n_terms) return fail(FG_ERR_INVALID, "query %u: term_ord out of range", qi);
+                const TermInfo& ti = hf.terms[lf.term_ord];
+                if (ti.df_global == 0) continue;  // empty scorer
+                DevLeaf L{};
+                L.blk_begin = ti.blk_begin;
+                L.n_blocks = ti.n_blocks;
+                L.weight = lf.boost * (fg_bm25_idf(ti.df_global, N) * (1.0f + K1));
+                L.cnorm = hf.cnorm;
+                L.fn_field = (hf.flags & FG_FIELD_HAS_FIELDNORMS) ? (int32_t)lf.field : -1;
+                if (ti.n_blocks == 0) continue;  // present globally, absent in this shard
+                lc.cost += ti.bytes;
+                lc.df += ti.df_local;
+                lc.leaves.push_back(L);
+            }
+            if (all) {
+                if (c.occur == FG_OCCUR_MUST && lc.leaves.empty()) { const_score += all_boost; has_all_only = true; continue; }
+                return fail(FG_ERR_UNSUPPORTED, "query %u: AllQuery leaf outside a Must clause is not supported", qi);
+            }
+            if (lc.leaves.empty()) {
+                if (c.occur == FG_OCCUR_MUST) empty = true;
+                continue;
+            }
+            (c.occur == FG_OCCUR_MUST ? must : c.occur == FG_OCCUR_SHOULD ? should : mnot).push_back(std::move(lc));
+        }
+        DevQuery& D = dq[qi];
+        memset(&D, 0, sizeof(D));
+        D.k = q.k;
+        D.const_score = const_score;
+        D.leaf_begin = (uint32_t)dl.size();
+        if (has_all_only && must.empty() && !empty) {
+            if (should.empty() && mnot.empty())
+                return fail(FG_ERR_UNSUPPORTED, "query %u: pure AllQuery is answered by the host (first k alive docs)", qi);
+            return fail(FG_ERR_UNSUPPORTED, "query %u: AllQuery Must with only Should/MustNot siblings not supported", qi);
+        }
+        if (empty || (must.empty() && should.empty())) { D.n_leaves = 0; D.n_items = 0; D.item_begin = (uint32_t)items.size(); continue; }
+        if (must.size() > (size_t)MAX_MUST) return fail(FG_ERR_UNSUPPORTED, "query %u: more than %d Must clauses", qi, MAX_MUST);
+        std::stable_sort(must.begin(), must.end(), [](const LClause& a, const LClause& b) { return a.df < b.df; });
+
+        std::vector<DevLeaf> ql;
+        uint64_t insert_postings = 0, total_bytes = 0;
+        auto leaf_df = [&](const DevLeaf& L) { return (uint64_t)L.n_blocks * BLOCK; };
+        if (!must.empty()) {
+            D.all_must = (1u << must.size()) - 1u;
+            for (size_t ci = 0; ci < must.size(); ci++) {
+                for (size_t li = 0; li < must[ci].leaves.size(); li++) {
+                    DevLeaf L = must[ci].leaves[li];
+                    L.bit = 1u << ci;
+                    L.role = ci == 0 ? ROLE_INSERT : ROLE_MUST;
+                    L.req = (1u << ci) - 1u;
+                    if (ci == 0) insert_postings += leaf_df(L);
+                    ql.push_back(L);
+                }
+                total_bytes += must[ci].cost;
+            }
+            D.n_insert = (uint32_t)must[0].leaves.size();
+            for (auto& c : should)
+                for (auto L : c.leaves) { L.bit = 0; L.role = ROLE_SHOULD; L.req = D.all_must; ql.push_back(L); }
+            for (auto& c : should) total_bytes += c.cost / 4;
+        } else {
+            D.all_must = BIT_SHOULD;
+            D.flags |= QF_NO_MUST;
+            for (auto& c : should) {
+                for (auto L : c.leaves) { L.bit = BIT_SHOULD; L.role = ROLE_INSERT; L.req = 0; insert_postings += leaf_df(L); ql.push_back(L); }
+                total_bytes += c.cost;
+            }
+            D.n_insert = (uint32_t)ql.size();
+        }
+        for (auto& c : mnot) {
+            for (auto L : c.leaves) { L.bit = BIT_NOT; L.role = ROLE_NOT; L.req = 0; ql.push_back(L); }
+            total_bytes += c.cost / 4;
+        }
+        if (ql.size() > (size_t)MAX_LEAVES)
+            return fail(FG_ERR_UNSUPPORTED, "query %u: %zu live leaves > %d", qi, ql.size(), MAX_LEAVES);
+        // candidate-bitmap rebuild points: after the last leaf of a clause when the next leaf filters
+        for (size_t i = 0; i + 1 < ql.size(); i++) {
+            const DevLeaf& nx = ql[i + 1];
+            if (nx.role == ROLE_INSERT) continue;
+            const bool boundary = ql[i].role != nx.role || ql[i].bit != nx.bit;
+            if (!boundary) continue;
+            if (ql[i].role == ROLE_SHOULD) continue;  // bitmap of all-Must candidates is still valid
+            // mask the NEXT leaf's docs must carry (MustNot filters on the matching candidates)
+            ql[i].build_cb = nx.role == ROLE_NOT ? D.all_must : nx.req;
+        }
+        D.n_leaves = (uint32_t)ql.size();
+        for (auto& L : ql) dl.push_back(L);
+
+        // ---- mode + work items ----
+        const uint32_t nd = ix->n_docs;
+        const uint32_t mode = (insert_postings * (uint64_t)DW >= DENSE_MIN * (uint64_t)std::max<uint32_t>(nd, 1)) ? MODE_DENSE : MODE_HASH;
+        uint64_t want = std::max<uint64_t>(1, (total_bytes + ITEM_BYTES / 2) / ITEM_BYTES);
+        const uint32_t min_span = mode == MODE_DENSE ? (uint32_t)DW : HASH_MIN_SPAN;
+        const uint64_t max_items = std::max<uint64_t>(1, nd / min_span);
+        const uint32_t ni = (uint32_t)std::min(want, max_items);
+        D.item_begin = (uint32_t)items.size();
+        D.n_items = ni;
+        for (uint32_t j = 0; j < ni; j++) {
+            DevItem it{};
+            it.query = qi;
+            it.doc_lo = (uint32_t)((uint64_t)nd * j / ni);
+            it.doc_hi = (uint32_t)((uint64_t)nd * (j + 1) / ni);
+            it.mode = mode;
+            it.slot = D.item_begin + j;
+            items.push_back(it);
+            item_cost.push_back(total_bytes / ni);
+        }
+    }
+
+    // heavy items first (the hardware CTA scheduler is the work queue)
+    std::vector<uint32_t> order(items.size());
+    for (uint32_t i = 0; i < order.size(); i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return item_cost[a] > item_cost[b]; });
+    std::vector<DevItem> sorted(items.size());
+    for (size_t i = 0; i < order.size(); i++) sorted[i] = items[order[i]];
+
+    fg_ctx* ctx = ix->ctx;
+    CU(cudaSetDevice(ctx->device));
+    std::unique_ptr<fg_batch, void (*)(fg_batch*)> b(new fg_batch(), fg_batch_release);
+    b->ix = ix;
+    b->n_queries = qb->n_queries;
+    b->n_items = (uint32_t)items.size();
+    b->kcap = kmax;
+    b->ks = kmax <= 32 ? 1 : 4;
+    b->sum_k = sum_k;
+    auto up = [&](const void* src, size_t bytes, void** dst) -> int32_t {
+        CU(cudaMalloc(dst, std::max<size_t>(bytes, 16)));
+        if (bytes) CU(cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        return FG_OK;
+    };
+    int32_t rc;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    if ((rc = up(dq.data(), dq.size() * sizeof(DevQuery), (void**)&b->d_queries))) return rc;
+    if ((rc = up(dl.data(), dl.size() * sizeof(DevLeaf), (void**)&b->d_leaves))) return rc;
+    if ((rc = up(sorted.data(), sorted.size() * sizeof(DevItem), (void**)&b->d_items))) return rc;
+    CU(cudaMalloc((void**)&b->d_partial, std::max<size_t>((size_t)b->n_items * b->kcap * 8, 16)));
+    CU(cudaMalloc((void**)&b->d_partial_count, std::max<size_t>((size_t)b->n_items * 4, 16)));
+    CU(cudaMalloc((void**)&b->d_stats, 4 * sizeof(unsigned long long)));
+    CU(cudaStreamSynchronize(ctx->stream));  // host vectors go out of scope
+    *out = b.release();
+    return FG_OK;
+}
+
+extern "C" int32_t fg_batch_execute(fg_batch* b, uint32_t flags, uint32_t k_stride, void* d_hits,
+                                    void* d_n_hits, void* d_match_count, void* d_match_bitmap) {
+    if (!b || !d_hits || !d_n_hits) return fail(FG_ERR_INVALID, "fg_batch_execute: NULL argument");
+    if (k_stride < b->kcap) return fail(FG_ERR_INVALID, "k_stride %u < max k %u", k_stride, b->kcap);
+    fg_index* ix = b->ix;
+    fg_ctx* ctx = ix->ctx;
+    CU(cudaSetDevice(ctx->device));
+    std::lock_guard<std::mutex> g(ctx->mu);
+    cudaStream_t st = ctx->stream;
+    CU(cudaMemsetAsync(b->d_stats, 0, 4 * sizeof(unsigned long long), st));
+    SearchParams p{};
+    p.ix = ix->dev;
+    p.queries = b->d_queries;
+    p.leaves = b->d_leaves;
+    p.items = b->d_items;
+    p.n_items = b->n_items;
+    p.kcap = b->kcap;
+    p.partial = b->d_partial;
+    p.partial_count = b->d_partial_count;
+    p.stats = b->d_stats;
+    p.match_bitmap = (uint32_t*)d_match_bitmap;
+    p.bitmap_words = (ix->n_docs + 31) / 32;
+    p.exact_filter = (flags & FG_EXEC_EXACT_ACCOUNTING) ? 1 : 0;
+    launch_search(p, b->ks, st);
+    MergeParams m{};
+    m.queries = b->d_queries;
+    m.n_queries = b->n_queries;
+    m.kcap = b->kcap;
+    m.partial = b->d_partial;
+    m.partial_count = b->d_partial_count;
+    m.k_stride = k_stride;
+    m.doc_base = ix->doc_base;
+    m.out_hits = d_hits;
+    m.out_n = (uint32_t*)d_n_hits;
+    m.out_count = (uint32_t*)d_match_count;
+    launch_merge(m, b->ks, st);
+    b->n_launches = (b->n_items ? 1 : 0) + (b->n_queries ? 1 : 0);
+    CU(cudaGetLastError());
+    return FG_OK;
+}
+
+extern "C" int32_t fg_batch_get_stats(fg_batch* b, fg_batch_stats* out) {
+    if (!b || !out) return fail(FG_ERR_INVALID, "NULL argument");
+    fg_ctx* ctx = b->ix->ctx;
+    CU(cudaSetDevice(ctx->device));
+    unsigned long long h[4];
+    {
+        std::lock_guard<std::mutex> g(ctx->mu);
+        CU(cudaStreamSynchronize(ctx->stream));
+        CU(cudaMemcpy(h, b->d_stats, sizeof(h), cudaMemcpyDeviceToHost));
+    }
+    out->bytes_blocks = h[0];
+    out->bytes_redecode = h[1];
+    out->scored_postings = h[2];
+    out->n_work_items = b->n_items;
+    out->n_launches = b->n_launches;
+    out->n_queries = b->n_queries;
+    out->sum_k = b->sum_k;
+    return FG_OK;
+}
+
+extern "C" int32_t fg_search_batch(fg_index* ix, const fg_query_batch* qb, uint32_t k_stride,
+                                   fg_hit* out_hits, uint32_t* out_n_hits, uint32_t* out_match_count) {
+    if (!ix || !qb || !out_hits || !out_n_hits) return fail(FG_ERR_INVALID, "fg_search_batch: NULL argument");
+    fg_batch* b = nullptr;
+    int32_t rc = fg_batch_prepare(ix, qb, &b);
+    if (rc) return rc;
+    std::unique_ptr<fg_batch, void (*)(fg_batch*)> guard(b, fg_batch_release);
+    if (k_stride < b->kcap) return fail(FG_ERR_INVALID, "k_stride %u < max k %u", k_stride, b->kcap);
+    fg_ctx* ctx = ix->ctx;
+    const size_t nq = qb->n_queries;
+    if (nq == 0) return FG_OK;
+    void *d_hits = nullptr, *d_n = nullptr, *d_c = nullptr;
+    CU(cudaMalloc(&d_hits, nq * k_stride * sizeof(fg_hit)));
+    std::unique_ptr<void, void (*)(void*)> g1(d_hits, [](void* p) { cudaFree(p); });
+    CU(cudaMalloc(&d_n, nq * 4));
+    std::unique_ptr<void, void (*)(void*)> g2(d_n, [](void* p) { cudaFree(p); });
+    CU(cudaMalloc(&d_c, nq * 4));
+    std::unique_ptr<void, void (*)(void*)> g3(d_c, [](void* p) { cudaFree(p); });
+    rc = fg_batch_execute(b, 0, k_stride, d_hits, d_n, d_c, nullptr);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    CU(cudaMemcpyAsync(out_hits, d_hits, nq * k_stride * sizeof(fg_hit), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(out_n_hits, d_n, nq * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_match_count) CU(cudaMemcpyAsync(out_match_count, d_c, nq * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return FG_OK;
+}
+
+extern "C" int32_t fg_merge_topk_device(fg_ctx* ctx, const void* d_hits, const void* d_n,
+                                        uint32_t n_ranks, uint32_t n_queries, uint32_t k,
+                                        uint32_t k_stride, void* d_out_hits, void* d_out_n) {
+    if (!ctx || !d_hits || !d_n || !d_out_hits || !d_out_n) return fail(FG_ERR_INVALID, "NULL argument");
+    if (k == 0 || k > 128 || k > k_stride) return fail(FG_ERR_INVALID, "k must be in [1, min(128, k_stride)]");
+    CU(cudaSetDevice(ctx->device));
+    std::lock_guard<std::mutex> g(ctx->mu);
+    launch_merge_gathered(d_hits, (const uint32_t*)d_n, n_ranks, n_queries, k, k_stride, d_out_hits,
+                          (uint32_t*)d_out_n, k <= 32 ? 1 : 4, ctx->stream);
+    CU(cudaGetLastError());
+    return FG_OK;
+}

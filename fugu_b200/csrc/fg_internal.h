@@ -1,0 +1,124 @@
+// Internal structures shared by the host side (layout builder, plan lowering) and the kernels.
+// Not part of the ABI (include/fugu_gpu.h is).
+#pragma once
+#include <stdint.h>
+
+namespace fg {
+
+// ---- HBM posting layout ----------------------------------------------------------------------
+// A term's postings are cut into blocks of 128. Block b stores
+//   gaps  g_i = doc_i - doc_{i-1} - 1  (doc_{-1} = first_base - 1), bit-packed with `bd` bits each,
+//   tf_i - 1                             bit-packed with `bt` bits each,
+// as two little-endian horizontal bit streams (value i at bit i*width), doc stream first, each
+// padded to 128 values, so a block occupies 16*(bd+bt) bytes and starts 16-byte aligned.
+// One 16-byte skip entry per block:
+struct SkipEntry {
+    uint32_t last_doc;    // doc id of the last posting of the block
+    uint32_t first_base;  // previous block's last_doc + 1 (0 for a term's first block)
+    uint32_t off16;       // payload offset in 16-byte units
+    uint32_t packed;      // bd[0:6) | bt[6:12) | (n-1)[12:19)
+};
+constexpr int BLOCK = 128;
+static inline uint32_t pack_meta(uint32_t bd, uint32_t bt, uint32_t n) {
+    return bd | (bt << 6) | ((n - 1) << 12);
+}
+
+constexpr int MAX_FIELDS = 8;     // fields per index
+constexpr int MAX_LEAVES = 16;    // live leaves per query on the device
+constexpr int MAX_MUST = 6;       // Must clauses per query (mask bits 0..5)
+constexpr uint32_t BIT_SHOULD = 0x40, BIT_NOT = 0x80;
+
+// leaf roles, in evaluation order inside a query
+enum : uint32_t { ROLE_INSERT = 0, ROLE_MUST = 1, ROLE_SHOULD = 2, ROLE_NOT = 3 };
+
+struct DevLeaf {
+    uint32_t blk_begin;  // first skip entry of the term
+    uint32_t n_blocks;
+    float weight;        // boost * idf * (1 + K1), from GLOBAL statistics
+    float cnorm;         // constant BM25 norm when the field has no fieldnorms
+    int32_t fn_field;    // field slot for fieldnorm ids / cache table, -1 = use cnorm
+    uint32_t bit;        // mask bit this leaf's clause sets
+    uint32_t role;
+    uint32_t req;        // mask bits a slot must already carry (filter roles)
+    uint32_t build_cb;   // rebuild the candidate bitmap after this leaf (mask value to test), 0 = no
+    uint32_t pad[3];
+};
+
+constexpr uint32_t MODE_DENSE = 0, MODE_HASH = 1;
+constexpr uint32_t QF_NO_MUST = 1;
+
+struct DevQuery {
+    uint32_t leaf_begin;
+    uint32_t n_leaves;
+    uint32_t n_insert;    // leading leaves with ROLE_INSERT
+    uint32_t k;
+    uint32_t all_must;    // mask a matching slot must equal (low 7 bits)
+    uint32_t flags;
+    float const_score;    // sum of Must AllQuery scores
+    uint32_t item_begin;  // work items of this query are contiguous in the partial arrays
+    uint32_t n_items;
+    uint32_t pad[3];
+};
+
+struct DevItem {
+    uint32_t query;
+    uint32_t doc_lo, doc_hi;
+    uint32_t mode;
+    uint32_t slot;  // index into partial arrays (query.item_begin + j)
+    uint32_t pad[3];
+};
+
+struct DevIndex {
+    const uint4* skip;
+    const uint8_t* blk;
+    const uint8_t* fnorm[MAX_FIELDS];
+    const float* cache;  // [MAX_FIELDS][256]
+    const uint32_t* alive;
+    uint32_t n_docs;
+    uint32_t doc_base;
+};
+
+struct SearchParams {
+    DevIndex ix;
+    const DevQuery* queries;
+    const DevLeaf* leaves;
+    const DevItem* items;
+    uint32_t n_items;
+    uint32_t kcap;               // entries per partial list
+    uint64_t* partial;           // [n_items][kcap] sortable keys, 0 = empty
+    uint32_t* partial_count;     // [n_items] matching docs
+    unsigned long long* stats;   // [4]: bytes_blocks, bytes_redecode, scored, -
+    uint32_t* match_bitmap;      // optional
+    uint32_t bitmap_words;
+    uint32_t exact_filter;
+};
+
+struct MergeParams {
+    const DevQuery* queries;
+    uint32_t n_queries;
+    uint32_t kcap;
+    const uint64_t* partial;
+    const uint32_t* partial_count;
+    uint32_t k_stride;
+    uint32_t doc_base;
+    void* out_hits;        // fg_hit [n_queries][k_stride]
+    uint32_t* out_n;
+    uint32_t* out_count;   // may be null
+};
+
+// kernel geometry
+constexpr int NT = 256;          // threads per CTA
+constexpr int NW = NT / 32;      // warps per CTA
+constexpr int DW = 8192;         // dense window: docs per round
+constexpr int HS = 4096;         // hash slots per round
+constexpr int HBLK = 16;         // insert-leaf blocks per hash round (<= HS/2/128)
+constexpr int CBW = 256;         // candidate bitmap words (8192 bits)
+
+void launch_search(const SearchParams& p, int ks, void* stream);
+void launch_merge(const MergeParams& p, int ks, void* stream);
+void launch_merge_gathered(const void* hits, const uint32_t* n, uint32_t n_ranks, uint32_t n_queries,
+                           uint32_t k, uint32_t k_stride, void* out_hits, uint32_t* out_n, int ks,
+                           void* stream);
+int search_smem_bytes(int ks);
+
+}  // namespace fg

@@ -1,0 +1,200 @@
+/* fugu_gpu.h — C ABI of the B200-native query hot path for fugu.
+ *
+ * What this replaces in the reference (paths relative to /root/reference):
+ *   the single call  `searcher.search(&base_query, &TopDocs::with_limit(search_limit))`
+ *   at src/db/search.rs:162, i.e. posting decode -> boolean AND/OR -> BM25 -> top-k, which today
+ *   runs inside the un-vendored crate tantivy 0.24.1 (Cargo.toml:48, Cargo.lock:4609-4612).
+ *   Everything before that line (query parsing / planning, src/db/search.rs:86-160) and after it
+ *   (hit hydration / pagination, src/db/search.rs:169-217) stays on the host.
+ *
+ * Contract:
+ *   - plain C, plain pointers and sizes; no torch / C++ types cross the boundary;
+ *   - every entry point returns an int32 status (FG_OK = 0, negative = error) and never unwinds;
+ *     fg_last_error() returns a thread-local message for the last failing call on this thread;
+ *   - thread-safe and re-entrant: axum handlers call Dataset::search concurrently
+ *     (src/server/server_main.rs:50, src/db/config.rs:188-190); calls on one fg_ctx serialise on its
+ *     stream; an fg_index is an immutable snapshot (mirrors a tantivy `Searcher`);
+ *   - inputs are borrowed for the duration of the call, fg_index_upload copies, results are written
+ *     into caller-allocated buffers, handles are released by explicit *_destroy / *_release;
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *     FG_ERR_NO_DEVICE.
+ *
+ * Semantics implemented on the device are tantivy 0.24.1's as fugu configures them
+ * (SURVEY.md Appendix A): BM25 with K1 = 1.2, B = 0.75 in f32, 256-entry fieldnorm table,
+ * boolean Must / Should / MustNot with one level of grouping, TopDocs order
+ * (score descending, doc id ascending).
+ */
+#ifndef FUGU_GPU_H
+#define FUGU_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes (src/db/search.rs:79 returns Result<_, Box<dyn Error>>; HTTP 500 on Err,
+ *      src/server/handlers/search.rs:196-205) ---- */
+#define FG_OK 0
+#define FG_ERR_INVALID (-1)     /* bad argument (NULL, k == 0: TopDocs::with_limit asserts limit >= 1) */
+#define FG_ERR_UNSUPPORTED (-2) /* plan node the device path does not evaluate (phrase, range, deep trees) */
+#define FG_ERR_CUDA (-3)        /* CUDA runtime error; message in fg_last_error() */
+#define FG_ERR_OOM (-4)
+#define FG_ERR_NO_DEVICE (-5)   /* no CUDA device: the product never falls back to a CPU path */
+
+const char* fg_last_error(void);
+const char* fg_version(void);
+
+/* ---- context: one per (process, device) ---- */
+typedef struct fg_ctx fg_ctx;
+int32_t fg_ctx_create(int32_t device, fg_ctx** out);
+void fg_ctx_destroy(fg_ctx* ctx);
+/* Run all work of this context on `cuda_stream` (a cudaStream_t / CUstream, e.g. torch's current
+ * stream) instead of the context's own stream. NULL restores the own stream. */
+int32_t fg_ctx_set_stream(fg_ctx* ctx, void* cuda_stream);
+int32_t fg_ctx_synchronize(fg_ctx* ctx);
+
+/* ---- index snapshot ----------------------------------------------------------------------
+ * The reference-side loader walks tantivy's PUBLIC per-segment API
+ * (SegmentReader::inverted_index(field), term stream, read_postings(.., WithFreqs),
+ * get_fieldnorms_reader, alive_bitset) and hands over one flat CSR per field, so this library never
+ * parses tantivy's private files (src/db/core.rs:53-55,238-245 own them).
+ * Doc ids are shard-local, dense, 0..n_docs; `doc_id_base` is added to every reported hit. */
+#define FG_FIELD_HAS_FIELDNORMS 1u /* TEXT fields (src/db/schemas.rs:9-17); facet fields have none */
+#define FG_FIELD_HAS_FREQS 2u      /* term_freqs given; otherwise tf == 1 (facet / Basic postings) */
+
+typedef struct {
+    uint32_t flags;
+    uint32_t n_terms;
+    uint64_t total_num_tokens;       /* GLOBAL over all shards/segments (Bm25Weight average fieldnorm) */
+    const uint8_t* fieldnorm_ids;    /* [n_docs] tantivy fieldnorm ids, or NULL (constant norm 1) */
+    const uint64_t* term_offsets;    /* [n_terms + 1] into doc_ids / term_freqs */
+    const uint32_t* doc_ids;         /* strictly ascending within a term */
+    const uint32_t* term_freqs;      /* or NULL */
+    const uint32_t* global_doc_freq; /* [n_terms] df summed over all shards, or NULL = local df */
+} fg_field_desc;
+
+typedef struct {
+    uint32_t n_docs;              /* docs of this shard = sum of max_doc of its segments */
+    uint32_t doc_id_base;         /* global doc id of local doc 0 */
+    uint64_t global_n_docs;       /* sum of max_doc over ALL shards; 0 = n_docs */
+    uint32_t n_fields;
+    uint32_t reserved;
+    const fg_field_desc* fields;  /* field id = position in this array */
+    const uint32_t* alive_bitset; /* [ceil(n_docs/32)] bit set = alive, or NULL = all alive */
+} fg_index_desc;
+
+typedef struct fg_index fg_index;
+int32_t fg_index_upload(fg_ctx* ctx, const fg_index_desc* desc, fg_index** out);
+void fg_index_release(fg_index* index);
+
+typedef struct {
+    uint64_t n_postings;
+    uint64_t n_blocks;
+    uint64_t packed_bytes;  /* bit-packed doc/tf payload */
+    uint64_t skip_bytes;    /* 16 B per block */
+    uint64_t device_bytes;  /* everything resident in HBM for this snapshot */
+    uint32_t n_docs;
+    uint32_t n_fields;
+} fg_index_info;
+int32_t fg_index_get_info(const fg_index* index, fg_index_info* out);
+/* document frequency / layout of one term (host copy of the term table) */
+int32_t fg_index_term_info(const fg_index* index, uint32_t field, uint32_t term_ord,
+                           uint32_t* local_df, uint32_t* global_df, uint32_t* n_blocks,
+                           uint64_t* packed_bytes);
+
+/* ---- query plan ---------------------------------------------------------------------------
+ * One level of grouping, which is what Dataset::search builds (src/db/search.rs:108-151):
+ *   clause = (occur, leaves[]); leaves inside a clause are OR-ed and their scores summed
+ *            (word -> (text:w OR name:w) expansion; the facet Should-group of build_facet_query,
+ *             src/db/search.rs:221-289);
+ *   query  = clauses[]; Must clauses intersect, Should clauses add score (and select docs when there
+ *            is no Must clause), MustNot clauses exclude. */
+#define FG_OCCUR_SHOULD 0u
+#define FG_OCCUR_MUST 1u
+#define FG_OCCUR_MUST_NOT 2u
+#define FG_TERM_MISSING 0xFFFFFFFFu /* term absent from the dictionary: empty scorer */
+#define FG_TERM_ALL 0xFFFFFFFEu     /* AllQuery leaf (src/db/search.rs:115-116,258-261): score 1.0 */
+
+typedef struct {
+    uint32_t field;
+    uint32_t term_ord;
+    float boost; /* 1.0 unless `term^boost` */
+} fg_leaf;
+
+typedef struct {
+    uint32_t occur;
+    uint32_t leaf_begin; /* into fg_query_batch.leaves */
+    uint32_t n_leaves;
+} fg_clause;
+
+typedef struct {
+    uint32_t k;            /* TopDocs limit = page*per_page + per_page (src/db/search.rs:154-160) */
+    uint32_t clause_begin; /* into fg_query_batch.clauses */
+    uint32_t n_clauses;
+} fg_query;
+
+typedef struct {
+    uint32_t n_queries;
+    uint32_t n_clauses;
+    uint32_t n_leaves;
+    uint32_t reserved;
+    const fg_query* queries;
+    const fg_clause* clauses;
+    const fg_leaf* leaves;
+} fg_query_batch;
+
+typedef struct {
+    float score;
+    uint32_t doc; /* global doc id = doc_id_base + local id */
+} fg_hit;
+
+/* The reference-facing call: host buffers in, host buffers out, blocking.
+ * out_hits[q*k_stride + r] = r-th best hit of query q (score desc, doc asc); out_n_hits[q] <= k;
+ * out_match_count[q] (may be NULL) = number of documents matching query q on this shard. */
+int32_t fg_search_batch(fg_index* index, const fg_query_batch* batch, uint32_t k_stride,
+                        fg_hit* out_hits, uint32_t* out_n_hits, uint32_t* out_match_count);
+
+/* ---- split-phase form (batches resident in HBM; CUDA-event timing; multi-GPU merge) --------- */
+typedef struct fg_batch fg_batch;
+/* lowers the plan (weights from GLOBAL statistics, work items) and uploads it to the device */
+int32_t fg_batch_prepare(fg_index* index, const fg_query_batch* batch, fg_batch** out);
+void fg_batch_release(fg_batch* b);
+#define FG_EXEC_EXACT_ACCOUNTING 1u /* exact block-need test for the algorithmic-byte counters (slow) */
+/* Launches the search kernels for the prepared batch on the context's stream (asynchronous).
+ * d_hits [n_queries*k_stride] fg_hit, d_n_hits [n_queries], d_match_count [n_queries] or NULL:
+ * DEVICE pointers. d_match_bitmap: NULL, or DEVICE [n_queries * ceil(n_docs/32)] words, zeroed by
+ * the caller, in which every matching local doc id gets its bit set (parity tests). */
+int32_t fg_batch_execute(fg_batch* b, uint32_t flags, uint32_t k_stride, void* d_hits,
+                         void* d_n_hits, void* d_match_count, void* d_match_bitmap);
+
+typedef struct {
+    uint64_t bytes_blocks;    /* packed bytes + 16 B skip entry of every block decoded (counted once) */
+    uint64_t bytes_redecode;  /* bytes of blocks decoded again (round/work-item boundaries) */
+    uint64_t scored_postings; /* (doc, leaf) pairs scored = 1 B fieldnorm gathers */
+    uint64_t n_work_items;
+    uint64_t n_launches;      /* kernels launched by the last fg_batch_execute */
+    uint64_t n_queries;
+    uint64_t sum_k;           /* sum of k over queries (8 B result per hit) */
+} fg_batch_stats;
+/* synchronises the stream and reads the device counters of the last fg_batch_execute */
+int32_t fg_batch_get_stats(fg_batch* b, fg_batch_stats* out);
+
+/* Merge of per-shard results after the all-gather: `d_gathered_hits` is
+ * [n_ranks][n_queries][k_stride] fg_hit, `d_gathered_n` is [n_ranks][n_queries]; writes the k best
+ * per query under (score desc, doc asc) to d_out_hits [n_queries][k_stride] / d_out_n. All DEVICE
+ * pointers; asynchronous on the context's stream. */
+int32_t fg_merge_topk_device(fg_ctx* ctx, const void* d_gathered_hits, const void* d_gathered_n,
+                             uint32_t n_ranks, uint32_t n_queries, uint32_t k, uint32_t k_stride,
+                             void* d_out_hits, void* d_out_n);
+
+/* ---- scoring helpers shared with the host planner (tantivy fieldnorm / Bm25Weight) ---------- */
+uint8_t fg_fieldnorm_to_id(uint32_t num_tokens);
+uint32_t fg_id_to_fieldnorm(uint8_t id);
+float fg_bm25_idf(uint64_t doc_freq, uint64_t doc_count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FUGU_GPU_H */

@@ -1,0 +1,71 @@
+"""ctypes binding of oracle/liboracle.so (the C++ restatement in oracle/oracle.cpp).
+
+TEST INFRASTRUCTURE ONLY — the product (fugu_b200/) never imports this module.
+It consumes the very same fg_index_desc / fg_query_batch structures the GPU library is given.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from fugu_b200 import _native as nat
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(_HERE, "liboracle.so")
+_lib = None
+
+
+def build() -> None:
+    src = os.path.join(_HERE, "oracle.cpp")
+    if os.path.exists(LIB) and os.path.getmtime(LIB) >= os.path.getmtime(src):
+        return
+    subprocess.check_call(["g++", "-O3", "-std=c++17", "-shared", "-fPIC", "-pthread", "-o", LIB, src])
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB):
+            build()
+        L = C.CDLL(LIB)
+        vp, u32, u64, i32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int32
+        L.orc_fieldnorm_to_id.argtypes = [u32]
+        L.orc_fieldnorm_to_id.restype = C.c_uint8
+        L.orc_id_to_fieldnorm.argtypes = [C.c_uint8]
+        L.orc_id_to_fieldnorm.restype = u32
+        L.orc_idf.argtypes = [u64, u64]
+        L.orc_idf.restype = C.c_float
+        L.orc_bm25_score.argtypes = [C.c_float, u64, u64, u64, C.c_uint8, u32]
+        L.orc_bm25_score.restype = C.c_float
+        L.orc_search_batch.argtypes = [C.POINTER(nat.IndexDesc), C.POINTER(nat.QueryBatch), u32, vp, vp, vp, vp, i32]
+        L.orc_search_batch.restype = i32
+        L.orc_algorithmic_bytes.argtypes = [C.POINTER(nat.IndexDesc), C.POINTER(nat.QueryBatch), vp, vp, i32]
+        L.orc_algorithmic_bytes.restype = i32
+        _lib = L
+    return _lib
+
+
+def search(desc: nat.HostIndexDesc, batch: nat.HostBatch, k_stride: int | None = None, threads: int = 1,
+           want_bitmap: bool = False):
+    ks = k_stride or batch.kmax
+    hits = np.zeros((batch.n_queries, ks), nat.HIT_DT)
+    n = np.zeros(batch.n_queries, np.uint32)
+    cnt = np.zeros(batch.n_queries, np.uint32)
+    words = (desc.n_docs + 31) // 32
+    bm = np.zeros((batch.n_queries, words), np.uint32) if want_bitmap else None
+    rc = lib().orc_search_batch(C.byref(desc.desc), C.byref(batch.batch), ks, hits.ctypes.data, n.ctypes.data,
+                                cnt.ctypes.data, None if bm is None else bm.ctypes.data, threads)
+    if rc != 0:
+        raise nat.FgError(rc, "oracle")
+    return (hits, n, cnt, bm) if want_bitmap else (hits, n, cnt)
+
+
+def algorithmic_bytes(desc: nat.HostIndexDesc, batch: nat.HostBatch, threads: int = 1):
+    b = np.zeros(batch.n_queries, np.uint64)
+    s = np.zeros(batch.n_queries, np.uint64)
+    rc = lib().orc_algorithmic_bytes(C.byref(desc.desc), C.byref(batch.batch), b.ctypes.data, s.ctypes.data, threads)
+    assert rc == 0
+    return b, s

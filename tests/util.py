@@ -1,0 +1,120 @@
+"""Shared helpers of the parity tests: a tiny planner for the synthetic "wN" query grammar, the
+tolerance-aware top-k comparison and the GPU-vs-oracle batch check."""
+from __future__ import annotations
+
+import numpy as np
+
+from fugu_b200 import _native as nat
+
+REL_TOL = 1e-5  # BASELINE.json north_star: BM25 scores within 1e-5 relative in f32
+
+
+def plan_queries(qs: list[dict], vocab: int, n_text_fields: int = 1, facet_lookup=None) -> nat.HostBatch:
+    """Lower synthetic fugu-syntax strings ("w3 AND w9", "w3 w9 w41") the way Dataset::search does
+    (src/db/search.rs:108-151): each word -> Should group over the default fields [text, name];
+    AND -> Must clauses, whitespace -> Should clauses; filters -> one Must clause OR-ing the facet
+    terms. term ordinal of "wN" is N-1."""
+    out = []
+    for q in qs:
+        s = q["query"]
+        conj = " AND " in s
+        words = [w for w in s.replace(" AND ", " ").split() if w]
+        clauses = []
+        for w in words:
+            r = int(w[1:])
+            t = r - 1 if 1 <= r <= vocab else nat.FG_TERM_MISSING
+            leaves = [(f, t, 1.0) for f in range(n_text_fields)]
+            clauses.append((nat.FG_OCCUR_MUST if conj else nat.FG_OCCUR_SHOULD, leaves))
+        filters = q.get("filters") or []
+        if filters:
+            # Bool[Must(text_query), Must(facet group)]: Should words collapse into one Must clause
+            if not conj:
+                merged = [l for _, ls in clauses for l in ls]
+                clauses = [(nat.FG_OCCUR_MUST, merged)]
+            fl = []
+            for f in filters:
+                fid, t = facet_lookup(f)
+                fl.append((fid, t, 1.0))
+            clauses.append((nat.FG_OCCUR_MUST, fl))
+        out.append({"k": q["k"], "clauses": clauses})
+    return nat.HostBatch(out)
+
+
+def close(a: float, b: float, tol: float = REL_TOL) -> bool:
+    return abs(a - b) <= tol * max(abs(a), abs(b), 1e-30)
+
+
+def check_topk(g: np.ndarray, o: np.ndarray, k: int, tol: float = REL_TOL, ctx: str = "") -> None:
+    """g, o: HIT_DT arrays of equal length (the valid hits). Scores must agree rank-wise within
+    tol; doc ids must agree except inside runs of scores tied within tol (and such a run may be
+    cut differently only when it touches the k-th position)."""
+    assert len(g) == len(o), f"{ctx}: n_hits {len(g)} != {len(o)}"
+    n = len(o)
+    for i in range(n):
+        assert close(float(g["score"][i]), float(o["score"][i]), tol), \
+            f"{ctx}: rank {i}: score {g['score'][i]!r} vs oracle {o['score'][i]!r}"
+    i = 0
+    while i < n:
+        j = i
+        while j + 1 < n and close(float(o["score"][j + 1]), float(o["score"][j]), 4 * tol):
+            j += 1
+        gd, od = set(g["doc"][i:j + 1].tolist()), set(o["doc"][i:j + 1].tolist())
+        if gd != od:
+            assert j == n - 1 and n == k, f"{ctx}: ranks {i}..{j}: docs {sorted(gd)} vs oracle {sorted(od)}"
+        i = j + 1
+
+
+def gpu_search_device(index: nat.Index, batch: nat.HostBatch, want_bitmap: bool = False, flags: int = 0):
+    """Split-phase path with device buffers provided by torch; returns numpy results (+ stats)."""
+    import torch
+
+    ks = batch.kmax
+    nq = batch.n_queries
+    dev = torch.device("cuda:0")
+    d_hits = torch.zeros((nq, ks, 2), dtype=torch.int32, device=dev)
+    d_n = torch.zeros(nq, dtype=torch.int32, device=dev)
+    d_c = torch.zeros(nq, dtype=torch.int32, device=dev)
+    words = (index.n_docs + 31) // 32
+    d_bm = torch.zeros((nq, words), dtype=torch.int32, device=dev) if want_bitmap else None
+    torch.cuda.synchronize()
+    pb = index.prepare(batch)
+    pb.execute(d_hits.data_ptr(), d_n.data_ptr(), d_c.data_ptr(), None if d_bm is None else d_bm.data_ptr(),
+               k_stride=ks, flags=flags)
+    st = pb.stats()
+    index.ctx.synchronize()
+    hits = d_hits.cpu().numpy().view(np.uint32).reshape(nq, ks, 2)
+    out = np.zeros((nq, ks), nat.HIT_DT)
+    out["score"] = hits[:, :, 0].view(np.float32)
+    out["doc"] = hits[:, :, 1]
+    res = (out, d_n.cpu().numpy().view(np.uint32), d_c.cpu().numpy().view(np.uint32),
+           None if d_bm is None else d_bm.cpu().numpy().view(np.uint32), st)
+    pb.close()
+    return res
+
+
+def check_batch_against_oracle(index: nat.Index, desc: nat.HostIndexDesc, batch: nat.HostBatch,
+                               bitmaps: bool = True, threads: int = 4) -> dict:
+    """GPU (through the C ABI) vs oracle on the same descriptor + plan: matched doc-id sets and
+    counts bit-exact, scores within REL_TOL, order identical modulo ties."""
+    from oracle import orc
+
+    if bitmaps:
+        o_hits, o_n, o_c, o_bm = orc.search(desc, batch, threads=threads, want_bitmap=True)
+    else:
+        o_hits, o_n, o_c = orc.search(desc, batch, threads=threads)
+        o_bm = None
+    g_hits, g_n, g_c, g_bm, st = gpu_search_device(index, batch, want_bitmap=bitmaps)
+    # also through the blocking host-buffer call
+    h_hits, h_n, h_c = index.search(batch)
+    assert np.array_equal(h_n, g_n) and np.array_equal(h_c, g_c)
+    assert np.array_equal(h_hits["doc"], g_hits["doc"]) and np.array_equal(h_hits["score"], g_hits["score"])
+    bad = np.nonzero(g_c != o_c)[0]
+    assert len(bad) == 0, f"match counts differ for queries {bad[:10]}: gpu {g_c[bad[:10]]} oracle {o_c[bad[:10]]}"
+    assert np.array_equal(g_n, o_n), f"n_hits differ: {np.nonzero(g_n != o_n)[0][:10]}"
+    if bitmaps:
+        diff = np.nonzero((g_bm != o_bm).any(axis=1))[0]
+        assert len(diff) == 0, f"matched doc-id sets differ for queries {diff[:10]}"
+    for qi in range(batch.n_queries):
+        n = int(o_n[qi])
+        check_topk(g_hits[qi, :n], o_hits[qi, :n], int(batch.q["k"][qi]), ctx=f"query {qi}")
+    return {"stats": st, "o_counts": o_c}
