@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""bench.py — fugu query hot path on B200: queries/s + algorithmic posting GB/s vs the HBM roofline.
+
+Workload (BASELINE.json configs[1], SURVEY.md 8(d) "C2"): 1M-doc synthetic Zipfian corpus
+(vocab 200k, 10% of docs carry metadata.name), 5000 mixed 1-4-term AND/OR queries, top-10.
+A "step" = one pass of the hot path (posting decode -> AND/OR -> BM25 -> top-k, + per-query merge)
+over the whole 5000-query batch.
+
+  value    : queries/s with the index AND the lowered query batch resident in HBM, CUDA-event time
+  e2e      : queries/s through the reference-facing blocking call fg_search_batch with HOST buffers
+             (plan lowering, H2D of the plan, kernels, D2H of hits inside the timed region)
+  roofline : algorithmic posting bytes of one search_kernel launch / its CUDA-event duration vs
+             MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline / --impl reference : the CPU oracle (restatement of tantivy 0.24.1 semantics — the
+             real reference cannot be built here: no Rust toolchain) on the box's host cores.
+
+N > 1 (torchrun): documents are sharded by doc-id range (strong scaling: fixed corpus), every rank
+evaluates the whole batch on its shard, local top-k -> all_gather (NCCL) -> on-device merge.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--docs", type=int, default=1_000_000)
+    ap.add_argument("--vocab", type=int, default=200_000)
+    ap.add_argument("--queries", type=int, default=5_000)
+    ap.add_argument("--cfg", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
+    return ap.parse_args()
+
+
+def env_rank():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_model() -> str:
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.lines: list[str] = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1])); mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_workload(args, rank: int, world: int):
+    """Corpus shard of this rank (doc-id range), the query strings and the lowered plan."""
+    from fugu_b200 import _native as nat
+    from fugu_b200 import synth
+
+    base = synth.CONFIGS[args.cfg]
+    cfg = synth.Config(cfg=base.cfg, n_docs=args.docs, vocab=args.vocab, n_queries=args.queries, k=base.k,
+                       name_pct=base.name_pct, n_ns=base.n_ns)
+    corpus = synth.Corpus.for_config(cfg)
+    d0, d1 = cfg.n_docs * rank // world, cfg.n_docs * (rank + 1) // world
+    fields = synth.build_fields(corpus, d0, d1)
+    queries = synth.gen_queries(cfg)
+    return cfg, corpus, fields, queries, d0, d1
+
+
+def peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path on the box's host cores. The real reference
+    (Rust + tantivy 0.24.1) cannot be built here, so this is the oracle port (oracle/oracle.cpp)."""
+    rank, _, world = env_rank()
+    if rank != 0:
+        return
+    from fugu_b200 import _native as nat
+    from fugu_b200 import synth
+    from oracle import orc
+
+    cfg, corpus, fields, queries, d0, d1 = build_workload(args, 0, 1)
+    desc = nat.HostIndexDesc(cfg.n_docs, fields)
+    n_fields = len(fields)
+    cores = host_cores()
+    # bounded sample: each step = the whole batch when it is small enough, else a prefix
+    nq = min(len(queries), 5000)
+    sample = queries[:nq]
+    times = []
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        batch = synth.lower_queries(sample, vocab=cfg.vocab, n_text_fields=n_fields)  # planning inside, as on the GPU e2e arm
+        orc.search(desc, batch, threads=cores)
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append(dt)
+    tot = sum(times)
+    qps = nq * len(times) / tot
+    line = {
+        "impl": "reference", "metric": "queries_per_sec", "value": qps, "unit": "queries/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(times), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(cfg, args, 1),
+        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port",
+                         "sample": f"{nq} of {len(queries)} queries per step, oracle C++ (exhaustive DAAT, -O3), "
+                                   f"{cores} threads one query per thread, cpu: {cpu_model()}"},
+        "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(cfg, args, world):
+    return {"workload": f"C{cfg.cfg}: {cfg.n_docs}-doc synthetic Zipfian corpus (vocab {cfg.vocab}, {cfg.name_pct}% docs with name), "
+                        f"{cfg.n_queries} mixed 1-4-term AND/OR queries, top-{cfg.k}",
+            "n_docs": cfg.n_docs, "n_queries": cfg.n_queries, "k": cfg.k,
+            "sharding": f"doc-id range x{world}" if world > 1 else "single shard",
+            "l2": "index fits L2 (126 MB): L2 flushed (256 MiB memset) before every timed step" if not args.no_flush else "warm L2 (no flush)"}
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    rank, local_rank, world = env_rank()
+    import torch
+
+    from fugu_b200 import _native as nat
+    from fugu_b200 import synth
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device: the product has no CPU fallback"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfg, corpus, fields, queries, d0, d1 = build_workload(args, rank, world)
+    n_local = d1 - d0
+    if world > 1:
+        # global statistics (tantivy computes N, df and total_num_tokens over all segments, A.4)
+        for f in fields:
+            df = torch.from_numpy(np.diff(f["term_offsets"]).astype(np.int64)).to(dev)
+            dist.all_reduce(df)
+            f["global_doc_freq"] = df.cpu().numpy().astype(np.uint32)
+            tt = torch.tensor([f["total_num_tokens"]], dtype=torch.int64, device=dev)
+            dist.all_reduce(tt)
+            f["total_num_tokens"] = int(tt.item())
+    desc = nat.HostIndexDesc(n_local, fields, doc_id_base=d0, global_n_docs=cfg.n_docs)
+    ctx = nat.Context(local_rank)
+    stream = torch.cuda.current_stream(dev)
+    ctx.set_stream(stream.cuda_stream)
+    t0 = time.perf_counter()
+    index = nat.Index(ctx, desc)
+    upload_s = time.perf_counter() - t0
+    info = index.info()
+    n_fields = len(fields)
+    batch = synth.lower_queries(queries, vocab=cfg.vocab, n_text_fields=n_fields)
+    nq, k = batch.n_queries, batch.kmax
+    pb = index.prepare(batch)
+
+    d_hits = torch.zeros((nq, k, 2), dtype=torch.int32, device=dev)
+    d_n = torch.zeros(nq, dtype=torch.int32, device=dev)
+    d_c = torch.zeros(nq, dtype=torch.int32, device=dev)
+    if world > 1:
+        g_hits = torch.zeros((world, nq, k, 2), dtype=torch.int32, device=dev)
+        g_n = torch.zeros((world, nq), dtype=torch.int32, device=dev)
+        f_hits = torch.zeros((nq, k, 2), dtype=torch.int32, device=dev)
+        f_n = torch.zeros(nq, dtype=torch.int32, device=dev)
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step():
+        pb.execute(d_hits.data_ptr(), d_n.data_ptr(), d_c.data_ptr(), None, k_stride=k)
+        if world > 1:
+            dist.all_gather_into_tensor(g_hits, d_hits)
+            dist.all_gather_into_tensor(g_n, d_n)
+            nat.merge_topk_device(ctx, g_hits.data_ptr(), g_n.data_ptr(), world, nq, k, k, f_hits.data_ptr(), f_n.data_ptr())
+
+    # exact algorithmic-byte accounting pass (untimed)
+    pb.execute(d_hits.data_ptr(), d_n.data_ptr(), d_c.data_ptr(), None, k_stride=k, flags=nat.FG_EXEC_EXACT_ACCOUNTING)
+    st = pb.stats()
+    algo_bytes = st.bytes_blocks + st.scored_postings + 8 * st.sum_k
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kern_ms = []
+    torch.cuda.synchronize()
+    for i in range(args.steps):
+        if not args.no_flush:
+            flush_buf.fill_(i & 0xFF)
+        ev[i][0].record(stream)
+        step()
+        ev[i][1].record(stream)
+        if i % 4 == 3 or i == args.steps - 1:
+            s2 = pb.stats()  # synchronises; per-launch search-kernel time from the library's own events
+            kern_ms.append(s2.search_kernel_ms)
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = sum(a.elapsed_time(b) for a, b in ev)
+    if dist:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+        ab = torch.tensor([float(algo_bytes)], dtype=torch.float64, device=dev)
+        dist.all_reduce(ab)
+        algo_total = float(ab.item())
+    else:
+        algo_total = float(algo_bytes)
+    st_timed = pb.stats()
+    ms_per_step = total_ms / args.steps
+    qps = nq / (ms_per_step * 1e-3)
+
+    # ---- e2e through the blocking host-buffer ABI call ----
+    e2e_times = []
+    for it in range(2 + min(args.steps, 10)):
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        hb = synth.lower_queries(queries, vocab=cfg.vocab, n_text_fields=n_fields)  # query strings -> plan (host)
+        h_hits, h_n, h_c = index.search(hb)
+        if world > 1:
+            dist.all_gather_into_tensor(g_hits, torch.from_numpy(h_hits.view(np.int32).reshape(nq, k, 2)).to(dev))
+            dist.all_gather_into_tensor(g_n, torch.from_numpy(h_n.view(np.int32)).to(dev))
+            nat.merge_topk_device(ctx, g_hits.data_ptr(), g_n.data_ptr(), world, nq, k, k, f_hits.data_ptr(), f_n.data_ptr())
+            f_hits.cpu(); f_n.cpu()
+        dt = time.perf_counter() - t0
+        if it >= 2:
+            e2e_times.append(dt)
+    e2e_s = float(np.mean(e2e_times))
+    if dist:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    plan_bytes = batch.q.nbytes + batch.c.nbytes + batch.l.nbytes
+    lowered_bytes = nq * 48 + len(batch.l) * 48 + st.n_work_items * 32
+    out_bytes = nq * k * 8 + nq * 8
+
+    if rank != 0:
+        if dist:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = peak_hbm()
+    kms = float(np.mean(kern_ms)) if kern_ms else ms_per_step
+    achieved = algo_bytes / (kms * 1e-3) / 1e9  # this rank's launch
+    line = {
+        "metric": "queries_per_sec", "value": qps, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(cfg, args, world),
+        "posting_gbs": algo_total / (ms_per_step * 1e-3) / 1e9,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src, "kernel": "search_kernel",
+                     "kernel_ms": kms, "algorithmic_bytes_per_launch": int(algo_bytes),
+                     "bytes_per_query": algo_bytes / nq,
+                     "touched_block_bytes": int(st_timed.bytes_blocks), "redecode_bytes": int(st_timed.bytes_redecode),
+                     "note": "index (%.0f MB) fits the 126 MB L2; L2 is flushed before each timed step" % (info.device_bytes / 1e6)},
+        "e2e": {"value": nq / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": int(lowered_bytes),
+                "d2h_bytes_per_step": int(out_bytes), "ms_per_step": e2e_s * 1e3,
+                "what": "query strings -> host plan lowering -> fg_search_batch (host buffers; H2D plan, kernels, D2H hits)"},
+        "gpu_launches": int(st_timed.n_launches + (1 if world > 1 else 0)) * args.steps,
+        "clocks": clocks,
+        "index": {"postings": int(info.n_postings), "blocks": int(info.n_blocks), "packed_bytes": int(info.packed_bytes),
+                  "device_bytes": int(info.device_bytes), "upload_s": upload_s, "work_items": int(st.n_work_items)},
+    }
+    if not args.no_cpu_baseline:
+        from oracle import orc  # cpu_baseline leg: the one place bench.py may run the oracle (as the measured CPU arm)
+
+        odesc = nat.HostIndexDesc(n_local, fields, doc_id_base=d0, global_n_docs=cfg.n_docs) if world > 1 else desc
+        cores = host_cores()
+        ns = min(nq, 5000)
+        sub = synth.lower_queries(queries[:ns], vocab=cfg.vocab, n_text_fields=n_fields)
+        best = None
+        t_end = time.perf_counter() + 20
+        for _ in range(3):
+            t0 = time.perf_counter()
+            orc.search(odesc, sub, threads=cores)
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+            if time.perf_counter() > t_end:
+                break
+        t0 = time.perf_counter()
+        orc.search(odesc, synth.lower_queries(queries[:max(1, ns // 10)], vocab=cfg.vocab, n_text_fields=n_fields), threads=1)
+        dt1 = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": ns / best, "unit": "queries/s", "cores": cores, "kind": "port",
+                                "single_thread_qps": max(1, ns // 10) / dt1,
+                                "sample": f"first {ns} queries of the batch on rank 0's shard, best of 3, oracle C++ "
+                                          f"(restatement of tantivy 0.24.1 semantics, exhaustive DAAT), {cores} threads; cpu: {cpu_model()}"}
+    print(json.dumps(line), flush=True)
+    if dist:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

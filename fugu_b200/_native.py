@@ -94,6 +94,8 @@ class BatchStats(C.Structure):
         ("n_launches", C.c_uint64),
         ("n_queries", C.c_uint64),
         ("sum_k", C.c_uint64),
+        ("search_kernel_ms", C.c_float),
+        ("merge_kernel_ms", C.c_float),
     ]
 
 

@@ -398,6 +398,7 @@ struct fg_batch {
     uint32_t* d_partial_count = nullptr;
     unsigned long long* d_stats = nullptr;
     uint64_t n_launches = 0;
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};  // before search, after search, after merge
 };
 
 static uint64_t env_u64(const char* name, uint64_t dflt) {
@@ -410,6 +411,7 @@ extern "C" void fg_batch_release(fg_batch* b) {
     if (b->ix && b->ix->ctx) cudaSetDevice(b->ix->ctx->device);
     cudaFree(b->d_queries); cudaFree(b->d_leaves); cudaFree(b->d_items);
     cudaFree(b->d_partial); cudaFree(b->d_partial_count); cudaFree(b->d_stats);
+    for (auto& e : b->ev) if (e) cudaEventDestroy(e);
     delete b;
 }
 
@@ -604,6 +606,7 @@ extern "C" int32_t fg_batch_prepare(fg_index* ix, const fg_query_batch* qb, fg_b
     CU(cudaMalloc((void**)&b->d_partial, std::max<size_t>((size_t)b->n_items * b->kcap * 8, 16)));
     CU(cudaMalloc((void**)&b->d_partial_count, std::max<size_t>((size_t)b->n_items * 4, 16)));
     CU(cudaMalloc((void**)&b->d_stats, 4 * sizeof(unsigned long long)));
+    for (auto& e : b->ev) CU(cudaEventCreate(&e));
     CU(cudaStreamSynchronize(ctx->stream));  // host vectors go out of scope
     *out = b.release();
     return FG_OK;
@@ -632,7 +635,9 @@ extern "C" int32_t fg_batch_execute(fg_batch* b, uint32_t flags, uint32_t k_stri
     p.match_bitmap = (uint32_t*)d_match_bitmap;
     p.bitmap_words = (ix->n_docs + 31) / 32;
     p.exact_filter = (flags & FG_EXEC_EXACT_ACCOUNTING) ? 1 : 0;
+    CU(cudaEventRecord(b->ev[0], st));
     launch_search(p, b->ks, st);
+    CU(cudaEventRecord(b->ev[1], st));
     MergeParams m{};
     m.queries = b->d_queries;
     m.n_queries = b->n_queries;
@@ -645,6 +650,7 @@ extern "C" int32_t fg_batch_execute(fg_batch* b, uint32_t flags, uint32_t k_stri
     m.out_n = (uint32_t*)d_n_hits;
     m.out_count = (uint32_t*)d_match_count;
     launch_merge(m, b->ks, st);
+    CU(cudaEventRecord(b->ev[2], st));
     b->n_launches = (b->n_items ? 1 : 0) + (b->n_queries ? 1 : 0);
     CU(cudaGetLastError());
     return FG_OK;
@@ -667,6 +673,11 @@ extern "C" int32_t fg_batch_get_stats(fg_batch* b, fg_batch_stats* out) {
     out->n_launches = b->n_launches;
     out->n_queries = b->n_queries;
     out->sum_k = b->sum_k;
+    out->search_kernel_ms = out->merge_kernel_ms = 0.f;
+    if (b->n_launches) {
+        CU(cudaEventElapsedTime(&out->search_kernel_ms, b->ev[0], b->ev[1]));
+        CU(cudaEventElapsedTime(&out->merge_kernel_ms, b->ev[1], b->ev[2]));
+    }
     return FG_OK;
 }
 

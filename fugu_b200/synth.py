@@ -248,3 +248,36 @@ def gen_queries(c: Config, n: int | None = None, vocab: int | None = None) -> li
             raise ValueError(c.cfg)
         out.append({"query": s, "filters": filters, "k": c.k})
     return out
+
+
+def lower_queries(qs: list[dict], vocab: int, n_text_fields: int = 1, facet_lookup=None):
+    """Lower synthetic fugu-syntax strings ("w3 AND w9", "w3 w9 w41") the way Dataset::search does
+    (src/db/search.rs:108-151): each word -> Should group over the default fields [text, name];
+    AND -> Must clauses, whitespace -> Should clauses; filters -> one Must clause OR-ing the facet
+    terms. term ordinal of "wN" is N-1."""
+    from . import _native as nat
+
+    out = []
+    for q in qs:
+        s = q["query"]
+        conj = " AND " in s
+        words = [w for w in s.replace(" AND ", " ").split() if w]
+        clauses = []
+        for w in words:
+            r = int(w[1:])
+            t = r - 1 if 1 <= r <= vocab else nat.FG_TERM_MISSING
+            leaves = [(f, t, 1.0) for f in range(n_text_fields)]
+            clauses.append((nat.FG_OCCUR_MUST if conj else nat.FG_OCCUR_SHOULD, leaves))
+        filters = q.get("filters") or []
+        if filters:
+            # Bool[Must(text_query), Must(facet group)]: Should words collapse into one Must clause
+            if not conj:
+                merged = [l for _, ls in clauses for l in ls]
+                clauses = [(nat.FG_OCCUR_MUST, merged)]
+            fl = []
+            for f in filters:
+                fid, t = facet_lookup(f)
+                fl.append((fid, t, 1.0))
+            clauses.append((nat.FG_OCCUR_MUST, fl))
+        out.append({"k": q["k"], "clauses": clauses})
+    return nat.HostBatch(out)

@@ -177,6 +177,8 @@ typedef struct {
     uint64_t n_launches;      /* kernels launched by the last fg_batch_execute */
     uint64_t n_queries;
     uint64_t sum_k;           /* sum of k over queries (8 B result per hit) */
+    float search_kernel_ms;   /* CUDA-event time of the search kernel of the last execute */
+    float merge_kernel_ms;    /* ... and of the per-query merge kernel */
 } fg_batch_stats;
 /* synchronises the stream and reads the device counters of the last fg_batch_execute */
 int32_t fg_batch_get_stats(fg_batch* b, fg_batch_stats* out);

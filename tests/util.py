@@ -9,35 +9,7 @@ from fugu_b200 import _native as nat
 REL_TOL = 1e-5  # BASELINE.json north_star: BM25 scores within 1e-5 relative in f32
 
 
-def plan_queries(qs: list[dict], vocab: int, n_text_fields: int = 1, facet_lookup=None) -> nat.HostBatch:
-    """Lower synthetic fugu-syntax strings ("w3 AND w9", "w3 w9 w41") the way Dataset::search does
-    (src/db/search.rs:108-151): each word -> Should group over the default fields [text, name];
-    AND -> Must clauses, whitespace -> Should clauses; filters -> one Must clause OR-ing the facet
-    terms. term ordinal of "wN" is N-1."""
-    out = []
-    for q in qs:
-        s = q["query"]
-        conj = " AND " in s
-        words = [w for w in s.replace(" AND ", " ").split() if w]
-        clauses = []
-        for w in words:
-            r = int(w[1:])
-            t = r - 1 if 1 <= r <= vocab else nat.FG_TERM_MISSING
-            leaves = [(f, t, 1.0) for f in range(n_text_fields)]
-            clauses.append((nat.FG_OCCUR_MUST if conj else nat.FG_OCCUR_SHOULD, leaves))
-        filters = q.get("filters") or []
-        if filters:
-            # Bool[Must(text_query), Must(facet group)]: Should words collapse into one Must clause
-            if not conj:
-                merged = [l for _, ls in clauses for l in ls]
-                clauses = [(nat.FG_OCCUR_MUST, merged)]
-            fl = []
-            for f in filters:
-                fid, t = facet_lookup(f)
-                fl.append((fid, t, 1.0))
-            clauses.append((nat.FG_OCCUR_MUST, fl))
-        out.append({"k": q["k"], "clauses": clauses})
-    return nat.HostBatch(out)
+from fugu_b200.synth import lower_queries as plan_queries  # noqa: E402,F401
 
 
 def close(a: float, b: float, tol: float = REL_TOL) -> bool:
