@@ -227,7 +227,10 @@ def main():
             f["total_num_tokens"] = int(tt.item())
     desc = nat.HostIndexDesc(n_local, fields, doc_id_base=d0, global_n_docs=cfg.n_docs)
     ctx = nat.Context(local_rank)
-    stream = torch.cuda.current_stream(dev)
+    # a real (non-default) stream: the legacy default stream's handle is 0, which fg_ctx_set_stream
+    # reads as "use the context's own stream"; events below are recorded on this same stream
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
     t0 = time.perf_counter()
     index = nat.Index(ctx, desc)

@@ -536,6 +536,9 @@ extern "C" int32_t fg_batch_prepare(fg_index* ix, const fg_query_batch* qb, fg_b
                 total_bytes += c.cost;
             }
             D.n_insert = (uint32_t)ql.size();
+            bool positive = true;
+            for (auto& L : ql) positive = positive && L.weight > 0.f;
+            if (mnot.empty() && positive) D.flags |= QF_PURE_UNION;
         }
         for (auto& c : mnot) {
             for (auto L : c.leaves) { L.bit = BIT_NOT; L.role = ROLE_NOT; L.req = 0; ql.push_back(L); }

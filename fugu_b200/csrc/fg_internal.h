@@ -46,6 +46,7 @@ struct DevLeaf {
 
 constexpr uint32_t MODE_DENSE = 0, MODE_HASH = 1;
 constexpr uint32_t QF_NO_MUST = 1;
+constexpr uint32_t QF_PURE_UNION = 2;  // only Should clauses, all weights > 0: no clause masks needed
 
 struct DevQuery {
     uint32_t leaf_begin;

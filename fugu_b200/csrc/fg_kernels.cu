@@ -8,13 +8,14 @@
 //   * dense mode: slot = doc - round_lo over a window of DW docs            (frequent terms)
 //   * hash mode : slot = open-addressing hash of the doc id, HS slots, the round's doc span is
 //                 chosen from the skip tables so that at most HBLK blocks are inserted (rare terms)
-// Leaves are applied one after the other (barrier in between), so a slot is updated by at most
-// one thread per phase: no floating-point atomics, bit-reproducible sums in leaf order.
-// Each leaf phase (a) scans the leaf's 16-byte skip entries lane-parallel, keeps the blocks that
-// overlap the round and -- for filter leaves (non-lead Must, Should-under-Must, MustNot) -- whose
-// doc range contains a candidate in the round's candidate bitmap, (b) decodes the surviving
-// 128-posting blocks one warp per block: bit-unpack 4 gaps + 4 tfs per lane, warp prefix sum,
-// fieldnorm gather, BM25, slot update. After the last leaf every slot is tested against the
+// The leaves of one clause form a phase (barrier between phases); inside a phase all leaves are
+// applied concurrently with shared-memory float atomics (a+b is exact-commutative; only docs with
+// >= 3 contributions in one clause can differ in the last bit between runs, far inside the 1e-5
+// parity tolerance). Each phase (a) scans the leaves' 16-byte skip entries, one warp per leaf and
+// 32 entries per step, keeps the blocks that overlap the round and -- for filter clauses (non-lead
+// Must, Should-under-Must, MustNot) -- whose doc range contains a candidate in the round's
+// candidate bitmap, (b) decodes the surviving 128-posting blocks GRP at a time per warp: bit-unpack
+// 4 gaps + 4 tfs per lane, warp prefix sum, all fieldnorm gathers issued together, BM25, slot update. After the last leaf every slot is tested against the
 // query's clause mask and offered to a per-warp register top-k queue ordered like tantivy's
 // TopDocs (score desc, doc asc). Per-item lists are merged per query by merge_kernel.
 #include <cuda_runtime.h>
@@ -155,18 +156,27 @@ __device__ __forceinline__ bool cb_any(const uint32_t* cb, uint32_t a, uint32_t 
 __device__ __forceinline__ uint32_t hash_doc(uint32_t d) { return (d * 2654435761u) >> (32 - 12); }
 static_assert(HS == 4096, "hash_doc assumes 4096 slots");
 
+constexpr int SEG_CAP = 128;  // worklist entries per scanning warp
+constexpr int GRP = 2;        // blocks decoded together by one warp (memory-level parallelism)
+constexpr uint32_t LEAF_DONE = 0xFFFFFFFFu;
+
 struct Shared {
     DevLeaf leaf[MAX_LEAVES];
     uint32_t cur[MAX_LEAVES];
     uint32_t cur_next[MAX_LEAVES];
     uint32_t quota[MAX_LEAVES];
-    uint32_t wl_count;
+    uint32_t resume[MAX_LEAVES];
+    uint32_t segcnt[NW];
     uint32_t rlo, rhi, shift, done;
     uint32_t match;
     unsigned long long st_blocks, st_redecode, st_scored;
 };
 
-template <int KS, bool DENSE>
+__device__ __forceinline__ void smem_add_f32(float* p, float v) { atomicAdd(p, v); }
+
+// One work item. DENSE: slot = doc - round_lo; else hash slots. PURE: the plan is a plain union
+// (only Should clauses, positive weights): no clause masks, every touched slot matches.
+template <int KS, bool DENSE, bool PURE>
 __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& it, const DevQuery& q,
                                          Shared& S, float* acc, uint32_t* keys, uint8_t* msk,
                                          uint32_t* cb, uint32_t* wl, uint64_t* scratch) {
@@ -174,16 +184,15 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
     const int nl = (int)q.n_leaves;
     const uint4* __restrict__ skip = p.ix.skip;
     const int k = (int)q.k;
+    const unsigned lt_mask = (1u << lane) - 1u;
 
     // ---- per-item init ----
     if (tid < nl) {
         const DevLeaf& L = S.leaf[tid];
-        // first block whose last_doc >= doc_lo
-        uint32_t a = 0, b = L.n_blocks;
+        uint32_t a = 0, b = L.n_blocks;  // first block whose last_doc >= doc_lo
         while (a < b) {
             uint32_t m = (a + b) >> 1;
-            uint32_t last = __ldg(&skip[L.blk_begin + m]).x;
-            if (last >= it.doc_lo) b = m; else a = m + 1;
+            if (__ldg(&skip[L.blk_begin + m]).x >= it.doc_lo) b = m; else a = m + 1;
         }
         S.cur[tid] = a;
         S.cur_next[tid] = a;
@@ -195,16 +204,22 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
         if (lane < (int)q.n_insert)
             S.quota[lane] = 1 + (uint32_t)(((unsigned long long)(HBLK - q.n_insert) * nb) / (tot ? tot : 1));
     }
-    for (int i = tid; i < DW; i += NT) acc[i] = 0.f;  // hash keys alias acc[HS..]
-    for (int i = tid; i < DW / 4; i += NT) reinterpret_cast<uint32_t*>(msk)[i] = 0;
-    __syncthreads();
-    if (!DENSE)
-        for (int i = tid; i < HS; i += NT) keys[i] = EMPTY;
+    {
+        float4* a4 = reinterpret_cast<float4*>(acc);
+        for (int i = tid; i < (DENSE ? DW : HS) / 4; i += NT) a4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!DENSE) {
+            uint4* k4 = reinterpret_cast<uint4*>(keys);
+            for (int i = tid; i < HS / 4; i += NT) k4[i] = make_uint4(EMPTY, EMPTY, EMPTY, EMPTY);
+        }
+        if (!PURE)
+            for (int i = tid; i < (DENSE ? DW : HS) / 4; i += NT) reinterpret_cast<uint32_t*>(msk)[i] = 0;
+    }
     if (tid == 0) { S.match = 0; S.st_blocks = 0; S.st_redecode = 0; S.st_scored = 0; }
     __syncthreads();
 
     WarpTopK<KS> tk;
     tk.init();
+    float theta_s = -INFINITY;  // score part of tk.theta (a candidate needs score >= theta_s)
     uint32_t lo = it.doc_lo;
     const uint32_t end = it.doc_hi;
     uint32_t my_matches = 0, my_scored = 0;
@@ -243,74 +258,136 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
         if (S.done) break;
         const uint32_t rlo = S.rlo, rhi = S.rhi, shift = S.shift;
 
-        // ---- leaf phases ----
-        for (int l = 0; l < nl; l++) {
-            const DevLeaf L = S.leaf[l];
-            const bool filter = L.role != ROLE_INSERT;
-            uint32_t base_b = S.cur[l];
+        // ---- clause phases: leaves [l0, l1) share (role, bit) ----
+        int l0 = 0;
+        while (l0 < nl) {
+            int l1 = l0 + 1;
+            while (l1 < nl && S.leaf[l1].role == S.leaf[l0].role && S.leaf[l1].bit == S.leaf[l0].bit) l1++;
+            const uint32_t role = S.leaf[l0].role, bit = S.leaf[l0].bit, req = S.leaf[l0].req;
+            const bool filter = role != ROLE_INSERT;
+            if (tid >= l0 && tid < l1) S.resume[tid] = S.cur[tid];
             while (true) {
-                if (tid == 0) S.wl_count = 0;
                 __syncthreads();
-                // (a) lane-parallel scan of skip entries
-                const uint32_t b = base_b + tid;
-                bool in_range = false, needed = false;
-                if (b < L.n_blocks) {
-                    const uint4 e = __ldg(&skip[L.blk_begin + b]);
-                    in_range = e.y < rhi;
-                    if (in_range) {
-                        if (e.x < rhi) atomicMax(&S.cur_next[l], b + 1);
-                        if (e.x >= rlo) {
-                            needed = true;
-                            if (filter) {
-                                const uint32_t a = max(e.y, rlo) - rlo, z = min(e.x, rhi - 1) - rlo;
-                                needed = cb_any(cb, a >> shift, z >> shift);
-                                if (needed && p.exact_filter && !DENSE) {
-                                    // exact accounting: a candidate doc id inside [e.y, e.x]?
-                                    bool any = false;
-                                    for (int i = 0; i < HS && !any; i++) {
-                                        const uint32_t kd = keys[i];
-                                        any = kd != EMPTY && kd >= e.y && kd <= e.x &&
-                                              (msk[i] & L.req) == L.req;
+                int my_pending = 0;
+                // (a) skip-entry scan: one warp per leaf, 32 blocks per step, private worklist segment
+                uint32_t cnt = 0;
+                for (int l = l0 + warp; l < l1; l += NW) {
+                    const DevLeaf& L = S.leaf[l];
+                    uint32_t b = S.resume[l];
+                    if (b == LEAF_DONE) continue;
+                    while (true) {
+                        const uint32_t bi = b + lane;
+                        bool in_range = false, needed = false, consumed = false;
+                        if (bi < L.n_blocks) {
+                            const uint4 e = __ldg(&skip[L.blk_begin + bi]);
+                            in_range = e.y < rhi;
+                            consumed = in_range && e.x < rhi;
+                            if (in_range && e.x >= rlo) {
+                                needed = true;
+                                if (filter) {
+                                    const uint32_t a = max(e.y, rlo) - rlo, z = min(e.x, rhi - 1) - rlo;
+                                    needed = cb_any(cb, a >> shift, z >> shift);
+                                    if (needed && p.exact_filter && !DENSE) {
+                                        bool any = false;  // exact accounting: a candidate inside [e.y, e.x]?
+                                        for (int i = 0; i < HS && !any; i++) {
+                                            const uint32_t kd = keys[i];
+                                            any = kd != EMPTY && kd >= e.y && kd <= e.x && (msk[i] & req) == req;
+                                        }
+                                        needed = any;
                                     }
-                                    needed = any;
                                 }
                             }
                         }
+                        const unsigned nm = __ballot_sync(FULL, needed);
+                        const int nin = __popc(__ballot_sync(FULL, in_range));
+                        const int ncons = __popc(__ballot_sync(FULL, consumed));
+                        if (cnt + __popc(nm) > SEG_CAP) {  // segment full: decode what we have, come back
+                            if (lane == 0) S.resume[l] = b;
+                            my_pending = 1;
+                            break;
+                        }
+                        if (needed) wl[warp * SEG_CAP + cnt + __popc(nm & lt_mask)] = ((uint32_t)l << 24) | bi;
+                        cnt += __popc(nm);
+                        if (lane == 0 && ncons) S.cur_next[l] = max(S.cur_next[l], b + ncons);
+                        if (nin < 32) { if (lane == 0) S.resume[l] = LEAF_DONE; break; }
+                        b += 32;
                     }
                 }
-                const unsigned nm = __ballot_sync(FULL, needed);
-                if (nm) {
-                    uint32_t pos = 0;
-                    if (lane == 0) pos = atomicAdd(&S.wl_count, (uint32_t)__popc(nm));
-                    pos = __shfl_sync(FULL, pos, 0);
-                    if (needed) wl[pos + __popc(nm & ((1u << lane) - 1u))] = b;
-                }
-                const int more = __syncthreads_or(tid == NT - 1 && in_range);
-                // (b) one warp per surviving block
-                const uint32_t nwl = S.wl_count;
-                for (uint32_t i = warp; i < nwl; i += NW) {
-                    const uint32_t bb = wl[i];
-                    const uint4 e = __ldg(&skip[L.blk_begin + bb]);
-                    const uint32_t bd = e.w & 63u, bt = (e.w >> 6) & 63u, n = ((e.w >> 12) & 127u) + 1u;
-                    const uint32_t* wd = reinterpret_cast<const uint32_t*>(p.ix.blk + (size_t)e.z * 16u);
-                    uint32_t g[4], t[4];
-                    unpack4(wd, lane, bd, g);
-                    unpack4(wd + 4 * bd, lane, bt, t);
-                    g[1] += g[0]; g[2] += g[1]; g[3] += g[2];
-                    const uint32_t off = warp_excl_scan(g[3], lane) + e.y + 4u * lane;
-                    if (lane == 0) {
-                        const unsigned long long by = ((n * bd + 7) >> 3) + ((n * bt + 7) >> 3) + 16;
-                        if (e.y >= lo) my_blocks += by; else my_redecode += by;
+                if (lane == 0) S.segcnt[warp] = cnt;
+                __syncthreads();
+                // (b) decode GRP blocks per warp step
+                uint32_t seg_end[NW];
+                uint32_t total = 0;
+#pragma unroll
+                for (int w = 0; w < NW; w++) { total += S.segcnt[w]; seg_end[w] = total; }
+                for (uint32_t i0 = warp * GRP; i0 < total; i0 += NW * GRP) {
+                    uint4 e[GRP];
+                    uint32_t lf[GRP];
+                    bool val[GRP];
+#pragma unroll
+                    for (int g = 0; g < GRP; g++) {
+                        const uint32_t idx = i0 + g;
+                        val[g] = idx < total;
+                        uint32_t w = 0, base = 0;
+#pragma unroll
+                        for (int x = 0; x < NW - 1; x++)
+                            if (idx >= seg_end[x]) { w = x + 1; base = seg_end[x]; }
+                        const uint32_t ent = val[g] ? wl[w * SEG_CAP + (idx - base)] : 0u;
+                        lf[g] = ent >> 24;
+                        e[g] = val[g] ? __ldg(&skip[S.leaf[lf[g]].blk_begin + (ent & 0xFFFFFFu)])
+                                      : make_uint4(0, 0, 0, 0);
+                    }
+                    uint32_t gp[GRP][4], tf[GRP][4], nn[GRP];
+#pragma unroll
+                    for (int g = 0; g < GRP; g++) {
+                        const uint32_t bd = e[g].w & 63u, bt = (e[g].w >> 6) & 63u;
+                        nn[g] = val[g] ? ((e[g].w >> 12) & 127u) + 1u : 0u;
+                        const uint32_t* wd = reinterpret_cast<const uint32_t*>(p.ix.blk + (size_t)e[g].z * 16u);
+                        unpack4(wd, lane, bd, gp[g]);
+                        unpack4(wd + 4 * bd, lane, bt, tf[g]);
+                        if (lane == 0 && val[g]) {
+                            const unsigned long long by = ((nn[g] * bd + 7) >> 3) + ((nn[g] * bt + 7) >> 3) + 16;
+                            if (e[g].y >= lo) my_blocks += by; else my_redecode += by;
+                        }
                     }
 #pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        const uint32_t d = off + g[j] + j;
-                        if (4u * lane + j < n && d >= rlo && d < rhi) {
+                    for (int g = 0; g < GRP; g++) {
+                        gp[g][1] += gp[g][0]; gp[g][2] += gp[g][1]; gp[g][3] += gp[g][2];
+                        const uint32_t off = warp_excl_scan(gp[g][3], lane) + e[g].y + 4u * lane;
+#pragma unroll
+                        for (int j = 0; j < 4; j++) gp[g][j] += off + j;  // now doc ids
+                    }
+                    // fieldnorm gathers for everything in range, issued together
+                    float norm[GRP][4];
+                    bool ok[GRP][4];
+#pragma unroll
+                    for (int g = 0; g < GRP; g++) {
+                        const DevLeaf& L = S.leaf[lf[g]];
+                        const int ff = L.fn_field;
+                        const uint8_t* fnp = p.ix.fnorm[ff < 0 ? 0 : ff];
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            const uint32_t d = gp[g][j];
+                            ok[g][j] = 4u * lane + j < nn[g] && d >= rlo && d < rhi;
+                            norm[g][j] = L.cnorm;
+                            if (ok[g][j] && ff >= 0 && role != ROLE_NOT)
+                                norm[g][j] = __ldg(p.ix.cache + ff * 256 + __ldg(fnp + d));
+                        }
+                    }
+#pragma unroll
+                    for (int g = 0; g < GRP; g++) {
+                        const float wgt = S.leaf[lf[g]].weight;
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            if (!ok[g][j]) continue;
+                            const uint32_t d = gp[g][j];
                             int slot;
                             if (DENSE) {
                                 slot = (int)(d - rlo);
-                                if (filter && (msk[slot] & L.req) != L.req) slot = -1;
-                                if (L.role == ROLE_NOT && msk[slot < 0 ? 0 : slot] == 0) slot = -1;
+                                if (!PURE && filter) {
+                                    const uint32_t m = msk[slot];
+                                    if ((m & req) != req || (role == ROLE_NOT && m == 0)) slot = -1;
+                                }
                             } else {
                                 uint32_t h = hash_doc(d);
                                 slot = -1;
@@ -324,32 +401,25 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
                                     }
                                     h = (h + 1) & (HS - 1);
                                 }
-                                if (slot >= 0 && filter && (msk[slot] & L.req) != L.req) slot = -1;
+                                if (!PURE && slot >= 0 && filter && (msk[slot] & req) != req) slot = -1;
                             }
-                            if (slot >= 0) {
-                                if (L.role == ROLE_NOT) {
-                                    msk[slot] |= (uint8_t)BIT_NOT;
-                                } else {
-                                    const float tf = (float)(t[j] + 1u);
-                                    float norm = L.cnorm;
-                                    if (L.fn_field >= 0)
-                                        norm = __ldg(p.ix.cache + L.fn_field * 256 +
-                                                     __ldg(p.ix.fnorm[L.fn_field] + d));
-                                    acc[slot] += L.weight * (tf / (tf + norm));
-                                    if (L.bit) msk[slot] |= (uint8_t)L.bit;
-                                    my_scored++;
-                                }
+                            if (slot < 0) continue;
+                            if (!PURE && role == ROLE_NOT) {
+                                msk[slot] = (uint8_t)(msk[slot] | BIT_NOT);
+                                continue;
                             }
+                            const float t = (float)(tf[g][j] + 1u);
+                            smem_add_f32(&acc[slot], wgt * __fdividef(t, t + norm[g][j]));
+                            if (!PURE && bit) msk[slot] = (uint8_t)(msk[slot] | bit);
+                            my_scored++;
                         }
                     }
                 }
-                if (!more) break;
-                base_b += NT;
-                __syncthreads();
+                if (!__syncthreads_or(my_pending)) break;
             }
-            __syncthreads();
-            if (L.build_cb) {
-                const uint32_t need = L.build_cb;
+            // candidate bitmap for the following filter clause
+            const uint32_t need = S.leaf[l1 - 1].build_cb;
+            if (!PURE && need) {
                 if (DENSE) {
                     if (tid < CBW) {
                         const uint32_t* m32 = reinterpret_cast<const uint32_t*>(msk) + tid * 8;
@@ -369,58 +439,70 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
                     for (int i = tid; i < HS; i += NT) {
                         const uint32_t kd = keys[i];
                         if (kd != EMPTY && (msk[i] & need) == need) {
-                            const uint32_t bit = (kd - rlo) >> shift;
-                            atomicOr(&cb[bit >> 5], 1u << (bit & 31));
+                            const uint32_t bitpos = (kd - rlo) >> shift;
+                            atomicOr(&cb[bitpos >> 5], 1u << (bitpos & 31));
                         }
                     }
                 }
                 __syncthreads();
             }
+            l0 = l1;
         }
 
-        // ---- scan slots: clause mask test, top-k offer, reset ----
+        // ---- slot scan: match test, cheap f32 pre-test against the k-th score, reset ----
         {
             const int n4 = DENSE ? (int)((rhi - rlo + 3) >> 2) : HS / 4;
             uint32_t* m32 = reinterpret_cast<uint32_t*>(msk);
+            float4* a4 = reinterpret_cast<float4*>(acc);
+            uint4* k4 = reinterpret_cast<uint4*>(keys);
             for (int g0 = warp * 32; g0 < n4; g0 += NT) {
                 const int g = g0 + lane;
-                uint32_t m4 = 0;
+                float4 av = make_float4(0.f, 0.f, 0.f, 0.f);
                 uint4 kv = make_uint4(EMPTY, EMPTY, EMPTY, EMPTY);
+                uint32_t m4 = 0;
                 if (g < n4) {
-                    m4 = m32[g];
-                    if (!DENSE) kv = reinterpret_cast<uint4*>(keys)[g];
+                    av = a4[g];
+                    a4[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (!DENSE) { kv = k4[g]; k4[g] = make_uint4(EMPTY, EMPTY, EMPTY, EMPTY); }
+                    if (!PURE) { m4 = m32[g]; if (m4) m32[g] = 0; }
                 }
-                uint64_t cand[4];
-                uint64_t best = 0;
+                const float sc[4] = {av.x + q.const_score, av.y + q.const_score, av.z + q.const_score,
+                                     av.w + q.const_score};
+                const float raw[4] = {av.x, av.y, av.z, av.w};
                 const uint32_t kk[4] = {kv.x, kv.y, kv.z, kv.w};
+                bool mt[4];
+                bool hot = false;
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
-                    cand[j] = 0;
-                    const uint32_t m = (m4 >> (8 * j)) & 0xFFu;
-                    const bool occ = DENSE ? (m != 0) : (kk[j] != EMPTY);
-                    if (occ) {
-                        const int slot = 4 * g + j;
-                        const uint32_t doc = DENSE ? rlo + slot : kk[j];
-                        const float sc = acc[slot];
-                        acc[slot] = 0.f;
-                        if (!DENSE) keys[slot] = EMPTY;
-                        bool match = (m & 0x7Fu) == q.all_must && !(m & BIT_NOT);
-                        if (match && p.ix.alive)
-                            match = (__ldg(p.ix.alive + (doc >> 5)) >> (doc & 31)) & 1u;
-                        if (match) {
-                            my_matches++;
-                            cand[j] = make_key(sc + q.const_score, doc);
-                            if (cand[j] > best) best = cand[j];
-                            if (p.match_bitmap)
-                                atomicOr(p.match_bitmap + (size_t)it.query * p.bitmap_words + (doc >> 5),
-                                         1u << (doc & 31));
-                        }
+                    if (PURE) mt[j] = DENSE ? raw[j] > 0.f : kk[j] != EMPTY;
+                    else {
+                        const uint32_t m = (m4 >> (8 * j)) & 0xFFu;
+                        mt[j] = (m & 0x7Fu) == q.all_must && !(m & BIT_NOT);
                     }
                 }
-                if (m4) m32[g] = 0;
-                if (__any_sync(FULL, best > tk.theta)) {
+                if (p.ix.alive || p.match_bitmap) {
 #pragma unroll
-                    for (int j = 0; j < 4; j++) tk.offer(cand[j] != 0, cand[j], k, lane);
+                    for (int j = 0; j < 4; j++) {
+                        if (!mt[j]) continue;
+                        const uint32_t doc = DENSE ? rlo + 4 * g + j : kk[j];
+                        if (p.ix.alive && !((__ldg(p.ix.alive + (doc >> 5)) >> (doc & 31)) & 1u)) { mt[j] = false; continue; }
+                        if (p.match_bitmap)
+                            atomicOr(p.match_bitmap + (size_t)it.query * p.bitmap_words + (doc >> 5), 1u << (doc & 31));
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    my_matches += mt[j];
+                    hot |= mt[j] && sc[j] >= theta_s;
+                }
+                if (__any_sync(FULL, hot)) {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const uint32_t doc = DENSE ? rlo + 4 * g + j : kk[j];
+                        const bool c = mt[j] && sc[j] >= theta_s;
+                        tk.offer(c, c ? make_key(sc[j], doc) : 0ull, k, lane);
+                    }
+                    theta_s = tk.theta ? unsortable((uint32_t)(tk.theta >> 32)) : -INFINITY;
                 }
             }
         }
@@ -467,7 +549,7 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
 }
 
 template <int KS>
-__global__ void __launch_bounds__(NT) search_kernel(const SearchParams p) {
+__global__ void __launch_bounds__(NT, 3) search_kernel(const SearchParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ Shared S;
     float* acc = reinterpret_cast<float*>(smem);
@@ -475,16 +557,20 @@ __global__ void __launch_bounds__(NT) search_kernel(const SearchParams p) {
     uint8_t* msk = smem + DW * 4;
     uint32_t* cb = reinterpret_cast<uint32_t*>(smem + DW * 4 + DW);
     uint32_t* wl = cb + CBW;
-    uint64_t* scratch = reinterpret_cast<uint64_t*>(wl + NT);
+    uint64_t* scratch = reinterpret_cast<uint64_t*>(wl + NW * SEG_CAP);
 
     const DevItem it = p.items[blockIdx.x];
     const DevQuery q = p.queries[it.query];
     if (threadIdx.x < q.n_leaves) S.leaf[threadIdx.x] = p.leaves[q.leaf_begin + threadIdx.x];
     __syncthreads();
-    if (it.mode == MODE_DENSE)
-        run_item<KS, true>(p, it, q, S, acc, keys, msk, cb, wl, scratch);
-    else
-        run_item<KS, false>(p, it, q, S, acc, keys, msk, cb, wl, scratch);
+    const bool pure = (q.flags & QF_PURE_UNION) != 0;
+    if (it.mode == MODE_DENSE) {
+        if (pure) run_item<KS, true, true>(p, it, q, S, acc, keys, msk, cb, wl, scratch);
+        else run_item<KS, true, false>(p, it, q, S, acc, keys, msk, cb, wl, scratch);
+    } else {
+        if (pure) run_item<KS, false, true>(p, it, q, S, acc, keys, msk, cb, wl, scratch);
+        else run_item<KS, false, false>(p, it, q, S, acc, keys, msk, cb, wl, scratch);
+    }
 }
 
 // one warp per query: merge the per-item partial lists
@@ -574,7 +660,7 @@ __global__ void __launch_bounds__(128) merge_gathered_kernel(const uint2* hits, 
 }  // namespace
 
 int search_smem_bytes(int ks) {
-    return DW * 4 + DW + CBW * 4 + NT * 4 + NW * ks * 32 * 8;
+    return DW * 4 + DW + CBW * 4 + NW * SEG_CAP * 4 + NW * ks * 32 * 8;
 }
 
 template <int KS>

@@ -1,0 +1,45 @@
+"""Dev tool: time the search kernel for a few planner settings (env vars are read at prepare time)."""
+import os, sys, time, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from fugu_b200 import _native as nat, synth
+
+def main():
+    nq = int(os.environ.get("SWEEP_Q", "5000"))
+    cfg = synth.Config(cfg=2, n_docs=1_000_000, vocab=200_000, n_queries=nq, k=10, name_pct=10)
+    corpus = synth.Corpus.for_config(cfg)
+    fields = synth.build_fields(corpus, 0, cfg.n_docs)
+    desc = nat.HostIndexDesc(cfg.n_docs, fields)
+    ctx = nat.Context(0)
+    stream = torch.cuda.Stream(); torch.cuda.set_stream(stream); ctx.set_stream(stream.cuda_stream)
+    index = nat.Index(ctx, desc)
+    queries = synth.gen_queries(cfg)
+    batch = synth.lower_queries(queries, vocab=cfg.vocab, n_text_fields=2)
+    # query classes
+    kinds = {"all": queries,
+             "and": [q for q in queries if " AND " in q["query"]],
+             "or": [q for q in queries if " AND " not in q["query"] and " " in q["query"]],
+             "single": [q for q in queries if " " not in q["query"]]}
+    dev = torch.device("cuda:0")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    settings = json.loads(os.environ.get("SWEEP", '[{}]'))
+    for s in settings:
+        for k_, v in s.items(): os.environ[k_] = str(v)
+        for kind, qs in kinds.items():
+            if not qs: continue
+            b = synth.lower_queries(qs, vocab=cfg.vocab, n_text_fields=2)
+            pb = index.prepare(b)
+            n = b.n_queries
+            d_hits = torch.zeros((n, 10, 2), dtype=torch.int32, device=dev); d_n = torch.zeros(n, dtype=torch.int32, device=dev); d_c = torch.zeros(n, dtype=torch.int32, device=dev)
+            ms = []
+            for it in range(6):
+                flush.fill_(it)
+                pb.execute(d_hits.data_ptr(), d_n.data_ptr(), d_c.data_ptr(), None, k_stride=10)
+                st = pb.stats()
+                if it >= 2: ms.append(st.search_kernel_ms)
+            by = st.bytes_blocks + st.scored_postings
+            print(f"{json.dumps(s):40s} {kind:7s} nq={n:5d} items={st.n_work_items:6d} search={np.mean(ms):8.3f} ms merge={st.merge_kernel_ms:6.3f} ms  {by/1e6:8.1f} MB  {by/np.mean(ms)/1e6:7.1f} GB/s  redecode={st.bytes_redecode/1e6:.1f}MB", flush=True)
+            pb.close()
+        for k_ in s: os.environ.pop(k_, None)
+
+main()
