@@ -28,6 +28,7 @@ FG_OCCUR_SHOULD, FG_OCCUR_MUST, FG_OCCUR_MUST_NOT = 0, 1, 2
 FG_TERM_MISSING = 0xFFFFFFFF
 FG_TERM_ALL = 0xFFFFFFFE
 FG_EXEC_EXACT_ACCOUNTING = 1
+FG_EXEC_DETERMINISTIC = 2
 
 
 class FgError(RuntimeError):

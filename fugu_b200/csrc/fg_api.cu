@@ -431,6 +431,7 @@ extern "C" int32_t fg_batch_prepare(fg_index* ix, const fg_query_batch* qb, fg_b
         return fail(FG_ERR_INVALID, "fg_batch_prepare: NULL arrays");
     const uint64_t ITEM_BYTES = env_u64("FG_ITEM_BYTES", 65536);
     const uint64_t DENSE_MIN = env_u64("FG_DENSE_MIN", 1536);  // insert postings per dense window
+    const uint64_t DENSE_MIN_MUST = env_u64("FG_DENSE_MIN_MUST", 256);  // same, plans with Must clauses
     const uint32_t HASH_MIN_SPAN = 4096;
 
     std::vector<DevQuery> dq(qb->n_queries);
@@ -561,7 +562,8 @@ extern "C" int32_t fg_batch_prepare(fg_index* ix, const fg_query_batch* qb, fg_b
 
         // ---- mode + work items ----
         const uint32_t nd = ix->n_docs;
-        const uint32_t mode = (insert_postings * (uint64_t)DW >= DENSE_MIN * (uint64_t)std::max<uint32_t>(nd, 1)) ? MODE_DENSE : MODE_HASH;
+        const uint64_t dmin = must.empty() ? DENSE_MIN : DENSE_MIN_MUST;
+        const uint32_t mode = (insert_postings * (uint64_t)DW >= dmin * (uint64_t)std::max<uint32_t>(nd, 1)) ? MODE_DENSE : MODE_HASH;
         uint64_t want = std::max<uint64_t>(1, (total_bytes + ITEM_BYTES / 2) / ITEM_BYTES);
         const uint32_t min_span = mode == MODE_DENSE ? (uint32_t)DW : HASH_MIN_SPAN;
         const uint64_t max_items = std::max<uint64_t>(1, nd / min_span);
@@ -638,6 +640,7 @@ extern "C" int32_t fg_batch_execute(fg_batch* b, uint32_t flags, uint32_t k_stri
     p.match_bitmap = (uint32_t*)d_match_bitmap;
     p.bitmap_words = (ix->n_docs + 31) / 32;
     p.exact_filter = (flags & FG_EXEC_EXACT_ACCOUNTING) ? 1 : 0;
+    p.deterministic = (flags & FG_EXEC_DETERMINISTIC) ? 1 : 0;
     CU(cudaEventRecord(b->ev[0], st));
     launch_search(p, b->ks, st);
     CU(cudaEventRecord(b->ev[1], st));

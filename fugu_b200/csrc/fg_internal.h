@@ -92,6 +92,7 @@ struct SearchParams {
     uint32_t* match_bitmap;      // optional
     uint32_t bitmap_words;
     uint32_t exact_filter;
+    uint32_t deterministic;     // one phase per leaf: bit-reproducible sums in leaf order
 };
 
 struct MergeParams {
@@ -111,9 +112,12 @@ struct MergeParams {
 constexpr int NT = 256;          // threads per CTA
 constexpr int NW = NT / 32;      // warps per CTA
 constexpr int DW = 8192;         // dense window: docs per round
-constexpr int HS = 4096;         // hash slots per round
+constexpr int HS_LOG2 = 12;
+constexpr int HS = 1 << HS_LOG2; // hash slots per round
 constexpr int HBLK = 16;         // insert-leaf blocks per hash round (<= HS/2/128)
-constexpr int CBW = 256;         // candidate bitmap words (8192 bits)
+constexpr int SLOTS = DW > HS ? DW : HS;
+constexpr int CBW = 1024;        // candidate bitmap words (32768 bits; dense mode uses the first DW bits)
+constexpr int CB_LOG2 = 15;
 
 void launch_search(const SearchParams& p, int ks, void* stream);
 void launch_merge(const MergeParams& p, int ks, void* stream);

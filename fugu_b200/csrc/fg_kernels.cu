@@ -153,8 +153,7 @@ __device__ __forceinline__ bool cb_any(const uint32_t* cb, uint32_t a, uint32_t 
     return (cb[wz] & mz) != 0;
 }
 
-__device__ __forceinline__ uint32_t hash_doc(uint32_t d) { return (d * 2654435761u) >> (32 - 12); }
-static_assert(HS == 4096, "hash_doc assumes 4096 slots");
+__device__ __forceinline__ uint32_t hash_doc(uint32_t d) { return (d * 2654435761u) >> (32 - HS_LOG2); }
 
 constexpr int SEG_CAP = 128;  // worklist entries per scanning warp
 constexpr int GRP = 2;        // blocks decoded together by one warp (memory-level parallelism)
@@ -165,7 +164,8 @@ struct Shared {
     uint32_t cur[MAX_LEAVES];
     uint32_t cur_next[MAX_LEAVES];
     uint32_t quota[MAX_LEAVES];
-    uint32_t resume[MAX_LEAVES];
+    uint32_t resume[MAX_LEAVES * NW];
+    uint32_t phase_end[MAX_LEAVES];
     uint32_t segcnt[NW];
     uint32_t rlo, rhi, shift, done;
     uint32_t match;
@@ -196,6 +196,9 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
         }
         S.cur[tid] = a;
         S.cur_next[tid] = a;
+        int l1 = tid + 1;  // leaves [tid, phase_end) share (role, bit) = one clause phase
+        while (!p.deterministic && l1 < nl && S.leaf[l1].role == L.role && S.leaf[l1].bit == L.bit) l1++;
+        S.phase_end[tid] = (uint32_t)l1;
     }
     if (!DENSE && warp == 0) {
         // share HBLK insert blocks per round among the insert leaves, proportional to list length
@@ -206,13 +209,13 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
     }
     {
         float4* a4 = reinterpret_cast<float4*>(acc);
-        for (int i = tid; i < (DENSE ? DW : HS) / 4; i += NT) a4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = tid; i < SLOTS / 4; i += NT) a4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (!DENSE) {
             uint4* k4 = reinterpret_cast<uint4*>(keys);
             for (int i = tid; i < HS / 4; i += NT) k4[i] = make_uint4(EMPTY, EMPTY, EMPTY, EMPTY);
         }
         if (!PURE)
-            for (int i = tid; i < (DENSE ? DW : HS) / 4; i += NT) reinterpret_cast<uint32_t*>(msk)[i] = 0;
+            for (int i = tid; i < SLOTS / 4; i += NT) reinterpret_cast<uint32_t*>(msk)[i] = 0;
     }
     if (tid == 0) { S.match = 0; S.st_blocks = 0; S.st_redecode = 0; S.st_scored = 0; }
     __syncthreads();
@@ -250,7 +253,7 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
                 S.rlo = rlo;
                 S.rhi = rhi;
                 const uint32_t span = rhi - rlo;
-                int sh = span > 1 ? (32 - __clz(span - 1)) - 13 : 0;
+                int sh = span > 1 ? (32 - __clz(span - 1)) - CB_LOG2 : 0;
                 S.shift = sh > 0 ? sh : 0;
             }
         }
@@ -261,19 +264,26 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
         // ---- clause phases: leaves [l0, l1) share (role, bit) ----
         int l0 = 0;
         while (l0 < nl) {
-            int l1 = l0 + 1;
-            while (l1 < nl && S.leaf[l1].role == S.leaf[l0].role && S.leaf[l1].bit == S.leaf[l0].bit) l1++;
+            const int l1 = (int)S.phase_end[l0];
             const uint32_t role = S.leaf[l0].role, bit = S.leaf[l0].bit, req = S.leaf[l0].req;
             const bool filter = role != ROLE_INSERT;
-            if (tid >= l0 && tid < l1) S.resume[tid] = S.cur[tid];
+            for (int i = tid; i < (l1 - l0) * NW; i += NT) {
+                const int l = l0 + i / NW, w = i % NW;
+                const uint32_t c0 = (uint32_t)((w - l) & (NW - 1));  // this warp's first chunk of leaf l
+                // insert leaves touch a bounded number of blocks per round: warps beyond it sit out
+                const uint32_t maxb = filter ? 0xFFFFFFFFu : (DENSE ? (uint32_t)(DW / BLOCK + 2) : S.quota[l]);
+                S.resume[l * NW + w] = (c0 * 32u < maxb && S.cur[l] + c0 * 32u < S.leaf[l].n_blocks)
+                                           ? S.cur[l] + c0 * 32u : LEAF_DONE;
+            }
             while (true) {
                 __syncthreads();
                 int my_pending = 0;
-                // (a) skip-entry scan: one warp per leaf, 32 blocks per step, private worklist segment
+                // (a) skip-entry scan: every warp takes 32-entry chunks warp, warp+NW, ... of each leaf
+                //     and appends the needed blocks to its private worklist segment
                 uint32_t cnt = 0;
-                for (int l = l0 + warp; l < l1; l += NW) {
+                for (int l = l0; l < l1; l++) {
                     const DevLeaf& L = S.leaf[l];
-                    uint32_t b = S.resume[l];
+                    uint32_t b = S.resume[l * NW + warp];
                     if (b == LEAF_DONE) continue;
                     while (true) {
                         const uint32_t bi = b + lane;
@@ -302,25 +312,24 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
                         const int nin = __popc(__ballot_sync(FULL, in_range));
                         const int ncons = __popc(__ballot_sync(FULL, consumed));
                         if (cnt + __popc(nm) > SEG_CAP) {  // segment full: decode what we have, come back
-                            if (lane == 0) S.resume[l] = b;
+                            if (lane == 0) S.resume[l * NW + warp] = b;
                             my_pending = 1;
                             break;
                         }
                         if (needed) wl[warp * SEG_CAP + cnt + __popc(nm & lt_mask)] = ((uint32_t)l << 24) | bi;
                         cnt += __popc(nm);
-                        if (lane == 0 && ncons) S.cur_next[l] = max(S.cur_next[l], b + ncons);
-                        if (nin < 32) { if (lane == 0) S.resume[l] = LEAF_DONE; break; }
-                        b += 32;
+                        if (lane == 0 && ncons) atomicMax(&S.cur_next[l], b + ncons);
+                        if (nin < 32) { if (lane == 0) S.resume[l * NW + warp] = LEAF_DONE; break; }
+                        b += 32 * NW;
                     }
                 }
                 if (lane == 0) S.segcnt[warp] = cnt;
                 __syncthreads();
                 // (b) decode GRP blocks per warp step
-                uint32_t seg_end[NW];
-                uint32_t total = 0;
-#pragma unroll
-                for (int w = 0; w < NW; w++) { total += S.segcnt[w]; seg_end[w] = total; }
-                for (uint32_t i0 = warp * GRP; i0 < total; i0 += NW * GRP) {
+                for (int sg = 0; sg < NW; sg++) {
+                const uint32_t total = S.segcnt[sg];
+                const uint32_t* seg = wl + sg * SEG_CAP;
+                for (uint32_t i0 = (uint32_t)((warp - sg) & (NW - 1)) * GRP; i0 < total; i0 += NW * GRP) {
                     uint4 e[GRP];
                     uint32_t lf[GRP];
                     bool val[GRP];
@@ -328,11 +337,7 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
                     for (int g = 0; g < GRP; g++) {
                         const uint32_t idx = i0 + g;
                         val[g] = idx < total;
-                        uint32_t w = 0, base = 0;
-#pragma unroll
-                        for (int x = 0; x < NW - 1; x++)
-                            if (idx >= seg_end[x]) { w = x + 1; base = seg_end[x]; }
-                        const uint32_t ent = val[g] ? wl[w * SEG_CAP + (idx - base)] : 0u;
+                        const uint32_t ent = val[g] ? seg[idx] : 0u;
                         lf[g] = ent >> 24;
                         e[g] = val[g] ? __ldg(&skip[S.leaf[lf[g]].blk_begin + (ent & 0xFFFFFFu)])
                                       : make_uint4(0, 0, 0, 0);
@@ -357,9 +362,49 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
 #pragma unroll
                         for (int j = 0; j < 4; j++) gp[g][j] += off + j;  // now doc ids
                     }
-                    // fieldnorm gathers for everything in range, issued together
+                    // slot lookup / insertion first (filter clauses touch only existing candidates) ...
+                    int slot[GRP][4];
+#pragma unroll
+                    for (int g = 0; g < GRP; g++) {
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            const uint32_t d = gp[g][j];
+                            int sl = -1;
+                            if (4u * lane + j < nn[g] && d >= rlo && d < rhi) {
+                                if (DENSE) {
+                                    sl = (int)(d - rlo);
+                                    if (!PURE && filter) {
+                                        const uint32_t m = msk[sl];
+                                        if ((m & req) != req || (role == ROLE_NOT && m == 0)) sl = -1;
+                                    }
+                                } else if (!filter || ((cb[((d - rlo) >> shift) >> 5] >> (((d - rlo) >> shift) & 31)) & 1u)) {
+                                    uint32_t h = hash_doc(d);
+                                    while (true) {
+                                        uint32_t kd = keys[h];
+                                        if (kd == d) { sl = (int)h; break; }
+                                        if (kd == EMPTY) {
+                                            if (filter) break;
+                                            kd = atomicCAS(&keys[h], EMPTY, d);
+                                            if (kd == EMPTY || kd == d) { sl = (int)h; break; }
+                                        }
+                                        h = (h + 1) & (HS - 1);
+                                    }
+                                    if (!PURE && sl >= 0 && filter && (msk[sl] & req) != req) sl = -1;
+                                }
+                            }
+                            slot[g][j] = sl;
+                        }
+                    }
+                    if (!PURE && role == ROLE_NOT) {
+#pragma unroll
+                        for (int g = 0; g < GRP; g++)
+#pragma unroll
+                            for (int j = 0; j < 4; j++)
+                                if (slot[g][j] >= 0) msk[slot[g][j]] = (uint8_t)(msk[slot[g][j]] | BIT_NOT);
+                        continue;
+                    }
+                    // ... then the fieldnorm gathers of the surviving postings, issued together ...
                     float norm[GRP][4];
-                    bool ok[GRP][4];
 #pragma unroll
                     for (int g = 0; g < GRP; g++) {
                         const DevLeaf& L = S.leaf[lf[g]];
@@ -367,53 +412,26 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
                         const uint8_t* fnp = p.ix.fnorm[ff < 0 ? 0 : ff];
 #pragma unroll
                         for (int j = 0; j < 4; j++) {
-                            const uint32_t d = gp[g][j];
-                            ok[g][j] = 4u * lane + j < nn[g] && d >= rlo && d < rhi;
                             norm[g][j] = L.cnorm;
-                            if (ok[g][j] && ff >= 0 && role != ROLE_NOT)
-                                norm[g][j] = __ldg(p.ix.cache + ff * 256 + __ldg(fnp + d));
+                            if (slot[g][j] >= 0 && ff >= 0)
+                                norm[g][j] = __ldg(p.ix.cache + ff * 256 + __ldg(fnp + gp[g][j]));
                         }
                     }
+                    // ... then BM25 and the slot update
 #pragma unroll
                     for (int g = 0; g < GRP; g++) {
                         const float wgt = S.leaf[lf[g]].weight;
 #pragma unroll
                         for (int j = 0; j < 4; j++) {
-                            if (!ok[g][j]) continue;
-                            const uint32_t d = gp[g][j];
-                            int slot;
-                            if (DENSE) {
-                                slot = (int)(d - rlo);
-                                if (!PURE && filter) {
-                                    const uint32_t m = msk[slot];
-                                    if ((m & req) != req || (role == ROLE_NOT && m == 0)) slot = -1;
-                                }
-                            } else {
-                                uint32_t h = hash_doc(d);
-                                slot = -1;
-                                while (true) {
-                                    uint32_t kd = keys[h];
-                                    if (kd == d) { slot = (int)h; break; }
-                                    if (kd == EMPTY) {
-                                        if (filter) break;
-                                        kd = atomicCAS(&keys[h], EMPTY, d);
-                                        if (kd == EMPTY || kd == d) { slot = (int)h; break; }
-                                    }
-                                    h = (h + 1) & (HS - 1);
-                                }
-                                if (!PURE && slot >= 0 && filter && (msk[slot] & req) != req) slot = -1;
-                            }
-                            if (slot < 0) continue;
-                            if (!PURE && role == ROLE_NOT) {
-                                msk[slot] = (uint8_t)(msk[slot] | BIT_NOT);
-                                continue;
-                            }
+                            const int sl = slot[g][j];
+                            if (sl < 0) continue;
                             const float t = (float)(tf[g][j] + 1u);
-                            smem_add_f32(&acc[slot], wgt * __fdividef(t, t + norm[g][j]));
-                            if (!PURE && bit) msk[slot] = (uint8_t)(msk[slot] | bit);
+                            smem_add_f32(&acc[sl], wgt * __fdividef(t, t + norm[g][j]));
+                            if (!PURE && bit) msk[sl] = (uint8_t)(msk[sl] | bit);
                             my_scored++;
                         }
                     }
+                }
                 }
                 if (!__syncthreads_or(my_pending)) break;
             }
@@ -421,7 +439,7 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
             const uint32_t need = S.leaf[l1 - 1].build_cb;
             if (!PURE && need) {
                 if (DENSE) {
-                    if (tid < CBW) {
+                    if (tid < DW / 32) {
                         const uint32_t* m32 = reinterpret_cast<const uint32_t*>(msk) + tid * 8;
                         uint32_t word = 0;
 #pragma unroll
@@ -434,7 +452,7 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
                         cb[tid] = word;
                     }
                 } else {
-                    if (tid < CBW) cb[tid] = 0;
+                    for (int i = tid; i < CBW; i += NT) cb[i] = 0;
                     __syncthreads();
                     for (int i = tid; i < HS; i += NT) {
                         const uint32_t kd = keys[i];
@@ -553,9 +571,9 @@ __global__ void __launch_bounds__(NT, 3) search_kernel(const SearchParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ Shared S;
     float* acc = reinterpret_cast<float*>(smem);
-    uint32_t* keys = reinterpret_cast<uint32_t*>(smem) + HS;  // aliases acc[HS..] (hash mode only)
-    uint8_t* msk = smem + DW * 4;
-    uint32_t* cb = reinterpret_cast<uint32_t*>(smem + DW * 4 + DW);
+    uint32_t* keys = reinterpret_cast<uint32_t*>(smem + SLOTS * 4);  // hash mode only
+    uint8_t* msk = smem + SLOTS * 4 + HS * 4;
+    uint32_t* cb = reinterpret_cast<uint32_t*>(smem + SLOTS * 4 + HS * 4 + SLOTS);
     uint32_t* wl = cb + CBW;
     uint64_t* scratch = reinterpret_cast<uint64_t*>(wl + NW * SEG_CAP);
 
@@ -660,7 +678,7 @@ __global__ void __launch_bounds__(128) merge_gathered_kernel(const uint2* hits, 
 }  // namespace
 
 int search_smem_bytes(int ks) {
-    return DW * 4 + DW + CBW * 4 + NW * SEG_CAP * 4 + NW * ks * 32 * 8;
+    return SLOTS * 4 + HS * 4 + SLOTS + CBW * 4 + NW * SEG_CAP * 4 + NW * ks * 32 * 8;
 }
 
 template <int KS>

@@ -162,6 +162,9 @@ typedef struct fg_batch fg_batch;
 int32_t fg_batch_prepare(fg_index* index, const fg_query_batch* batch, fg_batch** out);
 void fg_batch_release(fg_batch* b);
 #define FG_EXEC_EXACT_ACCOUNTING 1u /* exact block-need test for the algorithmic-byte counters (slow) */
+#define FG_EXEC_DETERMINISTIC 2u    /* apply leaves one at a time: bit-reproducible f32 sums (slower);
+                                       default sums the leaves of a clause with float atomics, which can
+                                       differ in the last bit for docs with >= 3 contributions */
 /* Launches the search kernels for the prepared batch on the context's stream (asynchronous).
  * d_hits [n_queries*k_stride] fg_hit, d_n_hits [n_queries], d_match_count [n_queries] or NULL:
  * DEVICE pointers. d_match_bitmap: NULL, or DEVICE [n_queries * ceil(n_docs/32)] words, zeroed by

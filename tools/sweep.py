@@ -20,13 +20,23 @@ def main():
              "and": [q for q in queries if " AND " in q["query"]],
              "or": [q for q in queries if " AND " not in q["query"] and " " in q["query"]],
              "single": [q for q in queries if " " not in q["query"]]}
+    offs = [f["term_offsets"] for f in fields]
+    def sumdf(q):
+        tot = 0
+        for w in q["query"].replace(" AND ", " ").split():
+            t = int(w[1:]) - 1
+            for o in offs: tot += int(o[t + 1] - o[t])
+        return tot
+    thr = 1536 * cfg.n_docs / 8192
+    kinds["or_dense"] = [q for q in kinds["or"] + kinds["single"] if sumdf(q) >= thr]
+    kinds["or_hash"] = [q for q in kinds["or"] + kinds["single"] if sumdf(q) < thr]
     dev = torch.device("cuda:0")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     settings = json.loads(os.environ.get("SWEEP", '[{}]'))
     for s in settings:
         for k_, v in s.items(): os.environ[k_] = str(v)
         for kind, qs in kinds.items():
-            if not qs: continue
+            if not qs or os.environ.get("SWEEP_KIND", kind) != kind: continue
             b = synth.lower_queries(qs, vocab=cfg.vocab, n_text_fields=2)
             pb = index.prepare(b)
             n = b.n_queries
