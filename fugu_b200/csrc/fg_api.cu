@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "../../include/fugu_gpu.h"
+#include "fg_error.h"
 #include "fg_internal.h"
 
 using namespace fg;
@@ -26,6 +27,13 @@ using namespace fg;
 // ------------------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
 static int32_t fail(int32_t code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+int32_t fg::host_fail(int32_t code, const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
@@ -354,6 +362,16 @@ extern "C" int32_t fg_index_upload(fg_ctx* ctx, const fg_index_desc* d, fg_index
         if ((rc = dev_copy(d->alive_bitset, ((size_t)d->n_docs + 31) / 32 * 4, (const void**)&ix->dev.alive))) return rc;
     ix->dev.n_docs = d->n_docs;
     ix->dev.doc_base = d->doc_id_base;
+    ix->dev.n_alive = d->n_docs;
+    if (d->alive_bitset) {
+        uint32_t na = 0;
+        for (uint32_t w = 0; w < (d->n_docs + 31) / 32; w++) {
+            uint32_t x = d->alive_bitset[w];
+            if (w == d->n_docs / 32 && (d->n_docs & 31)) x &= (1u << (d->n_docs & 31)) - 1u;
+            na += (uint32_t)__builtin_popcount(x);
+        }
+        ix->dev.n_alive = na;
+    }
 
     ix->info.n_postings = n_postings;
     ix->info.n_blocks = n_blocks;
@@ -501,8 +519,11 @@ extern "C" int32_t fg_batch_prepare(fg_index* ix, const fg_query_batch* qb, fg_b
         D.const_score = const_score;
         D.leaf_begin = (uint32_t)dl.size();
         if (has_all_only && must.empty() && !empty) {
-            if (should.empty() && mnot.empty())
-                return fail(FG_ERR_UNSUPPORTED, "query %u: pure AllQuery is answered by the host (first k alive docs)", qi);
+            if (should.empty() && mnot.empty()) {  // pure AllQuery: every alive doc, score = boost
+                D.flags |= QF_ALL;
+                D.n_leaves = 0; D.n_items = 0; D.item_begin = (uint32_t)items.size();
+                continue;
+            }
             return fail(FG_ERR_UNSUPPORTED, "query %u: AllQuery Must with only Should/MustNot siblings not supported", qi);
         }
         if (empty || (must.empty() && should.empty())) { D.n_leaves = 0; D.n_items = 0; D.item_begin = (uint32_t)items.size(); continue; }
@@ -652,6 +673,9 @@ extern "C" int32_t fg_batch_execute(fg_batch* b, uint32_t flags, uint32_t k_stri
     m.partial_count = b->d_partial_count;
     m.k_stride = k_stride;
     m.doc_base = ix->doc_base;
+    m.alive = ix->dev.alive;
+    m.n_docs = ix->n_docs;
+    m.n_alive = ix->dev.n_alive;
     m.out_hits = d_hits;
     m.out_n = (uint32_t*)d_n_hits;
     m.out_count = (uint32_t*)d_match_count;

@@ -1,0 +1,864 @@
+// Host side of the query path above the device ABI: tokenizer, tantivy-style query parser,
+// the planning half of Dataset::search and a small dataset builder (include/fugu_host.h).
+// Mirrors /root/reference/src/db/search.rs:74-324,594-610 (fugu side) and SURVEY.md Appendix
+// A.1/A.2 (tantivy 0.24.1 side, upstream-recalled). No search arithmetic happens here: every
+// search goes to the device through fg_search_batch.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/fugu_host.h"
+#include "fg_error.h"
+#include "fg_unicode_tables.h"
+
+using fg::host_fail;
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// A.1 default analyzer: SimpleTokenizer -> RemoveLongFilter(40) -> LowerCaser
+// ------------------------------------------------------------------------------------------
+inline bool decode_utf8(const unsigned char* s, size_t n, size_t& i, uint32_t& cp) {
+    const unsigned char c = s[i];
+    if (c < 0x80) { cp = c; i += 1; return true; }
+    int len = (c >> 5) == 0x6 ? 2 : (c >> 4) == 0xE ? 3 : (c >> 3) == 0x1E ? 4 : 0;
+    if (!len || i + len > n) { cp = 0xFFFD; i += 1; return false; }
+    cp = c & (0xFF >> (len + 1));
+    for (int k = 1; k < len; k++) {
+        if ((s[i + k] & 0xC0) != 0x80) { cp = 0xFFFD; i += 1; return false; }
+        cp = (cp << 6) | (s[i + k] & 0x3F);
+    }
+    i += len;
+    return true;
+}
+inline bool is_alnum_cp(uint32_t cp) {
+    if (cp < 0x80) return (cp >= '0' && cp <= '9') || (cp >= 'a' && cp <= 'z') || (cp >= 'A' && cp <= 'Z');
+    int lo = 0, hi = fg::kNumAlnumRanges - 1;
+    while (lo <= hi) {
+        int mid = (lo + hi) >> 1;
+        if (cp < fg::kAlnumRanges[mid].lo) hi = mid - 1;
+        else if (cp > fg::kAlnumRanges[mid].hi) lo = mid + 1;
+        else return true;
+    }
+    return false;
+}
+inline void append_utf8(std::string& o, uint32_t cp) {
+    if (cp < 0x80) o.push_back((char)cp);
+    else if (cp < 0x800) { o.push_back((char)(0xC0 | (cp >> 6))); o.push_back((char)(0x80 | (cp & 0x3F))); }
+    else if (cp < 0x10000) { o.push_back((char)(0xE0 | (cp >> 12))); o.push_back((char)(0x80 | ((cp >> 6) & 0x3F))); o.push_back((char)(0x80 | (cp & 0x3F))); }
+    else { o.push_back((char)(0xF0 | (cp >> 18))); o.push_back((char)(0x80 | ((cp >> 12) & 0x3F))); o.push_back((char)(0x80 | ((cp >> 6) & 0x3F))); o.push_back((char)(0x80 | (cp & 0x3F))); }
+}
+inline void append_lower(std::string& o, uint32_t cp) {
+    if (cp < 0x80) { o.push_back((char)((cp >= 'A' && cp <= 'Z') ? cp + 32 : cp)); return; }
+    int lo = 0, hi = fg::kNumLowerMap - 1;
+    while (lo <= hi) {
+        int mid = (lo + hi) >> 1;
+        if (cp < fg::kLowerMap[mid].cp) hi = mid - 1;
+        else if (cp > fg::kLowerMap[mid].cp) lo = mid + 1;
+        else { o += fg::kLowerMap[mid].utf8; return; }
+    }
+    append_utf8(o, cp);
+}
+void tokenize(const char* text, size_t n, std::vector<std::string>& out) {
+    const unsigned char* s = (const unsigned char*)text;
+    size_t i = 0;
+    while (i < n) {
+        // skip separators
+        size_t j = i;
+        uint32_t cp;
+        decode_utf8(s, n, j, cp);
+        if (!is_alnum_cp(cp)) { i = j; continue; }
+        // maximal alphanumeric run [i, e)
+        size_t e = j;
+        while (e < n) {
+            size_t k = e;
+            decode_utf8(s, n, k, cp);
+            if (!is_alnum_cp(cp)) break;
+            e = k;
+        }
+        if (e - i < 40) {  // RemoveLongFilter::limit(40): keep tokens with len_bytes < 40 (before lowercasing)
+            std::string tok;
+            tok.reserve(e - i);
+            size_t k = i;
+            while (k < e) { decode_utf8(s, e, k, cp); append_lower(tok, cp); }
+            out.push_back(std::move(tok));
+        }
+        i = e;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// facet paths: Facet::from_text("/a/b/c") -> one term per ancestor ("/a", "/a/b", "/a/b/c")
+// ------------------------------------------------------------------------------------------
+bool facet_segments(const std::string& path, std::vector<std::string>& segs) {
+    if (path.empty() || path[0] != '/') return false;
+    std::string cur;
+    bool esc = false;
+    for (size_t i = 1; i < path.size(); i++) {
+        char c = path[i];
+        if (esc) { cur.push_back(c); esc = false; continue; }
+        if (c == '\\') { esc = true; continue; }
+        if (c == '/') { segs.push_back(cur); cur.clear(); continue; }
+        cur.push_back(c);
+    }
+    if (path.size() > 1) segs.push_back(cur);
+    return true;
+}
+std::string facet_key(const std::vector<std::string>& segs, size_t n) {
+    std::string k;
+    for (size_t i = 0; i < n; i++) { k.push_back('/'); k += segs[i]; }
+    return k;
+}
+// normalize_facet_path, src/db/search.rs:594-600
+std::string normalize_facet_path(const std::string& p) { return (!p.empty() && p[0] == '/') ? p : "/" + p; }
+
+// ------------------------------------------------------------------------------------------
+// A.2 query grammar (tantivy-query-grammar 0.24 subset) -> user AST
+// ------------------------------------------------------------------------------------------
+enum Occ : int { O_NONE = -1, O_SHOULD = 0, O_MUST = 1, O_NOT = 2 };
+struct Ast {
+    enum Kind { LEAF, ALL, CLAUSE } kind = LEAF;
+    std::string field;   // LEAF: explicit field or ""
+    std::string text;    // LEAF: literal
+    bool quoted = false;
+    float boost = 1.f;
+    std::vector<std::pair<int, Ast>> kids;  // CLAUSE: (occur or O_NONE, child)
+};
+struct ParseError { std::string msg; bool unsupported = false; };
+
+struct Parser {
+    const std::string& s;
+    size_t i = 0;
+    explicit Parser(const std::string& q) : s(q) {}
+    void ws() { while (i < s.size() && isspace((unsigned char)s[i])) i++; }
+    bool eof() const { return i >= s.size(); }
+    static bool special(char c) { return strchr("()[]{}\":^~", c) != nullptr; }
+    bool keyword(const char* kw) {
+        size_t n = strlen(kw);
+        if (s.compare(i, n, kw) != 0) return false;
+        if (i + n < s.size() && !isspace((unsigned char)s[i + n]) && s[i + n] != '(') return false;
+        return true;
+    }
+    std::string word() {
+        std::string w;
+        while (i < s.size() && !isspace((unsigned char)s[i]) && !special(s[i])) {
+            if (s[i] == '\\' && i + 1 < s.size()) { w.push_back(s[i + 1]); i += 2; continue; }
+            w.push_back(s[i++]);
+        }
+        return w;
+    }
+    void boost(Ast& a) {
+        if (i < s.size() && s[i] == '^') {
+            size_t j = i + 1;
+            char* end = nullptr;
+            float b = strtof(s.c_str() + j, &end);
+            if (end == s.c_str() + j) throw ParseError{"expected a number after '^'"};
+            a.boost *= b;
+            i = end - s.c_str();
+        }
+    }
+    Ast leaf() {
+        ws();
+        if (eof()) throw ParseError{"unexpected end of query"};
+        Ast a;
+        char c = s[i];
+        if (c == '(') {
+            i++;
+            a = seq(true);
+            ws();
+            if (eof() || s[i] != ')') throw ParseError{"missing ')'"};
+            i++;
+            boost(a);
+            return a;
+        }
+        if (c == '[' || c == '{') throw ParseError{"range queries are not evaluated on the device", true};
+        if (c == ')' || c == ']' || c == '}' || c == '^' || c == '~' || c == ':') throw ParseError{std::string("unexpected '") + c + "'"};
+        if (c == '*' && (i + 1 == s.size() || isspace((unsigned char)s[i + 1]) || s[i + 1] == ')')) {
+            i++;
+            a.kind = Ast::ALL;
+            return a;
+        }
+        if (c == '"') {
+            size_t j = s.find('"', i + 1);
+            if (j == std::string::npos) throw ParseError{"unbalanced '\"'"};
+            a.text = s.substr(i + 1, j - i - 1);
+            a.quoted = true;
+            i = j + 1;
+            if (i < s.size() && s[i] == '~') throw ParseError{"phrase slop is not evaluated on the device", true};
+            boost(a);
+            return a;
+        }
+        std::string w = word();
+        if (w.empty()) throw ParseError{"empty term"};
+        if (i < s.size() && s[i] == ':') {  // field:literal
+            i++;
+            if (eof() || isspace((unsigned char)s[i])) throw ParseError{"missing value after ':'"};
+            Ast v = leaf();
+            if (v.kind != Ast::LEAF) {
+                if (v.kind == Ast::CLAUSE) throw ParseError{"field:(...) groups are not supported", true};
+                throw ParseError{"field:* is not supported", true};
+            }
+            v.field = w;
+            return v;
+        }
+        if (i < s.size() && s[i] == '~') throw ParseError{"fuzzy terms are not evaluated on the device", true};
+        a.text = w;
+        boost(a);
+        return a;
+    }
+    // (occur, leaf): '+', '-' prefixes and the NOT keyword
+    std::pair<int, Ast> occur_leaf() {
+        ws();
+        int occ = O_NONE;
+        if (!eof() && (s[i] == '+' || s[i] == '-') && i + 1 < s.size() && !isspace((unsigned char)s[i + 1])) {
+            occ = s[i] == '+' ? O_MUST : O_NOT;
+            i++;
+        } else if (keyword("NOT")) {
+            i += 3;
+            occ = O_NOT;
+        }
+        Ast a = leaf();
+        return {occ, std::move(a)};
+    }
+    // one item of the top-level sequence: a single occur_leaf or a chain `x AND y OR z`
+    std::pair<int, Ast> item() {
+        auto first = occur_leaf();
+        std::vector<std::vector<std::pair<int, Ast>>> dnf;  // aggregate_binary_expressions
+        dnf.emplace_back();
+        dnf.back().push_back(std::move(first));
+        bool chain = false;
+        while (true) {
+            size_t save = i;
+            ws();
+            bool is_and = keyword("AND"), is_or = !is_and && keyword("OR");
+            if (!is_and && !is_or) { i = save; break; }
+            i += is_and ? 3 : 2;
+            ws();
+            if (eof()) throw ParseError{"dangling boolean operator"};
+            auto nx = occur_leaf();
+            chain = true;
+            if (is_and) dnf.back().push_back(std::move(nx));
+            else { dnf.emplace_back(); dnf.back().push_back(std::move(nx)); }
+        }
+        if (!chain) return std::move(dnf[0][0]);
+        auto make_and = [](std::vector<std::pair<int, Ast>>& g) -> std::pair<int, Ast> {
+            if (g.size() == 1) return std::move(g[0]);
+            Ast c;
+            c.kind = Ast::CLAUSE;
+            for (auto& x : g) c.kids.emplace_back(x.first == O_NONE ? O_MUST : x.first, std::move(x.second));
+            return {O_NONE, std::move(c)};
+        };
+        if (dnf.size() == 1) return make_and(dnf[0]);
+        Ast c;
+        c.kind = Ast::CLAUSE;
+        for (auto& g : dnf) {
+            auto x = make_and(g);
+            c.kids.emplace_back(x.first == O_NONE ? O_SHOULD : x.first, std::move(x.second));
+        }
+        return {O_NONE, std::move(c)};
+    }
+    Ast seq(bool in_paren) {
+        Ast c;
+        c.kind = Ast::CLAUSE;
+        while (true) {
+            ws();
+            if (eof()) break;
+            if (s[i] == ')') { if (in_paren) break; throw ParseError{"unbalanced ')'"}; }
+            c.kids.push_back(item());
+        }
+        if (c.kids.empty()) throw ParseError{"empty query"};
+        if (c.kids.size() == 1 && c.kids[0].first == O_NONE) return std::move(c.kids[0].second);
+        return c;
+    }
+};
+
+// escape_query_string, src/db/search.rs:603-610
+std::string escape_query_string(const std::string& q) {
+    std::string o;
+    for (char c : q)
+        if (!strchr("()[]{}\":+-!~*?\\^", c)) o.push_back(c);
+    return o;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// dataset
+// ------------------------------------------------------------------------------------------
+struct FieldBuild {
+    std::unordered_map<std::string, uint32_t> dict;
+    std::vector<std::vector<std::pair<uint32_t, uint32_t>>> postings;  // term -> (doc, tf)
+    uint64_t total_tokens = 0;
+    std::vector<uint32_t> doc_len;
+    uint32_t term(const std::string& t) {
+        auto it = dict.find(t);
+        if (it != dict.end()) return it->second;
+        uint32_t o = (uint32_t)postings.size();
+        dict.emplace(t, o);
+        postings.emplace_back();
+        return o;
+    }
+};
+
+struct fgh_dataset {
+    fg_ctx* ctx = nullptr;
+    fg_index* index = nullptr;
+    std::mutex mu;
+    FieldBuild f[3];
+    std::vector<std::string> ids;
+    std::unordered_map<std::string, uint32_t> id2doc;
+    std::vector<uint8_t> alive;  // per doc
+    bool adopted = false;
+    bool dirty = false;
+    uint32_t n_docs = 0;
+    uint32_t doc_base = 0;
+};
+
+extern "C" int32_t fgh_dataset_create(fg_ctx* ctx, fgh_dataset** out) {
+    if (!out) return host_fail(FG_ERR_INVALID, "fgh_dataset_create: out is NULL");
+    *out = new fgh_dataset();
+    (*out)->ctx = ctx;
+    return FG_OK;
+}
+extern "C" void fgh_dataset_destroy(fgh_dataset* ds) {
+    if (!ds) return;
+    if (ds->index) fg_index_release(ds->index);
+    delete ds;
+}
+extern "C" uint32_t fgh_dataset_num_docs(const fgh_dataset* ds) { return ds ? ds->n_docs : 0; }
+extern "C" fg_index* fgh_dataset_index(fgh_dataset* ds) { return ds ? ds->index : nullptr; }
+
+extern "C" int32_t fgh_tokenize(const char* text, char* buf, uint32_t cap) {
+    if (!text || !buf) return -1;
+    std::vector<std::string> t;
+    tokenize(text, strlen(text), t);
+    size_t pos = 0;
+    for (auto& x : t) {
+        if (pos + x.size() + 1 > cap) return -1;
+        memcpy(buf + pos, x.c_str(), x.size() + 1);
+        pos += x.size() + 1;
+    }
+    return (int32_t)t.size();
+}
+
+static void delete_doc_locked(fgh_dataset* ds, const std::string& id) {
+    auto it = ds->id2doc.find(id);
+    if (it != ds->id2doc.end()) {
+        ds->alive[it->second] = 0;
+        ds->id2doc.erase(it);
+        ds->dirty = true;
+    }
+}
+
+extern "C" int32_t fgh_dataset_delete(fgh_dataset* ds, const char* id) {
+    if (!ds || !id) return host_fail(FG_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> g(ds->mu);
+    if (ds->adopted) return host_fail(FG_ERR_UNSUPPORTED, "adopted datasets are immutable");
+    delete_doc_locked(ds, id);
+    return FG_OK;
+}
+
+extern "C" int32_t fgh_dataset_upsert(fgh_dataset* ds, const char* id, const char* text, const char* name,
+                                      const char* const* facets, uint32_t n_facets) {
+    if (!ds || !id || !text) return host_fail(FG_ERR_INVALID, "fgh_dataset_upsert: NULL argument");
+    // ObjectRecord::validate, src/object.rs:31-78
+    const size_t idl = strlen(id), tl = strlen(text);
+    if (idl == 0) return host_fail(FG_ERR_INVALID, "Object ID cannot be empty");
+    if (idl > 256) return host_fail(FG_ERR_INVALID, "Object ID too long (max 256 characters)");
+    if (tl == 0) return host_fail(FG_ERR_INVALID, "Object text cannot be empty");
+    if (tl > 10000) return host_fail(FG_ERR_INVALID, "Text too long (max 10000 characters)");
+    if (n_facets > 100) return host_fail(FG_ERR_INVALID, "Too many facets (max 100 per object)");
+    for (uint32_t i = 0; i < n_facets; i++) {
+        if (!facets[i] || !facets[i][0]) return host_fail(FG_ERR_INVALID, "Facet at index %u cannot be empty", i);
+        if (strlen(facets[i]) > 512) return host_fail(FG_ERR_INVALID, "Facet at index %u too long (max 512 characters)", i);
+    }
+    std::lock_guard<std::mutex> g(ds->mu);
+    if (ds->adopted) return host_fail(FG_ERR_UNSUPPORTED, "adopted datasets are immutable");
+    delete_doc_locked(ds, id);  // delete_term(id) then add_document, src/db/document.rs:38-48
+    const uint32_t doc = ds->n_docs++;
+    ds->ids.emplace_back(id);
+    ds->id2doc[id] = doc;
+    ds->alive.push_back(1);
+    auto index_text = [&](FieldBuild& fb, const char* s) {
+        std::vector<std::string> toks;
+        if (s) tokenize(s, strlen(s), toks);
+        fb.doc_len.push_back((uint32_t)toks.size());
+        fb.total_tokens += toks.size();
+        std::sort(toks.begin(), toks.end());
+        for (size_t i = 0; i < toks.size();) {
+            size_t j = i + 1;
+            while (j < toks.size() && toks[j] == toks[i]) j++;
+            fb.postings[fb.term(toks[i])].emplace_back(doc, (uint32_t)(j - i));
+            i = j;
+        }
+    };
+    index_text(ds->f[FGH_FIELD_TEXT], text);
+    index_text(ds->f[FGH_FIELD_NAME], name);
+    {
+        FieldBuild& fb = ds->f[FGH_FIELD_FACET];
+        std::vector<std::string> keys;
+        for (uint32_t i = 0; i < n_facets; i++) {
+            std::vector<std::string> segs;
+            if (!facet_segments(normalize_facet_path(facets[i]), segs)) continue;  // Facet::from_text Err -> skipped (document.rs:322-329)
+            for (size_t n = 1; n <= segs.size(); n++) keys.push_back(facet_key(segs, n));
+        }
+        fb.doc_len.push_back((uint32_t)keys.size());
+        fb.total_tokens += keys.size();
+        std::sort(keys.begin(), keys.end());
+        keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
+        for (auto& k : keys) fb.postings[fb.term(k)].emplace_back(doc, 1u);
+    }
+    ds->dirty = true;
+    return FG_OK;
+}
+
+extern "C" int32_t fgh_dataset_commit(fgh_dataset* ds) {
+    if (!ds) return host_fail(FG_ERR_INVALID, "NULL dataset");
+    std::lock_guard<std::mutex> g(ds->mu);
+    if (ds->adopted) return FG_OK;
+    if (!ds->ctx) return host_fail(FG_ERR_NO_DEVICE, "dataset has no device context (planning only)");
+    struct Csr { std::vector<uint64_t> off; std::vector<uint32_t> docs, tfs; std::vector<uint8_t> fn; };
+    Csr c[3];
+    fg_field_desc fd[3];
+    memset(fd, 0, sizeof(fd));
+    for (int f = 0; f < 3; f++) {
+        FieldBuild& fb = ds->f[f];
+        c[f].off.resize(fb.postings.size() + 1);
+        uint64_t n = 0;
+        for (size_t t = 0; t < fb.postings.size(); t++) { c[f].off[t] = n; n += fb.postings[t].size(); }
+        c[f].off[fb.postings.size()] = n;
+        c[f].docs.resize(n);
+        c[f].tfs.resize(n);
+        for (size_t t = 0; t < fb.postings.size(); t++)
+            for (size_t i = 0; i < fb.postings[t].size(); i++) {
+                c[f].docs[c[f].off[t] + i] = fb.postings[t][i].first;
+                c[f].tfs[c[f].off[t] + i] = fb.postings[t][i].second;
+            }
+        fd[f].n_terms = (uint32_t)fb.postings.size();
+        fd[f].total_num_tokens = fb.total_tokens;
+        fd[f].term_offsets = c[f].off.data();
+        fd[f].doc_ids = c[f].docs.data();
+        if (f != (int)FGH_FIELD_FACET) {
+            c[f].fn.resize(ds->n_docs);
+            for (uint32_t d = 0; d < ds->n_docs; d++) c[f].fn[d] = fg_fieldnorm_to_id(fb.doc_len[d]);
+            fd[f].flags = FG_FIELD_HAS_FIELDNORMS | FG_FIELD_HAS_FREQS;
+            fd[f].fieldnorm_ids = c[f].fn.data();
+            fd[f].term_freqs = c[f].tfs.data();
+        }
+    }
+    std::vector<uint32_t> alive((ds->n_docs + 31) / 32, 0);
+    bool any_dead = false;
+    for (uint32_t d = 0; d < ds->n_docs; d++) {
+        if (ds->alive[d]) alive[d >> 5] |= 1u << (d & 31);
+        else any_dead = true;
+    }
+    fg_index_desc desc;
+    memset(&desc, 0, sizeof(desc));
+    desc.n_docs = ds->n_docs;
+    desc.n_fields = 3;
+    desc.fields = fd;
+    desc.alive_bitset = any_dead ? alive.data() : nullptr;
+    fg_index* nx = nullptr;
+    int32_t rc = fg_index_upload(ds->ctx, &desc, &nx);
+    if (rc) return rc;
+    if (ds->index) fg_index_release(ds->index);
+    ds->index = nx;
+    ds->dirty = false;
+    return FG_OK;
+}
+
+extern "C" int32_t fgh_dataset_adopt(fgh_dataset* ds, const fg_index_desc* desc, const char* const* terms,
+                                     const uint64_t* terms_bytes) {
+    if (!ds || !desc) return host_fail(FG_ERR_INVALID, "NULL argument");
+    if (desc->n_fields > 3) return host_fail(FG_ERR_INVALID, "adopt expects fields [text, name, facet]");
+    std::lock_guard<std::mutex> g(ds->mu);
+    if (ds->ctx) {
+        fg_index* nx = nullptr;
+        int32_t rc = fg_index_upload(ds->ctx, desc, &nx);
+        if (rc) return rc;
+        if (ds->index) fg_index_release(ds->index);
+        ds->index = nx;
+    }
+    for (uint32_t f = 0; f < desc->n_fields; f++) {
+        ds->f[f] = FieldBuild();
+        if (!terms || !terms[f]) continue;
+        const char* p = terms[f];
+        const char* end = p + terms_bytes[f];
+        ds->f[f].dict.reserve(desc->fields[f].n_terms * 2);
+        for (uint32_t t = 0; t < desc->fields[f].n_terms && p < end; t++) {
+            size_t l = strlen(p);
+            ds->f[f].dict.emplace(std::string(p, l), t);
+            p += l + 1;
+        }
+    }
+    ds->adopted = true;
+    ds->n_docs = desc->n_docs;
+    ds->doc_base = desc->doc_id_base;
+    return FG_OK;
+}
+
+extern "C" int32_t fgh_dataset_doc_id(const fgh_dataset* ds, uint32_t doc, char* buf, uint32_t cap) {
+    if (!ds || !buf) return -1;
+    if (ds->adopted) {  // synthetic corpora: "d%09u" 
+        int n = snprintf(buf, cap, "d%09u", doc);
+        return n < (int)cap ? n : -1;
+    }
+    if (doc >= ds->ids.size() || ds->ids[doc].size() + 1 > cap) return -1;
+    memcpy(buf, ds->ids[doc].c_str(), ds->ids[doc].size() + 1);
+    return (int32_t)ds->ids[doc].size();
+}
+
+extern "C" uint32_t fgh_dataset_term_ord(const fgh_dataset* ds, uint32_t field, const char* token) {
+    if (!ds || field > 2 || !token) return FG_TERM_MISSING;
+    auto it = ds->f[field].dict.find(token);
+    return it == ds->f[field].dict.end() ? FG_TERM_MISSING : it->second;
+}
+
+// ------------------------------------------------------------------------------------------
+// planning: user AST -> one level of clauses (what the device evaluates)
+// ------------------------------------------------------------------------------------------
+namespace {
+
+struct Group {                 // OR-ed leaves whose scores add up (word -> fields, facet group)
+    std::vector<fg_leaf> leaves;
+    bool all = false;          // AllQuery
+    float all_boost = 0.f;
+};
+struct LNode {                 // logical AST after field expansion / tokenisation
+    bool is_group = true;
+    Group g;
+    std::vector<std::pair<int, LNode>> kids;
+};
+
+struct Planner {
+    const fgh_dataset* ds;
+    explicit Planner(const fgh_dataset* d) : ds(d) {}
+
+    int field_of(const std::string& name) const {
+        if (name == "text") return FGH_FIELD_TEXT;
+        if (name == "name") return FGH_FIELD_NAME;
+        return -1;
+    }
+    void term_leaf(Group& g, uint32_t field, const std::string& literal, float boost) const {
+        std::vector<std::string> toks;
+        tokenize(literal.c_str(), literal.size(), toks);
+        if (toks.empty()) return;  // the analyzer dropped everything: no query for this field
+        if (toks.size() > 1) throw ParseError{"a literal that tokenises to several tokens is a PhraseQuery (needs positions)", true};
+        fg_leaf l;
+        l.field = field;
+        l.term_ord = fgh_dataset_term_ord(ds, field, toks[0].c_str());
+        l.boost = boost;
+        g.leaves.push_back(l);
+    }
+    LNode lower(const Ast& a, float boost) const {
+        LNode n;
+        if (a.kind == Ast::ALL) {
+            n.g.all = true;
+            n.g.all_boost = boost * a.boost;
+            return n;
+        }
+        if (a.kind == Ast::LEAF) {
+            const float b = boost * a.boost;
+            if (!a.field.empty()) {
+                int f = field_of(a.field);
+                if (f < 0) {
+                    if (a.field == "id" || a.field == "namespace" || a.field == "organization" || a.field == "conversation_id" ||
+                        a.field == "data_type" || a.field == "facet" || a.field == "metadata" || a.field.rfind("date_", 0) == 0)
+                        throw ParseError{"field '" + a.field + "' is not loaded on the device", true};
+                    throw ParseError{"Field does not exist: '" + a.field + "'"};
+                }
+                term_leaf(n.g, (uint32_t)f, a.text, b);
+            } else {  // default fields [text, name], src/db/search.rs:108-112
+                term_leaf(n.g, FGH_FIELD_TEXT, a.text, b);
+                term_leaf(n.g, FGH_FIELD_NAME, a.text, b);
+            }
+            return n;
+        }
+        n.is_group = false;
+        for (auto& k : a.kids) n.kids.emplace_back(k.first == O_NONE ? O_SHOULD : k.first, lower(k.second, boost * a.boost));
+        return n;
+    }
+};
+
+struct FlatClause { int occ; Group g; };
+
+bool all_should_groups(const LNode& n) {
+    if (n.is_group) return true;
+    for (auto& k : n.kids)
+        if (k.first != O_SHOULD || !all_should_groups(k.second)) return false;
+    return true;
+}
+void collect_groups(const LNode& n, Group& into) {
+    if (n.is_group) {
+        into.leaves.insert(into.leaves.end(), n.g.leaves.begin(), n.g.leaves.end());
+        if (n.g.all) { into.all = true; into.all_boost += n.g.all_boost; }
+        return;
+    }
+    for (auto& k : n.kids) collect_groups(k.second, into);
+}
+// Lift `node` (a boolean node seen under occur `occ`) into the flat clause list.
+void flatten(const LNode& n, int occ, std::vector<FlatClause>& out, int depth) {
+    if (n.is_group) { out.push_back({occ, n.g}); return; }
+    if (all_should_groups(n)) {  // Should-of-Should is a union whose scores add: one group
+        if (occ == O_SHOULD && depth == 0) {  // keep top-level Should words as separate clauses
+            for (auto& k : n.kids) flatten(k.second, O_SHOULD, out, depth + 1);
+            return;
+        }
+        FlatClause c{occ, {}};
+        collect_groups(n, c.g);
+        out.push_back(std::move(c));
+        return;
+    }
+    if (occ == O_MUST || depth == 0) {
+        // Must(Bool[Must a, Should b, MustNot c]) == Must a, Should b, MustNot c at this level
+        for (auto& k : n.kids) {
+            if (k.second.is_group || all_should_groups(k.second)) flatten(k.second, k.first, out, depth + 1);
+            else if (k.first == O_MUST) flatten(k.second, O_MUST, out, depth + 1);
+            else throw ParseError{"nested boolean (OR of AND groups / negated groups) is not evaluated on the device", true};
+        }
+        return;
+    }
+    throw ParseError{"nested boolean (OR of AND groups / negated groups) is not evaluated on the device", true};
+}
+
+// parse_filters + build_facet_query, src/db/search.rs:221-324
+void facet_group(const fgh_dataset* ds, const char* const* filters, uint32_t n, Group& g, bool& any_term) {
+    for (uint32_t i = 0; i < n; i++) {
+        std::string f = filters[i] ? filters[i] : "";
+        // Dataset::search drops filters of the form *x* before build_facet_query (:98-105); the
+        // wildcard post-filter branch is dead because parse_filters never emits Wildcard (F8)
+        if (!f.empty() && f.front() == '*' && f.back() == '*') continue;
+        std::string norm = normalize_facet_path(f);
+        std::string path;
+        if (norm.size() >= 2 && norm.compare(norm.size() - 2, 2, "/*") == 0) path = norm.substr(0, norm.size() - 2);  // Prefix -> exact term (:273-281)
+        else if (norm.find('=') != std::string::npos) path = norm.substr(0, norm.find('='));                         // a=b -> path a (:306-313)
+        else path = norm;
+        std::vector<std::string> segs;
+        if (!facet_segments(path, segs)) continue;  // Facet::from_text Err: filter silently dropped (:234,277)
+        any_term = true;
+        fg_leaf l;
+        l.field = FGH_FIELD_FACET;
+        l.term_ord = fgh_dataset_term_ord(ds, FGH_FIELD_FACET, facet_key(segs, segs.size()).c_str());
+        l.boost = 1.f;
+        g.leaves.push_back(l);
+    }
+}
+
+int32_t plan_impl(const fgh_dataset* ds, const char* query, const char* const* filters, uint32_t n_filters,
+                  uint32_t page, uint32_t per_page, fgh_plan_t* out) {
+    memset(out, 0, sizeof(*out));
+    const uint64_t limit = (uint64_t)page * per_page + per_page;  // src/db/search.rs:154-160
+    if (limit == 0) return host_fail(FG_ERR_INVALID, "per_page == 0: TopDocs::with_limit panics on a zero limit");
+    if (limit > 0xFFFFFFFFull) return host_fail(FG_ERR_INVALID, "page*per_page overflows");
+    out->k = (uint32_t)limit;
+    out->offset = page * per_page;
+    std::string q = query ? query : "";
+    bool blank = true;
+    for (char c : q) if (!isspace((unsigned char)c)) blank = false;
+
+    std::vector<FlatClause> flat;
+    Planner pl(ds);
+    bool text_all = false;
+    float text_all_boost = 1.f;
+    try {
+        if (blank) {
+            text_all = true;  // AllQuery, :115-116
+        } else {
+            LNode root;
+            try {
+                Parser p(q);
+                Ast a = p.seq(false);
+                root = pl.lower(a, 1.f);
+            } catch (ParseError& e) {
+                if (e.unsupported) throw;
+                // fallback: strip special characters and retry (:120-125); a second error is Err
+                out->used_fallback = 1;
+                std::string esc = escape_query_string(q);
+                Parser p(esc);
+                Ast a = p.seq(false);
+                root = pl.lower(a, 1.f);
+            }
+            if (root.is_group && root.g.all && root.g.leaves.empty()) { text_all = true; text_all_boost = root.g.all_boost; }
+            else flatten(root, O_SHOULD, flat, 0);
+        }
+    } catch (ParseError& e) {
+        return host_fail(e.unsupported ? FG_ERR_UNSUPPORTED : FG_ERR_INVALID, "query '%s': %s", q.c_str(), e.msg.c_str());
+    }
+
+    // non-wildcard filters present -> Must-join with the facet query (:131-144)
+    uint32_t n_nonwild = 0;
+    for (uint32_t i = 0; i < n_filters; i++) {
+        std::string f = filters[i] ? filters[i] : "";
+        if (!(!f.empty() && f.front() == '*' && f.back() == '*')) n_nonwild++;
+    }
+    if (n_nonwild) {
+        Group fg_;
+        bool any = false;
+        facet_group(ds, filters, n_filters, fg_, any);
+        if (text_all) {
+            // empty text query: the facet query alone (:136-138); no valid term -> AllQuery (:258-261)
+            flat.clear();
+            if (any) flat.push_back({O_SHOULD, fg_});
+            else out->is_all = 1;
+        } else {
+            // Bool[(Must, text_query), (Must, facet_query)]
+            std::vector<FlatClause> joined;
+            bool has_must = false;
+            for (auto& c : flat) if (c.occ == O_MUST) has_must = true;
+            if (!has_must) {
+                // Must(Bool[Should.., MustNot..]): without a Must child at least one Should has to
+                // match, so the Should clauses become ONE Must group (a union whose scores add)
+                FlatClause m{O_MUST, {}};
+                bool any_should = false;
+                for (auto& c : flat) {
+                    if (c.occ != O_SHOULD) continue;
+                    any_should = true;
+                    m.g.leaves.insert(m.g.leaves.end(), c.g.leaves.begin(), c.g.leaves.end());
+                    if (c.g.all) { m.g.all = true; m.g.all_boost += c.g.all_boost; }
+                }
+                if (any_should) joined.push_back(std::move(m));
+                for (auto& c : flat) if (c.occ == O_NOT) joined.push_back(c);
+                if (!any_should) {  // only MustNot: matches nothing, and so does the Must-join
+                    joined.clear();
+                    flat.clear();
+                    out->n_clauses = 0;
+                    out->n_leaves = 0;
+                    return FG_OK;
+                }
+            } else {
+                joined = flat;
+            }
+            FlatClause fc{O_MUST, {}};
+            if (any) fc.g = fg_;
+            else { fc.g.all = true; fc.g.all_boost = 1.f; }  // AllQuery Must: +1.0 on every hit
+            joined.push_back(std::move(fc));
+            flat.swap(joined);
+        }
+    } else if (text_all) {
+        out->is_all = 1;
+    }
+    if (out->is_all) {
+        out->n_clauses = 1;
+        out->clauses[0] = {FG_OCCUR_MUST, 0, 1};
+        out->n_leaves = 1;
+        out->leaves[0] = {0, FG_TERM_ALL, text_all ? text_all_boost : 1.f};
+        return FG_OK;
+    }
+    for (auto& c : flat) {
+        if (out->n_clauses >= FGH_MAX_PLAN_CLAUSES) return host_fail(FG_ERR_UNSUPPORTED, "too many clauses");
+        fg_clause& oc = out->clauses[out->n_clauses++];
+        oc.occur = c.occ == O_MUST ? FG_OCCUR_MUST : c.occ == O_NOT ? FG_OCCUR_MUST_NOT : FG_OCCUR_SHOULD;
+        oc.leaf_begin = out->n_leaves;
+        auto push = [&](const fg_leaf& l) -> bool {
+            if (out->n_leaves >= FGH_MAX_PLAN_LEAVES) return false;
+            out->leaves[out->n_leaves++] = l;
+            return true;
+        };
+        if (c.g.all) {
+            if (!c.g.leaves.empty() || c.occ != O_MUST)
+                return host_fail(FG_ERR_UNSUPPORTED, "'*' mixed with other terms outside a Must clause");
+            if (!push({0, FG_TERM_ALL, c.g.all_boost})) return host_fail(FG_ERR_UNSUPPORTED, "too many leaves");
+        }
+        for (auto& l : c.g.leaves)
+            if (!push(l)) return host_fail(FG_ERR_UNSUPPORTED, "too many leaves");
+        oc.n_leaves = out->n_leaves - oc.leaf_begin;
+    }
+    return FG_OK;
+}
+
+}  // namespace
+
+extern "C" int32_t fgh_plan(const fgh_dataset* ds, const char* query, const char* const* filters,
+                            uint32_t n_filters, uint32_t page, uint32_t per_page, fgh_plan_t* out) {
+    if (!ds || !out) return host_fail(FG_ERR_INVALID, "fgh_plan: NULL argument");
+    return plan_impl(ds, query, filters, n_filters, page, per_page, out);
+}
+
+extern "C" int32_t fgh_search_batch(fgh_dataset* ds, uint32_t n, const char* const* queries,
+                                    const char* const* filters, const uint32_t* filter_offsets,
+                                    const uint32_t* pages, const uint32_t* per_pages, uint32_t stride,
+                                    fg_hit* out_hits, uint32_t* out_n, uint32_t* out_match_count,
+                                    int32_t* status) {
+    if (!ds || (n && (!queries || !out_hits || !out_n))) return host_fail(FG_ERR_INVALID, "fgh_search_batch: NULL argument");
+    if (!ds->index) return host_fail(ds->ctx ? FG_ERR_INVALID : FG_ERR_NO_DEVICE, "dataset has no device snapshot (commit first)");
+    if (n == 0) return FG_OK;
+    std::vector<fgh_plan_t> plans(n);
+    std::vector<int32_t> rc(n, FG_OK);
+    std::vector<std::string> errs(n);
+    unsigned hw = std::thread::hardware_concurrency();
+    int T = (int)std::max(1u, std::min<unsigned>(hw ? hw : 4, std::min<unsigned>(32, n / 64 + 1)));
+    auto work = [&](int t) {
+        for (uint32_t i = (uint32_t)((uint64_t)n * t / T); i < (uint32_t)((uint64_t)n * (t + 1) / T); i++) {
+            const uint32_t f0 = filter_offsets ? filter_offsets[i] : 0, f1 = filter_offsets ? filter_offsets[i + 1] : 0;
+            rc[i] = plan_impl(ds, queries[i], filters ? filters + f0 : nullptr, f1 - f0, pages ? pages[i] : 0,
+                              per_pages ? per_pages[i] : 20, &plans[i]);
+            if (rc[i]) errs[i] = fg_last_error();
+        }
+    };
+    if (T == 1) work(0);
+    else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < T; t++) th.emplace_back(work, t);
+        for (auto& x : th) x.join();
+    }
+    // one flat batch; queries that failed to plan become empty plans (match nothing)
+    std::vector<fg_query> fq(n);
+    std::vector<fg_clause> fc;
+    std::vector<fg_leaf> fl;
+    uint32_t kmax = 1;
+    int32_t first_err = FG_OK;
+    for (uint32_t i = 0; i < n; i++) {
+        if (status) status[i] = rc[i];
+        if (rc[i] && !first_err) { first_err = rc[i]; host_fail(rc[i], "%s", errs[i].c_str()); }
+        fq[i].k = rc[i] ? 1 : plans[i].k;
+        fq[i].clause_begin = (uint32_t)fc.size();
+        fq[i].n_clauses = rc[i] ? 0 : plans[i].n_clauses;
+        if (!rc[i]) {
+            for (uint32_t c = 0; c < plans[i].n_clauses; c++) {
+                fg_clause cl = plans[i].clauses[c];
+                cl.leaf_begin += (uint32_t)fl.size();
+                fc.push_back(cl);
+            }
+            fl.insert(fl.end(), plans[i].leaves, plans[i].leaves + plans[i].n_leaves);
+        }
+        kmax = std::max(kmax, fq[i].k);
+    }
+    if (first_err && !status) return first_err;  // single-status callers see the first failure
+    fg_query_batch qb;
+    memset(&qb, 0, sizeof(qb));
+    qb.n_queries = n;
+    qb.n_clauses = (uint32_t)fc.size();
+    qb.n_leaves = (uint32_t)fl.size();
+    qb.queries = fq.data();
+    qb.clauses = fc.data();
+    qb.leaves = fl.data();
+    std::vector<fg_hit> hits((size_t)n * kmax);
+    std::vector<uint32_t> nh(n), cnt(n);
+    int32_t r = fg_search_batch(ds->index, &qb, kmax, hits.data(), nh.data(), cnt.data());
+    if (r) return r;
+    for (uint32_t i = 0; i < n; i++) {
+        const uint32_t off = rc[i] ? 0 : plans[i].offset, pp = per_pages ? per_pages[i] : 20;
+        uint32_t m = nh[i] > off ? std::min(nh[i] - off, std::min(pp, stride)) : 0;  // skip(offset).take(per_page)
+        if (rc[i]) m = 0;
+        for (uint32_t j = 0; j < m; j++) out_hits[(size_t)i * stride + j] = hits[(size_t)i * kmax + off + j];
+        out_n[i] = m;
+        if (out_match_count) out_match_count[i] = rc[i] ? 0 : cnt[i];
+    }
+    return FG_OK;
+}
+
+extern "C" int32_t fgh_search(fgh_dataset* ds, const char* query, const char* const* filters, uint32_t n_filters,
+                              uint32_t page, uint32_t per_page, fg_hit* out_hits, uint32_t* out_n,
+                              uint32_t* out_match_count) {
+    const uint32_t offs[2] = {0, n_filters};
+    return fgh_search_batch(ds, 1, &query, filters, offs, &page, &per_page, per_page, out_hits, out_n,
+                            out_match_count, nullptr);
+}

@@ -46,6 +46,7 @@ struct DevLeaf {
 
 constexpr uint32_t MODE_DENSE = 0, MODE_HASH = 1;
 constexpr uint32_t QF_NO_MUST = 1;
+constexpr uint32_t QF_ALL = 4;         // pure AllQuery: first k alive docs, score = const_score
 constexpr uint32_t QF_PURE_UNION = 2;  // only Should clauses, all weights > 0: no clause masks needed
 
 struct DevQuery {
@@ -77,6 +78,7 @@ struct DevIndex {
     const uint32_t* alive;
     uint32_t n_docs;
     uint32_t doc_base;
+    uint32_t n_alive;
 };
 
 struct SearchParams {
@@ -103,6 +105,8 @@ struct MergeParams {
     const uint32_t* partial_count;
     uint32_t k_stride;
     uint32_t doc_base;
+    const uint32_t* alive;
+    uint32_t n_docs, n_alive;
     void* out_hits;        // fg_hit [n_queries][k_stride]
     uint32_t* out_n;
     uint32_t* out_count;   // may be null

@@ -599,6 +599,25 @@ __global__ void __launch_bounds__(128) merge_kernel(const MergeParams p) {
     if (qi >= p.n_queries) return;
     const DevQuery q = p.queries[qi];
     const int k = (int)q.k;
+    if (q.flags & QF_ALL) {  // AllQuery: the first k alive docs (every score equals const_score)
+        uint2* outp = reinterpret_cast<uint2*>(p.out_hits) + (size_t)qi * p.k_stride;
+        uint32_t found = 0;
+        for (uint32_t base = 0; base < p.n_docs && found < (uint32_t)k; base += 32) {
+            const uint32_t d = base + lane;
+            const bool al = d < p.n_docs && (!p.alive || ((p.alive[d >> 5] >> (d & 31)) & 1u));
+            const unsigned m = __ballot_sync(FULL, al);
+            const uint32_t r = found + __popc(m & ((1u << lane) - 1u));
+            if (al && r < (uint32_t)k && r < p.k_stride) outp[r] = make_uint2(__float_as_uint(q.const_score), d + p.doc_base);
+            found += __popc(m);
+        }
+        const uint32_t nh_all = min(min(found, (uint32_t)k), p.k_stride);
+        for (uint32_t r = nh_all + lane; r < p.k_stride; r += 32) outp[r] = make_uint2(0u, 0xFFFFFFFFu);
+        if (lane == 0) {
+            p.out_n[qi] = nh_all;
+            if (p.out_count) p.out_count[qi] = p.n_alive;
+        }
+        return;
+    }
     WarpTopK<KS> tk;
     tk.init();
     const uint64_t* src = p.partial + (size_t)q.item_begin * p.kcap;

@@ -1,0 +1,291 @@
+"""Python mirror of the reference's host interface for the query path, over the C ABI in
+include/fugu_host.h (which itself mirrors the Rust code name by name).
+
+    Dataset.search(query, filters, page, per_page)   <->  Dataset::search         src/db/search.rs:74-218
+    Dataset.upsert(records) / ingest                  <->  DocumentOperations::upsert  src/db/document.rs:23-67
+    ObjectRecord + facet path derivation              <->  src/object.rs:31-111, src/db/document.rs:277-312,
+                                                           src/db/utils.rs:11-55
+    perform_search (per_page clamp)                   <->  src/server/handlers/search.rs:350-402
+
+All searching happens on the GPU through libfugu_gpu.so; this module only marshals strings.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Any
+
+import numpy as np
+
+from . import _native as nat
+
+FIELD_TEXT, FIELD_NAME, FIELD_FACET = 0, 1, 2
+MAX_PLAN_CLAUSES, MAX_PLAN_LEAVES = 16, 64
+
+
+class _Leaf(C.Structure):
+    _fields_ = [("field", C.c_uint32), ("term_ord", C.c_uint32), ("boost", C.c_float)]
+
+
+class _Clause(C.Structure):
+    _fields_ = [("occur", C.c_uint32), ("leaf_begin", C.c_uint32), ("n_leaves", C.c_uint32)]
+
+
+class Plan(C.Structure):
+    _fields_ = [("k", C.c_uint32), ("offset", C.c_uint32), ("n_clauses", C.c_uint32), ("n_leaves", C.c_uint32),
+                ("is_all", C.c_uint32), ("used_fallback", C.c_uint32),
+                ("clauses", _Clause * MAX_PLAN_CLAUSES), ("leaves", _Leaf * MAX_PLAN_LEAVES)]
+
+    def as_dict(self) -> dict:
+        cl = []
+        for i in range(self.n_clauses):
+            c = self.clauses[i]
+            cl.append((int(c.occur), [(int(self.leaves[j].field), int(self.leaves[j].term_ord), float(self.leaves[j].boost))
+                                      for j in range(c.leaf_begin, c.leaf_begin + c.n_leaves)]))
+        return {"k": int(self.k), "offset": int(self.offset), "is_all": bool(self.is_all),
+                "used_fallback": bool(self.used_fallback), "clauses": cl}
+
+
+HOST_SYMBOLS = [
+    "fgh_dataset_create", "fgh_dataset_destroy", "fgh_dataset_upsert", "fgh_dataset_delete", "fgh_dataset_commit",
+    "fgh_dataset_adopt", "fgh_dataset_num_docs", "fgh_dataset_index", "fgh_dataset_doc_id", "fgh_dataset_term_ord",
+    "fgh_tokenize", "fgh_plan", "fgh_search", "fgh_search_batch",
+]
+_bound = False
+
+
+def _L():
+    global _bound
+    L = nat.lib()
+    if not _bound:
+        vp, u32, i32 = C.c_void_p, C.c_uint32, C.c_int32
+        cpp = C.POINTER(C.c_char_p)
+        L.fgh_dataset_create.argtypes = [vp, C.POINTER(vp)]
+        L.fgh_dataset_destroy.argtypes = [vp]
+        L.fgh_dataset_destroy.restype = None
+        L.fgh_dataset_upsert.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_char_p, cpp, u32]
+        L.fgh_dataset_delete.argtypes = [vp, C.c_char_p]
+        L.fgh_dataset_commit.argtypes = [vp]
+        L.fgh_dataset_adopt.argtypes = [vp, C.POINTER(nat.IndexDesc), cpp, C.POINTER(C.c_uint64)]
+        L.fgh_dataset_num_docs.argtypes = [vp]
+        L.fgh_dataset_num_docs.restype = u32
+        L.fgh_dataset_index.argtypes = [vp]
+        L.fgh_dataset_index.restype = vp
+        L.fgh_dataset_doc_id.argtypes = [vp, u32, C.c_char_p, u32]
+        L.fgh_dataset_term_ord.argtypes = [vp, u32, C.c_char_p]
+        L.fgh_dataset_term_ord.restype = u32
+        L.fgh_tokenize.argtypes = [C.c_char_p, C.c_char_p, u32]
+        L.fgh_plan.argtypes = [vp, C.c_char_p, cpp, u32, u32, u32, C.POINTER(Plan)]
+        L.fgh_search.argtypes = [vp, C.c_char_p, cpp, u32, u32, u32, vp, vp, vp]
+        L.fgh_search_batch.argtypes = [vp, u32, cpp, cpp, vp, vp, vp, u32, vp, vp, vp, vp]
+        _bound = True
+    return L
+
+
+def tokenize(text: str) -> list[str]:
+    """tantivy "default" analyzer (SimpleTokenizer -> RemoveLongFilter(40) -> LowerCaser)."""
+    raw = text.encode("utf-8")
+    buf = C.create_string_buffer(2 * len(raw) + 64)
+    n = _L().fgh_tokenize(raw, buf, len(buf))
+    if n < 0:
+        raise nat.FgError(nat.FG_ERR_INVALID, "tokenize buffer too small")
+    out, pos = [], 0
+    b = buf.raw
+    for _ in range(n):
+        e = b.index(b"\0", pos)
+        out.append(b[pos:e].decode("utf-8"))
+        pos = e + 1
+    return out
+
+
+@dataclass
+class ObjectRecord:
+    """src/object.rs:8-29 (fields that influence the docs index)."""
+    id: str
+    text: str
+    metadata: dict | None = None
+    facets: list[str] | None = None
+    namespace: str | None = None
+    organization: str | None = None
+    conversation_id: str | None = None
+    data_type: str | None = None
+
+    def generate_namespace_facets(self) -> list[str]:
+        """src/object.rs:81-111"""
+        out = []
+        if self.namespace is not None:
+            out.append(f"/namespace/{self.namespace}")
+            if self.organization is not None:
+                out.append(f"/namespace/{self.namespace}/organization/{self.organization}")
+            if self.conversation_id is not None:
+                out.append(f"/namespace/{self.namespace}/conversation/{self.conversation_id}")
+            if self.data_type is not None:
+                out.append(f"/namespace/{self.namespace}/data/{self.data_type}")
+        return out
+
+    def name(self) -> str | None:
+        """metadata.name when it is a string (src/db/document.rs:131-139)."""
+        if self.metadata and isinstance(self.metadata.get("name"), str):
+            return self.metadata["name"]
+        return None
+
+
+def _metadata_facets(value: Any, prefix: list[str]) -> list[list[str]]:
+    """create_metadata_facets, src/db/utils.rs:26-55"""
+    out = []
+    if isinstance(value, dict):
+        for k, v in value.items():
+            out += _metadata_facets(v, prefix + [k])
+    elif isinstance(value, list):
+        for it in value:
+            out += _metadata_facets(it, list(prefix))
+    elif isinstance(value, str) and value:
+        out.append(prefix + [value])
+    return out
+
+
+def all_facet_paths(rec: ObjectRecord) -> list[str]:
+    """get_all_facet_paths, src/db/document.rs:277-312 (including its use of only the FIRST path
+    component of a metadata facet, `facet_path.first()`)."""
+    out = []
+    if rec.facets is not None:
+        for p in rec.facets:
+            out.append(p if p.startswith("/") else "/" + p)
+    else:
+        out += rec.generate_namespace_facets()
+        if rec.metadata:
+            for k, v in rec.metadata.items():
+                for path in _metadata_facets(v, [k]):
+                    first = path[0]
+                    out.append(first if first.startswith("/") else f"/metadata/{first}")
+    return out
+
+
+@dataclass
+class FuguSearchResult:
+    """src/db/search.rs:20-27 (text/metadata/facets hydration stays with the caller's doc store)."""
+    id: str
+    score: float
+    doc: int = -1
+
+
+@dataclass
+class SearchResponse:
+    """src/server/types.rs:146-152"""
+    results: list[FuguSearchResult]
+    total: int
+    page: int
+    per_page: int
+    query: str
+
+
+class Dataset:
+    """Mirror of `Dataset` (docs index only) whose search runs on the GPU."""
+
+    def __init__(self, ctx: nat.Context | None):
+        self.ctx = ctx
+        self.h = C.c_void_p()
+        nat.check(_L().fgh_dataset_create(ctx.h if ctx is not None else None, C.byref(self.h)))
+        self._keep = None
+
+    # ---- ingest -------------------------------------------------------------------------
+    def upsert(self, records: list[ObjectRecord], commit: bool = True) -> None:
+        L = _L()
+        for r in records:
+            facets = [f.encode() for f in all_facet_paths(r)]
+            arr = (C.c_char_p * max(len(facets), 1))(*facets)
+            nm = r.name()
+            nat.check(L.fgh_dataset_upsert(self.h, r.id.encode(), r.text.encode(), None if nm is None else nm.encode(),
+                                           arr, len(facets)))
+        if commit:
+            self.commit()
+
+    def delete(self, id_: str, commit: bool = True) -> None:
+        nat.check(_L().fgh_dataset_delete(self.h, id_.encode()))
+        if commit:
+            self.commit()
+
+    def commit(self) -> None:
+        nat.check(_L().fgh_dataset_commit(self.h))
+
+    def adopt(self, desc: nat.HostIndexDesc, terms: list[list[str] | None]) -> None:
+        """Adopt a pre-built CSR (synthetic corpora) + per-field term dictionaries."""
+        n = len(terms)
+        blobs = [None if t is None else b"".join(x.encode() + b"\0" for x in t) for t in terms]
+        bufs = [None if b is None else C.create_string_buffer(b, len(b)) for b in blobs]
+        arr = (C.c_char_p * n)()
+        for i, bf in enumerate(bufs):
+            arr[i] = None if bf is None else C.cast(bf, C.c_char_p)
+        sizes = (C.c_uint64 * n)(*[0 if b is None else len(b) for b in blobs])
+        nat.check(_L().fgh_dataset_adopt(self.h, C.byref(desc.desc), arr, sizes))
+        self._keep = (desc, bufs)
+
+    # ---- introspection ------------------------------------------------------------------
+    @property
+    def num_docs(self) -> int:
+        return int(_L().fgh_dataset_num_docs(self.h))
+
+    def doc_id(self, doc: int) -> str:
+        buf = C.create_string_buffer(300)
+        n = _L().fgh_dataset_doc_id(self.h, doc, buf, 300)
+        return buf.value.decode() if n >= 0 else "unknown"
+
+    def term_ord(self, field_: int, token: str) -> int:
+        return int(_L().fgh_dataset_term_ord(self.h, field_, token.encode()))
+
+    def plan(self, query: str, filters: list[str] | None = None, page: int = 0, per_page: int = 20) -> Plan:
+        filters = filters or []
+        arr = (C.c_char_p * max(len(filters), 1))(*[f.encode() for f in filters])
+        p = Plan()
+        nat.check(_L().fgh_plan(self.h, query.encode(), arr, len(filters), page, per_page, C.byref(p)))
+        return p
+
+    # ---- search -------------------------------------------------------------------------
+    def search(self, query: str, filters: list[str] | None = None, page: int = 0, per_page: int = 20) -> list[FuguSearchResult]:
+        """Dataset::search(query, filters, page, per_page) -> the requested page of hits."""
+        filters = filters or []
+        arr = (C.c_char_p * max(len(filters), 1))(*[f.encode() for f in filters])
+        hits = np.zeros(max(per_page, 1), nat.HIT_DT)
+        n = C.c_uint32()
+        cnt = C.c_uint32()
+        nat.check(_L().fgh_search(self.h, query.encode(), arr, len(filters), page, per_page, hits.ctypes.data,
+                                  C.byref(n), C.byref(cnt)))
+        return [FuguSearchResult(self.doc_id(int(h["doc"])), float(h["score"]), int(h["doc"])) for h in hits[:n.value]]
+
+    def search_batch(self, queries: list[str], filters: list[list[str]] | None = None, page: int = 0, per_page: int = 20):
+        """Batched form: returns (hits[n, per_page], n_hits[n], match_count[n], status[n])."""
+        n = len(queries)
+        qarr = (C.c_char_p * max(n, 1))(*[q.encode() for q in queries])
+        farr = foffs = None
+        if filters is not None:
+            flat = [f.encode() for fl in filters for f in fl]
+            farr = (C.c_char_p * max(len(flat), 1))(*flat)
+            foffs = np.zeros(n + 1, np.uint32)
+            foffs[1:] = np.cumsum([len(fl) for fl in filters])
+        pages = np.full(n, page, np.uint32)
+        pps = np.full(n, per_page, np.uint32)
+        hits = np.zeros((n, per_page), nat.HIT_DT)
+        nh = np.zeros(n, np.uint32)
+        cnt = np.zeros(n, np.uint32)
+        status = np.zeros(n, np.int32)
+        nat.check(_L().fgh_search_batch(self.h, n, qarr, farr, None if foffs is None else foffs.ctypes.data,
+                                        pages.ctypes.data, pps.ctypes.data, per_page, hits.ctypes.data, nh.ctypes.data,
+                                        cnt.ctypes.data, status.ctypes.data))
+        return hits, nh, cnt, status
+
+    def close(self) -> None:
+        if self.h:
+            _L().fgh_dataset_destroy(self.h)
+            self.h = C.c_void_p()
+
+
+def perform_search(datasets: dict[str, Dataset], namespace: str, query: str, filters: list[str], page: int,
+                   per_page: int) -> SearchResponse:
+    """src/server/handlers/search.rs:350-402: dataset lookup, per_page clamp to 20 when 0 or > 100."""
+    ds = datasets.get(namespace)
+    if ds is None:
+        raise KeyError(f"Namespace '{namespace}' not found")
+    if per_page == 0 or per_page > 100:
+        per_page = 20
+    results = ds.search(query, filters, page, per_page)
+    return SearchResponse(results=results, total=len(results), page=page, per_page=per_page, query=query)

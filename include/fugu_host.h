@@ -1,0 +1,107 @@
+/* fugu_host.h — host side of the query path, above the device ABI (include/fugu_gpu.h).
+ *
+ * The reference's host code is Rust; no Rust toolchain exists in the build image, so the host side
+ * is C++ behind this C ABI, mirroring the reference interface for the path name by name:
+ *
+ *   fgh_dataset_*        <->  Dataset / NamedIndex "docs" index   (src/db/core.rs:39-188,205-497)
+ *   fgh_dataset_upsert   <->  DocumentOperations::upsert          (src/db/document.rs:23-67:
+ *                              delete_term(id) + add_document; the docs schema src/db/schemas.rs:7-31
+ *                              decides what is tokenised: `text`, `name` TEXT, `facet` Facet)
+ *   fgh_dataset_commit   <->  writer.commit() + reader reload     (src/db/document.rs:65; core.rs:86)
+ *   fgh_search           <->  Dataset::search(query, filters, page, per_page)   (src/db/search.rs:74-218)
+ *   fgh_plan             <->  the planning half of it: QueryParser::for_index(.., [text, name]) +
+ *                              parse_query + escape fallback (:108-127,603-610), parse_filters (:292-324),
+ *                              build_facet_query (:221-289), Must-join (:132-151), limit (:154-160)
+ *   fgh_tokenize         <->  tantivy's "default" analyzer selected by TEXT
+ *                              (SimpleTokenizer -> RemoveLongFilter(40) -> LowerCaser)
+ *
+ * Hit hydration (searcher.doc + convert_doc_to_search_result, src/db/search.rs:172-207,534-590) is
+ * reduced to the doc -> id side table; stored fields stay with the caller.
+ *
+ * Same error convention as fugu_gpu.h (int32 status, fg_last_error()).
+ */
+#ifndef FUGU_HOST_H
+#define FUGU_HOST_H
+
+#include "fugu_gpu.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* field ids of the docs index as this library lays them out */
+#define FGH_FIELD_TEXT 0u
+#define FGH_FIELD_NAME 1u
+#define FGH_FIELD_FACET 2u
+
+typedef struct fgh_dataset fgh_dataset;
+
+/* ctx may be NULL: the dataset then only plans (fgh_plan / fgh_tokenize work, searches fail). */
+int32_t fgh_dataset_create(fg_ctx* ctx, fgh_dataset** out);
+void fgh_dataset_destroy(fgh_dataset* ds);
+
+/* Upsert one record. `name` may be NULL (no metadata.name). `facets` are facet path strings
+ * ("/namespace/ns01/organization/org3"); every ancestor path becomes its own term, as tantivy
+ * indexes a Facet. If `id` already exists the old document is deleted (alive bit cleared; statistics
+ * keep counting it until a merge, as tantivy's do) and a new document is appended.
+ * Validation limits of ObjectRecord::validate (src/object.rs:31-78) are enforced. */
+int32_t fgh_dataset_upsert(fgh_dataset* ds, const char* id, const char* text, const char* name,
+                           const char* const* facets, uint32_t n_facets);
+int32_t fgh_dataset_delete(fgh_dataset* ds, const char* id);
+/* Build the CSR of the pending state and upload a new device snapshot (swaps the fg_index). */
+int32_t fgh_dataset_commit(fgh_dataset* ds);
+
+/* Alternative to upsert+commit for large pre-built corpora: adopt a flat CSR (uploaded as is) plus
+ * the term dictionaries needed for planning. `terms[f]` = n_terms NUL-terminated strings packed
+ * back to back, in term-ordinal order (NULL for a field nobody queries by string). */
+int32_t fgh_dataset_adopt(fgh_dataset* ds, const fg_index_desc* desc, const char* const* terms,
+                          const uint64_t* terms_bytes);
+
+uint32_t fgh_dataset_num_docs(const fgh_dataset* ds);
+fg_index* fgh_dataset_index(fgh_dataset* ds); /* current snapshot (NULL before the first commit) */
+/* external id of a doc (global doc id as reported in fg_hit.doc); returns length or -1 */
+int32_t fgh_dataset_doc_id(const fgh_dataset* ds, uint32_t doc, char* buf, uint32_t cap);
+/* term ordinal of a token in a field, FG_TERM_MISSING when absent */
+uint32_t fgh_dataset_term_ord(const fgh_dataset* ds, uint32_t field, const char* token);
+
+/* tokens of `text` under the default analyzer, written NUL-separated into buf; returns the token
+ * count, or -1 when buf is too small */
+int32_t fgh_tokenize(const char* text, char* buf, uint32_t cap);
+
+/* ---- planning ---- */
+#define FGH_MAX_PLAN_CLAUSES 16
+#define FGH_MAX_PLAN_LEAVES 64
+typedef struct {
+    uint32_t k;          /* page*per_page + per_page */
+    uint32_t offset;     /* page*per_page */
+    uint32_t n_clauses;
+    uint32_t n_leaves;
+    uint32_t is_all;     /* the whole query is AllQuery (empty query, no usable filter) */
+    uint32_t used_fallback; /* parse_query failed and the escaped retry was used (src/db/search.rs:120-125) */
+    fg_clause clauses[FGH_MAX_PLAN_CLAUSES];
+    fg_leaf leaves[FGH_MAX_PLAN_LEAVES];
+} fgh_plan_t;
+/* FG_ERR_INVALID = parse error even after the fallback (the reference returns Err -> HTTP 500);
+ * FG_ERR_UNSUPPORTED = valid tantivy query the device path does not evaluate (phrase, range,
+ * fuzzy, true OR-of-AND trees). */
+int32_t fgh_plan(const fgh_dataset* ds, const char* query, const char* const* filters,
+                 uint32_t n_filters, uint32_t page, uint32_t per_page, fgh_plan_t* out);
+
+/* ---- search: Dataset::search for one request / a batch of requests ----
+ * Writes the requested page (after skip(offset).take(per_page), src/db/search.rs:210-211) to
+ * out_hits[q*per_page_stride ..], the number of hits in the page to out_n[q] and, when not NULL,
+ * the number of matching docs to out_match_count[q]. status[q] (may be NULL) receives a per-query
+ * FG_* code so that one bad query does not fail a batch. */
+int32_t fgh_search(fgh_dataset* ds, const char* query, const char* const* filters, uint32_t n_filters,
+                   uint32_t page, uint32_t per_page, fg_hit* out_hits, uint32_t* out_n,
+                   uint32_t* out_match_count);
+int32_t fgh_search_batch(fgh_dataset* ds, uint32_t n, const char* const* queries,
+                         const char* const* filters, const uint32_t* filter_offsets /* [n+1] or NULL */,
+                         const uint32_t* pages /* or NULL = 0 */, const uint32_t* per_pages /* or NULL = 20 */,
+                         uint32_t per_page_stride, fg_hit* out_hits, uint32_t* out_n,
+                         uint32_t* out_match_count, int32_t* status);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FUGU_HOST_H */

@@ -50,3 +50,189 @@ def test_config3_small_or_top100(ctx):
     batch = plan_queries(synth.gen_queries(cfg), vocab=cfg.vocab, n_text_fields=1)
     check_batch_against_oracle(index, desc, batch)
     index.close()
+
+
+def test_golden_cases_through_dataset_search(ctx):
+    """The reference-facing path: ObjectRecords -> Dataset.upsert/delete/commit -> Dataset.search
+    (query string, filters, page, per_page) on the GPU == committed golden hits (ids + scores)."""
+    from tests.util import check_topk, golden_dataset
+
+    g, ds, ix = golden_dataset(ctx)
+    ds.commit()
+    n_ok = 0
+    for c in g["cases"]:
+        try:
+            res = ds.search(c["query"], c["filters"], c["page"], c["per_page"])
+        except nat.FgError as e:
+            assert c.get("error") == {nat.FG_ERR_INVALID: "invalid", nat.FG_ERR_UNSUPPORTED: "unsupported"}[e.code], c
+            continue
+        assert "error" not in c, c
+        got = np.zeros(len(res), nat.HIT_DT)
+        got["doc"] = [r.doc for r in res]
+        got["score"] = [r.score for r in res]
+        want = np.zeros(len(c["hits"]), nat.HIT_DT)
+        want["doc"] = [ix.ids.index(i) if i not in ix.by_id else ix.by_id[i] for i, _ in c["hits"]]
+        want["score"] = [s for _, s in c["hits"]]
+        # a page is a slice of the top-(page+1)*per_page list: ties may be cut at either end
+        assert len(got) == len(want), c
+        for a, b in zip(got["score"], want["score"]):
+            assert abs(a - b) <= 1e-5 * max(abs(a), abs(b), 1e-30), c
+        if c["page"] == 0:
+            check_topk(got, want, k=c["per_page"], ctx=repr(c["query"]))
+            assert [r.id for r in res] == [ix.ids[d] for d in got["doc"]]
+        n_ok += 1
+    assert n_ok >= 50
+    # batched form agrees with the one-at-a-time form
+    qs = [c["query"] for c in g["cases"] if "error" not in c and c["page"] == 0]
+    fl = [c["filters"] for c in g["cases"] if "error" not in c and c["page"] == 0]
+    hits, nh, cnt, status = ds.search_batch(qs, fl, 0, 10)
+    assert (status == 0).all()
+    want_cnt = [c["match_count"] for c in g["cases"] if "error" not in c and c["page"] == 0]
+    assert cnt.tolist() == want_cnt
+    ds.close()
+
+
+def test_upsert_delete_snapshot_semantics(ctx):
+    """Upsert of an existing id deletes the old doc (alive bit) but statistics keep counting it
+    (A.4), as the python twin models; a new commit swaps the snapshot."""
+    from fugu_b200.dataset import Dataset, ObjectRecord
+    from oracle import oracle_py as op
+
+    ds, ix = Dataset(ctx), op.PyIndex()
+    recs = [("a", "one two three"), ("b", "two three four four"), ("c", "five six"), ("a", "two two two seven")]
+    for i, t in recs:
+        ds.upsert([ObjectRecord(id=i, text=t)], commit=False)
+        ix.upsert(i, t)
+    ds.commit()
+    for q in ["two", "three", "seven", "one", ""]:
+        want, n = op.search(ix, q, [], 0, 10)
+        got = ds.search(q, [], 0, 10)
+        assert [r.id for r in got] == [ix.ids[d] for d, _ in want], q
+        for r, (_, s) in zip(got, want):
+            assert abs(r.score - s) <= 1e-5 * max(abs(s), 1e-30)
+    ds.delete("b")
+    ix.delete("b")
+    want, n = op.search(ix, "three", [], 0, 10)
+    assert [r.id for r in ds.search("three")] == [ix.ids[d] for d, _ in want] == []
+    ds.close()
+
+
+def test_sharded_search_and_device_merge(ctx):
+    """Doc-id-range shards with global statistics + fg_merge_topk_device == single index (the
+    multi-GPU data path of SURVEY.md 8(e), emulated on one device as two shard snapshots)."""
+    import torch
+    from oracle import orc
+    from tests.util import check_topk, gpu_search_device
+
+    cfg = synth.Config(cfg=2, n_docs=40_000, vocab=8_000, n_queries=200, k=10, name_pct=10)
+    corpus = synth.Corpus.for_config(cfg)
+    whole = nat.HostIndexDesc(cfg.n_docs, synth.build_fields(corpus, 0, cfg.n_docs))
+    batch = plan_queries(synth.gen_queries(cfg), vocab=cfg.vocab, n_text_fields=2)
+    o_hits, o_n, o_c = orc.search(whole, batch, threads=4)
+    R = 3
+    bounds = [cfg.n_docs * r // R for r in range(R + 1)]
+    shard_fields = [synth.build_fields(corpus, bounds[r], bounds[r + 1]) for r in range(R)]
+    for f in range(2):
+        gdf = sum(np.diff(sf[f]["term_offsets"]).astype(np.int64) for sf in shard_fields).astype(np.uint32)
+        tot = sum(sf[f]["total_num_tokens"] for sf in shard_fields)
+        for sf in shard_fields:
+            sf[f]["global_doc_freq"] = gdf
+            sf[f]["total_num_tokens"] = tot
+    nq, k = batch.n_queries, batch.kmax
+    g_hits = np.zeros((R, nq, k), nat.HIT_DT)
+    g_n = np.zeros((R, nq), np.uint32)
+    counts = np.zeros(nq, np.int64)
+    for r in range(R):
+        desc = nat.HostIndexDesc(bounds[r + 1] - bounds[r], shard_fields[r], doc_id_base=bounds[r], global_n_docs=cfg.n_docs)
+        index = nat.Index(ctx, desc)
+        h, n, c, _, _ = gpu_search_device(index, batch)
+        g_hits[r], g_n[r] = h, n
+        counts += c
+        index.close()
+    dev = torch.device("cuda:0")
+    d_g = torch.from_numpy(g_hits.view(np.int32).reshape(R, nq, k, 2).copy()).to(dev)
+    d_gn = torch.from_numpy(g_n.view(np.int32)).to(dev)
+    d_out = torch.zeros((nq, k, 2), dtype=torch.int32, device=dev)
+    d_on = torch.zeros(nq, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    nat.merge_topk_device(ctx, d_g.data_ptr(), d_gn.data_ptr(), R, nq, k, k, d_out.data_ptr(), d_on.data_ptr())
+    ctx.synchronize()
+    raw = d_out.cpu().numpy().view(np.uint32)
+    got = np.zeros((nq, k), nat.HIT_DT)
+    got["score"] = raw[..., 0].view(np.float32)
+    got["doc"] = raw[..., 1]
+    on = d_on.cpu().numpy()
+    assert counts.tolist() == o_c.astype(np.int64).tolist()
+    assert on.tolist() == o_n.tolist()
+    for q in range(nq):
+        check_topk(got[q, :on[q]], o_hits[q, :o_n[q]], k=k, ctx=f"query {q}")
+
+
+def test_accounting_matches_oracle_definition(ctx):
+    """fg_batch_stats (exact accounting mode) == the oracle's independent algorithmic-byte count."""
+    from oracle import orc
+    from tests.util import gpu_search_device
+
+    cfg = synth.Config(cfg=2, n_docs=60_000, vocab=10_000, n_queries=300, k=10, name_pct=10)
+    corpus, desc, index = _setup(ctx, cfg)
+    batch = plan_queries(synth.gen_queries(cfg), vocab=cfg.vocab, n_text_fields=2)
+    by, sc = orc.algorithmic_bytes(desc, batch, threads=4)
+    *_, st = gpu_search_device(index, batch, flags=nat.FG_EXEC_EXACT_ACCOUNTING)
+    assert st.scored_postings == int(sc.sum())
+    # blocks straddling work-item boundaries are only counted by the item that owns their start;
+    # filter-clause blocks first needed in a later round count as re-decodes -> a lower bound within 3%
+    assert st.bytes_blocks <= int(by.sum())
+    assert st.bytes_blocks >= 0.97 * int(by.sum()), (st.bytes_blocks, int(by.sum()))
+    index.close()
+
+
+def test_edge_cases(ctx):
+    """Empty / ragged inputs: empty batch, empty posting lists, tail blocks (n % 128 != 0), k larger
+    than the match count, missing terms, a term present in every doc, boosts, MustNot."""
+    from oracle import orc
+    from tests.util import check_batch_against_oracle
+
+    rng = np.random.default_rng(11)
+    n_docs = 5000
+    lists = [np.arange(n_docs, dtype=np.uint32),                                   # every doc (gaps of 0 bits)
+             np.sort(rng.choice(n_docs, 1, replace=False)).astype(np.uint32),     # single posting
+             np.sort(rng.choice(n_docs, 127, replace=False)).astype(np.uint32),   # just under one block
+             np.sort(rng.choice(n_docs, 128, replace=False)).astype(np.uint32),   # exactly one block
+             np.sort(rng.choice(n_docs, 129, replace=False)).astype(np.uint32),   # one block + 1
+             np.zeros(0, np.uint32),                                               # empty list
+             np.array([0, n_docs - 1], np.uint32),                                 # first and last doc
+             np.sort(rng.choice(n_docs, 2500, replace=False)).astype(np.uint32)]
+    offs = np.concatenate([[0], np.cumsum([len(x) for x in lists])]).astype(np.uint64)
+    docs = np.concatenate(lists)
+    tfs = rng.integers(1, 300, len(docs)).astype(np.uint32)
+    fn = rng.integers(0, 120, n_docs).astype(np.uint8)
+    desc = nat.HostIndexDesc(n_docs, [{"term_offsets": offs, "doc_ids": docs, "term_freqs": tfs, "fieldnorm_ids": fn,
+                                       "total_num_tokens": int(n_docs * 50)}])
+    index = nat.Index(ctx, desc)
+    S, M, N = nat.FG_OCCUR_SHOULD, nat.FG_OCCUR_MUST, nat.FG_OCCUR_MUST_NOT
+    T = lambda t, b=1.0: (0, t, b)
+    qs = [{"k": 10, "clauses": [(S, [T(t)])]} for t in range(8)]
+    qs += [{"k": 128, "clauses": [(S, [T(4)])]}, {"k": 100, "clauses": [(S, [T(1)]), (S, [T(6)])]},
+           {"k": 10, "clauses": [(M, [T(0)]), (M, [T(7)]), (M, [T(4)])]},
+           {"k": 10, "clauses": [(M, [T(0)]), (N, [T(7)])]},
+           {"k": 10, "clauses": [(S, [T(2), T(3), T(4)]), (N, [T(0)])]},
+           {"k": 10, "clauses": [(M, [T(5)]), (S, [T(0)])]},
+           {"k": 10, "clauses": [(S, [T(nat.FG_TERM_MISSING)])]},
+           {"k": 10, "clauses": [(M, [T(7, 2.0)]), (S, [T(3, 0.5)]), (S, [T(6, 3.0)])]},
+           {"k": 10, "clauses": []},
+           {"k": 5, "clauses": [(M, [T(nat.FG_TERM_ALL)])]},
+           {"k": 10, "clauses": [(M, [T(nat.FG_TERM_ALL)]), (M, [T(3)])]}]
+    batch = nat.HostBatch(qs[:-2] + qs[-1:])
+    check_batch_against_oracle(index, desc, batch)
+    # pure AllQuery: first k alive docs, score 1.0 (the oracle leaves this to the host layer)
+    h, n, c = index.search(nat.HostBatch([qs[-2]]))
+    assert n[0] == 5 and c[0] == n_docs and h[0]["doc"].tolist() == [0, 1, 2, 3, 4] and (h[0]["score"] == 1.0).all()
+    # empty batch
+    h, n, c = index.search(nat.HostBatch([]))
+    assert len(n) == 0
+    # k == 0 is an error (TopDocs::with_limit asserts), k > 128 unsupported for now
+    for k, code in ((0, nat.FG_ERR_INVALID), (129, nat.FG_ERR_UNSUPPORTED)):
+        with pytest.raises(nat.FgError) as e:
+            index.search(nat.HostBatch([{"k": k, "clauses": [(S, [T(0)])]}]))
+        assert e.value.code == code
+    index.close()

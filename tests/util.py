@@ -99,3 +99,69 @@ def check_batch_against_oracle(index: nat.Index, desc: nat.HostIndexDesc, batch:
         n = int(o_n[qi])
         check_topk(g_hits[qi, :n], o_hits[qi, :n], int(batch.q["k"][qi]), ctx=f"query {qi}")
     return {"stats": st, "o_counts": o_c}
+
+
+def batch_from_plans(plans) -> nat.HostBatch:
+    """fgh_plan_t list -> flat fg_query_batch (what fgh_search_batch assembles internally)."""
+    qs = []
+    for p in plans:
+        d = p.as_dict()
+        qs.append({"k": d["k"], "clauses": d["clauses"]})
+    return nat.HostBatch(qs)
+
+
+def golden(name: str):
+    import json
+    import os
+
+    return json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name)))
+
+
+def golden_dataset(ctx):
+    """The Dataset (C++ host layer) loaded with the golden corpus, plus the python-twin index."""
+    from fugu_b200.dataset import Dataset, ObjectRecord
+    from oracle import oracle_py as op
+
+    g = golden("search_cases.json")
+    ds = Dataset(ctx)
+    ix = op.PyIndex()
+    recs = []
+    for d in g["docs"]:
+        recs.append(ObjectRecord(id=d["id"], text=d["text"], metadata={"name": d["name"]} if d["name"] else None, facets=d["facets"]))
+        ix.upsert(d["id"], d["text"], d["name"], d["facets"])
+    ds.upsert(recs, commit=False)
+    for i in g["deletes"]:
+        ds.delete(i, commit=False)
+        ix.delete(i)
+    return g, ds, ix
+
+
+def host_desc_from_pyindex(ix) -> nat.HostIndexDesc:
+    """CSR descriptor (text, name, facet) of a python-twin index, term ordinals = sorted terms.
+    Returns (desc, [term lists])."""
+    fields, terms = [], []
+    for f in range(3):
+        ts = sorted(ix.post[f])
+        offs, docs, tfs = [0], [], []
+        for t in ts:
+            for d in sorted(ix.post[f][t]):
+                docs.append(d)
+                tfs.append(ix.post[f][t][d])
+            offs.append(len(docs))
+        from oracle import oracle_py as op
+
+        fd = {"term_offsets": np.array(offs, np.uint64), "doc_ids": np.array(docs, np.uint32),
+              "total_num_tokens": ix.total_tokens[f]}
+        if f != 2:
+            fd["term_freqs"] = np.array(tfs, np.uint32)
+            fd["fieldnorm_ids"] = np.array([op.fieldnorm_to_id(n) for n in ix.doc_len[f]], np.uint8)
+        else:
+            fd["term_freqs"] = None
+            fd["fieldnorm_ids"] = None
+        fields.append(fd)
+        terms.append(ts)
+    alive = np.zeros((ix.n_docs + 31) // 32, np.uint32)
+    for d, a in enumerate(ix.alive):
+        if a:
+            alive[d >> 5] |= np.uint32(1 << (d & 31))
+    return nat.HostIndexDesc(ix.n_docs, fields, alive_bitset=alive), terms
