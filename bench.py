@@ -135,6 +135,17 @@ def build_workload(args, rank: int, world: int):
     return cfg, corpus, fields, queries, d0, d1
 
 
+def term_lists(corpus, cfg, n_fields):
+    """Term dictionaries of the synthetic corpus (term ordinal r-1 <-> "w<r>"; facet paths)."""
+    words = [f"w{i + 1}" for i in range(cfg.vocab)]
+    terms = [words]
+    if n_fields >= 2:
+        terms.append(words if cfg.name_pct > 0 else [])
+    if n_fields >= 3:
+        terms.append([corpus.facet_path(i) for i in range(corpus.facet_vocab())])
+    return terms
+
+
 def peak_hbm():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -156,16 +167,20 @@ def run_reference(args):
     from oracle import orc
 
     cfg, corpus, fields, queries, d0, d1 = build_workload(args, 0, 1)
+    from fugu_b200.dataset import Dataset, QuerySet
+
     desc = nat.HostIndexDesc(cfg.n_docs, fields)
     n_fields = len(fields)
     cores = host_cores()
+    pds = Dataset(None)  # planning only (no device): the same C++ planner both arms use
+    pds.adopt(desc, term_lists(corpus, cfg, n_fields))
     # bounded sample: each step = the whole batch when it is small enough, else a prefix
     nq = min(len(queries), 5000)
-    sample = queries[:nq]
+    qset = QuerySet([q["query"] for q in queries[:nq]], [q["filters"] for q in queries[:nq]], 0, cfg.k)
     times = []
     for it in range(args.warmup + args.steps):
         t0 = time.perf_counter()
-        batch = synth.lower_queries(sample, vocab=cfg.vocab, n_text_fields=n_fields)  # planning inside, as on the GPU e2e arm
+        batch, _ = pds.plan_batch(qset)  # query strings -> plan, inside the timed region as on the GPU e2e arm
         orc.search(desc, batch, threads=cores)
         dt = time.perf_counter() - t0
         if it >= args.warmup:
@@ -232,12 +247,18 @@ def main():
     stream = torch.cuda.Stream(dev)
     torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
+    from fugu_b200.dataset import Dataset, QuerySet
+
+    n_fields = len(fields)
     t0 = time.perf_counter()
-    index = nat.Index(ctx, desc)
+    ds = Dataset(ctx)
+    ds.adopt(desc, term_lists(corpus, cfg, n_fields))  # fg_index_upload + term dictionaries for the planner
+    index = ds.index()
     upload_s = time.perf_counter() - t0
     info = index.info()
-    n_fields = len(fields)
-    batch = synth.lower_queries(queries, vocab=cfg.vocab, n_text_fields=n_fields)
+    qset = QuerySet([q["query"] for q in queries], [q["filters"] for q in queries], 0, cfg.k)
+    batch, pstatus = ds.plan_batch(qset)
+    assert (pstatus == 0).all(), "planner rejected a benchmark query"
     nq, k = batch.n_queries, batch.kmax
     pb = index.prepare(batch)
 
@@ -308,8 +329,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        hb = synth.lower_queries(queries, vocab=cfg.vocab, n_text_fields=n_fields)  # query strings -> plan (host)
-        h_hits, h_n, h_c = index.search(hb)
+        h_hits, h_n, h_c, _ = ds.search_batch(qset)  # fgh_search_batch: strings -> plan -> H2D -> kernels -> D2H
         if world > 1:
             dist.all_gather_into_tensor(g_hits, torch.from_numpy(h_hits.view(np.int32).reshape(nq, k, 2)).to(dev))
             dist.all_gather_into_tensor(g_n, torch.from_numpy(h_n.view(np.int32)).to(dev))
@@ -323,7 +343,6 @@ def main():
         t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    plan_bytes = batch.q.nbytes + batch.c.nbytes + batch.l.nbytes
     lowered_bytes = nq * 48 + len(batch.l) * 48 + st.n_work_items * 32
     out_bytes = nq * k * 8 + nq * 8
 
@@ -349,7 +368,7 @@ def main():
                      "note": "index (%.0f MB) fits the 126 MB L2; L2 is flushed before each timed step" % (info.device_bytes / 1e6)},
         "e2e": {"value": nq / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": int(lowered_bytes),
                 "d2h_bytes_per_step": int(out_bytes), "ms_per_step": e2e_s * 1e3,
-                "what": "query strings -> host plan lowering -> fg_search_batch (host buffers; H2D plan, kernels, D2H hits)"},
+                "what": "fgh_search_batch: query strings (host) -> C++ planner -> plan lowering -> H2D plan -> kernels -> D2H hits (host)"},
         "gpu_launches": int(st_timed.n_launches + (1 if world > 1 else 0)) * args.steps,
         "clocks": clocks,
         "index": {"postings": int(info.n_postings), "blocks": int(info.n_blocks), "packed_bytes": int(info.packed_bytes),
@@ -361,7 +380,7 @@ def main():
         odesc = nat.HostIndexDesc(n_local, fields, doc_id_base=d0, global_n_docs=cfg.n_docs) if world > 1 else desc
         cores = host_cores()
         ns = min(nq, 5000)
-        sub = synth.lower_queries(queries[:ns], vocab=cfg.vocab, n_text_fields=n_fields)
+        sub, _ = ds.plan_batch(QuerySet([q["query"] for q in queries[:ns]], [q["filters"] for q in queries[:ns]], 0, cfg.k))
         best = None
         t_end = time.perf_counter() + 20
         for _ in range(3):
@@ -372,7 +391,8 @@ def main():
             if time.perf_counter() > t_end:
                 break
         t0 = time.perf_counter()
-        orc.search(odesc, synth.lower_queries(queries[:max(1, ns // 10)], vocab=cfg.vocab, n_text_fields=n_fields), threads=1)
+        sub1, _ = ds.plan_batch(QuerySet([q["query"] for q in queries[:max(1, ns // 10)]], None, 0, cfg.k))
+        orc.search(odesc, sub1, threads=1)
         dt1 = time.perf_counter() - t0
         line["cpu_baseline"] = {"value": ns / best, "unit": "queries/s", "cores": cores, "kind": "port",
                                 "single_thread_qps": max(1, ns // 10) / dt1,

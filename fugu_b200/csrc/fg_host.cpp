@@ -782,25 +782,33 @@ extern "C" int32_t fgh_plan(const fgh_dataset* ds, const char* query, const char
     return plan_impl(ds, query, filters, n_filters, page, per_page, out);
 }
 
-extern "C" int32_t fgh_search_batch(fgh_dataset* ds, uint32_t n, const char* const* queries,
-                                    const char* const* filters, const uint32_t* filter_offsets,
-                                    const uint32_t* pages, const uint32_t* per_pages, uint32_t stride,
-                                    fg_hit* out_hits, uint32_t* out_n, uint32_t* out_match_count,
-                                    int32_t* status) {
-    if (!ds || (n && (!queries || !out_hits || !out_n))) return host_fail(FG_ERR_INVALID, "fgh_search_batch: NULL argument");
-    if (!ds->index) return host_fail(ds->ctx ? FG_ERR_INVALID : FG_ERR_NO_DEVICE, "dataset has no device snapshot (commit first)");
-    if (n == 0) return FG_OK;
+namespace {
+// plan n requests (multi-threaded) into one flat batch; failed plans become empty queries
+struct PlannedBatch {
+    std::vector<fg_query> q;
+    std::vector<fg_clause> c;
+    std::vector<fg_leaf> l;
+    std::vector<uint32_t> offset;
+    std::vector<int32_t> rc;
+    uint32_t kmax = 1;
+    int32_t first_err = FG_OK;
+    std::string first_msg;
+};
+void plan_batch(const fgh_dataset* ds, uint32_t n, const char* const* queries, const char* const* filters,
+                const uint32_t* filter_offsets, const uint32_t* pages, const uint32_t* per_pages, PlannedBatch& pb) {
     std::vector<fgh_plan_t> plans(n);
-    std::vector<int32_t> rc(n, FG_OK);
+    pb.rc.assign(n, FG_OK);
     std::vector<std::string> errs(n);
     unsigned hw = std::thread::hardware_concurrency();
+    const char* e = getenv("FG_HOST_THREADS");
+    if (e) hw = (unsigned)atoi(e);
     int T = (int)std::max(1u, std::min<unsigned>(hw ? hw : 4, std::min<unsigned>(32, n / 64 + 1)));
     auto work = [&](int t) {
         for (uint32_t i = (uint32_t)((uint64_t)n * t / T); i < (uint32_t)((uint64_t)n * (t + 1) / T); i++) {
             const uint32_t f0 = filter_offsets ? filter_offsets[i] : 0, f1 = filter_offsets ? filter_offsets[i + 1] : 0;
-            rc[i] = plan_impl(ds, queries[i], filters ? filters + f0 : nullptr, f1 - f0, pages ? pages[i] : 0,
-                              per_pages ? per_pages[i] : 20, &plans[i]);
-            if (rc[i]) errs[i] = fg_last_error();
+            pb.rc[i] = plan_impl(ds, queries[i], filters ? filters + f0 : nullptr, f1 - f0, pages ? pages[i] : 0,
+                                 per_pages ? per_pages[i] : 20, &plans[i]);
+            if (pb.rc[i]) errs[i] = fg_last_error();
         }
     };
     if (T == 1) work(0);
@@ -809,48 +817,80 @@ extern "C" int32_t fgh_search_batch(fgh_dataset* ds, uint32_t n, const char* con
         for (int t = 0; t < T; t++) th.emplace_back(work, t);
         for (auto& x : th) x.join();
     }
-    // one flat batch; queries that failed to plan become empty plans (match nothing)
-    std::vector<fg_query> fq(n);
-    std::vector<fg_clause> fc;
-    std::vector<fg_leaf> fl;
-    uint32_t kmax = 1;
-    int32_t first_err = FG_OK;
+    pb.q.resize(n);
+    pb.offset.assign(n, 0);
     for (uint32_t i = 0; i < n; i++) {
-        if (status) status[i] = rc[i];
-        if (rc[i] && !first_err) { first_err = rc[i]; host_fail(rc[i], "%s", errs[i].c_str()); }
-        fq[i].k = rc[i] ? 1 : plans[i].k;
-        fq[i].clause_begin = (uint32_t)fc.size();
-        fq[i].n_clauses = rc[i] ? 0 : plans[i].n_clauses;
-        if (!rc[i]) {
+        const bool bad = pb.rc[i] != FG_OK;
+        if (bad && !pb.first_err) { pb.first_err = pb.rc[i]; pb.first_msg = errs[i]; }
+        pb.q[i].k = bad ? 1 : plans[i].k;
+        pb.q[i].clause_begin = (uint32_t)pb.c.size();
+        pb.q[i].n_clauses = bad ? 0 : plans[i].n_clauses;
+        if (!bad) {
+            pb.offset[i] = plans[i].offset;
             for (uint32_t c = 0; c < plans[i].n_clauses; c++) {
                 fg_clause cl = plans[i].clauses[c];
-                cl.leaf_begin += (uint32_t)fl.size();
-                fc.push_back(cl);
+                cl.leaf_begin += (uint32_t)pb.l.size();
+                pb.c.push_back(cl);
             }
-            fl.insert(fl.end(), plans[i].leaves, plans[i].leaves + plans[i].n_leaves);
+            pb.l.insert(pb.l.end(), plans[i].leaves, plans[i].leaves + plans[i].n_leaves);
         }
-        kmax = std::max(kmax, fq[i].k);
+        pb.kmax = std::max(pb.kmax, pb.q[i].k);
     }
-    if (first_err && !status) return first_err;  // single-status callers see the first failure
+}
+}  // namespace
+
+extern "C" int32_t fgh_plan_batch(const fgh_dataset* ds, uint32_t n, const char* const* queries,
+                                  const char* const* filters, const uint32_t* filter_offsets,
+                                  const uint32_t* pages, const uint32_t* per_pages, fg_query* out_queries,
+                                  fg_clause* out_clauses, uint32_t cap_clauses, fg_leaf* out_leaves,
+                                  uint32_t cap_leaves, uint32_t* n_clauses, uint32_t* n_leaves, int32_t* status) {
+    if (!ds || (n && (!queries || !out_queries || !out_clauses || !out_leaves)) || !n_clauses || !n_leaves)
+        return host_fail(FG_ERR_INVALID, "fgh_plan_batch: NULL argument");
+    PlannedBatch pb;
+    plan_batch(ds, n, queries, filters, filter_offsets, pages, per_pages, pb);
+    if (pb.c.size() > cap_clauses || pb.l.size() > cap_leaves) return host_fail(FG_ERR_INVALID, "fgh_plan_batch: output capacity too small");
+    if (n) memcpy(out_queries, pb.q.data(), n * sizeof(fg_query));
+    if (!pb.c.empty()) memcpy(out_clauses, pb.c.data(), pb.c.size() * sizeof(fg_clause));
+    if (!pb.l.empty()) memcpy(out_leaves, pb.l.data(), pb.l.size() * sizeof(fg_leaf));
+    *n_clauses = (uint32_t)pb.c.size();
+    *n_leaves = (uint32_t)pb.l.size();
+    if (status) memcpy(status, pb.rc.data(), n * sizeof(int32_t));
+    if (pb.first_err && !status) return host_fail(pb.first_err, "%s", pb.first_msg.c_str());
+    return FG_OK;
+}
+
+extern "C" int32_t fgh_search_batch(fgh_dataset* ds, uint32_t n, const char* const* queries,
+                                    const char* const* filters, const uint32_t* filter_offsets,
+                                    const uint32_t* pages, const uint32_t* per_pages, uint32_t stride,
+                                    fg_hit* out_hits, uint32_t* out_n, uint32_t* out_match_count,
+                                    int32_t* status) {
+    if (!ds || (n && (!queries || !out_hits || !out_n))) return host_fail(FG_ERR_INVALID, "fgh_search_batch: NULL argument");
+    if (!ds->index) return host_fail(ds->ctx ? FG_ERR_INVALID : FG_ERR_NO_DEVICE, "dataset has no device snapshot (commit first)");
+    if (n == 0) return FG_OK;
+    PlannedBatch pb;
+    plan_batch(ds, n, queries, filters, filter_offsets, pages, per_pages, pb);
+    if (status) memcpy(status, pb.rc.data(), n * sizeof(int32_t));
+    if (pb.first_err && !status) return host_fail(pb.first_err, "%s", pb.first_msg.c_str());  // single-status callers see the first failure
     fg_query_batch qb;
     memset(&qb, 0, sizeof(qb));
     qb.n_queries = n;
-    qb.n_clauses = (uint32_t)fc.size();
-    qb.n_leaves = (uint32_t)fl.size();
-    qb.queries = fq.data();
-    qb.clauses = fc.data();
-    qb.leaves = fl.data();
+    qb.n_clauses = (uint32_t)pb.c.size();
+    qb.n_leaves = (uint32_t)pb.l.size();
+    qb.queries = pb.q.data();
+    qb.clauses = pb.c.data();
+    qb.leaves = pb.l.data();
+    const uint32_t kmax = pb.kmax;
     std::vector<fg_hit> hits((size_t)n * kmax);
     std::vector<uint32_t> nh(n), cnt(n);
     int32_t r = fg_search_batch(ds->index, &qb, kmax, hits.data(), nh.data(), cnt.data());
     if (r) return r;
     for (uint32_t i = 0; i < n; i++) {
-        const uint32_t off = rc[i] ? 0 : plans[i].offset, pp = per_pages ? per_pages[i] : 20;
-        uint32_t m = nh[i] > off ? std::min(nh[i] - off, std::min(pp, stride)) : 0;  // skip(offset).take(per_page)
-        if (rc[i]) m = 0;
+        const bool bad = pb.rc[i] != FG_OK;
+        const uint32_t off = pb.offset[i], pp = per_pages ? per_pages[i] : 20;
+        uint32_t m = (!bad && nh[i] > off) ? std::min(nh[i] - off, std::min(pp, stride)) : 0;  // skip(offset).take(per_page)
         for (uint32_t j = 0; j < m; j++) out_hits[(size_t)i * stride + j] = hits[(size_t)i * kmax + off + j];
         out_n[i] = m;
-        if (out_match_count) out_match_count[i] = rc[i] ? 0 : cnt[i];
+        if (out_match_count) out_match_count[i] = bad ? 0 : cnt[i];
     }
     return FG_OK;
 }

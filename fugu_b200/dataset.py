@@ -49,7 +49,7 @@ class Plan(C.Structure):
 HOST_SYMBOLS = [
     "fgh_dataset_create", "fgh_dataset_destroy", "fgh_dataset_upsert", "fgh_dataset_delete", "fgh_dataset_commit",
     "fgh_dataset_adopt", "fgh_dataset_num_docs", "fgh_dataset_index", "fgh_dataset_doc_id", "fgh_dataset_term_ord",
-    "fgh_tokenize", "fgh_plan", "fgh_search", "fgh_search_batch",
+    "fgh_tokenize", "fgh_plan", "fgh_plan_batch", "fgh_search", "fgh_search_batch",
 ]
 _bound = False
 
@@ -76,6 +76,7 @@ def _L():
         L.fgh_dataset_term_ord.restype = u32
         L.fgh_tokenize.argtypes = [C.c_char_p, C.c_char_p, u32]
         L.fgh_plan.argtypes = [vp, C.c_char_p, cpp, u32, u32, u32, C.POINTER(Plan)]
+        L.fgh_plan_batch.argtypes = [vp, u32, cpp, cpp, vp, vp, vp, vp, vp, u32, vp, u32, C.POINTER(u32), C.POINTER(u32), vp]
         L.fgh_search.argtypes = [vp, C.c_char_p, cpp, u32, u32, u32, vp, vp, vp]
         L.fgh_search_batch.argtypes = [vp, u32, cpp, cpp, vp, vp, vp, u32, vp, vp, vp, vp]
         _bound = True
@@ -179,6 +180,25 @@ class SearchResponse:
     query: str
 
 
+class QuerySet:
+    """Request strings marshalled once into the char** arrays of the batched calls (so that a
+    timed loop measures the library, not Python string encoding)."""
+
+    def __init__(self, queries: list[str], filters: list[list[str]] | None = None, page: int = 0, per_page: int = 20):
+        n = len(queries)
+        self.n, self.page, self.per_page = n, page, per_page
+        self.qarr = (C.c_char_p * max(n, 1))(*[q.encode() for q in queries])
+        self.farr = self.foffs = None
+        if filters is not None and any(filters):
+            flat = [f.encode() for fl in filters for f in fl]
+            self.farr = (C.c_char_p * max(len(flat), 1))(*flat)
+            self.foffs = np.zeros(n + 1, np.uint32)
+            self.foffs[1:] = np.cumsum([len(fl) for fl in filters])
+        self.pages = np.full(n, page, np.uint32)
+        self.pps = np.full(n, per_page, np.uint32)
+        self.in_bytes = sum(len(q) + 1 for q in queries) + (0 if filters is None else sum(len(f) + 1 for fl in filters for f in fl))
+
+
 class Dataset:
     """Mirror of `Dataset` (docs index only) whose search runs on the GPU."""
 
@@ -240,6 +260,29 @@ class Dataset:
         nat.check(_L().fgh_plan(self.h, query.encode(), arr, len(filters), page, per_page, C.byref(p)))
         return p
 
+    def plan_batch(self, queries, filters: list[list[str]] | None = None, page: int = 0, per_page: int = 20):
+        """fgh_plan_batch -> (HostBatch, status[n]): the flat fg_query_batch of n requests."""
+        qs = queries if isinstance(queries, QuerySet) else QuerySet(queries, filters, page, per_page)
+        n = qs.n
+        q = np.zeros(n, nat.QUERY_DT)
+        c = np.zeros(max(n * MAX_PLAN_CLAUSES, 1), nat.CLAUSE_DT)
+        l = np.zeros(max(n * MAX_PLAN_LEAVES, 1), nat.LEAF_DT)
+        nc, nl = C.c_uint32(), C.c_uint32()
+        status = np.zeros(n, np.int32)
+        nat.check(_L().fgh_plan_batch(self.h, n, qs.qarr, qs.farr, None if qs.foffs is None else qs.foffs.ctypes.data,
+                                      qs.pages.ctypes.data, qs.pps.ctypes.data, q.ctypes.data, c.ctypes.data, len(c),
+                                      l.ctypes.data, len(l), C.byref(nc), C.byref(nl), status.ctypes.data))
+        return nat.HostBatch.from_arrays(q, c[:nc.value].copy(), l[:nl.value].copy()), status
+
+    def index(self) -> nat.Index:
+        """Non-owning handle of the current device snapshot."""
+        ix = nat.Index.__new__(nat.Index)
+        ix.ctx = self.ctx
+        ix.h = C.c_void_p(_L().fgh_dataset_index(self.h))
+        ix.n_docs = self.num_docs
+        ix.close = lambda: None
+        return ix
+
     # ---- search -------------------------------------------------------------------------
     def search(self, query: str, filters: list[str] | None = None, page: int = 0, per_page: int = 20) -> list[FuguSearchResult]:
         """Dataset::search(query, filters, page, per_page) -> the requested page of hits."""
@@ -252,24 +295,16 @@ class Dataset:
                                   C.byref(n), C.byref(cnt)))
         return [FuguSearchResult(self.doc_id(int(h["doc"])), float(h["score"]), int(h["doc"])) for h in hits[:n.value]]
 
-    def search_batch(self, queries: list[str], filters: list[list[str]] | None = None, page: int = 0, per_page: int = 20):
+    def search_batch(self, queries, filters: list[list[str]] | None = None, page: int = 0, per_page: int = 20):
         """Batched form: returns (hits[n, per_page], n_hits[n], match_count[n], status[n])."""
-        n = len(queries)
-        qarr = (C.c_char_p * max(n, 1))(*[q.encode() for q in queries])
-        farr = foffs = None
-        if filters is not None:
-            flat = [f.encode() for fl in filters for f in fl]
-            farr = (C.c_char_p * max(len(flat), 1))(*flat)
-            foffs = np.zeros(n + 1, np.uint32)
-            foffs[1:] = np.cumsum([len(fl) for fl in filters])
-        pages = np.full(n, page, np.uint32)
-        pps = np.full(n, per_page, np.uint32)
+        qs = queries if isinstance(queries, QuerySet) else QuerySet(queries, filters, page, per_page)
+        n, per_page = qs.n, qs.per_page
         hits = np.zeros((n, per_page), nat.HIT_DT)
         nh = np.zeros(n, np.uint32)
         cnt = np.zeros(n, np.uint32)
         status = np.zeros(n, np.int32)
-        nat.check(_L().fgh_search_batch(self.h, n, qarr, farr, None if foffs is None else foffs.ctypes.data,
-                                        pages.ctypes.data, pps.ctypes.data, per_page, hits.ctypes.data, nh.ctypes.data,
+        nat.check(_L().fgh_search_batch(self.h, n, qs.qarr, qs.farr, None if qs.foffs is None else qs.foffs.ctypes.data,
+                                        qs.pages.ctypes.data, qs.pps.ctypes.data, per_page, hits.ctypes.data, nh.ctypes.data,
                                         cnt.ctypes.data, status.ctypes.data))
         return hits, nh, cnt, status
 

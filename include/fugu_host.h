@@ -87,6 +87,16 @@ typedef struct {
 int32_t fgh_plan(const fgh_dataset* ds, const char* query, const char* const* filters,
                  uint32_t n_filters, uint32_t page, uint32_t per_page, fgh_plan_t* out);
 
+/* Plans n requests (multi-threaded) into one flat fg_query_batch in caller-allocated arrays
+ * (worst case FGH_MAX_PLAN_CLAUSES / FGH_MAX_PLAN_LEAVES per query). Requests that fail to plan
+ * become empty queries and report their code in status[q] (when status is NULL the first failure is
+ * returned instead). */
+int32_t fgh_plan_batch(const fgh_dataset* ds, uint32_t n, const char* const* queries,
+                       const char* const* filters, const uint32_t* filter_offsets,
+                       const uint32_t* pages, const uint32_t* per_pages, fg_query* out_queries,
+                       fg_clause* out_clauses, uint32_t cap_clauses, fg_leaf* out_leaves,
+                       uint32_t cap_leaves, uint32_t* n_clauses, uint32_t* n_leaves, int32_t* status);
+
 /* ---- search: Dataset::search for one request / a batch of requests ----
  * Writes the requested page (after skip(offset).take(per_page), src/db/search.rs:210-211) to
  * out_hits[q*per_page_stride ..], the number of hits in the page to out_n[q] and, when not NULL,
