@@ -29,6 +29,7 @@ FG_TERM_MISSING = 0xFFFFFFFF
 FG_TERM_ALL = 0xFFFFFFFE
 FG_EXEC_EXACT_ACCOUNTING = 1
 FG_EXEC_DETERMINISTIC = 2
+FG_EXEC_COUNTERS = 4
 
 
 class FgError(RuntimeError):

@@ -3,6 +3,7 @@
 // batch execution. No CPU evaluation path exists here: without a CUDA device every compute entry
 // point returns FG_ERR_NO_DEVICE.
 #include <cuda_runtime.h>
+#include <time.h>
 
 #include <algorithm>
 #include <cmath>
@@ -415,10 +416,16 @@ struct fg_batch {
     uint64_t* d_partial = nullptr;
     uint32_t* d_partial_count = nullptr;
     unsigned long long* d_stats = nullptr;
+    uint32_t* d_qtheta = nullptr;
     uint64_t n_launches = 0;
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};  // before search, after search, after merge
 };
 
+static double now_ms() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
 static uint64_t env_u64(const char* name, uint64_t dflt) {
     const char* e = getenv(name);
     return e ? strtoull(e, nullptr, 10) : dflt;
@@ -428,7 +435,7 @@ extern "C" void fg_batch_release(fg_batch* b) {
     if (!b) return;
     if (b->ix && b->ix->ctx) cudaSetDevice(b->ix->ctx->device);
     cudaFree(b->d_queries); cudaFree(b->d_leaves); cudaFree(b->d_items);
-    cudaFree(b->d_partial); cudaFree(b->d_partial_count); cudaFree(b->d_stats);
+    cudaFree(b->d_partial); cudaFree(b->d_partial_count); cudaFree(b->d_stats); cudaFree(b->d_qtheta);
     for (auto& e : b->ev) if (e) cudaEventDestroy(e);
     delete b;
 }
@@ -447,6 +454,7 @@ extern "C" int32_t fg_batch_prepare(fg_index* ix, const fg_query_batch* qb, fg_b
     *out = nullptr;
     if (qb->n_queries && (!qb->queries || (qb->n_clauses && !qb->clauses) || (qb->n_leaves && !qb->leaves)))
         return fail(FG_ERR_INVALID, "fg_batch_prepare: NULL arrays");
+    const double t_begin = now_ms();
     const uint64_t ITEM_BYTES = env_u64("FG_ITEM_BYTES", 65536);
     const uint64_t DENSE_MIN = env_u64("FG_DENSE_MIN", 1536);  // insert postings per dense window
     const uint64_t DENSE_MIN_MUST = env_u64("FG_DENSE_MIN_MUST", 256);  // same, plans with Must clauses
@@ -603,6 +611,7 @@ extern "C" int32_t fg_batch_prepare(fg_index* ix, const fg_query_batch* qb, fg_b
         }
     }
 
+    const double t_lower = now_ms();
     // heavy items first (the hardware CTA scheduler is the work queue)
     std::vector<uint32_t> order(items.size());
     for (uint32_t i = 0; i < order.size(); i++) order[i] = i;
@@ -631,9 +640,12 @@ extern "C" int32_t fg_batch_prepare(fg_index* ix, const fg_query_batch* qb, fg_b
     if ((rc = up(sorted.data(), sorted.size() * sizeof(DevItem), (void**)&b->d_items))) return rc;
     CU(cudaMalloc((void**)&b->d_partial, std::max<size_t>((size_t)b->n_items * b->kcap * 8, 16)));
     CU(cudaMalloc((void**)&b->d_partial_count, std::max<size_t>((size_t)b->n_items * 4, 16)));
-    CU(cudaMalloc((void**)&b->d_stats, 4 * sizeof(unsigned long long)));
+    CU(cudaMalloc((void**)&b->d_stats, 16 * sizeof(unsigned long long)));
+    CU(cudaMalloc((void**)&b->d_qtheta, std::max<size_t>((size_t)b->n_queries * 4, 16)));
     for (auto& e : b->ev) CU(cudaEventCreate(&e));
     CU(cudaStreamSynchronize(ctx->stream));  // host vectors go out of scope
+    if (getenv("FG_TIMING"))
+        fprintf(stderr, "[fg_batch_prepare] lowering %.2f ms, sort+upload %.2f ms (%zu items)\n", t_lower - t_begin, now_ms() - t_lower, items.size());
     *out = b.release();
     return FG_OK;
 }
@@ -647,7 +659,8 @@ extern "C" int32_t fg_batch_execute(fg_batch* b, uint32_t flags, uint32_t k_stri
     CU(cudaSetDevice(ctx->device));
     std::lock_guard<std::mutex> g(ctx->mu);
     cudaStream_t st = ctx->stream;
-    CU(cudaMemsetAsync(b->d_stats, 0, 4 * sizeof(unsigned long long), st));
+    CU(cudaMemsetAsync(b->d_stats, 0, 16 * sizeof(unsigned long long), st));
+    CU(cudaMemsetAsync(b->d_qtheta, 0, std::max<size_t>((size_t)b->n_queries * 4, 16), st));
     SearchParams p{};
     p.ix = ix->dev;
     p.queries = b->d_queries;
@@ -662,6 +675,9 @@ extern "C" int32_t fg_batch_execute(fg_batch* b, uint32_t flags, uint32_t k_stri
     p.bitmap_words = (ix->n_docs + 31) / 32;
     p.exact_filter = (flags & FG_EXEC_EXACT_ACCOUNTING) ? 1 : 0;
     p.deterministic = (flags & FG_EXEC_DETERMINISTIC) ? 1 : 0;
+    p.acct = (flags & (FG_EXEC_EXACT_ACCOUNTING | FG_EXEC_COUNTERS)) ? 1 : 0;
+    p.qtheta = (flags & FG_EXEC_DETERMINISTIC) ? nullptr : b->d_qtheta;
+    p.prof = getenv("FG_PROF") ? b->d_stats + 8 : nullptr;
     CU(cudaEventRecord(b->ev[0], st));
     launch_search(p, b->ks, st);
     CU(cudaEventRecord(b->ev[1], st));
@@ -696,6 +712,13 @@ extern "C" int32_t fg_batch_get_stats(fg_batch* b, fg_batch_stats* out) {
         CU(cudaStreamSynchronize(ctx->stream));
         CU(cudaMemcpy(h, b->d_stats, sizeof(h), cudaMemcpyDeviceToHost));
     }
+    if (getenv("FG_PROF")) {
+        unsigned long long pr[8];
+        cudaMemcpy(pr, b->d_stats + 8, sizeof(pr), cudaMemcpyDeviceToHost);
+        const double ni = b->n_items ? (double)b->n_items : 1.0;
+        fprintf(stderr, "[prof] per item (cycles): init %.0f setup %.0f scan %.0f decode %.0f slotscan %.0f epilogue %.0f rounds %.1f\n",
+                pr[0] / ni, pr[1] / ni, pr[2] / ni, pr[3] / ni, pr[4] / ni, pr[5] / ni, pr[7] / ni);
+    }
     out->bytes_blocks = h[0];
     out->bytes_redecode = h[1];
     out->scored_postings = h[2];
@@ -714,8 +737,11 @@ extern "C" int32_t fg_batch_get_stats(fg_batch* b, fg_batch_stats* out) {
 extern "C" int32_t fg_search_batch(fg_index* ix, const fg_query_batch* qb, uint32_t k_stride,
                                    fg_hit* out_hits, uint32_t* out_n_hits, uint32_t* out_match_count) {
     if (!ix || !qb || !out_hits || !out_n_hits) return fail(FG_ERR_INVALID, "fg_search_batch: NULL argument");
+    const bool timing = getenv("FG_TIMING") != nullptr;
+    const double t0 = now_ms();
     fg_batch* b = nullptr;
     int32_t rc = fg_batch_prepare(ix, qb, &b);
+    const double t1 = now_ms();
     if (rc) return rc;
     std::unique_ptr<fg_batch, void (*)(fg_batch*)> guard(b, fg_batch_release);
     if (k_stride < b->kcap) return fail(FG_ERR_INVALID, "k_stride %u < max k %u", k_stride, b->kcap);
@@ -736,6 +762,8 @@ extern "C" int32_t fg_search_batch(fg_index* ix, const fg_query_batch* qb, uint3
     CU(cudaMemcpyAsync(out_n_hits, d_n, nq * 4, cudaMemcpyDeviceToHost, ctx->stream));
     if (out_match_count) CU(cudaMemcpyAsync(out_match_count, d_c, nq * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
+    if (timing)
+        fprintf(stderr, "[fg_search_batch] prepare %.2f ms, alloc+execute+d2h %.2f ms (n=%zu)\n", t1 - t0, now_ms() - t1, nq);
     return FG_OK;
 }
 

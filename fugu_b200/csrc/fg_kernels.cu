@@ -20,6 +20,7 @@
 // TopDocs (score desc, doc asc). Per-item lists are merged per query by merge_kernel.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "fg_internal.h"
 
@@ -156,7 +157,6 @@ __device__ __forceinline__ bool cb_any(const uint32_t* cb, uint32_t a, uint32_t 
 __device__ __forceinline__ uint32_t hash_doc(uint32_t d) { return (d * 2654435761u) >> (32 - HS_LOG2); }
 
 constexpr int SEG_CAP = 128;  // worklist entries per scanning warp
-constexpr int GRP = 2;        // blocks decoded together by one warp (memory-level parallelism)
 constexpr uint32_t LEAF_DONE = 0xFFFFFFFFu;
 
 struct Shared {
@@ -176,7 +176,7 @@ __device__ __forceinline__ void smem_add_f32(float* p, float v) { atomicAdd(p, v
 
 // One work item. DENSE: slot = doc - round_lo; else hash slots. PURE: the plan is a plain union
 // (only Should clauses, positive weights): no clause masks, every touched slot matches.
-template <int KS, bool DENSE, bool PURE>
+template <int KS, int GRP, bool DENSE, bool PURE>
 __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& it, const DevQuery& q,
                                          Shared& S, float* acc, uint32_t* keys, uint8_t* msk,
                                          uint32_t* cb, uint32_t* wl, uint64_t* scratch) {
@@ -209,17 +209,20 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
     }
     {
         float4* a4 = reinterpret_cast<float4*>(acc);
-        for (int i = tid; i < SLOTS / 4; i += NT) a4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = tid; i < (DENSE ? DW : HS) / 4; i += NT) a4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (!DENSE) {
             uint4* k4 = reinterpret_cast<uint4*>(keys);
             for (int i = tid; i < HS / 4; i += NT) k4[i] = make_uint4(EMPTY, EMPTY, EMPTY, EMPTY);
         }
         if (!PURE)
-            for (int i = tid; i < SLOTS / 4; i += NT) reinterpret_cast<uint32_t*>(msk)[i] = 0;
+            for (int i = tid; i < (DENSE ? DW : HS) / 4; i += NT) reinterpret_cast<uint32_t*>(msk)[i] = 0;
     }
     if (tid == 0) { S.match = 0; S.st_blocks = 0; S.st_redecode = 0; S.st_scored = 0; }
     __syncthreads();
 
+    long long pt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tp = clock64();
+#define PROF(i) do { if (p.prof && tid == 0) { const long long now_ = clock64(); pt[i] += now_ - tp; tp = now_; } } while (0)
     WarpTopK<KS> tk;
     tk.init();
     float theta_s = -INFINITY;  // score part of tk.theta (a candidate needs score >= theta_s)
@@ -227,6 +230,7 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
     const uint32_t end = it.doc_hi;
     uint32_t my_matches = 0, my_scored = 0;
     unsigned long long my_blocks = 0, my_redecode = 0;
+    PROF(0);  // item init
 
     while (true) {
         // ---- round setup ----
@@ -260,6 +264,8 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
         __syncthreads();
         if (S.done) break;
         const uint32_t rlo = S.rlo, rhi = S.rhi, shift = S.shift;
+        PROF(1);  // round setup
+        if (p.prof && tid == 0) pt[7]++;
 
         // ---- clause phases: leaves [l0, l1) share (role, bit) ----
         int l0 = 0;
@@ -267,6 +273,7 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
             const int l1 = (int)S.phase_end[l0];
             const uint32_t role = S.leaf[l0].role, bit = S.leaf[l0].bit, req = S.leaf[l0].req;
             const bool filter = role != ROLE_INSERT;
+            const bool solo = (l1 - l0) == 1;  // one leaf in the phase: a slot is touched by one thread only
             for (int i = tid; i < (l1 - l0) * NW; i += NT) {
                 const int l = l0 + i / NW, w = i % NW;
                 const uint32_t c0 = (uint32_t)((w - l) & (NW - 1));  // this warp's first chunk of leaf l
@@ -325,6 +332,7 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
                 }
                 if (lane == 0) S.segcnt[warp] = cnt;
                 __syncthreads();
+                PROF(2);  // skip scan
                 // (b) decode GRP blocks per warp step
                 for (int sg = 0; sg < NW; sg++) {
                 const uint32_t total = S.segcnt[sg];
@@ -350,7 +358,7 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
                         const uint32_t* wd = reinterpret_cast<const uint32_t*>(p.ix.blk + (size_t)e[g].z * 16u);
                         unpack4(wd, lane, bd, gp[g]);
                         unpack4(wd + 4 * bd, lane, bt, tf[g]);
-                        if (lane == 0 && val[g]) {
+                        if (p.acct && lane == 0 && val[g]) {
                             const unsigned long long by = ((nn[g] * bd + 7) >> 3) + ((nn[g] * bt + 7) >> 3) + 16;
                             if (e[g].y >= lo) my_blocks += by; else my_redecode += by;
                         }
@@ -364,13 +372,16 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
                     }
                     // slot lookup / insertion first (filter clauses touch only existing candidates) ...
                     int slot[GRP][4];
+                    bool inside[GRP];  // block entirely inside the round: no per-posting range test
+#pragma unroll
+                    for (int g = 0; g < GRP; g++) inside[g] = e[g].y >= rlo && e[g].x < rhi;
 #pragma unroll
                     for (int g = 0; g < GRP; g++) {
 #pragma unroll
                         for (int j = 0; j < 4; j++) {
                             const uint32_t d = gp[g][j];
                             int sl = -1;
-                            if (4u * lane + j < nn[g] && d >= rlo && d < rhi) {
+                            if (4u * lane + j < nn[g] && (inside[g] || (d >= rlo && d < rhi))) {
                                 if (DENSE) {
                                     sl = (int)(d - rlo);
                                     if (!PURE && filter) {
@@ -426,14 +437,17 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
                             const int sl = slot[g][j];
                             if (sl < 0) continue;
                             const float t = (float)(tf[g][j] + 1u);
-                            smem_add_f32(&acc[sl], wgt * __fdividef(t, t + norm[g][j]));
+                            const float v = wgt * __fdividef(t, t + norm[g][j]);
+                            if (solo) acc[sl] += v; else smem_add_f32(&acc[sl], v);
                             if (!PURE && bit) msk[sl] = (uint8_t)(msk[sl] | bit);
-                            my_scored++;
+                            if (p.acct) my_scored++;
                         }
                     }
                 }
                 }
-                if (!__syncthreads_or(my_pending)) break;
+                const int more_ = __syncthreads_or(my_pending);
+                PROF(3);  // decode + apply
+                if (!more_) break;
             }
             // candidate bitmap for the following filter clause
             const uint32_t need = S.leaf[l1 - 1].build_cb;
@@ -469,10 +483,17 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
 
         // ---- slot scan: match test, cheap f32 pre-test against the k-th score, reset ----
         {
+            // score threshold shared by all work items of the query: >= k docs are known to score at
+            // least this much, so anything strictly below can never reach the final top-k
+            if (p.qtheta) {
+                const uint32_t gt = __ldcg(p.qtheta + it.query);
+                if (gt) theta_s = fmaxf(theta_s, unsortable(gt));
+            }
             const int n4 = DENSE ? (int)((rhi - rlo + 3) >> 2) : HS / 4;
             uint32_t* m32 = reinterpret_cast<uint32_t*>(msk);
             float4* a4 = reinterpret_cast<float4*>(acc);
             uint4* k4 = reinterpret_cast<uint4*>(keys);
+            const bool generic = !PURE || p.ix.alive != nullptr || p.match_bitmap != nullptr;
             for (int g0 = warp * 32; g0 < n4; g0 += NT) {
                 const int g = g0 + lane;
                 float4 av = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -484,43 +505,58 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
                     if (!DENSE) { kv = k4[g]; k4[g] = make_uint4(EMPTY, EMPTY, EMPTY, EMPTY); }
                     if (!PURE) { m4 = m32[g]; if (m4) m32[g] = 0; }
                 }
-                const float sc[4] = {av.x + q.const_score, av.y + q.const_score, av.z + q.const_score,
-                                     av.w + q.const_score};
                 const float raw[4] = {av.x, av.y, av.z, av.w};
                 const uint32_t kk[4] = {kv.x, kv.y, kv.z, kv.w};
                 bool mt[4];
-                bool hot = false;
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    if (PURE) mt[j] = DENSE ? raw[j] > 0.f : kk[j] != EMPTY;
-                    else {
-                        const uint32_t m = (m4 >> (8 * j)) & 0xFFu;
-                        mt[j] = (m & 0x7Fu) == q.all_must && !(m & BIT_NOT);
-                    }
-                }
-                if (p.ix.alive || p.match_bitmap) {
+                bool hot;
+                if (!generic) {
+                    // pure union, no deletes: every touched slot matches and its score is > 0
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
-                        if (!mt[j]) continue;
-                        const uint32_t doc = DENSE ? rlo + 4 * g + j : kk[j];
-                        if (p.ix.alive && !((__ldg(p.ix.alive + (doc >> 5)) >> (doc & 31)) & 1u)) { mt[j] = false; continue; }
-                        if (p.match_bitmap)
-                            atomicOr(p.match_bitmap + (size_t)it.query * p.bitmap_words + (doc >> 5), 1u << (doc & 31));
+                        mt[j] = DENSE ? raw[j] > 0.f : kk[j] != EMPTY;
+                        my_matches += mt[j];
                     }
-                }
+                    const float mx = fmaxf(fmaxf(raw[0], raw[1]), fmaxf(raw[2], raw[3]));
+                    hot = mx + q.const_score >= theta_s && (DENSE ? mx > 0.f : true);
+                } else {
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    my_matches += mt[j];
-                    hot |= mt[j] && sc[j] >= theta_s;
+                    for (int j = 0; j < 4; j++) {
+                        if (PURE) mt[j] = DENSE ? raw[j] > 0.f : kk[j] != EMPTY;
+                        else {
+                            const uint32_t m = (m4 >> (8 * j)) & 0xFFu;
+                            mt[j] = (m & 0x7Fu) == q.all_must && !(m & BIT_NOT);
+                        }
+                    }
+                    if (p.ix.alive || p.match_bitmap) {
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            if (!mt[j]) continue;
+                            const uint32_t doc = DENSE ? rlo + 4 * g + j : kk[j];
+                            if (p.ix.alive && !((__ldg(p.ix.alive + (doc >> 5)) >> (doc & 31)) & 1u)) { mt[j] = false; continue; }
+                            if (p.match_bitmap)
+                                atomicOr(p.match_bitmap + (size_t)it.query * p.bitmap_words + (doc >> 5), 1u << (doc & 31));
+                        }
+                    }
+                    hot = false;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        my_matches += mt[j];
+                        hot |= mt[j] && raw[j] + q.const_score >= theta_s;
+                    }
                 }
                 if (__any_sync(FULL, hot)) {
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
                         const uint32_t doc = DENSE ? rlo + 4 * g + j : kk[j];
-                        const bool c = mt[j] && sc[j] >= theta_s;
-                        tk.offer(c, c ? make_key(sc[j], doc) : 0ull, k, lane);
+                        const float sc = raw[j] + q.const_score;
+                        const bool c = mt[j] && sc >= theta_s;
+                        tk.offer(c, c ? make_key(sc, doc) : 0ull, k, lane);
                     }
-                    theta_s = tk.theta ? unsortable((uint32_t)(tk.theta >> 32)) : -INFINITY;
+                    const float mine = tk.theta ? unsortable((uint32_t)(tk.theta >> 32)) : -INFINITY;
+                    if (mine > theta_s) {
+                        theta_s = mine;
+                        if (p.qtheta && lane == 0) atomicMax(p.qtheta + it.query, sortable(mine));
+                    }
                 }
             }
         }
@@ -528,6 +564,7 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
         if (tid < nl) S.cur[tid] = max(S.cur[tid], S.cur_next[tid]);
         lo = rhi;
         __syncthreads();
+        PROF(4);  // slot scan
     }
 
     // ---- per-item epilogue: merge the warp queues, write the partial list ----
@@ -557,6 +594,10 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
         }
         if (lane == 0) {
             p.partial_count[it.slot] = S.match;
+            if (p.prof) {
+                PROF(5);  // epilogue
+                for (int i = 0; i < 8; i++) atomicAdd(p.prof + i, (unsigned long long)pt[i]);
+            }
             if (p.stats) {
                 atomicAdd(p.stats + 0, S.st_blocks);
                 atomicAdd(p.stats + 1, S.st_redecode);
@@ -566,15 +607,20 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
     }
 }
 
-template <int KS>
-__global__ void __launch_bounds__(NT, 3) search_kernel(const SearchParams p) {
+template <int KS, int GRP, int MINB>
+__global__ void __launch_bounds__(NT, MINB) search_kernel(const SearchParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ Shared S;
+    // [0, 32K)   dense: acc[DW]            | hash: acc[HS] + keys[HS]
+    // [32K, 40K) dense: msk[DW]            | hash: msk[HS] + candidate bitmap (CBW words)
+    // [40K, 41K) dense: candidate bitmap (DW bits)
+    static_assert(2 * HS <= DW && HS + CBW * 4 <= DW, "hash layout must fit the dense regions");
     float* acc = reinterpret_cast<float*>(smem);
-    uint32_t* keys = reinterpret_cast<uint32_t*>(smem + SLOTS * 4);  // hash mode only
-    uint8_t* msk = smem + SLOTS * 4 + HS * 4;
-    uint32_t* cb = reinterpret_cast<uint32_t*>(smem + SLOTS * 4 + HS * 4 + SLOTS);
-    uint32_t* wl = cb + CBW;
+    uint32_t* keys = reinterpret_cast<uint32_t*>(smem) + HS;
+    uint8_t* msk = smem + DW * 4;
+    uint32_t* cb_dense = reinterpret_cast<uint32_t*>(smem + DW * 4 + DW);
+    uint32_t* cb_hash = reinterpret_cast<uint32_t*>(msk + HS);
+    uint32_t* wl = cb_dense + DW / 32;
     uint64_t* scratch = reinterpret_cast<uint64_t*>(wl + NW * SEG_CAP);
 
     const DevItem it = p.items[blockIdx.x];
@@ -583,11 +629,11 @@ __global__ void __launch_bounds__(NT, 3) search_kernel(const SearchParams p) {
     __syncthreads();
     const bool pure = (q.flags & QF_PURE_UNION) != 0;
     if (it.mode == MODE_DENSE) {
-        if (pure) run_item<KS, true, true>(p, it, q, S, acc, keys, msk, cb, wl, scratch);
-        else run_item<KS, true, false>(p, it, q, S, acc, keys, msk, cb, wl, scratch);
+        if (pure) run_item<KS, GRP, true, true>(p, it, q, S, acc, keys, msk, cb_dense, wl, scratch);
+        else run_item<KS, GRP, true, false>(p, it, q, S, acc, keys, msk, cb_dense, wl, scratch);
     } else {
-        if (pure) run_item<KS, false, true>(p, it, q, S, acc, keys, msk, cb, wl, scratch);
-        else run_item<KS, false, false>(p, it, q, S, acc, keys, msk, cb, wl, scratch);
+        if (pure) run_item<KS, GRP, false, true>(p, it, q, S, acc, keys, msk, cb_hash, wl, scratch);
+        else run_item<KS, GRP, false, false>(p, it, q, S, acc, keys, msk, cb_hash, wl, scratch);
     }
 }
 
@@ -697,25 +743,32 @@ __global__ void __launch_bounds__(128) merge_gathered_kernel(const uint2* hits, 
 }  // namespace
 
 int search_smem_bytes(int ks) {
-    return SLOTS * 4 + HS * 4 + SLOTS + CBW * 4 + NW * SEG_CAP * 4 + NW * ks * 32 * 8;
+    return DW * 4 + DW + DW / 8 + NW * SEG_CAP * 4 + NW * ks * 32 * 8;
 }
 
-template <int KS>
+template <int KS, int GRP, int MINB>
 static void launch_search_t(const SearchParams& p, cudaStream_t st) {
     static bool configured = false;
     const int smem = search_smem_bytes(KS);
     if (!configured) {
-        cudaFuncSetAttribute(search_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(search_kernel<KS, GRP, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         configured = true;
     }
-    search_kernel<KS><<<p.n_items, NT, smem, st>>>(p);
+    search_kernel<KS, GRP, MINB><<<p.n_items, NT, smem, st>>>(p);
 }
 
 void launch_search(const SearchParams& p, int ks, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (p.n_items == 0) return;
-    if (ks <= 1) launch_search_t<1>(p, st);
-    else launch_search_t<4>(p, st);
+    static const int variant = getenv("FG_VARIANT") ? atoi(getenv("FG_VARIANT")) : 0;
+    if (ks > 1) { launch_search_t<4, 1, 3>(p, st); return; }
+    switch (variant) {
+        case 1: launch_search_t<1, 2, 4>(p, st); break;
+        case 2: launch_search_t<1, 4, 3>(p, st); break;
+        case 4: launch_search_t<1, 1, 5>(p, st); break;
+        case 5: launch_search_t<1, 2, 3>(p, st); break;
+        default: launch_search_t<1, 1, 4>(p, st); break;
+    }
 }
 
 void launch_merge(const MergeParams& p, int ks, void* stream) {

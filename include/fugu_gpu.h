@@ -162,6 +162,7 @@ typedef struct fg_batch fg_batch;
 int32_t fg_batch_prepare(fg_index* index, const fg_query_batch* batch, fg_batch** out);
 void fg_batch_release(fg_batch* b);
 #define FG_EXEC_EXACT_ACCOUNTING 1u /* exact block-need test for the algorithmic-byte counters (slow) */
+#define FG_EXEC_COUNTERS 4u         /* maintain bytes_blocks / bytes_redecode / scored_postings (cheap) */
 #define FG_EXEC_DETERMINISTIC 2u    /* apply leaves one at a time: bit-reproducible f32 sums (slower);
                                        default sums the leaves of a clause with float atomics, which can
                                        differ in the last bit for docs with >= 3 contributions */

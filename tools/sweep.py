@@ -44,10 +44,11 @@ def main():
             ms = []
             for it in range(6):
                 flush.fill_(it)
-                pb.execute(d_hits.data_ptr(), d_n.data_ptr(), d_c.data_ptr(), None, k_stride=10)
+                pb.execute(d_hits.data_ptr(), d_n.data_ptr(), d_c.data_ptr(), None, k_stride=10, flags=(nat.FG_EXEC_COUNTERS if it == 0 else 0))
+                if it == 0: s0 = pb.stats()
                 st = pb.stats()
                 if it >= 2: ms.append(st.search_kernel_ms)
-            by = st.bytes_blocks + st.scored_postings
+            st = s0; by = st.bytes_blocks + st.scored_postings
             print(f"{json.dumps(s):40s} {kind:7s} nq={n:5d} items={st.n_work_items:6d} search={np.mean(ms):8.3f} ms merge={st.merge_kernel_ms:6.3f} ms  {by/1e6:8.1f} MB  {by/np.mean(ms)/1e6:7.1f} GB/s  redecode={st.bytes_redecode/1e6:.1f}MB", flush=True)
             pb.close()
         for k_ in s: os.environ.pop(k_, None)
