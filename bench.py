@@ -342,6 +342,8 @@ def main():
         if it >= 2:
             e2e_times.append(dt)
     e2e_s = float(np.mean(e2e_times))
+    if os.environ.get("FG_TIMING"):
+        print("e2e_times ms", [round(x * 1e3, 2) for x in e2e_times], file=sys.stderr)
     if dist:
         t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

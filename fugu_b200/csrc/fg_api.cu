@@ -90,7 +90,42 @@ struct fg_ctx {
     cudaStream_t stream = nullptr;
     std::mutex mu;
     int n_sms = 0;
+    // small cache of device blocks for the per-call buffers (plans, partial lists, results):
+    // cudaMalloc/cudaFree per request would dominate the host side of a 5000-query batch
+    std::mutex pool_mu;
+    std::vector<std::pair<void*, size_t>> pool;
+    size_t pool_bytes = 0;
 };
+
+static cudaError_t pool_alloc(fg_ctx* c, void** out, size_t bytes) {
+    bytes = std::max<size_t>((bytes + 255) & ~(size_t)255, 256);
+    {
+        std::lock_guard<std::mutex> g(c->pool_mu);
+        int best = -1;
+        for (int i = 0; i < (int)c->pool.size(); i++)
+            if (c->pool[i].second >= bytes && c->pool[i].second <= 4 * bytes + (1 << 16) &&
+                (best < 0 || c->pool[i].second < c->pool[best].second)) best = i;
+        if (best >= 0) {
+            *out = c->pool[best].first;
+            c->pool_bytes -= c->pool[best].second;
+            c->pool.erase(c->pool.begin() + best);
+            return cudaSuccess;
+        }
+    }
+    return cudaMalloc(out, bytes);
+}
+// NOTE: callers must have synchronised the stream that last used `p`
+static void pool_free(fg_ctx* c, void* p, size_t bytes) {
+    if (!p) return;
+    bytes = std::max<size_t>((bytes + 255) & ~(size_t)255, 256);
+    std::lock_guard<std::mutex> g(c->pool_mu);
+    if (c->pool.size() < 64 && c->pool_bytes + bytes <= ((size_t)1 << 30)) {
+        c->pool.emplace_back(p, bytes);
+        c->pool_bytes += bytes;
+    } else {
+        cudaFree(p);
+    }
+}
 
 extern "C" int32_t fg_ctx_create(int32_t device, fg_ctx** out) {
     if (!out) return fail(FG_ERR_INVALID, "fg_ctx_create: out is NULL");
@@ -119,6 +154,7 @@ extern "C" void fg_ctx_destroy(fg_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->own) cudaStreamDestroy(c->own);
+    for (auto& b : c->pool) cudaFree(b.first);
     delete c;
 }
 extern "C" int32_t fg_ctx_set_stream(fg_ctx* c, void* s) {
@@ -417,6 +453,7 @@ struct fg_batch {
     uint32_t* d_partial_count = nullptr;
     unsigned long long* d_stats = nullptr;
     uint32_t* d_qtheta = nullptr;
+    size_t sz[7] = {0, 0, 0, 0, 0, 0, 0};
     uint64_t n_launches = 0;
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};  // before search, after search, after merge
 };
@@ -434,8 +471,13 @@ static uint64_t env_u64(const char* name, uint64_t dflt) {
 extern "C" void fg_batch_release(fg_batch* b) {
     if (!b) return;
     if (b->ix && b->ix->ctx) cudaSetDevice(b->ix->ctx->device);
-    cudaFree(b->d_queries); cudaFree(b->d_leaves); cudaFree(b->d_items);
-    cudaFree(b->d_partial); cudaFree(b->d_partial_count); cudaFree(b->d_stats); cudaFree(b->d_qtheta);
+    if (b->ix && b->ix->ctx) {
+        fg_ctx* c = b->ix->ctx;
+        cudaStreamSynchronize(c->stream);  // nothing in flight may still use the blocks we recycle
+        pool_free(c, b->d_queries, b->sz[0]); pool_free(c, b->d_leaves, b->sz[1]); pool_free(c, b->d_items, b->sz[2]);
+        pool_free(c, b->d_partial, b->sz[3]); pool_free(c, b->d_partial_count, b->sz[4]);
+        pool_free(c, b->d_stats, b->sz[5]); pool_free(c, b->d_qtheta, b->sz[6]);
+    }
     for (auto& e : b->ev) if (e) cudaEventDestroy(e);
     delete b;
 }
@@ -628,20 +670,25 @@ extern "C" int32_t fg_batch_prepare(fg_index* ix, const fg_query_batch* qb, fg_b
     b->kcap = kmax;
     b->ks = kmax <= 32 ? 1 : 4;
     b->sum_k = sum_k;
-    auto up = [&](const void* src, size_t bytes, void** dst) -> int32_t {
-        CU(cudaMalloc(dst, std::max<size_t>(bytes, 16)));
+    auto up = [&](const void* src, size_t bytes, void** dst, size_t* sz) -> int32_t {
+        *sz = std::max<size_t>(bytes, 16);
+        CU(pool_alloc(ctx, dst, *sz));
         if (bytes) CU(cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
         return FG_OK;
     };
     int32_t rc;
     std::lock_guard<std::mutex> g(ctx->mu);
-    if ((rc = up(dq.data(), dq.size() * sizeof(DevQuery), (void**)&b->d_queries))) return rc;
-    if ((rc = up(dl.data(), dl.size() * sizeof(DevLeaf), (void**)&b->d_leaves))) return rc;
-    if ((rc = up(sorted.data(), sorted.size() * sizeof(DevItem), (void**)&b->d_items))) return rc;
-    CU(cudaMalloc((void**)&b->d_partial, std::max<size_t>((size_t)b->n_items * b->kcap * 8, 16)));
-    CU(cudaMalloc((void**)&b->d_partial_count, std::max<size_t>((size_t)b->n_items * 4, 16)));
-    CU(cudaMalloc((void**)&b->d_stats, 16 * sizeof(unsigned long long)));
-    CU(cudaMalloc((void**)&b->d_qtheta, std::max<size_t>((size_t)b->n_queries * 4, 16)));
+    if ((rc = up(dq.data(), dq.size() * sizeof(DevQuery), (void**)&b->d_queries, &b->sz[0]))) return rc;
+    if ((rc = up(dl.data(), dl.size() * sizeof(DevLeaf), (void**)&b->d_leaves, &b->sz[1]))) return rc;
+    if ((rc = up(sorted.data(), sorted.size() * sizeof(DevItem), (void**)&b->d_items, &b->sz[2]))) return rc;
+    b->sz[3] = std::max<size_t>((size_t)b->n_items * b->kcap * 8, 16);
+    b->sz[4] = std::max<size_t>((size_t)b->n_items * 4, 16);
+    b->sz[5] = 16 * sizeof(unsigned long long);
+    b->sz[6] = std::max<size_t>((size_t)b->n_queries * 4, 16);
+    CU(pool_alloc(ctx, (void**)&b->d_partial, b->sz[3]));
+    CU(pool_alloc(ctx, (void**)&b->d_partial_count, b->sz[4]));
+    CU(pool_alloc(ctx, (void**)&b->d_stats, b->sz[5]));
+    CU(pool_alloc(ctx, (void**)&b->d_qtheta, b->sz[6]));
     for (auto& e : b->ev) CU(cudaEventCreate(&e));
     CU(cudaStreamSynchronize(ctx->stream));  // host vectors go out of scope
     if (getenv("FG_TIMING"))
@@ -749,12 +796,16 @@ extern "C" int32_t fg_search_batch(fg_index* ix, const fg_query_batch* qb, uint3
     const size_t nq = qb->n_queries;
     if (nq == 0) return FG_OK;
     void *d_hits = nullptr, *d_n = nullptr, *d_c = nullptr;
-    CU(cudaMalloc(&d_hits, nq * k_stride * sizeof(fg_hit)));
-    std::unique_ptr<void, void (*)(void*)> g1(d_hits, [](void* p) { cudaFree(p); });
-    CU(cudaMalloc(&d_n, nq * 4));
-    std::unique_ptr<void, void (*)(void*)> g2(d_n, [](void* p) { cudaFree(p); });
-    CU(cudaMalloc(&d_c, nq * 4));
-    std::unique_ptr<void, void (*)(void*)> g3(d_c, [](void* p) { cudaFree(p); });
+    struct Guard {
+        fg_ctx* c; void* p = nullptr; size_t sz = 0;
+        ~Guard() { if (p) { cudaStreamSynchronize(c->stream); pool_free(c, p, sz); } }
+    } g1{ctx}, g2{ctx}, g3{ctx};
+    CU(pool_alloc(ctx, &d_hits, nq * k_stride * sizeof(fg_hit)));
+    g1.p = d_hits; g1.sz = nq * k_stride * sizeof(fg_hit);
+    CU(pool_alloc(ctx, &d_n, nq * 4));
+    g2.p = d_n; g2.sz = nq * 4;
+    CU(pool_alloc(ctx, &d_c, nq * 4));
+    g3.p = d_c; g3.sz = nq * 4;
     rc = fg_batch_execute(b, 0, k_stride, d_hits, d_n, d_c, nullptr);
     if (rc) return rc;
     std::lock_guard<std::mutex> g(ctx->mu);

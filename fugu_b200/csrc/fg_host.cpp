@@ -293,16 +293,58 @@ std::string escape_query_string(const std::string& q) {
 // ------------------------------------------------------------------------------------------
 // dataset
 // ------------------------------------------------------------------------------------------
+// string -> term ordinal, open addressing over a byte pool (lookups take (ptr, len): no allocation)
+struct TermDict {
+    struct Ent { uint64_t off; uint32_t len, ord; };
+    std::vector<char> pool;
+    std::vector<Ent> ents;
+    std::vector<uint32_t> table;  // index into ents + 1, 0 = empty
+    static uint64_t hash(const char* s, size_t n) {
+        uint64_t h = 1469598103934665603ull;
+        for (size_t i = 0; i < n; i++) { h ^= (unsigned char)s[i]; h *= 1099511628211ull; }
+        return h ^ (h >> 29);
+    }
+    void reserve(size_t n) { if (table.size() < 2 * n + 16) rehash(2 * n + 16); }
+    void rehash(size_t want) {
+        size_t cap = 16;
+        while (cap < want) cap <<= 1;
+        table.assign(cap, 0);
+        for (uint32_t i = 0; i < ents.size(); i++) place(i);
+    }
+    void place(uint32_t i) {
+        size_t m = table.size() - 1, h = hash(pool.data() + ents[i].off, ents[i].len) & m;
+        while (table[h]) h = (h + 1) & m;
+        table[h] = i + 1;
+    }
+    uint32_t find(const char* s, size_t n) const {
+        if (table.empty()) return FG_TERM_MISSING;
+        size_t m = table.size() - 1, h = hash(s, n) & m;
+        while (table[h]) {
+            const Ent& e = ents[table[h] - 1];
+            if (e.len == n && memcmp(pool.data() + e.off, s, n) == 0) return e.ord;
+            h = (h + 1) & m;
+        }
+        return FG_TERM_MISSING;
+    }
+    void insert(const char* s, size_t n, uint32_t ord) {
+        if ((ents.size() + 1) * 2 > table.size()) rehash((ents.size() + 1) * 4);
+        ents.push_back({(uint64_t)pool.size(), (uint32_t)n, ord});
+        pool.insert(pool.end(), s, s + n);
+        place((uint32_t)ents.size() - 1);
+    }
+    size_t size() const { return ents.size(); }
+};
+
 struct FieldBuild {
-    std::unordered_map<std::string, uint32_t> dict;
+    TermDict dict;
     std::vector<std::vector<std::pair<uint32_t, uint32_t>>> postings;  // term -> (doc, tf)
     uint64_t total_tokens = 0;
     std::vector<uint32_t> doc_len;
     uint32_t term(const std::string& t) {
-        auto it = dict.find(t);
-        if (it != dict.end()) return it->second;
-        uint32_t o = (uint32_t)postings.size();
-        dict.emplace(t, o);
+        uint32_t o = dict.find(t.data(), t.size());
+        if (o != FG_TERM_MISSING) return o;
+        o = (uint32_t)postings.size();
+        dict.insert(t.data(), t.size(), o);
         postings.emplace_back();
         return o;
     }
@@ -492,10 +534,10 @@ extern "C" int32_t fgh_dataset_adopt(fgh_dataset* ds, const fg_index_desc* desc,
         if (!terms || !terms[f]) continue;
         const char* p = terms[f];
         const char* end = p + terms_bytes[f];
-        ds->f[f].dict.reserve(desc->fields[f].n_terms * 2);
+        ds->f[f].dict.reserve(desc->fields[f].n_terms);
         for (uint32_t t = 0; t < desc->fields[f].n_terms && p < end; t++) {
             size_t l = strlen(p);
-            ds->f[f].dict.emplace(std::string(p, l), t);
+            ds->f[f].dict.insert(p, l, t);
             p += l + 1;
         }
     }
@@ -518,8 +560,7 @@ extern "C" int32_t fgh_dataset_doc_id(const fgh_dataset* ds, uint32_t doc, char*
 
 extern "C" uint32_t fgh_dataset_term_ord(const fgh_dataset* ds, uint32_t field, const char* token) {
     if (!ds || field > 2 || !token) return FG_TERM_MISSING;
-    auto it = ds->f[field].dict.find(token);
-    return it == ds->f[field].dict.end() ? FG_TERM_MISSING : it->second;
+    return ds->f[field].dict.find(token, strlen(token));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -794,21 +835,102 @@ struct PlannedBatch {
     int32_t first_err = FG_OK;
     std::string first_msg;
 };
+
+// Fast path for the overwhelmingly common request shape: no filters, only ASCII alphanumeric
+// words separated by blanks, optionally all joined by AND. Produces exactly what the general
+// parser produces for such strings (bare words -> Should groups over [text, name]; `a AND b` ->
+// Must groups) without building an AST. Returns false when the string needs the general parser.
+bool plan_fast(const fgh_dataset* ds, const char* q, uint32_t page, uint32_t per_page,
+               std::vector<fg_clause>& c, std::vector<fg_leaf>& l, fg_query& out, uint32_t& offset) {
+    const uint64_t limit = (uint64_t)page * per_page + per_page;
+    if (limit == 0 || limit > 0xFFFFFFFFull || !q) return false;
+    struct W { const char* p; uint32_t n; };
+    W words[16];
+    int nw = 0;
+    const char* p = q;
+    while (*p) {
+        while (*p == ' ' || *p == '\t') p++;
+        if (!*p) break;
+        const char* s0 = p;
+        while (*p && *p != ' ' && *p != '\t') {
+            const unsigned char ch = (unsigned char)*p;
+            if (!((ch >= '0' && ch <= '9') || (ch >= 'a' && ch <= 'z') || (ch >= 'A' && ch <= 'Z'))) return false;
+            p++;
+        }
+        if (nw == 16 || p - s0 >= 40) return false;
+        words[nw++] = {s0, (uint32_t)(p - s0)};
+    }
+    if (nw == 0) return false;  // blank query = AllQuery: general path
+    auto is = [](const W& w, const char* kw) { return w.n == strlen(kw) && memcmp(w.p, kw, w.n) == 0; };
+    bool conj = false;
+    for (int i = 0; i < nw; i++) {
+        if (is(words[i], "OR") || is(words[i], "NOT")) return false;
+        if (is(words[i], "AND")) conj = true;
+    }
+    if (conj) {  // strictly  w AND w AND w ...
+        if (nw % 2 == 0) return false;
+        for (int i = 0; i < nw; i++)
+            if ((i % 2 == 1) != is(words[i], "AND")) return false;
+    }
+    const size_t c0 = c.size();
+    out.k = (uint32_t)limit;
+    out.clause_begin = (uint32_t)c0;
+    offset = page * per_page;
+    char low[40];
+    for (int i = 0; i < nw; i += conj ? 2 : 1) {
+        for (uint32_t j = 0; j < words[i].n; j++) {
+            const char ch = words[i].p[j];
+            low[j] = (ch >= 'A' && ch <= 'Z') ? (char)(ch + 32) : ch;
+        }
+        fg_clause cl;
+        cl.occur = conj ? FG_OCCUR_MUST : FG_OCCUR_SHOULD;
+        cl.leaf_begin = (uint32_t)l.size();
+        cl.n_leaves = 2;
+        l.push_back({FGH_FIELD_TEXT, ds->f[FGH_FIELD_TEXT].dict.find(low, words[i].n), 1.f});
+        l.push_back({FGH_FIELD_NAME, ds->f[FGH_FIELD_NAME].dict.find(low, words[i].n), 1.f});
+        c.push_back(cl);
+    }
+    out.n_clauses = (uint32_t)(c.size() - c0);
+    return true;
+}
+
 void plan_batch(const fgh_dataset* ds, uint32_t n, const char* const* queries, const char* const* filters,
                 const uint32_t* filter_offsets, const uint32_t* pages, const uint32_t* per_pages, PlannedBatch& pb) {
-    std::vector<fgh_plan_t> plans(n);
     pb.rc.assign(n, FG_OK);
-    std::vector<std::string> errs(n);
+    pb.q.resize(n);
+    pb.offset.assign(n, 0);
     unsigned hw = std::thread::hardware_concurrency();
     const char* e = getenv("FG_HOST_THREADS");
     if (e) hw = (unsigned)atoi(e);
-    int T = (int)std::max(1u, std::min<unsigned>(hw ? hw : 4, std::min<unsigned>(32, n / 64 + 1)));
+    // the fast path plans ~3M requests/s per thread: only very large batches are worth threads
+    const int T = (int)std::max(1u, std::min<unsigned>(hw ? hw : 4, std::min<unsigned>(16, n / 4096 + 1)));
+    struct Part { std::vector<fg_clause> c; std::vector<fg_leaf> l; std::vector<std::string> errs; uint32_t a, b; };
+    std::vector<Part> parts((size_t)T);
     auto work = [&](int t) {
-        for (uint32_t i = (uint32_t)((uint64_t)n * t / T); i < (uint32_t)((uint64_t)n * (t + 1) / T); i++) {
+        Part& P = parts[t];
+        P.a = (uint32_t)((uint64_t)n * t / T);
+        P.b = (uint32_t)((uint64_t)n * (t + 1) / T);
+        P.errs.resize(P.b - P.a);
+        fgh_plan_t plan;
+        for (uint32_t i = P.a; i < P.b; i++) {
             const uint32_t f0 = filter_offsets ? filter_offsets[i] : 0, f1 = filter_offsets ? filter_offsets[i + 1] : 0;
-            pb.rc[i] = plan_impl(ds, queries[i], filters ? filters + f0 : nullptr, f1 - f0, pages ? pages[i] : 0,
-                                 per_pages ? per_pages[i] : 20, &plans[i]);
-            if (pb.rc[i]) errs[i] = fg_last_error();
+            const uint32_t page = pages ? pages[i] : 0, pp = per_pages ? per_pages[i] : 20;
+            if (f1 == f0 && plan_fast(ds, queries[i], page, pp, P.c, P.l, pb.q[i], pb.offset[i])) continue;
+            pb.rc[i] = plan_impl(ds, queries[i], filters ? filters + f0 : nullptr, f1 - f0, page, pp, &plan);
+            const bool bad = pb.rc[i] != FG_OK;
+            if (bad) P.errs[i - P.a] = fg_last_error();
+            pb.q[i].k = bad ? 1 : plan.k;
+            pb.q[i].clause_begin = (uint32_t)P.c.size();
+            pb.q[i].n_clauses = bad ? 0 : plan.n_clauses;
+            if (!bad) {
+                pb.offset[i] = plan.offset;
+                for (uint32_t c = 0; c < plan.n_clauses; c++) {
+                    fg_clause cl = plan.clauses[c];
+                    cl.leaf_begin += (uint32_t)P.l.size();
+                    P.c.push_back(cl);
+                }
+                P.l.insert(P.l.end(), plan.leaves, plan.leaves + plan.n_leaves);
+            }
         }
     };
     if (T == 1) work(0);
@@ -817,24 +939,17 @@ void plan_batch(const fgh_dataset* ds, uint32_t n, const char* const* queries, c
         for (int t = 0; t < T; t++) th.emplace_back(work, t);
         for (auto& x : th) x.join();
     }
-    pb.q.resize(n);
-    pb.offset.assign(n, 0);
-    for (uint32_t i = 0; i < n; i++) {
-        const bool bad = pb.rc[i] != FG_OK;
-        if (bad && !pb.first_err) { pb.first_err = pb.rc[i]; pb.first_msg = errs[i]; }
-        pb.q[i].k = bad ? 1 : plans[i].k;
-        pb.q[i].clause_begin = (uint32_t)pb.c.size();
-        pb.q[i].n_clauses = bad ? 0 : plans[i].n_clauses;
-        if (!bad) {
-            pb.offset[i] = plans[i].offset;
-            for (uint32_t c = 0; c < plans[i].n_clauses; c++) {
-                fg_clause cl = plans[i].clauses[c];
-                cl.leaf_begin += (uint32_t)pb.l.size();
-                pb.c.push_back(cl);
-            }
-            pb.l.insert(pb.l.end(), plans[i].leaves, plans[i].leaves + plans[i].n_leaves);
+    // concatenate the per-thread parts (clause / leaf indices become global)
+    for (int t = 0; t < T; t++) {
+        Part& P = parts[t];
+        const uint32_t cb = (uint32_t)pb.c.size(), lb = (uint32_t)pb.l.size();
+        for (auto cl : P.c) { cl.leaf_begin += lb; pb.c.push_back(cl); }
+        pb.l.insert(pb.l.end(), P.l.begin(), P.l.end());
+        for (uint32_t i = P.a; i < P.b; i++) {
+            pb.q[i].clause_begin += cb;
+            pb.kmax = std::max(pb.kmax, pb.q[i].k);
+            if (pb.rc[i] != FG_OK && !pb.first_err) { pb.first_err = pb.rc[i]; pb.first_msg = P.errs[i - P.a]; }
         }
-        pb.kmax = std::max(pb.kmax, pb.q[i].k);
     }
 }
 }  // namespace

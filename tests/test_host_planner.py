@@ -140,3 +140,24 @@ def test_object_record_facets_and_clamp():
     assert perform_search({"ns": fk}, "ns", "q", [], 0, 100).per_page == 100
     with pytest.raises(KeyError):
         perform_search({}, "missing", "q", [], 0, 10)
+
+
+def test_fast_path_equals_general_parser(small):
+    """fgh_plan_batch's AST-free fast path (ASCII words, optional all-AND) == the general parser."""
+    ix, desc, ds = small
+    qs = ["red", "red apple", "RED  Apple", " red", "red AND pie", "red AND pie AND cherry", "red AND", "AND red",
+          "red OR pie", "red NOT pie", "red AND pie cherry", "red pie AND cherry", "zzz", "zzz AND red", "a" * 45,
+          "red-apple", "red_apple", "réd", "red\tpie", "red AND AND pie", "red and pie"]
+    batch, status = ds.plan_batch(qs, None, 1, 7)
+    for i, q in enumerate(qs):
+        try:
+            want = ds.plan(q, [], 1, 7).as_dict()
+        except nat.FgError as e:
+            assert status[i] == e.code, q
+            continue
+        assert status[i] == 0, q
+        got_k = int(batch.q["k"][i])
+        cb, nc = int(batch.q["clause_begin"][i]), int(batch.q["n_clauses"][i])
+        got = [(int(c["occur"]), [(int(l["field"]), int(l["term_ord"]), float(l["boost"]))
+                                   for l in batch.l[c["leaf_begin"]:c["leaf_begin"] + c["n_leaves"]]]) for c in batch.c[cb:cb + nc]]
+        assert got_k == want["k"] == 14 and got == want["clauses"], q
