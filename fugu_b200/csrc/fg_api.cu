@@ -90,6 +90,9 @@ struct fg_ctx {
     cudaStream_t stream = nullptr;
     std::mutex mu;
     int n_sms = 0;
+    // side streams + events: the per-class search kernels of one batch run concurrently
+    cudaStream_t aux[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t fork_ev = nullptr, join_ev[3] = {nullptr, nullptr, nullptr};
     // small cache of device blocks for the per-call buffers (plans, partial lists, results):
     // cudaMalloc/cudaFree per request would dominate the host side of a 5000-query batch
     std::mutex pool_mu;
@@ -147,6 +150,11 @@ extern "C" int32_t fg_ctx_create(int32_t device, fg_ctx** out) {
     c->n_sms = pr.multiProcessorCount;
     CU(cudaStreamCreateWithFlags(&c->own, cudaStreamNonBlocking));
     c->stream = c->own;
+    for (int i = 0; i < 3; i++) {
+        CU(cudaStreamCreateWithFlags(&c->aux[i], cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&c->join_ev[i], cudaEventDisableTiming));
+    }
+    CU(cudaEventCreateWithFlags(&c->fork_ev, cudaEventDisableTiming));
     *out = c;
     return FG_OK;
 }
@@ -154,6 +162,8 @@ extern "C" void fg_ctx_destroy(fg_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->own) cudaStreamDestroy(c->own);
+    for (int i = 0; i < 3; i++) { if (c->aux[i]) cudaStreamDestroy(c->aux[i]); if (c->join_ev[i]) cudaEventDestroy(c->join_ev[i]); }
+    if (c->fork_ev) cudaEventDestroy(c->fork_ev);
     for (auto& b : c->pool) cudaFree(b.first);
     delete c;
 }
@@ -454,6 +464,7 @@ struct fg_batch {
     unsigned long long* d_stats = nullptr;
     uint32_t* d_qtheta = nullptr;
     size_t sz[7] = {0, 0, 0, 0, 0, 0, 0};
+    uint32_t class_count[4] = {0, 0, 0, 0};
     uint64_t n_launches = 0;
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};  // before search, after search, after merge
 };
@@ -648,6 +659,7 @@ extern "C" int32_t fg_batch_prepare(fg_index* ix, const fg_query_batch* qb, fg_b
             it.doc_hi = (uint32_t)((uint64_t)nd * (j + 1) / ni);
             it.mode = mode;
             it.slot = D.item_begin + j;
+            it.cls = (mode == MODE_DENSE ? 0u : 2u) + ((D.flags & QF_PURE_UNION) ? 0u : 1u);
             items.push_back(it);
             item_cost.push_back(total_bytes / ni);
         }
@@ -657,9 +669,14 @@ extern "C" int32_t fg_batch_prepare(fg_index* ix, const fg_query_batch* qb, fg_b
     // heavy items first (the hardware CTA scheduler is the work queue)
     std::vector<uint32_t> order(items.size());
     for (uint32_t i = 0; i < order.size(); i++) order[i] = i;
-    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return item_cost[a] > item_cost[b]; });
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+        if (items[a].cls != items[b].cls) return items[a].cls < items[b].cls;  // one launch per kernel class
+        return item_cost[a] > item_cost[b];
+    });
     std::vector<DevItem> sorted(items.size());
     for (size_t i = 0; i < order.size(); i++) sorted[i] = items[order[i]];
+    uint32_t class_count[4] = {0, 0, 0, 0};
+    for (auto& it : items) class_count[it.cls]++;
 
     fg_ctx* ctx = ix->ctx;
     CU(cudaSetDevice(ctx->device));
@@ -670,6 +687,7 @@ extern "C" int32_t fg_batch_prepare(fg_index* ix, const fg_query_batch* qb, fg_b
     b->kcap = kmax;
     b->ks = kmax <= 32 ? 1 : 4;
     b->sum_k = sum_k;
+    for (int i = 0; i < 4; i++) b->class_count[i] = class_count[i];
     auto up = [&](const void* src, size_t bytes, void** dst, size_t* sz) -> int32_t {
         *sz = std::max<size_t>(bytes, 16);
         CU(pool_alloc(ctx, dst, *sz));
@@ -726,7 +744,19 @@ extern "C" int32_t fg_batch_execute(fg_batch* b, uint32_t flags, uint32_t k_stri
     p.qtheta = (flags & FG_EXEC_DETERMINISTIC) ? nullptr : b->d_qtheta;
     p.prof = getenv("FG_PROF") ? b->d_stats + 8 : nullptr;
     CU(cudaEventRecord(b->ev[0], st));
-    launch_search(p, b->ks, st);
+    {
+        // fork: class 0 on the main stream, classes 1..3 on side streams, join before the merge
+        void* streams[4] = {st, ctx->aux[0], ctx->aux[1], ctx->aux[2]};
+        CU(cudaEventRecord(ctx->fork_ev, st));
+        for (int i = 0; i < 3; i++)
+            if (b->class_count[i + 1]) CU(cudaStreamWaitEvent(ctx->aux[i], ctx->fork_ev, 0));
+        launch_search(p, b->ks, b->class_count, streams);
+        for (int i = 0; i < 3; i++)
+            if (b->class_count[i + 1]) {
+                CU(cudaEventRecord(ctx->join_ev[i], ctx->aux[i]));
+                CU(cudaStreamWaitEvent(st, ctx->join_ev[i], 0));
+            }
+    }
     CU(cudaEventRecord(b->ev[1], st));
     MergeParams m{};
     m.queries = b->d_queries;
@@ -744,7 +774,8 @@ extern "C" int32_t fg_batch_execute(fg_batch* b, uint32_t flags, uint32_t k_stri
     m.out_count = (uint32_t*)d_match_count;
     launch_merge(m, b->ks, st);
     CU(cudaEventRecord(b->ev[2], st));
-    b->n_launches = (b->n_items ? 1 : 0) + (b->n_queries ? 1 : 0);
+    b->n_launches = (b->n_queries ? 1 : 0);
+    for (int i = 0; i < 4; i++) b->n_launches += b->class_count[i] ? 1 : 0;
     CU(cudaGetLastError());
     return FG_OK;
 }

@@ -67,7 +67,8 @@ struct DevItem {
     uint32_t doc_lo, doc_hi;
     uint32_t mode;
     uint32_t slot;  // index into partial arrays (query.item_begin + j)
-    uint32_t pad[3];
+    uint32_t cls;   // kernel class: 0 dense pure, 1 dense masked, 2 hash pure, 3 hash masked
+    uint32_t pad[2];
 };
 
 struct DevIndex {
@@ -87,6 +88,7 @@ struct SearchParams {
     const DevLeaf* leaves;
     const DevItem* items;
     uint32_t n_items;
+    uint32_t item_begin;         // first item of this launch (items are grouped by kernel class)
     uint32_t kcap;               // entries per partial list
     uint64_t* partial;           // [n_items][kcap] sortable keys, 0 = empty
     uint32_t* partial_count;     // [n_items] matching docs
@@ -126,11 +128,11 @@ constexpr int SLOTS = DW > HS ? DW : HS;
 constexpr int CBW = 1024;        // candidate bitmap words (32768 bits; dense mode uses the first DW bits)
 constexpr int CB_LOG2 = 15;
 
-void launch_search(const SearchParams& p, int ks, void* stream);
+void launch_search(const SearchParams& p, int ks, const uint32_t class_count[4], void* const streams[4]);
 void launch_merge(const MergeParams& p, int ks, void* stream);
 void launch_merge_gathered(const void* hits, const uint32_t* n, uint32_t n_ranks, uint32_t n_queries,
                            uint32_t k, uint32_t k_stride, void* out_hits, uint32_t* out_n, int ks,
                            void* stream);
-int search_smem_bytes(int ks);
+int search_smem_bytes(int ks, bool pure);
 
 }  // namespace fg

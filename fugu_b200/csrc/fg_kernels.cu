@@ -167,7 +167,7 @@ struct Shared {
     uint32_t resume[MAX_LEAVES * NW];
     uint32_t phase_end[MAX_LEAVES];
     uint32_t segcnt[NW];
-    uint32_t rlo, rhi, shift, done;
+    uint32_t rlo, rhi, shift, done, gtheta;
     uint32_t match;
     unsigned long long st_blocks, st_redecode, st_scored;
 };
@@ -220,9 +220,13 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
     if (tid == 0) { S.match = 0; S.st_blocks = 0; S.st_redecode = 0; S.st_scored = 0; }
     __syncthreads();
 
+#ifdef FG_PROFILE_PHASES  // dev tool: per-phase cycle counters (costs registers; off in product builds)
     long long pt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long tp = clock64();
 #define PROF(i) do { if (p.prof && tid == 0) { const long long now_ = clock64(); pt[i] += now_ - tp; tp = now_; } } while (0)
+#else
+#define PROF(i) do { } while (0)
+#endif
     WarpTopK<KS> tk;
     tk.init();
     float theta_s = -INFINITY;  // score part of tk.theta (a candidate needs score >= theta_s)
@@ -259,13 +263,16 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
                 const uint32_t span = rhi - rlo;
                 int sh = span > 1 ? (32 - __clz(span - 1)) - CB_LOG2 : 0;
                 S.shift = sh > 0 ? sh : 0;
+                S.gtheta = p.qtheta ? __ldcg(p.qtheta + it.query) : 0u;
             }
         }
         __syncthreads();
         if (S.done) break;
         const uint32_t rlo = S.rlo, rhi = S.rhi, shift = S.shift;
         PROF(1);  // round setup
+#ifdef FG_PROFILE_PHASES
         if (p.prof && tid == 0) pt[7]++;
+#endif
 
         // ---- clause phases: leaves [l0, l1) share (role, bit) ----
         int l0 = 0;
@@ -485,8 +492,8 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
         {
             // score threshold shared by all work items of the query: >= k docs are known to score at
             // least this much, so anything strictly below can never reach the final top-k
-            if (p.qtheta) {
-                const uint32_t gt = __ldcg(p.qtheta + it.query);
+            {
+                const uint32_t gt = S.gtheta;
                 if (gt) theta_s = fmaxf(theta_s, unsortable(gt));
             }
             const int n4 = DENSE ? (int)((rhi - rlo + 3) >> 2) : HS / 4;
@@ -594,10 +601,12 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
         }
         if (lane == 0) {
             p.partial_count[it.slot] = S.match;
+#ifdef FG_PROFILE_PHASES
             if (p.prof) {
                 PROF(5);  // epilogue
                 for (int i = 0; i < 8; i++) atomicAdd(p.prof + i, (unsigned long long)pt[i]);
             }
+#endif
             if (p.stats) {
                 atomicAdd(p.stats + 0, S.st_blocks);
                 atomicAdd(p.stats + 1, S.st_redecode);
@@ -607,11 +616,12 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
     }
 }
 
-template <int KS, int GRP, int MINB>
+template <int KS, int GRP, int MINB, bool DENSE, bool PURE>
 __global__ void __launch_bounds__(NT, MINB) search_kernel(const SearchParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ Shared S;
     // [0, 32K)   dense: acc[DW]            | hash: acc[HS] + keys[HS]
+    // masked plans only (pure unions need neither masks nor candidate bitmaps):
     // [32K, 40K) dense: msk[DW]            | hash: msk[HS] + candidate bitmap (CBW words)
     // [40K, 41K) dense: candidate bitmap (DW bits)
     static_assert(2 * HS <= DW && HS + CBW * 4 <= DW, "hash layout must fit the dense regions");
@@ -620,21 +630,14 @@ __global__ void __launch_bounds__(NT, MINB) search_kernel(const SearchParams p) 
     uint8_t* msk = smem + DW * 4;
     uint32_t* cb_dense = reinterpret_cast<uint32_t*>(smem + DW * 4 + DW);
     uint32_t* cb_hash = reinterpret_cast<uint32_t*>(msk + HS);
-    uint32_t* wl = cb_dense + DW / 32;
+    uint32_t* wl = PURE ? reinterpret_cast<uint32_t*>(smem + DW * 4) : cb_dense + DW / 32;
     uint64_t* scratch = reinterpret_cast<uint64_t*>(wl + NW * SEG_CAP);
 
-    const DevItem it = p.items[blockIdx.x];
+    const DevItem it = p.items[p.item_begin + blockIdx.x];
     const DevQuery q = p.queries[it.query];
     if (threadIdx.x < q.n_leaves) S.leaf[threadIdx.x] = p.leaves[q.leaf_begin + threadIdx.x];
     __syncthreads();
-    const bool pure = (q.flags & QF_PURE_UNION) != 0;
-    if (it.mode == MODE_DENSE) {
-        if (pure) run_item<KS, GRP, true, true>(p, it, q, S, acc, keys, msk, cb_dense, wl, scratch);
-        else run_item<KS, GRP, true, false>(p, it, q, S, acc, keys, msk, cb_dense, wl, scratch);
-    } else {
-        if (pure) run_item<KS, GRP, false, true>(p, it, q, S, acc, keys, msk, cb_hash, wl, scratch);
-        else run_item<KS, GRP, false, false>(p, it, q, S, acc, keys, msk, cb_hash, wl, scratch);
-    }
+    run_item<KS, GRP, DENSE, PURE>(p, it, q, S, acc, keys, msk, DENSE ? cb_dense : cb_hash, wl, scratch);
 }
 
 // one warp per query: merge the per-item partial lists
@@ -742,32 +745,41 @@ __global__ void __launch_bounds__(128) merge_gathered_kernel(const uint2* hits, 
 
 }  // namespace
 
-int search_smem_bytes(int ks) {
-    return DW * 4 + DW + DW / 8 + NW * SEG_CAP * 4 + NW * ks * 32 * 8;
+int search_smem_bytes(int ks, bool pure) {
+    return DW * 4 + (pure ? 0 : DW + DW / 8) + NW * SEG_CAP * 4 + NW * ks * 32 * 8;
 }
 
-template <int KS, int GRP, int MINB>
-static void launch_search_t(const SearchParams& p, cudaStream_t st) {
+#ifndef PURE_MINB
+#define PURE_MINB 5
+#endif
+template <int KS, int GRP, int MINB, bool DENSE, bool PURE>
+static void launch_one(SearchParams p, uint32_t begin, uint32_t count, cudaStream_t st) {
+    if (!count) return;
     static bool configured = false;
-    const int smem = search_smem_bytes(KS);
+    const int smem = search_smem_bytes(KS, PURE);
     if (!configured) {
-        cudaFuncSetAttribute(search_kernel<KS, GRP, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(search_kernel<KS, GRP, MINB, DENSE, PURE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         configured = true;
     }
-    search_kernel<KS, GRP, MINB><<<p.n_items, NT, smem, st>>>(p);
+    p.item_begin = begin;
+    search_kernel<KS, GRP, MINB, DENSE, PURE><<<count, NT, smem, st>>>(p);
 }
 
-void launch_search(const SearchParams& p, int ks, void* stream) {
-    cudaStream_t st = (cudaStream_t)stream;
-    if (p.n_items == 0) return;
-    static const int variant = getenv("FG_VARIANT") ? atoi(getenv("FG_VARIANT")) : 0;
-    if (ks > 1) { launch_search_t<4, 1, 3>(p, st); return; }
-    switch (variant) {
-        case 1: launch_search_t<1, 2, 4>(p, st); break;
-        case 2: launch_search_t<1, 4, 3>(p, st); break;
-        case 4: launch_search_t<1, 1, 5>(p, st); break;
-        case 5: launch_search_t<1, 2, 3>(p, st); break;
-        default: launch_search_t<1, 1, 4>(p, st); break;
+// items are grouped by kernel class: [dense pure | dense masked | hash pure | hash masked]
+void launch_search(const SearchParams& p, int ks, const uint32_t class_count[4], void* const streams[4]) {
+    cudaStream_t s0 = (cudaStream_t)streams[0], s1 = (cudaStream_t)streams[1], s2 = (cudaStream_t)streams[2],
+                 s3 = (cudaStream_t)streams[3];
+    const uint32_t b1 = class_count[0], b2 = b1 + class_count[1], b3 = b2 + class_count[2];
+    if (ks <= 1) {
+        launch_one<1, 1, PURE_MINB, true, true>(p, 0, class_count[0], s0);
+        launch_one<1, 1, 4, true, false>(p, b1, class_count[1], s1);
+        launch_one<1, 1, PURE_MINB, false, true>(p, b2, class_count[2], s2);
+        launch_one<1, 1, 4, false, false>(p, b3, class_count[3], s3);
+    } else {
+        launch_one<4, 1, 3, true, true>(p, 0, class_count[0], s0);
+        launch_one<4, 1, 3, true, false>(p, b1, class_count[1], s1);
+        launch_one<4, 1, 3, false, true>(p, b2, class_count[2], s2);
+        launch_one<4, 1, 3, false, false>(p, b3, class_count[3], s3);
     }
 }
 
