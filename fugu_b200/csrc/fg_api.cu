@@ -509,6 +509,8 @@ extern "C" int32_t fg_batch_prepare(fg_index* ix, const fg_query_batch* qb, fg_b
         return fail(FG_ERR_INVALID, "fg_batch_prepare: NULL arrays");
     const double t_begin = now_ms();
     const uint64_t ITEM_BYTES = env_u64("FG_ITEM_BYTES", 65536);
+    const uint64_t ITEM_BYTES_HASH = env_u64("FG_ITEM_BYTES_HASH", 24576);      // pure unions in hash mode
+    const uint64_t ITEM_BYTES_MASKED = env_u64("FG_ITEM_BYTES_MASKED", 98304);  // plans with Must / MustNot clauses
     const uint64_t DENSE_MIN = env_u64("FG_DENSE_MIN", 1536);  // insert postings per dense window
     const uint64_t DENSE_MIN_MUST = env_u64("FG_DENSE_MIN_MUST", 256);  // same, plans with Must clauses
     const uint32_t HASH_MIN_SPAN = 4096;
@@ -646,10 +648,17 @@ extern "C" int32_t fg_batch_prepare(fg_index* ix, const fg_query_batch* qb, fg_b
         const uint32_t nd = ix->n_docs;
         const uint64_t dmin = must.empty() ? DENSE_MIN : DENSE_MIN_MUST;
         const uint32_t mode = (insert_postings * (uint64_t)DW >= dmin * (uint64_t)std::max<uint32_t>(nd, 1)) ? MODE_DENSE : MODE_HASH;
-        uint64_t want = std::max<uint64_t>(1, (total_bytes + ITEM_BYTES / 2) / ITEM_BYTES);
+        const uint64_t ib = !(D.flags & QF_PURE_UNION) ? ITEM_BYTES_MASKED : (mode == MODE_DENSE ? ITEM_BYTES : ITEM_BYTES_HASH);
+        uint64_t want = std::max<uint64_t>(1, (total_bytes + ib / 2) / ib);
         const uint32_t min_span = mode == MODE_DENSE ? (uint32_t)DW : HASH_MIN_SPAN;
         const uint64_t max_items = std::max<uint64_t>(1, nd / min_span);
         const uint32_t ni = (uint32_t)std::min(want, max_items);
+        if (mode == MODE_DENSE) {
+            // long insert lists get a phase of their own: a slot is then touched by one thread only
+            const uint64_t SOLO_MIN_BLOCKS = env_u64("FG_SOLO_MIN_BLOCKS", 0xFFFFFFFFull);
+            for (size_t i = D.leaf_begin; i < dl.size(); i++)
+                if (dl[i].role == ROLE_INSERT && dl[i].n_blocks >= SOLO_MIN_BLOCKS) dl[i].solo = 1;
+        }
         D.item_begin = (uint32_t)items.size();
         D.n_items = ni;
         for (uint32_t j = 0; j < ni; j++) {

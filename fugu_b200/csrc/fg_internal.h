@@ -41,7 +41,8 @@ struct DevLeaf {
     uint32_t role;
     uint32_t req;        // mask bits a slot must already carry (filter roles)
     uint32_t build_cb;   // rebuild the candidate bitmap after this leaf (mask value to test), 0 = no
-    uint32_t pad[3];
+    uint32_t solo;       // long list in a dense-mode plan: gets a phase of its own (plain adds, no atomics)
+    uint32_t pad[2];
 };
 
 constexpr uint32_t MODE_DENSE = 0, MODE_HASH = 1;

@@ -197,7 +197,8 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
         S.cur[tid] = a;
         S.cur_next[tid] = a;
         int l1 = tid + 1;  // leaves [tid, phase_end) share (role, bit) = one clause phase
-        while (!p.deterministic && l1 < nl && S.leaf[l1].role == L.role && S.leaf[l1].bit == L.bit) l1++;
+        while (!p.deterministic && !L.solo && l1 < nl && S.leaf[l1].role == L.role && S.leaf[l1].bit == L.bit &&
+               !S.leaf[l1].solo) l1++;
         S.phase_end[tid] = (uint32_t)l1;
     }
     if (!DENSE && warp == 0) {
@@ -356,6 +357,41 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
                         lf[g] = ent >> 24;
                         e[g] = val[g] ? __ldg(&skip[S.leaf[lf[g]].blk_begin + (ent & 0xFFFFFFu)])
                                       : make_uint4(0, 0, 0, 0);
+                    }
+                    // ---- fast path (the bulk of dense-mode work): one full block that lies entirely inside
+                    // the window, both widths in 1..8, a TEXT leaf of a pure union. Straight-line code, no
+                    // per-posting predicates, no masks; plain adds when the phase has a single leaf.
+                    if (GRP == 1 && DENSE && PURE && !p.acct && val[0]) {
+                        const uint4 e0 = e[0];
+                        const uint32_t bd = e0.w & 63u, bt = (e0.w >> 6) & 63u;
+                        const DevLeaf& L0 = S.leaf[lf[0]];
+                        if (((e0.w >> 12) & 127u) == 127u && e0.y >= rlo && e0.x < rhi && bd - 1u < 8u && bt < 9u &&
+                            L0.fn_field >= 0) {
+                            const uint32_t* wd = reinterpret_cast<const uint32_t*>(p.ix.blk + (size_t)e0.z * 16u);
+                            const uint32_t bit0 = (uint32_t)lane * 4u * bd, bitt = (uint32_t)lane * 4u * bt;
+                            const uint32_t* wt = wd + 4 * bd;
+                            const uint32_t a0 = __ldg(wd + (bit0 >> 5)), a1 = __ldg(wd + (bit0 >> 5) + 1);
+                            uint32_t t0 = 0, t1 = 0;
+                            if (bt) { t0 = __ldg(wt + (bitt >> 5)); t1 = __ldg(wt + (bitt >> 5) + 1); }
+                            const uint32_t xd = __funnelshift_r(a0, a1, bit0 & 31), md = (1u << bd) - 1u;
+                            const uint32_t xt = __funnelshift_r(t0, t1, bitt & 31), mt_ = (1u << bt) - 1u;
+                            const uint32_t g0 = xd & md, g1 = g0 + ((xd >> bd) & md), g2 = g1 + ((xd >> (2 * bd)) & md),
+                                           g3 = g2 + ((xd >> (3 * bd)) & md);
+                            const uint32_t base = warp_excl_scan(g3, lane) + e0.y + 4u * lane - rlo;  // slot of posting 0 minus its gap sum
+                            const uint8_t* fnp = p.ix.fnorm[L0.fn_field] + rlo;
+                            const float* cache = p.ix.cache + L0.fn_field * 256;
+                            const float wgt = L0.weight;
+                            const uint32_t s0 = base + g0, s1 = base + g1 + 1u, s2 = base + g2 + 2u, s3 = base + g3 + 3u;
+                            const float n0 = __ldg(cache + __ldg(fnp + s0)), n1 = __ldg(cache + __ldg(fnp + s1)),
+                                        n2 = __ldg(cache + __ldg(fnp + s2)), n3 = __ldg(cache + __ldg(fnp + s3));
+                            const float f0 = (float)((xt & mt_) + 1u), f1 = (float)(((xt >> bt) & mt_) + 1u),
+                                        f2 = (float)(((xt >> (2 * bt)) & mt_) + 1u), f3 = (float)(((xt >> (3 * bt)) & mt_) + 1u);
+                            const float v0 = wgt * __fdividef(f0, f0 + n0), v1 = wgt * __fdividef(f1, f1 + n1),
+                                        v2 = wgt * __fdividef(f2, f2 + n2), v3 = wgt * __fdividef(f3, f3 + n3);
+                            if (solo) { acc[s0] += v0; acc[s1] += v1; acc[s2] += v2; acc[s3] += v3; }
+                            else { smem_add_f32(&acc[s0], v0); smem_add_f32(&acc[s1], v1); smem_add_f32(&acc[s2], v2); smem_add_f32(&acc[s3], v3); }
+                            continue;
+                        }
                     }
                     uint32_t gp[GRP][4], tf[GRP][4], nn[GRP];
 #pragma unroll
