@@ -2,7 +2,11 @@
 NVCC ?= /usr/local/cuda/bin/nvcc
 CXX ?= g++
 ARCH := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS := -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC,-Wall,-Wno-unused-function -Iinclude
+PROFILE ?= 0
+ifeq ($(PROFILE),1)
+EXTRA := -DFG_PROFILE_PHASES
+endif
+NVFLAGS := $(EXTRA) -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC,-Wall,-Wno-unused-function -Iinclude
 CSRC := fugu_b200/csrc
 
 all: fugu_b200/libfugu_gpu.so fugu_b200/synth/libfugu_synth.so oracle/liboracle.so

@@ -154,10 +154,47 @@ __device__ __forceinline__ bool cb_any(const uint32_t* cb, uint32_t a, uint32_t 
     return (cb[wz] & mz) != 0;
 }
 
-__device__ __forceinline__ uint32_t hash_doc(uint32_t d) { return (d * 2654435761u) >> (32 - HS_LOG2); }
+// Bucketised open addressing: the hash picks a 16-byte bucket of 4 keys (one LDS.128), an insert
+// takes the first empty key of the bucket and moves to the next bucket only when it is full. Far
+// fewer dependent probes than per-slot linear probing (a full bucket at load 0.6 is rare).
+__device__ __forceinline__ uint32_t hash_bucket(uint32_t d) { return (d * 2654435761u) >> (32 - (HS_LOG2 - 2)); }
+
+// claim (or find) the slot of doc d; the table never fills (rounds insert <= HBLK*128 + RES_CAP docs)
+__device__ __forceinline__ int hash_insert(uint32_t* keys, uint32_t d) {
+    uint32_t h = hash_bucket(d);
+    while (true) {
+        const uint4 k = reinterpret_cast<const uint4*>(keys)[h];
+        if (k.x == d) return (int)(4 * h);
+        if (k.y == d) return (int)(4 * h + 1);
+        if (k.z == d) return (int)(4 * h + 2);
+        if (k.w == d) return (int)(4 * h + 3);
+        const int e = k.x == EMPTY ? 0 : k.y == EMPTY ? 1 : k.z == EMPTY ? 2 : k.w == EMPTY ? 3 : -1;
+        if (e >= 0) {
+            const uint32_t old = atomicCAS(&keys[4 * h + e], EMPTY, d);
+            if (old == EMPTY || old == d) return (int)(4 * h + e);
+            continue;  // somebody else took that key: look at the same bucket again
+        }
+        h = (h + 1) & (HS / 4 - 1);
+    }
+}
+// slot of doc d or -1 (a bucket with an empty key ends the search: inserts fill buckets in order)
+__device__ __forceinline__ int hash_find(const uint32_t* keys, uint32_t d) {
+    uint32_t h = hash_bucket(d);
+    while (true) {
+        const uint4 k = reinterpret_cast<const uint4*>(keys)[h];
+        if (k.x == d) return (int)(4 * h);
+        if (k.y == d) return (int)(4 * h + 1);
+        if (k.z == d) return (int)(4 * h + 2);
+        if (k.w == d) return (int)(4 * h + 3);
+        if (k.w == EMPTY) return -1;  // keys fill x, y, z, w in order
+        h = (h + 1) & (HS / 4 - 1);
+    }
+}
 
 constexpr int SEG_CAP = 128;  // worklist entries per scanning warp
 constexpr uint32_t LEAF_DONE = 0xFFFFFFFFu;
+constexpr int RES_CAP = 512;        // resident postings per work item (short lists decoded once per item)
+constexpr int RES_MAX_BLOCKS = 3;   // a leaf is resident when it has at most this many blocks in the item's range
 
 struct Shared {
     DevLeaf leaf[MAX_LEAVES];
@@ -166,6 +203,9 @@ struct Shared {
     uint32_t quota[MAX_LEAVES];
     uint32_t resume[MAX_LEAVES * NW];
     uint32_t phase_end[MAX_LEAVES];
+    uint32_t res_cnt[MAX_LEAVES];   // blocks of the leaf inside the item's doc range (init only)
+    uint32_t resident[MAX_LEAVES];
+    uint32_t res_n;
     uint32_t segcnt[NW];
     uint32_t rlo, rhi, shift, done, gtheta;
     uint32_t match;
@@ -179,7 +219,8 @@ __device__ __forceinline__ void smem_add_f32(float* p, float v) { atomicAdd(p, v
 template <int KS, int GRP, bool DENSE, bool PURE>
 __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& it, const DevQuery& q,
                                          Shared& S, float* acc, uint32_t* keys, uint8_t* msk,
-                                         uint32_t* cb, uint32_t* wl, uint64_t* scratch) {
+                                         uint32_t* cb, uint32_t* wl, uint64_t* scratch, uint32_t* res_doc,
+                                         float* res_val) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nl = (int)q.n_leaves;
     const uint4* __restrict__ skip = p.ix.skip;
@@ -200,14 +241,81 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
         while (!p.deterministic && !L.solo && l1 < nl && S.leaf[l1].role == L.role && S.leaf[l1].bit == L.bit &&
                !S.leaf[l1].solo) l1++;
         S.phase_end[tid] = (uint32_t)l1;
+        // blocks of an insert leaf that overlap the item's doc range (few => resident)
+        uint32_t cnt = 0xFFFFu;
+        if (L.role == ROLE_INSERT && !p.deterministic) {
+            uint32_t a2 = a, b2 = L.n_blocks;  // first block whose first_base >= doc_hi
+            while (a2 < b2) {
+                uint32_t m = (a2 + b2) >> 1;
+                if (__ldg(&skip[L.blk_begin + m]).y >= it.doc_hi) b2 = m; else a2 = m + 1;
+            }
+            cnt = a2 - a;
+        }
+        S.res_cnt[tid] = cnt;
     }
-    if (!DENSE && warp == 0) {
-        // share HBLK insert blocks per round among the insert leaves, proportional to list length
-        uint32_t nb = lane < (int)q.n_insert ? S.leaf[lane].n_blocks : 0;
-        uint32_t tot = warp_sum(nb);
-        if (lane < (int)q.n_insert)
-            S.quota[lane] = 1 + (uint32_t)(((unsigned long long)(HBLK - q.n_insert) * nb) / (tot ? tot : 1));
+    if (tid == 0) { S.res_n = 0; S.match = 0; S.st_blocks = 0; S.st_redecode = 0; S.st_scored = 0; }
+    __syncthreads();
+    if (warp == 0) {
+        // resident leaves: short lists are decoded ONCE per item into (doc, score) pairs and applied to
+        // every round from shared memory, instead of re-decoding their straddling blocks each round
+        const bool ins = lane < (int)q.n_insert;
+        const uint32_t c = ins ? S.res_cnt[lane] : 0xFFFFu;
+        const bool cand = c <= (uint32_t)RES_MAX_BLOCKS;
+        uint32_t pre = cand ? c * BLOCK : 0u;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(FULL, pre, o);
+            if (lane >= o) pre += y;
+        }
+        const bool res = cand && pre <= (uint32_t)RES_CAP;
+        if (lane < nl) S.resident[lane] = res ? 1u : 0u;
+        // hash mode: share HBLK insert blocks per round among the STREAMING insert leaves, by list length
+        const uint32_t nb = (ins && !res) ? S.leaf[lane].n_blocks : 0u;
+        const uint32_t tot = warp_sum(nb);
+        const uint32_t n_stream = __popc(__ballot_sync(FULL, ins && !res));
+        if (ins) S.quota[lane] = 1 + (uint32_t)(((unsigned long long)(HBLK - n_stream) * nb) / (tot ? tot : 1));
     }
+    __syncthreads();
+    for (int l = 0; l < (int)q.n_insert; l++) {
+        if (!S.resident[l]) continue;
+        const DevLeaf& L = S.leaf[l];
+        const uint32_t b0 = S.cur[l], b1 = b0 + S.res_cnt[l];
+        for (uint32_t bb = b0 + warp; bb < b1; bb += NW) {
+            const uint4 e = __ldg(&skip[L.blk_begin + bb]);
+            const uint32_t bd = e.w & 63u, bt = (e.w >> 6) & 63u, n = ((e.w >> 12) & 127u) + 1u;
+            const uint32_t* wd = reinterpret_cast<const uint32_t*>(p.ix.blk + (size_t)e.z * 16u);
+            uint32_t g[4], t[4];
+            unpack4(wd, lane, bd, g);
+            unpack4(wd + 4 * bd, lane, bt, t);
+            g[1] += g[0]; g[2] += g[1]; g[3] += g[2];
+            const uint32_t off = warp_excl_scan(g[3], lane) + e.y + 4u * lane;
+            uint32_t scored_here = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint32_t d = off + g[j] + j;
+                const bool ok = 4u * lane + j < n && d >= it.doc_lo && d < it.doc_hi;
+                const unsigned m = __ballot_sync(FULL, ok);
+                uint32_t pos = 0;
+                if (lane == 0 && m) pos = atomicAdd(&S.res_n, (uint32_t)__popc(m));
+                pos = __shfl_sync(FULL, pos, 0) + __popc(m & ((1u << lane) - 1u));
+                if (ok) {
+                    float norm = L.cnorm;
+                    if (L.fn_field >= 0) norm = __ldg(p.ix.cache + L.fn_field * 256 + __ldg(p.ix.fnorm[L.fn_field] + d));
+                    const float tf = (float)(t[j] + 1u);
+                    res_doc[pos] = d;
+                    res_val[pos] = L.weight * __fdividef(tf, tf + norm);
+                }
+                scored_here += __popc(m);
+            }
+            if (p.acct && lane == 0) {
+                const unsigned long long by = ((n * bd + 7) >> 3) + ((n * bt + 7) >> 3) + 16;
+                if (e.y >= it.doc_lo) atomicAdd(&S.st_blocks, by); else atomicAdd(&S.st_redecode, by);
+                atomicAdd(&S.st_scored, (unsigned long long)scored_here);
+            }
+        }
+    }
+    __syncthreads();
+    if (tid < (int)q.n_insert && S.resident[tid]) { S.cur[tid] = S.leaf[tid].n_blocks; S.cur_next[tid] = S.leaf[tid].n_blocks; }
     {
         float4* a4 = reinterpret_cast<float4*>(acc);
         for (int i = tid; i < (DENSE ? DW : HS) / 4; i += NT) a4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -218,7 +326,6 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
         if (!PURE)
             for (int i = tid; i < (DENSE ? DW : HS) / 4; i += NT) reinterpret_cast<uint32_t*>(msk)[i] = 0;
     }
-    if (tid == 0) { S.match = 0; S.st_blocks = 0; S.st_redecode = 0; S.st_scored = 0; }
     __syncthreads();
 
 #ifdef FG_PROFILE_PHASES  // dev tool: per-phase cycle counters (costs registers; off in product builds)
@@ -252,6 +359,10 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
                     }
                 }
             }
+            for (uint32_t i = lane; i < S.res_n; i += 32) {  // next resident posting at or after lo
+                const uint32_t d = res_doc[i];
+                if (d >= lo) fb = min(fb, d);
+            }
             fb = warp_min(fb);
             chi = warp_min(chi);
             if (lane == 0) {
@@ -271,6 +382,18 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
         if (S.done) break;
         const uint32_t rlo = S.rlo, rhi = S.rhi, shift = S.shift;
         PROF(1);  // round setup
+        if (S.res_n) {  // resident postings of this round (uniform branch)
+            const uint32_t rbit = S.leaf[0].bit;
+            for (uint32_t i = tid; i < S.res_n; i += NT) {
+                const uint32_t d = res_doc[i];
+                if (d >= rlo && d < rhi) {
+                    const int sl = DENSE ? (int)(d - rlo) : hash_insert(keys, d);
+                    smem_add_f32(&acc[sl], res_val[i]);
+                    if (!PURE && rbit) msk[sl] = (uint8_t)(msk[sl] | rbit);
+                }
+            }
+            __syncthreads();
+        }
 #ifdef FG_PROFILE_PHASES
         if (p.prof && tid == 0) pt[7]++;
 #endif
@@ -432,17 +555,7 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
                                         if ((m & req) != req || (role == ROLE_NOT && m == 0)) sl = -1;
                                     }
                                 } else if (!filter || ((cb[((d - rlo) >> shift) >> 5] >> (((d - rlo) >> shift) & 31)) & 1u)) {
-                                    uint32_t h = hash_doc(d);
-                                    while (true) {
-                                        uint32_t kd = keys[h];
-                                        if (kd == d) { sl = (int)h; break; }
-                                        if (kd == EMPTY) {
-                                            if (filter) break;
-                                            kd = atomicCAS(&keys[h], EMPTY, d);
-                                            if (kd == EMPTY || kd == d) { sl = (int)h; break; }
-                                        }
-                                        h = (h + 1) & (HS - 1);
-                                    }
+                                    sl = filter ? hash_find(keys, d) : hash_insert(keys, d);
                                     if (!PURE && sl >= 0 && filter && (msk[sl] & req) != req) sl = -1;
                                 }
                             }
@@ -673,7 +786,9 @@ __global__ void __launch_bounds__(NT, MINB) search_kernel(const SearchParams p) 
     const DevQuery q = p.queries[it.query];
     if (threadIdx.x < q.n_leaves) S.leaf[threadIdx.x] = p.leaves[q.leaf_begin + threadIdx.x];
     __syncthreads();
-    run_item<KS, GRP, DENSE, PURE>(p, it, q, S, acc, keys, msk, DENSE ? cb_dense : cb_hash, wl, scratch);
+    uint32_t* res_doc = reinterpret_cast<uint32_t*>(scratch + NW * KS * 32);
+    float* res_val = reinterpret_cast<float*>(res_doc + RES_CAP);
+    run_item<KS, GRP, DENSE, PURE>(p, it, q, S, acc, keys, msk, DENSE ? cb_dense : cb_hash, wl, scratch, res_doc, res_val);
 }
 
 // one warp per query: merge the per-item partial lists
@@ -782,7 +897,7 @@ __global__ void __launch_bounds__(128) merge_gathered_kernel(const uint2* hits, 
 }  // namespace
 
 int search_smem_bytes(int ks, bool pure) {
-    return DW * 4 + (pure ? 0 : DW + DW / 8) + NW * SEG_CAP * 4 + NW * ks * 32 * 8;
+    return DW * 4 + (pure ? 0 : DW + DW / 8) + NW * SEG_CAP * 4 + NW * ks * 32 * 8 + RES_CAP * 8;
 }
 
 #ifndef PURE_MINB
