@@ -749,6 +749,7 @@ extern "C" int32_t fg_batch_execute(fg_batch* b, uint32_t flags, uint32_t k_stri
     p.bitmap_words = (ix->n_docs + 31) / 32;
     p.exact_filter = (flags & FG_EXEC_EXACT_ACCOUNTING) ? 1 : 0;
     p.deterministic = (flags & FG_EXEC_DETERMINISTIC) ? 1 : 0;
+    p.want_counts = d_match_count ? 1 : 0;
     p.acct = (flags & (FG_EXEC_EXACT_ACCOUNTING | FG_EXEC_COUNTERS)) ? 1 : 0;
     p.qtheta = (flags & FG_EXEC_DETERMINISTIC) ? nullptr : b->d_qtheta;
     p.prof = getenv("FG_PROF") ? b->d_stats + 8 : nullptr;

@@ -98,6 +98,7 @@ struct SearchParams {
     uint32_t bitmap_words;
     uint32_t exact_filter;
     uint32_t deterministic;     // one phase per leaf: bit-reproducible sums in leaf order
+    uint32_t want_counts;       // the caller asked for match counts (the reference's TopDocs does not)
     uint32_t acct;              // maintain the byte / scored-posting counters
     unsigned long long* prof;   // optional [8] cycle counters (dev tool)
     uint32_t* qtheta;           // [n_queries] sortable f32: score every work item may prune below (0 = none)

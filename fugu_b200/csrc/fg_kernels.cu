@@ -650,6 +650,32 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
             float4* a4 = reinterpret_cast<float4*>(acc);
             uint4* k4 = reinterpret_cast<uint4*>(keys);
             const bool generic = !PURE || p.ix.alive != nullptr || p.match_bitmap != nullptr;
+            if (DENSE && PURE && !generic) {
+                // tight loop for the bulk case (pure union, dense window, no deletes): a touched slot has
+                // a positive score and matches; only slots that can enter the top-k take the slow path
+                const bool count = p.want_counts != 0;
+                for (int g0 = warp * 32; g0 < n4; g0 += NT) {
+                    const int g = g0 + lane;
+                    float4 av = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (g < n4) { av = a4[g]; a4[g] = make_float4(0.f, 0.f, 0.f, 0.f); }
+                    if (count) my_matches += (av.x > 0.f) + (av.y > 0.f) + (av.z > 0.f) + (av.w > 0.f);
+                    const float mx = fmaxf(fmaxf(av.x, av.y), fmaxf(av.z, av.w));
+                    if (__any_sync(FULL, mx > 0.f && mx + q.const_score >= theta_s)) {
+                        const float raw[4] = {av.x, av.y, av.z, av.w};
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            const float sc = raw[j] + q.const_score;
+                            const bool c = raw[j] > 0.f && sc >= theta_s;
+                            tk.offer(c, c ? make_key(sc, rlo + 4 * g + j) : 0ull, k, lane);
+                        }
+                        const float mine = tk.theta ? unsortable((uint32_t)(tk.theta >> 32)) : -INFINITY;
+                        if (mine > theta_s) {
+                            theta_s = mine;
+                            if (p.qtheta && lane == 0) atomicMax(p.qtheta + it.query, sortable(mine));
+                        }
+                    }
+                }
+            } else
             for (int g0 = warp * 32; g0 < n4; g0 += NT) {
                 const int g = g0 + lane;
                 float4 av = make_float4(0.f, 0.f, 0.f, 0.f);
