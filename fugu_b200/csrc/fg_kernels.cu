@@ -516,6 +516,61 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
                             continue;
                         }
                     }
+                    // ---- filter fast path (non-lead Must / Should-under-Must / MustNot blocks): only doc ids
+                    // are unpacked for the whole block; a posting survives only if it hits a candidate slot
+                    // (mask test / candidate bitmap + bucket lookup), and only survivors fetch their tf,
+                    // fieldnorm and score. In an intersection ~1 posting in 128 survives.
+                    if (GRP == 1 && !PURE && filter && val[0]) {
+                        const uint4 e0 = e[0];
+                        const uint32_t bd = e0.w & 63u, bt = (e0.w >> 6) & 63u, n = ((e0.w >> 12) & 127u) + 1u;
+                        const DevLeaf& L0 = S.leaf[lf[0]];
+                        const uint32_t* wd = reinterpret_cast<const uint32_t*>(p.ix.blk + (size_t)e0.z * 16u);
+                        const uint32_t* wt = wd + 4 * bd;
+                        uint32_t gg[4];
+                        unpack4(wd, lane, bd, gg);
+                        gg[1] += gg[0]; gg[2] += gg[1]; gg[3] += gg[2];
+                        const uint32_t off = warp_excl_scan(gg[3], lane) + e0.y + 4u * lane;
+                        if (p.acct && lane == 0) {
+                            const unsigned long long by = ((n * bd + 7) >> 3) + ((n * bt + 7) >> 3) + 16;
+                            if (e0.y >= lo) my_blocks += by; else my_redecode += by;
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            const uint32_t d = off + gg[j] + j, idx = 4u * lane + j;
+                            int sl = -1;
+                            if (idx < n && d >= rlo && d < rhi) {
+                                if (DENSE) {
+                                    sl = (int)(d - rlo);
+                                    const uint32_t m = msk[sl];
+                                    if ((m & req) != req || (role == ROLE_NOT && m == 0)) sl = -1;
+                                } else if ((cb[((d - rlo) >> shift) >> 5] >> (((d - rlo) >> shift) & 31)) & 1u) {
+                                    sl = hash_find(keys, d);
+                                    if (sl >= 0 && (msk[sl] & req) != req) sl = -1;
+                                }
+                            }
+                            if (sl >= 0) {
+                                if (role == ROLE_NOT) {
+                                    msk[sl] = (uint8_t)(msk[sl] | BIT_NOT);
+                                } else {
+                                    uint32_t tfv = 0;
+                                    if (bt) {
+                                        const uint32_t bp = idx * bt;
+                                        const uint32_t w0 = __ldg(wt + (bp >> 5)), w1 = __ldg(wt + (bp >> 5) + 1);
+                                        tfv = __funnelshift_r(w0, w1, bp & 31) & (bt >= 32 ? 0xFFFFFFFFu : ((1u << bt) - 1u));
+                                    }
+                                    float norm = L0.cnorm;
+                                    if (L0.fn_field >= 0)
+                                        norm = __ldg(p.ix.cache + L0.fn_field * 256 + __ldg(p.ix.fnorm[L0.fn_field] + d));
+                                    const float t = (float)(tfv + 1u);
+                                    const float v = L0.weight * __fdividef(t, t + norm);
+                                    if (solo) acc[sl] += v; else smem_add_f32(&acc[sl], v);
+                                    if (bit) msk[sl] = (uint8_t)(msk[sl] | bit);
+                                    if (p.acct) my_scored++;
+                                }
+                            }
+                        }
+                        continue;
+                    }
                     uint32_t gp[GRP][4], tf[GRP][4], nn[GRP];
 #pragma unroll
                     for (int g = 0; g < GRP; g++) {
