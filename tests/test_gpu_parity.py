@@ -236,3 +236,52 @@ def test_edge_cases(ctx):
             index.search(nat.HostBatch([{"k": k, "clauses": [(S, [T(0)])]}]))
         assert e.value.code == code
     index.close()
+
+
+def test_config5_facet_filters(ctx):
+    """Config 5 shape at 60k docs: 2-term OR text + 1-2 facet filters (Must group, OR inside) over
+    namespace/organization/data facets with ancestor terms (src/object.rs:81-111), planned by the
+    C++ host layer from query + filter strings."""
+    from fugu_b200.dataset import Dataset
+    from oracle import orc
+    from tests.util import check_topk, gpu_search_device
+
+    cfg = synth.Config(cfg=5, n_docs=60_000, vocab=5_000, n_queries=300, k=10, n_ns=64)
+    corpus = synth.Corpus.for_config(cfg)
+    fields = synth.build_fields(corpus, 0, cfg.n_docs)
+    assert len(fields) == 3
+    desc = nat.HostIndexDesc(cfg.n_docs, fields)
+    ds = Dataset(ctx)
+    words = [f"w{i + 1}" for i in range(cfg.vocab)]
+    ds.adopt(desc, [words, [], [corpus.facet_path(i) for i in range(corpus.facet_vocab())]])
+    qs = synth.gen_queries(cfg)
+    batch, status = ds.plan_batch([q["query"] for q in qs], [q["filters"] for q in qs], 0, 10)
+    assert (status == 0).all()
+    o_hits, o_n, o_c = orc.search(desc, batch, threads=4)
+    g_hits, g_n, g_c, _, _ = gpu_search_device(ds.index(), batch)
+    assert np.array_equal(g_c, o_c) and np.array_equal(g_n, o_n)
+    assert (o_c > 0).sum() > 100  # the filters actually select documents
+    for qi in range(batch.n_queries):
+        check_topk(g_hits[qi, :g_n[qi]], o_hits[qi, :o_n[qi]], k=10, ctx=f"query {qi}: {qs[qi]}")
+    # and through the string API, page 1
+    h, nh, cnt, st = ds.search_batch([q["query"] for q in qs[:50]], [q["filters"] for q in qs[:50]], 1, 5)
+    assert (st == 0).all() and np.array_equal(cnt, o_c[:50])
+    ds.close()
+
+
+def test_config4_three_term_and_with_deletes(ctx):
+    """Config 4 shape (3-term AND) at 150k docs with 5% of the docs deleted (alive bitset)."""
+    from tests.util import check_batch_against_oracle
+
+    cfg = synth.Config(cfg=4, n_docs=150_000, vocab=20_000, n_queries=300, k=10)
+    corpus = synth.Corpus.for_config(cfg)
+    fields = synth.build_fields(corpus, 0, cfg.n_docs)
+    rng = np.random.default_rng(3)
+    alive = np.full((cfg.n_docs + 31) // 32, 0xFFFFFFFF, np.uint32)
+    for d in rng.choice(cfg.n_docs, cfg.n_docs // 20, replace=False):
+        alive[d >> 5] &= ~np.uint32(1 << (d & 31))
+    desc = nat.HostIndexDesc(cfg.n_docs, fields, alive_bitset=alive)
+    index = nat.Index(ctx, desc)
+    batch = plan_queries(synth.gen_queries(cfg), vocab=cfg.vocab, n_text_fields=1)
+    check_batch_against_oracle(index, desc, batch)
+    index.close()
