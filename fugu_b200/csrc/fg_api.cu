@@ -493,14 +493,6 @@ extern "C" void fg_batch_release(fg_batch* b) {
     delete b;
 }
 
-namespace {
-struct LClause {
-    uint32_t occur;
-    uint64_t cost;  // bytes (work estimate)
-    uint64_t df;    // sum of local doc freqs = tantivy's scorer cost (Intersection order)
-    std::vector<DevLeaf> leaves;
-};
-}  // namespace
 
 extern "C" int32_t fg_batch_prepare(fg_index* ix, const fg_query_batch* qb, fg_batch** out) {
     if (!ix || !qb || !out) return fail(FG_ERR_INVALID, "fg_batch_prepare: NULL argument");
@@ -523,6 +515,16 @@ extern "C" int32_t fg_batch_prepare(fg_index* ix, const fg_query_batch* qb, fg_b
     uint64_t sum_k = 0;
     const uint64_t N = ix->global_n_docs;
 
+    const uint64_t SOLO_MIN_BLOCKS = env_u64("FG_SOLO_MIN_BLOCKS", 0xFFFFFFFFull);
+    // per-query scratch (fixed arrays: the lowering of a 5000-query batch must not allocate per query)
+    constexpr int MAXC = 32, MAXT = 64;
+    struct CRec { uint32_t occur, begin, count; uint64_t cost, df; };
+    CRec crec[MAXC];
+    DevLeaf tmp[MAXT];
+    dl.reserve((size_t)qb->n_leaves);
+    items.reserve((size_t)qb->n_queries * 4);
+    item_cost.reserve((size_t)qb->n_queries * 4);
+
     for (uint32_t qi = 0; qi < qb->n_queries; qi++) {
         const fg_query& q = qb->queries[qi];
         if (q.k == 0) return fail(FG_ERR_INVALID, "query %u: k == 0 (TopDocs::with_limit requires limit >= 1)", qi);
@@ -531,19 +533,17 @@ extern "C" int32_t fg_batch_prepare(fg_index* ix, const fg_query_batch* qb, fg_b
             return fail(FG_ERR_INVALID, "query %u: clause range out of bounds", qi);
         kmax = std::max(kmax, q.k);
         sum_k += q.k;
-        std::vector<LClause> must, should, mnot;
+        int nc = 0, nt = 0;          // live clauses / leaves of this query
+        int must_idx[MAXC], n_must = 0, n_should = 0, n_not = 0;
         float const_score = 0.f;
-        bool empty = false;   // a Must clause that can never match
+        bool empty = false;          // a Must clause that can never match
         bool has_all_only = false;
         for (uint32_t ci = 0; ci < q.n_clauses; ci++) {
             const fg_clause& c = qb->clauses[q.clause_begin + ci];
             if ((uint64_t)c.leaf_begin + c.n_leaves > qb->n_leaves)
                 return fail(FG_ERR_INVALID, "query %u: leaf range out of bounds", qi);
             if (c.occur > FG_OCCUR_MUST_NOT) return fail(FG_ERR_INVALID, "query %u: bad occur", qi);
-            LClause lc;
-            lc.occur = c.occur;
-            lc.cost = 0;
-            lc.df = 0;
+            CRec cr{c.occur, (uint32_t)nt, 0, 0, 0};
             bool all = false;
             float all_boost = 0.f;
             for (uint32_t li = 0; li < c.n_leaves; li++) {
@@ -554,112 +554,116 @@ extern "C" int32_t fg_batch_prepare(fg_index* ix, const fg_query_batch* qb, fg_b
                 const HostField& hf = ix->fields[lf.field];
                 if (lf.term_ord >= hf.n_terms) return fail(FG_ERR_INVALID, "query %u: term_ord out of range", qi);
                 const TermInfo& ti = hf.terms[lf.term_ord];
-                if (ti.df_global == 0) continue;  // empty scorer
-                DevLeaf L{};
+                if (ti.df_global == 0 || ti.n_blocks == 0) continue;  // empty scorer (globally, or in this shard)
+                if (nt >= MAXT) return fail(FG_ERR_UNSUPPORTED, "query %u: too many leaves", qi);
+                DevLeaf& L = tmp[nt++];
+                memset(&L, 0, sizeof(L));
                 L.blk_begin = ti.blk_begin;
                 L.n_blocks = ti.n_blocks;
                 L.weight = lf.boost * (fg_bm25_idf(ti.df_global, N) * (1.0f + K1));
                 L.cnorm = hf.cnorm;
                 L.fn_field = (hf.flags & FG_FIELD_HAS_FIELDNORMS) ? (int32_t)lf.field : -1;
-                if (ti.n_blocks == 0) continue;  // present globally, absent in this shard
-                lc.cost += ti.bytes;
-                lc.df += ti.df_local;
-                lc.leaves.push_back(L);
+                cr.cost += ti.bytes;
+                cr.df += ti.df_local;
+                cr.count++;
             }
             if (all) {
-                if (c.occur == FG_OCCUR_MUST && lc.leaves.empty()) { const_score += all_boost; has_all_only = true; continue; }
+                if (c.occur == FG_OCCUR_MUST && cr.count == 0) { const_score += all_boost; has_all_only = true; continue; }
                 return fail(FG_ERR_UNSUPPORTED, "query %u: AllQuery leaf outside a Must clause is not supported", qi);
             }
-            if (lc.leaves.empty()) {
+            if (cr.count == 0) {
                 if (c.occur == FG_OCCUR_MUST) empty = true;
                 continue;
             }
-            (c.occur == FG_OCCUR_MUST ? must : c.occur == FG_OCCUR_SHOULD ? should : mnot).push_back(std::move(lc));
+            if (nc >= MAXC) return fail(FG_ERR_UNSUPPORTED, "query %u: too many clauses", qi);
+            if (c.occur == FG_OCCUR_MUST) must_idx[n_must++] = nc;
+            else if (c.occur == FG_OCCUR_SHOULD) n_should++;
+            else n_not++;
+            crec[nc++] = cr;
         }
         DevQuery& D = dq[qi];
         memset(&D, 0, sizeof(D));
         D.k = q.k;
         D.const_score = const_score;
         D.leaf_begin = (uint32_t)dl.size();
-        if (has_all_only && must.empty() && !empty) {
-            if (should.empty() && mnot.empty()) {  // pure AllQuery: every alive doc, score = boost
+        D.item_begin = (uint32_t)items.size();
+        if (has_all_only && n_must == 0 && !empty) {
+            if (n_should == 0 && n_not == 0) {  // pure AllQuery: every alive doc, score = boost
                 D.flags |= QF_ALL;
-                D.n_leaves = 0; D.n_items = 0; D.item_begin = (uint32_t)items.size();
                 continue;
             }
             return fail(FG_ERR_UNSUPPORTED, "query %u: AllQuery Must with only Should/MustNot siblings not supported", qi);
         }
-        if (empty || (must.empty() && should.empty())) { D.n_leaves = 0; D.n_items = 0; D.item_begin = (uint32_t)items.size(); continue; }
-        if (must.size() > (size_t)MAX_MUST) return fail(FG_ERR_UNSUPPORTED, "query %u: more than %d Must clauses", qi, MAX_MUST);
-        std::stable_sort(must.begin(), must.end(), [](const LClause& a, const LClause& b) { return a.df < b.df; });
-
-        std::vector<DevLeaf> ql;
+        if (empty || (n_must == 0 && n_should == 0)) continue;
+        if (n_must > MAX_MUST) return fail(FG_ERR_UNSUPPORTED, "query %u: more than %d Must clauses", qi, MAX_MUST);
+        // Must clauses by ascending Sum(df) = tantivy's Intersection order (stable insertion sort)
+        for (int i = 1; i < n_must; i++) {
+            const int x = must_idx[i];
+            int j = i - 1;
+            while (j >= 0 && crec[must_idx[j]].df > crec[x].df) { must_idx[j + 1] = must_idx[j]; j--; }
+            must_idx[j + 1] = x;
+        }
+        const size_t ql0 = dl.size();
         uint64_t insert_postings = 0, total_bytes = 0;
-        auto leaf_df = [&](const DevLeaf& L) { return (uint64_t)L.n_blocks * BLOCK; };
-        if (!must.empty()) {
-            D.all_must = (1u << must.size()) - 1u;
-            for (size_t ci = 0; ci < must.size(); ci++) {
-                for (size_t li = 0; li < must[ci].leaves.size(); li++) {
-                    DevLeaf L = must[ci].leaves[li];
-                    L.bit = 1u << ci;
-                    L.role = ci == 0 ? ROLE_INSERT : ROLE_MUST;
-                    L.req = (1u << ci) - 1u;
-                    if (ci == 0) insert_postings += leaf_df(L);
-                    ql.push_back(L);
-                }
-                total_bytes += must[ci].cost;
+        auto emit = [&](const CRec& cr, uint32_t bit, uint32_t role, uint32_t req, bool ins) {
+            for (uint32_t i = 0; i < cr.count; i++) {
+                DevLeaf L = tmp[cr.begin + i];
+                L.bit = bit; L.role = role; L.req = req;
+                if (ins) insert_postings += (uint64_t)L.n_blocks * BLOCK;
+                dl.push_back(L);
             }
-            D.n_insert = (uint32_t)must[0].leaves.size();
-            for (auto& c : should)
-                for (auto L : c.leaves) { L.bit = 0; L.role = ROLE_SHOULD; L.req = D.all_must; ql.push_back(L); }
-            for (auto& c : should) total_bytes += c.cost / 4;
+        };
+        if (n_must) {
+            D.all_must = (1u << n_must) - 1u;
+            for (int ci = 0; ci < n_must; ci++) {
+                const CRec& cr = crec[must_idx[ci]];
+                emit(cr, 1u << ci, ci == 0 ? ROLE_INSERT : ROLE_MUST, (1u << ci) - 1u, ci == 0);
+                total_bytes += cr.cost;
+            }
+            D.n_insert = crec[must_idx[0]].count;
+            for (int i = 0; i < nc; i++)
+                if (crec[i].occur == FG_OCCUR_SHOULD) { emit(crec[i], 0, ROLE_SHOULD, D.all_must, false); total_bytes += crec[i].cost / 4; }
         } else {
             D.all_must = BIT_SHOULD;
             D.flags |= QF_NO_MUST;
-            for (auto& c : should) {
-                for (auto L : c.leaves) { L.bit = BIT_SHOULD; L.role = ROLE_INSERT; L.req = 0; insert_postings += leaf_df(L); ql.push_back(L); }
-                total_bytes += c.cost;
-            }
-            D.n_insert = (uint32_t)ql.size();
+            for (int i = 0; i < nc; i++)
+                if (crec[i].occur == FG_OCCUR_SHOULD) { emit(crec[i], BIT_SHOULD, ROLE_INSERT, 0, true); total_bytes += crec[i].cost; }
+            D.n_insert = (uint32_t)(dl.size() - ql0);
             bool positive = true;
-            for (auto& L : ql) positive = positive && L.weight > 0.f;
-            if (mnot.empty() && positive) D.flags |= QF_PURE_UNION;
+            for (size_t i = ql0; i < dl.size(); i++) positive = positive && dl[i].weight > 0.f;
+            if (n_not == 0 && positive) D.flags |= QF_PURE_UNION;
         }
-        for (auto& c : mnot) {
-            for (auto L : c.leaves) { L.bit = BIT_NOT; L.role = ROLE_NOT; L.req = 0; ql.push_back(L); }
-            total_bytes += c.cost / 4;
-        }
-        if (ql.size() > (size_t)MAX_LEAVES)
-            return fail(FG_ERR_UNSUPPORTED, "query %u: %zu live leaves > %d", qi, ql.size(), MAX_LEAVES);
+        for (int i = 0; i < nc; i++)
+            if (crec[i].occur == FG_OCCUR_MUST_NOT) { emit(crec[i], BIT_NOT, ROLE_NOT, 0, false); total_bytes += crec[i].cost / 4; }
+        const size_t nql = dl.size() - ql0;
+        if (nql > (size_t)MAX_LEAVES)
+            return fail(FG_ERR_UNSUPPORTED, "query %u: %zu live leaves > %d", qi, nql, MAX_LEAVES);
         // candidate-bitmap rebuild points: after the last leaf of a clause when the next leaf filters
-        for (size_t i = 0; i + 1 < ql.size(); i++) {
-            const DevLeaf& nx = ql[i + 1];
+        for (size_t i = ql0; i + 1 < dl.size(); i++) {
+            const DevLeaf& nx = dl[i + 1];
             if (nx.role == ROLE_INSERT) continue;
-            const bool boundary = ql[i].role != nx.role || ql[i].bit != nx.bit;
+            const bool boundary = dl[i].role != nx.role || dl[i].bit != nx.bit;
             if (!boundary) continue;
-            if (ql[i].role == ROLE_SHOULD) continue;  // bitmap of all-Must candidates is still valid
+            if (dl[i].role == ROLE_SHOULD) continue;  // bitmap of all-Must candidates is still valid
             // mask the NEXT leaf's docs must carry (MustNot filters on the matching candidates)
-            ql[i].build_cb = nx.role == ROLE_NOT ? D.all_must : nx.req;
+            dl[i].build_cb = nx.role == ROLE_NOT ? D.all_must : nx.req;
         }
-        D.n_leaves = (uint32_t)ql.size();
-        for (auto& L : ql) dl.push_back(L);
+        D.n_leaves = (uint32_t)nql;
 
         // ---- mode + work items ----
         const uint32_t nd = ix->n_docs;
-        const uint64_t dmin = must.empty() ? DENSE_MIN : DENSE_MIN_MUST;
+        const uint64_t dmin = n_must ? DENSE_MIN_MUST : DENSE_MIN;
         const uint32_t mode = (insert_postings * (uint64_t)DW >= dmin * (uint64_t)std::max<uint32_t>(nd, 1)) ? MODE_DENSE : MODE_HASH;
         const uint64_t ib = !(D.flags & QF_PURE_UNION) ? ITEM_BYTES_MASKED : (mode == MODE_DENSE ? ITEM_BYTES : ITEM_BYTES_HASH);
         uint64_t want = std::max<uint64_t>(1, (total_bytes + ib / 2) / ib);
         const uint32_t min_span = mode == MODE_DENSE ? (uint32_t)DW : HASH_MIN_SPAN;
         const uint64_t max_items = std::max<uint64_t>(1, nd / min_span);
         const uint32_t ni = (uint32_t)std::min(want, max_items);
-        if (mode == MODE_DENSE) {
+        if (mode == MODE_DENSE && SOLO_MIN_BLOCKS != 0xFFFFFFFFull) {
             // long insert lists get a phase of their own: a slot is then touched by one thread only
-            const uint64_t SOLO_MIN_BLOCKS = env_u64("FG_SOLO_MIN_BLOCKS", 0xFFFFFFFFull);
-            for (size_t i = D.leaf_begin; i < dl.size(); i++)
+            for (size_t i = ql0; i < dl.size(); i++)
                 if (dl[i].role == ROLE_INSERT && dl[i].n_blocks >= SOLO_MIN_BLOCKS) dl[i].solo = 1;
         }
-        D.item_begin = (uint32_t)items.size();
         D.n_items = ni;
         for (uint32_t j = 0; j < ni; j++) {
             DevItem it{};
@@ -675,15 +679,22 @@ extern "C" int32_t fg_batch_prepare(fg_index* ix, const fg_query_batch* qb, fg_b
     }
 
     const double t_lower = now_ms();
-    // heavy items first (the hardware CTA scheduler is the work queue)
-    std::vector<uint32_t> order(items.size());
-    for (uint32_t i = 0; i < order.size(); i++) order[i] = i;
-    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
-        if (items[a].cls != items[b].cls) return items[a].cls < items[b].cls;  // one launch per kernel class
-        return item_cost[a] > item_cost[b];
-    });
+    // one launch per kernel class, heavy items first inside a class (the hardware CTA scheduler is
+    // the work queue): counting sort on (class, 64 half-octave cost buckets), O(n)
     std::vector<DevItem> sorted(items.size());
-    for (size_t i = 0; i < order.size(); i++) sorted[i] = items[order[i]];
+    {
+        auto bucket = [&](size_t i) -> uint32_t {
+            const uint64_t c = item_cost[i] >> 8;  // 256-byte granules
+            const uint32_t lg = c ? 63u - (uint32_t)__builtin_clzll(c) : 0u;
+            const uint32_t sub = (lg && ((c >> (lg - 1)) & 1u)) ? 1u : 0u;
+            const uint32_t bk = std::min<uint32_t>(63u, lg * 2u + sub);
+            return items[i].cls * 64u + (63u - bk);
+        };
+        uint32_t hist[257] = {0};
+        for (size_t i = 0; i < items.size(); i++) hist[bucket(i) + 1]++;
+        for (int i = 0; i < 256; i++) hist[i + 1] += hist[i];
+        for (size_t i = 0; i < items.size(); i++) sorted[hist[bucket(i)]++] = items[i];
+    }
     uint32_t class_count[4] = {0, 0, 0, 0};
     for (auto& it : items) class_count[it.cls]++;
 
