@@ -146,6 +146,16 @@ def term_lists(corpus, cfg, n_fields):
     return terms
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the search kernels of one step, from the
+    committed `ncu --set full` capture of this command (profiles/r01_traffic.json), or None."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        return json.load(open(p))["dram_bytes_per_step"]
+    except Exception:
+        return None
+
+
 def peak_hbm():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -366,7 +376,8 @@ def main():
         "config": workload_config(cfg, args, world),
         "posting_gbs": algo_total / (ms_per_step * 1e-3) / 1e9,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "kernel": "search_kernel",
+                     "traffic": ncu_traffic(), "peak_source": peak_src,
+                     "kernel": "search_kernel (4 class instantiations dense/hash x pure/masked, launched concurrently; timed as one group)",
                      "kernel_ms": kms, "algorithmic_bytes_per_launch": int(algo_bytes),
                      "bytes_per_query": algo_bytes / nq,
                      "touched_block_bytes": int(st_touched.bytes_blocks), "redecode_bytes": int(st_touched.bytes_redecode),
