@@ -500,10 +500,10 @@ extern "C" int32_t fg_batch_prepare(fg_index* ix, const fg_query_batch* qb, fg_b
     if (qb->n_queries && (!qb->queries || (qb->n_clauses && !qb->clauses) || (qb->n_leaves && !qb->leaves)))
         return fail(FG_ERR_INVALID, "fg_batch_prepare: NULL arrays");
     const double t_begin = now_ms();
-    const uint64_t ITEM_BYTES = env_u64("FG_ITEM_BYTES", 65536);
+    const uint64_t ITEM_BYTES = env_u64("FG_ITEM_BYTES", 131072);
     const uint64_t ITEM_BYTES_HASH = env_u64("FG_ITEM_BYTES_HASH", 24576);      // pure unions in hash mode
     const uint64_t ITEM_BYTES_MASKED = env_u64("FG_ITEM_BYTES_MASKED", 98304);  // plans with Must / MustNot clauses
-    const uint64_t DENSE_MIN = env_u64("FG_DENSE_MIN", 1536);  // insert postings per dense window
+    const uint64_t DENSE_MIN = env_u64("FG_DENSE_MIN", 1024);  // insert postings per dense window
     const uint64_t DENSE_MIN_MUST = env_u64("FG_DENSE_MIN_MUST", 256);  // same, plans with Must clauses
     const uint32_t HASH_MIN_SPAN = 4096;
 
@@ -528,7 +528,7 @@ extern "C" int32_t fg_batch_prepare(fg_index* ix, const fg_query_batch* qb, fg_b
     for (uint32_t qi = 0; qi < qb->n_queries; qi++) {
         const fg_query& q = qb->queries[qi];
         if (q.k == 0) return fail(FG_ERR_INVALID, "query %u: k == 0 (TopDocs::with_limit requires limit >= 1)", qi);
-        if (q.k > 128) return fail(FG_ERR_UNSUPPORTED, "query %u: k = %u > 128 not supported yet", qi, q.k);
+        if (q.k > 1024) return fail(FG_ERR_UNSUPPORTED, "query %u: k = %u > 1024 not supported", qi, q.k);
         if ((uint64_t)q.clause_begin + q.n_clauses > qb->n_clauses)
             return fail(FG_ERR_INVALID, "query %u: clause range out of bounds", qi);
         kmax = std::max(kmax, q.k);
@@ -705,7 +705,7 @@ extern "C" int32_t fg_batch_prepare(fg_index* ix, const fg_query_batch* qb, fg_b
     b->n_queries = qb->n_queries;
     b->n_items = (uint32_t)items.size();
     b->kcap = kmax;
-    b->ks = kmax <= 32 ? 1 : 4;
+    b->ks = kmax <= 32 ? 1 : kmax <= 128 ? 4 : 32;
     b->sum_k = sum_k;
     for (int i = 0; i < 4; i++) b->class_count[i] = class_count[i];
     auto up = [&](const void* src, size_t bytes, void** dst, size_t* sz) -> int32_t {
@@ -874,11 +874,11 @@ extern "C" int32_t fg_merge_topk_device(fg_ctx* ctx, const void* d_hits, const v
                                         uint32_t n_ranks, uint32_t n_queries, uint32_t k,
                                         uint32_t k_stride, void* d_out_hits, void* d_out_n) {
     if (!ctx || !d_hits || !d_n || !d_out_hits || !d_out_n) return fail(FG_ERR_INVALID, "NULL argument");
-    if (k == 0 || k > 128 || k > k_stride) return fail(FG_ERR_INVALID, "k must be in [1, min(128, k_stride)]");
+    if (k == 0 || k > 1024 || k > k_stride) return fail(FG_ERR_INVALID, "k must be in [1, min(1024, k_stride)]");
     CU(cudaSetDevice(ctx->device));
     std::lock_guard<std::mutex> g(ctx->mu);
     launch_merge_gathered(d_hits, (const uint32_t*)d_n, n_ranks, n_queries, k, k_stride, d_out_hits,
-                          (uint32_t*)d_out_n, k <= 32 ? 1 : 4, ctx->stream);
+                          (uint32_t*)d_out_n, k <= 32 ? 1 : k <= 128 ? 4 : 32, ctx->stream);
     CU(cudaGetLastError());
     return FG_OK;
 }

@@ -1007,11 +1007,16 @@ void launch_search(const SearchParams& p, int ks, const uint32_t class_count[4],
         launch_one<1, 1, 4, true, false>(p, b1, class_count[1], s1);
         launch_one<1, 1, PURE_MINB, false, true>(p, b2, class_count[2], s2);
         launch_one<1, 1, 4, false, false>(p, b3, class_count[3], s3);
-    } else {
+    } else if (ks <= 4) {
         launch_one<4, 1, 3, true, true>(p, 0, class_count[0], s0);
         launch_one<4, 1, 3, true, false>(p, b1, class_count[1], s1);
         launch_one<4, 1, 3, false, true>(p, b2, class_count[2], s2);
         launch_one<4, 1, 3, false, false>(p, b3, class_count[3], s3);
+    } else {  // k up to 1024: 32 queue rows per lane (slow path: deep pagination only)
+        launch_one<32, 1, 1, true, true>(p, 0, class_count[0], s0);
+        launch_one<32, 1, 1, true, false>(p, b1, class_count[1], s1);
+        launch_one<32, 1, 1, false, true>(p, b2, class_count[2], s2);
+        launch_one<32, 1, 1, false, false>(p, b3, class_count[3], s3);
     }
 }
 
@@ -1020,7 +1025,8 @@ void launch_merge(const MergeParams& p, int ks, void* stream) {
     if (p.n_queries == 0) return;
     const unsigned grid = (p.n_queries + 3) / 4;
     if (ks <= 1) merge_kernel<1><<<grid, 128, 0, st>>>(p);
-    else merge_kernel<4><<<grid, 128, 0, st>>>(p);
+    else if (ks <= 4) merge_kernel<4><<<grid, 128, 0, st>>>(p);
+    else merge_kernel<32><<<grid, 128, 0, st>>>(p);
 }
 
 void launch_merge_gathered(const void* hits, const uint32_t* n, uint32_t n_ranks, uint32_t n_queries,
@@ -1032,9 +1038,12 @@ void launch_merge_gathered(const void* hits, const uint32_t* n, uint32_t n_ranks
     if (ks <= 1)
         merge_gathered_kernel<1><<<grid, 128, 0, st>>>((const uint2*)hits, n, n_ranks, n_queries, k,
                                                        k_stride, (uint2*)out_hits, out_n);
-    else
+    else if (ks <= 4)
         merge_gathered_kernel<4><<<grid, 128, 0, st>>>((const uint2*)hits, n, n_ranks, n_queries, k,
                                                        k_stride, (uint2*)out_hits, out_n);
+    else
+        merge_gathered_kernel<32><<<grid, 128, 0, st>>>((const uint2*)hits, n, n_ranks, n_queries, k,
+                                                        k_stride, (uint2*)out_hits, out_n);
 }
 
 }  // namespace fg

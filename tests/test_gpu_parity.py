@@ -230,8 +230,8 @@ def test_edge_cases(ctx):
     # empty batch
     h, n, c = index.search(nat.HostBatch([]))
     assert len(n) == 0
-    # k == 0 is an error (TopDocs::with_limit asserts), k > 128 unsupported for now
-    for k, code in ((0, nat.FG_ERR_INVALID), (129, nat.FG_ERR_UNSUPPORTED)):
+    # k == 0 is an error (TopDocs::with_limit asserts), k > 1024 is not supported
+    for k, code in ((0, nat.FG_ERR_INVALID), (1025, nat.FG_ERR_UNSUPPORTED)):
         with pytest.raises(nat.FgError) as e:
             index.search(nat.HostBatch([{"k": k, "clauses": [(S, [T(0)])]}]))
         assert e.value.code == code
@@ -284,4 +284,16 @@ def test_config4_three_term_and_with_deletes(ctx):
     index = nat.Index(ctx, desc)
     batch = plan_queries(synth.gen_queries(cfg), vocab=cfg.vocab, n_text_fields=1)
     check_batch_against_oracle(index, desc, batch)
+    index.close()
+
+
+def test_deep_pagination_k_up_to_1024(ctx):
+    """limit = page*per_page + per_page beyond 128 (32-row register queue): k = 300 and k = 1000."""
+    cfg = synth.Config(cfg=2, n_docs=30_000, vocab=5_000, n_queries=40, k=10, name_pct=10)
+    corpus, desc, index = _setup(ctx, cfg)
+    qs = synth.gen_queries(cfg)
+    for i, q in enumerate(qs):
+        q["k"] = 300 if i % 2 else 1000
+    batch = plan_queries(qs, vocab=cfg.vocab, n_text_fields=2)
+    check_batch_against_oracle(index, desc, batch, bitmaps=False)
     index.close()

@@ -19,9 +19,12 @@ for l in dis.split("\n"):
     if m and fn: funcs[fn].append((line, m.group(2)))
 name = [f for f in funcs if sub in f][0]
 ins = funcs[name]
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+skip = os.environ.get("LAUNCH_SKIP", "0")
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--launch-skip", skip, "--launch-count", "1"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.split("\n")))
 hdr = rows[1]; data = [r for r in rows[2:] if len(r) == len(hdr)]
+if len(data) > len(ins):  # several kernels in the page: keep the rows of the requested one
+    data = data[:len(ins)]
 assert len(data) == len(ins), (len(data), len(ins))
 iex = hdr.index('Instructions Executed'); smp = hdr.index('# Samples')
 cols = {k: hdr.index(k) for k in ['stall_barrier', 'stall_long_sb', 'stall_short_sb', 'stall_wait', 'stall_branch_resolving', 'stall_not_selected', 'stall_math', 'stall_mio', 'stall_lg']}
