@@ -210,12 +210,16 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+QUERY_SHAPES = {1: "two-term AND queries", 2: "mixed 1-4-term AND/OR queries", 3: "OR queries of 2-6 of the 64 most frequent terms",
+                4: "3-term AND queries", 5: "2-term OR queries with 1-2 facet filters"}
+
+
 def workload_config(cfg, args, world):
     return {"workload": f"C{cfg.cfg}: {cfg.n_docs}-doc synthetic Zipfian corpus (vocab {cfg.vocab}, {cfg.name_pct}% docs with name), "
-                        f"{cfg.n_queries} mixed 1-4-term AND/OR queries, top-{cfg.k}",
+                        f"{cfg.n_queries} {QUERY_SHAPES.get(cfg.cfg, 'queries')}, top-{cfg.k}",
             "n_docs": cfg.n_docs, "n_queries": cfg.n_queries, "k": cfg.k,
             "sharding": f"doc-id range x{world}" if world > 1 else "single shard",
-            "l2": "index fits L2 (126 MB): L2 flushed (256 MiB memset) before every timed step" if not args.no_flush else "warm L2 (no flush)"}
+            "l2": "L2 flushed (256 MiB memset) before every timed step" if not args.no_flush else "warm L2 (no flush)"}
 
 
 def main():
@@ -381,7 +385,8 @@ def main():
                      "kernel_ms": kms, "algorithmic_bytes_per_launch": int(algo_bytes),
                      "bytes_per_query": algo_bytes / nq,
                      "touched_block_bytes": int(st_touched.bytes_blocks), "redecode_bytes": int(st_touched.bytes_redecode),
-                     "note": "index (%.0f MB) fits the 126 MB L2; L2 is flushed before each timed step" % (info.device_bytes / 1e6)},
+                     "note": "index snapshot is %.0f MB in HBM (L2 is 126 MB); L2 is flushed before each timed step; "
+                             "traffic = ncu dram bytes of the C2 step (profiles/r01_traffic.json)" % (info.device_bytes / 1e6)},
         "e2e": {"value": nq / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": int(lowered_bytes),
                 "d2h_bytes_per_step": int(out_bytes), "ms_per_step": e2e_s * 1e3,
                 "what": "fgh_search_batch: query strings (host) -> C++ planner -> plan lowering -> H2D plan -> kernels -> D2H hits (host)"},
