@@ -404,7 +404,9 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
             const int l1 = (int)S.phase_end[l0];
             const uint32_t role = S.leaf[l0].role, bit = S.leaf[l0].bit, req = S.leaf[l0].req;
             const bool filter = role != ROLE_INSERT;
-            const bool solo = (l1 - l0) == 1;  // one leaf in the phase: a slot is touched by one thread only
+            int n_stream = 0;  // leaves of the phase that still stream blocks (resident ones were applied above)
+            for (int l = l0; l < l1; l++) n_stream += S.resident[l] ? 0 : 1;
+            const bool solo = n_stream <= 1;  // one streaming leaf: a slot is touched by one thread only
             for (int i = tid; i < (l1 - l0) * NW; i += NT) {
                 const int l = l0 + i / NW, w = i % NW;
                 const uint32_t c0 = (uint32_t)((w - l) & (NW - 1));  // this warp's first chunk of leaf l

@@ -297,3 +297,50 @@ def test_deep_pagination_k_up_to_1024(ctx):
     batch = plan_queries(qs, vocab=cfg.vocab, n_text_fields=2)
     check_batch_against_oracle(index, desc, batch, bitmaps=False)
     index.close()
+
+
+def test_concurrent_callers_share_one_index(ctx):
+    """The ABI is thread-safe and re-entrant (axum handlers call Dataset::search concurrently,
+    src/server/server_main.rs:50): 8 host threads hammer one snapshot; every result equals the
+    single-threaded answer."""
+    import threading
+
+    from fugu_b200.dataset import Dataset
+
+    cfg = synth.Config(cfg=2, n_docs=40_000, vocab=8_000, n_queries=240, k=10, name_pct=10)
+    corpus = synth.Corpus.for_config(cfg)
+    desc = nat.HostIndexDesc(cfg.n_docs, synth.build_fields(corpus, 0, cfg.n_docs))
+    ds = Dataset(ctx)
+    words = [f"w{i + 1}" for i in range(cfg.vocab)]
+    ds.adopt(desc, [words, words])
+    qs = [q["query"] for q in synth.gen_queries(cfg)]
+    want = ds.search_batch(qs, None, 0, 10)
+    errors = []
+
+    def worker(t):
+        try:
+            for rep in range(3):
+                part = qs[t::8]
+                h, n, c, st = ds.search_batch(part, None, 0, 10)
+                assert (st == 0).all()
+                assert np.array_equal(c, want[2][t::8]) and np.array_equal(n, want[1][t::8])
+                for i in range(len(part)):
+                    check_topk_local(h[i, :n[i]], want[0][t::8][i, :n[i]])
+                # single-request form as well
+                r = ds.search(part[0], [], 0, 10)
+                assert len(r) == int(n[0])
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    from tests.util import check_topk
+
+    def check_topk_local(a, b):
+        check_topk(a, b, k=10, ctx="concurrent")
+
+    th = [threading.Thread(target=worker, args=(t,)) for t in range(8)]
+    for x in th:
+        x.start()
+    for x in th:
+        x.join()
+    assert not errors, errors[:3]
+    ds.close()
