@@ -207,6 +207,7 @@ struct Shared {
     uint32_t resident[MAX_LEAVES];
     uint32_t res_n;
     uint32_t segcnt[NW];
+    uint32_t leafmask;  // leaves with at least one needed block in the current scan pass
     uint32_t rlo, rhi, shift, done, gtheta;
     uint32_t match;
     unsigned long long st_blocks, st_redecode, st_scored;
@@ -404,9 +405,6 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
             const int l1 = (int)S.phase_end[l0];
             const uint32_t role = S.leaf[l0].role, bit = S.leaf[l0].bit, req = S.leaf[l0].req;
             const bool filter = role != ROLE_INSERT;
-            int n_stream = 0;  // leaves of the phase that still stream blocks (resident ones were applied above)
-            for (int l = l0; l < l1; l++) n_stream += S.resident[l] ? 0 : 1;
-            const bool solo = n_stream <= 1;  // one streaming leaf: a slot is touched by one thread only
             for (int i = tid; i < (l1 - l0) * NW; i += NT) {
                 const int l = l0 + i / NW, w = i % NW;
                 const uint32_t c0 = (uint32_t)((w - l) & (NW - 1));  // this warp's first chunk of leaf l
@@ -416,6 +414,7 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
                                            ? S.cur[l] + c0 * 32u : LEAF_DONE;
             }
             while (true) {
+                if (tid == 0) S.leafmask = 0;
                 __syncthreads();
                 int my_pending = 0;
                 // (a) skip-entry scan: every warp takes 32-entry chunks warp, warp+NW, ... of each leaf
@@ -457,6 +456,7 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
                             break;
                         }
                         if (needed) wl[warp * SEG_CAP + cnt + __popc(nm & lt_mask)] = ((uint32_t)l << 24) | bi;
+                        if (lane == 0 && nm) atomicOr(&S.leafmask, 1u << l);
                         cnt += __popc(nm);
                         if (lane == 0 && ncons) atomicMax(&S.cur_next[l], b + ncons);
                         if (nin < 32) { if (lane == 0) S.resume[l * NW + warp] = LEAF_DONE; break; }
@@ -466,6 +466,9 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
                 if (lane == 0) S.segcnt[warp] = cnt;
                 __syncthreads();
                 PROF(2);  // skip scan
+                // only one leaf has blocks in this pass (typical: the other leaves of the clause are short or
+                // resident): a slot is then touched by one thread only -> plain adds instead of CAS-loop atomics
+                const bool solo = __popc(S.leafmask) <= 1;
                 // (b) decode GRP blocks per warp step
                 for (int sg = 0; sg < NW; sg++) {
                 const uint32_t total = S.segcnt[sg];
