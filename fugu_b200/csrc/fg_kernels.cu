@@ -55,7 +55,7 @@ struct WarpTopK {
         for (int s = 0; s < KS; s++) q[s] = 0;
         theta = 0;
     }
-    __device__ __forceinline__ void insert(uint64_t c, int k, int lane) {
+    __device__ __forceinline__ void insert_body(uint64_t c, int k, int lane) {
         int pos = 0;
 #pragma unroll
         for (int s = 0; s < KS; s++) pos += __popc(__ballot_sync(FULL, q[s] > c));
@@ -76,6 +76,12 @@ struct WarpTopK {
             if (s == ((k - 1) >> 5)) t = v;
         }
         theta = t;
+    }
+    // KS = 32 (deep pagination) would inline 32-row shifts at every offer() site (1.4 MB of SASS per
+    // kernel, minutes of compile time): call it out of line there; the hot KS <= 4 variants inline it
+    __device__ __noinline__ void insert_call(uint64_t c, int k, int lane) { insert_body(c, k, lane); }
+    __device__ __forceinline__ void insert(uint64_t c, int k, int lane) {
+        if (KS > 4) insert_call(c, k, lane); else insert_body(c, k, lane);
     }
     // warp-collective: every lane may bring one candidate
     __device__ __forceinline__ void offer(bool valid, uint64_t key, int k, int lane) {
