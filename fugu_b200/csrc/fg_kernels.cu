@@ -197,9 +197,11 @@ __device__ __forceinline__ int hash_find(const uint32_t* keys, uint32_t d) {
     }
 }
 
+constexpr int RES_CAP_ = 512;
+static_assert(MAX_LEAVES * BLOCK + RES_CAP_ <= HS * 5 / 8, "hash rounds must never fill the table");
 constexpr int SEG_CAP = 128;  // worklist entries per scanning warp
 constexpr uint32_t LEAF_DONE = 0xFFFFFFFFu;
-constexpr int RES_CAP = 512;        // resident postings per work item (short lists decoded once per item)
+constexpr int RES_CAP = RES_CAP_;        // resident postings per work item (short lists decoded once per item)
 constexpr int RES_MAX_BLOCKS = 3;   // a leaf is resident when it has at most this many blocks in the item's range
 
 struct Shared {
@@ -280,7 +282,10 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
         const uint32_t nb = (ins && !res) ? S.leaf[lane].n_blocks : 0u;
         const uint32_t tot = warp_sum(nb);
         const uint32_t n_stream = __popc(__ballot_sync(FULL, ins && !res));
-        if (ins) S.quota[lane] = 1 + (uint32_t)(((unsigned long long)(HBLK - n_stream) * nb) / (tot ? tot : 1));
+        // every streaming leaf gets at least one block; more than HBLK leaves still fit the table
+        // (MAX_LEAVES * 128 + RES_CAP <= HS * 5 / 8)
+        const uint32_t extra = n_stream < (uint32_t)HBLK ? (uint32_t)HBLK - n_stream : 0u;
+        if (ins) S.quota[lane] = 1 + (uint32_t)(((unsigned long long)extra * nb) / (tot ? tot : 1));
     }
     __syncthreads();
     for (int l = 0; l < (int)q.n_insert; l++) {

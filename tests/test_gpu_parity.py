@@ -344,3 +344,17 @@ def test_concurrent_callers_share_one_index(ctx):
         x.join()
     assert not errors, errors[:3]
     ds.close()
+
+
+def test_many_leaf_union_in_hash_mode(ctx):
+    """8-word OR over two fields = 16 sparse insert leaves (more leaves than hash-round block quota)."""
+    cfg = synth.Config(cfg=2, n_docs=60_000, vocab=30_000, n_queries=1, k=10, name_pct=30)
+    corpus, desc, index = _setup(ctx, cfg)
+    rng = np.random.default_rng(9)
+    qs = [{"query": " ".join(f"w{int(r)}" for r in rng.choice(np.arange(200, 3000), 8, replace=False)), "filters": [], "k": 10}
+          for _ in range(40)]
+    qs += [{"query": " ".join(f"w{int(r)}" for r in rng.choice(np.arange(1, 40), 8, replace=False)), "filters": [], "k": 10}
+           for _ in range(10)]
+    batch = plan_queries(qs, vocab=cfg.vocab, n_text_fields=2)
+    check_batch_against_oracle(index, desc, batch)
+    index.close()
