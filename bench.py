@@ -84,7 +84,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -301,14 +301,20 @@ def main():
     pb.execute(d_hits.data_ptr(), d_n.data_ptr(), d_c.data_ptr(), None, k_stride=k, flags=nat.FG_EXEC_COUNTERS)
     st_touched = pb.stats()
 
-    for _ in range(args.warmup):
-        step()
-    torch.cuda.synchronize()
-    if dist:
-        dist.barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        step()
+    # keep the GPU under the same load for ~0.5 s so that nvidia-smi (>= 50 ms period) sees the clocks
+    # the timed steps run at; these extra steps are untimed warm-up
+    t_hold = time.perf_counter() + 0.5
+    while time.perf_counter() < t_hold:
+        step()
+        torch.cuda.synchronize()
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     kern_ms = []
     torch.cuda.synchronize()

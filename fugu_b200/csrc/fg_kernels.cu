@@ -356,9 +356,10 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
     unsigned long long my_blocks = 0, my_redecode = 0;
     PROF(0);  // item init
 
-    while (true) {
-        // ---- round setup ----
-        if (warp == 0) {
+    // Round setup, run by warp 0 only: next round's doc range + the scan resume points of phase 0.
+    // For rounds after the first it runs inside the previous round's slot scan (its global loads
+    // overlap the scan), so a round needs no setup barrier of its own.
+    auto round_setup = [&](uint32_t lo_) {
             uint32_t fb = EMPTY, chi = end;
             if (lane < (int)q.n_insert) {
                 const DevLeaf& L = S.leaf[lane];
@@ -373,12 +374,12 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
             }
             for (uint32_t i = lane; i < S.res_n; i += 32) {  // next resident posting at or after lo
                 const uint32_t d = res_doc[i];
-                if (d >= lo) fb = min(fb, d);
+                if (d >= lo_) fb = min(fb, d);
             }
             fb = warp_min(fb);
             chi = warp_min(chi);
             if (lane == 0) {
-                uint32_t rlo = fb == EMPTY ? end : max(lo, fb);
+                uint32_t rlo = fb == EMPTY ? end : max(lo_, fb);
                 uint32_t rhi = DENSE ? (uint32_t)min((unsigned long long)rlo + DW, (unsigned long long)end) : chi;
                 S.done = rlo >= end;
                 if (rhi < rlo) rhi = rlo;
@@ -389,7 +390,23 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
                 S.shift = sh > 0 ? sh : 0;
                 S.gtheta = p.qtheta ? __ldcg(p.qtheta + it.query) : 0u;
             }
-        }
+            // scan resume points of phase 0 (insert leaves), see the phase loop
+            {
+                const int pl1 = (int)S.phase_end[0];
+                for (int i = lane; i < pl1 * NW; i += 32) {
+                    const int l = i / NW, w = i % NW;
+                    const uint32_t c0 = (uint32_t)((w - l) & (NW - 1));
+                    const uint32_t maxb = S.leaf[l].role != ROLE_INSERT ? 0xFFFFFFFFu
+                                          : (DENSE ? (uint32_t)(DW / BLOCK + 2) : S.quota[l]);
+                    S.resume[l * NW + w] = (c0 * 32u < maxb && S.cur[l] + c0 * 32u < S.leaf[l].n_blocks)
+                                               ? S.cur[l] + c0 * 32u : LEAF_DONE;
+                }
+                if (lane == 0) S.leafmask = 0;
+            }
+    };
+    if (warp == 0) round_setup(lo);
+
+    while (true) {
         __syncthreads();
         if (S.done) break;
         const uint32_t rlo = S.rlo, rhi = S.rhi, shift = S.shift;
@@ -416,17 +433,23 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
             const int l1 = (int)S.phase_end[l0];
             const uint32_t role = S.leaf[l0].role, bit = S.leaf[l0].bit, req = S.leaf[l0].req;
             const bool filter = role != ROLE_INSERT;
-            for (int i = tid; i < (l1 - l0) * NW; i += NT) {
-                const int l = l0 + i / NW, w = i % NW;
-                const uint32_t c0 = (uint32_t)((w - l) & (NW - 1));  // this warp's first chunk of leaf l
-                // insert leaves touch a bounded number of blocks per round: warps beyond it sit out
-                const uint32_t maxb = filter ? 0xFFFFFFFFu : (DENSE ? (uint32_t)(DW / BLOCK + 2) : S.quota[l]);
-                S.resume[l * NW + w] = (c0 * 32u < maxb && S.cur[l] + c0 * 32u < S.leaf[l].n_blocks)
-                                           ? S.cur[l] + c0 * 32u : LEAF_DONE;
+            bool prepared = l0 == 0;  // phase 0's first pass was prepared by round_setup (no barrier needed)
+            if (!prepared) {
+                for (int i = tid; i < (l1 - l0) * NW; i += NT) {
+                    const int l = l0 + i / NW, w = i % NW;
+                    const uint32_t c0 = (uint32_t)((w - l) & (NW - 1));  // this warp's first chunk of leaf l
+                    // insert leaves touch a bounded number of blocks per round: warps beyond it sit out
+                    const uint32_t maxb = filter ? 0xFFFFFFFFu : (DENSE ? (uint32_t)(DW / BLOCK + 2) : S.quota[l]);
+                    S.resume[l * NW + w] = (c0 * 32u < maxb && S.cur[l] + c0 * 32u < S.leaf[l].n_blocks)
+                                               ? S.cur[l] + c0 * 32u : LEAF_DONE;
+                }
             }
             while (true) {
-                if (tid == 0) S.leafmask = 0;
-                __syncthreads();
+                if (!prepared) {
+                    if (tid == 0) S.leafmask = 0;
+                    __syncthreads();
+                }
+                prepared = false;
                 int my_pending = 0;
                 // (a) skip-entry scan: every warp takes 32-entry chunks warp, warp+NW, ... of each leaf
                 //     and appends the needed blocks to its private worklist segment
@@ -708,6 +731,12 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
             l0 = l1;
         }
 
+        // warp 0 advances the leaf cursors and prepares the next round while the others already scan
+        if (warp == 0) {
+            if (lane < nl) S.cur[lane] = max(S.cur[lane], S.cur_next[lane]);
+            __syncwarp();
+            round_setup(rhi);
+        }
         // ---- slot scan: match test, cheap f32 pre-test against the k-th score, reset ----
         {
             // score threshold shared by all work items of the query: >= k docs are known to score at
@@ -814,9 +843,7 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
             }
         }
 
-        if (tid < nl) S.cur[tid] = max(S.cur[tid], S.cur_next[tid]);
-        lo = rhi;
-        __syncthreads();
+        lo = rhi;  // (the barrier that ends the round is the one at the top of the loop)
         PROF(4);  // slot scan
     }
 
