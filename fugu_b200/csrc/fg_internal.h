@@ -125,7 +125,7 @@ constexpr int NW = NT / 32;      // warps per CTA
 constexpr int DW = 8192;         // dense window: docs per round
 constexpr int HS_LOG2 = 12;
 constexpr int HS = 1 << HS_LOG2; // hash slots per round
-constexpr int HBLK = 12;         // insert-leaf blocks per hash round (<= HS/2/128)
+constexpr int HBLK = 16;         // insert-leaf blocks per hash round (<= HS/2/128)
 constexpr int SLOTS = DW > HS ? DW : HS;
 constexpr int CBW = 1024;        // candidate bitmap words (32768 bits; dense mode uses the first DW bits)
 constexpr int CB_LOG2 = 15;
