@@ -324,9 +324,8 @@ def main():
         ev[i][0].record(stream)
         step()
         ev[i][1].record(stream)
-        if i % 4 == 3 or i == args.steps - 1:
-            s2 = pb.stats()  # synchronises; per-launch search-kernel time from the library's own events
-            kern_ms.append(s2.search_kernel_ms)
+        s2 = pb.stats()  # synchronises; per-launch search-kernel time from the library's own CUDA events
+        kern_ms.append(s2.search_kernel_ms)
     torch.cuda.synchronize()
     if dist:
         dist.barrier()
