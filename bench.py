@@ -293,11 +293,15 @@ def main():
             dist.all_gather_into_tensor(g_n, d_n)
             nat.merge_topk_device(ctx, g_hits.data_ptr(), g_n.data_ptr(), world, nq, k, k, f_hits.data_ptr(), f_n.data_ptr())
 
-    # exact algorithmic-byte accounting pass (untimed)
-    pb.execute(d_hits.data_ptr(), d_n.data_ptr(), d_c.data_ptr(), None, k_stride=k, flags=nat.FG_EXEC_EXACT_ACCOUNTING)
-    st = pb.stats()
+    # exact algorithmic-byte accounting pass (untimed). SURVEY.md 8(d) states the algorithmic bytes on
+    # the posting-block layout, so this pass lowers the plan WITHOUT dense tf columns (every leaf decoded
+    # from its blocks); the timed batch `pb` uses the columns.
+    pb_blocks = index.prepare(batch, nat.FG_PREP_NO_COLUMNS)
+    pb_blocks.execute(d_hits.data_ptr(), d_n.data_ptr(), d_c.data_ptr(), None, k_stride=k, flags=nat.FG_EXEC_EXACT_ACCOUNTING)
+    st = pb_blocks.stats()
     algo_bytes = st.bytes_blocks + st.scored_postings + 8 * st.sum_k
-    # touched bytes of the normal (coarse-filter) execution, counters on (untimed)
+    pb_blocks.close()
+    # touched block bytes of the normal execution (columns on, coarse filter), counters on (untimed)
     pb.execute(d_hits.data_ptr(), d_n.data_ptr(), d_c.data_ptr(), None, k_stride=k, flags=nat.FG_EXEC_COUNTERS)
     st_touched = pb.stats()
 
@@ -367,7 +371,7 @@ def main():
         t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    lowered_bytes = nq * 48 + len(batch.l) * 48 + st.n_work_items * 32
+    lowered_bytes = nq * 48 + len(batch.l) * 64 + st_touched.n_work_items * 32
     out_bytes = nq * k * 8 + nq * 8
 
     if rank != 0:
@@ -398,7 +402,8 @@ def main():
         "gpu_launches": int(st_timed.n_launches + (1 if world > 1 else 0)) * args.steps,
         "clocks": clocks,
         "index": {"postings": int(info.n_postings), "blocks": int(info.n_blocks), "packed_bytes": int(info.packed_bytes),
-                  "device_bytes": int(info.device_bytes), "upload_s": upload_s, "work_items": int(st.n_work_items)},
+                  "device_bytes": int(info.device_bytes), "upload_s": upload_s, "work_items": int(st_touched.n_work_items),
+                  "tf_columns": int(info.n_columns), "tf_column_bytes": int(info.column_bytes)},
     }
     if not args.no_cpu_baseline:
         from oracle import orc  # cpu_baseline leg: the one place bench.py may run the oracle (as the measured CPU arm)

@@ -30,6 +30,7 @@ FG_TERM_ALL = 0xFFFFFFFE
 FG_EXEC_EXACT_ACCOUNTING = 1
 FG_EXEC_DETERMINISTIC = 2
 FG_EXEC_COUNTERS = 4
+FG_PREP_NO_COLUMNS = 1
 
 
 class FgError(RuntimeError):
@@ -72,6 +73,9 @@ class IndexInfo(C.Structure):
         ("device_bytes", C.c_uint64),
         ("n_docs", C.c_uint32),
         ("n_fields", C.c_uint32),
+        ("column_bytes", C.c_uint64),
+        ("n_columns", C.c_uint32),
+        ("reserved", C.c_uint32),
     ]
 
 
@@ -111,7 +115,7 @@ HIT_DT = np.dtype([("score", "<f4"), ("doc", "<u4")])
 ABI_SYMBOLS = [
     "fg_last_error", "fg_version", "fg_ctx_create", "fg_ctx_destroy", "fg_ctx_set_stream",
     "fg_ctx_synchronize", "fg_index_upload", "fg_index_release", "fg_index_get_info",
-    "fg_index_term_info", "fg_search_batch", "fg_batch_prepare", "fg_batch_release",
+    "fg_index_term_info", "fg_search_batch", "fg_batch_prepare", "fg_batch_prepare_ex", "fg_batch_release",
     "fg_batch_execute", "fg_batch_get_stats", "fg_merge_topk_device", "fg_fieldnorm_to_id",
     "fg_id_to_fieldnorm", "fg_bm25_idf",
 ]
@@ -144,6 +148,7 @@ def lib() -> C.CDLL:
     L.fg_index_term_info.argtypes = [vp, u32, u32, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32), C.POINTER(u64)]
     L.fg_search_batch.argtypes = [vp, C.POINTER(QueryBatch), u32, vp, vp, vp]
     L.fg_batch_prepare.argtypes = [vp, C.POINTER(QueryBatch), C.POINTER(vp)]
+    L.fg_batch_prepare_ex.argtypes = [vp, C.POINTER(QueryBatch), u32, C.POINTER(vp)]
     L.fg_batch_release.argtypes = [vp]
     L.fg_batch_release.restype = None
     L.fg_batch_execute.argtypes = [vp, u32, u32, vp, vp, vp, vp]
@@ -291,8 +296,8 @@ class Index:
         check(lib().fg_search_batch(self.h, C.byref(batch.batch), ks, _ptr(hits), _ptr(n), _ptr(cnt)))
         return hits, n, cnt
 
-    def prepare(self, batch: HostBatch) -> "PreparedBatch":
-        return PreparedBatch(self, batch)
+    def prepare(self, batch: HostBatch, prep_flags: int = 0) -> "PreparedBatch":
+        return PreparedBatch(self, batch, prep_flags)
 
     def close(self) -> None:
         if self.h:
@@ -301,12 +306,12 @@ class Index:
 
 
 class PreparedBatch:
-    def __init__(self, index: Index, batch: HostBatch):
+    def __init__(self, index: Index, batch: HostBatch, prep_flags: int = 0):
         self.index = index
         self.h = C.c_void_p()
         self.n_queries = batch.n_queries
         self.kmax = batch.kmax
-        check(lib().fg_batch_prepare(index.h, C.byref(batch.batch), C.byref(self.h)))
+        check(lib().fg_batch_prepare_ex(index.h, C.byref(batch.batch), prep_flags, C.byref(self.h)))
 
     def execute(self, d_hits: int, d_n: int, d_count: int | None = None, d_bitmap: int | None = None,
                 k_stride: int | None = None, flags: int = 0) -> None:

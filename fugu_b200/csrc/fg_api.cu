@@ -186,6 +186,7 @@ extern "C" int32_t fg_ctx_synchronize(fg_ctx* c) {
 struct TermInfo {
     uint32_t blk_begin, n_blocks, df_local, df_global;
     uint64_t bytes;  // packed payload + 16 B skip per block
+    int32_t col;     // dense tf column of the term (index into fg_index::d_cols) or -1
 };
 struct HostField {
     uint32_t flags = 0;
@@ -202,8 +203,16 @@ struct fg_index {
     fg_index_info info{};
     DevIndex dev{};
     std::vector<void*> allocs;
+    // dense tf columns of the most frequent terms (see build_columns)
+    const uint8_t* d_cols = nullptr;
+    uint64_t col_stride = 0;
+    uint32_t n_cols = 0;
 };
 
+static uint64_t env_u64_early(const char* name, uint64_t dflt) {
+    const char* e = getenv(name);
+    return e ? strtoull(e, nullptr, 10) : dflt;
+}
 static int host_threads() {
     unsigned h = std::thread::hardware_concurrency();
     const char* e = getenv("FG_HOST_THREADS");
@@ -283,6 +292,7 @@ extern "C" int32_t fg_index_upload(fg_ctx* ctx, const fg_index_desc* d, fg_index
             if (n_blocks + ti.n_blocks > 0xFFFFFFF0ull) return fail(FG_ERR_UNSUPPORTED, "too many blocks");
             ti.blk_begin = (uint32_t)n_blocks;
             ti.bytes = 0;
+            ti.col = -1;
             n_blocks += ti.n_blocks;
             n_postings += n;
         }
@@ -401,8 +411,12 @@ extern "C" int32_t fg_index_upload(fg_ctx* ctx, const fg_index_desc* d, fg_index
     if ((rc = dev_copy(cache.data(), cache.size() * 4, (const void**)&ix->dev.cache))) return rc;
     for (uint32_t f = 0; f < d->n_fields; f++) {
         ix->dev.fnorm[f] = nullptr;
-        if (d->fields[f].flags & FG_FIELD_HAS_FIELDNORMS)
-            if ((rc = dev_copy(d->fields[f].fieldnorm_ids, d->n_docs, (const void**)&ix->dev.fnorm[f]))) return rc;
+        if (d->fields[f].flags & FG_FIELD_HAS_FIELDNORMS) {
+            // padded: the slot scan reads the fieldnorm ids of 4 docs with one 32-bit load
+            std::vector<uint8_t> fnp(((size_t)d->n_docs + 15) / 16 * 16 + 16, 0);
+            if (d->n_docs) memcpy(fnp.data(), d->fields[f].fieldnorm_ids, d->n_docs);
+            if ((rc = dev_copy(fnp.data(), fnp.size(), (const void**)&ix->dev.fnorm[f]))) return rc;
+        }
     }
     ix->dev.alive = nullptr;
     if (d->alive_bitset)
@@ -418,6 +432,59 @@ extern "C" int32_t fg_index_upload(fg_ctx* ctx, const fg_index_desc* d, fg_index
             na += (uint32_t)__builtin_popcount(x);
         }
         ix->dev.n_alive = na;
+    }
+
+    // ---- dense tf columns -----------------------------------------------------------------
+    // A term that occurs in at least 1/FG_COL_DIV of the shard's docs additionally gets a dense
+    // column: one byte per doc holding its term frequency (0 = absent). Leaves on such terms skip
+    // block decode entirely: the slot scan reads 4 docs per 32-bit load and computes
+    // w * tf / (tf + cache[fieldnorm]) from the column byte and the fieldnorm byte, and an
+    // intersection looks a candidate up with one byte load instead of a skip search + block decode.
+    // 1 B/doc/term of HBM buys ~20x fewer instructions per posting on the lists that carry most of
+    // the postings of a Zipfian query mix. The posting blocks stay (exact accounting, tf > 255).
+    {
+        const uint64_t col_div = env_u64_early("FG_COL_DIV", 16);
+        const uint64_t col_min_df = env_u64_early("FG_COL_MIN_DF", 128);
+        const uint64_t budget = env_u64_early("FG_COL_MAX_MB", 16384) << 20;
+        const uint64_t stride = (((uint64_t)d->n_docs + 15) & ~(uint64_t)15) + 16;
+        struct Cand { uint32_t f, t, df; };
+        std::vector<Cand> cand;
+        if (col_div && d->n_docs)
+            for (uint32_t f = 0; f < d->n_fields; f++) {
+                const fg_field_desc& fd = d->fields[f];
+                const bool freqs = (fd.flags & FG_FIELD_HAS_FREQS) && fd.term_freqs;
+                for (uint32_t t = 0; t < fd.n_terms; t++) {
+                    const TermInfo& ti = ix->fields[f].terms[t];
+                    if ((uint64_t)ti.df_local * col_div < d->n_docs || ti.df_local < col_min_df) continue;
+                    bool ok = true;  // a byte must hold every tf of the list
+                    if (freqs) {
+                        const uint32_t* tfs = fd.term_freqs + fd.term_offsets[t];
+                        for (uint32_t i = 0; i < ti.df_local && ok; i++) ok = tfs[i] <= 255;
+                    }
+                    if (ok) cand.push_back({f, t, ti.df_local});
+                }
+            }
+        std::stable_sort(cand.begin(), cand.end(), [](const Cand& a, const Cand& b) { return a.df > b.df; });
+        while (!cand.empty() && cand.size() * stride > budget) cand.pop_back();
+        if (!cand.empty()) {
+            std::vector<uint8_t> cols(cand.size() * stride, 0);
+            parallel_for(cand.size(), T, [&](uint64_t a, uint64_t b, int) {
+                for (uint64_t c = a; c < b; c++) {
+                    const fg_field_desc& fd = d->fields[cand[c].f];
+                    const bool freqs = (fd.flags & FG_FIELD_HAS_FREQS) && fd.term_freqs;
+                    const uint64_t o = fd.term_offsets[cand[c].t];
+                    uint8_t* col = cols.data() + c * stride;
+                    for (uint32_t i = 0; i < cand[c].df; i++)
+                        col[fd.doc_ids[o + i]] = freqs ? (uint8_t)fd.term_freqs[o + i] : (uint8_t)1;
+                }
+            });
+            if ((rc = dev_copy(cols.data(), cols.size(), (const void**)&ix->d_cols))) return rc;
+            for (size_t c = 0; c < cand.size(); c++) ix->fields[cand[c].f].terms[cand[c].t].col = (int32_t)c;
+            ix->col_stride = stride;
+            ix->n_cols = (uint32_t)cand.size();
+        }
+        ix->info.n_columns = ix->n_cols;
+        ix->info.column_bytes = ix->n_cols * stride;
     }
 
     ix->info.n_postings = n_postings;
@@ -495,7 +562,13 @@ extern "C" void fg_batch_release(fg_batch* b) {
 
 
 extern "C" int32_t fg_batch_prepare(fg_index* ix, const fg_query_batch* qb, fg_batch** out) {
+    return fg_batch_prepare_ex(ix, qb, 0, out);
+}
+
+extern "C" int32_t fg_batch_prepare_ex(fg_index* ix, const fg_query_batch* qb, uint32_t prep_flags, fg_batch** out) {
     if (!ix || !qb || !out) return fail(FG_ERR_INVALID, "fg_batch_prepare: NULL argument");
+    const bool use_cols = !(prep_flags & FG_PREP_NO_COLUMNS) && ix->n_cols && !getenv("FG_NO_COLUMNS");
+    const uint64_t COL_COST_DIV = std::max<uint64_t>(1, env_u64("FG_COL_COST_DIV", 4));
     *out = nullptr;
     if (qb->n_queries && (!qb->queries || (qb->n_clauses && !qb->clauses) || (qb->n_leaves && !qb->leaves)))
         return fail(FG_ERR_INVALID, "fg_batch_prepare: NULL arrays");
@@ -518,7 +591,8 @@ extern "C" int32_t fg_batch_prepare(fg_index* ix, const fg_query_batch* qb, fg_b
     const uint64_t SOLO_MIN_BLOCKS = env_u64("FG_SOLO_MIN_BLOCKS", 0xFFFFFFFFull);
     // per-query scratch (fixed arrays: the lowering of a 5000-query batch must not allocate per query)
     constexpr int MAXC = 32, MAXT = 64;
-    struct CRec { uint32_t occur, begin, count; uint64_t cost, df; };
+    struct CRec { uint32_t occur, begin, count, ncol; uint64_t cost, df; };
+    DevLeaf ctmp[MAXT];  // column leaves of the query (appended after its block leaves)
     CRec crec[MAXC];
     DevLeaf tmp[MAXT];
     dl.reserve((size_t)qb->n_leaves);
@@ -543,7 +617,7 @@ extern "C" int32_t fg_batch_prepare(fg_index* ix, const fg_query_batch* qb, fg_b
             if ((uint64_t)c.leaf_begin + c.n_leaves > qb->n_leaves)
                 return fail(FG_ERR_INVALID, "query %u: leaf range out of bounds", qi);
             if (c.occur > FG_OCCUR_MUST_NOT) return fail(FG_ERR_INVALID, "query %u: bad occur", qi);
-            CRec cr{c.occur, (uint32_t)nt, 0, 0, 0};
+            CRec cr{c.occur, (uint32_t)nt, 0, 0, 0, 0};
             bool all = false;
             float all_boost = 0.f;
             for (uint32_t li = 0; li < c.n_leaves; li++) {
@@ -563,7 +637,12 @@ extern "C" int32_t fg_batch_prepare(fg_index* ix, const fg_query_batch* qb, fg_b
                 L.weight = lf.boost * (fg_bm25_idf(ti.df_global, N) * (1.0f + K1));
                 L.cnorm = hf.cnorm;
                 L.fn_field = (hf.flags & FG_FIELD_HAS_FIELDNORMS) ? (int32_t)lf.field : -1;
-                cr.cost += ti.bytes;
+                if (use_cols && ti.col >= 0) {
+                    L.col = ix->d_cols + (uint64_t)ti.col * ix->col_stride;
+                    cr.ncol++;
+                } else {
+                    cr.cost += ti.bytes;
+                }
                 cr.df += ti.df_local;
                 cr.count++;
             }
@@ -605,55 +684,87 @@ extern "C" int32_t fg_batch_prepare(fg_index* ix, const fg_query_batch* qb, fg_b
         }
         const size_t ql0 = dl.size();
         uint64_t insert_postings = 0, total_bytes = 0;
-        auto emit = [&](const CRec& cr, uint32_t bit, uint32_t role, uint32_t req, bool ins) {
+        int n_ctmp = 0;
+        bool col_insert = false;
+        // Block leaves go to `dl` in evaluation order; column leaves are collected in ctmp and
+        // appended behind them (they are applied in the slot scan, after every block phase).
+        // `req` = mask bits a slot must already carry when a filter leaf touches it; only bits that
+        // block phases decide completely may be required: a clause with a column leaf sets its bit
+        // as late as the slot scan. A filter leaf left without any usable precondition is LF_NOFILT.
+        auto emit = [&](const CRec& cr, uint32_t bit, uint32_t role, uint32_t req, bool ins, bool nofilt) {
             for (uint32_t i = 0; i < cr.count; i++) {
                 DevLeaf L = tmp[cr.begin + i];
                 L.bit = bit; L.role = role; L.req = req;
+                if (L.col) {
+                    if (ins) col_insert = true;
+                    ctmp[n_ctmp++] = L;
+                    continue;
+                }
+                if (nofilt) L.lflags |= LF_NOFILT;
                 if (ins) insert_postings += (uint64_t)L.n_blocks * BLOCK;
                 dl.push_back(L);
             }
         };
+        uint32_t complete = 0, need_not = 0;
         if (n_must) {
             D.all_must = (1u << n_must) - 1u;
             for (int ci = 0; ci < n_must; ci++) {
                 const CRec& cr = crec[must_idx[ci]];
-                emit(cr, 1u << ci, ci == 0 ? ROLE_INSERT : ROLE_MUST, (1u << ci) - 1u, ci == 0);
+                const uint32_t req = ((1u << ci) - 1u) & complete;
+                emit(cr, 1u << ci, ci == 0 ? ROLE_INSERT : ROLE_MUST, req, ci == 0, ci != 0 && req == 0);
+                if (cr.ncol == 0) complete |= 1u << ci;
                 total_bytes += cr.cost;
             }
-            D.n_insert = crec[must_idx[0]].count;
+            D.n_insert = 0;
+            for (size_t i = ql0; i < dl.size(); i++) D.n_insert += dl[i].role == ROLE_INSERT;
             for (int i = 0; i < nc; i++)
-                if (crec[i].occur == FG_OCCUR_SHOULD) { emit(crec[i], 0, ROLE_SHOULD, D.all_must, false); total_bytes += crec[i].cost / 4; }
+                if (crec[i].occur == FG_OCCUR_SHOULD) { emit(crec[i], 0, ROLE_SHOULD, complete, false, complete == 0); total_bytes += crec[i].cost / 4; }
+            need_not = complete;
         } else {
             D.all_must = BIT_SHOULD;
             D.flags |= QF_NO_MUST;
+            bool any_col = false, positive = true;
             for (int i = 0; i < nc; i++)
-                if (crec[i].occur == FG_OCCUR_SHOULD) { emit(crec[i], BIT_SHOULD, ROLE_INSERT, 0, true); total_bytes += crec[i].cost; }
+                if (crec[i].occur == FG_OCCUR_SHOULD) {
+                    emit(crec[i], BIT_SHOULD, ROLE_INSERT, 0, true, false);
+                    total_bytes += crec[i].cost;
+                    any_col = any_col || crec[i].ncol;
+                }
             D.n_insert = (uint32_t)(dl.size() - ql0);
-            bool positive = true;
             for (size_t i = ql0; i < dl.size(); i++) positive = positive && dl[i].weight > 0.f;
+            for (int i = 0; i < n_ctmp; i++) positive = positive && ctmp[i].weight > 0.f;
             if (n_not == 0 && positive) D.flags |= QF_PURE_UNION;
+            complete = any_col ? 0u : BIT_SHOULD;
+            need_not = complete;
         }
         for (int i = 0; i < nc; i++)
-            if (crec[i].occur == FG_OCCUR_MUST_NOT) { emit(crec[i], BIT_NOT, ROLE_NOT, 0, false); total_bytes += crec[i].cost / 4; }
-        const size_t nql = dl.size() - ql0;
-        if (nql > (size_t)MAX_LEAVES)
-            return fail(FG_ERR_UNSUPPORTED, "query %u: %zu live leaves > %d", qi, nql, MAX_LEAVES);
+            if (crec[i].occur == FG_OCCUR_MUST_NOT) { emit(crec[i], BIT_NOT, ROLE_NOT, 0, false, need_not == 0); total_bytes += crec[i].cost / 4; }
+        const size_t nbl = dl.size() - ql0;  // block leaves
+        if (nbl + (size_t)n_ctmp > (size_t)MAX_LEAVES)
+            return fail(FG_ERR_UNSUPPORTED, "query %u: %zu live leaves > %d", qi, nbl + (size_t)n_ctmp, MAX_LEAVES);
         // candidate-bitmap rebuild points: after the last leaf of a clause when the next leaf filters
         for (size_t i = ql0; i + 1 < dl.size(); i++) {
             const DevLeaf& nx = dl[i + 1];
-            if (nx.role == ROLE_INSERT) continue;
+            if (nx.role == ROLE_INSERT || (nx.lflags & LF_NOFILT)) continue;
             const bool boundary = dl[i].role != nx.role || dl[i].bit != nx.bit;
             if (!boundary) continue;
             if (dl[i].role == ROLE_SHOULD) continue;  // bitmap of all-Must candidates is still valid
             // mask the NEXT leaf's docs must carry (MustNot filters on the matching candidates)
-            dl[i].build_cb = nx.role == ROLE_NOT ? D.all_must : nx.req;
+            dl[i].build_cb = nx.role == ROLE_NOT ? need_not : nx.req;
         }
-        D.n_leaves = (uint32_t)nql;
+        D.n_leaves = (uint32_t)nbl;
+        D.n_col = (uint32_t)n_ctmp;
+        D.col_req = n_must ? complete : 0u;
+        if (col_insert) D.flags |= QF_COL_INSERT;
+        for (int i = 0; i < n_ctmp; i++) dl.push_back(ctmp[i]);
 
         // ---- mode + work items ----
         const uint32_t nd = ix->n_docs;
         const uint64_t dmin = n_must ? DENSE_MIN_MUST : DENSE_MIN;
-        const uint32_t mode = (insert_postings * (uint64_t)DW >= dmin * (uint64_t)std::max<uint32_t>(nd, 1)) ? MODE_DENSE : MODE_HASH;
+        const uint32_t mode = (col_insert || insert_postings * (uint64_t)DW >= dmin * (uint64_t)std::max<uint32_t>(nd, 1)) ? MODE_DENSE : MODE_HASH;
+        // a dense window reads 1 B per doc per column leaf (+ the fieldnorm byte), at a fraction of the
+        // per-byte cost of packed blocks; hash rounds only gather the columns at their candidates
+        if (mode == MODE_DENSE && n_ctmp) total_bytes += (uint64_t)nd * (uint64_t)(n_ctmp + 1) / COL_COST_DIV;
         const uint64_t ib = !(D.flags & QF_PURE_UNION) ? ITEM_BYTES_MASKED : (mode == MODE_DENSE ? ITEM_BYTES : ITEM_BYTES_HASH);
         uint64_t want = std::max<uint64_t>(1, (total_bytes + ib / 2) / ib);
         const uint32_t min_span = mode == MODE_DENSE ? (uint32_t)DW : HASH_MIN_SPAN;
@@ -668,8 +779,9 @@ extern "C" int32_t fg_batch_prepare(fg_index* ix, const fg_query_batch* qb, fg_b
         for (uint32_t j = 0; j < ni; j++) {
             DevItem it{};
             it.query = qi;
-            it.doc_lo = (uint32_t)((uint64_t)nd * j / ni);
-            it.doc_hi = (uint32_t)((uint64_t)nd * (j + 1) / ni);
+            // 4-aligned cuts: dense windows read columns / fieldnorms of 4 docs per 32-bit load
+            it.doc_lo = (uint32_t)((uint64_t)nd * j / ni) & ~3u;
+            it.doc_hi = j + 1 == ni ? nd : ((uint32_t)((uint64_t)nd * (j + 1) / ni) & ~3u);
             it.mode = mode;
             it.slot = D.item_begin + j;
             it.cls = (mode == MODE_DENSE ? 0u : 2u) + ((D.flags & QF_PURE_UNION) ? 0u : 1u);

@@ -42,13 +42,22 @@ struct DevLeaf {
     uint32_t req;        // mask bits a slot must already carry (filter roles)
     uint32_t build_cb;   // rebuild the candidate bitmap after this leaf (mask value to test), 0 = no
     uint32_t solo;       // long list in a dense-mode plan: gets a phase of its own (plain adds, no atomics)
-    uint32_t pad[2];
+    uint32_t lflags;     // LF_*
+    uint32_t pad0;
+    const uint8_t* col;  // dense tf column of the term (1 byte per doc, 0 = absent) or nullptr: a column
+                         // leaf has no block phases, it is applied to the round's slots in the slot scan
+    uint32_t pad1[2];
 };
+static_assert(sizeof(DevLeaf) == 64, "DevLeaf is uploaded as a flat array");
+// a filter-role leaf whose precondition bits are not known before the slot scan (an earlier clause
+// has a column leaf): applied to every doc of the dense window, no candidate pre-test
+constexpr uint32_t LF_NOFILT = 1;
 
 constexpr uint32_t MODE_DENSE = 0, MODE_HASH = 1;
 constexpr uint32_t QF_NO_MUST = 1;
 constexpr uint32_t QF_ALL = 4;         // pure AllQuery: first k alive docs, score = const_score
 constexpr uint32_t QF_PURE_UNION = 2;  // only Should clauses, all weights > 0: no clause masks needed
+constexpr uint32_t QF_COL_INSERT = 8;  // an insert-role leaf is a column leaf: every doc of the range is a candidate
 
 struct DevQuery {
     uint32_t leaf_begin;
@@ -60,8 +69,11 @@ struct DevQuery {
     float const_score;    // sum of Must AllQuery scores
     uint32_t item_begin;  // work items of this query are contiguous in the partial arrays
     uint32_t n_items;
-    uint32_t pad[3];
+    uint32_t n_col;       // column leaves, stored after the n_leaves block leaves
+    uint32_t col_req;     // mask bits block phases have fully decided: a slot lacking one can never match
+    uint32_t pad[1];
 };
+static_assert(sizeof(DevQuery) == 48, "DevQuery is uploaded as a flat array");
 
 struct DevItem {
     uint32_t query;

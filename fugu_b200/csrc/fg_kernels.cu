@@ -44,6 +44,14 @@ __device__ __forceinline__ uint64_t make_key(float score, uint32_t doc) {
     return ((uint64_t)sortable(score) << 32) | (uint32_t)(~doc);
 }
 
+// tf / (tf + norm) with one MUFU.RCP + one FMUL. __fdividef also guards denominators below 2^-126
+// (two compares + four scalings per call); here tf + norm >= 0.3. Error <= 2 ulp, inside the 1e-5 bar.
+__device__ __forceinline__ float tf_factor(float t, float n) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t + n));
+    return t * r;
+}
+
 // Per-warp top-k in registers: rank r lives in lane r%32, row r/32; sorted best first.
 template <int KS>
 struct WarpTopK {
@@ -205,6 +213,7 @@ constexpr int RES_CAP = RES_CAP_;        // resident postings per work item (sho
 constexpr int RES_MAX_BLOCKS = 3;   // a leaf is resident when it has at most this many blocks in the item's range
 
 struct Shared {
+    DevQuery q;
     DevLeaf leaf[MAX_LEAVES];
     uint32_t cur[MAX_LEAVES];
     uint32_t cur_next[MAX_LEAVES];
@@ -218,10 +227,107 @@ struct Shared {
     uint32_t leafmask;  // leaves with at least one needed block in the current scan pass
     uint32_t rlo, rhi, shift, done, gtheta;
     uint32_t match;
+    int32_t col_field;  // >= 0: every column leaf takes its norms from this fieldnorm field (ctab holds its cache)
+    float ctab[256];    // BM25 norm cache K1*(1-B+B*dl/avg) of col_field, by fieldnorm id
     unsigned long long st_blocks, st_redecode, st_scored;
 };
 
+// byte j of w as a float (PRMT into the mantissa of 2^23, one FADD): column tfs without I2F
+__device__ __forceinline__ float byte_f32(uint32_t w, int j) {
+    return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650u | (uint32_t)j)) - 8388608.0f;
+}
+
 __device__ __forceinline__ void smem_add_f32(float* p, float v) { atomicAdd(p, v); }
+
+// ---- column leaves (dense tf columns, fg_api.cu: fg_index_upload) ---------------------------------
+// Pure-union dense window: add the scores of every column leaf to the 4 docs rlo + 4g .. +3.
+// A column byte of 0 (term absent) contributes exactly 0 (0 / (0 + norm), norm > 0).
+__device__ __forceinline__ void col_add_dense(const Shared& S, const SearchParams& p, int nl, int ncol,
+                                              uint32_t doc0, float v[4]) {
+    if (S.col_field >= 0) {
+        const uint32_t fn4 = __ldg(reinterpret_cast<const uint32_t*>(p.ix.fnorm[S.col_field] + doc0));
+        const DevLeaf* L = &S.leaf[nl];
+        int c = 0;
+        uint32_t ta = __ldg(reinterpret_cast<const uint32_t*>(L[0].col + doc0)), tb = 0;
+        if (ncol > 1) tb = __ldg(reinterpret_cast<const uint32_t*>(L[1].col + doc0));
+        float n[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) n[j] = S.ctab[(fn4 >> (8 * j)) & 255u];
+        while (true) {
+            {
+                const float w = L[c].weight;
+#pragma unroll
+                for (int j = 0; j < 4; j++) v[j] += w * tf_factor(byte_f32(ta, j), n[j]);
+            }
+            if (c + 1 >= ncol) break;
+            {
+                const float w = L[c + 1].weight;
+#pragma unroll
+                for (int j = 0; j < 4; j++) v[j] += w * tf_factor(byte_f32(tb, j), n[j]);
+            }
+            c += 2;
+            if (c >= ncol) break;
+            ta = __ldg(reinterpret_cast<const uint32_t*>(L[c].col + doc0));
+            if (c + 1 < ncol) tb = __ldg(reinterpret_cast<const uint32_t*>(L[c + 1].col + doc0));
+        }
+    } else {  // column leaves of different fields (facet columns have a constant norm)
+        for (int c = 0; c < ncol; c++) {
+            const DevLeaf& L = S.leaf[nl + c];
+            const uint32_t t4 = __ldg(reinterpret_cast<const uint32_t*>(L.col + doc0));
+            uint32_t fn4 = 0;
+            if (L.fn_field >= 0) fn4 = __ldg(reinterpret_cast<const uint32_t*>(p.ix.fnorm[L.fn_field] + doc0));
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const float n = L.fn_field >= 0 ? __ldg(p.ix.cache + L.fn_field * 256 + ((fn4 >> (8 * j)) & 255u)) : L.cnorm;
+                const float t = byte_f32(t4, j);
+                v[j] += L.weight * tf_factor(t, n);
+            }
+        }
+    }
+}
+
+// Masked plans (and pure unions that filter deleted docs): apply every column leaf to 4 slots.
+// DENSE: slots are the docs doc0 .. doc0+3; hash: slot j holds doc kk[j]. A slot takes part when
+// ok[j]; a present term adds its score and sets its clause bit (or BIT_NOT).
+template <bool DENSE>
+__device__ __forceinline__ void col_apply(const Shared& S, const SearchParams& p, int nl, int ncol,
+                                          uint32_t doc0, const uint32_t kk[4], const bool ok[4],
+                                          float v[4], uint32_t m[4]) {
+    if (!(ok[0] || ok[1] || ok[2] || ok[3])) return;
+    float n[4] = {0.f, 0.f, 0.f, 0.f};
+    const int cf = S.col_field;
+    if (cf >= 0) {
+        if (DENSE) {
+            const uint32_t fn4 = __ldg(reinterpret_cast<const uint32_t*>(p.ix.fnorm[cf] + doc0));
+#pragma unroll
+            for (int j = 0; j < 4; j++) n[j] = S.ctab[(fn4 >> (8 * j)) & 255u];
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (ok[j]) n[j] = S.ctab[__ldg(p.ix.fnorm[cf] + kk[j])];
+        }
+    }
+    for (int c = 0; c < ncol; c++) {
+        const DevLeaf& L = S.leaf[nl + c];
+        uint32_t t4 = 0;
+        if (DENSE) t4 = __ldg(reinterpret_cast<const uint32_t*>(L.col + doc0));
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if (!ok[j]) continue;
+            const uint32_t tb = DENSE ? (t4 >> (8 * j)) & 255u : (uint32_t)__ldg(L.col + kk[j]);
+            if (!tb) continue;
+            if (L.role == ROLE_NOT) { m[j] |= BIT_NOT; continue; }
+            float nn = n[j];
+            if (cf < 0) {
+                const uint32_t d = DENSE ? doc0 + j : kk[j];
+                nn = L.fn_field >= 0 ? __ldg(p.ix.cache + L.fn_field * 256 + __ldg(p.ix.fnorm[L.fn_field] + d)) : L.cnorm;
+            }
+            const float t = (float)tb;
+            v[j] += L.weight * tf_factor(t, nn);
+            m[j] |= L.bit;
+        }
+    }
+}
 
 // One work item. DENSE: slot = doc - round_lo; else hash slots. PURE: the plan is a plain union
 // (only Should clauses, positive weights): no clause masks, every touched slot matches.
@@ -231,7 +337,8 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
                                          uint32_t* cb, uint32_t* wl, uint64_t* scratch, uint32_t* res_doc,
                                          float* res_val) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int nl = (int)q.n_leaves;
+    const int nl = (int)q.n_leaves;   // block leaves; the q.n_col column leaves follow them in S.leaf
+    const int ncol = (int)q.n_col;
     const uint4* __restrict__ skip = p.ix.skip;
     const int k = (int)q.k;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -262,8 +369,14 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
         }
         S.res_cnt[tid] = cnt;
     }
-    if (tid == 0) { S.res_n = 0; S.match = 0; S.st_blocks = 0; S.st_redecode = 0; S.st_scored = 0; }
+    if (tid == 0) {
+        S.res_n = 0; S.match = 0; S.st_blocks = 0; S.st_redecode = 0; S.st_scored = 0;
+        int cf = ncol ? S.leaf[nl].fn_field : -1;
+        for (int c = 1; c < ncol; c++) if (S.leaf[nl + c].fn_field != cf) cf = -1;
+        S.col_field = cf;
+    }
     __syncthreads();
+    if (ncol && S.col_field >= 0) S.ctab[tid] = __ldg(p.ix.cache + S.col_field * 256 + tid);
     if (warp == 0) {
         // resident leaves: short lists are decoded ONCE per item into (doc, score) pairs and applied to
         // every round from shared memory, instead of re-decoding their straddling blocks each round
@@ -315,7 +428,7 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
                     if (L.fn_field >= 0) norm = __ldg(p.ix.cache + L.fn_field * 256 + __ldg(p.ix.fnorm[L.fn_field] + d));
                     const float tf = (float)(t[j] + 1u);
                     res_doc[pos] = d;
-                    res_val[pos] = L.weight * __fdividef(tf, tf + norm);
+                    res_val[pos] = L.weight * tf_factor(tf, norm);
                 }
                 scored_here += __popc(m);
             }
@@ -378,10 +491,15 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
             }
             fb = warp_min(fb);
             chi = warp_min(chi);
+            if (DENSE && (q.flags & QF_COL_INSERT)) fb = lo_;  // a column insert leaf: every doc is a candidate
             if (lane == 0) {
                 uint32_t rlo = fb == EMPTY ? end : max(lo_, fb);
+                const bool fin = rlo >= end;
+                // dense windows start 4-aligned (lo_ is: work items are cut at multiples of 4 and a full
+                // window spans DW docs): columns and fieldnorms are read 4 docs per 32-bit load
+                if (DENSE) rlo &= ~3u;
                 uint32_t rhi = DENSE ? (uint32_t)min((unsigned long long)rlo + DW, (unsigned long long)end) : chi;
-                S.done = rlo >= end;
+                S.done = fin;
                 if (rhi < rlo) rhi = rlo;
                 S.rlo = rlo;
                 S.rhi = rhi;
@@ -392,7 +510,7 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
             }
             // scan resume points of phase 0 (insert leaves), see the phase loop
             {
-                const int pl1 = (int)S.phase_end[0];
+                const int pl1 = nl ? (int)S.phase_end[0] : 0;
                 for (int i = lane; i < pl1 * NW; i += 32) {
                     const int l = i / NW, w = i % NW;
                     const uint32_t c0 = (uint32_t)((w - l) & (NW - 1));
@@ -432,7 +550,9 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
         while (l0 < nl) {
             const int l1 = (int)S.phase_end[l0];
             const uint32_t role = S.leaf[l0].role, bit = S.leaf[l0].bit, req = S.leaf[l0].req;
-            const bool filter = role != ROLE_INSERT;
+            // LF_NOFILT: a filter-role leaf without usable precondition bits (an earlier clause has a
+            // column leaf): it is applied to every doc of the dense window like an insert leaf
+            const bool filter = role != ROLE_INSERT && !(S.leaf[l0].lflags & LF_NOFILT);
             bool prepared = l0 == 0;  // phase 0's first pass was prepared by round_setup (no barrier needed)
             if (!prepared) {
                 for (int i = tid; i < (l1 - l0) * NW; i += NT) {
@@ -548,8 +668,8 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
                                         n2 = __ldg(cache + __ldg(fnp + s2)), n3 = __ldg(cache + __ldg(fnp + s3));
                             const float f0 = (float)((xt & mt_) + 1u), f1 = (float)(((xt >> bt) & mt_) + 1u),
                                         f2 = (float)(((xt >> (2 * bt)) & mt_) + 1u), f3 = (float)(((xt >> (3 * bt)) & mt_) + 1u);
-                            const float v0 = wgt * __fdividef(f0, f0 + n0), v1 = wgt * __fdividef(f1, f1 + n1),
-                                        v2 = wgt * __fdividef(f2, f2 + n2), v3 = wgt * __fdividef(f3, f3 + n3);
+                            const float v0 = wgt * tf_factor(f0, n0), v1 = wgt * tf_factor(f1, n1),
+                                        v2 = wgt * tf_factor(f2, n2), v3 = wgt * tf_factor(f3, n3);
                             if (solo) { acc[s0] += v0; acc[s1] += v1; acc[s2] += v2; acc[s3] += v3; }
                             else { smem_add_f32(&acc[s0], v0); smem_add_f32(&acc[s1], v1); smem_add_f32(&acc[s2], v2); smem_add_f32(&acc[s3], v3); }
                             continue;
@@ -601,7 +721,7 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
                                     if (L0.fn_field >= 0)
                                         norm = __ldg(p.ix.cache + L0.fn_field * 256 + __ldg(p.ix.fnorm[L0.fn_field] + d));
                                     const float t = (float)(tfv + 1u);
-                                    const float v = L0.weight * __fdividef(t, t + norm);
+                                    const float v = L0.weight * tf_factor(t, norm);
                                     if (solo) acc[sl] += v; else smem_add_f32(&acc[sl], v);
                                     if (bit) msk[sl] = (uint8_t)(msk[sl] | bit);
                                     if (p.acct) my_scored++;
@@ -687,7 +807,7 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
                             const int sl = slot[g][j];
                             if (sl < 0) continue;
                             const float t = (float)(tf[g][j] + 1u);
-                            const float v = wgt * __fdividef(t, t + norm[g][j]);
+                            const float v = wgt * tf_factor(t, norm[g][j]);
                             if (solo) acc[sl] += v; else smem_add_f32(&acc[sl], v);
                             if (!PURE && bit) msk[sl] = (uint8_t)(msk[sl] | bit);
                             if (p.acct) my_scored++;
@@ -754,10 +874,18 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
                 // tight loop for the bulk case (pure union, dense window, no deletes): a touched slot has
                 // a positive score and matches; only slots that can enter the top-k take the slow path
                 const bool count = p.want_counts != 0;
+                const bool use_acc = nl > 0;  // without block leaves the slots stay zero: scores come from columns
                 for (int g0 = warp * 32; g0 < n4; g0 += NT) {
                     const int g = g0 + lane;
                     float4 av = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (g < n4) { av = a4[g]; a4[g] = make_float4(0.f, 0.f, 0.f, 0.f); }
+                    if (g < n4) {
+                        if (use_acc) { av = a4[g]; a4[g] = make_float4(0.f, 0.f, 0.f, 0.f); }
+                        if (ncol) {
+                            float v[4] = {av.x, av.y, av.z, av.w};
+                            col_add_dense(S, p, nl, ncol, rlo + 4u * (uint32_t)g, v);
+                            av = make_float4(v[0], v[1], v[2], v[3]);
+                        }
+                    }
                     if (count) my_matches += (av.x > 0.f) + (av.y > 0.f) + (av.z > 0.f) + (av.w > 0.f);
                     const float mx = fmaxf(fmaxf(av.x, av.y), fmaxf(av.z, av.w));
                     if (__any_sync(FULL, mx > 0.f && mx + q.const_score >= theta_s)) {
@@ -787,8 +915,17 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
                     if (!DENSE) { kv = k4[g]; k4[g] = make_uint4(EMPTY, EMPTY, EMPTY, EMPTY); }
                     if (!PURE) { m4 = m32[g]; if (m4) m32[g] = 0; }
                 }
-                const float raw[4] = {av.x, av.y, av.z, av.w};
+                float raw[4] = {av.x, av.y, av.z, av.w};
                 const uint32_t kk[4] = {kv.x, kv.y, kv.z, kv.w};
+                uint32_t mm[4] = {m4 & 0xFFu, (m4 >> 8) & 0xFFu, (m4 >> 16) & 0xFFu, m4 >> 24};
+                if (ncol && g < n4) {
+                    // column leaves: only slots that still can match (col_req = the Must bits block phases decide)
+                    bool ok[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                        ok[j] = (DENSE || kk[j] != EMPTY) && (PURE || (mm[j] & q.col_req) == q.col_req);
+                    col_apply<DENSE>(S, p, nl, ncol, rlo + 4u * (uint32_t)g, kk, ok, raw, mm);
+                }
                 bool mt[4];
                 bool hot;
                 if (!generic) {
@@ -805,7 +942,7 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
                     for (int j = 0; j < 4; j++) {
                         if (PURE) mt[j] = DENSE ? raw[j] > 0.f : kk[j] != EMPTY;
                         else {
-                            const uint32_t m = (m4 >> (8 * j)) & 0xFFu;
+                            const uint32_t m = mm[j];
                             mt[j] = (m & 0x7Fu) == q.all_must && !(m & BIT_NOT);
                         }
                     }
@@ -907,9 +1044,13 @@ __global__ void __launch_bounds__(NT, MINB) search_kernel(const SearchParams p) 
     uint64_t* scratch = reinterpret_cast<uint64_t*>(wl + NW * SEG_CAP);
 
     const DevItem it = p.items[p.item_begin + blockIdx.x];
-    const DevQuery q = p.queries[it.query];
-    if (threadIdx.x < q.n_leaves) S.leaf[threadIdx.x] = p.leaves[q.leaf_begin + threadIdx.x];
+    {
+        const DevQuery q0 = p.queries[it.query];
+        if (threadIdx.x == 0) S.q = q0;  // the plan header lives in shared memory: it is read in every round
+        if (threadIdx.x < q0.n_leaves + q0.n_col) S.leaf[threadIdx.x] = p.leaves[q0.leaf_begin + threadIdx.x];
+    }
     __syncthreads();
+    const DevQuery& q = S.q;
     uint32_t* res_doc = reinterpret_cast<uint32_t*>(scratch + NW * KS * 32);
     float* res_val = reinterpret_cast<float*>(res_doc + RES_CAP);
     run_item<KS, GRP, DENSE, PURE>(p, it, q, S, acc, keys, msk, DENSE ? cb_dense : cb_hash, wl, scratch, res_doc, res_val);
@@ -1025,7 +1166,7 @@ int search_smem_bytes(int ks, bool pure) {
 }
 
 #ifndef PURE_MINB
-#define PURE_MINB 5
+#define PURE_MINB 4
 #endif
 template <int KS, int GRP, int MINB, bool DENSE, bool PURE>
 static void launch_one(SearchParams p, uint32_t begin, uint32_t count, cudaStream_t st) {

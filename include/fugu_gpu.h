@@ -97,6 +97,9 @@ typedef struct {
     uint64_t device_bytes;  /* everything resident in HBM for this snapshot */
     uint32_t n_docs;
     uint32_t n_fields;
+    uint64_t column_bytes;  /* dense tf columns of the most frequent terms (1 B per doc per column) */
+    uint32_t n_columns;
+    uint32_t reserved;
 } fg_index_info;
 int32_t fg_index_get_info(const fg_index* index, fg_index_info* out);
 /* document frequency / layout of one term (host copy of the term table) */
@@ -160,6 +163,11 @@ int32_t fg_search_batch(fg_index* index, const fg_query_batch* batch, uint32_t k
 typedef struct fg_batch fg_batch;
 /* lowers the plan (weights from GLOBAL statistics, work items) and uploads it to the device */
 int32_t fg_batch_prepare(fg_index* index, const fg_query_batch* batch, fg_batch** out);
+/* same with lowering options. FG_PREP_NO_COLUMNS evaluates every leaf from its posting blocks even
+ * when the term has a dense tf column: the block path is what the algorithmic-byte definition
+ *  and the exact-accounting counters are stated on. */
+#define FG_PREP_NO_COLUMNS 1u
+int32_t fg_batch_prepare_ex(fg_index* index, const fg_query_batch* batch, uint32_t prep_flags, fg_batch** out);
 void fg_batch_release(fg_batch* b);
 #define FG_EXEC_EXACT_ACCOUNTING 1u /* exact block-need test for the algorithmic-byte counters (slow) */
 #define FG_EXEC_COUNTERS 4u         /* maintain bytes_blocks / bytes_redecode / scored_postings (cheap) */

@@ -358,3 +358,61 @@ def test_many_leaf_union_in_hash_mode(ctx):
     batch = plan_queries(qs, vocab=cfg.vocab, n_text_fields=2)
     check_batch_against_oracle(index, desc, batch)
     index.close()
+
+
+def test_dense_tf_columns_every_plan_shape(ctx):
+    """Terms in >= 1/16 of the docs get a dense tf column (1 B/doc) and are applied in the slot scan
+    instead of block phases. Every role a column leaf can play, mixed with block leaves, text columns
+    (fieldnorms) next to facet columns (constant norm), tf = 255, boosts, deletes -- against the oracle
+    and against the block path (FG_PREP_NO_COLUMNS)."""
+    rng = np.random.default_rng(5)
+    n_docs = 40_003  # ragged: the last window ends off a multiple of 4
+    def lst(p):
+        return np.sort(rng.choice(n_docs, int(n_docs * p), replace=False)).astype(np.uint32)
+    text_lists = [lst(0.9), lst(0.5), lst(0.2), lst(0.07), lst(0.03), lst(0.004), lst(0.0005),
+                  np.arange(n_docs, dtype=np.uint32)]
+    facet_lists = [lst(0.25), lst(0.5), lst(0.01)]
+    def field(lists, freqs, norms):
+        offs = np.concatenate([[0], np.cumsum([len(x) for x in lists])]).astype(np.uint64)
+        docs = np.concatenate(lists)
+        fd = {"term_offsets": offs, "doc_ids": docs, "total_num_tokens": int(n_docs * 40) if norms else 0,
+              "term_freqs": None, "fieldnorm_ids": None}
+        if freqs:
+            tf = rng.integers(1, 9, len(docs)).astype(np.uint32)
+            tf[rng.integers(0, len(docs), 50)] = 255
+            fd["term_freqs"] = tf
+        if norms:
+            fd["fieldnorm_ids"] = rng.integers(1, 90, n_docs).astype(np.uint8)
+        return fd
+    alive = np.full((n_docs + 31) // 32, 0xFFFFFFFF, np.uint32)
+    for d in rng.choice(n_docs, 500, replace=False):
+        alive[d >> 5] &= ~np.uint32(1 << (d & 31))
+    fields = [field(text_lists, True, True), field(facet_lists, False, False)]
+    S, M, N = nat.FG_OCCUR_SHOULD, nat.FG_OCCUR_MUST, nat.FG_OCCUR_MUST_NOT
+    T = lambda t, b=1.0: (0, t, b)
+    F = lambda t, b=1.0: (1, t, b)
+    shapes = [
+        [(S, [T(0)])], [(S, [T(7)])], [(S, [T(0)]), (S, [T(1)]), (S, [T(2)])],
+        [(S, [T(0), T(5)]), (S, [T(3), T(6)])],                       # column + block leaves in one clause
+        [(S, [T(4)]), (S, [T(5)])],                                  # no column at all
+        [(M, [T(0)])], [(M, [T(0)]), (M, [T(1)])], [(M, [T(1)]), (M, [T(2)]), (M, [T(0)])],
+        [(M, [T(5)]), (M, [T(0)])], [(M, [T(0)]), (M, [T(5)])],      # block lead, column filter
+        [(M, [T(4)]), (M, [T(1), T(6)]), (M, [T(0)])],
+        [(M, [T(0), T(5)]), (M, [T(1), T(4)])],                      # mixed clauses: column lead, NOFILT block filter
+        [(M, [T(2)]), (M, [T(4)]), (M, [T(3)])],                     # column lead, block clause, column clause
+        [(M, [T(1)]), (S, [T(4)])], [(M, [T(4)]), (S, [T(0)])], [(M, [T(0)]), (S, [T(1)]), (S, [T(5)])],
+        [(S, [T(0)]), (N, [T(4)])], [(S, [T(4)]), (N, [T(0)])], [(S, [T(1)]), (N, [T(2)])],
+        [(M, [T(1)]), (N, [T(0)])], [(M, [T(5)]), (N, [T(1)]), (S, [T(2)])], [(M, [T(1)]), (M, [T(4)]), (N, [T(3)])],
+        [(S, [T(0, 2.5)]), (S, [T(3, 0.5)])], [(S, [T(0, -1.0)]), (S, [T(4)])],   # negative boost: masked union
+        [(M, [T(4)]), (M, [F(0), F(2)])], [(S, [T(1)]), (S, [T(5)]), (M, [F(1)])],  # facet Must group (constant norm)
+        [(M, [F(0), F(1)])], [(M, [T(0)]), (M, [F(1)]), (N, [F(0)])],
+        [(M, [T(nat.FG_TERM_ALL)]), (M, [T(0)])],
+    ]
+    qs = [{"k": k, "clauses": sh} for sh in shapes for k in (10, 100)]
+    batch = nat.HostBatch(qs)
+    for al in (None, alive):
+        desc = nat.HostIndexDesc(n_docs, fields, alive_bitset=al)
+        index = nat.Index(ctx, desc)
+        assert index.info().n_columns == 7  # text: 0.9 0.5 0.2 0.07 and the all-docs list; facets: 0.25 0.5
+        check_batch_against_oracle(index, desc, batch)
+        index.close()

@@ -36,9 +36,14 @@ def check_topk(g: np.ndarray, o: np.ndarray, k: int, tol: float = REL_TOL, ctx: 
         i = j + 1
 
 
-def gpu_search_device(index: nat.Index, batch: nat.HostBatch, want_bitmap: bool = False, flags: int = 0):
-    """Split-phase path with device buffers provided by torch; returns numpy results (+ stats)."""
+def gpu_search_device(index: nat.Index, batch: nat.HostBatch, want_bitmap: bool = False, flags: int = 0,
+                      prep_flags: int = 0):
+    """Split-phase path with device buffers provided by torch; returns numpy results (+ stats).
+    The byte counters are defined on the block path: accounting runs lower the plan without columns."""
     import torch
+
+    if flags & (nat.FG_EXEC_EXACT_ACCOUNTING | nat.FG_EXEC_COUNTERS):
+        prep_flags |= nat.FG_PREP_NO_COLUMNS
 
     ks = batch.kmax
     nq = batch.n_queries
@@ -49,7 +54,7 @@ def gpu_search_device(index: nat.Index, batch: nat.HostBatch, want_bitmap: bool 
     words = (index.n_docs + 31) // 32
     d_bm = torch.zeros((nq, words), dtype=torch.int32, device=dev) if want_bitmap else None
     torch.cuda.synchronize()
-    pb = index.prepare(batch)
+    pb = index.prepare(batch, prep_flags)
     pb.execute(d_hits.data_ptr(), d_n.data_ptr(), d_c.data_ptr(), None if d_bm is None else d_bm.data_ptr(),
                k_stride=ks, flags=flags)
     st = pb.stats()
@@ -89,6 +94,16 @@ def check_batch_against_oracle(index: nat.Index, desc: nat.HostIndexDesc, batch:
     for qi in range(batch.n_queries):
         n = int(g_n[qi])
         check_topk(d1[0][qi, :n], g_hits[qi, :n], int(batch.q["k"][qi]), ctx=f"deterministic-vs-default query {qi}")
+    # the block path alone (terms with a dense tf column evaluated from their posting blocks)
+    if index.info().n_columns:
+        b_hits, b_n, b_c, b_bm, _ = gpu_search_device(index, batch, want_bitmap=bitmaps, prep_flags=nat.FG_PREP_NO_COLUMNS)
+        assert np.array_equal(b_c, o_c), f"block path: match counts differ for queries {np.nonzero(b_c != o_c)[0][:10]}"
+        assert np.array_equal(b_n, o_n)
+        if bitmaps:
+            assert np.array_equal(b_bm, o_bm), "block path: matched doc-id sets differ"
+        for qi in range(batch.n_queries):
+            n = int(o_n[qi])
+            check_topk(b_hits[qi, :n], o_hits[qi, :n], int(batch.q["k"][qi]), ctx=f"block path, query {qi}")
     bad = np.nonzero(g_c != o_c)[0]
     assert len(bad) == 0, f"match counts differ for queries {bad[:10]}: gpu {g_c[bad[:10]]} oracle {o_c[bad[:10]]}"
     assert np.array_equal(g_n, o_n), f"n_hits differ: {np.nonzero(g_n != o_n)[0][:10]}"
