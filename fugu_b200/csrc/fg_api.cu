@@ -569,6 +569,7 @@ extern "C" int32_t fg_batch_prepare_ex(fg_index* ix, const fg_query_batch* qb, u
     if (!ix || !qb || !out) return fail(FG_ERR_INVALID, "fg_batch_prepare: NULL argument");
     const bool use_cols = !(prep_flags & FG_PREP_NO_COLUMNS) && ix->n_cols && !getenv("FG_NO_COLUMNS");
     const uint64_t COL_COST_DIV = std::max<uint64_t>(1, env_u64("FG_COL_COST_DIV", 4));
+    const uint64_t STREAM_MAX_BPW = env_u64("FG_STREAM_MAX_BPW", 6);  // blocks per dense window of a streamed leaf
     *out = nullptr;
     if (qb->n_queries && (!qb->queries || (qb->n_clauses && !qb->clauses) || (qb->n_leaves && !qb->leaves)))
         return fail(FG_ERR_INVALID, "fg_batch_prepare: NULL arrays");
@@ -753,6 +754,7 @@ extern "C" int32_t fg_batch_prepare_ex(fg_index* ix, const fg_query_batch* qb, u
             dl[i].build_cb = nx.role == ROLE_NOT ? need_not : nx.req;
         }
         D.n_leaves = (uint32_t)nbl;
+        D.n_stream = 0;
         D.n_col = (uint32_t)n_ctmp;
         D.col_req = n_must ? complete : 0u;
         if (col_insert) D.flags |= QF_COL_INSERT;
@@ -762,6 +764,17 @@ extern "C" int32_t fg_batch_prepare_ex(fg_index* ix, const fg_query_batch* qb, u
         const uint32_t nd = ix->n_docs;
         const uint64_t dmin = n_must ? DENSE_MIN_MUST : DENSE_MIN;
         const uint32_t mode = (col_insert || insert_postings * (uint64_t)DW >= dmin * (uint64_t)std::max<uint32_t>(nd, 1)) ? MODE_DENSE : MODE_HASH;
+        // sparse insert leaves of a dense-window pure union are streamed by one warp each (no skip scan,
+        // no phase barriers): stable-partition them behind the leaves that keep their clause phases
+        if (mode == MODE_DENSE && (D.flags & QF_PURE_UNION) && STREAM_MAX_BPW) {
+            DevLeaf* B = dl.data() + ql0;
+            auto streams = [&](const DevLeaf& L) { return (uint64_t)L.n_blocks * DW <= STREAM_MAX_BPW * (uint64_t)std::max<uint32_t>(nd, 1); };
+            DevLeaf st[MAX_LEAVES];
+            uint32_t ns = 0, np = 0;
+            for (size_t i = 0; i < nbl; i++) { if (streams(B[i])) st[ns++] = B[i]; else B[np++] = B[i]; }
+            for (uint32_t i = 0; i < ns; i++) { st[i].lflags |= LF_STREAM; B[np + i] = st[i]; }
+            D.n_stream = ns;
+        }
         // a dense window reads 1 B per doc per column leaf (+ the fieldnorm byte), at a fraction of the
         // per-byte cost of packed blocks; hash rounds only gather the columns at their candidates
         if (mode == MODE_DENSE && n_ctmp) total_bytes += (uint64_t)nd * (uint64_t)(n_ctmp + 1) / COL_COST_DIV;
@@ -779,9 +792,9 @@ extern "C" int32_t fg_batch_prepare_ex(fg_index* ix, const fg_query_batch* qb, u
         for (uint32_t j = 0; j < ni; j++) {
             DevItem it{};
             it.query = qi;
-            // 4-aligned cuts: dense windows read columns / fieldnorms of 4 docs per 32-bit load
-            it.doc_lo = (uint32_t)((uint64_t)nd * j / ni) & ~3u;
-            it.doc_hi = j + 1 == ni ? nd : ((uint32_t)((uint64_t)nd * (j + 1) / ni) & ~3u);
+            // 16-aligned cuts: dense windows read columns / fieldnorms of 8 docs per 64-bit load
+            it.doc_lo = (uint32_t)((uint64_t)nd * j / ni) & ~15u;
+            it.doc_hi = j + 1 == ni ? nd : ((uint32_t)((uint64_t)nd * (j + 1) / ni) & ~15u);
             it.mode = mode;
             it.slot = D.item_begin + j;
             it.cls = (mode == MODE_DENSE ? 0u : 2u) + ((D.flags & QF_PURE_UNION) ? 0u : 1u);

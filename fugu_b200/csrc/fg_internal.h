@@ -52,6 +52,7 @@ static_assert(sizeof(DevLeaf) == 64, "DevLeaf is uploaded as a flat array");
 // a filter-role leaf whose precondition bits are not known before the slot scan (an earlier clause
 // has a column leaf): applied to every doc of the dense window, no candidate pre-test
 constexpr uint32_t LF_NOFILT = 1;
+constexpr uint32_t LF_STREAM = 2;  // streamed by one warp (see DevQuery::n_stream)
 
 constexpr uint32_t MODE_DENSE = 0, MODE_HASH = 1;
 constexpr uint32_t QF_NO_MUST = 1;
@@ -71,7 +72,7 @@ struct DevQuery {
     uint32_t n_items;
     uint32_t n_col;       // column leaves, stored after the n_leaves block leaves
     uint32_t col_req;     // mask bits block phases have fully decided: a slot lacking one can never match
-    uint32_t pad[1];
+    uint32_t n_stream;    // trailing block leaves (of the n_leaves) that are streamed, one warp per leaf
 };
 static_assert(sizeof(DevQuery) == 48, "DevQuery is uploaded as a flat array");
 

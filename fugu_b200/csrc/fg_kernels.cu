@@ -227,6 +227,7 @@ struct Shared {
     uint32_t leafmask;  // leaves with at least one needed block in the current scan pass
     uint32_t rlo, rhi, shift, done, gtheta;
     uint32_t match;
+    uint32_t theta_cta;  // sortable f32: best k-th score any warp of this CTA has reached (shared pre-test threshold)
     int32_t col_field;  // >= 0: every column leaf takes its norms from this fieldnorm field (ctab holds its cache)
     float ctab[256];    // BM25 norm cache K1*(1-B+B*dl/avg) of col_field, by fieldnorm id
     unsigned long long st_blocks, st_redecode, st_scored;
@@ -236,8 +237,66 @@ struct Shared {
 __device__ __forceinline__ float byte_f32(uint32_t w, int j) {
     return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650u | (uint32_t)j)) - 8388608.0f;
 }
+// same with the 2^23 pattern held in a register, so that the selector is an immediate of PRMT
+template <int J>
+__device__ __forceinline__ float byte_f32_r(uint32_t w, uint32_t magic) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(w), "r"(magic), "n"(0x7650 | J));
+    return __uint_as_float(r) - 8388608.0f;
+}
+__device__ __forceinline__ void col_term8(uint2 t, float w, uint32_t magic, const float n[8], float v[8]) {
+    v[0] += w * tf_factor(byte_f32_r<0>(t.x, magic), n[0]);
+    v[1] += w * tf_factor(byte_f32_r<1>(t.x, magic), n[1]);
+    v[2] += w * tf_factor(byte_f32_r<2>(t.x, magic), n[2]);
+    v[3] += w * tf_factor(byte_f32_r<3>(t.x, magic), n[3]);
+    v[4] += w * tf_factor(byte_f32_r<0>(t.y, magic), n[4]);
+    v[5] += w * tf_factor(byte_f32_r<1>(t.y, magic), n[5]);
+    v[6] += w * tf_factor(byte_f32_r<2>(t.y, magic), n[6]);
+    v[7] += w * tf_factor(byte_f32_r<3>(t.y, magic), n[7]);
+}
+// number of non-zero bytes of x
+__device__ __forceinline__ uint32_t nonzero_bytes(uint32_t x) {
+    return __popc((((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u);
+}
 
 __device__ __forceinline__ void smem_add_f32(float* p, float v) { atomicAdd(p, v); }
+
+// ---- streamed leaves ---------------------------------------------------------------------------
+// A sparse insert leaf of a dense-window pure union (a few blocks per window at most) is walked by ONE
+// warp, block after block, without skip scan / worklist / phase barriers: decode, score, float atomics.
+__device__ __forceinline__ uint32_t stream_block(const SearchParams& p, const DevLeaf& L, const uint4 e,
+                                                 uint32_t rlo, uint32_t rhi, float* acc, int lane) {
+    const uint32_t bd = e.w & 63u, bt = (e.w >> 6) & 63u, n = ((e.w >> 12) & 127u) + 1u;
+    const uint32_t* wd = reinterpret_cast<const uint32_t*>(p.ix.blk + (size_t)e.z * 16u);
+    uint32_t g[4], t[4];
+    unpack4(wd, lane, bd, g);
+    unpack4(wd + 4 * bd, lane, bt, t);
+    g[1] += g[0]; g[2] += g[1]; g[3] += g[2];
+    const uint32_t off = warp_excl_scan(g[3], lane) + e.y + 4u * lane;
+    uint32_t d[4];
+    bool ok[4];
+    float nrm[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        d[j] = off + g[j] + j;
+        ok[j] = 4u * lane + j < n && d[j] >= rlo && d[j] < rhi;
+    }
+    const int ff = L.fn_field;
+    const uint8_t* fnp = p.ix.fnorm[ff < 0 ? 0 : ff];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        nrm[j] = L.cnorm;
+        if (ok[j] && ff >= 0) nrm[j] = __ldg(p.ix.cache + ff * 256 + __ldg(fnp + d[j]));
+    }
+    uint32_t cnt = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+        if (ok[j]) {
+            smem_add_f32(&acc[d[j] - rlo], L.weight * tf_factor((float)(t[j] + 1u), nrm[j]));
+            cnt++;
+        }
+    return cnt;
+}
 
 // ---- column leaves (dense tf columns, fg_api.cu: fg_index_upload) ---------------------------------
 // Pure-union dense window: add the scores of every column leaf to the 4 docs rlo + 4g .. +3.
@@ -339,6 +398,7 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nl = (int)q.n_leaves;   // block leaves; the q.n_col column leaves follow them in S.leaf
     const int ncol = (int)q.n_col;
+    const int nlp = nl - (int)q.n_stream;  // leaves evaluated in clause phases; [nlp, nl) are streamed
     const uint4* __restrict__ skip = p.ix.skip;
     const int k = (int)q.k;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -354,7 +414,7 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
         S.cur[tid] = a;
         S.cur_next[tid] = a;
         int l1 = tid + 1;  // leaves [tid, phase_end) share (role, bit) = one clause phase
-        while (!p.deterministic && !L.solo && l1 < nl && S.leaf[l1].role == L.role && S.leaf[l1].bit == L.bit &&
+        while (!p.deterministic && !L.solo && l1 < nlp && S.leaf[l1].role == L.role && S.leaf[l1].bit == L.bit &&
                !S.leaf[l1].solo) l1++;
         S.phase_end[tid] = (uint32_t)l1;
         // blocks of an insert leaf that overlap the item's doc range (few => resident)
@@ -370,7 +430,7 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
         S.res_cnt[tid] = cnt;
     }
     if (tid == 0) {
-        S.res_n = 0; S.match = 0; S.st_blocks = 0; S.st_redecode = 0; S.st_scored = 0;
+        S.res_n = 0; S.match = 0; S.theta_cta = 0; S.st_blocks = 0; S.st_redecode = 0; S.st_scored = 0;
         int cf = ncol ? S.leaf[nl].fn_field : -1;
         for (int c = 1; c < ncol; c++) if (S.leaf[nl + c].fn_field != cf) cf = -1;
         S.col_field = cf;
@@ -495,10 +555,12 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
             if (lane == 0) {
                 uint32_t rlo = fb == EMPTY ? end : max(lo_, fb);
                 const bool fin = rlo >= end;
-                // dense windows start 4-aligned (lo_ is: work items are cut at multiples of 4 and a full
-                // window spans DW docs): columns and fieldnorms are read 4 docs per 32-bit load
-                if (DENSE) rlo &= ~3u;
+                // dense windows start 16-aligned (lo_ is: work items are cut at multiples of 16 and a full
+                // window spans DW docs): columns and fieldnorms are read 8 docs per 64-bit load
+                if (DENSE) rlo &= ~15u;
                 uint32_t rhi = DENSE ? (uint32_t)min((unsigned long long)rlo + DW, (unsigned long long)end) : chi;
+                // a plan of column leaves only keeps nothing in the slots: one round covers the whole range
+                if (DENSE && PURE && nl == 0 && !p.ix.alive && !p.match_bitmap) rhi = end;
                 S.done = fin;
                 if (rhi < rlo) rhi = rlo;
                 S.rlo = rlo;
@@ -510,7 +572,7 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
             }
             // scan resume points of phase 0 (insert leaves), see the phase loop
             {
-                const int pl1 = nl ? (int)S.phase_end[0] : 0;
+                const int pl1 = nlp ? (int)S.phase_end[0] : 0;
                 for (int i = lane; i < pl1 * NW; i += 32) {
                     const int l = i / NW, w = i % NW;
                     const uint32_t c0 = (uint32_t)((w - l) & (NW - 1));
@@ -545,9 +607,41 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
         if (p.prof && tid == 0) pt[7]++;
 #endif
 
+        // ---- streamed leaves: warp w walks the leaves nlp + w, nlp + w + NW, ... ----
+        if (DENSE && PURE && q.n_stream) {
+            for (int l = nlp + (p.deterministic ? 0 : warp); l < nl; l += (p.deterministic ? 1 : NW)) {
+                if (p.deterministic) {  // bit-reproducible sums: one leaf at a time, in leaf order
+                    __syncthreads();
+                    if (warp != (l - nlp) % NW) continue;
+                }
+                if (S.resident[l]) continue;
+                const DevLeaf& L = S.leaf[l];
+                uint32_t b = S.cur[l];
+                while (b < L.n_blocks) {
+                    const uint4 e = __ldg(&skip[L.blk_begin + b]);
+                    if (e.y >= rhi) break;
+                    if (e.x >= rlo) {
+                        const uint32_t c = stream_block(p, L, e, rlo, rhi, acc, lane);
+                        if (p.acct) {
+                            my_scored += c;
+                            if (lane == 0) {
+                                const uint32_t bd = e.w & 63u, bt = (e.w >> 6) & 63u, n = ((e.w >> 12) & 127u) + 1u;
+                                const unsigned long long by = ((n * bd + 7) >> 3) + ((n * bt + 7) >> 3) + 16;
+                                if (e.y >= lo) my_blocks += by; else my_redecode += by;
+                            }
+                        }
+                    }
+                    if (e.x >= rhi) break;  // continues into the next window
+                    b++;
+                }
+                if (lane == 0) { S.cur[l] = b; S.cur_next[l] = b; }
+            }
+            if (nlp == 0 || p.deterministic) __syncthreads();
+        }
+
         // ---- clause phases: leaves [l0, l1) share (role, bit) ----
         int l0 = 0;
-        while (l0 < nl) {
+        while (l0 < nlp) {
             const int l1 = (int)S.phase_end[l0];
             const uint32_t role = S.leaf[l0].role, bit = S.leaf[l0].bit, req = S.leaf[l0].req;
             // LF_NOFILT: a filter-role leaf without usable precondition bits (an earlier clause has a
@@ -622,7 +716,7 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
                 PROF(2);  // skip scan
                 // only one leaf has blocks in this pass (typical: the other leaves of the clause are short or
                 // resident): a slot is then touched by one thread only -> plain adds instead of CAS-loop atomics
-                const bool solo = __popc(S.leafmask) <= 1;
+                const bool solo = __popc(S.leafmask) <= 1 && !q.n_stream;  // streamed leaves add concurrently
                 // (b) decode GRP blocks per warp step
                 for (int sg = 0; sg < NW; sg++) {
                 const uint32_t total = S.segcnt[sg];
@@ -862,7 +956,7 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
             // score threshold shared by all work items of the query: >= k docs are known to score at
             // least this much, so anything strictly below can never reach the final top-k
             {
-                const uint32_t gt = S.gtheta;
+                const uint32_t gt = max(S.gtheta, S.theta_cta);  // other items of the query / other warps of this CTA
                 if (gt) theta_s = fmaxf(theta_s, unsortable(gt));
             }
             const int n4 = DENSE ? (int)((rhi - rlo + 3) >> 2) : HS / 4;
@@ -875,6 +969,86 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
                 // a positive score and matches; only slots that can enter the top-k take the slow path
                 const bool count = p.want_counts != 0;
                 const bool use_acc = nl > 0;  // without block leaves the slots stay zero: scores come from columns
+                if (ncol && S.col_field >= 0) {
+                    // column windows: 8 docs per thread and step. The fieldnorm ids and every column's tf
+                    // bytes arrive as one 64-bit load each (windows start 16-aligned), the norms come
+                    // from the 1 KB table in shared memory, a term costs PRMT, 2 FADD, MUFU.RCP, FMUL, FFMA.
+                    uint32_t magic;
+                    asm volatile("mov.u32 %0, 0x4B000000;" : "=r"(magic));
+                    const int n8 = (int)((rhi - rlo + 7) >> 3);
+                    const DevLeaf* CL = &S.leaf[nl];
+                    const uint8_t* fnb = p.ix.fnorm[S.col_field] + rlo;
+                    uint32_t seen_t = 0;
+                    for (int g0 = warp * 32; g0 < n8; g0 += NT) {
+                        const int g = g0 + lane;
+                        {   // threshold reached by any warp of the CTA
+                            const uint32_t tc = S.theta_cta;
+                            if (tc != seen_t) { seen_t = tc; theta_s = fmaxf(theta_s, unsortable(tc)); }
+                        }
+                        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                        uint32_t px = 0, py = 0;  // OR of the columns' tf bytes: non-zero byte = doc matches
+                        if (g < n8) {
+                            const uint32_t o8 = 8u * (uint32_t)g;
+                            const uint2 fn8 = __ldg(reinterpret_cast<const uint2*>(fnb + o8));
+                            uint2 ta = __ldg(reinterpret_cast<const uint2*>(CL[0].col + rlo + o8)), tb = make_uint2(0u, 0u);
+                            if (ncol > 1) tb = __ldg(reinterpret_cast<const uint2*>(CL[1].col + rlo + o8));
+                            if (use_acc) {
+                                const float4 a0 = a4[2 * g], a1 = a4[2 * g + 1];
+                                a4[2 * g] = make_float4(0.f, 0.f, 0.f, 0.f);
+                                a4[2 * g + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                                v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w;
+                                v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
+                            }
+                            float n[8];
+#pragma unroll
+                            for (int j = 0; j < 4; j++) {
+                                n[j] = S.ctab[(fn8.x >> (8 * j)) & 255u];
+                                n[4 + j] = S.ctab[(fn8.y >> (8 * j)) & 255u];
+                            }
+                            int c = 0;
+                            while (true) {
+                                col_term8(ta, CL[c].weight, magic, n, v);
+                                px |= ta.x; py |= ta.y;
+                                if (c + 1 >= ncol) break;
+                                col_term8(tb, CL[c + 1].weight, magic, n, v);
+                                px |= tb.x; py |= tb.y;
+                                c += 2;
+                                if (c >= ncol) break;
+                                ta = __ldg(reinterpret_cast<const uint2*>(CL[c].col + rlo + o8));
+                                if (c + 1 < ncol) tb = __ldg(reinterpret_cast<const uint2*>(CL[c + 1].col + rlo + o8));
+                            }
+                        }
+                        if (count) {
+                            if (use_acc) {
+#pragma unroll
+                                for (int j = 0; j < 8; j++) my_matches += v[j] > 0.f;
+                            } else {
+                                my_matches += nonzero_bytes(px) + nonzero_bytes(py);
+                            }
+                        }
+                        const float mx = fmaxf(fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3])), fmaxf(fmaxf(v[4], v[5]), fmaxf(v[6], v[7])));
+                        if (__any_sync(FULL, mx > 0.f && mx + q.const_score >= theta_s)) {
+#pragma unroll
+                            for (int j = 0; j < 8; j++) {
+                                const float sc = v[j] + q.const_score;
+                                const bool c = v[j] > 0.f && sc >= theta_s;
+                                tk.offer(c, c ? make_key(sc, rlo + 8 * g + j) : 0ull, k, lane);
+                            }
+                            const float mine = tk.theta ? unsortable((uint32_t)(tk.theta >> 32)) : -INFINITY;
+                            if (mine > theta_s) {
+                                theta_s = mine;
+                                if (lane == 0) {
+                                    atomicMax(&S.theta_cta, sortable(mine));
+                                    if (p.qtheta) atomicMax(p.qtheta + it.query, sortable(mine));
+                                }
+                            } else if (p.qtheta) {
+                                // a long round: pick up what the other work items of the query have reached
+                                const uint32_t gq = __ldcg(p.qtheta + it.query);
+                                if (gq > seen_t) { if (lane == 0) atomicMax(&S.theta_cta, gq); theta_s = fmaxf(theta_s, unsortable(gq)); }
+                            }
+                        }
+                    }
+                } else
                 for (int g0 = warp * 32; g0 < n4; g0 += NT) {
                     const int g = g0 + lane;
                     float4 av = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -899,7 +1073,10 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
                         const float mine = tk.theta ? unsortable((uint32_t)(tk.theta >> 32)) : -INFINITY;
                         if (mine > theta_s) {
                             theta_s = mine;
-                            if (p.qtheta && lane == 0) atomicMax(p.qtheta + it.query, sortable(mine));
+                            if (lane == 0) {
+                                atomicMax(&S.theta_cta, sortable(mine));
+                                if (p.qtheta) atomicMax(p.qtheta + it.query, sortable(mine));
+                            }
                         }
                     }
                 }
@@ -974,7 +1151,10 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
                     const float mine = tk.theta ? unsortable((uint32_t)(tk.theta >> 32)) : -INFINITY;
                     if (mine > theta_s) {
                         theta_s = mine;
-                        if (p.qtheta && lane == 0) atomicMax(p.qtheta + it.query, sortable(mine));
+                        if (lane == 0) {
+                            atomicMax(&S.theta_cta, sortable(mine));
+                            if (p.qtheta) atomicMax(p.qtheta + it.query, sortable(mine));
+                        }
                     }
                 }
             }
