@@ -14,6 +14,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libfugu_gpu.so")
+LIB_PATH = os.environ.get("FG_LIB", LIB_PATH)  # dev: alternative builds of the same library
 
 FG_OK = 0
 FG_ERR_INVALID = -1

@@ -91,8 +91,8 @@ struct fg_ctx {
     std::mutex mu;
     int n_sms = 0;
     // side streams + events: the per-class search kernels of one batch run concurrently
-    cudaStream_t aux[3] = {nullptr, nullptr, nullptr};
-    cudaEvent_t fork_ev = nullptr, join_ev[3] = {nullptr, nullptr, nullptr};
+    cudaStream_t aux[NCLS - 1] = {};
+    cudaEvent_t fork_ev = nullptr, join_ev[NCLS - 1] = {};
     // small cache of device blocks for the per-call buffers (plans, partial lists, results):
     // cudaMalloc/cudaFree per request would dominate the host side of a 5000-query batch
     std::mutex pool_mu;
@@ -150,7 +150,7 @@ extern "C" int32_t fg_ctx_create(int32_t device, fg_ctx** out) {
     c->n_sms = pr.multiProcessorCount;
     CU(cudaStreamCreateWithFlags(&c->own, cudaStreamNonBlocking));
     c->stream = c->own;
-    for (int i = 0; i < 3; i++) {
+    for (int i = 0; i < NCLS - 1; i++) {
         CU(cudaStreamCreateWithFlags(&c->aux[i], cudaStreamNonBlocking));
         CU(cudaEventCreateWithFlags(&c->join_ev[i], cudaEventDisableTiming));
     }
@@ -162,7 +162,7 @@ extern "C" void fg_ctx_destroy(fg_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->own) cudaStreamDestroy(c->own);
-    for (int i = 0; i < 3; i++) { if (c->aux[i]) cudaStreamDestroy(c->aux[i]); if (c->join_ev[i]) cudaEventDestroy(c->join_ev[i]); }
+    for (int i = 0; i < NCLS - 1; i++) { if (c->aux[i]) cudaStreamDestroy(c->aux[i]); if (c->join_ev[i]) cudaEventDestroy(c->join_ev[i]); }
     if (c->fork_ev) cudaEventDestroy(c->fork_ev);
     for (auto& b : c->pool) cudaFree(b.first);
     delete c;
@@ -531,7 +531,7 @@ struct fg_batch {
     unsigned long long* d_stats = nullptr;
     uint32_t* d_qtheta = nullptr;
     size_t sz[7] = {0, 0, 0, 0, 0, 0, 0};
-    uint32_t class_count[4] = {0, 0, 0, 0};
+    uint32_t class_count[NCLS] = {};
     uint64_t n_launches = 0;
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};  // before search, after search, after merge
 };
@@ -569,6 +569,8 @@ extern "C" int32_t fg_batch_prepare_ex(fg_index* ix, const fg_query_batch* qb, u
     if (!ix || !qb || !out) return fail(FG_ERR_INVALID, "fg_batch_prepare: NULL argument");
     const bool use_cols = !(prep_flags & FG_PREP_NO_COLUMNS) && ix->n_cols && !getenv("FG_NO_COLUMNS");
     const uint64_t COL_COST_DIV = std::max<uint64_t>(1, env_u64("FG_COL_COST_DIV", 4));
+    const bool USE_COLSCAN = env_u64("FG_COLSCAN", 1) != 0;
+    uint64_t n_colscan_items = 0;
     const uint64_t STREAM_MAX_BPW = env_u64("FG_STREAM_MAX_BPW", 6);  // blocks per dense window of a streamed leaf
     *out = nullptr;
     if (qb->n_queries && (!qb->queries || (qb->n_clauses && !qb->clauses) || (qb->n_leaves && !qb->leaves)))
@@ -789,6 +791,11 @@ extern "C" int32_t fg_batch_prepare_ex(fg_index* ix, const fg_query_batch* qb, u
                 if (dl[i].role == ROLE_INSERT && dl[i].n_blocks >= SOLO_MIN_BLOCKS) dl[i].solo = 1;
         }
         D.n_items = ni;
+        // column-scan class: a pure union with a column insert leaf whose block leaves are all streamed
+        // and whose column leaves share one fieldnorm field
+        bool colscan = USE_COLSCAN && mode == MODE_DENSE && (D.flags & QF_PURE_UNION) && col_insert && D.n_stream == nbl && nbl <= (size_t)NW && q.k <= 128;
+        for (int i = 0; colscan && i < n_ctmp; i++) colscan = ctmp[i].fn_field >= 0 && ctmp[i].fn_field == ctmp[0].fn_field;
+        n_colscan_items += colscan ? ni : 0;
         for (uint32_t j = 0; j < ni; j++) {
             DevItem it{};
             it.query = qi;
@@ -797,12 +804,14 @@ extern "C" int32_t fg_batch_prepare_ex(fg_index* ix, const fg_query_batch* qb, u
             it.doc_hi = j + 1 == ni ? nd : ((uint32_t)((uint64_t)nd * (j + 1) / ni) & ~15u);
             it.mode = mode;
             it.slot = D.item_begin + j;
-            it.cls = (mode == MODE_DENSE ? 0u : 2u) + ((D.flags & QF_PURE_UNION) ? 0u : 1u);
+            it.cls = colscan ? 4u : (mode == MODE_DENSE ? 0u : 2u) + ((D.flags & QF_PURE_UNION) ? 0u : 1u);
             items.push_back(it);
             item_cost.push_back(total_bytes / ni);
         }
     }
 
+    if (kmax > 128 && n_colscan_items)  // the column-scan kernel has no 32-row queue variant
+        for (auto& it : items) if (it.cls == 4u) it.cls = 0u;
     const double t_lower = now_ms();
     // one launch per kernel class, heavy items first inside a class (the hardware CTA scheduler is
     // the work queue): counting sort on (class, 64 half-octave cost buckets), O(n)
@@ -815,12 +824,12 @@ extern "C" int32_t fg_batch_prepare_ex(fg_index* ix, const fg_query_batch* qb, u
             const uint32_t bk = std::min<uint32_t>(63u, lg * 2u + sub);
             return items[i].cls * 64u + (63u - bk);
         };
-        uint32_t hist[257] = {0};
+        uint32_t hist[NCLS * 64 + 1] = {0};
         for (size_t i = 0; i < items.size(); i++) hist[bucket(i) + 1]++;
-        for (int i = 0; i < 256; i++) hist[i + 1] += hist[i];
+        for (int i = 0; i < NCLS * 64; i++) hist[i + 1] += hist[i];
         for (size_t i = 0; i < items.size(); i++) sorted[hist[bucket(i)]++] = items[i];
     }
-    uint32_t class_count[4] = {0, 0, 0, 0};
+    uint32_t class_count[NCLS] = {};
     for (auto& it : items) class_count[it.cls]++;
 
     fg_ctx* ctx = ix->ctx;
@@ -832,7 +841,7 @@ extern "C" int32_t fg_batch_prepare_ex(fg_index* ix, const fg_query_batch* qb, u
     b->kcap = kmax;
     b->ks = kmax <= 32 ? 1 : kmax <= 128 ? 4 : 32;
     b->sum_k = sum_k;
-    for (int i = 0; i < 4; i++) b->class_count[i] = class_count[i];
+    for (int i = 0; i < NCLS; i++) b->class_count[i] = class_count[i];
     auto up = [&](const void* src, size_t bytes, void** dst, size_t* sz) -> int32_t {
         *sz = std::max<size_t>(bytes, 16);
         CU(pool_alloc(ctx, dst, *sz));
@@ -892,12 +901,12 @@ extern "C" int32_t fg_batch_execute(fg_batch* b, uint32_t flags, uint32_t k_stri
     CU(cudaEventRecord(b->ev[0], st));
     {
         // fork: class 0 on the main stream, classes 1..3 on side streams, join before the merge
-        void* streams[4] = {st, ctx->aux[0], ctx->aux[1], ctx->aux[2]};
+        void* streams[NCLS] = {st, ctx->aux[0], ctx->aux[1], ctx->aux[2], ctx->aux[3]};
         CU(cudaEventRecord(ctx->fork_ev, st));
-        for (int i = 0; i < 3; i++)
+        for (int i = 0; i < NCLS - 1; i++)
             if (b->class_count[i + 1]) CU(cudaStreamWaitEvent(ctx->aux[i], ctx->fork_ev, 0));
         launch_search(p, b->ks, b->class_count, streams);
-        for (int i = 0; i < 3; i++)
+        for (int i = 0; i < NCLS - 1; i++)
             if (b->class_count[i + 1]) {
                 CU(cudaEventRecord(ctx->join_ev[i], ctx->aux[i]));
                 CU(cudaStreamWaitEvent(st, ctx->join_ev[i], 0));
@@ -921,7 +930,7 @@ extern "C" int32_t fg_batch_execute(fg_batch* b, uint32_t flags, uint32_t k_stri
     launch_merge(m, b->ks, st);
     CU(cudaEventRecord(b->ev[2], st));
     b->n_launches = (b->n_queries ? 1 : 0);
-    for (int i = 0; i < 4; i++) b->n_launches += b->class_count[i] ? 1 : 0;
+    for (int i = 0; i < NCLS; i++) b->n_launches += b->class_count[i] ? 1 : 0;
     CU(cudaGetLastError());
     return FG_OK;
 }

@@ -81,7 +81,7 @@ struct DevItem {
     uint32_t doc_lo, doc_hi;
     uint32_t mode;
     uint32_t slot;  // index into partial arrays (query.item_begin + j)
-    uint32_t cls;   // kernel class: 0 dense pure, 1 dense masked, 2 hash pure, 3 hash masked
+    uint32_t cls;   // kernel class: 0 dense pure, 1 dense masked, 2 hash pure, 3 hash masked, 4 column scan
     uint32_t pad[2];
 };
 
@@ -143,7 +143,12 @@ constexpr int SLOTS = DW > HS ? DW : HS;
 constexpr int CBW = 1024;        // candidate bitmap words (32768 bits; dense mode uses the first DW bits)
 constexpr int CB_LOG2 = 15;
 
-void launch_search(const SearchParams& p, int ks, const uint32_t class_count[4], void* const streams[4]);
+constexpr int NCLS = 5;          // kernel classes (DevItem::cls)
+#ifndef FG_CW
+#define FG_CW 6144
+#endif
+constexpr int CW = FG_CW;       // column-scan window (two accumulator buffers of CW floats)
+void launch_search(const SearchParams& p, int ks, const uint32_t class_count[NCLS], void* const streams[NCLS]);
 void launch_merge(const MergeParams& p, int ks, void* stream);
 void launch_merge_gathered(const void* hits, const uint32_t* n, uint32_t n_ranks, uint32_t n_queries,
                            uint32_t k, uint32_t k_stride, void* out_hits, uint32_t* out_n, int ks,

@@ -1236,6 +1236,279 @@ __global__ void __launch_bounds__(NT, MINB) search_kernel(const SearchParams p) 
     run_item<KS, GRP, DENSE, PURE>(p, it, q, S, acc, keys, msk, DENSE ? cb_dense : cb_hash, wl, scratch, res_doc, res_val);
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// Column-scan kernel (class 4): pure unions with at least one column insert leaf whose block leaves are
+// all streamed. Every doc of the item's range is a candidate, so the item is walked in fixed windows
+// of CW docs with TWO accumulator buffers: while all warps scan window r (columns + buffer r&1), the
+// warps that own streamed leaves first decode those leaves' blocks of window r+1 into the other
+// buffer, so the decode latency chain (skip entry -> payload -> fieldnorm -> norm) hides behind the
+// scan. Scan chunks (256 docs per warp step) are claimed dynamically, so a warp that streamed takes
+// fewer of them. One barrier per window, no skip scan, no worklists, no round setup.
+// ---------------------------------------------------------------------------------------------------
+struct CShared {
+    DevQuery q;
+    DevLeaf leaf[MAX_LEAVES];
+    float ctab[256];
+    uint32_t chunk[2];
+    uint32_t theta_cta;
+    uint32_t match;
+    unsigned long long st_blocks, st_redecode, st_scored;
+};
+
+template <int KS, int MINB>
+__global__ void __launch_bounds__(NT, MINB) colscan_kernel(const SearchParams p) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ CShared S;
+    float* acc = reinterpret_cast<float*>(smem);                       // [2][CW]
+    uint64_t* scratch = reinterpret_cast<uint64_t*>(smem + 2 * CW * 4);  // [NW][KS][32]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const DevItem it = p.items[p.item_begin + blockIdx.x];
+    {
+        const DevQuery q0 = p.queries[it.query];
+        if (tid == 0) {
+            S.q = q0;
+            S.chunk[0] = 0; S.chunk[1] = 0; S.match = 0;
+            S.theta_cta = p.qtheta ? __ldcg(p.qtheta + it.query) : 0u;
+            S.st_blocks = 0; S.st_redecode = 0; S.st_scored = 0;
+        }
+        if (tid < q0.n_leaves + q0.n_col) S.leaf[tid] = p.leaves[q0.leaf_begin + tid];
+    }
+    __syncthreads();
+    const DevQuery& q = S.q;
+    const int nl = (int)q.n_leaves, ncol = (int)q.n_col, k = (int)q.k;
+    const DevLeaf* CL = &S.leaf[nl];
+    const int cf = CL[0].fn_field;
+    S.ctab[tid] = __ldg(p.ix.cache + cf * 256 + tid);
+    if (nl) {
+        float4* a4 = reinterpret_cast<float4*>(acc);
+        for (int i = tid; i < 2 * CW / 4; i += NT) a4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const uint4* __restrict__ skip = p.ix.skip;
+    const uint32_t lo0 = it.doc_lo, end = it.doc_hi;
+    // Streamed leaf of this warp (leaf index = warp; the planner keeps nl <= NW for this class). A block is
+    // decoded and scored ONCE: its 128 (doc, score) pairs stay in registers (4 per lane, ascending docs)
+    // and are applied to whichever window they fall into, round after round -- no re-decode of blocks
+    // that straddle windows, however sparse the list.
+    uint32_t cur = 0;
+    uint32_t cd[4] = {EMPTY, EMPTY, EMPTY, EMPTY};  // carried postings, EMPTY = consumed
+    float cv[4] = {0.f, 0.f, 0.f, 0.f};
+    if (warp < nl) {
+        const DevLeaf& L = S.leaf[warp];
+        uint32_t a = 0, b = L.n_blocks;  // first block whose last_doc >= doc_lo
+        while (a < b) {
+            const uint32_t m = (a + b) >> 1;
+            if (__ldg(&skip[L.blk_begin + m]).x >= lo0) b = m; else a = m + 1;
+        }
+        cur = a;
+    }
+    uint32_t my_matches = 0, my_scored = 0;
+    unsigned long long my_blocks = 0, my_redecode = 0;
+    auto stream_leaf = [&](uint32_t wlo, uint32_t whi, float* buf) {
+        const DevLeaf& L = S.leaf[warp];
+        while (true) {
+            bool left = false;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                if (cd[j] < whi) {
+                    if (cd[j] >= wlo) { smem_add_f32(&buf[cd[j] - wlo], cv[j]); my_scored++; }
+                    cd[j] = EMPTY;
+                }
+                left = left || cd[j] != EMPTY;
+            }
+            if (__any_sync(FULL, left)) break;  // the block continues behind this window
+            if (cur >= L.n_blocks) break;
+            const uint4 e = __ldg(&skip[L.blk_begin + cur]);
+            if (e.y >= whi) break;              // the next block starts behind this window
+            cur++;
+            if (e.x < wlo) continue;            // (only before the item's first window)
+            const uint32_t bd = e.w & 63u, bt = (e.w >> 6) & 63u, n = ((e.w >> 12) & 127u) + 1u;
+            const uint32_t* wd = reinterpret_cast<const uint32_t*>(p.ix.blk + (size_t)e.z * 16u);
+            uint32_t g[4], t[4];
+            unpack4(wd, lane, bd, g);
+            unpack4(wd + 4 * bd, lane, bt, t);
+            g[1] += g[0]; g[2] += g[1]; g[3] += g[2];
+            const uint32_t off = warp_excl_scan(g[3], lane) + e.y + 4u * lane;
+            const int ff = L.fn_field;
+            const uint8_t* fnp = p.ix.fnorm[ff < 0 ? 0 : ff];
+            float nrm[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint32_t d = off + g[j] + j;
+                const bool ok = 4u * lane + j < n && d >= lo0 && d < end;
+                cd[j] = ok ? d : EMPTY;
+                nrm[j] = L.cnorm;
+                if (ok && ff >= 0) nrm[j] = __ldg(p.ix.cache + ff * 256 + __ldg(fnp + d));
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) cv[j] = L.weight * tf_factor((float)(t[j] + 1u), nrm[j]);
+            if (p.acct && lane == 0) my_blocks += ((n * bd + 7) >> 3) + ((n * bt + 7) >> 3) + 16;
+        }
+    };
+    auto stream_window = [&](uint32_t wlo, uint32_t whi, float* buf) {
+        if (p.deterministic) {  // bit-reproducible sums: one leaf at a time, in leaf order
+            for (int l = 0; l < nl; l++) {
+                if (warp == l) stream_leaf(wlo, whi, buf);
+                __syncthreads();
+            }
+        } else if (warp < nl) {
+            stream_leaf(wlo, whi, buf);
+        }
+    };
+    // without streamed leaves nothing lives in the accumulators: one window covers the whole range
+    const uint32_t step = nl ? (uint32_t)CW : (end - lo0 + 16u);
+    __syncthreads();
+    if (nl) {
+        stream_window(lo0, (uint32_t)min((unsigned long long)lo0 + step, (unsigned long long)end), acc);
+        __syncthreads();
+    }
+
+    WarpTopK<KS> tk;
+    tk.init();
+    float theta_s = -INFINITY;
+    uint32_t seen_t = 0;
+    uint32_t magic;
+    asm volatile("mov.u32 %0, 0x4B000000;" : "=r"(magic));
+    const bool count = p.want_counts != 0;
+    const uint8_t* fnb = p.ix.fnorm[cf];
+    const uint8_t* alive8 = reinterpret_cast<const uint8_t*>(p.ix.alive);
+
+    for (uint32_t wlo = lo0, r = 0; wlo < end; wlo += step, r++) {
+        const uint32_t whi = (uint32_t)min((unsigned long long)wlo + step, (unsigned long long)end);
+        float* buf = acc + (r & 1) * CW;
+        if (nl && whi < end)
+            stream_window(whi, (uint32_t)min((unsigned long long)whi + step, (unsigned long long)end), acc + ((r + 1) & 1) * CW);
+        const uint32_t n8 = (whi - wlo + 7) >> 3;
+        while (true) {
+            uint32_t c0 = 0;
+            if (lane == 0) c0 = atomicAdd(&S.chunk[r & 1], 1u);
+            c0 = __shfl_sync(FULL, c0, 0) * 32u;
+            if (c0 >= n8) break;
+            const uint32_t g = c0 + lane;
+            {   // threshold reached by any warp of the CTA
+                const uint32_t tc = S.theta_cta;
+                if (tc != seen_t) { seen_t = tc; theta_s = fmaxf(theta_s, unsortable(tc)); }
+            }
+            float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            uint32_t px = 0, py = 0;  // OR of the columns' tf bytes: non-zero byte = doc matches
+            float accmax = 0.f;
+            if (g < n8) {
+                const uint32_t d8 = wlo + 8u * g;
+                const uint2 fn8 = __ldg(reinterpret_cast<const uint2*>(fnb + d8));
+                uint2 ta = __ldg(reinterpret_cast<const uint2*>(CL[0].col + d8)), tb = make_uint2(0u, 0u);
+                if (ncol > 1) tb = __ldg(reinterpret_cast<const uint2*>(CL[1].col + d8));
+                if (nl) {
+                    float4* b4 = reinterpret_cast<float4*>(buf) + 2 * g;
+                    const float4 a0 = b4[0], a1 = b4[1];
+                    b4[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    b4[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w;
+                    v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
+                    accmax = fmaxf(fmaxf(fmaxf(a0.x, a0.y), fmaxf(a0.z, a0.w)), fmaxf(fmaxf(a1.x, a1.y), fmaxf(a1.z, a1.w)));
+                }
+                float n[8];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    n[j] = S.ctab[(fn8.x >> (8 * j)) & 255u];
+                    n[4 + j] = S.ctab[(fn8.y >> (8 * j)) & 255u];
+                }
+                int c = 0;
+                while (true) {
+                    col_term8(ta, CL[c].weight, magic, n, v);
+                    px |= ta.x; py |= ta.y;
+                    if (c + 1 >= ncol) break;
+                    col_term8(tb, CL[c + 1].weight, magic, n, v);
+                    px |= tb.x; py |= tb.y;
+                    c += 2;
+                    if (c >= ncol) break;
+                    ta = __ldg(reinterpret_cast<const uint2*>(CL[c].col + d8));
+                    if (c + 1 < ncol) tb = __ldg(reinterpret_cast<const uint2*>(CL[c + 1].col + d8));
+                }
+                if (alive8) {  // deleted docs: windows are 16-aligned, so docs d8..d8+7 are one byte of the bitset
+                    const uint32_t al = __ldg(alive8 + (d8 >> 3));
+#pragma unroll
+                    for (int j = 0; j < 8; j++) v[j] = ((al >> j) & 1u) ? v[j] : 0.f;
+                }
+                if (p.match_bitmap) {
+                    uint32_t bits = 0;
+#pragma unroll
+                    for (int j = 0; j < 8; j++) bits |= (v[j] > 0.f ? 1u : 0u) << j;
+                    if (bits) atomicOr(p.match_bitmap + (size_t)it.query * p.bitmap_words + (d8 >> 5), bits << (d8 & 31));
+                }
+            }
+            if (count) {
+                // matches = docs with a non-zero column byte, + docs that only streamed leaves touched (rare)
+                if (alive8 || accmax > 0.f) {
+#pragma unroll
+                    for (int j = 0; j < 8; j++) my_matches += v[j] > 0.f;
+                } else {
+                    my_matches += nonzero_bytes(px) + nonzero_bytes(py);
+                }
+            }
+            const float mx = fmaxf(fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3])), fmaxf(fmaxf(v[4], v[5]), fmaxf(v[6], v[7])));
+            if (__any_sync(FULL, mx > 0.f && mx + q.const_score >= theta_s)) {
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const float sc = v[j] + q.const_score;
+                    const bool c = v[j] > 0.f && sc >= theta_s;
+                    if (!__any_sync(FULL, c)) continue;
+                    tk.offer(c, c ? make_key(sc, wlo + 8 * g + j) : 0ull, k, lane);
+                }
+                const float mine = tk.theta ? unsortable((uint32_t)(tk.theta >> 32)) : -INFINITY;
+                if (mine > theta_s) {
+                    theta_s = mine;
+                    if (lane == 0) {
+                        atomicMax(&S.theta_cta, sortable(mine));
+                        if (p.qtheta) atomicMax(p.qtheta + it.query, sortable(mine));
+                    }
+                } else if (p.qtheta) {  // pick up what the other work items of the query have reached
+                    const uint32_t gq = __ldcg(p.qtheta + it.query);
+                    if (gq > seen_t) { if (lane == 0) atomicMax(&S.theta_cta, gq); theta_s = fmaxf(theta_s, unsortable(gq)); }
+                }
+            }
+        }
+        if (tid == 0) S.chunk[(r + 1) & 1] = 0;
+        __syncthreads();
+    }
+
+    // ---- epilogue: merge the warp queues, write the partial list ----
+    my_matches = warp_sum(my_matches);
+    my_scored = warp_sum(my_scored);
+    if (lane == 0) {
+        atomicAdd(&S.match, my_matches);
+        if (p.acct) {
+            atomicAdd(&S.st_scored, (unsigned long long)my_scored);
+            atomicAdd(&S.st_blocks, my_blocks);
+            atomicAdd(&S.st_redecode, my_redecode);
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < KS; s++) scratch[(warp * KS + s) * 32 + lane] = tk.q[s];
+    __syncthreads();
+    if (warp == 0) {
+        for (int w = 1; w < NW; w++) {
+#pragma unroll
+            for (int s = 0; s < KS; s++) {
+                const uint64_t c = scratch[(w * KS + s) * 32 + lane];
+                tk.offer(c != 0, c, k, lane);
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < KS; s++) {
+            const int rr = s * 32 + lane;
+            if (rr < (int)p.kcap) p.partial[(size_t)it.slot * p.kcap + rr] = rr < k ? tk.q[s] : 0;
+        }
+        if (lane == 0) {
+            p.partial_count[it.slot] = S.match;
+            if (p.stats && p.acct) {
+                atomicAdd(p.stats + 0, S.st_blocks);
+                atomicAdd(p.stats + 1, S.st_redecode);
+                atomicAdd(p.stats + 2, S.st_scored);
+            }
+        }
+    }
+}
+
 // one warp per query: merge the per-item partial lists
 template <int KS>
 __global__ void __launch_bounds__(128) merge_kernel(const MergeParams p) {
@@ -1361,11 +1634,29 @@ static void launch_one(SearchParams p, uint32_t begin, uint32_t count, cudaStrea
     search_kernel<KS, GRP, MINB, DENSE, PURE><<<count, NT, smem, st>>>(p);
 }
 
-// items are grouped by kernel class: [dense pure | dense masked | hash pure | hash masked]
-void launch_search(const SearchParams& p, int ks, const uint32_t class_count[4], void* const streams[4]) {
+#ifndef COLSCAN_MINB
+#define COLSCAN_MINB 4
+#endif
+template <int KS, int MINB>
+static void launch_colscan(SearchParams p, uint32_t begin, uint32_t count, cudaStream_t st) {
+    if (!count) return;
+    static bool configured = false;
+    const int smem = 2 * CW * 4 + NW * KS * 32 * 8;
+    if (!configured) {
+        cudaFuncSetAttribute(colscan_kernel<KS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        configured = true;
+    }
+    p.item_begin = begin;
+    colscan_kernel<KS, MINB><<<count, NT, smem, st>>>(p);
+}
+
+// items are grouped by kernel class: [dense pure | dense masked | hash pure | hash masked | column scan]
+void launch_search(const SearchParams& p, int ks, const uint32_t class_count[NCLS], void* const streams[NCLS]) {
     cudaStream_t s0 = (cudaStream_t)streams[0], s1 = (cudaStream_t)streams[1], s2 = (cudaStream_t)streams[2],
-                 s3 = (cudaStream_t)streams[3];
-    const uint32_t b1 = class_count[0], b2 = b1 + class_count[1], b3 = b2 + class_count[2];
+                 s3 = (cudaStream_t)streams[3], s4 = (cudaStream_t)streams[4];
+    const uint32_t b1 = class_count[0], b2 = b1 + class_count[1], b3 = b2 + class_count[2], b4 = b3 + class_count[3];
+    if (ks <= 1) launch_colscan<1, COLSCAN_MINB>(p, b4, class_count[4], s4);
+    else if (ks <= 4) launch_colscan<4, 3>(p, b4, class_count[4], s4);
     if (ks <= 1) {
         launch_one<1, 1, PURE_MINB, true, true>(p, 0, class_count[0], s0);
         launch_one<1, 1, 4, true, false>(p, b1, class_count[1], s1);
