@@ -286,8 +286,10 @@ def main():
         f_n = torch.zeros(nq, dtype=torch.int32, device=dev)
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
+    counts = bool(os.environ.get("FG_BENCH_COUNTS"))  # TopDocs::with_limit does not count matches: off by default
+
     def step():
-        pb.execute(d_hits.data_ptr(), d_n.data_ptr(), d_c.data_ptr(), None, k_stride=k)
+        pb.execute(d_hits.data_ptr(), d_n.data_ptr(), d_c.data_ptr() if counts else None, None, k_stride=k)
         if world > 1:
             dist.all_gather_into_tensor(g_hits, d_hits)
             dist.all_gather_into_tensor(g_n, d_n)
@@ -355,7 +357,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        h_hits, h_n, h_c, _ = ds.search_batch(qset)  # fgh_search_batch: strings -> plan -> H2D -> kernels -> D2H
+        h_hits, h_n, h_c, _ = ds.search_batch(qset, want_counts=counts)  # fgh_search_batch: strings -> plan -> H2D -> kernels -> D2H
         if world > 1:
             dist.all_gather_into_tensor(g_hits, torch.from_numpy(h_hits.view(np.int32).reshape(nq, k, 2)).to(dev))
             dist.all_gather_into_tensor(g_n, torch.from_numpy(h_n.view(np.int32)).to(dev))

@@ -990,8 +990,10 @@ extern "C" int32_t fg_search_batch(fg_index* ix, const fg_query_batch* qb, uint3
     g1.p = d_hits; g1.sz = nq * k_stride * sizeof(fg_hit);
     CU(pool_alloc(ctx, &d_n, nq * 4));
     g2.p = d_n; g2.sz = nq * 4;
-    CU(pool_alloc(ctx, &d_c, nq * 4));
-    g3.p = d_c; g3.sz = nq * 4;
+    if (out_match_count) {  // optional: the reference's TopDocs collector does not count matches
+        CU(pool_alloc(ctx, &d_c, nq * 4));
+        g3.p = d_c; g3.sz = nq * 4;
+    }
     rc = fg_batch_execute(b, 0, k_stride, d_hits, d_n, d_c, nullptr);
     if (rc) return rc;
     std::lock_guard<std::mutex> g(ctx->mu);

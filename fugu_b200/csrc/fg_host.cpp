@@ -997,7 +997,8 @@ extern "C" int32_t fgh_search_batch(fgh_dataset* ds, uint32_t n, const char* con
     const uint32_t kmax = pb.kmax;
     std::vector<fg_hit> hits((size_t)n * kmax);
     std::vector<uint32_t> nh(n), cnt(n);
-    int32_t r = fg_search_batch(ds->index, &qb, kmax, hits.data(), nh.data(), cnt.data());
+    // match counts are optional: the reference's TopDocs collector does not count (src/db/search.rs:162)
+    int32_t r = fg_search_batch(ds->index, &qb, kmax, hits.data(), nh.data(), out_match_count ? cnt.data() : nullptr);
     if (r) return r;
     for (uint32_t i = 0; i < n; i++) {
         const bool bad = pb.rc[i] != FG_OK;

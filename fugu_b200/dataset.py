@@ -295,17 +295,19 @@ class Dataset:
                                   C.byref(n), C.byref(cnt)))
         return [FuguSearchResult(self.doc_id(int(h["doc"])), float(h["score"]), int(h["doc"])) for h in hits[:n.value]]
 
-    def search_batch(self, queries, filters: list[list[str]] | None = None, page: int = 0, per_page: int = 20):
-        """Batched form: returns (hits[n, per_page], n_hits[n], match_count[n], status[n])."""
+    def search_batch(self, queries, filters: list[list[str]] | None = None, page: int = 0, per_page: int = 20,
+                     want_counts: bool = True):
+        """Batched form: returns (hits[n, per_page], n_hits[n], match_count[n], status[n]).
+        want_counts=False mirrors the reference exactly (TopDocs does not count matches): match_count is None."""
         qs = queries if isinstance(queries, QuerySet) else QuerySet(queries, filters, page, per_page)
         n, per_page = qs.n, qs.per_page
         hits = np.zeros((n, per_page), nat.HIT_DT)
         nh = np.zeros(n, np.uint32)
-        cnt = np.zeros(n, np.uint32)
+        cnt = np.zeros(n, np.uint32) if want_counts else None
         status = np.zeros(n, np.int32)
         nat.check(_L().fgh_search_batch(self.h, n, qs.qarr, qs.farr, None if qs.foffs is None else qs.foffs.ctypes.data,
                                         qs.pages.ctypes.data, qs.pps.ctypes.data, per_page, hits.ctypes.data, nh.ctypes.data,
-                                        cnt.ctypes.data, status.ctypes.data))
+                                        None if cnt is None else cnt.ctypes.data, status.ctypes.data))
         return hits, nh, cnt, status
 
     def close(self) -> None:
