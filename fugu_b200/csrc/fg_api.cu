@@ -766,16 +766,17 @@ extern "C" int32_t fg_batch_prepare_ex(fg_index* ix, const fg_query_batch* qb, u
         const uint32_t nd = ix->n_docs;
         const uint64_t dmin = n_must ? DENSE_MIN_MUST : DENSE_MIN;
         const uint32_t mode = (col_insert || insert_postings * (uint64_t)DW >= dmin * (uint64_t)std::max<uint32_t>(nd, 1)) ? MODE_DENSE : MODE_HASH;
-        // sparse insert leaves of a dense-window pure union are streamed by one warp each (no skip scan,
-        // no phase barriers): stable-partition them behind the leaves that keep their clause phases
-        if (mode == MODE_DENSE && (D.flags & QF_PURE_UNION) && STREAM_MAX_BPW) {
-            DevLeaf* B = dl.data() + ql0;
-            auto streams = [&](const DevLeaf& L) { return (uint64_t)L.n_blocks * DW <= STREAM_MAX_BPW * (uint64_t)std::max<uint32_t>(nd, 1); };
-            DevLeaf st[MAX_LEAVES];
-            uint32_t ns = 0, np = 0;
-            for (size_t i = 0; i < nbl; i++) { if (streams(B[i])) st[ns++] = B[i]; else B[np++] = B[i]; }
-            for (uint32_t i = 0; i < ns; i++) { st[i].lflags |= LF_STREAM; B[np + i] = st[i]; }
-            D.n_stream = ns;
+        // column-scan class: a pure union with a column insert leaf whose block leaves are all sparse enough
+        // to be streamed (one warp per leaf, at most NW of them) and whose column leaves share one
+        // fieldnorm field. Other dense plans keep their clause phases (all warps share the decode).
+        bool colscan = USE_COLSCAN && mode == MODE_DENSE && (D.flags & QF_PURE_UNION) && col_insert && nbl <= (size_t)NW &&
+                       q.k <= 128 && STREAM_MAX_BPW;
+        for (int i = 0; colscan && i < n_ctmp; i++) colscan = ctmp[i].fn_field >= 0 && ctmp[i].fn_field == ctmp[0].fn_field;
+        for (size_t i = 0; colscan && i < nbl; i++)
+            colscan = (uint64_t)dl[ql0 + i].n_blocks * DW <= STREAM_MAX_BPW * (uint64_t)std::max<uint32_t>(nd, 1);
+        if (colscan) {
+            for (size_t i = 0; i < nbl; i++) dl[ql0 + i].lflags |= LF_STREAM;
+            D.n_stream = (uint32_t)nbl;
         }
         // a dense window reads 1 B per doc per column leaf (+ the fieldnorm byte), at a fraction of the
         // per-byte cost of packed blocks; hash rounds only gather the columns at their candidates
@@ -791,11 +792,10 @@ extern "C" int32_t fg_batch_prepare_ex(fg_index* ix, const fg_query_batch* qb, u
                 if (dl[i].role == ROLE_INSERT && dl[i].n_blocks >= SOLO_MIN_BLOCKS) dl[i].solo = 1;
         }
         D.n_items = ni;
-        // column-scan class: a pure union with a column insert leaf whose block leaves are all streamed
-        // and whose column leaves share one fieldnorm field
-        bool colscan = USE_COLSCAN && mode == MODE_DENSE && (D.flags & QF_PURE_UNION) && col_insert && D.n_stream == nbl && nbl <= (size_t)NW && q.k <= 128;
-        for (int i = 0; colscan && i < n_ctmp; i++) colscan = ctmp[i].fn_field >= 0 && ctmp[i].fn_field == ctmp[0].fn_field;
         n_colscan_items += colscan ? ni : 0;
+        if (getenv("FG_DEBUG_PLAN") && !colscan && mode == MODE_DENSE)
+            fprintf(stderr, "[plan] q%u dense %s: %zu block leaves (%u streamed), %d column leaves, col_insert %d, k %u, items %u, bytes %llu\n", qi,
+                    (D.flags & QF_PURE_UNION) ? "pure" : "masked", nbl, D.n_stream, n_ctmp, (int)col_insert, q.k, ni, (unsigned long long)total_bytes);
         for (uint32_t j = 0; j < ni; j++) {
             DevItem it{};
             it.query = qi;
