@@ -568,7 +568,9 @@ extern "C" int32_t fg_batch_prepare(fg_index* ix, const fg_query_batch* qb, fg_b
 extern "C" int32_t fg_batch_prepare_ex(fg_index* ix, const fg_query_batch* qb, uint32_t prep_flags, fg_batch** out) {
     if (!ix || !qb || !out) return fail(FG_ERR_INVALID, "fg_batch_prepare: NULL argument");
     const bool use_cols = !(prep_flags & FG_PREP_NO_COLUMNS) && ix->n_cols && !getenv("FG_NO_COLUMNS");
-    const uint64_t COL_COST_DIV = std::max<uint64_t>(1, env_u64("FG_COL_COST_DIV", 4));
+    const uint64_t COL_COST_DIV = std::max<uint64_t>(1, env_u64("FG_COL_COST_DIV", 16));
+    const uint64_t COL_COST_DIV_PHASES = std::max<uint64_t>(1, env_u64("FG_COL_COST_DIV_PHASES", 2));
+    const uint64_t WINDOW_COST = env_u64("FG_WINDOW_COST", 4096);
     const bool USE_COLSCAN = env_u64("FG_COLSCAN", 1) != 0;
     uint64_t n_colscan_items = 0;
     const uint64_t STREAM_MAX_BPW = env_u64("FG_STREAM_MAX_BPW", 6);  // blocks per dense window of a streamed leaf
@@ -780,7 +782,9 @@ extern "C" int32_t fg_batch_prepare_ex(fg_index* ix, const fg_query_batch* qb, u
         }
         // a dense window reads 1 B per doc per column leaf (+ the fieldnorm byte), at a fraction of the
         // per-byte cost of packed blocks; hash rounds only gather the columns at their candidates
-        if (mode == MODE_DENSE && n_ctmp) total_bytes += (uint64_t)nd * (uint64_t)(n_ctmp + 1) / COL_COST_DIV;
+        if (mode == MODE_DENSE && n_ctmp) total_bytes += (uint64_t)nd * (uint64_t)(n_ctmp + 1) / (colscan ? COL_COST_DIV : COL_COST_DIV_PHASES);
+        // a dense window of the phase kernels has a fixed cost (barriers, skip scans, slot scan) whatever it decodes
+        if (mode == MODE_DENSE && !colscan) total_bytes += (uint64_t)(nd / DW + 1) * WINDOW_COST;
         const uint64_t ib = !(D.flags & QF_PURE_UNION) ? ITEM_BYTES_MASKED : (mode == MODE_DENSE ? ITEM_BYTES : ITEM_BYTES_HASH);
         uint64_t want = std::max<uint64_t>(1, (total_bytes + ib / 2) / ib);
         const uint32_t min_span = mode == MODE_DENSE ? (uint32_t)DW : HASH_MIN_SPAN;

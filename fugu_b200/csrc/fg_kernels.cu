@@ -1291,6 +1291,7 @@ __global__ void __launch_bounds__(NT, MINB) colscan_kernel(const SearchParams p)
     // and are applied to whichever window they fall into, round after round -- no re-decode of blocks
     // that straddle windows, however sparse the list.
     uint32_t cur = 0;
+    uint4 e_cur = make_uint4(0u, 0u, 0u, 0u);  // skip entry of block `cur`, fetched one block ahead
     uint32_t cd[4] = {EMPTY, EMPTY, EMPTY, EMPTY};  // carried postings, EMPTY = consumed
     float cv[4] = {0.f, 0.f, 0.f, 0.f};
     if (warp < nl) {
@@ -1301,6 +1302,7 @@ __global__ void __launch_bounds__(NT, MINB) colscan_kernel(const SearchParams p)
             if (__ldg(&skip[L.blk_begin + m]).x >= lo0) b = m; else a = m + 1;
         }
         cur = a;
+        if (cur < L.n_blocks) e_cur = __ldg(&skip[L.blk_begin + cur]);
     }
     uint32_t my_matches = 0, my_scored = 0;
     unsigned long long my_blocks = 0, my_redecode = 0;
@@ -1318,9 +1320,10 @@ __global__ void __launch_bounds__(NT, MINB) colscan_kernel(const SearchParams p)
             }
             if (__any_sync(FULL, left)) break;  // the block continues behind this window
             if (cur >= L.n_blocks) break;
-            const uint4 e = __ldg(&skip[L.blk_begin + cur]);
+            const uint4 e = e_cur;              // (loaded when the previous block was taken)
             if (e.y >= whi) break;              // the next block starts behind this window
             cur++;
+            if (cur < L.n_blocks) e_cur = __ldg(&skip[L.blk_begin + cur]);
             if (e.x < wlo) continue;            // (only before the item's first window)
             const uint32_t bd = e.w & 63u, bt = (e.w >> 6) & 63u, n = ((e.w >> 12) & 127u) + 1u;
             const uint32_t* wd = reinterpret_cast<const uint32_t*>(p.ix.blk + (size_t)e.z * 16u);
@@ -1338,7 +1341,10 @@ __global__ void __launch_bounds__(NT, MINB) colscan_kernel(const SearchParams p)
                 const bool ok = 4u * lane + j < n && d >= lo0 && d < end;
                 cd[j] = ok ? d : EMPTY;
                 nrm[j] = L.cnorm;
-                if (ok && ff >= 0) nrm[j] = __ldg(p.ix.cache + ff * 256 + __ldg(fnp + d));
+                if (ok && ff >= 0) {
+                    const uint32_t id = __ldg(fnp + d);
+                    nrm[j] = ff == cf ? S.ctab[id] : __ldg(p.ix.cache + ff * 256 + id);
+                }
             }
 #pragma unroll
             for (int j = 0; j < 4; j++) cv[j] = L.weight * tf_factor((float)(t[j] + 1u), nrm[j]);
