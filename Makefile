@@ -13,9 +13,9 @@ all: fugu_b200/libfugu_gpu.so fugu_b200/synth/libfugu_synth.so oracle/liboracle.
 
 $(CSRC)/fg_kernels.o: $(CSRC)/fg_kernels.cu $(CSRC)/fg_internal.h
 	$(NVCC) $(NVFLAGS) -Xptxas -v -c $< -o $@
-$(CSRC)/fg_api.o: $(CSRC)/fg_api.cu $(CSRC)/fg_internal.h $(CSRC)/fg_error.h include/fugu_gpu.h
+$(CSRC)/fg_api.o: $(CSRC)/fg_api.cu $(CSRC)/fg_internal.h $(CSRC)/fg_error.h $(CSRC)/fg_pool.h include/fugu_gpu.h
 	$(NVCC) $(NVFLAGS) -c $< -o $@
-$(CSRC)/fg_host.o: $(CSRC)/fg_host.cpp $(CSRC)/fg_error.h $(CSRC)/fg_unicode_tables.h include/fugu_gpu.h include/fugu_host.h
+$(CSRC)/fg_host.o: $(CSRC)/fg_host.cpp $(CSRC)/fg_error.h $(CSRC)/fg_pool.h $(CSRC)/fg_unicode_tables.h include/fugu_gpu.h include/fugu_host.h
 	$(CXX) -O2 -std=c++17 -fPIC -Wall -Iinclude -c $< -o $@
 
 fugu_b200/libfugu_gpu.so: $(CSRC)/fg_kernels.o $(CSRC)/fg_api.o $(CSRC)/fg_host.o

@@ -117,7 +117,7 @@ ABI_SYMBOLS = [
     "fg_last_error", "fg_version", "fg_ctx_create", "fg_ctx_destroy", "fg_ctx_set_stream",
     "fg_ctx_synchronize", "fg_index_upload", "fg_index_release", "fg_index_get_info",
     "fg_index_term_info", "fg_search_batch", "fg_batch_prepare", "fg_batch_prepare_ex", "fg_batch_release",
-    "fg_batch_execute", "fg_batch_get_stats", "fg_merge_topk_device", "fg_fieldnorm_to_id",
+    "fg_batch_execute", "fg_batch_submit", "fg_batch_collect", "fg_batch_get_stats", "fg_merge_topk_device", "fg_fieldnorm_to_id",
     "fg_id_to_fieldnorm", "fg_bm25_idf",
 ]
 
@@ -153,6 +153,8 @@ def lib() -> C.CDLL:
     L.fg_batch_release.argtypes = [vp]
     L.fg_batch_release.restype = None
     L.fg_batch_execute.argtypes = [vp, u32, u32, vp, vp, vp, vp]
+    L.fg_batch_submit.argtypes = [vp, u32, u32, i32]
+    L.fg_batch_collect.argtypes = [vp, vp, vp, vp]
     L.fg_batch_get_stats.argtypes = [vp, C.POINTER(BatchStats)]
     L.fg_merge_topk_device.argtypes = [vp, vp, vp, u32, u32, u32, u32, vp, vp]
     L.fg_fieldnorm_to_id.argtypes = [u32]

@@ -20,6 +20,7 @@
 #include "../../include/fugu_gpu.h"
 #include "fg_error.h"
 #include "fg_internal.h"
+#include "fg_pool.h"
 
 using namespace fg;
 
@@ -98,7 +99,36 @@ struct fg_ctx {
     std::mutex pool_mu;
     std::vector<std::pair<void*, size_t>> pool;
     size_t pool_bytes = 0;
+    // plan uploads run on their own stream: a pageable-memory H2D copy first waits for everything queued
+    // on its stream, which on the compute stream would serialise the upload of batch i+1 behind the
+    // kernels of batch i (fg_batch_submit / fgh_search_batch pipeline host work under device work)
+    cudaStream_t up = nullptr;
+    std::vector<std::pair<void*, size_t>> hpool;  // page-locked staging blocks for asynchronous result copies
 };
+
+static cudaError_t pinned_alloc(fg_ctx* c, void** out, size_t bytes) {
+    bytes = std::max<size_t>((bytes + 4095) & ~(size_t)4095, 4096);
+    {
+        std::lock_guard<std::mutex> g(c->pool_mu);
+        int best = -1;
+        for (int i = 0; i < (int)c->hpool.size(); i++)
+            if (c->hpool[i].second >= bytes && c->hpool[i].second <= 4 * bytes + (1 << 16) &&
+                (best < 0 || c->hpool[i].second < c->hpool[best].second)) best = i;
+        if (best >= 0) {
+            *out = c->hpool[best].first;
+            c->hpool.erase(c->hpool.begin() + best);
+            return cudaSuccess;
+        }
+    }
+    return cudaHostAlloc(out, bytes, cudaHostAllocDefault);
+}
+static void pinned_free(fg_ctx* c, void* p, size_t bytes) {
+    if (!p) return;
+    bytes = std::max<size_t>((bytes + 4095) & ~(size_t)4095, 4096);
+    std::lock_guard<std::mutex> g(c->pool_mu);
+    if (c->hpool.size() < 16) c->hpool.emplace_back(p, bytes);
+    else cudaFreeHost(p);
+}
 
 static cudaError_t pool_alloc(fg_ctx* c, void** out, size_t bytes) {
     bytes = std::max<size_t>((bytes + 255) & ~(size_t)255, 256);
@@ -155,6 +185,7 @@ extern "C" int32_t fg_ctx_create(int32_t device, fg_ctx** out) {
         CU(cudaEventCreateWithFlags(&c->join_ev[i], cudaEventDisableTiming));
     }
     CU(cudaEventCreateWithFlags(&c->fork_ev, cudaEventDisableTiming));
+    CU(cudaStreamCreateWithFlags(&c->up, cudaStreamNonBlocking));
     *out = c;
     return FG_OK;
 }
@@ -165,6 +196,8 @@ extern "C" void fg_ctx_destroy(fg_ctx* c) {
     for (int i = 0; i < NCLS - 1; i++) { if (c->aux[i]) cudaStreamDestroy(c->aux[i]); if (c->join_ev[i]) cudaEventDestroy(c->join_ev[i]); }
     if (c->fork_ev) cudaEventDestroy(c->fork_ev);
     for (auto& b : c->pool) cudaFree(b.first);
+    for (auto& b : c->hpool) cudaFreeHost(b.first);
+    if (c->up) cudaStreamDestroy(c->up);
     delete c;
 }
 extern "C" int32_t fg_ctx_set_stream(fg_ctx* c, void* s) {
@@ -534,6 +567,13 @@ struct fg_batch {
     uint32_t class_count[NCLS] = {};
     uint64_t n_launches = 0;
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};  // before search, after search, after merge
+    cudaEvent_t ev_up = nullptr, ev_done = nullptr;   // plan uploaded / results staged on the host
+    // fg_batch_submit: device result block, its page-locked host copy, layout
+    void* d_out = nullptr;
+    void* h_out = nullptr;
+    size_t out_sz = 0;
+    uint32_t sub_k_stride = 0;
+    bool sub_counts = false;
 };
 
 static double now_ms() {
@@ -555,8 +595,12 @@ extern "C" void fg_batch_release(fg_batch* b) {
         pool_free(c, b->d_queries, b->sz[0]); pool_free(c, b->d_leaves, b->sz[1]); pool_free(c, b->d_items, b->sz[2]);
         pool_free(c, b->d_partial, b->sz[3]); pool_free(c, b->d_partial_count, b->sz[4]);
         pool_free(c, b->d_stats, b->sz[5]); pool_free(c, b->d_qtheta, b->sz[6]);
+        pool_free(c, b->d_out, b->out_sz);
+        pinned_free(c, b->h_out, b->out_sz);
     }
     for (auto& e : b->ev) if (e) cudaEventDestroy(e);
+    if (b->ev_up) cudaEventDestroy(b->ev_up);
+    if (b->ev_done) cudaEventDestroy(b->ev_done);
     delete b;
 }
 
@@ -572,7 +616,6 @@ extern "C" int32_t fg_batch_prepare_ex(fg_index* ix, const fg_query_batch* qb, u
     const uint64_t COL_COST_DIV_PHASES = std::max<uint64_t>(1, env_u64("FG_COL_COST_DIV_PHASES", 2));
     const uint64_t WINDOW_COST = env_u64("FG_WINDOW_COST", 4096);
     const bool USE_COLSCAN = env_u64("FG_COLSCAN", 1) != 0;
-    uint64_t n_colscan_items = 0;
     const uint64_t STREAM_MAX_BPW = env_u64("FG_STREAM_MAX_BPW", 6);  // blocks per dense window of a streamed leaf
     *out = nullptr;
     if (qb->n_queries && (!qb->queries || (qb->n_clauses && !qb->clauses) || (qb->n_leaves && !qb->leaves)))
@@ -586,231 +629,287 @@ extern "C" int32_t fg_batch_prepare_ex(fg_index* ix, const fg_query_batch* qb, u
     const uint32_t HASH_MIN_SPAN = 4096;
 
     std::vector<DevQuery> dq(qb->n_queries);
+    const uint64_t N = ix->global_n_docs;
+    const uint64_t SOLO_MIN_BLOCKS = env_u64("FG_SOLO_MIN_BLOCKS", 0xFFFFFFFFull);
+    constexpr int MAXC = 32, MAXT = 64;
+    struct CRec { uint32_t occur, begin, count, ncol; uint64_t cost, df; };
+    // The lowering of one query is independent of the others: large batches are lowered by several host
+    // threads into per-thread leaf / item arrays that are concatenated afterwards (leaf_begin, item_begin
+    // and item slots are rebased).
+    struct LowerOut {
+        std::vector<DevLeaf> dl;
+        std::vector<DevItem> items;
+        std::vector<uint64_t> item_cost;
+        uint32_t kmax = 1;
+        uint64_t sum_k = 0, n_colscan_items = 0;
+        int32_t rc = FG_OK;
+        std::string err;
+    };
+    auto lfail = [](LowerOut& o, int32_t code, const char* fmt, ...) -> int32_t {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof(buf), fmt, ap);
+        va_end(ap);
+        o.rc = code;
+        o.err = buf;
+        return code;
+    };
+    auto lower_range = [&](uint32_t q_begin, uint32_t q_end, LowerOut& o) -> int32_t {
+        std::vector<DevLeaf>& dl = o.dl;
+        std::vector<DevItem>& items = o.items;
+        std::vector<uint64_t>& item_cost = o.item_cost;
+        uint32_t& kmax = o.kmax;
+        uint64_t& sum_k = o.sum_k;
+        uint64_t& n_colscan_items = o.n_colscan_items;
+        // per-query scratch (fixed arrays: the lowering of a 5000-query batch must not allocate per query)
+        DevLeaf ctmp[MAXT];  // column leaves of the query (appended after its block leaves)
+        CRec crec[MAXC];
+        DevLeaf tmp[MAXT];
+        const size_t nq_part = q_end - q_begin;
+        dl.reserve((size_t)((uint64_t)qb->n_leaves * nq_part / std::max<uint32_t>(qb->n_queries, 1)) + 64);
+        items.reserve(nq_part * 4);
+        item_cost.reserve(nq_part * 4);
+        for (uint32_t qi = q_begin; qi < q_end; qi++) {
+            const fg_query& q = qb->queries[qi];
+            if (q.k == 0) return lfail(o, FG_ERR_INVALID, "query %u: k == 0 (TopDocs::with_limit requires limit >= 1)", qi);
+            if (q.k > 1024) return lfail(o, FG_ERR_UNSUPPORTED, "query %u: k = %u > 1024 not supported", qi, q.k);
+            if ((uint64_t)q.clause_begin + q.n_clauses > qb->n_clauses)
+                return lfail(o, FG_ERR_INVALID, "query %u: clause range out of bounds", qi);
+            kmax = std::max(kmax, q.k);
+            sum_k += q.k;
+            int nc = 0, nt = 0;          // live clauses / leaves of this query
+            int must_idx[MAXC], n_must = 0, n_should = 0, n_not = 0;
+            float const_score = 0.f;
+            bool empty = false;          // a Must clause that can never match
+            bool has_all_only = false;
+            for (uint32_t ci = 0; ci < q.n_clauses; ci++) {
+                const fg_clause& c = qb->clauses[q.clause_begin + ci];
+                if ((uint64_t)c.leaf_begin + c.n_leaves > qb->n_leaves)
+                    return lfail(o, FG_ERR_INVALID, "query %u: leaf range out of bounds", qi);
+                if (c.occur > FG_OCCUR_MUST_NOT) return lfail(o, FG_ERR_INVALID, "query %u: bad occur", qi);
+                CRec cr{c.occur, (uint32_t)nt, 0, 0, 0, 0};
+                bool all = false;
+                float all_boost = 0.f;
+                for (uint32_t li = 0; li < c.n_leaves; li++) {
+                    const fg_leaf& lf = qb->leaves[c.leaf_begin + li];
+                    if (lf.term_ord == FG_TERM_ALL) { all = true; all_boost += lf.boost; continue; }
+                    if (lf.term_ord == FG_TERM_MISSING) continue;
+                    if (lf.field >= ix->fields.size()) return lfail(o, FG_ERR_INVALID, "query %u: field %u out of range", qi, lf.field);
+                    const HostField& hf = ix->fields[lf.field];
+                    if (lf.term_ord >= hf.n_terms) return lfail(o, FG_ERR_INVALID, "query %u: term_ord out of range", qi);
+                    const TermInfo& ti = hf.terms[lf.term_ord];
+                    if (ti.df_global == 0 || ti.n_blocks == 0) continue;  // empty scorer (globally, or in this shard)
+                    if (nt >= MAXT) return lfail(o, FG_ERR_UNSUPPORTED, "query %u: too many leaves", qi);
+                    DevLeaf& L = tmp[nt++];
+                    memset(&L, 0, sizeof(L));
+                    L.blk_begin = ti.blk_begin;
+                    L.n_blocks = ti.n_blocks;
+                    L.weight = lf.boost * (fg_bm25_idf(ti.df_global, N) * (1.0f + K1));
+                    L.cnorm = hf.cnorm;
+                    L.fn_field = (hf.flags & FG_FIELD_HAS_FIELDNORMS) ? (int32_t)lf.field : -1;
+                    if (use_cols && ti.col >= 0) {
+                        L.col = ix->d_cols + (uint64_t)ti.col * ix->col_stride;
+                        cr.ncol++;
+                    } else {
+                        cr.cost += ti.bytes;
+                    }
+                    cr.df += ti.df_local;
+                    cr.count++;
+                }
+                if (all) {
+                    if (c.occur == FG_OCCUR_MUST && cr.count == 0) { const_score += all_boost; has_all_only = true; continue; }
+                    return lfail(o, FG_ERR_UNSUPPORTED, "query %u: AllQuery leaf outside a Must clause is not supported", qi);
+                }
+                if (cr.count == 0) {
+                    if (c.occur == FG_OCCUR_MUST) empty = true;
+                    continue;
+                }
+                if (nc >= MAXC) return lfail(o, FG_ERR_UNSUPPORTED, "query %u: too many clauses", qi);
+                if (c.occur == FG_OCCUR_MUST) must_idx[n_must++] = nc;
+                else if (c.occur == FG_OCCUR_SHOULD) n_should++;
+                else n_not++;
+                crec[nc++] = cr;
+            }
+            DevQuery& D = dq[qi];
+            memset(&D, 0, sizeof(D));
+            D.k = q.k;
+            D.const_score = const_score;
+            D.leaf_begin = (uint32_t)dl.size();
+            D.item_begin = (uint32_t)items.size();
+            if (has_all_only && n_must == 0 && !empty) {
+                if (n_should == 0 && n_not == 0) {  // pure AllQuery: every alive doc, score = boost
+                    D.flags |= QF_ALL;
+                    continue;
+                }
+                return lfail(o, FG_ERR_UNSUPPORTED, "query %u: AllQuery Must with only Should/MustNot siblings not supported", qi);
+            }
+            if (empty || (n_must == 0 && n_should == 0)) continue;
+            if (n_must > MAX_MUST) return lfail(o, FG_ERR_UNSUPPORTED, "query %u: more than %d Must clauses", qi, MAX_MUST);
+            // Must clauses by ascending Sum(df) = tantivy's Intersection order (stable insertion sort)
+            for (int i = 1; i < n_must; i++) {
+                const int x = must_idx[i];
+                int j = i - 1;
+                while (j >= 0 && crec[must_idx[j]].df > crec[x].df) { must_idx[j + 1] = must_idx[j]; j--; }
+                must_idx[j + 1] = x;
+            }
+            const size_t ql0 = dl.size();
+            uint64_t insert_postings = 0, total_bytes = 0;
+            int n_ctmp = 0;
+            bool col_insert = false;
+            // Block leaves go to `dl` in evaluation order; column leaves are collected in ctmp and
+            // appended behind them (they are applied in the slot scan, after every block phase).
+            // `req` = mask bits a slot must already carry when a filter leaf touches it; only bits that
+            // block phases decide completely may be required: a clause with a column leaf sets its bit
+            // as late as the slot scan. A filter leaf left without any usable precondition is LF_NOFILT.
+            auto emit = [&](const CRec& cr, uint32_t bit, uint32_t role, uint32_t req, bool ins, bool nofilt) {
+                for (uint32_t i = 0; i < cr.count; i++) {
+                    DevLeaf L = tmp[cr.begin + i];
+                    L.bit = bit; L.role = role; L.req = req;
+                    if (L.col) {
+                        if (ins) col_insert = true;
+                        ctmp[n_ctmp++] = L;
+                        continue;
+                    }
+                    if (nofilt) L.lflags |= LF_NOFILT;
+                    if (ins) insert_postings += (uint64_t)L.n_blocks * BLOCK;
+                    dl.push_back(L);
+                }
+            };
+            uint32_t complete = 0, need_not = 0;
+            if (n_must) {
+                D.all_must = (1u << n_must) - 1u;
+                for (int ci = 0; ci < n_must; ci++) {
+                    const CRec& cr = crec[must_idx[ci]];
+                    const uint32_t req = ((1u << ci) - 1u) & complete;
+                    emit(cr, 1u << ci, ci == 0 ? ROLE_INSERT : ROLE_MUST, req, ci == 0, ci != 0 && req == 0);
+                    if (cr.ncol == 0) complete |= 1u << ci;
+                    total_bytes += cr.cost;
+                }
+                D.n_insert = 0;
+                for (size_t i = ql0; i < dl.size(); i++) D.n_insert += dl[i].role == ROLE_INSERT;
+                for (int i = 0; i < nc; i++)
+                    if (crec[i].occur == FG_OCCUR_SHOULD) { emit(crec[i], 0, ROLE_SHOULD, complete, false, complete == 0); total_bytes += crec[i].cost / 4; }
+                need_not = complete;
+            } else {
+                D.all_must = BIT_SHOULD;
+                D.flags |= QF_NO_MUST;
+                bool any_col = false, positive = true;
+                for (int i = 0; i < nc; i++)
+                    if (crec[i].occur == FG_OCCUR_SHOULD) {
+                        emit(crec[i], BIT_SHOULD, ROLE_INSERT, 0, true, false);
+                        total_bytes += crec[i].cost;
+                        any_col = any_col || crec[i].ncol;
+                    }
+                D.n_insert = (uint32_t)(dl.size() - ql0);
+                for (size_t i = ql0; i < dl.size(); i++) positive = positive && dl[i].weight > 0.f;
+                for (int i = 0; i < n_ctmp; i++) positive = positive && ctmp[i].weight > 0.f;
+                if (n_not == 0 && positive) D.flags |= QF_PURE_UNION;
+                complete = any_col ? 0u : BIT_SHOULD;
+                need_not = complete;
+            }
+            for (int i = 0; i < nc; i++)
+                if (crec[i].occur == FG_OCCUR_MUST_NOT) { emit(crec[i], BIT_NOT, ROLE_NOT, 0, false, need_not == 0); total_bytes += crec[i].cost / 4; }
+            const size_t nbl = dl.size() - ql0;  // block leaves
+            if (nbl + (size_t)n_ctmp > (size_t)MAX_LEAVES)
+                return lfail(o, FG_ERR_UNSUPPORTED, "query %u: %zu live leaves > %d", qi, nbl + (size_t)n_ctmp, MAX_LEAVES);
+            // candidate-bitmap rebuild points: after the last leaf of a clause when the next leaf filters
+            for (size_t i = ql0; i + 1 < dl.size(); i++) {
+                const DevLeaf& nx = dl[i + 1];
+                if (nx.role == ROLE_INSERT || (nx.lflags & LF_NOFILT)) continue;
+                const bool boundary = dl[i].role != nx.role || dl[i].bit != nx.bit;
+                if (!boundary) continue;
+                if (dl[i].role == ROLE_SHOULD) continue;  // bitmap of all-Must candidates is still valid
+                // mask the NEXT leaf's docs must carry (MustNot filters on the matching candidates)
+                dl[i].build_cb = nx.role == ROLE_NOT ? need_not : nx.req;
+            }
+            D.n_leaves = (uint32_t)nbl;
+            D.n_stream = 0;
+            D.n_col = (uint32_t)n_ctmp;
+            D.col_req = n_must ? complete : 0u;
+            if (col_insert) D.flags |= QF_COL_INSERT;
+            for (int i = 0; i < n_ctmp; i++) dl.push_back(ctmp[i]);
+
+            // ---- mode + work items ----
+            const uint32_t nd = ix->n_docs;
+            const uint64_t dmin = n_must ? DENSE_MIN_MUST : DENSE_MIN;
+            const uint32_t mode = (col_insert || insert_postings * (uint64_t)DW >= dmin * (uint64_t)std::max<uint32_t>(nd, 1)) ? MODE_DENSE : MODE_HASH;
+            // column-scan class: a pure union with a column insert leaf whose block leaves are all sparse enough
+            // to be streamed (one warp per leaf, at most NW of them) and whose column leaves share one
+            // fieldnorm field. Other dense plans keep their clause phases (all warps share the decode).
+            bool colscan = USE_COLSCAN && mode == MODE_DENSE && (D.flags & QF_PURE_UNION) && col_insert && nbl <= (size_t)NW &&
+                           q.k <= 128 && STREAM_MAX_BPW;
+            for (int i = 0; colscan && i < n_ctmp; i++) colscan = ctmp[i].fn_field >= 0 && ctmp[i].fn_field == ctmp[0].fn_field;
+            for (size_t i = 0; colscan && i < nbl; i++)
+                colscan = (uint64_t)dl[ql0 + i].n_blocks * DW <= STREAM_MAX_BPW * (uint64_t)std::max<uint32_t>(nd, 1);
+            if (colscan) {
+                for (size_t i = 0; i < nbl; i++) dl[ql0 + i].lflags |= LF_STREAM;
+                D.n_stream = (uint32_t)nbl;
+            }
+            // a dense window reads 1 B per doc per column leaf (+ the fieldnorm byte), at a fraction of the
+            // per-byte cost of packed blocks; hash rounds only gather the columns at their candidates
+            if (mode == MODE_DENSE && n_ctmp) total_bytes += (uint64_t)nd * (uint64_t)(n_ctmp + 1) / (colscan ? COL_COST_DIV : COL_COST_DIV_PHASES);
+            // a dense window of the phase kernels has a fixed cost (barriers, skip scans, slot scan) whatever it decodes
+            if (mode == MODE_DENSE && !colscan) total_bytes += (uint64_t)(nd / DW + 1) * WINDOW_COST;
+            const uint64_t ib = !(D.flags & QF_PURE_UNION) ? ITEM_BYTES_MASKED : (mode == MODE_DENSE ? ITEM_BYTES : ITEM_BYTES_HASH);
+            uint64_t want = std::max<uint64_t>(1, (total_bytes + ib / 2) / ib);
+            const uint32_t min_span = mode == MODE_DENSE ? (uint32_t)DW : HASH_MIN_SPAN;
+            const uint64_t max_items = std::max<uint64_t>(1, nd / min_span);
+            const uint32_t ni = (uint32_t)std::min(want, max_items);
+            if (mode == MODE_DENSE && SOLO_MIN_BLOCKS != 0xFFFFFFFFull) {
+                // long insert lists get a phase of their own: a slot is then touched by one thread only
+                for (size_t i = ql0; i < dl.size(); i++)
+                    if (dl[i].role == ROLE_INSERT && dl[i].n_blocks >= SOLO_MIN_BLOCKS) dl[i].solo = 1;
+            }
+            D.n_items = ni;
+            n_colscan_items += colscan ? ni : 0;
+            if (getenv("FG_DEBUG_PLAN") && !colscan && mode == MODE_DENSE)
+                fprintf(stderr, "[plan] q%u dense %s: %zu block leaves (%u streamed), %d column leaves, col_insert %d, k %u, items %u, bytes %llu\n", qi,
+                        (D.flags & QF_PURE_UNION) ? "pure" : "masked", nbl, D.n_stream, n_ctmp, (int)col_insert, q.k, ni, (unsigned long long)total_bytes);
+            for (uint32_t j = 0; j < ni; j++) {
+                DevItem it{};
+                it.query = qi;
+                // 16-aligned cuts: dense windows read columns / fieldnorms of 8 docs per 64-bit load
+                it.doc_lo = (uint32_t)((uint64_t)nd * j / ni) & ~15u;
+                it.doc_hi = j + 1 == ni ? nd : ((uint32_t)((uint64_t)nd * (j + 1) / ni) & ~15u);
+                it.mode = mode;
+                it.slot = D.item_begin + j;
+                it.cls = colscan ? 4u : (mode == MODE_DENSE ? 0u : 2u) + ((D.flags & QF_PURE_UNION) ? 0u : 1u);
+                items.push_back(it);
+                item_cost.push_back(total_bytes / ni);
+            }
+        }
+        return FG_OK;
+    };
+    const int LT = (int)std::max<uint64_t>(1, std::min<uint64_t>({(uint64_t)HostPool::get().size(), 8, (uint64_t)qb->n_queries / 256 + 1}));
+    std::vector<LowerOut> parts((size_t)LT);
+    HostPool::get().run(LT, [&](int t) {
+        lower_range((uint32_t)((uint64_t)qb->n_queries * t / LT), (uint32_t)((uint64_t)qb->n_queries * (t + 1) / LT), parts[t]);
+    });
+    for (auto& o : parts)
+        if (o.rc != FG_OK) return fail(o.rc, "%s", o.err.c_str());
     std::vector<DevLeaf> dl;
     std::vector<DevItem> items;
     std::vector<uint64_t> item_cost;
     uint32_t kmax = 1;
-    uint64_t sum_k = 0;
-    const uint64_t N = ix->global_n_docs;
-
-    const uint64_t SOLO_MIN_BLOCKS = env_u64("FG_SOLO_MIN_BLOCKS", 0xFFFFFFFFull);
-    // per-query scratch (fixed arrays: the lowering of a 5000-query batch must not allocate per query)
-    constexpr int MAXC = 32, MAXT = 64;
-    struct CRec { uint32_t occur, begin, count, ncol; uint64_t cost, df; };
-    DevLeaf ctmp[MAXT];  // column leaves of the query (appended after its block leaves)
-    CRec crec[MAXC];
-    DevLeaf tmp[MAXT];
-    dl.reserve((size_t)qb->n_leaves);
-    items.reserve((size_t)qb->n_queries * 4);
-    item_cost.reserve((size_t)qb->n_queries * 4);
-
-    for (uint32_t qi = 0; qi < qb->n_queries; qi++) {
-        const fg_query& q = qb->queries[qi];
-        if (q.k == 0) return fail(FG_ERR_INVALID, "query %u: k == 0 (TopDocs::with_limit requires limit >= 1)", qi);
-        if (q.k > 1024) return fail(FG_ERR_UNSUPPORTED, "query %u: k = %u > 1024 not supported", qi, q.k);
-        if ((uint64_t)q.clause_begin + q.n_clauses > qb->n_clauses)
-            return fail(FG_ERR_INVALID, "query %u: clause range out of bounds", qi);
-        kmax = std::max(kmax, q.k);
-        sum_k += q.k;
-        int nc = 0, nt = 0;          // live clauses / leaves of this query
-        int must_idx[MAXC], n_must = 0, n_should = 0, n_not = 0;
-        float const_score = 0.f;
-        bool empty = false;          // a Must clause that can never match
-        bool has_all_only = false;
-        for (uint32_t ci = 0; ci < q.n_clauses; ci++) {
-            const fg_clause& c = qb->clauses[q.clause_begin + ci];
-            if ((uint64_t)c.leaf_begin + c.n_leaves > qb->n_leaves)
-                return fail(FG_ERR_INVALID, "query %u: leaf range out of bounds", qi);
-            if (c.occur > FG_OCCUR_MUST_NOT) return fail(FG_ERR_INVALID, "query %u: bad occur", qi);
-            CRec cr{c.occur, (uint32_t)nt, 0, 0, 0, 0};
-            bool all = false;
-            float all_boost = 0.f;
-            for (uint32_t li = 0; li < c.n_leaves; li++) {
-                const fg_leaf& lf = qb->leaves[c.leaf_begin + li];
-                if (lf.term_ord == FG_TERM_ALL) { all = true; all_boost += lf.boost; continue; }
-                if (lf.term_ord == FG_TERM_MISSING) continue;
-                if (lf.field >= ix->fields.size()) return fail(FG_ERR_INVALID, "query %u: field %u out of range", qi, lf.field);
-                const HostField& hf = ix->fields[lf.field];
-                if (lf.term_ord >= hf.n_terms) return fail(FG_ERR_INVALID, "query %u: term_ord out of range", qi);
-                const TermInfo& ti = hf.terms[lf.term_ord];
-                if (ti.df_global == 0 || ti.n_blocks == 0) continue;  // empty scorer (globally, or in this shard)
-                if (nt >= MAXT) return fail(FG_ERR_UNSUPPORTED, "query %u: too many leaves", qi);
-                DevLeaf& L = tmp[nt++];
-                memset(&L, 0, sizeof(L));
-                L.blk_begin = ti.blk_begin;
-                L.n_blocks = ti.n_blocks;
-                L.weight = lf.boost * (fg_bm25_idf(ti.df_global, N) * (1.0f + K1));
-                L.cnorm = hf.cnorm;
-                L.fn_field = (hf.flags & FG_FIELD_HAS_FIELDNORMS) ? (int32_t)lf.field : -1;
-                if (use_cols && ti.col >= 0) {
-                    L.col = ix->d_cols + (uint64_t)ti.col * ix->col_stride;
-                    cr.ncol++;
-                } else {
-                    cr.cost += ti.bytes;
-                }
-                cr.df += ti.df_local;
-                cr.count++;
-            }
-            if (all) {
-                if (c.occur == FG_OCCUR_MUST && cr.count == 0) { const_score += all_boost; has_all_only = true; continue; }
-                return fail(FG_ERR_UNSUPPORTED, "query %u: AllQuery leaf outside a Must clause is not supported", qi);
-            }
-            if (cr.count == 0) {
-                if (c.occur == FG_OCCUR_MUST) empty = true;
-                continue;
-            }
-            if (nc >= MAXC) return fail(FG_ERR_UNSUPPORTED, "query %u: too many clauses", qi);
-            if (c.occur == FG_OCCUR_MUST) must_idx[n_must++] = nc;
-            else if (c.occur == FG_OCCUR_SHOULD) n_should++;
-            else n_not++;
-            crec[nc++] = cr;
-        }
-        DevQuery& D = dq[qi];
-        memset(&D, 0, sizeof(D));
-        D.k = q.k;
-        D.const_score = const_score;
-        D.leaf_begin = (uint32_t)dl.size();
-        D.item_begin = (uint32_t)items.size();
-        if (has_all_only && n_must == 0 && !empty) {
-            if (n_should == 0 && n_not == 0) {  // pure AllQuery: every alive doc, score = boost
-                D.flags |= QF_ALL;
-                continue;
-            }
-            return fail(FG_ERR_UNSUPPORTED, "query %u: AllQuery Must with only Should/MustNot siblings not supported", qi);
-        }
-        if (empty || (n_must == 0 && n_should == 0)) continue;
-        if (n_must > MAX_MUST) return fail(FG_ERR_UNSUPPORTED, "query %u: more than %d Must clauses", qi, MAX_MUST);
-        // Must clauses by ascending Sum(df) = tantivy's Intersection order (stable insertion sort)
-        for (int i = 1; i < n_must; i++) {
-            const int x = must_idx[i];
-            int j = i - 1;
-            while (j >= 0 && crec[must_idx[j]].df > crec[x].df) { must_idx[j + 1] = must_idx[j]; j--; }
-            must_idx[j + 1] = x;
-        }
-        const size_t ql0 = dl.size();
-        uint64_t insert_postings = 0, total_bytes = 0;
-        int n_ctmp = 0;
-        bool col_insert = false;
-        // Block leaves go to `dl` in evaluation order; column leaves are collected in ctmp and
-        // appended behind them (they are applied in the slot scan, after every block phase).
-        // `req` = mask bits a slot must already carry when a filter leaf touches it; only bits that
-        // block phases decide completely may be required: a clause with a column leaf sets its bit
-        // as late as the slot scan. A filter leaf left without any usable precondition is LF_NOFILT.
-        auto emit = [&](const CRec& cr, uint32_t bit, uint32_t role, uint32_t req, bool ins, bool nofilt) {
-            for (uint32_t i = 0; i < cr.count; i++) {
-                DevLeaf L = tmp[cr.begin + i];
-                L.bit = bit; L.role = role; L.req = req;
-                if (L.col) {
-                    if (ins) col_insert = true;
-                    ctmp[n_ctmp++] = L;
-                    continue;
-                }
-                if (nofilt) L.lflags |= LF_NOFILT;
-                if (ins) insert_postings += (uint64_t)L.n_blocks * BLOCK;
-                dl.push_back(L);
-            }
-        };
-        uint32_t complete = 0, need_not = 0;
-        if (n_must) {
-            D.all_must = (1u << n_must) - 1u;
-            for (int ci = 0; ci < n_must; ci++) {
-                const CRec& cr = crec[must_idx[ci]];
-                const uint32_t req = ((1u << ci) - 1u) & complete;
-                emit(cr, 1u << ci, ci == 0 ? ROLE_INSERT : ROLE_MUST, req, ci == 0, ci != 0 && req == 0);
-                if (cr.ncol == 0) complete |= 1u << ci;
-                total_bytes += cr.cost;
-            }
-            D.n_insert = 0;
-            for (size_t i = ql0; i < dl.size(); i++) D.n_insert += dl[i].role == ROLE_INSERT;
-            for (int i = 0; i < nc; i++)
-                if (crec[i].occur == FG_OCCUR_SHOULD) { emit(crec[i], 0, ROLE_SHOULD, complete, false, complete == 0); total_bytes += crec[i].cost / 4; }
-            need_not = complete;
-        } else {
-            D.all_must = BIT_SHOULD;
-            D.flags |= QF_NO_MUST;
-            bool any_col = false, positive = true;
-            for (int i = 0; i < nc; i++)
-                if (crec[i].occur == FG_OCCUR_SHOULD) {
-                    emit(crec[i], BIT_SHOULD, ROLE_INSERT, 0, true, false);
-                    total_bytes += crec[i].cost;
-                    any_col = any_col || crec[i].ncol;
-                }
-            D.n_insert = (uint32_t)(dl.size() - ql0);
-            for (size_t i = ql0; i < dl.size(); i++) positive = positive && dl[i].weight > 0.f;
-            for (int i = 0; i < n_ctmp; i++) positive = positive && ctmp[i].weight > 0.f;
-            if (n_not == 0 && positive) D.flags |= QF_PURE_UNION;
-            complete = any_col ? 0u : BIT_SHOULD;
-            need_not = complete;
-        }
-        for (int i = 0; i < nc; i++)
-            if (crec[i].occur == FG_OCCUR_MUST_NOT) { emit(crec[i], BIT_NOT, ROLE_NOT, 0, false, need_not == 0); total_bytes += crec[i].cost / 4; }
-        const size_t nbl = dl.size() - ql0;  // block leaves
-        if (nbl + (size_t)n_ctmp > (size_t)MAX_LEAVES)
-            return fail(FG_ERR_UNSUPPORTED, "query %u: %zu live leaves > %d", qi, nbl + (size_t)n_ctmp, MAX_LEAVES);
-        // candidate-bitmap rebuild points: after the last leaf of a clause when the next leaf filters
-        for (size_t i = ql0; i + 1 < dl.size(); i++) {
-            const DevLeaf& nx = dl[i + 1];
-            if (nx.role == ROLE_INSERT || (nx.lflags & LF_NOFILT)) continue;
-            const bool boundary = dl[i].role != nx.role || dl[i].bit != nx.bit;
-            if (!boundary) continue;
-            if (dl[i].role == ROLE_SHOULD) continue;  // bitmap of all-Must candidates is still valid
-            // mask the NEXT leaf's docs must carry (MustNot filters on the matching candidates)
-            dl[i].build_cb = nx.role == ROLE_NOT ? need_not : nx.req;
-        }
-        D.n_leaves = (uint32_t)nbl;
-        D.n_stream = 0;
-        D.n_col = (uint32_t)n_ctmp;
-        D.col_req = n_must ? complete : 0u;
-        if (col_insert) D.flags |= QF_COL_INSERT;
-        for (int i = 0; i < n_ctmp; i++) dl.push_back(ctmp[i]);
-
-        // ---- mode + work items ----
-        const uint32_t nd = ix->n_docs;
-        const uint64_t dmin = n_must ? DENSE_MIN_MUST : DENSE_MIN;
-        const uint32_t mode = (col_insert || insert_postings * (uint64_t)DW >= dmin * (uint64_t)std::max<uint32_t>(nd, 1)) ? MODE_DENSE : MODE_HASH;
-        // column-scan class: a pure union with a column insert leaf whose block leaves are all sparse enough
-        // to be streamed (one warp per leaf, at most NW of them) and whose column leaves share one
-        // fieldnorm field. Other dense plans keep their clause phases (all warps share the decode).
-        bool colscan = USE_COLSCAN && mode == MODE_DENSE && (D.flags & QF_PURE_UNION) && col_insert && nbl <= (size_t)NW &&
-                       q.k <= 128 && STREAM_MAX_BPW;
-        for (int i = 0; colscan && i < n_ctmp; i++) colscan = ctmp[i].fn_field >= 0 && ctmp[i].fn_field == ctmp[0].fn_field;
-        for (size_t i = 0; colscan && i < nbl; i++)
-            colscan = (uint64_t)dl[ql0 + i].n_blocks * DW <= STREAM_MAX_BPW * (uint64_t)std::max<uint32_t>(nd, 1);
-        if (colscan) {
-            for (size_t i = 0; i < nbl; i++) dl[ql0 + i].lflags |= LF_STREAM;
-            D.n_stream = (uint32_t)nbl;
-        }
-        // a dense window reads 1 B per doc per column leaf (+ the fieldnorm byte), at a fraction of the
-        // per-byte cost of packed blocks; hash rounds only gather the columns at their candidates
-        if (mode == MODE_DENSE && n_ctmp) total_bytes += (uint64_t)nd * (uint64_t)(n_ctmp + 1) / (colscan ? COL_COST_DIV : COL_COST_DIV_PHASES);
-        // a dense window of the phase kernels has a fixed cost (barriers, skip scans, slot scan) whatever it decodes
-        if (mode == MODE_DENSE && !colscan) total_bytes += (uint64_t)(nd / DW + 1) * WINDOW_COST;
-        const uint64_t ib = !(D.flags & QF_PURE_UNION) ? ITEM_BYTES_MASKED : (mode == MODE_DENSE ? ITEM_BYTES : ITEM_BYTES_HASH);
-        uint64_t want = std::max<uint64_t>(1, (total_bytes + ib / 2) / ib);
-        const uint32_t min_span = mode == MODE_DENSE ? (uint32_t)DW : HASH_MIN_SPAN;
-        const uint64_t max_items = std::max<uint64_t>(1, nd / min_span);
-        const uint32_t ni = (uint32_t)std::min(want, max_items);
-        if (mode == MODE_DENSE && SOLO_MIN_BLOCKS != 0xFFFFFFFFull) {
-            // long insert lists get a phase of their own: a slot is then touched by one thread only
-            for (size_t i = ql0; i < dl.size(); i++)
-                if (dl[i].role == ROLE_INSERT && dl[i].n_blocks >= SOLO_MIN_BLOCKS) dl[i].solo = 1;
-        }
-        D.n_items = ni;
-        n_colscan_items += colscan ? ni : 0;
-        if (getenv("FG_DEBUG_PLAN") && !colscan && mode == MODE_DENSE)
-            fprintf(stderr, "[plan] q%u dense %s: %zu block leaves (%u streamed), %d column leaves, col_insert %d, k %u, items %u, bytes %llu\n", qi,
-                    (D.flags & QF_PURE_UNION) ? "pure" : "masked", nbl, D.n_stream, n_ctmp, (int)col_insert, q.k, ni, (unsigned long long)total_bytes);
-        for (uint32_t j = 0; j < ni; j++) {
-            DevItem it{};
-            it.query = qi;
-            // 16-aligned cuts: dense windows read columns / fieldnorms of 8 docs per 64-bit load
-            it.doc_lo = (uint32_t)((uint64_t)nd * j / ni) & ~15u;
-            it.doc_hi = j + 1 == ni ? nd : ((uint32_t)((uint64_t)nd * (j + 1) / ni) & ~15u);
-            it.mode = mode;
-            it.slot = D.item_begin + j;
-            it.cls = colscan ? 4u : (mode == MODE_DENSE ? 0u : 2u) + ((D.flags & QF_PURE_UNION) ? 0u : 1u);
-            items.push_back(it);
-            item_cost.push_back(total_bytes / ni);
+    uint64_t sum_k = 0, n_colscan_items = 0;
+    if (LT == 1) {
+        dl.swap(parts[0].dl); items.swap(parts[0].items); item_cost.swap(parts[0].item_cost);
+        kmax = parts[0].kmax; sum_k = parts[0].sum_k; n_colscan_items = parts[0].n_colscan_items;
+    } else {
+        size_t nl_tot = 0, ni_tot = 0;
+        for (auto& o : parts) { nl_tot += o.dl.size(); ni_tot += o.items.size(); }
+        dl.reserve(nl_tot); items.reserve(ni_tot); item_cost.reserve(ni_tot);
+        for (int t = 0; t < LT; t++) {
+            LowerOut& o = parts[t];
+            const uint32_t lb = (uint32_t)dl.size(), ib = (uint32_t)items.size();
+            const uint32_t q0 = (uint32_t)((uint64_t)qb->n_queries * t / LT), q1 = (uint32_t)((uint64_t)qb->n_queries * (t + 1) / LT);
+            for (uint32_t qi = q0; qi < q1; qi++) { dq[qi].leaf_begin += lb; dq[qi].item_begin += ib; }
+            for (auto& it : o.items) it.slot += ib;
+            dl.insert(dl.end(), o.dl.begin(), o.dl.end());
+            items.insert(items.end(), o.items.begin(), o.items.end());
+            item_cost.insert(item_cost.end(), o.item_cost.begin(), o.item_cost.end());
+            kmax = std::max(kmax, o.kmax); sum_k += o.sum_k; n_colscan_items += o.n_colscan_items;
         }
     }
 
@@ -849,7 +948,7 @@ extern "C" int32_t fg_batch_prepare_ex(fg_index* ix, const fg_query_batch* qb, u
     auto up = [&](const void* src, size_t bytes, void** dst, size_t* sz) -> int32_t {
         *sz = std::max<size_t>(bytes, 16);
         CU(pool_alloc(ctx, dst, *sz));
-        if (bytes) CU(cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        if (bytes) CU(cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, ctx->up));
         return FG_OK;
     };
     int32_t rc;
@@ -866,7 +965,10 @@ extern "C" int32_t fg_batch_prepare_ex(fg_index* ix, const fg_query_batch* qb, u
     CU(pool_alloc(ctx, (void**)&b->d_stats, b->sz[5]));
     CU(pool_alloc(ctx, (void**)&b->d_qtheta, b->sz[6]));
     for (auto& e : b->ev) CU(cudaEventCreate(&e));
-    CU(cudaStreamSynchronize(ctx->stream));  // host vectors go out of scope
+    CU(cudaEventCreateWithFlags(&b->ev_up, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&b->ev_done, cudaEventDisableTiming));
+    CU(cudaEventRecord(b->ev_up, ctx->up));
+    CU(cudaStreamSynchronize(ctx->up));  // host vectors go out of scope (the compute stream is not touched)
     if (getenv("FG_TIMING"))
         fprintf(stderr, "[fg_batch_prepare] lowering %.2f ms, sort+upload %.2f ms (%zu items)\n", t_lower - t_begin, now_ms() - t_lower, items.size());
     *out = b.release();
@@ -882,6 +984,7 @@ extern "C" int32_t fg_batch_execute(fg_batch* b, uint32_t flags, uint32_t k_stri
     CU(cudaSetDevice(ctx->device));
     std::lock_guard<std::mutex> g(ctx->mu);
     cudaStream_t st = ctx->stream;
+    CU(cudaStreamWaitEvent(st, b->ev_up, 0));
     CU(cudaMemsetAsync(b->d_stats, 0, 16 * sizeof(unsigned long long), st));
     CU(cudaMemsetAsync(b->d_qtheta, 0, std::max<size_t>((size_t)b->n_queries * 4, 16), st));
     SearchParams p{};
@@ -1007,6 +1110,45 @@ extern "C" int32_t fg_search_batch(fg_index* ix, const fg_query_batch* qb, uint3
     CU(cudaStreamSynchronize(ctx->stream));
     if (timing)
         fprintf(stderr, "[fg_search_batch] prepare %.2f ms, alloc+execute+d2h %.2f ms (n=%zu)\n", t1 - t0, now_ms() - t1, nq);
+    return FG_OK;
+}
+
+extern "C" int32_t fg_batch_submit(fg_batch* b, uint32_t flags, uint32_t k_stride, int32_t want_counts) {
+    if (!b) return fail(FG_ERR_INVALID, "fg_batch_submit: NULL batch");
+    if (k_stride < b->kcap) return fail(FG_ERR_INVALID, "k_stride %u < max k %u", k_stride, b->kcap);
+    if (b->d_out) return fail(FG_ERR_INVALID, "fg_batch_submit: batch already submitted");
+    fg_ctx* ctx = b->ix->ctx;
+    CU(cudaSetDevice(ctx->device));
+    const size_t nq = b->n_queries;
+    b->sub_k_stride = k_stride;
+    b->sub_counts = want_counts != 0;
+    if (nq == 0) return FG_OK;
+    const size_t hits_b = nq * k_stride * sizeof(fg_hit);
+    b->out_sz = hits_b + 2 * nq * 4;
+    CU(pool_alloc(ctx, &b->d_out, b->out_sz));
+    CU(pinned_alloc(ctx, &b->h_out, b->out_sz));
+    char* d = (char*)b->d_out;
+    int32_t rc = fg_batch_execute(b, flags, k_stride, d, d + hits_b, want_counts ? d + hits_b + nq * 4 : nullptr, nullptr);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    CU(cudaMemcpyAsync(b->h_out, b->d_out, b->out_sz, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaEventRecord(b->ev_done, ctx->stream));
+    return FG_OK;
+}
+
+extern "C" int32_t fg_batch_collect(fg_batch* b, fg_hit* out_hits, uint32_t* out_n_hits, uint32_t* out_match_count) {
+    if (!b || !out_hits || !out_n_hits) return fail(FG_ERR_INVALID, "fg_batch_collect: NULL argument");
+    const size_t nq = b->n_queries;
+    if (nq == 0) return FG_OK;
+    if (!b->h_out) return fail(FG_ERR_INVALID, "fg_batch_collect: batch was not submitted");
+    if (out_match_count && !b->sub_counts) return fail(FG_ERR_INVALID, "fg_batch_collect: the batch was submitted without match counts");
+    CU(cudaSetDevice(b->ix->ctx->device));
+    CU(cudaEventSynchronize(b->ev_done));
+    const size_t hits_b = nq * b->sub_k_stride * sizeof(fg_hit);
+    const char* h = (const char*)b->h_out;
+    memcpy(out_hits, h, hits_b);
+    memcpy(out_n_hits, h + hits_b, nq * 4);
+    if (out_match_count) memcpy(out_match_count, h + hits_b + nq * 4, nq * 4);
     return FG_OK;
 }
 

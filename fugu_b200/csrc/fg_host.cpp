@@ -17,6 +17,7 @@
 
 #include "../../include/fugu_host.h"
 #include "fg_error.h"
+#include "fg_pool.h"
 #include "fg_unicode_tables.h"
 
 using fg::host_fail;
@@ -902,8 +903,8 @@ void plan_batch(const fgh_dataset* ds, uint32_t n, const char* const* queries, c
     unsigned hw = std::thread::hardware_concurrency();
     const char* e = getenv("FG_HOST_THREADS");
     if (e) hw = (unsigned)atoi(e);
-    // the fast path plans ~3M requests/s per thread: only very large batches are worth threads
-    const int T = (int)std::max(1u, std::min<unsigned>(hw ? hw : 4, std::min<unsigned>(16, n / 4096 + 1)));
+    // the fast path plans ~3M requests/s per thread; a thread costs ~30 us to start
+    const int T = (int)std::max(1u, std::min<unsigned>({hw ? hw : 4u, (unsigned)fg::HostPool::get().size(), 8u, n / 256 + 1}));
     struct Part { std::vector<fg_clause> c; std::vector<fg_leaf> l; std::vector<std::string> errs; uint32_t a, b; };
     std::vector<Part> parts((size_t)T);
     auto work = [&](int t) {
@@ -933,12 +934,7 @@ void plan_batch(const fgh_dataset* ds, uint32_t n, const char* const* queries, c
             }
         }
     };
-    if (T == 1) work(0);
-    else {
-        std::vector<std::thread> th;
-        for (int t = 0; t < T; t++) th.emplace_back(work, t);
-        for (auto& x : th) x.join();
-    }
+    fg::HostPool::get().run(T, work);
     // concatenate the per-thread parts (clause / leaf indices become global)
     for (int t = 0; t < T; t++) {
         Part& P = parts[t];
@@ -982,31 +978,60 @@ extern "C" int32_t fgh_search_batch(fgh_dataset* ds, uint32_t n, const char* con
     if (!ds || (n && (!queries || !out_hits || !out_n))) return host_fail(FG_ERR_INVALID, "fgh_search_batch: NULL argument");
     if (!ds->index) return host_fail(ds->ctx ? FG_ERR_INVALID : FG_ERR_NO_DEVICE, "dataset has no device snapshot (commit first)");
     if (n == 0) return FG_OK;
-    PlannedBatch pb;
-    plan_batch(ds, n, queries, filters, filter_offsets, pages, per_pages, pb);
-    if (status) memcpy(status, pb.rc.data(), n * sizeof(int32_t));
-    if (pb.first_err && !status) return host_fail(pb.first_err, "%s", pb.first_msg.c_str());  // single-status callers see the first failure
-    fg_query_batch qb;
-    memset(&qb, 0, sizeof(qb));
-    qb.n_queries = n;
-    qb.n_clauses = (uint32_t)pb.c.size();
-    qb.n_leaves = (uint32_t)pb.l.size();
-    qb.queries = pb.q.data();
-    qb.clauses = pb.c.data();
-    qb.leaves = pb.l.data();
-    const uint32_t kmax = pb.kmax;
-    std::vector<fg_hit> hits((size_t)n * kmax);
-    std::vector<uint32_t> nh(n), cnt(n);
-    // match counts are optional: the reference's TopDocs collector does not count (src/db/search.rs:162)
-    int32_t r = fg_search_batch(ds->index, &qb, kmax, hits.data(), nh.data(), out_match_count ? cnt.data() : nullptr);
-    if (r) return r;
-    for (uint32_t i = 0; i < n; i++) {
-        const bool bad = pb.rc[i] != FG_OK;
-        const uint32_t off = pb.offset[i], pp = per_pages ? per_pages[i] : 20;
-        uint32_t m = (!bad && nh[i] > off) ? std::min(nh[i] - off, std::min(pp, stride)) : 0;  // skip(offset).take(per_page)
-        for (uint32_t j = 0; j < m; j++) out_hits[(size_t)i * stride + j] = hits[(size_t)i * kmax + off + j];
-        out_n[i] = m;
-        if (out_match_count) out_match_count[i] = bad ? 0 : cnt[i];
+    // Large requests are cut into a few chunks and pipelined: while the device evaluates chunk i
+    // (fg_batch_submit returns at once) this thread parses, plans and lowers chunk i+1, so the host
+    // side of the call hides under the kernels instead of adding to them.
+    uint32_t nch = std::min<uint32_t>(2, n / 3072 + 1);
+    if (const char* e = getenv("FG_PIPELINE_CHUNKS")) nch = (uint32_t)std::max(1, atoi(e));
+    nch = std::max<uint32_t>(1, std::min(nch, n));
+    struct Chunk { uint32_t a, b; PlannedBatch pb; fg_batch* batch = nullptr; };
+    std::vector<Chunk> ch(nch);
+    struct Cleanup {
+        std::vector<Chunk>& c;
+        ~Cleanup() { for (auto& x : c) if (x.batch) fg_batch_release(x.batch); }
+    } cleanup{ch};
+    for (uint32_t i = 0; i < nch; i++) {
+        Chunk& C = ch[i];
+        C.a = (uint32_t)((uint64_t)n * i / nch);
+        C.b = (uint32_t)((uint64_t)n * (i + 1) / nch);
+        const uint32_t m = C.b - C.a;
+        plan_batch(ds, m, queries + C.a, filters, filter_offsets ? filter_offsets + C.a : nullptr,
+                   pages ? pages + C.a : nullptr, per_pages ? per_pages + C.a : nullptr, C.pb);
+        if (status) memcpy(status + C.a, C.pb.rc.data(), m * sizeof(int32_t));
+        if (C.pb.first_err && !status) return host_fail(C.pb.first_err, "%s", C.pb.first_msg.c_str());  // single-status callers see the first failure
+        fg_query_batch qb;
+        memset(&qb, 0, sizeof(qb));
+        qb.n_queries = m;
+        qb.n_clauses = (uint32_t)C.pb.c.size();
+        qb.n_leaves = (uint32_t)C.pb.l.size();
+        qb.queries = C.pb.q.data();
+        qb.clauses = C.pb.c.data();
+        qb.leaves = C.pb.l.data();
+        int32_t r = fg_batch_prepare(ds->index, &qb, &C.batch);
+        if (r) return r;
+        // match counts are optional: the reference's TopDocs collector does not count (src/db/search.rs:162)
+        r = fg_batch_submit(C.batch, 0, C.pb.kmax, out_match_count ? 1 : 0);
+        if (r) return r;
+    }
+    std::vector<fg_hit> hits;
+    std::vector<uint32_t> nh, cnt;
+    for (uint32_t i = 0; i < nch; i++) {
+        Chunk& C = ch[i];
+        const uint32_t m = C.b - C.a, kmax = C.pb.kmax;
+        hits.resize((size_t)m * kmax);
+        nh.resize(m);
+        cnt.resize(m);
+        int32_t r = fg_batch_collect(C.batch, hits.data(), nh.data(), out_match_count ? cnt.data() : nullptr);
+        if (r) return r;
+        for (uint32_t j = 0; j < m; j++) {
+            const uint32_t qi = C.a + j;
+            const bool bad = C.pb.rc[j] != FG_OK;
+            const uint32_t off = C.pb.offset[j], pp = per_pages ? per_pages[qi] : 20;
+            uint32_t take = (!bad && nh[j] > off) ? std::min(nh[j] - off, std::min(pp, stride)) : 0;  // skip(offset).take(per_page)
+            for (uint32_t x = 0; x < take; x++) out_hits[(size_t)qi * stride + x] = hits[(size_t)j * kmax + off + x];
+            out_n[qi] = take;
+            if (out_match_count) out_match_count[qi] = bad ? 0 : cnt[j];
+        }
     }
     return FG_OK;
 }

@@ -181,6 +181,15 @@ void fg_batch_release(fg_batch* b);
 int32_t fg_batch_execute(fg_batch* b, uint32_t flags, uint32_t k_stride, void* d_hits,
                          void* d_n_hits, void* d_match_count, void* d_match_bitmap);
 
+/* Asynchronous host-buffer form. fg_batch_submit launches the prepared batch and queues the
+ * device->host copy of its results into page-locked staging owned by the batch; it returns at once.
+ * fg_batch_collect blocks until the results have arrived and copies them into the caller's buffers
+ * (same layout as fg_search_batch; out_match_count may be NULL, and must be when want_counts was 0).
+ * A host thread can plan and prepare batch i+1 while batch i runs: fgh_search_batch pipelines large
+ * requests this way. One submit per prepared batch. */
+int32_t fg_batch_submit(fg_batch* b, uint32_t flags, uint32_t k_stride, int32_t want_counts);
+int32_t fg_batch_collect(fg_batch* b, fg_hit* out_hits, uint32_t* out_n_hits, uint32_t* out_match_count);
+
 typedef struct {
     uint64_t bytes_blocks;    /* packed bytes + 16 B skip entry of every block decoded (counted once) */
     uint64_t bytes_redecode;  /* bytes of blocks decoded again (round/work-item boundaries) */
