@@ -7,10 +7,11 @@ A "step" = one pass of the hot path (posting decode -> AND/OR -> BM25 -> top-k, 
 over the whole 5000-query batch.
 
   value    : queries/s with the index AND the lowered query batch resident in HBM, CUDA-event time
-  e2e      : queries/s through the reference-facing blocking call fg_search_batch with HOST buffers
-             (plan lowering, H2D of the plan, kernels, D2H of hits inside the timed region)
-  roofline : algorithmic posting bytes of one search_kernel launch / its CUDA-event duration vs
-             MEASURED_PEAKS.json hbm_gbs
+  e2e      : queries/s through the reference-facing blocking call fgh_search_batch with HOST buffers
+             (query strings -> planner -> plan lowering -> H2D of the plan -> kernels -> D2H of hits, all
+             inside the timed region)
+  roofline : algorithmic posting bytes (stated on the posting-block layout) of one step's
+             concurrent group of search kernels / its CUDA-event duration vs MEASURED_PEAKS.json hbm_gbs
   cpu_baseline / --impl reference : the CPU oracle (restatement of tantivy 0.24.1 semantics — the
              real reference cannot be built here: no Rust toolchain) on the box's host cores.
 
@@ -147,9 +148,10 @@ def term_lists(corpus, cfg, n_fields):
 
 
 def ncu_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum of the search kernels of one step, from the
-    committed `ncu --set full` capture of this command (profiles/r01_traffic.json), or None."""
-    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    """dram__bytes_read.sum + dram__bytes_write.sum of the kernels of one step, from the committed
+    `ncu --set full` capture of this command (profiles/r01b_traffic.json, written by
+    tools/ncu_summary.py), or None."""
+    p = os.path.join(ROOT, "profiles", "r01b_traffic.json")
     try:
         return json.load(open(p))["dram_bytes_per_step"]
     except Exception:
@@ -238,6 +240,8 @@ def main():
     dev = torch.device("cuda", local_rank)
     dist = None
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout (one JSON line)
         import torch.distributed as dist_mod
 
         dist = dist_mod
@@ -392,15 +396,20 @@ def main():
         "posting_gbs": algo_total / (ms_per_step * 1e-3) / 1e9,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": ncu_traffic(), "peak_source": peak_src,
-                     "kernel": "search_kernel (4 class instantiations dense/hash x pure/masked, launched concurrently; timed as one group)",
+                     "kernel": "one step's search kernels, launched concurrently and timed as one group: colscan_kernel (pure unions "
+                               "with a dense-tf-column leaf; ~3/4 of the step's instructions) + search_kernel x4 (dense/hash x pure/masked)",
                      "kernel_ms": kms, "algorithmic_bytes_per_launch": int(algo_bytes),
                      "bytes_per_query": algo_bytes / nq,
                      "touched_block_bytes": int(st_touched.bytes_blocks), "redecode_bytes": int(st_touched.bytes_redecode),
-                     "note": "index snapshot is %.0f MB in HBM (L2 is 126 MB); L2 is flushed before each timed step; "
-                             "traffic = ncu dram bytes of the C2 step (profiles/r01_traffic.json)" % (info.device_bytes / 1e6)},
+                     "note": "algorithmic bytes are counted on the posting-block layout by an untimed exact-accounting pass "
+                             "that evaluates every leaf from its blocks; the timed pass reads 1 B/doc dense tf columns for terms "
+                             "in >= 1/16 of the docs instead of their blocks. Index snapshot is %.0f MB in HBM incl. %.0f MB of "
+                             "columns (L2 is 126 MB); L2 is flushed before each timed step; traffic = ncu dram bytes of one C2 "
+                             "step (profiles/r01b_traffic.json)" % (info.device_bytes / 1e6, info.column_bytes / 1e6)},
         "e2e": {"value": nq / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": int(lowered_bytes),
                 "d2h_bytes_per_step": int(out_bytes), "ms_per_step": e2e_s * 1e3,
-                "what": "fgh_search_batch: query strings (host) -> C++ planner -> plan lowering -> H2D plan -> kernels -> D2H hits (host)"},
+                "what": "fgh_search_batch: query strings (host) -> C++ planner -> plan lowering -> H2D plan -> kernels -> D2H hits "
+                        "(host); requests above 3072 queries are pipelined in two chunks; match counts %s" % ("on" if counts else "off (TopDocs does not count)")},
         "gpu_launches": int(st_timed.n_launches + (1 if world > 1 else 0)) * args.steps,
         "clocks": clocks,
         "index": {"postings": int(info.n_postings), "blocks": int(info.n_blocks), "packed_bytes": int(info.packed_bytes),

@@ -321,6 +321,20 @@ class PreparedBatch:
         check(lib().fg_batch_execute(self.h, flags, k_stride or self.kmax, C.c_void_p(d_hits), C.c_void_p(d_n),
                                      C.c_void_p(d_count or 0), C.c_void_p(d_bitmap or 0)))
 
+    def submit(self, k_stride: int | None = None, want_counts: bool = True, flags: int = 0) -> None:
+        """fg_batch_submit: launch + queue the device->host copy of the results; returns at once."""
+        self._sub = (k_stride or self.kmax, want_counts)
+        check(lib().fg_batch_submit(self.h, flags, self._sub[0], 1 if want_counts else 0))
+
+    def collect(self):
+        """fg_batch_collect: wait for a submitted batch, return (hits, n_hits, match_count | None)."""
+        ks, want_counts = self._sub
+        hits = np.zeros((self.n_queries, ks), HIT_DT)
+        n = np.zeros(self.n_queries, np.uint32)
+        cnt = np.zeros(self.n_queries, np.uint32) if want_counts else None
+        check(lib().fg_batch_collect(self.h, _ptr(hits), _ptr(n), _ptr(cnt)))
+        return hits, n, cnt
+
     def stats(self) -> BatchStats:
         s = BatchStats()
         check(lib().fg_batch_get_stats(self.h, C.byref(s)))

@@ -416,3 +416,59 @@ def test_dense_tf_columns_every_plan_shape(ctx):
         assert index.info().n_columns == 7  # text: 0.9 0.5 0.2 0.07 and the all-docs list; facets: 0.25 0.5
         check_batch_against_oracle(index, desc, batch)
         index.close()
+
+
+def test_async_submit_collect_and_pipelined_requests(ctx):
+    """fg_batch_submit / fg_batch_collect (asynchronous host-buffer form): several batches in flight at
+    once return what the blocking call returns; fgh_search_batch gives the same answers whether it
+    runs a request as one batch or pipelines it in chunks; counts are optional (TopDocs does not count)."""
+    import os
+
+    from fugu_b200.dataset import Dataset
+    from tests.util import check_topk
+
+    cfg = synth.Config(cfg=2, n_docs=60_000, vocab=10_000, n_queries=900, k=10, name_pct=10)
+    corpus = synth.Corpus.for_config(cfg)
+    desc = nat.HostIndexDesc(cfg.n_docs, synth.build_fields(corpus, 0, cfg.n_docs))
+    ds = Dataset(ctx)
+    words = [f"w{i + 1}" for i in range(cfg.vocab)]
+    ds.adopt(desc, [words, words])
+    index = ds.index()
+    qs = synth.gen_queries(cfg)
+    parts = [plan_queries(qs[i::3], vocab=cfg.vocab, n_text_fields=2) for i in range(3)]
+    want = [index.search(b) for b in parts]
+    pbs = [index.prepare(b) for b in parts]
+    for i, pb in enumerate(pbs):
+        pb.submit(want_counts=(i != 1))
+    for i in (2, 0, 1):  # collected out of order
+        h, n, c = pbs[i].collect()
+        assert np.array_equal(n, want[i][1])
+        assert (c is None) if i == 1 else np.array_equal(c, want[i][2])
+        for q in range(parts[i].n_queries):
+            check_topk(h[q, :n[q]], want[i][0][q, :n[q]], k=10, ctx=f"batch {i} query {q}")
+        pbs[i].close()
+    with pytest.raises(nat.FgError):  # counts were not requested at submit time
+        pb = index.prepare(parts[0]); pb.submit(want_counts=False)
+        try:
+            nat.check(nat.lib().fg_batch_collect(pb.h, nat._ptr(np.zeros((parts[0].n_queries, 10), nat.HIT_DT)),
+                                                 nat._ptr(np.zeros(parts[0].n_queries, np.uint32)),
+                                                 nat._ptr(np.zeros(parts[0].n_queries, np.uint32))))
+        finally:
+            pb.close()
+    strings = [q["query"] for q in qs]
+    ref = None
+    for chunks in ("1", "2", "5"):
+        os.environ["FG_PIPELINE_CHUNKS"] = chunks
+        try:
+            got = ds.search_batch(strings, None, 0, 10)
+            nocnt = ds.search_batch(strings, None, 0, 10, want_counts=False)
+        finally:
+            os.environ.pop("FG_PIPELINE_CHUNKS")
+        assert (got[3] == 0).all() and nocnt[2] is None and np.array_equal(nocnt[1], got[1])
+        if ref is None:
+            ref = got
+            continue
+        assert np.array_equal(got[1], ref[1]) and np.array_equal(got[2], ref[2])
+        for q in range(len(strings)):
+            check_topk(got[0][q, :got[1][q]], ref[0][q, :ref[1][q]], k=10, ctx=f"chunks {chunks} query {q}")
+    ds.close()
