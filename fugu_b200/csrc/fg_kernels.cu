@@ -19,6 +19,7 @@
 // query's clause mask and offered to a per-warp register top-k queue ordered like tantivy's
 // TopDocs (score desc, doc asc). Per-item lists are merged per query by merge_kernel.
 #include <cuda_runtime.h>
+#include <type_traits>
 #include <stdint.h>
 #include <stdlib.h>
 
@@ -1385,32 +1386,48 @@ __global__ void __launch_bounds__(NT, MINB) colscan_kernel(const SearchParams p)
         if (nl && whi < end)
             stream_window(whi, (uint32_t)min((unsigned long long)whi + step, (unsigned long long)end), acc + ((r + 1) & 1) * CW);
         const uint32_t n8 = (whi - wlo + 7) >> 3;
-        while (true) {
-            uint32_t c0 = 0;
-            if (lane == 0) c0 = atomicAdd(&S.chunk[r & 1], 1u);
-            c0 = __shfl_sync(FULL, c0, 0) * 32u;
-            if (c0 >= n8) break;
-            const uint32_t g = c0 + lane;
-            {   // threshold reached by any warp of the CTA
-                const uint32_t tc = S.theta_cta;
-                if (tc != seen_t) { seen_t = tc; theta_s = fmaxf(theta_s, unsortable(tc)); }
-            }
-            float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            uint32_t px = 0, py = 0;  // OR of the columns' tf bytes: non-zero byte = doc matches
-            float accmax = 0.f;
-            if (g < n8) {
-                const uint32_t d8 = wlo + 8u * g;
-                const uint2 fn8 = __ldg(reinterpret_cast<const uint2*>(fnb + d8));
-                uint2 ta = __ldg(reinterpret_cast<const uint2*>(CL[0].col + d8)), tb = make_uint2(0u, 0u);
-                if (ncol > 1) tb = __ldg(reinterpret_cast<const uint2*>(CL[1].col + d8));
-                if (nl) {
+        // The scan loop is instantiated per (number of column leaves: 1, 2, any) x (streamed leaves yes/no):
+        // column pointers and weights live in registers, no loop over columns, no accumulator traffic for
+        // plans without streamed leaves. Lanes past the end of the last window are clamped, not branched.
+        auto chunk_loop = [&](auto nc_tag, auto acc_tag) {
+            constexpr int NC = decltype(nc_tag)::value;
+            constexpr bool ACC = decltype(acc_tag)::value;
+            const uint8_t* fnw = fnb + wlo;
+            const uint8_t* cp0 = CL[0].col + wlo;
+            const float w0 = CL[0].weight;
+            const uint8_t* cp1 = NC == 1 ? cp0 : CL[1].col + wlo;
+            const float w1 = NC == 1 ? 0.f : CL[1].weight;
+            const uint32_t chunk_addr = (uint32_t)__cvta_generic_to_shared(&S.chunk[r & 1]);
+            const bool slow = count || alive8 != nullptr || p.match_bitmap != nullptr;
+            while (true) {
+                uint32_t c0 = 0;
+                if (lane == 0) asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(c0) : "r"(chunk_addr) : "memory");
+                c0 = __shfl_sync(FULL, c0, 0) * 32u;
+                if (c0 >= n8) break;
+                const bool active = c0 + lane < n8;
+                const uint32_t g = active ? c0 + lane : n8 - 1;
+                const uint32_t o8 = 8u * g;
+                const uint2 fn8 = __ldg(reinterpret_cast<const uint2*>(fnw + o8));
+                const uint2 ta = __ldg(reinterpret_cast<const uint2*>(cp0 + o8));
+                uint2 tb = make_uint2(0u, 0u);
+                if (NC != 1) tb = __ldg(reinterpret_cast<const uint2*>(cp1 + o8));
+                {   // threshold reached by any warp of the CTA
+                    const uint32_t tc = S.theta_cta;
+                    if (tc != seen_t) { seen_t = tc; theta_s = fmaxf(theta_s, unsortable(tc)); }
+                }
+                float v[8];
+                float accmax = 0.f;
+                if (ACC) {
                     float4* b4 = reinterpret_cast<float4*>(buf) + 2 * g;
                     const float4 a0 = b4[0], a1 = b4[1];
                     b4[0] = make_float4(0.f, 0.f, 0.f, 0.f);
                     b4[1] = make_float4(0.f, 0.f, 0.f, 0.f);
                     v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w;
                     v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
-                    accmax = fmaxf(fmaxf(fmaxf(a0.x, a0.y), fmaxf(a0.z, a0.w)), fmaxf(fmaxf(a1.x, a1.y), fmaxf(a1.z, a1.w)));
+                    if (slow) accmax = fmaxf(fmaxf(fmaxf(a0.x, a0.y), fmaxf(a0.z, a0.w)), fmaxf(fmaxf(a1.x, a1.y), fmaxf(a1.z, a1.w)));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; j++) v[j] = 0.f;
                 }
                 float n[8];
 #pragma unroll
@@ -1418,60 +1435,73 @@ __global__ void __launch_bounds__(NT, MINB) colscan_kernel(const SearchParams p)
                     n[j] = S.ctab[(fn8.x >> (8 * j)) & 255u];
                     n[4 + j] = S.ctab[(fn8.y >> (8 * j)) & 255u];
                 }
-                int c = 0;
-                while (true) {
-                    col_term8(ta, CL[c].weight, magic, n, v);
-                    px |= ta.x; py |= ta.y;
-                    if (c + 1 >= ncol) break;
-                    col_term8(tb, CL[c + 1].weight, magic, n, v);
-                    px |= tb.x; py |= tb.y;
-                    c += 2;
-                    if (c >= ncol) break;
-                    ta = __ldg(reinterpret_cast<const uint2*>(CL[c].col + d8));
-                    if (c + 1 < ncol) tb = __ldg(reinterpret_cast<const uint2*>(CL[c + 1].col + d8));
-                }
-                if (alive8) {  // deleted docs: windows are 16-aligned, so docs d8..d8+7 are one byte of the bitset
-                    const uint32_t al = __ldg(alive8 + (d8 >> 3));
-#pragma unroll
-                    for (int j = 0; j < 8; j++) v[j] = ((al >> j) & 1u) ? v[j] : 0.f;
-                }
-                if (p.match_bitmap) {
-                    uint32_t bits = 0;
-#pragma unroll
-                    for (int j = 0; j < 8; j++) bits |= (v[j] > 0.f ? 1u : 0u) << j;
-                    if (bits) atomicOr(p.match_bitmap + (size_t)it.query * p.bitmap_words + (d8 >> 5), bits << (d8 & 31));
-                }
-            }
-            if (count) {
-                // matches = docs with a non-zero column byte, + docs that only streamed leaves touched (rare)
-                if (alive8 || accmax > 0.f) {
-#pragma unroll
-                    for (int j = 0; j < 8; j++) my_matches += v[j] > 0.f;
-                } else {
-                    my_matches += nonzero_bytes(px) + nonzero_bytes(py);
-                }
-            }
-            const float mx = fmaxf(fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3])), fmaxf(fmaxf(v[4], v[5]), fmaxf(v[6], v[7])));
-            if (__any_sync(FULL, mx > 0.f && mx + q.const_score >= theta_s)) {
-#pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    const float sc = v[j] + q.const_score;
-                    const bool c = v[j] > 0.f && sc >= theta_s;
-                    if (!__any_sync(FULL, c)) continue;
-                    tk.offer(c, c ? make_key(sc, wlo + 8 * g + j) : 0ull, k, lane);
-                }
-                const float mine = tk.theta ? unsortable((uint32_t)(tk.theta >> 32)) : -INFINITY;
-                if (mine > theta_s) {
-                    theta_s = mine;
-                    if (lane == 0) {
-                        atomicMax(&S.theta_cta, sortable(mine));
-                        if (p.qtheta) atomicMax(p.qtheta + it.query, sortable(mine));
+                col_term8(ta, w0, magic, n, v);
+                if (NC != 1) col_term8(tb, w1, magic, n, v);
+                uint32_t px = ta.x | tb.x, py = ta.y | tb.y;  // OR of the columns' tf bytes: non-zero byte = doc matches
+                if (NC == 0) {
+                    for (int c = 2; c < ncol; c++) {
+                        const uint2 tc2 = __ldg(reinterpret_cast<const uint2*>(CL[c].col + wlo + o8));
+                        col_term8(tc2, CL[c].weight, magic, n, v);
+                        px |= tc2.x; py |= tc2.y;
                     }
-                } else if (p.qtheta) {  // pick up what the other work items of the query have reached
-                    const uint32_t gq = __ldcg(p.qtheta + it.query);
-                    if (gq > seen_t) { if (lane == 0) atomicMax(&S.theta_cta, gq); theta_s = fmaxf(theta_s, unsortable(gq)); }
+                }
+                if (slow) {
+                    const uint32_t d8 = wlo + o8;
+                    if (alive8) {  // deleted docs: windows are 16-aligned, so docs d8..d8+7 are one byte of the bitset
+                        const uint32_t al = __ldg(alive8 + (d8 >> 3));
+#pragma unroll
+                        for (int j = 0; j < 8; j++) v[j] = ((al >> j) & 1u) ? v[j] : 0.f;
+                    }
+                    if (p.match_bitmap && active) {
+                        uint32_t bits = 0;
+#pragma unroll
+                        for (int j = 0; j < 8; j++) bits |= (v[j] > 0.f ? 1u : 0u) << j;
+                        if (bits) atomicOr(p.match_bitmap + (size_t)it.query * p.bitmap_words + (d8 >> 5), bits << (d8 & 31));
+                    }
+                    if (count && active) {
+                        // matches = docs with a non-zero column byte, + docs that only streamed leaves touched (rare)
+                        if (alive8 || accmax > 0.f) {
+#pragma unroll
+                            for (int j = 0; j < 8; j++) my_matches += v[j] > 0.f;
+                        } else {
+                            my_matches += nonzero_bytes(px) + nonzero_bytes(py);
+                        }
+                    }
+                }
+                const float mx = fmaxf(fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3])), fmaxf(fmaxf(v[4], v[5]), fmaxf(v[6], v[7])));
+                if (__any_sync(FULL, active && mx > 0.f && mx + q.const_score >= theta_s)) {
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const float sc = v[j] + q.const_score;
+                        const bool c = active && v[j] > 0.f && sc >= theta_s;
+                        if (!__any_sync(FULL, c)) continue;
+                        tk.offer(c, c ? make_key(sc, wlo + o8 + j) : 0ull, k, lane);
+                    }
+                    const float mine = tk.theta ? unsortable((uint32_t)(tk.theta >> 32)) : -INFINITY;
+                    if (mine > theta_s) {
+                        theta_s = mine;
+                        if (lane == 0) {
+                            atomicMax(&S.theta_cta, sortable(mine));
+                            if (p.qtheta) atomicMax(p.qtheta + it.query, sortable(mine));
+                        }
+                    } else if (p.qtheta) {  // pick up what the other work items of the query have reached
+                        const uint32_t gq = __ldcg(p.qtheta + it.query);
+                        if (gq > seen_t) { if (lane == 0) atomicMax(&S.theta_cta, gq); theta_s = fmaxf(theta_s, unsortable(gq)); }
+                    }
                 }
             }
+        };
+        using I0 = std::integral_constant<int, 0>;
+        using I1 = std::integral_constant<int, 1>;
+        using I2 = std::integral_constant<int, 2>;
+        if (nl) {
+            if (ncol == 1) chunk_loop(I1{}, std::true_type{});
+            else if (ncol == 2) chunk_loop(I2{}, std::true_type{});
+            else chunk_loop(I0{}, std::true_type{});
+        } else {
+            if (ncol == 1) chunk_loop(I1{}, std::false_type{});
+            else if (ncol == 2) chunk_loop(I2{}, std::false_type{});
+            else chunk_loop(I0{}, std::false_type{});
         }
         if (tid == 0) S.chunk[(r + 1) & 1] = 0;
         __syncthreads();
