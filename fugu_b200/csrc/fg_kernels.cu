@@ -1295,20 +1295,26 @@ __global__ void __launch_bounds__(NT, MINB) colscan_kernel(const SearchParams p)
     uint4 e_cur = make_uint4(0u, 0u, 0u, 0u);  // skip entry of block `cur`, fetched one block ahead
     uint32_t cd[4] = {EMPTY, EMPTY, EMPTY, EMPTY};  // carried postings, EMPTY = consumed
     float cv[4] = {0.f, 0.f, 0.f, 0.f};
-    if (warp < nl) {
-        const DevLeaf& L = S.leaf[warp];
+    // The NW warps share the plan's nl streamed leaves: warp w walks every nsub-th block of leaf w % nl
+    // (sub-stream w / nl), so a plan with one or two streamed leaves still decodes on all warps.
+    // (deterministic mode: one warp per leaf, leaves add in leaf order)
+    const int nsub = (nl && !p.deterministic) ? NW / nl : 1;
+    const int my_leaf = nl ? warp % nl : 0, my_sub = nl ? warp / nl : 0;
+    const bool streams = nl && my_sub < nsub;
+    if (streams) {
+        const DevLeaf& L = S.leaf[my_leaf];
         uint32_t a = 0, b = L.n_blocks;  // first block whose last_doc >= doc_lo
         while (a < b) {
             const uint32_t m = (a + b) >> 1;
             if (__ldg(&skip[L.blk_begin + m]).x >= lo0) b = m; else a = m + 1;
         }
-        cur = a;
+        cur = a + (uint32_t)((my_sub + nsub - (int)(a % (uint32_t)nsub)) % nsub);  // first block >= a of this sub-stream
         if (cur < L.n_blocks) e_cur = __ldg(&skip[L.blk_begin + cur]);
     }
     uint32_t my_matches = 0, my_scored = 0;
     unsigned long long my_blocks = 0, my_redecode = 0;
     auto stream_leaf = [&](uint32_t wlo, uint32_t whi, float* buf) {
-        const DevLeaf& L = S.leaf[warp];
+        const DevLeaf& L = S.leaf[my_leaf];
         while (true) {
             bool left = false;
 #pragma unroll
@@ -1323,7 +1329,7 @@ __global__ void __launch_bounds__(NT, MINB) colscan_kernel(const SearchParams p)
             if (cur >= L.n_blocks) break;
             const uint4 e = e_cur;              // (loaded when the previous block was taken)
             if (e.y >= whi) break;              // the next block starts behind this window
-            cur++;
+            cur += (uint32_t)nsub;
             if (cur < L.n_blocks) e_cur = __ldg(&skip[L.blk_begin + cur]);
             if (e.x < wlo) continue;            // (only before the item's first window)
             const uint32_t bd = e.w & 63u, bt = (e.w >> 6) & 63u, n = ((e.w >> 12) & 127u) + 1u;
@@ -1358,7 +1364,7 @@ __global__ void __launch_bounds__(NT, MINB) colscan_kernel(const SearchParams p)
                 if (warp == l) stream_leaf(wlo, whi, buf);
                 __syncthreads();
             }
-        } else if (warp < nl) {
+        } else if (streams) {
             stream_leaf(wlo, whi, buf);
         }
     };
