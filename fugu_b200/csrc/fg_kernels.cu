@@ -146,6 +146,16 @@ __device__ __forceinline__ void unpack4(const uint32_t* __restrict__ w, int lane
         v[1] = (x >> b) & m;
         v[2] = (x >> (2 * b)) & m;
         v[3] = (x >> (3 * b)) & m;
+    } else if (b <= 16) {
+        // 4 values = 4*b <= 64 bits starting at bit0: at most three consecutive words (sparse lists: 9..14 bits)
+        const uint32_t wi = bit0 >> 5, sh = bit0 & 31;
+        const uint32_t w0 = __ldg(w + wi), w1 = __ldg(w + wi + 1), w2 = __ldg(w + wi + 2);
+        const uint32_t x0 = __funnelshift_r(w0, w1, sh), x1 = __funnelshift_r(w1, w2, sh);  // bits [bit0, bit0+64)
+        const uint32_t m = (1u << b) - 1u;
+        v[0] = x0 & m;
+        v[1] = __funnelshift_r(x0, x1, b) & m;
+        v[2] = __funnelshift_rc(x0, x1, 2 * b) & m;  // (clamped form: 2*b may be 32)
+        v[3] = 3 * b >= 32 ? (x1 >> (3 * b - 32)) & m : __funnelshift_r(x0, x1, 3 * b) & m;
     } else {
         const uint32_t m = b >= 32 ? 0xFFFFFFFFu : ((1u << b) - 1u);
 #pragma unroll
