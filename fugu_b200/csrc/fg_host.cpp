@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "../../include/fugu_host.h"
+#include <time.h>
 #include "fg_error.h"
 #include "fg_pool.h"
 #include "fg_unicode_tables.h"
@@ -984,16 +985,32 @@ extern "C" int32_t fgh_search_batch(fgh_dataset* ds, uint32_t n, const char* con
     uint32_t nch = std::min<uint32_t>(2, n / 3072 + 1);
     if (const char* e = getenv("FG_PIPELINE_CHUNKS")) nch = (uint32_t)std::max(1, atoi(e));
     nch = std::max<uint32_t>(1, std::min(nch, n));
+    double first_frac = 1.0 / nch;
+    if (nch > 1) first_frac = 0.2;
+    if (const char* e = getenv("FG_PIPELINE_FIRST")) first_frac = std::min(0.9, std::max(0.05, atof(e)));
     struct Chunk { uint32_t a, b; PlannedBatch pb; fg_batch* batch = nullptr; };
     std::vector<Chunk> ch(nch);
     struct Cleanup {
         std::vector<Chunk>& c;
         ~Cleanup() { for (auto& x : c) if (x.batch) fg_batch_release(x.batch); }
     } cleanup{ch};
+    const bool timing = getenv("FG_TIMING") != nullptr;
+    auto now_ms = []() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
+    const double t_start = now_ms();
+    double t_plan = 0, t_prep = 0, t_sub = 0;
     for (uint32_t i = 0; i < nch; i++) {
         Chunk& C = ch[i];
-        C.a = (uint32_t)((uint64_t)n * i / nch);
-        C.b = (uint32_t)((uint64_t)n * (i + 1) / nch);
+        const double t0 = now_ms();
+        // uneven cut: the first chunk is small, so the device starts early, and sized so that it keeps the
+        // device busy about as long as the host needs for the rest (host ~ 1/3 of the device time per query)
+        auto cut = [&](uint32_t j) -> uint32_t {
+            if (j == 0) return 0;
+            if (j >= nch) return n;
+            const double first = first_frac, rest = (1.0 - first_frac) / (nch - 1);
+            return (uint32_t)std::min<double>(n, n * (first + rest * (j - 1)));
+        };
+        C.a = cut(i);
+        C.b = cut(i + 1);
         const uint32_t m = C.b - C.a;
         plan_batch(ds, m, queries + C.a, filters, filter_offsets ? filter_offsets + C.a : nullptr,
                    pages ? pages + C.a : nullptr, per_pages ? per_pages + C.a : nullptr, C.pb);
@@ -1007,12 +1024,16 @@ extern "C" int32_t fgh_search_batch(fgh_dataset* ds, uint32_t n, const char* con
         qb.queries = C.pb.q.data();
         qb.clauses = C.pb.c.data();
         qb.leaves = C.pb.l.data();
+        const double t1 = now_ms();
         int32_t r = fg_batch_prepare(ds->index, &qb, &C.batch);
         if (r) return r;
+        const double t2 = now_ms();
         // match counts are optional: the reference's TopDocs collector does not count (src/db/search.rs:162)
         r = fg_batch_submit(C.batch, 0, C.pb.kmax, out_match_count ? 1 : 0);
         if (r) return r;
+        t_plan += t1 - t0; t_prep += t2 - t1; t_sub += now_ms() - t2;
     }
+    const double t_submitted = now_ms();
     std::vector<fg_hit> hits;
     std::vector<uint32_t> nh, cnt;
     for (uint32_t i = 0; i < nch; i++) {
@@ -1033,6 +1054,9 @@ extern "C" int32_t fgh_search_batch(fgh_dataset* ds, uint32_t n, const char* con
             if (out_match_count) out_match_count[qi] = bad ? 0 : cnt[j];
         }
     }
+    if (timing)
+        fprintf(stderr, "[fgh_search_batch] n=%u chunks=%u: plan %.2f prepare %.2f submit %.2f | all submitted at %.2f, done at %.2f ms\n",
+                n, nch, t_plan, t_prep, t_sub, t_submitted - t_start, now_ms() - t_start);
     return FG_OK;
 }
 
