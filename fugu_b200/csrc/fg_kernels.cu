@@ -1454,11 +1454,21 @@ __global__ void __launch_bounds__(NT, MINB) colscan_kernel(const SearchParams p)
                 col_term8(ta, w0, magic, n, v);
                 if (NC != 1) col_term8(tb, w1, magic, n, v);
                 uint32_t px = ta.x | tb.x, py = ta.y | tb.y;  // OR of the columns' tf bytes: non-zero byte = doc matches
-                if (NC == 0) {
-                    for (int c = 2; c < ncol; c++) {
-                        const uint2 tc2 = __ldg(reinterpret_cast<const uint2*>(CL[c].col + wlo + o8));
-                        col_term8(tc2, CL[c].weight, magic, n, v);
-                        px |= tc2.x; py |= tc2.y;
+                if (NC == 0) {  // three or more column leaves: in pairs, the next pair's loads in flight
+                    uint2 t2 = make_uint2(0u, 0u), t3 = t2;
+                    int c = 2;
+                    t2 = __ldg(reinterpret_cast<const uint2*>(CL[2].col + wlo + o8));
+                    if (ncol > 3) t3 = __ldg(reinterpret_cast<const uint2*>(CL[3].col + wlo + o8));
+                    while (true) {
+                        col_term8(t2, CL[c].weight, magic, n, v);
+                        px |= t2.x; py |= t2.y;
+                        if (c + 1 >= ncol) break;
+                        col_term8(t3, CL[c + 1].weight, magic, n, v);
+                        px |= t3.x; py |= t3.y;
+                        c += 2;
+                        if (c >= ncol) break;
+                        t2 = __ldg(reinterpret_cast<const uint2*>(CL[c].col + wlo + o8));
+                        if (c + 1 < ncol) t3 = __ldg(reinterpret_cast<const uint2*>(CL[c + 1].col + wlo + o8));
                     }
                 }
                 if (slow) {
