@@ -85,7 +85,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -99,7 +99,7 @@ class ClockSampler:
     def stop(self) -> dict:
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.25)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -212,6 +212,7 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+EXCHANGE_NOTE: dict = {}  # filled by main(): how the per-shard top-k lists were exchanged
 QUERY_SHAPES = {1: "two-term AND queries", 2: "mixed 1-4-term AND/OR queries", 3: "OR queries of 2-6 of the 64 most frequent terms",
                 4: "3-term AND queries", 5: "2-term OR queries with 1-2 facet filters"}
 
@@ -221,7 +222,77 @@ def workload_config(cfg, args, world):
                         f"{cfg.n_queries} {QUERY_SHAPES.get(cfg.cfg, 'queries')}, top-{cfg.k}",
             "n_docs": cfg.n_docs, "n_queries": cfg.n_queries, "k": cfg.k,
             "sharding": f"doc-id range x{world}" if world > 1 else "single shard",
+            "exchange": EXCHANGE_NOTE.get("mode", "none"),
             "l2": "L2 flushed (256 MiB memset) before every timed step" if not args.no_flush else "warm L2 (no flush)"}
+
+
+class Exchange:
+    """The multi-GPU exchange step of the path: all-gather of the per-shard top-k lists,
+    plus the small control-plane reductions of the bench. The data path is NCCL over NVLink
+    (`all_gather_into_tensor` on device tensors). The control plane (global statistics, barriers, timing
+    reductions) runs on a gloo group with CPU tensors. If NCCL cannot bring its communicator up on this
+    box (probe with a deadline), the all-gather falls back to D2H -> gloo -> H2D and the JSON line says
+    so (`config.exchange`) instead of the run hanging."""
+
+    def __init__(self, dist, torch, dev, probe_seconds: float = 90.0, force: str | None = None):
+        self.dist, self.torch, self.dev = dist, torch, dev
+        self.world = dist.get_world_size()
+        self.ctl = dist.new_group(backend="gloo")
+        self.mode = force or "nccl"
+        if self.mode == "nccl":
+            ok = {"v": False}
+
+            def probe():
+                t = torch.ones(8, device=dev)
+                dist.all_reduce(t)
+                ok["v"] = bool(t.cpu()[0].item() == self.world)
+
+            th = threading.Thread(target=probe, daemon=True)
+            th.start()
+            th.join(probe_seconds)
+            flag = torch.tensor([1 if ok["v"] else 0], dtype=torch.int64)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.ctl)  # all ranks take the same route
+            if int(flag.item()) == 0:
+                self.mode = "gloo"
+                sys.stderr.write(f"bench.py: NCCL did not come up within {probe_seconds:.0f} s; exchanging through host memory (gloo)\n")
+
+    def barrier(self):
+        self.dist.barrier(group=self.ctl)
+
+    def allreduce_cpu(self, arr: np.ndarray, op: str = "sum") -> np.ndarray:
+        t = self.torch.from_numpy(np.ascontiguousarray(arr).copy())
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX if op == "max" else self.dist.ReduceOp.SUM, group=self.ctl)
+        return t.numpy()
+
+    def all_gather(self, out, inp):
+        """out [world, ...] <- inp [...] from every rank (device tensors)."""
+        if self.mode == "nccl":
+            self.dist.all_gather_into_tensor(out, inp)
+            return
+        h = inp.cpu()
+        parts = [self.torch.empty_like(h) for _ in range(self.world)]
+        self.dist.all_gather(parts, h, group=self.ctl)
+        out.copy_(self.torch.stack(parts).to(out.device, non_blocking=False))
+
+
+def arm_watchdog(seconds: float):
+    """A hung collective or kernel must not eat the caller's whole time limit: after `seconds` dump every
+    thread's Python stack to stderr and exit non-zero (FG_BENCH_DEADLINE overrides; 0 disables)."""
+    import faulthandler
+
+    seconds = float(os.environ.get("FG_BENCH_DEADLINE", seconds))
+    if seconds <= 0:
+        return
+    faulthandler.enable()
+    faulthandler.dump_traceback_later(max(30.0, seconds - 20.0), repeat=False, file=sys.stderr)
+
+    def _kill():
+        time.sleep(seconds)
+        sys.stderr.write(f"bench.py: no result after {seconds:.0f} s (rank {os.environ.get('RANK', '0')}), giving up\n")
+        sys.stderr.flush()
+        os._exit(124)
+
+    threading.Thread(target=_kill, daemon=True).start()
 
 
 def main():
@@ -230,6 +301,14 @@ def main():
         run_reference(args)
         return
     rank, local_rank, world = env_rank()
+    arm_watchdog(420 if world == 1 else 300)
+    if world > 1:
+        # one process per GPU on ONE node: keep NCCL's bootstrap on the loopback interface (the container's
+        # hostname may not resolve / its interfaces may be filtered), no InfiniBand probing, and leave the
+        # host cores to all ranks (planner / lowering pools and the upload's packing threads)
+        os.environ.setdefault("NCCL_SOCKET_IFNAME", "lo")
+        os.environ.setdefault("NCCL_IB_DISABLE", "1")
+        os.environ.setdefault("FG_HOST_THREADS", str(max(2, host_cores() // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world))))))
     import torch
 
     from fugu_b200 import _native as nat
@@ -245,19 +324,18 @@ def main():
         import torch.distributed as dist_mod
 
         dist = dist_mod
-        dist.init_process_group("nccl", device_id=dev)
+        dist.init_process_group("cpu:gloo,cuda:nccl")  # NCCL communicator is created by Exchange's probe
+    xch = Exchange(dist, torch, dev, force=os.environ.get("FG_BENCH_EXCHANGE")) if dist else None
+    EXCHANGE_NOTE["mode"] = ("NCCL all_gather_into_tensor + on-device merge" if xch.mode == "nccl" else
+                             "host-memory (gloo) all-gather + on-device merge: NCCL did not initialise") if xch else "none"
 
     cfg, corpus, fields, queries, d0, d1 = build_workload(args, rank, world)
     n_local = d1 - d0
     if world > 1:
         # global statistics (tantivy computes N, df and total_num_tokens over all segments, A.4)
         for f in fields:
-            df = torch.from_numpy(np.diff(f["term_offsets"]).astype(np.int64)).to(dev)
-            dist.all_reduce(df)
-            f["global_doc_freq"] = df.cpu().numpy().astype(np.uint32)
-            tt = torch.tensor([f["total_num_tokens"]], dtype=torch.int64, device=dev)
-            dist.all_reduce(tt)
-            f["total_num_tokens"] = int(tt.item())
+            f["global_doc_freq"] = xch.allreduce_cpu(np.diff(f["term_offsets"]).astype(np.int64)).astype(np.uint32)
+            f["total_num_tokens"] = int(xch.allreduce_cpu(np.array([f["total_num_tokens"]], np.int64))[0])
     desc = nat.HostIndexDesc(n_local, fields, doc_id_base=d0, global_n_docs=cfg.n_docs)
     ctx = nat.Context(local_rank)
     # a real (non-default) stream: the legacy default stream's handle is 0, which fg_ctx_set_stream
@@ -295,8 +373,8 @@ def main():
     def step():
         pb.execute(d_hits.data_ptr(), d_n.data_ptr(), d_c.data_ptr() if counts else None, None, k_stride=k)
         if world > 1:
-            dist.all_gather_into_tensor(g_hits, d_hits)
-            dist.all_gather_into_tensor(g_n, d_n)
+            xch.all_gather(g_hits, d_hits)
+            xch.all_gather(g_n, d_n)
             nat.merge_topk_device(ctx, g_hits.data_ptr(), g_n.data_ptr(), world, nq, k, k, f_hits.data_ptr(), f_n.data_ptr())
 
     # exact algorithmic-byte accounting pass (untimed). SURVEY.md 8(d) states the algorithmic bytes on
@@ -318,13 +396,13 @@ def main():
         step()
     # keep the GPU under the same load for ~0.5 s so that nvidia-smi (>= 50 ms period) sees the clocks
     # the timed steps run at; these extra steps are untimed warm-up
-    t_hold = time.perf_counter() + 0.5
+    t_hold = time.perf_counter() + 1.0
     while time.perf_counter() < t_hold:
         step()
         torch.cuda.synchronize()
     torch.cuda.synchronize()
     if dist:
-        dist.barrier()
+        xch.barrier()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     kern_ms = []
     torch.cuda.synchronize()
@@ -338,16 +416,12 @@ def main():
         kern_ms.append(s2.search_kernel_ms)
     torch.cuda.synchronize()
     if dist:
-        dist.barrier()
+        xch.barrier()
     clocks = sampler.stop() if rank == 0 else None
     total_ms = sum(a.elapsed_time(b) for a, b in ev)
     if dist:
-        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
-        ab = torch.tensor([float(algo_bytes)], dtype=torch.float64, device=dev)
-        dist.all_reduce(ab)
-        algo_total = float(ab.item())
+        total_ms = float(xch.allreduce_cpu(np.array([total_ms], np.float64), "max")[0])
+        algo_total = float(xch.allreduce_cpu(np.array([float(algo_bytes)], np.float64))[0])
     else:
         algo_total = float(algo_bytes)
     st_timed = pb.stats()
@@ -358,13 +432,13 @@ def main():
     e2e_times = []
     for it in range(2 + min(args.steps, 10)):
         if dist:
-            dist.barrier()
+            xch.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         h_hits, h_n, h_c, _ = ds.search_batch(qset, want_counts=counts)  # fgh_search_batch: strings -> plan -> H2D -> kernels -> D2H
         if world > 1:
-            dist.all_gather_into_tensor(g_hits, torch.from_numpy(h_hits.view(np.int32).reshape(nq, k, 2)).to(dev))
-            dist.all_gather_into_tensor(g_n, torch.from_numpy(h_n.view(np.int32)).to(dev))
+            xch.all_gather(g_hits, torch.from_numpy(h_hits.view(np.int32).reshape(nq, k, 2)).to(dev))
+            xch.all_gather(g_n, torch.from_numpy(h_n.view(np.int32)).to(dev))
             nat.merge_topk_device(ctx, g_hits.data_ptr(), g_n.data_ptr(), world, nq, k, k, f_hits.data_ptr(), f_n.data_ptr())
             f_hits.cpu(); f_n.cpu()
         dt = time.perf_counter() - t0
@@ -374,15 +448,20 @@ def main():
     if os.environ.get("FG_TIMING"):
         print("e2e_times ms", [round(x * 1e3, 2) for x in e2e_times], file=sys.stderr)
     if dist:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
+        e2e_s = float(xch.allreduce_cpu(np.array([e2e_s], np.float64), "max")[0])
     lowered_bytes = nq * 48 + len(batch.l) * 64 + st_touched.n_work_items * 32
     out_bytes = nq * k * 8 + nq * 8
 
+    def shutdown():
+        if not dist:
+            return
+        if xch.mode != "nccl":  # a communicator that never came up cannot be torn down either
+            sys.stdout.flush()
+            os._exit(0)
+        dist.destroy_process_group()
+
     if rank != 0:
-        if dist:
-            dist.destroy_process_group()
+        shutdown()
         return
 
     peak, peak_src = peak_hbm()
@@ -441,8 +520,7 @@ def main():
                                 "sample": f"first {ns} queries of the batch on rank 0's shard, best of 3, oracle C++ "
                                           f"(restatement of tantivy 0.24.1 semantics, exhaustive DAAT), {cores} threads; cpu: {cpu_model()}"}
     print(json.dumps(line), flush=True)
-    if dist:
-        dist.destroy_process_group()
+    shutdown()
 
 
 if __name__ == "__main__":

@@ -91,3 +91,38 @@ def test_two_rank_sharded_search_equals_single_shard():
         got["score"] = [x[0] for x in m]
         got["doc"] = [x[1] for x in m]
         check_topk(got, hits[q, :n[q]], k=batch.kmax, ctx=f"query {q}")
+
+
+def _exchange_worker(rank, world, port, ret):
+    import bench
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    x = bench.Exchange(dist, torch, torch.device("cpu"), force="gloo")  # the host-memory route of bench.py
+    df = x.allreduce_cpu(np.arange(5, dtype=np.int64) * (rank + 1))
+    mx = x.allreduce_cpu(np.array([float(rank)], np.float64), "max")
+    inp = torch.full((3, 2), rank, dtype=torch.int32)
+    out = torch.zeros((world, 3, 2), dtype=torch.int32)
+    x.all_gather(out, inp)
+    x.barrier()
+    if rank == 0:
+        ret["df"] = df.tolist()
+        ret["mx"] = float(mx[0])
+        ret["out"] = out.numpy().tolist()
+        ret["mode"] = x.mode
+    dist.destroy_process_group()
+
+
+def test_bench_exchange_host_memory_route():
+    """bench.py's Exchange helper (control-plane reductions + the gloo fallback of the top-k all-gather,
+    used when NCCL cannot initialise) on two CPU ranks."""
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_exchange_worker, args=(2, port, ret), nprocs=2, join=True)
+    assert ret["mode"] == "gloo"
+    assert ret["df"] == [0, 3, 6, 9, 12] and ret["mx"] == 1.0
+    assert ret["out"] == [[[0, 0]] * 3, [[1, 1]] * 3]
