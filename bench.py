@@ -307,6 +307,7 @@ def main():
         # hostname may not resolve / its interfaces may be filtered), no InfiniBand probing, and leave the
         # host cores to all ranks (planner / lowering pools and the upload's packing threads)
         os.environ.setdefault("NCCL_SOCKET_IFNAME", "lo")
+        os.environ.setdefault("GLOO_SOCKET_IFNAME", "lo")
         os.environ.setdefault("NCCL_IB_DISABLE", "1")
         os.environ.setdefault("FG_HOST_THREADS", str(max(2, host_cores() // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world))))))
     import torch
@@ -392,14 +393,22 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    torch.cuda.synchronize()
+    t_w = time.perf_counter()
     for _ in range(args.warmup):
         step()
-    # keep the GPU under the same load for ~0.5 s so that nvidia-smi (>= 50 ms period) sees the clocks
-    # the timed steps run at; these extra steps are untimed warm-up
-    t_hold = time.perf_counter() + 1.0
-    while time.perf_counter() < t_hold:
+    torch.cuda.synchronize()
+    # keep the GPU under the same load for ~1 s so that nvidia-smi (200 ms period) sees the clocks the
+    # timed steps run at; these extra steps are untimed warm-up. Every step contains collectives when
+    # N > 1, so ALL RANKS MUST RUN THE SAME NUMBER OF THEM: the count is agreed on (max over ranks), never
+    # decided by each rank's own clock (a rank-local `while time < deadline` loop deadlocks as soon as two
+    # ranks disagree by one step).
+    t_step = max((time.perf_counter() - t_w) / max(args.warmup, 1), 1e-4)
+    n_hold = int(min(2000, max(1, round(1.0 / t_step)))) if args.warmup else 100
+    if dist:
+        n_hold = int(xch.allreduce_cpu(np.array([n_hold], np.int64), "max")[0])
+    for _ in range(n_hold):
         step()
-        torch.cuda.synchronize()
     torch.cuda.synchronize()
     if dist:
         xch.barrier()
