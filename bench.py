@@ -228,41 +228,25 @@ def workload_config(cfg, args, world):
 
 class Exchange:
     """The multi-GPU exchange step of the path: all-gather of the per-shard top-k lists,
-    plus the small control-plane reductions of the bench. The data path is NCCL over NVLink
-    (`all_gather_into_tensor` on device tensors). The control plane (global statistics, barriers, timing
-    reductions) runs on a gloo group with CPU tensors. If NCCL cannot bring its communicator up on this
-    box (probe with a deadline), the all-gather falls back to D2H -> gloo -> H2D and the JSON line says
-    so (`config.exchange`) instead of the run hanging."""
+    plus the small control-plane reductions of the bench (global statistics, barriers, max-over-ranks
+    timing). Default route: everything on NCCL with device tensors (`all_gather_into_tensor` over
+    NVLink) - the configuration verified on B200s. `FG_BENCH_EXCHANGE=gloo` is an explicit opt-in for a
+    box whose NCCL cannot initialise: the lists then travel D2H -> gloo -> H2D and the JSON line says so
+    (`config.exchange`)."""
 
-    def __init__(self, dist, torch, dev, probe_seconds: float = 90.0, force: str | None = None):
-        self.dist, self.torch, self.dev = dist, torch, dev
+    def __init__(self, dist, torch, dev, mode: str = "nccl"):
+        self.dist, self.torch, self.dev, self.mode = dist, torch, dev, mode
         self.world = dist.get_world_size()
-        self.ctl = dist.new_group(backend="gloo")
-        self.mode = force or "nccl"
-        if self.mode == "nccl":
-            ok = {"v": False}
-
-            def probe():
-                t = torch.ones(8, device=dev)
-                dist.all_reduce(t)
-                ok["v"] = bool(t.cpu()[0].item() == self.world)
-
-            th = threading.Thread(target=probe, daemon=True)
-            th.start()
-            th.join(probe_seconds)
-            flag = torch.tensor([1 if ok["v"] else 0], dtype=torch.int64)
-            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.ctl)  # all ranks take the same route
-            if int(flag.item()) == 0:
-                self.mode = "gloo"
-                sys.stderr.write(f"bench.py: NCCL did not come up within {probe_seconds:.0f} s; exchanging through host memory (gloo)\n")
 
     def barrier(self):
-        self.dist.barrier(group=self.ctl)
+        self.dist.barrier()
 
     def allreduce_cpu(self, arr: np.ndarray, op: str = "sum") -> np.ndarray:
         t = self.torch.from_numpy(np.ascontiguousarray(arr).copy())
-        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX if op == "max" else self.dist.ReduceOp.SUM, group=self.ctl)
-        return t.numpy()
+        if self.mode == "nccl":
+            t = t.to(self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX if op == "max" else self.dist.ReduceOp.SUM)
+        return t.cpu().numpy()
 
     def all_gather(self, out, inp):
         """out [world, ...] <- inp [...] from every rank (device tensors)."""
@@ -271,7 +255,7 @@ class Exchange:
             return
         h = inp.cpu()
         parts = [self.torch.empty_like(h) for _ in range(self.world)]
-        self.dist.all_gather(parts, h, group=self.ctl)
+        self.dist.all_gather(parts, h)
         out.copy_(self.torch.stack(parts).to(out.device, non_blocking=False))
 
 
@@ -303,12 +287,7 @@ def main():
     rank, local_rank, world = env_rank()
     arm_watchdog(420 if world == 1 else 300)
     if world > 1:
-        # one process per GPU on ONE node: keep NCCL's bootstrap on the loopback interface (the container's
-        # hostname may not resolve / its interfaces may be filtered), no InfiniBand probing, and leave the
-        # host cores to all ranks (planner / lowering pools and the upload's packing threads)
-        os.environ.setdefault("NCCL_SOCKET_IFNAME", "lo")
-        os.environ.setdefault("GLOO_SOCKET_IFNAME", "lo")
-        os.environ.setdefault("NCCL_IB_DISABLE", "1")
+        # leave the host cores to all ranks (planner / lowering pools and the upload's packing threads)
         os.environ.setdefault("FG_HOST_THREADS", str(max(2, host_cores() // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world))))))
     import torch
 
@@ -325,10 +304,15 @@ def main():
         import torch.distributed as dist_mod
 
         dist = dist_mod
-        dist.init_process_group("cpu:gloo,cuda:nccl")  # NCCL communicator is created by Exchange's probe
-    xch = Exchange(dist, torch, dev, force=os.environ.get("FG_BENCH_EXCHANGE")) if dist else None
+        xmode = os.environ.get("FG_BENCH_EXCHANGE", "nccl")
+        if xmode == "nccl":
+            dist.init_process_group("nccl", device_id=dev)
+        else:
+            os.environ.setdefault("GLOO_SOCKET_IFNAME", "lo")
+            dist.init_process_group("gloo")
+    xch = Exchange(dist, torch, dev, mode=xmode) if dist else None
     EXCHANGE_NOTE["mode"] = ("NCCL all_gather_into_tensor + on-device merge" if xch.mode == "nccl" else
-                             "host-memory (gloo) all-gather + on-device merge: NCCL did not initialise") if xch else "none"
+                             "host-memory (gloo) all-gather + on-device merge (FG_BENCH_EXCHANGE=gloo)") if xch else "none"
 
     cfg, corpus, fields, queries, d0, d1 = build_workload(args, rank, world)
     n_local = d1 - d0
@@ -462,12 +446,8 @@ def main():
     out_bytes = nq * k * 8 + nq * 8
 
     def shutdown():
-        if not dist:
-            return
-        if xch.mode != "nccl":  # a communicator that never came up cannot be torn down either
-            sys.stdout.flush()
-            os._exit(0)
-        dist.destroy_process_group()
+        if dist:
+            dist.destroy_process_group()
 
     if rank != 0:
         shutdown()

@@ -98,7 +98,7 @@ def _exchange_worker(rank, world, port, ret):
 
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    x = bench.Exchange(dist, torch, torch.device("cpu"), force="gloo")  # the host-memory route of bench.py
+    x = bench.Exchange(dist, torch, torch.device("cpu"), mode="gloo")  # the host-memory route of bench.py
     df = x.allreduce_cpu(np.arange(5, dtype=np.int64) * (rank + 1))
     mx = x.allreduce_cpu(np.array([float(rank)], np.float64), "max")
     inp = torch.full((3, 2), rank, dtype=torch.int32)
@@ -114,8 +114,8 @@ def _exchange_worker(rank, world, port, ret):
 
 
 def test_bench_exchange_host_memory_route():
-    """bench.py's Exchange helper (control-plane reductions + the gloo fallback of the top-k all-gather,
-    used when NCCL cannot initialise) on two CPU ranks."""
+    """bench.py's Exchange helper (control-plane reductions + the opt-in host-memory route of the top-k
+    all-gather, FG_BENCH_EXCHANGE=gloo) on two CPU ranks."""
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
