@@ -286,6 +286,11 @@ def main():
         return
     rank, local_rank, world = env_rank()
     arm_watchdog(420 if world == 1 else 300)
+    # stdout carries exactly ONE JSON line: anything native libraries print there (NCCL's version banner)
+    # is sent to stderr; the line itself is written to the saved descriptor at the end
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         # leave the host cores to all ranks (planner / lowering pools and the upload's packing threads)
         os.environ.setdefault("FG_HOST_THREADS", str(max(2, host_cores() // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world))))))
@@ -508,7 +513,8 @@ def main():
                                 "single_thread_qps": max(1, ns // 10) / dt1,
                                 "sample": f"first {ns} queries of the batch on rank 0's shard, best of 3, oracle C++ "
                                           f"(restatement of tantivy 0.24.1 semantics, exhaustive DAAT), {cores} threads; cpu: {cpu_model()}"}
-    print(json.dumps(line), flush=True)
+    sys.stdout.flush()
+    os.write(json_fd, (json.dumps(line) + "\n").encode())
     shutdown()
 
 
