@@ -472,3 +472,18 @@ def test_async_submit_collect_and_pipelined_requests(ctx):
         for q in range(len(strings)):
             check_topk(got[0][q, :got[1][q]], ref[0][q, :ref[1][q]], k=10, ctx=f"chunks {chunks} query {q}")
     ds.close()
+
+
+def test_multi_item_plans_forced_small_items(ctx, monkeypatch):
+    """Work-item boundaries: with tiny item sizes every query is cut into many doc-id ranges (16-aligned
+    cuts, blocks straddling two items, streamed leaves starting mid-list, per-item partial top-k lists and
+    counts merged per query) -- the shape a 1 M-doc batch has, at a size the oracle checks in seconds."""
+    for k_, v_ in (("FG_ITEM_BYTES", "8192"), ("FG_ITEM_BYTES_HASH", "4096"), ("FG_ITEM_BYTES_MASKED", "8192"),
+                   ("FG_COL_COST_DIV", "1"), ("FG_COL_COST_DIV_PHASES", "1")):
+        monkeypatch.setenv(k_, v_)
+    cfg = synth.Config(cfg=2, n_docs=120_008, vocab=20_000, n_queries=400, k=10, name_pct=10)
+    corpus, desc, index = _setup(ctx, cfg)
+    batch = plan_queries(synth.gen_queries(cfg), vocab=cfg.vocab, n_text_fields=2)
+    res = check_batch_against_oracle(index, desc, batch)
+    assert res["stats"].n_work_items > 2 * batch.n_queries
+    index.close()
