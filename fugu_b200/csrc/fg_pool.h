@@ -2,6 +2,8 @@
 // (fg_api.cu). A 5000-query batch is planned and lowered in ~1 ms on one thread; starting fresh
 // std::threads for every call costs almost as much as the work they take over.
 #pragma once
+#include <unistd.h>
+
 #include <condition_variable>
 #include <functional>
 #include <mutex>
@@ -20,7 +22,8 @@ public:
     // runs fn(0) .. fn(n-1), fn(0) on the calling thread; returns when all are done.
     // Calls from different threads serialise (one job at a time).
     void run(int n, const std::function<void(int)>& fn) {
-        if (n <= 1 || workers_.empty()) {
+        // (a fork()ed child inherits this object but not its worker threads: run inline there)
+        if (n <= 1 || workers_.empty() || getpid() != pid_) {
             for (int i = 0; i < n; i++) fn(i);
             return;
         }
@@ -41,7 +44,7 @@ public:
     }
 
 private:
-    HostPool() {
+    HostPool() : pid_(getpid()) {
         unsigned hw = std::thread::hardware_concurrency();
         if (const char* e = getenv("FG_HOST_THREADS")) hw = (unsigned)atoi(e);
         const int n = (int)std::max(1u, std::min(hw ? hw : 4u, 8u));
@@ -72,6 +75,7 @@ private:
             seen = gen_;
         }
     }
+    const pid_t pid_;
     std::vector<std::thread> workers_;
     std::mutex mu_, job_mu_;
     std::condition_variable cv_, done_;
