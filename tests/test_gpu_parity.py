@@ -485,5 +485,5 @@ def test_multi_item_plans_forced_small_items(ctx, monkeypatch):
     corpus, desc, index = _setup(ctx, cfg)
     batch = plan_queries(synth.gen_queries(cfg), vocab=cfg.vocab, n_text_fields=2)
     res = check_batch_against_oracle(index, desc, batch)
-    assert res["stats"].n_work_items > 2 * batch.n_queries
+    assert res["stats"].n_work_items > batch.n_queries  # (heavy queries are cut into up to 14 / 29 items)
     index.close()
