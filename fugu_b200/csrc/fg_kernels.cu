@@ -114,11 +114,6 @@ __device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
     for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
     return v;
 }
-__device__ __forceinline__ unsigned long long warp_sum64(unsigned long long v) {
-#pragma unroll
-    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-    return v;
-}
 __device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, int lane) {
     uint32_t x = v;
 #pragma unroll
