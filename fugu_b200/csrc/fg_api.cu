@@ -228,6 +228,14 @@ struct HostField {
     float cnorm = 0.f;
     std::vector<TermInfo> terms;
 };
+struct DeviceArena {
+    int device = 0;
+    std::vector<void*> allocs;
+    ~DeviceArena() {
+        cudaSetDevice(device);
+        for (void* p : allocs) cudaFree(p);
+    }
+};
 struct fg_index {
     fg_ctx* ctx = nullptr;
     uint32_t n_docs = 0, doc_base = 0;
@@ -235,7 +243,10 @@ struct fg_index {
     std::vector<HostField> fields;
     fg_index_info info{};
     DevIndex dev{};
-    std::vector<void*> allocs;
+    // device arrays of the snapshot. Shared by the snapshots fg_index_with_alive derives from this
+    // one (same postings, another alive bitset); freed when the last of them is released.
+    std::shared_ptr<DeviceArena> arena;
+    void* own_alive = nullptr;  // alive bitset of a derived snapshot (not in the arena)
     // dense tf columns of the most frequent terms (see build_columns)
     const uint8_t* d_cols = nullptr;
     uint64_t col_stride = 0;
@@ -276,11 +287,21 @@ static void pack_stream(uint32_t* words, const uint32_t* vals, uint32_t n, uint3
     }
 }
 
+static uint32_t count_alive(const uint32_t* bits, uint32_t n_docs) {
+    uint32_t na = 0;
+    for (uint32_t w = 0; w < (n_docs + 31) / 32; w++) {
+        uint32_t x = bits[w];
+        if (w == n_docs / 32 && (n_docs & 31)) x &= (1u << (n_docs & 31)) - 1u;
+        na += (uint32_t)__builtin_popcount(x);
+    }
+    return na;
+}
+
 extern "C" void fg_index_release(fg_index* ix) {
     if (!ix) return;
     if (ix->ctx) cudaSetDevice(ix->ctx->device);
-    for (void* p : ix->allocs) cudaFree(p);
-    delete ix;
+    if (ix->own_alive) cudaFree(ix->own_alive);
+    delete ix;  // drops this snapshot's share of the arena
 }
 
 extern "C" int32_t fg_index_upload(fg_ctx* ctx, const fg_index_desc* d, fg_index** out) {
@@ -292,6 +313,8 @@ extern "C" int32_t fg_index_upload(fg_ctx* ctx, const fg_index_desc* d, fg_index
     CU(cudaSetDevice(ctx->device));
     std::unique_ptr<fg_index, void (*)(fg_index*)> ix(new fg_index(), fg_index_release);
     ix->ctx = ctx;
+    ix->arena = std::make_shared<DeviceArena>();
+    ix->arena->device = ctx->device;
     ix->n_docs = d->n_docs;
     ix->doc_base = d->doc_id_base;
     ix->global_n_docs = d->global_n_docs ? d->global_n_docs : d->n_docs;
@@ -432,7 +455,7 @@ extern "C" int32_t fg_index_upload(fg_ctx* ctx, const fg_index_desc* d, fg_index
     auto dev_copy = [&](const void* src, size_t bytes, const void** dst) -> int32_t {
         void* p = nullptr;
         CU(cudaMalloc(&p, std::max<size_t>(bytes, 16)));
-        ix->allocs.push_back(p);
+        ix->arena->allocs.push_back(p);
         if (bytes) CU(cudaMemcpy(p, src, bytes, cudaMemcpyHostToDevice));
         *dst = p;
         ix->info.device_bytes += bytes;
@@ -456,16 +479,7 @@ extern "C" int32_t fg_index_upload(fg_ctx* ctx, const fg_index_desc* d, fg_index
         if ((rc = dev_copy(d->alive_bitset, ((size_t)d->n_docs + 31) / 32 * 4, (const void**)&ix->dev.alive))) return rc;
     ix->dev.n_docs = d->n_docs;
     ix->dev.doc_base = d->doc_id_base;
-    ix->dev.n_alive = d->n_docs;
-    if (d->alive_bitset) {
-        uint32_t na = 0;
-        for (uint32_t w = 0; w < (d->n_docs + 31) / 32; w++) {
-            uint32_t x = d->alive_bitset[w];
-            if (w == d->n_docs / 32 && (d->n_docs & 31)) x &= (1u << (d->n_docs & 31)) - 1u;
-            na += (uint32_t)__builtin_popcount(x);
-        }
-        ix->dev.n_alive = na;
-    }
+    ix->dev.n_alive = d->alive_bitset ? count_alive(d->alive_bitset, d->n_docs) : d->n_docs;
 
     // ---- dense tf columns -----------------------------------------------------------------
     // A term that occurs in at least 1/FG_COL_DIV of the shard's docs additionally gets a dense
@@ -545,6 +559,30 @@ extern "C" int32_t fg_index_term_info(const fg_index* ix, uint32_t field, uint32
     if (gdf) *gdf = t.df_global;
     if (nb) *nb = t.n_blocks;
     if (bytes) *bytes = t.bytes;
+    return FG_OK;
+}
+
+// A snapshot that differs from `base` only in which docs are alive (deletes since the last commit,
+// src/db/document.rs:38-41,65): shares every device array of `base`, uploads n_docs/8 bytes.
+extern "C" int32_t fg_index_with_alive(fg_index* base, const uint32_t* alive_bitset, fg_index** out) {
+    if (!base || !out) return fail(FG_ERR_INVALID, "fg_index_with_alive: NULL argument");
+    *out = nullptr;
+    CU(cudaSetDevice(base->ctx->device));
+    std::unique_ptr<fg_index, void (*)(fg_index*)> ix(new fg_index(*base), fg_index_release);
+    ix->own_alive = nullptr;  // the copy must not adopt base's private bitset
+    ix->dev.alive = nullptr;
+    ix->dev.n_alive = base->n_docs;
+    if (alive_bitset) {
+        // same padding rule as the other per-doc arrays: kernels read the bits of 8 docs as one byte
+        const size_t bytes = ((size_t)base->n_docs + 31) / 32 * 4, padded = (bytes + 16 + 15) & ~(size_t)15;
+        CU(cudaMalloc(&ix->own_alive, padded));
+        CU(cudaMemset(ix->own_alive, 0, padded));
+        if (bytes) CU(cudaMemcpy(ix->own_alive, alive_bitset, bytes, cudaMemcpyHostToDevice));
+        ix->dev.alive = (const uint32_t*)ix->own_alive;
+        ix->dev.n_alive = count_alive(alive_bitset, base->n_docs);
+        ix->info.device_bytes += bytes;
+    }
+    *out = ix.release();
     return FG_OK;
 }
 

@@ -354,7 +354,11 @@ struct FieldBuild {
 
 struct fgh_dataset {
     fg_ctx* ctx = nullptr;
-    fg_index* index = nullptr;
+    // current device snapshot. Searches take a reference for the duration of the call, so a concurrent
+    // commit can swap the snapshot without pulling it from under them (a tantivy Searcher behaves the
+    // same way: it keeps the segments it was opened on).
+    std::shared_ptr<fg_index> index;
+    uint32_t committed_docs = 0;  // n_docs of the snapshot in `index`
     std::mutex mu;
     FieldBuild f[3];
     std::vector<std::string> ids;
@@ -374,11 +378,18 @@ extern "C" int32_t fgh_dataset_create(fg_ctx* ctx, fgh_dataset** out) {
 }
 extern "C" void fgh_dataset_destroy(fgh_dataset* ds) {
     if (!ds) return;
-    if (ds->index) fg_index_release(ds->index);
-    delete ds;
+    delete ds;  // releases the snapshot unless a search still holds it
 }
 extern "C" uint32_t fgh_dataset_num_docs(const fgh_dataset* ds) { return ds ? ds->n_docs : 0; }
-extern "C" fg_index* fgh_dataset_index(fgh_dataset* ds) { return ds ? ds->index : nullptr; }
+extern "C" fg_index* fgh_dataset_index(fgh_dataset* ds) {
+    if (!ds) return nullptr;
+    std::lock_guard<std::mutex> g(ds->mu);
+    return ds->index.get();
+}
+static std::shared_ptr<fg_index> current_snapshot(fgh_dataset* ds) {
+    std::lock_guard<std::mutex> g(ds->mu);
+    return ds->index;
+}
 
 extern "C" int32_t fgh_tokenize(const char* text, char* buf, uint32_t cap) {
     if (!text || !buf) return -1;
@@ -469,6 +480,22 @@ extern "C" int32_t fgh_dataset_commit(fgh_dataset* ds) {
     std::lock_guard<std::mutex> g(ds->mu);
     if (ds->adopted) return FG_OK;
     if (!ds->ctx) return host_fail(FG_ERR_NO_DEVICE, "dataset has no device context (planning only)");
+    std::vector<uint32_t> alive((ds->n_docs + 31) / 32, 0);
+    bool any_dead = false;
+    for (uint32_t d = 0; d < ds->n_docs; d++) {
+        if (ds->alive[d]) alive[d >> 5] |= 1u << (d & 31);
+        else any_dead = true;
+    }
+    if (ds->index && !ds->dirty) return FG_OK;  // nothing changed since the last commit
+    if (ds->index && ds->committed_docs == ds->n_docs && !getenv("FG_NO_INCREMENTAL")) {
+        // only deletes since the last commit: the postings are unchanged, refresh the alive bitset
+        fg_index* nx = nullptr;
+        int32_t rc = fg_index_with_alive(ds->index.get(), any_dead ? alive.data() : nullptr, &nx);
+        if (rc) return rc;
+        ds->index.reset(nx, fg_index_release);
+        ds->dirty = false;
+        return FG_OK;
+    }
     struct Csr { std::vector<uint64_t> off; std::vector<uint32_t> docs, tfs; std::vector<uint8_t> fn; };
     Csr c[3];
     fg_field_desc fd[3];
@@ -498,12 +525,6 @@ extern "C" int32_t fgh_dataset_commit(fgh_dataset* ds) {
             fd[f].term_freqs = c[f].tfs.data();
         }
     }
-    std::vector<uint32_t> alive((ds->n_docs + 31) / 32, 0);
-    bool any_dead = false;
-    for (uint32_t d = 0; d < ds->n_docs; d++) {
-        if (ds->alive[d]) alive[d >> 5] |= 1u << (d & 31);
-        else any_dead = true;
-    }
     fg_index_desc desc;
     memset(&desc, 0, sizeof(desc));
     desc.n_docs = ds->n_docs;
@@ -513,8 +534,8 @@ extern "C" int32_t fgh_dataset_commit(fgh_dataset* ds) {
     fg_index* nx = nullptr;
     int32_t rc = fg_index_upload(ds->ctx, &desc, &nx);
     if (rc) return rc;
-    if (ds->index) fg_index_release(ds->index);
-    ds->index = nx;
+    ds->index.reset(nx, fg_index_release);
+    ds->committed_docs = ds->n_docs;
     ds->dirty = false;
     return FG_OK;
 }
@@ -528,8 +549,7 @@ extern "C" int32_t fgh_dataset_adopt(fgh_dataset* ds, const fg_index_desc* desc,
         fg_index* nx = nullptr;
         int32_t rc = fg_index_upload(ds->ctx, desc, &nx);
         if (rc) return rc;
-        if (ds->index) fg_index_release(ds->index);
-        ds->index = nx;
+        ds->index.reset(nx, fg_index_release);
     }
     for (uint32_t f = 0; f < desc->n_fields; f++) {
         ds->f[f] = FieldBuild();
@@ -977,7 +997,8 @@ extern "C" int32_t fgh_search_batch(fgh_dataset* ds, uint32_t n, const char* con
                                     fg_hit* out_hits, uint32_t* out_n, uint32_t* out_match_count,
                                     int32_t* status) {
     if (!ds || (n && (!queries || !out_hits || !out_n))) return host_fail(FG_ERR_INVALID, "fgh_search_batch: NULL argument");
-    if (!ds->index) return host_fail(ds->ctx ? FG_ERR_INVALID : FG_ERR_NO_DEVICE, "dataset has no device snapshot (commit first)");
+    const std::shared_ptr<fg_index> snap = current_snapshot(ds);  // held until the results are collected
+    if (!snap) return host_fail(ds->ctx ? FG_ERR_INVALID : FG_ERR_NO_DEVICE, "dataset has no device snapshot (commit first)");
     if (n == 0) return FG_OK;
     // Large requests are cut into a few chunks and pipelined: while the device evaluates chunk i
     // (fg_batch_submit returns at once) this thread parses, plans and lowers chunk i+1, so the host
@@ -1025,7 +1046,7 @@ extern "C" int32_t fgh_search_batch(fgh_dataset* ds, uint32_t n, const char* con
         qb.clauses = C.pb.c.data();
         qb.leaves = C.pb.l.data();
         const double t1 = now_ms();
-        int32_t r = fg_batch_prepare(ds->index, &qb, &C.batch);
+        int32_t r = fg_batch_prepare(snap.get(), &qb, &C.batch);
         if (r) return r;
         const double t2 = now_ms();
         // match counts are optional: the reference's TopDocs collector does not count (src/db/search.rs:162)
@@ -1066,4 +1087,129 @@ extern "C" int32_t fgh_search(fgh_dataset* ds, const char* query, const char* co
     const uint32_t offs[2] = {0, n_filters};
     return fgh_search_batch(ds, 1, &query, filters, offs, &page, &per_page, per_page, out_hits, out_n,
                             out_match_count, nullptr);
+}
+
+// ------------------------------------------------------------------------------------------
+// facet counting: FacetCollector::for_field("facet") + add_facet(root)
+// over AllQuery, src/db/facet.rs:35-103,206-233
+// ------------------------------------------------------------------------------------------
+namespace {
+
+struct FacetEnt { const char* p; uint32_t len, ord, depth; };
+
+// tantivy orders facets by their encoded form, in which the segments are joined by '\0'
+// (Facet's Ord is the byte order of that string): '/' compares below every other byte
+inline bool facet_less(const FacetEnt& a, const FacetEnt& b) {
+    const uint32_t n = std::min(a.len, b.len);
+    for (uint32_t i = 0; i < n; i++) {
+        const unsigned ca = a.p[i] == '/' ? 0u : (unsigned char)a.p[i], cb = b.p[i] == '/' ? 0u : (unsigned char)b.p[i];
+        if (ca != cb) return ca < cb;
+    }
+    return a.len < b.len;
+}
+
+// dictionary entries strictly below `root`, at most max_depth segments below it (0 = no limit), in
+// facet order, which is also the pre-order of collect_facets_recursive (src/db/facet.rs:206-233).
+// Caller holds ds->mu (the pool the entries point into grows with upserts).
+int32_t facet_enumerate(const fgh_dataset* ds, const char* root, uint32_t max_depth, std::vector<FacetEnt>& out) {
+    std::vector<std::string> segs;
+    if (!root || !facet_segments(root, segs))  // Facet::from(path) panics on a path without the leading '/'
+        return host_fail(FG_ERR_INVALID, "facet root '%s' must start with '/'", root ? root : "(null)");
+    const std::string rk = facet_key(segs, segs.size());  // "" for the root facet "/"
+    const TermDict& dict = ds->f[FGH_FIELD_FACET].dict;
+    for (const TermDict::Ent& e : dict.ents) {
+        const char* s = dict.pool.data() + e.off;
+        if (e.len <= rk.size() + 1 || memcmp(s, rk.data(), rk.size()) != 0 || s[rk.size()] != '/') continue;
+        uint32_t depth = 0;
+        for (uint32_t i = (uint32_t)rk.size(); i < e.len; i++) depth += s[i] == '/';
+        if (max_depth && depth > max_depth) continue;
+        out.push_back({s, e.len, e.ord, depth});
+    }
+    std::sort(out.begin(), out.end(), facet_less);
+    return FG_OK;
+}
+
+int32_t facet_emit(const std::vector<FacetEnt>& ents, const std::vector<uint64_t>* counts, fgh_facet_entry* out,
+                   uint32_t cap, char* path_buf, uint32_t path_cap, uint32_t* n_out, uint32_t* path_bytes_out) {
+    uint32_t n = 0;
+    uint64_t bytes = 0;
+    for (size_t i = 0; i < ents.size(); i++) {
+        if (counts && (*counts)[i] == 0) continue;  // the collector reports facets of matching docs only
+        if (out) {
+            if (n >= cap || bytes + ents[i].len + 1 > path_cap)
+                return host_fail(FG_ERR_INVALID, "facet output too small (call with out == NULL for the required sizes)");
+            memcpy(path_buf + bytes, ents[i].p, ents[i].len);
+            path_buf[bytes + ents[i].len] = 0;
+            out[n] = {ents[i].ord, ents[i].depth, counts ? (*counts)[i] : 0, (uint32_t)bytes, ents[i].len};
+        }
+        n++;
+        bytes += ents[i].len + 1;
+    }
+    if (n_out) *n_out = n;
+    if (path_bytes_out) *path_bytes_out = (uint32_t)std::min<uint64_t>(bytes, 0xFFFFFFFFull);
+    return FG_OK;
+}
+
+}  // namespace
+
+extern "C" int32_t fgh_facet_children(const fgh_dataset* ds, const char* root, uint32_t max_depth,
+                                      fgh_facet_entry* out, uint32_t cap, char* path_buf, uint32_t path_cap,
+                                      uint32_t* n_out, uint32_t* path_bytes_out) {
+    if (!ds || (out && !path_buf)) return host_fail(FG_ERR_INVALID, "fgh_facet_children: NULL argument");
+    std::lock_guard<std::mutex> g(const_cast<fgh_dataset*>(ds)->mu);
+    std::vector<FacetEnt> ents;
+    if (int32_t rc = facet_enumerate(ds, root, max_depth, ents)) return rc;
+    return facet_emit(ents, nullptr, out, cap, path_buf, path_cap, n_out, path_bytes_out);
+}
+
+extern "C" int32_t fgh_facet_counts(fgh_dataset* ds, const char* root, uint32_t max_depth,
+                                    fgh_facet_entry* out, uint32_t cap, char* path_buf, uint32_t path_cap,
+                                    uint32_t* n_out, uint32_t* path_bytes_out) {
+    if (!ds || (out && !path_buf)) return host_fail(FG_ERR_INVALID, "fgh_facet_counts: NULL argument");
+    std::vector<FacetEnt> ents;
+    std::vector<std::string> keep;  // copies: the dictionary pool may grow once the lock is dropped
+    std::shared_ptr<fg_index> snap;
+    {
+        std::lock_guard<std::mutex> g(ds->mu);
+        if (int32_t rc = facet_enumerate(ds, root, max_depth, ents)) return rc;
+        snap = ds->index;
+        keep.reserve(ents.size());
+        for (auto& e : ents) { keep.emplace_back(e.p, e.len); }
+        for (size_t i = 0; i < ents.size(); i++) ents[i].p = keep[i].data();
+    }
+    if (!snap) return host_fail(ds->ctx ? FG_ERR_INVALID : FG_ERR_NO_DEVICE, "dataset has no device snapshot (commit first)");
+    if (!out) return facet_emit(ents, nullptr, nullptr, 0, nullptr, 0, n_out, path_bytes_out);  // size query: upper bounds
+    {
+        // facets first seen after the last commit are not in the snapshot's dictionary (ordinals are
+        // assigned in insertion order): they count 0 docs, like an uncommitted document in the reference
+        std::vector<FacetEnt> kept;
+        for (auto& e : ents)
+            if (fg_index_term_info(snap.get(), FGH_FIELD_FACET, e.ord, nullptr, nullptr, nullptr, nullptr) == FG_OK) kept.push_back(e);
+        ents.swap(kept);
+    }
+    // one single-leaf query per facet: its match count is the number of ALIVE docs that carry the
+    // facet or a descendant (every ancestor path of a document's facets is its own term)
+    const uint32_t n = (uint32_t)ents.size();
+    std::vector<uint64_t> counts(n, 0);
+    if (n) {
+        std::vector<fg_query> q(n);
+        std::vector<fg_clause> c(n);
+        std::vector<fg_leaf> l(n);
+        for (uint32_t i = 0; i < n; i++) {
+            q[i] = {1u, i, 1u};
+            c[i] = {FG_OCCUR_SHOULD, i, 1u};
+            l[i] = {FGH_FIELD_FACET, ents[i].ord, 1.f};
+        }
+        fg_query_batch qb;
+        memset(&qb, 0, sizeof(qb));
+        qb.n_queries = qb.n_clauses = qb.n_leaves = n;
+        qb.queries = q.data();
+        qb.clauses = c.data();
+        qb.leaves = l.data();
+        std::vector<fg_hit> hits(n);
+        std::vector<uint32_t> nh(n), cnt(n);
+        if (int32_t rc = fg_search_batch(snap.get(), &qb, 1, hits.data(), nh.data(), cnt.data())) return rc;
+        for (uint32_t i = 0; i < n; i++) counts[i] = cnt[i];
+    }
+    return facet_emit(ents, &counts, out, cap, path_buf, path_cap, n_out, path_bytes_out);
 }

@@ -6,6 +6,8 @@ include/fugu_host.h (which itself mirrors the Rust code name by name).
     ObjectRecord + facet path derivation              <->  src/object.rs:31-111, src/db/document.rs:277-312,
                                                            src/db/utils.rs:11-55
     perform_search (per_page clamp)                   <->  src/server/handlers/search.rs:350-402
+    Dataset.list_facet / get_facets / get_facets_at / get_namespace_facets / get_available_namespaces /
+    get_facet_tree / get_all_filter_paths             <->  src/db/facet.rs:33-270 (FacetCollector over AllQuery)
 
 All searching happens on the GPU through libfugu_gpu.so; this module only marshals strings.
 """
@@ -50,6 +52,7 @@ HOST_SYMBOLS = [
     "fgh_dataset_create", "fgh_dataset_destroy", "fgh_dataset_upsert", "fgh_dataset_delete", "fgh_dataset_commit",
     "fgh_dataset_adopt", "fgh_dataset_num_docs", "fgh_dataset_index", "fgh_dataset_doc_id", "fgh_dataset_term_ord",
     "fgh_tokenize", "fgh_plan", "fgh_plan_batch", "fgh_search", "fgh_search_batch",
+    "fgh_facet_children", "fgh_facet_counts",
 ]
 _bound = False
 
@@ -79,6 +82,8 @@ def _L():
         L.fgh_plan_batch.argtypes = [vp, u32, cpp, cpp, vp, vp, vp, vp, vp, u32, vp, u32, C.POINTER(u32), C.POINTER(u32), vp]
         L.fgh_search.argtypes = [vp, C.c_char_p, cpp, u32, u32, u32, vp, vp, vp]
         L.fgh_search_batch.argtypes = [vp, u32, cpp, cpp, vp, vp, vp, u32, vp, vp, vp, vp]
+        for fn in (L.fgh_facet_children, L.fgh_facet_counts):
+            fn.argtypes = [vp, C.c_char_p, u32, vp, u32, vp, u32, C.POINTER(u32), C.POINTER(u32)]
         _bound = True
     return L
 
@@ -178,6 +183,68 @@ class SearchResponse:
     page: int
     per_page: int
     query: str
+
+
+FACET_ENTRY_DT = np.dtype([("term_ord", "<u4"), ("depth", "<u4"), ("count", "<u8"), ("path_off", "<u4"), ("path_len", "<u4")])
+
+
+@dataclass
+class FacetNode:
+    """src/db/facet.rs:16-22"""
+    name: str
+    path: str
+    count: int
+    children: dict = field(default_factory=dict)  # name -> FacetNode, kept sorted by name (BTreeMap)
+
+
+@dataclass
+class FacetTreeResponse:
+    """src/db/facet.rs:25-30"""
+    tree: dict
+    max_depth: int
+    total_facets: int
+
+
+def build_facet_tree(all_facets: list[tuple[str, int]], max_depth: int | None) -> FacetTreeResponse:
+    """The host half of get_facet_tree, src/db/facet.rs:121-203, quirks included: facets whose depth
+    equals max_depth are collected (and counted in total_facets / max_depth) but not inserted, and a
+    parent's final count is its own count PLUS the totals of its children."""
+    tree: dict[str, FacetNode] = {}
+    actual_max_depth = 0
+    for path, count in all_facets:
+        if path == "/":
+            continue
+        comps = [s for s in path.split("/") if s]
+        depth = len(comps)
+        actual_max_depth = max(actual_max_depth, depth)
+        if max_depth is not None and depth >= max_depth:
+            continue
+        cur, cur_path = tree, ""
+        for i, comp in enumerate(comps):
+            cur_path += "/" + comp
+            leaf = i == len(comps) - 1
+            if comp not in cur:
+                cur[comp] = FacetNode(comp, cur_path, count if leaf else 0)
+            if leaf:
+                cur[comp].count = count
+            else:
+                cur = cur[comp].children
+
+    def update(node: FacetNode) -> int:
+        if not node.children:
+            return node.count
+        total = node.count
+        for ch in node.children.values():
+            total += update(ch)
+        node.count = total
+        return total
+
+    def sort_rec(m: dict) -> dict:
+        return {k: FacetNode(v.name, v.path, v.count, sort_rec(v.children)) for k, v in sorted(m.items())}
+
+    for n in tree.values():
+        update(n)
+    return FacetTreeResponse(sort_rec(tree), actual_max_depth, len(all_facets))
 
 
 class QuerySet:
@@ -309,6 +376,73 @@ class Dataset:
                                         qs.pages.ctypes.data, qs.pps.ctypes.data, per_page, hits.ctypes.data, nh.ctypes.data,
                                         None if cnt is None else cnt.ctypes.data, status.ctypes.data))
         return hits, nh, cnt, status
+
+    # ---- facets (src/db/facet.rs) -----------------------------------------------------------
+    def _facets(self, fn, root: str, max_depth: int) -> list[tuple[str, int, int]]:
+        n, nb = C.c_uint32(), C.c_uint32()
+        r = root.encode()
+        nat.check(fn(self.h, r, max_depth, None, 0, None, 0, C.byref(n), C.byref(nb)))  # size query
+        ents = np.zeros(max(n.value, 1), FACET_ENTRY_DT)
+        buf = C.create_string_buffer(max(nb.value, 1))
+        nat.check(fn(self.h, r, max_depth, ents.ctypes.data, len(ents), buf, len(buf), C.byref(n), C.byref(nb)))
+        raw = buf.raw
+        return [(raw[int(e["path_off"]):int(e["path_off"]) + int(e["path_len"])].decode(), int(e["count"]), int(e["depth"]))
+                for e in ents[:n.value]]
+
+    def facet_children(self, root: str = "/", max_depth: int = 1) -> list[str]:
+        """Facet dictionary entries below `root` (no device needed, no counts)."""
+        return [p for p, _, _ in self._facets(_L().fgh_facet_children, root, max_depth)]
+
+    def facet_counts(self, root: str = "/", max_depth: int = 1) -> list[tuple[str, int]]:
+        """fgh_facet_counts: (facet path, alive docs under it) below root, counted on the device."""
+        return [(p, c) for p, c, _ in self._facets(_L().fgh_facet_counts, root, max_depth)]
+
+    def list_facet(self, from_level: str) -> list[tuple[str, int]]:
+        """src/db/facet.rs:78-99: direct children of from_level with their doc counts."""
+        return self.facet_counts(from_level, 1)
+
+    def get_facets(self, namespace: str | None = None) -> list[tuple[str, int]]:
+        """src/db/facet.rs:102-106"""
+        return self.list_facet(namespace if namespace is not None else "/")
+
+    def get_facets_at(self, prefix: str) -> list[tuple[str, int]]:
+        """src/db/facet.rs:109-112"""
+        return self.list_facet(prefix)
+
+    def get_namespace_facets(self, namespace: str) -> list[tuple[str, int]]:
+        """src/db/facet.rs:35-51"""
+        return self.list_facet(f"/namespace/{namespace}")
+
+    def get_available_namespaces(self) -> list[str]:
+        """src/db/facet.rs:54-75"""
+        out = []
+        for p, _ in self.list_facet("/namespace"):
+            if p.startswith("/namespace/") and "/" not in p[len("/namespace/"):]:
+                out.append(p[len("/namespace/"):])
+        return sorted(set(out))
+
+    def get_facet_tree(self, max_depth: int | None = None) -> FacetTreeResponse:
+        """src/db/facet.rs:115-203. The reference walks the tree with one FacetCollector search per
+        node; here the whole walk is ONE device batch (one single-term count per facet)."""
+        if max_depth is not None and max_depth <= 0:
+            return build_facet_tree([], max_depth)  # collect_facets_recursive returns at once
+        return build_facet_tree(self.facet_counts("/", max_depth or 0), max_depth)
+
+    def get_all_filter_paths(self) -> dict[str, list[str]]:
+        """src/db/facet.rs:236-270: parents that have leaf children -> the leaf names."""
+        out: dict[str, list[str]] = {}
+
+        def walk(node: FacetNode):
+            if node.children:
+                leaves = [name for name, ch in node.children.items() if not ch.children]
+                if leaves:
+                    out[node.path] = leaves
+                for ch in node.children.values():
+                    walk(ch)
+
+        for n in self.get_facet_tree(None).tree.values():
+            walk(n)
+        return dict(sorted(out.items()))
 
     def close(self) -> None:
         if self.h:

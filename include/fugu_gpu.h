@@ -88,6 +88,13 @@ typedef struct {
 typedef struct fg_index fg_index;
 int32_t fg_index_upload(fg_ctx* ctx, const fg_index_desc* desc, fg_index** out);
 void fg_index_release(fg_index* index);
+/* Snapshot refresh after deletes only (DocumentOperations::upsert's delete_term + commit,
+ * src/db/document.rs:38-41,65): a new snapshot that shares every device array
+ * of `base` (postings, skip entries, fieldnorms, tf columns) and differs only in its alive bitset
+ * (NULL = all alive). Costs n_docs/8 bytes of upload. Statistics (N, df, total_num_tokens) keep
+ * counting deleted docs, as tantivy's do until a merge. `base` and the derived snapshot are released
+ * independently, in any order; the shared arrays are freed with the last of them. */
+int32_t fg_index_with_alive(fg_index* base, const uint32_t* alive_bitset, fg_index** out);
 
 typedef struct {
     uint64_t n_postings;

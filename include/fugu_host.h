@@ -48,7 +48,11 @@ void fgh_dataset_destroy(fgh_dataset* ds);
 int32_t fgh_dataset_upsert(fgh_dataset* ds, const char* id, const char* text, const char* name,
                            const char* const* facets, uint32_t n_facets);
 int32_t fgh_dataset_delete(fgh_dataset* ds, const char* id);
-/* Build the CSR of the pending state and upload a new device snapshot (swaps the fg_index). */
+/* Publish the pending state as a new device snapshot (swaps the fg_index; searches already running
+ * keep the snapshot they started on). Only deletes since the last commit: the new snapshot shares the
+ * posting arrays of the old one and uploads just the alive bitset (fg_index_with_alive, SURVEY.md 8(f)
+ * row f3). New documents: the CSR is rebuilt and uploaded whole (per-segment incremental upload is not
+ * implemented). Nothing pending: no-op. */
 int32_t fgh_dataset_commit(fgh_dataset* ds);
 
 /* Alternative to upsert+commit for large pre-built corpora: adopt a flat CSR (uploaded as is) plus
@@ -58,7 +62,8 @@ int32_t fgh_dataset_adopt(fgh_dataset* ds, const fg_index_desc* desc, const char
                           const uint64_t* terms_bytes);
 
 uint32_t fgh_dataset_num_docs(const fgh_dataset* ds);
-fg_index* fgh_dataset_index(fgh_dataset* ds); /* current snapshot (NULL before the first commit) */
+fg_index* fgh_dataset_index(fgh_dataset* ds); /* current snapshot (NULL before the first commit); owned by
+                                                 the dataset, valid until the next commit */
 /* external id of a doc (global doc id as reported in fg_hit.doc); returns length or -1 */
 int32_t fgh_dataset_doc_id(const fgh_dataset* ds, uint32_t doc, char* buf, uint32_t cap);
 /* term ordinal of a token in a field, FG_TERM_MISSING when absent */
@@ -110,6 +115,34 @@ int32_t fgh_search_batch(fgh_dataset* ds, uint32_t n, const char* const* queries
                          const uint32_t* pages /* or NULL = 0 */, const uint32_t* per_pages /* or NULL = 20 */,
                          uint32_t per_page_stride, fg_hit* out_hits, uint32_t* out_n,
                          uint32_t* out_match_count, int32_t* status);
+
+/* ---- facet counting -------------------------------------------------
+ * Mirrors `FacetCollector::for_field("facet")` + `add_facet(root)` run over `AllQuery`
+ * (src/db/facet.rs:35-103: get_namespace_facets / get_available_namespaces / list_facet) and the
+ * recursive walk of get_facet_tree (collect_facets_recursive, src/db/facet.rs:206-233).
+ * fgh_facet_counts reports every facet strictly below `root` down to `max_depth` segments (1 = the
+ * direct children, what one FacetCollector call returns; 0 = no limit) that at least one ALIVE document
+ * carries, with the number of such documents, in facet order (segments compared bytewise, a parent
+ * before its children = the pre-order of the reference's recursion). The counts are the match counts of
+ * one single-term query per facet, evaluated on the device by the search kernels (every ancestor path
+ * of a document's facets is its own term). fgh_facet_children lists the dictionary entries only
+ * (count = 0, no device needed).
+ * Paths are written NUL-terminated into path_buf; entry i's path starts at path_off. With out == NULL
+ * the calls only report upper bounds of the entries / path bytes needed in n_out / path_bytes_out.
+ * `root` must start with '/' (Facet::from panics otherwise): FG_ERR_INVALID. */
+typedef struct {
+    uint32_t term_ord; /* ordinal in the facet field's dictionary */
+    uint32_t depth;    /* segments below root (1 = direct child) */
+    uint64_t count;    /* alive documents under this facet */
+    uint32_t path_off;
+    uint32_t path_len;
+} fgh_facet_entry;
+int32_t fgh_facet_children(const fgh_dataset* ds, const char* root, uint32_t max_depth,
+                           fgh_facet_entry* out, uint32_t cap, char* path_buf, uint32_t path_cap,
+                           uint32_t* n_out, uint32_t* path_bytes_out);
+int32_t fgh_facet_counts(fgh_dataset* ds, const char* root, uint32_t max_depth,
+                         fgh_facet_entry* out, uint32_t cap, char* path_buf, uint32_t path_cap,
+                         uint32_t* n_out, uint32_t* path_bytes_out);
 
 #ifdef __cplusplus
 }

@@ -371,3 +371,81 @@ def search(ix: PyIndex, query: str, filters: list[str] | None = None, page: int 
     hits = top_k(ix, scores, limit)
     n_match = sum(1 for d in scores if ix.alive[d])
     return hits[page * per_page:page * per_page + per_page], n_match
+
+
+# ---- facet counting (src/db/facet.rs:33-233): FacetCollector over AllQuery ------------------------
+def _facet_sort_key(path: str):
+    """tantivy orders facets by their encoded form (segments joined by NUL)."""
+    return path[1:].replace("/", "\0").encode("utf-8")
+
+
+def facet_collect(ix: PyIndex, root: str) -> list[tuple[str, int]]:
+    """FacetCollector::for_field("facet") + add_facet(root), searched with AllQuery: for every ALIVE
+    doc, each direct child of `root` that one of the doc's facets equals or descends from is counted
+    once. -> [(child path, count)] in facet order, zero counts omitted."""
+    if not root.startswith("/"):
+        raise ValueError("Facet::from panics on a path without a leading '/'")
+    prefix = "/" if root == "/" else root + "/"  # "/a/" is a facet with an empty last segment: no children
+    counts: dict[str, int] = {}
+    for d in range(ix.n_docs):
+        if not ix.alive[d]:
+            continue
+        under = set()
+        for key, plist in ix.post[2].items():
+            if d in plist and key.startswith(prefix) and "/" not in key[len(prefix):]:
+                under.add(key)
+        for c in under:
+            counts[c] = counts.get(c, 0) + 1
+    return sorted(counts.items(), key=lambda t: _facet_sort_key(t[0]))
+
+
+def facet_collect_recursive(ix: PyIndex, path: str, depth: int, max_depth, out: list) -> None:
+    """collect_facets_recursive, src/db/facet.rs:206-233"""
+    if max_depth is not None and depth >= max_depth:
+        return
+    for facet, count in facet_collect(ix, path):
+        out.append((facet, count))
+        facet_collect_recursive(ix, facet, depth + 1, max_depth, out)
+
+
+def facet_tree(ix: PyIndex, max_depth=None) -> dict:
+    """get_facet_tree, src/db/facet.rs:115-203 -> {"tree": nested dicts, "max_depth", "total_facets"}."""
+    allf: list = []
+    facet_collect_recursive(ix, "/", 0, max_depth, allf)
+    tree: dict = {}
+    deepest = 0
+    for path, count in allf:
+        comps = [c for c in path.split("/") if c]
+        deepest = max(deepest, len(comps))
+        if max_depth is not None and len(comps) >= max_depth:
+            continue
+        level = tree
+        for i, c in enumerate(comps):
+            last = i == len(comps) - 1
+            node = level.setdefault(c, {"name": c, "path": "/" + "/".join(comps[:i + 1]), "count": count if last else 0, "children": {}})
+            if last:
+                node["count"] = count
+            level = node["children"]
+
+    def roll(node) -> int:
+        if node["children"]:
+            node["count"] = node["count"] + sum(roll(ch) for ch in node["children"].values())
+        return node["count"]
+
+    for n in tree.values():
+        roll(n)
+    return {"tree": tree, "max_depth": deepest, "total_facets": len(allf)}
+
+
+def facet_filter_paths(tree: dict) -> dict:
+    """get_all_filter_paths, src/db/facet.rs:236-270: every node that has leaf children -> their names."""
+    out: dict = {}
+    stack = list(tree.values())
+    while stack:
+        n = stack.pop()
+        kids = n["children"]
+        names = sorted(k for k in kids if not kids[k]["children"])
+        if names:
+            out[n["path"]] = names
+        stack.extend(kids.values())
+    return out
