@@ -31,6 +31,7 @@ FG_TERM_ALL = 0xFFFFFFFE
 FG_EXEC_EXACT_ACCOUNTING = 1
 FG_EXEC_DETERMINISTIC = 2
 FG_EXEC_COUNTERS = 4
+FG_EXEC_NO_PRUNE = 8
 FG_PREP_NO_COLUMNS = 1
 
 
@@ -103,6 +104,8 @@ class BatchStats(C.Structure):
         ("sum_k", C.c_uint64),
         ("search_kernel_ms", C.c_float),
         ("merge_kernel_ms", C.c_float),
+        ("colscan_chunks", C.c_uint64),
+        ("colscan_chunks_skipped", C.c_uint64),
     ]
 
 

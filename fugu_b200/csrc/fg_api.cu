@@ -1042,6 +1042,7 @@ extern "C" int32_t fg_batch_execute(fg_batch* b, uint32_t flags, uint32_t k_stri
     p.want_counts = d_match_count ? 1 : 0;
     p.acct = (flags & (FG_EXEC_EXACT_ACCOUNTING | FG_EXEC_COUNTERS)) ? 1 : 0;
     p.qtheta = (flags & FG_EXEC_DETERMINISTIC) ? nullptr : b->d_qtheta;
+    p.no_prune = ((flags & FG_EXEC_NO_PRUNE) || getenv("FG_NO_PRUNE")) ? 1 : 0;
     p.prof = getenv("FG_PROF") ? b->d_stats + 8 : nullptr;
     CU(cudaEventRecord(b->ev[0], st));
     {
@@ -1084,7 +1085,7 @@ extern "C" int32_t fg_batch_get_stats(fg_batch* b, fg_batch_stats* out) {
     if (!b || !out) return fail(FG_ERR_INVALID, "NULL argument");
     fg_ctx* ctx = b->ix->ctx;
     CU(cudaSetDevice(ctx->device));
-    unsigned long long h[4];
+    unsigned long long h[5];
     {
         std::lock_guard<std::mutex> g(ctx->mu);
         CU(cudaStreamSynchronize(ctx->stream));
@@ -1100,6 +1101,8 @@ extern "C" int32_t fg_batch_get_stats(fg_batch* b, fg_batch_stats* out) {
     out->bytes_blocks = h[0];
     out->bytes_redecode = h[1];
     out->scored_postings = h[2];
+    out->colscan_chunks = h[3];
+    out->colscan_chunks_skipped = h[4];
     out->n_work_items = b->n_items;
     out->n_launches = b->n_launches;
     out->n_queries = b->n_queries;

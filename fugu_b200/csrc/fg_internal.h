@@ -106,7 +106,7 @@ struct SearchParams {
     uint32_t kcap;               // entries per partial list
     uint64_t* partial;           // [n_items][kcap] sortable keys, 0 = empty
     uint32_t* partial_count;     // [n_items] matching docs
-    unsigned long long* stats;   // [4]: bytes_blocks, bytes_redecode, scored, -
+    unsigned long long* stats;   // [5]: bytes_blocks, bytes_redecode, scored, column-scan chunks seen, ... skipped
     uint32_t* match_bitmap;      // optional
     uint32_t bitmap_words;
     uint32_t exact_filter;
@@ -115,6 +115,7 @@ struct SearchParams {
     uint32_t acct;              // maintain the byte / scored-posting counters
     unsigned long long* prof;   // optional [8] cycle counters (dev tool)
     uint32_t* qtheta;           // [n_queries] sortable f32: score every work item may prune below (0 = none)
+    uint32_t no_prune;          // column scan: visit every chunk even when no doc of it can reach the top-k (A/B switch)
 };
 
 struct MergeParams {

@@ -25,6 +25,20 @@
 
 #include "fg_internal.h"
 
+// The same source also builds, with g++, against tests/emu/cuda_runtime.h (a SIMT emulation used only
+// by the CPU test-suite to check the kernels' logic where there is no GPU; FG_EMULATE is defined by
+// that header and by nothing in the product build). The few constructs g++ cannot take are spelled
+// through these macros; every inline-PTX statement has a plain-C++ twin under FG_EMULATE.
+#ifdef FG_EMULATE
+#define FG_MAGIC_2P23(m) m = 0x4B000000u
+#define FG_DYN_SMEM(name) unsigned char* name = fgemu::dyn_smem()
+#define FG_LAUNCH(kernel, grid, block, smem, stream, ...) fgemu::launch((grid), (block), (smem), [&]() { kernel(__VA_ARGS__); })
+#else
+#define FG_MAGIC_2P23(m) asm volatile("mov.u32 %0, 0x4B000000;" : "=r"(m))  /* opaque to constant folding: PRMT keeps a register operand */
+#define FG_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#define FG_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#endif
+
 namespace fg {
 
 namespace {
@@ -49,7 +63,11 @@ __device__ __forceinline__ uint64_t make_key(float score, uint32_t doc) {
 // (two compares + four scalings per call); here tf + norm >= 0.3. Error <= 2 ulp, inside the 1e-5 bar.
 __device__ __forceinline__ float tf_factor(float t, float n) {
     float r;
+#ifdef FG_EMULATE
+    r = 1.0f / (t + n);
+#else
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t + n));
+#endif
     return t * r;
 }
 
@@ -247,7 +265,11 @@ __device__ __forceinline__ float byte_f32(uint32_t w, int j) {
 template <int J>
 __device__ __forceinline__ float byte_f32_r(uint32_t w, uint32_t magic) {
     uint32_t r;
+#ifdef FG_EMULATE
+    r = __byte_perm(w, magic, 0x7650u | (uint32_t)J);
+#else
     asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(w), "r"(magic), "n"(0x7650 | J));
+#endif
     return __uint_as_float(r) - 8388608.0f;
 }
 __device__ __forceinline__ void col_term8(uint2 t, float w, uint32_t magic, const float n[8], float v[8]) {
@@ -980,7 +1002,7 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
                     // bytes arrive as one 64-bit load each (windows start 16-aligned), the norms come
                     // from the 1 KB table in shared memory, a term costs PRMT, 2 FADD, MUFU.RCP, FMUL, FFMA.
                     uint32_t magic;
-                    asm volatile("mov.u32 %0, 0x4B000000;" : "=r"(magic));
+                    FG_MAGIC_2P23(magic);
                     const int n8 = (int)((rhi - rlo + 7) >> 3);
                     const DevLeaf* CL = &S.leaf[nl];
                     const uint8_t* fnb = p.ix.fnorm[S.col_field] + rlo;
@@ -1214,7 +1236,7 @@ __device__ __forceinline__ void run_item(const SearchParams& p, const DevItem& i
 
 template <int KS, int GRP, int MINB, bool DENSE, bool PURE>
 __global__ void __launch_bounds__(NT, MINB) search_kernel(const SearchParams p) {
-    extern __shared__ __align__(16) unsigned char smem[];
+    FG_DYN_SMEM(smem);
     __shared__ Shared S;
     // [0, 32K)   dense: acc[DW]            | hash: acc[HS] + keys[HS]
     // masked plans only (pure unions need neither masks nor candidate bitmaps):
@@ -1260,14 +1282,24 @@ struct CShared {
     uint32_t theta_cta;
     uint32_t match;
     unsigned long long st_blocks, st_redecode, st_scored;
+    uint32_t st_chunks, st_skipped;  // counters mode only
+    uint32_t nhit[3];    // first-touch count of the hit list of window w (list w % 3), see CHIT
+    uint32_t wtheta[2];  // sortable f32: the query's threshold as published before round r (slot r & 1)
 };
+// Hit lists: while a window's streamed postings are added to its accumulators, the slot of every doc
+// touched for the first time is appended to the window's list (three lists in rotation: filled in round
+// w-1, read in round w, reset in round w+1). A window whose list did not overflow and whose docs
+// without a streamed posting can no longer reach the top-k is evaluated from the list alone.
+constexpr int CHIT = 512;
+constexpr int colscan_smem_bytes(int ks) { return 2 * CW * 4 + NW * ks * 32 * 8 + 3 * CHIT * 2; }
 
 template <int KS, int MINB>
 __global__ void __launch_bounds__(NT, MINB) colscan_kernel(const SearchParams p) {
-    extern __shared__ __align__(16) unsigned char smem[];
+    FG_DYN_SMEM(smem);
     __shared__ CShared S;
     float* acc = reinterpret_cast<float*>(smem);                       // [2][CW]
     uint64_t* scratch = reinterpret_cast<uint64_t*>(smem + 2 * CW * 4);  // [NW][KS][32]
+    uint16_t* hitlist = reinterpret_cast<uint16_t*>(smem + 2 * CW * 4 + NW * KS * 32 * 8);  // [3][CHIT]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const DevItem it = p.items[p.item_begin + blockIdx.x];
     {
@@ -1277,6 +1309,9 @@ __global__ void __launch_bounds__(NT, MINB) colscan_kernel(const SearchParams p)
             S.chunk[0] = 0; S.chunk[1] = 0; S.match = 0;
             S.theta_cta = p.qtheta ? __ldcg(p.qtheta + it.query) : 0u;
             S.st_blocks = 0; S.st_redecode = 0; S.st_scored = 0;
+            S.st_chunks = 0; S.st_skipped = 0;
+            S.nhit[0] = 0; S.nhit[1] = 0; S.nhit[2] = 0;
+            S.wtheta[0] = S.theta_cta; S.wtheta[1] = 0;
         }
         if (tid < q0.n_leaves + q0.n_col) S.leaf[tid] = p.leaves[q0.leaf_begin + tid];
     }
@@ -1318,14 +1353,26 @@ __global__ void __launch_bounds__(NT, MINB) colscan_kernel(const SearchParams p)
     }
     uint32_t my_matches = 0, my_scored = 0;
     unsigned long long my_blocks = 0, my_redecode = 0;
-    auto stream_leaf = [&](uint32_t wlo, uint32_t whi, float* buf) {
+    // (see "sparse-hit gating" below) every doc has to be visited when the caller wants match counts or
+    // the matched doc-id set
+    const bool may_prune = nl && !p.no_prune && p.want_counts == 0 && p.match_bitmap == nullptr;
+    const bool track = may_prune;
+    auto stream_leaf = [&](uint32_t wlo, uint32_t whi, float* buf, uint32_t li) {
         const DevLeaf& L = S.leaf[my_leaf];
         while (true) {
             bool left = false;
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 if (cd[j] < whi) {
-                    if (cd[j] >= wlo) { smem_add_f32(&buf[cd[j] - wlo], cv[j]); my_scored++; }
+                    if (cd[j] >= wlo) {
+                        const uint32_t slot = cd[j] - wlo;
+                        const float before = atomicAdd(&buf[slot], cv[j]);
+                        my_scored++;
+                        if (track && before == 0.f) {  // first posting of this doc in the window
+                            const uint32_t hi = atomicAdd(&S.nhit[li], 1u);
+                            if (hi < (uint32_t)CHIT) hitlist[li * CHIT + hi] = (uint16_t)slot;
+                        }
+                    }
                     cd[j] = EMPTY;
                 }
                 left = left || cd[j] != EMPTY;
@@ -1363,21 +1410,21 @@ __global__ void __launch_bounds__(NT, MINB) colscan_kernel(const SearchParams p)
             if (p.acct && lane == 0) my_blocks += ((n * bd + 7) >> 3) + ((n * bt + 7) >> 3) + 16;
         }
     };
-    auto stream_window = [&](uint32_t wlo, uint32_t whi, float* buf) {
+    auto stream_window = [&](uint32_t wlo, uint32_t whi, float* buf, uint32_t li) {
         if (p.deterministic) {  // bit-reproducible sums: one leaf at a time, in leaf order
             for (int l = 0; l < nl; l++) {
-                if (warp == l) stream_leaf(wlo, whi, buf);
+                if (warp == l) stream_leaf(wlo, whi, buf, li);
                 __syncthreads();
             }
         } else if (streams) {
-            stream_leaf(wlo, whi, buf);
+            stream_leaf(wlo, whi, buf, li);
         }
     };
     // without streamed leaves nothing lives in the accumulators: one window covers the whole range
     const uint32_t step = nl ? (uint32_t)CW : (end - lo0 + 16u);
     __syncthreads();
     if (nl) {
-        stream_window(lo0, (uint32_t)min((unsigned long long)lo0 + step, (unsigned long long)end), acc);
+        stream_window(lo0, (uint32_t)min((unsigned long long)lo0 + step, (unsigned long long)end), acc, 0u);
         __syncthreads();
     }
 
@@ -1386,17 +1433,74 @@ __global__ void __launch_bounds__(NT, MINB) colscan_kernel(const SearchParams p)
     float theta_s = -INFINITY;
     uint32_t seen_t = 0;
     uint32_t magic;
-    asm volatile("mov.u32 %0, 0x4B000000;" : "=r"(magic));
+    FG_MAGIC_2P23(magic);
     const bool count = p.want_counts != 0;
     const uint8_t* fnb = p.ix.fnorm[cf];
     const uint8_t* alive8 = reinterpret_cast<const uint8_t*>(p.ix.alive);
+    // Sparse-hit gating (MaxScore on the columns): tf/(tf+norm) < 1, so a doc that no streamed leaf
+    // touched scores below the sum of the column weights. Once the k-th best score known for the query
+    // (theta_s: this warp's queue, the CTA's and the other work items' through qtheta) exceeds that
+    // bound, only docs with a streamed posting can still enter the top-k, and a 256-doc chunk whose
+    // accumulators are all zero is skipped before its fieldnorm / column bytes are even loaded. Exactly
+    // the docs the `score >= theta_s` pre-test below would reject anyway: results do not change.
+    // Off when the caller wants match counts or the matched doc-id set (every doc must be visited).
+    // Two grains: a whole window is evaluated from its hit list (the docs streamed postings touched)
+    // when the gate already held before the round and the list did not overflow; otherwise the window
+    // is scanned and single 256-doc chunks without a hit are skipped.
+    float col_bound = q.const_score;
+    for (int c = 0; c < ncol; c++) col_bound += CL[c].weight * 1.000001f;  // rcp.approx: 1 ulp above 1 at most
 
     for (uint32_t wlo = lo0, r = 0; wlo < end; wlo += step, r++) {
         const uint32_t whi = (uint32_t)min((unsigned long long)wlo + step, (unsigned long long)end);
         float* buf = acc + (r & 1) * CW;
         if (nl && whi < end)
-            stream_window(whi, (uint32_t)min((unsigned long long)whi + step, (unsigned long long)end), acc + ((r + 1) & 1) * CW);
+            stream_window(whi, (uint32_t)min((unsigned long long)whi + step, (unsigned long long)end), acc + ((r + 1) & 1) * CW, (r + 1) % 3u);
         const uint32_t n8 = (whi - wlo + 7) >> 3;
+        // publishes the item's and the query's threshold; returns after a candidate entered this warp's queue
+        auto publish_theta = [&]() {
+            const float mine = tk.theta ? unsortable((uint32_t)(tk.theta >> 32)) : -INFINITY;
+            if (mine > theta_s) {
+                theta_s = mine;
+                if (lane == 0) {
+                    atomicMax(&S.theta_cta, sortable(mine));
+                    if (p.qtheta) atomicMax(p.qtheta + it.query, sortable(mine));
+                }
+            } else if (p.qtheta) {  // pick up what the other work items of the query have reached
+                const uint32_t gq = __ldcg(p.qtheta + it.query);
+                if (gq > seen_t) { if (lane == 0) atomicMax(&S.theta_cta, gq); theta_s = fmaxf(theta_s, unsortable(gq)); }
+            }
+        };
+        bool from_list = false;
+        if (may_prune) {
+            // the same for every thread of the CTA: the snapshot was written before the last barrier and the
+            // list of this window is complete
+            const uint32_t wt = S.wtheta[r & 1], nh = S.nhit[r % 3u];
+            if (wt) theta_s = fmaxf(theta_s, unsortable(wt));
+            from_list = wt != 0u && col_bound < unsortable(wt) && nh <= (uint32_t)CHIT;
+            if (from_list) {
+                const uint16_t* hl = hitlist + (r % 3u) * CHIT;
+                for (uint32_t base = (uint32_t)warp * 32u; base < nh; base += (uint32_t)NT) {
+                    const bool valid = base + lane < nh;
+                    const uint32_t slot = valid ? hl[base + lane] : 0u;
+                    const uint32_t d = wlo + slot;
+                    float v = 0.f;
+                    if (valid) {
+                        v = buf[slot];
+                        buf[slot] = 0.f;
+                        const float nrm = S.ctab[__ldg(fnb + d)];
+                        for (int c = 0; c < ncol; c++) v += CL[c].weight * tf_factor((float)__ldg(CL[c].col + d), nrm);
+                        if (alive8 && !((__ldg(alive8 + (d >> 3)) >> (d & 7u)) & 1u)) v = 0.f;
+                    }
+                    const float sc = v + q.const_score;
+                    const bool c = valid && v > 0.f && sc >= theta_s;
+                    if (__any_sync(FULL, c)) {
+                        tk.offer(c, c ? make_key(sc, d) : 0ull, k, lane);
+                        publish_theta();
+                    }
+                }
+                if (p.acct && tid == 0) { S.st_chunks += (n8 + 31) >> 5; S.st_skipped += (n8 + 31) >> 5; }
+            }
+        }
         // The scan loop is instantiated per (number of column leaves: 1, 2, any) x (streamed leaves yes/no):
         // column pointers and weights live in registers, no loop over columns, no accumulator traffic for
         // plans without streamed leaves. Lanes past the end of the last window are clamped, not branched.
@@ -1412,27 +1516,53 @@ __global__ void __launch_bounds__(NT, MINB) colscan_kernel(const SearchParams p)
             const bool slow = count || alive8 != nullptr || p.match_bitmap != nullptr;
             while (true) {
                 uint32_t c0 = 0;
-                if (lane == 0) asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(c0) : "r"(chunk_addr) : "memory");
-                c0 = __shfl_sync(FULL, c0, 0) * 32u;
+                if (lane == 0) {
+#ifdef FG_EMULATE
+                    c0 = atomicAdd(&S.chunk[r & 1], 1u);
+#else
+                    asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(c0) : "r"(chunk_addr) : "memory");
+#endif
+                    // lane 0 decides for the warp whether this chunk may be gated (its theta_s; the lanes'
+                    // copies can differ for a moment while another warp raises S.theta_cta) and sends the
+                    // decision along with the chunk number
+                    if (ACC && may_prune && col_bound < theta_s) c0 |= 0x80000000u;
+                }
+                c0 = __shfl_sync(FULL, c0, 0);
+                const bool gate = ACC && (c0 >> 31) != 0u;
+                c0 = (c0 & 0x7FFFFFFFu) * 32u;
                 if (c0 >= n8) break;
                 const bool active = c0 + lane < n8;
                 const uint32_t g = active ? c0 + lane : n8 - 1;
                 const uint32_t o8 = 8u * g;
-                const uint2 fn8 = __ldg(reinterpret_cast<const uint2*>(fnw + o8));
-                const uint2 ta = __ldg(reinterpret_cast<const uint2*>(cp0 + o8));
-                uint2 tb = make_uint2(0u, 0u);
-                if (NC != 1) tb = __ldg(reinterpret_cast<const uint2*>(cp1 + o8));
                 {   // threshold reached by any warp of the CTA
                     const uint32_t tc = S.theta_cta;
                     if (tc != seen_t) { seen_t = tc; theta_s = fmaxf(theta_s, unsortable(tc)); }
                 }
+                float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+                float4* b4 = reinterpret_cast<float4*>(buf) + 2 * g;
+                if (ACC) {
+                    a0 = b4[0];
+                    a1 = b4[1];
+                    if (p.acct && lane == 0) atomicAdd(&S.st_chunks, 1u);
+                    if (gate) {
+                        const float am = fmaxf(fmaxf(fmaxf(a0.x, a0.y), fmaxf(a0.z, a0.w)), fmaxf(fmaxf(a1.x, a1.y), fmaxf(a1.z, a1.w)));
+                        if (!__any_sync(FULL, active && am > 0.f)) {  // no streamed posting in these 256 docs (slots are already zero)
+                            if (p.acct && lane == 0) atomicAdd(&S.st_skipped, 1u);
+                            continue;
+                        }
+                    }
+                }
+                const uint2 fn8 = __ldg(reinterpret_cast<const uint2*>(fnw + o8));
+                const uint2 ta = __ldg(reinterpret_cast<const uint2*>(cp0 + o8));
+                uint2 tb = make_uint2(0u, 0u);
+                if (NC != 1) tb = __ldg(reinterpret_cast<const uint2*>(cp1 + o8));
                 float v[8];
                 float accmax = 0.f;
                 if (ACC) {
-                    float4* b4 = reinterpret_cast<float4*>(buf) + 2 * g;
-                    const float4 a0 = b4[0], a1 = b4[1];
-                    b4[0] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    b4[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (active) {  // a clamped lane reads the last group's slots too, but only their owner may clear them
+                        b4[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        b4[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
                     v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w;
                     v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
                     if (slow) accmax = fmaxf(fmaxf(fmaxf(a0.x, a0.y), fmaxf(a0.z, a0.w)), fmaxf(fmaxf(a1.x, a1.y), fmaxf(a1.z, a1.w)));
@@ -1498,24 +1628,16 @@ __global__ void __launch_bounds__(NT, MINB) colscan_kernel(const SearchParams p)
                         if (!__any_sync(FULL, c)) continue;
                         tk.offer(c, c ? make_key(sc, wlo + o8 + j) : 0ull, k, lane);
                     }
-                    const float mine = tk.theta ? unsortable((uint32_t)(tk.theta >> 32)) : -INFINITY;
-                    if (mine > theta_s) {
-                        theta_s = mine;
-                        if (lane == 0) {
-                            atomicMax(&S.theta_cta, sortable(mine));
-                            if (p.qtheta) atomicMax(p.qtheta + it.query, sortable(mine));
-                        }
-                    } else if (p.qtheta) {  // pick up what the other work items of the query have reached
-                        const uint32_t gq = __ldcg(p.qtheta + it.query);
-                        if (gq > seen_t) { if (lane == 0) atomicMax(&S.theta_cta, gq); theta_s = fmaxf(theta_s, unsortable(gq)); }
-                    }
+                    publish_theta();
                 }
             }
         };
         using I0 = std::integral_constant<int, 0>;
         using I1 = std::integral_constant<int, 1>;
         using I2 = std::integral_constant<int, 2>;
-        if (nl) {
+        if (from_list) {
+            // done above
+        } else if (nl) {
             if (ncol == 1) chunk_loop(I1{}, std::true_type{});
             else if (ncol == 2) chunk_loop(I2{}, std::true_type{});
             else chunk_loop(I0{}, std::true_type{});
@@ -1524,7 +1646,15 @@ __global__ void __launch_bounds__(NT, MINB) colscan_kernel(const SearchParams p)
             else if (ncol == 2) chunk_loop(I2{}, std::false_type{});
             else chunk_loop(I0{}, std::false_type{});
         }
-        if (tid == 0) S.chunk[(r + 1) & 1] = 0;
+        if (tid == 0) {
+            S.chunk[(r + 1) & 1] = 0;
+            if (may_prune) {
+                S.nhit[(r + 2) % 3u] = 0;  // the list window r+2 will fill in the next round (last read in round r-1)
+                uint32_t t = S.theta_cta;
+                if (p.qtheta) t = max(t, __ldcg(p.qtheta + it.query));
+                S.wtheta[(r + 1) & 1] = t;  // what round r+1 may rely on
+            }
+        }
         __syncthreads();
     }
 
@@ -1561,6 +1691,8 @@ __global__ void __launch_bounds__(NT, MINB) colscan_kernel(const SearchParams p)
                 atomicAdd(p.stats + 0, S.st_blocks);
                 atomicAdd(p.stats + 1, S.st_redecode);
                 atomicAdd(p.stats + 2, S.st_scored);
+                atomicAdd(p.stats + 3, (unsigned long long)S.st_chunks);   // chunks of windowed plans reached ...
+                atomicAdd(p.stats + 4, (unsigned long long)S.st_skipped);  // ... and skipped by the sparse-hit gate
             }
         }
     }
@@ -1688,7 +1820,8 @@ static void launch_one(SearchParams p, uint32_t begin, uint32_t count, cudaStrea
         configured = true;
     }
     p.item_begin = begin;
-    search_kernel<KS, GRP, MINB, DENSE, PURE><<<count, NT, smem, st>>>(p);
+    auto kernel = search_kernel<KS, GRP, MINB, DENSE, PURE>;
+    FG_LAUNCH(kernel, count, NT, smem, st, p);
 }
 
 #ifndef COLSCAN_MINB
@@ -1698,13 +1831,14 @@ template <int KS, int MINB>
 static void launch_colscan(SearchParams p, uint32_t begin, uint32_t count, cudaStream_t st) {
     if (!count) return;
     static bool configured = false;
-    const int smem = 2 * CW * 4 + NW * KS * 32 * 8;
+    const int smem = colscan_smem_bytes(KS);
     if (!configured) {
         cudaFuncSetAttribute(colscan_kernel<KS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         configured = true;
     }
     p.item_begin = begin;
-    colscan_kernel<KS, MINB><<<count, NT, smem, st>>>(p);
+    auto kernel = colscan_kernel<KS, MINB>;
+    FG_LAUNCH(kernel, count, NT, smem, st, p);
 }
 
 // items are grouped by kernel class: [dense pure | dense masked | hash pure | hash masked | column scan]
@@ -1736,9 +1870,9 @@ void launch_merge(const MergeParams& p, int ks, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (p.n_queries == 0) return;
     const unsigned grid = (p.n_queries + 3) / 4;
-    if (ks <= 1) merge_kernel<1><<<grid, 128, 0, st>>>(p);
-    else if (ks <= 4) merge_kernel<4><<<grid, 128, 0, st>>>(p);
-    else merge_kernel<32><<<grid, 128, 0, st>>>(p);
+    if (ks <= 1) FG_LAUNCH(merge_kernel<1>, grid, 128, 0, st, p);
+    else if (ks <= 4) FG_LAUNCH(merge_kernel<4>, grid, 128, 0, st, p);
+    else FG_LAUNCH(merge_kernel<32>, grid, 128, 0, st, p);
 }
 
 void launch_merge_gathered(const void* hits, const uint32_t* n, uint32_t n_ranks, uint32_t n_queries,
@@ -1748,14 +1882,14 @@ void launch_merge_gathered(const void* hits, const uint32_t* n, uint32_t n_ranks
     if (n_queries == 0) return;
     const unsigned grid = (n_queries + 3) / 4;
     if (ks <= 1)
-        merge_gathered_kernel<1><<<grid, 128, 0, st>>>((const uint2*)hits, n, n_ranks, n_queries, k,
-                                                       k_stride, (uint2*)out_hits, out_n);
+        FG_LAUNCH(merge_gathered_kernel<1>, grid, 128, 0, st, (const uint2*)hits, n, n_ranks, n_queries, k, k_stride,
+                  (uint2*)out_hits, out_n);
     else if (ks <= 4)
-        merge_gathered_kernel<4><<<grid, 128, 0, st>>>((const uint2*)hits, n, n_ranks, n_queries, k,
-                                                       k_stride, (uint2*)out_hits, out_n);
+        FG_LAUNCH(merge_gathered_kernel<4>, grid, 128, 0, st, (const uint2*)hits, n, n_ranks, n_queries, k, k_stride,
+                  (uint2*)out_hits, out_n);
     else
-        merge_gathered_kernel<32><<<grid, 128, 0, st>>>((const uint2*)hits, n, n_ranks, n_queries, k,
-                                                        k_stride, (uint2*)out_hits, out_n);
+        FG_LAUNCH(merge_gathered_kernel<32>, grid, 128, 0, st, (const uint2*)hits, n, n_ranks, n_queries, k, k_stride,
+                  (uint2*)out_hits, out_n);
 }
 
 }  // namespace fg

@@ -178,6 +178,9 @@ int32_t fg_batch_prepare_ex(fg_index* index, const fg_query_batch* batch, uint32
 void fg_batch_release(fg_batch* b);
 #define FG_EXEC_EXACT_ACCOUNTING 1u /* exact block-need test for the algorithmic-byte counters (slow) */
 #define FG_EXEC_COUNTERS 4u         /* maintain bytes_blocks / bytes_redecode / scored_postings (cheap) */
+#define FG_EXEC_NO_PRUNE 8u         /* column scan: visit every 256-doc chunk even when the query's k-th best score
+                                       already exceeds what a doc without a sparse-term posting can reach (A/B switch;
+                                       results are identical either way) */
 #define FG_EXEC_DETERMINISTIC 2u    /* apply leaves one at a time: bit-reproducible f32 sums (slower);
                                        default sums the leaves of a clause with float atomics, which can
                                        differ in the last bit for docs with >= 3 contributions */
@@ -207,6 +210,8 @@ typedef struct {
     uint64_t sum_k;           /* sum of k over queries (8 B result per hit) */
     float search_kernel_ms;   /* CUDA-event time of the search kernel of the last execute */
     float merge_kernel_ms;    /* ... and of the per-query merge kernel */
+    uint64_t colscan_chunks;         /* with FG_EXEC_COUNTERS: 256-doc chunks of windowed column-scan plans reached */
+    uint64_t colscan_chunks_skipped; /* ... of which skipped because no doc in them could enter the top-k */
 } fg_batch_stats;
 /* synchronises the stream and reads the device counters of the last fg_batch_execute */
 int32_t fg_batch_get_stats(fg_batch* b, fg_batch_stats* out);

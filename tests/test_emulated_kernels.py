@@ -1,0 +1,66 @@
+"""CPU: the product's kernel sources (fugu_b200/csrc/fg_kernels.cu + fg_api.cu + fg_host.cpp) compiled by
+g++ against the SIMT emulation in tests/emu and driven through the same C ABI by the SAME test
+functions the `-m gpu` suite runs on a B200 — so the kernels' logic (every plan shape, item boundary,
+delete / shard / merge path) is checked against the oracle on a box without a GPU, on every commit.
+
+This is test infrastructure: tests/emu/libfugu_emu.so is never loaded by the product or by bench.py,
+nothing it computes is reported anywhere, and it says nothing about performance. The emulation runs
+the threads of a CTA as fibers that switch only at warp collectives and barriers, i.e. a legal but
+very un-GPU-like interleaving — which is how it found a clamped lane clearing an accumulator slot its
+owner had not read yet (harmless in lock step, a data race by the letter of the memory model).
+The `-m gpu` run on hardware remains the parity gate; this suite is its early warning.
+"""
+import os
+import subprocess
+
+import pytest
+
+from fugu_b200 import _native as nat
+from fugu_b200 import dataset as dsm
+from tests import util
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMU_DIR = os.path.join(ROOT, "tests", "emu")
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    subprocess.check_call(["make", "-s", "-j4", "-C", EMU_DIR])
+    saved = (nat.LIB_PATH, nat._lib, dsm._bound, util.EMULATED)
+    nat.LIB_PATH, nat._lib, dsm._bound, util.EMULATED = os.path.join(EMU_DIR, "libfugu_emu.so"), None, False, True
+    c = nat.Context(0)
+    try:
+        yield c
+    finally:
+        c.close()
+        nat.LIB_PATH, nat._lib, dsm._bound, util.EMULATED = saved
+
+
+def _gpu_tests():
+    import tests.test_facets as tf
+    import tests.test_gpu_parity as gp
+
+    out = []
+    for mod in (gp, tf):
+        for name in sorted(dir(mod)):
+            fn = getattr(mod, name)
+            if not name.startswith("test_") or not callable(fn):
+                continue
+            marks = [m.name for m in getattr(fn, "pytestmark", [])] + [m.name for m in ([mod.pytestmark] if hasattr(mod, "pytestmark") else [])]
+            if "gpu" in marks:
+                out.append(pytest.param(fn, id=f"{mod.__name__.split('.')[-1]}::{name}"))
+    return out
+
+
+# scaled-down corpora for the tests whose GPU sizes would take minutes under emulation
+SCALE = {"n_docs": 0.25}
+
+
+@pytest.mark.parametrize("fn", _gpu_tests())
+def test_gpu_suite_under_emulation(ctx, fn, monkeypatch):
+    import inspect
+
+    kwargs = {}
+    if "monkeypatch" in inspect.signature(fn).parameters:
+        kwargs["monkeypatch"] = monkeypatch
+    fn(ctx, **kwargs)

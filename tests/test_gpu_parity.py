@@ -120,9 +120,8 @@ def test_upsert_delete_snapshot_semantics(ctx):
 def test_sharded_search_and_device_merge(ctx):
     """Doc-id-range shards with global statistics + fg_merge_topk_device == single index (the
     multi-GPU data path of SURVEY.md 8(e), emulated on one device as two shard snapshots)."""
-    import torch
     from oracle import orc
-    from tests.util import check_topk, gpu_search_device
+    from tests.util import DevBuf, check_topk, gpu_search_device
 
     cfg = synth.Config(cfg=2, n_docs=40_000, vocab=8_000, n_queries=200, k=10, name_pct=10)
     corpus = synth.Corpus.for_config(cfg)
@@ -149,19 +148,16 @@ def test_sharded_search_and_device_merge(ctx):
         g_hits[r], g_n[r] = h, n
         counts += c
         index.close()
-    dev = torch.device("cuda:0")
-    d_g = torch.from_numpy(g_hits.view(np.int32).reshape(R, nq, k, 2).copy()).to(dev)
-    d_gn = torch.from_numpy(g_n.view(np.int32)).to(dev)
-    d_out = torch.zeros((nq, k, 2), dtype=torch.int32, device=dev)
-    d_on = torch.zeros(nq, dtype=torch.int32, device=dev)
-    torch.cuda.synchronize()
-    nat.merge_topk_device(ctx, d_g.data_ptr(), d_gn.data_ptr(), R, nq, k, k, d_out.data_ptr(), d_on.data_ptr())
+    d_g = DevBuf(None, g_hits.view(np.int32).reshape(R, nq, k, 2))
+    d_gn = DevBuf(None, g_n.view(np.int32))
+    d_out, d_on = DevBuf((nq, k, 2)), DevBuf(nq)
+    nat.merge_topk_device(ctx, d_g.ptr, d_gn.ptr, R, nq, k, k, d_out.ptr, d_on.ptr)
     ctx.synchronize()
-    raw = d_out.cpu().numpy().view(np.uint32)
+    raw = d_out.numpy().view(np.uint32)
     got = np.zeros((nq, k), nat.HIT_DT)
     got["score"] = raw[..., 0].view(np.float32)
     got["doc"] = raw[..., 1]
-    on = d_on.cpu().numpy()
+    on = d_on.numpy()
     assert counts.tolist() == o_c.astype(np.int64).tolist()
     assert on.tolist() == o_n.tolist()
     for q in range(nq):

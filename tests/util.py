@@ -36,35 +36,52 @@ def check_topk(g: np.ndarray, o: np.ndarray, k: int, tol: float = REL_TOL, ctx: 
         i = j + 1
 
 
+EMULATED = False  # set by tests/test_emulated_kernels.py while the library under test is tests/emu/libfugu_emu.so
+
+
+class DevBuf:
+    """A zeroed (or copied) int32 buffer in the memory the library's kernels run on: a torch CUDA
+    tensor — or host memory while the kernel sources run under the SIMT emulation of tests/emu."""
+
+    def __init__(self, shape, src: np.ndarray | None = None):
+        if EMULATED:
+            self.a = np.zeros(shape, np.int32) if src is None else np.ascontiguousarray(src, dtype=np.int32).copy()
+            self.ptr = self.a.ctypes.data
+        else:
+            import torch
+
+            dev = torch.device("cuda:0")
+            self.t = torch.zeros(shape, dtype=torch.int32, device=dev) if src is None else \
+                torch.from_numpy(np.ascontiguousarray(src, dtype=np.int32).copy()).to(dev)
+            self.ptr = self.t.data_ptr()
+            torch.cuda.synchronize()
+
+    def numpy(self) -> np.ndarray:
+        return self.a.copy() if EMULATED else self.t.cpu().numpy()
+
+
 def gpu_search_device(index: nat.Index, batch: nat.HostBatch, want_bitmap: bool = False, flags: int = 0,
                       prep_flags: int = 0):
     """Split-phase path with device buffers provided by torch; returns numpy results (+ stats).
     The byte counters are defined on the block path: accounting runs lower the plan without columns."""
-    import torch
-
     if flags & (nat.FG_EXEC_EXACT_ACCOUNTING | nat.FG_EXEC_COUNTERS):
         prep_flags |= nat.FG_PREP_NO_COLUMNS
 
     ks = batch.kmax
     nq = batch.n_queries
-    dev = torch.device("cuda:0")
-    d_hits = torch.zeros((nq, ks, 2), dtype=torch.int32, device=dev)
-    d_n = torch.zeros(nq, dtype=torch.int32, device=dev)
-    d_c = torch.zeros(nq, dtype=torch.int32, device=dev)
+    d_hits, d_n, d_c = DevBuf((nq, ks, 2)), DevBuf(nq), DevBuf(nq)
     words = (index.n_docs + 31) // 32
-    d_bm = torch.zeros((nq, words), dtype=torch.int32, device=dev) if want_bitmap else None
-    torch.cuda.synchronize()
+    d_bm = DevBuf((nq, words)) if want_bitmap else None
     pb = index.prepare(batch, prep_flags)
-    pb.execute(d_hits.data_ptr(), d_n.data_ptr(), d_c.data_ptr(), None if d_bm is None else d_bm.data_ptr(),
-               k_stride=ks, flags=flags)
+    pb.execute(d_hits.ptr, d_n.ptr, d_c.ptr, None if d_bm is None else d_bm.ptr, k_stride=ks, flags=flags)
     st = pb.stats()
     index.ctx.synchronize()
-    hits = d_hits.cpu().numpy().view(np.uint32).reshape(nq, ks, 2)
+    hits = d_hits.numpy().view(np.uint32).reshape(nq, ks, 2)
     out = np.zeros((nq, ks), nat.HIT_DT)
     out["score"] = hits[:, :, 0].view(np.float32)
     out["doc"] = hits[:, :, 1]
-    res = (out, d_n.cpu().numpy().view(np.uint32), d_c.cpu().numpy().view(np.uint32),
-           None if d_bm is None else d_bm.cpu().numpy().view(np.uint32), st)
+    res = (out, d_n.numpy().view(np.uint32), d_c.numpy().view(np.uint32),
+           None if d_bm is None else d_bm.numpy().view(np.uint32), st)
     pb.close()
     return res
 
