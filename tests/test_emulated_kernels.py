@@ -52,13 +52,21 @@ def _gpu_tests():
     return out
 
 
-# scaled-down corpora for the tests whose GPU sizes would take minutes under emulation
-SCALE = {"n_docs": 0.25}
+# The default CPU run keeps the emulated part to about two minutes: the tests below cover every kernel
+# class, the column-scan windows with gating and hit lists, deletes, snapshot refresh, facets and the
+# Dataset front-end. FG_EMU_FULL=1 runs all `-m gpu` tests under emulation (about an hour on 8 cores).
+FAST = {"test_config1_two_term_and", "test_golden_cases_through_dataset_search", "test_upsert_delete_snapshot_semantics",
+        "test_gated_column_scan_equals_exhaustive", "test_facet_counts_golden_corpus_with_deletes",
+        "test_delete_only_commit_refreshes_alive_bitset", "test_with_alive_shares_arrays_and_outlives_its_base",
+        "test_facet_counts_large_synthetic_with_facet_columns"}
 
 
 @pytest.mark.parametrize("fn", _gpu_tests())
 def test_gpu_suite_under_emulation(ctx, fn, monkeypatch):
     import inspect
+
+    if fn.__name__ not in FAST and not os.environ.get("FG_EMU_FULL"):
+        pytest.skip("slow under emulation: set FG_EMU_FULL=1")
 
     kwargs = {}
     if "monkeypatch" in inspect.signature(fn).parameters:

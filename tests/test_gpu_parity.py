@@ -483,3 +483,60 @@ def test_multi_item_plans_forced_small_items(ctx, monkeypatch):
     res = check_batch_against_oracle(index, desc, batch)
     assert res["stats"].n_work_items > batch.n_queries  # (heavy queries are cut into up to 14 / 29 items)
     index.close()
+
+
+def test_gated_column_scan_equals_exhaustive(ctx):
+    """Sparse-hit gating of the column scan (windows evaluated from their hit lists, chunks without a
+    streamed posting skipped once such docs cannot reach the top-k): identical results with the gate on,
+    off (FG_EXEC_NO_PRUNE) and from the oracle; the counters prove the gate engaged; deletes included."""
+    from oracle import orc
+    from tests.util import DevBuf, check_topk
+
+    cfg = synth.Config(cfg=2, n_docs=50_000, vocab=10_000, n_queries=1, k=10, name_pct=10)
+    corpus = synth.Corpus.for_config(cfg)
+    fields = synth.build_fields(corpus, 0, cfg.n_docs)
+    rng = np.random.default_rng(21)
+    alive = np.full((cfg.n_docs + 31) // 32, 0xFFFFFFFF, np.uint32)
+    for d in rng.choice(cfg.n_docs, cfg.n_docs // 50, replace=False):
+        alive[d >> 5] &= ~np.uint32(1 << (d & 31))
+    qs = []
+    for i in range(36):
+        cols = rng.choice(np.arange(1, 40), 1 + i % 3, replace=False)      # frequent terms: dense tf columns
+        sparse = rng.choice(np.arange(150, 4000), 1 + (i // 3) % 3, replace=False)  # streamed leaves, from a few per window to one in many windows
+        words = [f"w{int(r)}" for r in list(cols) + list(sparse)]
+        rng.shuffle(words)
+        qs.append({"query": " ".join(words), "filters": [], "k": 10 if i % 4 else 100})
+    batch = plan_queries(qs, vocab=cfg.vocab, n_text_fields=2)
+    for bits in (None, alive):
+        desc = nat.HostIndexDesc(cfg.n_docs, fields, alive_bitset=bits)
+        index = nat.Index(ctx, desc)
+        assert index.info().n_columns >= 40
+        o_hits, o_n, _ = orc.search(desc, batch, threads=4)
+        nq, ks = batch.n_queries, batch.kmax
+        res = {}
+        for name, flags in (("gated", nat.FG_EXEC_COUNTERS), ("exhaustive", nat.FG_EXEC_COUNTERS | nat.FG_EXEC_NO_PRUNE)):
+            d_hits, d_n = DevBuf((nq, ks, 2)), DevBuf(nq)
+            pb = index.prepare(batch)
+            pb.execute(d_hits.ptr, d_n.ptr, None, None, k_stride=ks, flags=flags)  # no match counts: the TopDocs form
+            st = pb.stats()
+            raw = d_hits.numpy().view(np.uint32).reshape(nq, ks, 2)
+            out = np.zeros((nq, ks), nat.HIT_DT)
+            out["score"], out["doc"] = raw[:, :, 0].view(np.float32), raw[:, :, 1]
+            res[name] = (out, d_n.numpy().view(np.uint32), st.colscan_chunks, st.colscan_chunks_skipped)
+            pb.close()
+        g, e = res["gated"], res["exhaustive"]
+        assert e[3] == 0 and g[2] == e[2] > 0
+        assert g[3] > g[2] // 4, f"the gate skipped only {g[3]} of {g[2]} chunks"
+        assert np.array_equal(g[1], o_n) and np.array_equal(e[1], o_n)
+        for qi in range(nq):
+            n = int(o_n[qi])
+            k = int(batch.q["k"][qi])
+            check_topk(g[0][qi, :n], o_hits[qi, :n], k, ctx=f"gated query {qi} {qs[qi]['query']}")
+            check_topk(e[0][qi, :n], o_hits[qi, :n], k, ctx=f"exhaustive query {qi}")
+            # same kernels, same operation order: gated and exhaustive agree far inside the oracle tolerance
+            check_topk(g[0][qi, :n], e[0][qi, :n], k, tol=1e-6, ctx=f"gated vs exhaustive query {qi}")
+        # with match counts every doc is visited and the counts are exact
+        h_hits, h_n, h_c = index.search(batch)
+        _, _, o_c = orc.search(desc, batch, threads=4)
+        assert np.array_equal(h_c, o_c)
+        index.close()
