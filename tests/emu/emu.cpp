@@ -45,6 +45,22 @@ static char* g_stacks = nullptr;
 static std::vector<Fiber> g_fibers;
 static std::recursive_mutex g_launch_mu;
 
+static unsigned long long g_seed = 0, g_rng = 0;
+static unsigned next_rand() {
+    g_rng = g_rng * 6364136223846793005ull + 1442695040888963407ull;
+    return (unsigned)(g_rng >> 33);
+}
+// an odd stride is coprime with the (power-of-two-multiple-of-32) block sizes used here only if it shares
+// no factor with them: search for one
+static unsigned pick_stride(unsigned block) {
+    for (;;) {
+        unsigned s = (next_rand() % block) | 1u;
+        unsigned a = s, b = block;
+        while (b) { unsigned t = a % b; a = b; b = t; }
+        if (a == 1) return s;
+    }
+}
+
 void die(const char* what) {
     fprintf(stderr, "fgemu: %s (block %u, thread %u)\n", what, g_cta.bid.x, g_cur ? g_cur->tid.x : 0u);
     abort();
@@ -63,8 +79,12 @@ static void fiber_main() {
 void launch(unsigned grid, unsigned block, size_t smem, const std::function<void()>& body) {
     std::lock_guard<std::recursive_mutex> lock(g_launch_mu);
     if (g_cur) die("nested launch");
+    static const bool g_profile = getenv("FGEMU_PROFILE") != nullptr;
+    timespec t0;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
     if (block == 0 || block > MAX_THREADS || (block & 31)) die("block size must be a multiple of 32, at most 1024");
     if (!g_stacks) {
+        if (const char* e = getenv("FGEMU_SEED")) { g_seed = strtoull(e, nullptr, 10); g_rng = g_seed * 0x9E3779B97F4A7C15ull + 1; }
         g_stacks = (char*)mmap(nullptr, STACK * MAX_THREADS, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
         if (g_stacks == (char*)MAP_FAILED) die("mmap of the fiber stacks failed");
     }
@@ -98,7 +118,11 @@ void launch(unsigned grid, unsigned block, size_t smem, const std::function<void
         unsigned live = block;
         while (live) {
             const unsigned long long before = g_progress;
-            for (unsigned t = 0; t < block; t++) {
+            // FGEMU_SEED=n: a different (pseudo-random, reproducible) thread order in every scheduler pass,
+            // to shake out code that only works in lock step. Default: ascending thread ids.
+            const unsigned stride = g_seed ? pick_stride(block) : 1u, first = g_seed ? next_rand() % block : 0u;
+            for (unsigned i = 0; i < block; i++) {
+                const unsigned t = (first + (unsigned long long)i * stride) % block;
                 Fiber& f = g_fibers[t];
                 if (f.done) continue;
                 g_cur = &f;
@@ -127,6 +151,12 @@ void launch(unsigned grid, unsigned block, size_t smem, const std::function<void
     }
     g_body = nullptr;
     free(dyn);
+    if (g_profile) {  // FGEMU_PROFILE=1: host time per launch, a rough proxy for executed thread-instructions
+        timespec t1;
+        clock_gettime(CLOCK_MONOTONIC, &t1);
+        fprintf(stderr, "[fgemu] launch grid %u block %u smem %zu: %.1f ms\n", grid, block, smem,
+                (t1.tv_sec - t0.tv_sec) * 1e3 + (t1.tv_nsec - t0.tv_nsec) * 1e-6);
+    }
 }
 
 }  // namespace fgemu

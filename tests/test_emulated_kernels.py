@@ -76,3 +76,16 @@ def test_gpu_suite_under_emulation(ctx, fn, monkeypatch):
     if "monkeypatch" in inspect.signature(fn).parameters:
         kwargs["monkeypatch"] = monkeypatch
     fn(ctx, **kwargs)
+
+
+def test_shuffled_thread_schedule():
+    """The same kernels with the emulator resuming a CTA's threads in a different pseudo-random order in
+    every scheduler pass (FGEMU_SEED, read once per process, hence the subprocess): code that is only
+    correct because a warp happens to run in lock step fails here (this is how the two hazards named in
+    DESIGN.md 5b were found)."""
+    import sys
+
+    pick = "config1 or golden or upsert or edge_cases or config5 or facet_counts_golden or delete_only or gated"
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-p", "no:cacheprovider", "-k", pick],
+                       env=dict(os.environ, FGEMU_SEED="7"), cwd=ROOT, capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0 and " passed" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
