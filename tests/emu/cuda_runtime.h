@@ -212,7 +212,7 @@ struct cudaDeviceProp { int major, minor, multiProcessorCount; char name[64]; };
 
 static inline const char* cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : e == cudaErrorMemoryAllocation ? "out of memory" : "invalid value"; }
 static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
-static inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
+static inline cudaError_t cudaGetDeviceCount(int* n) { *n = 8; return cudaSuccess; }  /* one per rank of a multi-process test */
 static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) {
     memset(p, 0, sizeof(*p)); p->major = 10; p->minor = 0; p->multiProcessorCount = 148; strcpy(p->name, "SIMT emulator (tests/emu)");

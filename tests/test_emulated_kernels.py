@@ -85,7 +85,7 @@ def test_shuffled_thread_schedule():
     DESIGN.md 5b were found)."""
     import sys
 
-    pick = "config1 or golden or upsert or edge_cases or config5 or facet_counts_golden or delete_only or gated"
+    pick = "config1 or golden or upsert or edge_cases or config5 or facet_counts_golden or delete_only"
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-p", "no:cacheprovider", "-k", pick],
                        env=dict(os.environ, FGEMU_SEED="7"), cwd=ROOT, capture_output=True, text=True, timeout=1500)
     assert r.returncode == 0 and " passed" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]

@@ -17,7 +17,7 @@ def _run(*args, timeout=900):
 
 
 def test_bench_main_emits_one_complete_json_line():
-    r = _run("bench", "--docs", "30000", "--vocab", "6000", "--queries", "96", "--steps", "2", "--warmup", "1")
+    r = _run("bench", "--docs", "20000", "--vocab", "4000", "--queries", "64", "--steps", "2", "--warmup", "1")
     assert r.returncode == 0, r.stderr[-3000:]
     lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
     assert len(lines) == 1, r.stdout[-2000:]
@@ -47,6 +47,23 @@ def test_bench_reference_arm_line():
     d = json.loads([ln for ln in r.stdout.splitlines() if ln.strip()][-1])
     assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_bench_two_ranks_control_flow():
+    """torchrun, 2 ranks, doc-id-range shards: the multi-rank control flow of bench.py (global statistics,
+    agreed number of untimed hold steps, barriers, max-over-ranks timing, all-gather + merge per step) with
+    the host-memory exchange route. The N = 8 hang of round 1 was a rank-local step count in this flow."""
+    subprocess.check_call(["make", "-s", "-j4", "-C", os.path.join(ROOT, "tests", "emu")])
+    env = dict(os.environ, FG_BENCH_EXCHANGE="gloo", FG_BENCH_DEADLINE="600")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29617", DRIVER, "bench", "--gpus", "2", "--docs", "20000", "--vocab", "4000", "--queries", "48",
+                        "--steps", "2", "--warmup", "3", "--no-cpu-baseline"], cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-3000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1, r.stdout[-2000:]
+    d = json.loads(lines[0])
+    assert d["n_gpus"] == 2 and d["scaling"] == "strong" and d["value"] > 0 and "x2" in d["config"]["sharding"]
+    assert d["gpu_launches"] > 0 and d["e2e"]["value"] > 0
 
 
 def test_smoke_entry_point():
