@@ -531,7 +531,7 @@ def main():
                              "that evaluates every leaf from its blocks; the timed pass reads 1 B/doc dense tf columns for terms "
                              "in >= 1/16 of the docs instead of their blocks. Index snapshot is %.0f MB in HBM incl. %.0f MB of "
                              "columns (L2 is 126 MB); L2 is flushed before each timed step; traffic = ncu dram bytes of one C2 "
-                             "step (profiles/r01b_traffic.json)" % (info.device_bytes / 1e6, info.column_bytes / 1e6)},
+                             "step (profiles/r01b_traffic.json, captured before sparse-hit gating was added to the column scan)" % (info.device_bytes / 1e6, info.column_bytes / 1e6)},
         "e2e": {"value": nq / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": int(lowered_bytes),
                 "d2h_bytes_per_step": int(out_bytes), "ms_per_step": e2e_s * 1e3,
                 "what": "fgh_search_batch: query strings (host) -> C++ planner -> plan lowering -> H2D plan -> kernels -> D2H hits "
