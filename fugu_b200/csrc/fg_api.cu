@@ -220,6 +220,8 @@ struct TermInfo {
     uint32_t blk_begin, n_blocks, df_local, df_global;
     uint64_t bytes;  // packed payload + 16 B skip per block
     int32_t col;     // dense tf column of the term (index into fg_index::d_cols) or -1
+    float idf_w;     // idf(df_global, N) * (1 + K1): the leaf weight before the boost (one logf per term at upload,
+                     // not one per leaf per query in the lowering)
 };
 struct HostField {
     uint32_t flags = 0;
@@ -342,6 +344,7 @@ extern "C" int32_t fg_index_upload(fg_ctx* ctx, const fg_index_desc* d, fg_index
             TermInfo& ti = hf.terms[t];
             ti.df_local = (uint32_t)n;
             ti.df_global = fd.global_doc_freq ? fd.global_doc_freq[t] : (uint32_t)n;
+            ti.idf_w = fg_bm25_idf(ti.df_global, ix->global_n_docs) * (1.0f + K1);
             if (ti.df_global < ti.df_local)
                 return fail(FG_ERR_INVALID, "field %u term %u: global df < local df", f, t);
             ti.n_blocks = (uint32_t)((n + BLOCK - 1) / BLOCK);
@@ -667,7 +670,6 @@ extern "C" int32_t fg_batch_prepare_ex(fg_index* ix, const fg_query_batch* qb, u
     const uint32_t HASH_MIN_SPAN = 4096;
 
     std::vector<DevQuery> dq(qb->n_queries);
-    const uint64_t N = ix->global_n_docs;
     const uint64_t SOLO_MIN_BLOCKS = env_u64("FG_SOLO_MIN_BLOCKS", 0xFFFFFFFFull);
     constexpr int MAXC = 32, MAXT = 64;
     struct CRec { uint32_t occur, begin, count, ncol; uint64_t cost, df; };
@@ -743,7 +745,7 @@ extern "C" int32_t fg_batch_prepare_ex(fg_index* ix, const fg_query_batch* qb, u
                     memset(&L, 0, sizeof(L));
                     L.blk_begin = ti.blk_begin;
                     L.n_blocks = ti.n_blocks;
-                    L.weight = lf.boost * (fg_bm25_idf(ti.df_global, N) * (1.0f + K1));
+                    L.weight = lf.boost * ti.idf_w;
                     L.cnorm = hf.cnorm;
                     L.fn_field = (hf.flags & FG_FIELD_HAS_FIELDNORMS) ? (int32_t)lf.field : -1;
                     if (use_cols && ti.col >= 0) {
