@@ -96,6 +96,14 @@ def main():
     with open(os.path.join(HERE, "replay_queries.jsonl"), "w") as f:
         for c in cases:
             f.write(json.dumps({"query": c["query"], "filters": c["filters"], "page": {"page": c["page"], "per_page": c["per_page"]}}) + "\n")
+    # facet counting (src/db/facet.rs): what FacetCollector over AllQuery reports for a few roots, the
+    # recursive walk of get_facet_tree and the response of GET /facets/tree for three depths
+    roots = ["/", "/namespace", "/namespace/ns0", "/namespace/ns1/organization", "/namespace/ns3/data", "/nosuch"]
+    walk = []
+    op.facet_collect_recursive(ix, "/", 0, None, walk)
+    json.dump({"collect": {r: op.facet_collect(ix, r) for r in roots}, "walk": walk,
+               "tree": {str(md): op.facet_tree(ix, md) for md in (None, 2, 3)}},
+              open(os.path.join(HERE, "facet_cases.json"), "w"), indent=1)
     print(len(cases), "cases")
 
 

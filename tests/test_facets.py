@@ -77,6 +77,21 @@ def test_tree_builder_matches_twin(max_depth):
         assert ns.count == dict(op.facet_collect(ix, "/"))["/namespace"] + sum(c.count for c in ns.children.values())
 
 
+def test_golden_facet_fixture():
+    """tests/golden/facet_cases.json (written by make_golden.py from the twin; part of the replay kit: the
+    "tree" entries are what GET /facets/tree of a real fugu should answer for the replay corpus)."""
+    g = golden("facet_cases.json")
+    flat = [(p, c) for p, c in g["walk"]]
+    for md in (None, 2, 3):
+        want = g["tree"][str(md)]
+        sub = [(p, c) for p, c in flat if md is None or p.count("/") <= md]  # what the walk collects down to max_depth
+        got = build_facet_tree(sub, md)
+        assert got.total_facets == want["total_facets"] and got.max_depth == want["max_depth"], md
+        assert {k: _node_dict(v) for k, v in got.tree.items()} == want["tree"], md
+    assert [p for p, _ in g["collect"]["/namespace"]] == ["/namespace/ns0", "/namespace/ns1", "/namespace/ns2", "/namespace/ns3"]
+    assert g["collect"]["/nosuch"] == []
+
+
 # ---------------------------------------------------------------------------------------------
 @pytest.fixture(scope="module")
 def ctx():
@@ -89,8 +104,10 @@ def ctx():
 def test_facet_counts_golden_corpus_with_deletes(ctx):
     g, ds, ix = golden_dataset(ctx)
     ds.commit()
+    gf = golden("facet_cases.json")
     for root in ["/", "/namespace", "/namespace/ns0", "/namespace/ns1/organization", "/namespace/ns3/data", "/nosuch"]:
-        assert ds.list_facet(root) == op.facet_collect(ix, root), root
+        assert ds.list_facet(root) == op.facet_collect(ix, root) == [tuple(x) for x in gf["collect"][root]], root
+    assert ds.facet_counts("/", 0) == [tuple(x) for x in gf["walk"]]
     assert ds.get_available_namespaces() == sorted(p[len("/namespace/"):] for p, _ in op.facet_collect(ix, "/namespace"))
     assert ds.get_namespace_facets("ns2") == op.facet_collect(ix, "/namespace/ns2")
     assert ds.get_facets() == op.facet_collect(ix, "/")
