@@ -359,7 +359,7 @@ struct fgh_dataset {
     // same way: it keeps the segments it was opened on).
     std::shared_ptr<fg_index> index;
     uint32_t committed_docs = 0;  // n_docs of the snapshot in `index`
-    std::mutex mu;
+    mutable std::mutex mu;
     FieldBuild f[3];
     std::vector<std::string> ids;
     std::unordered_map<std::string, uint32_t> id2doc;
@@ -1161,7 +1161,7 @@ extern "C" int32_t fgh_facet_children(const fgh_dataset* ds, const char* root, u
                                       fgh_facet_entry* out, uint32_t cap, char* path_buf, uint32_t path_cap,
                                       uint32_t* n_out, uint32_t* path_bytes_out) {
     if (!ds || (out && !path_buf)) return host_fail(FG_ERR_INVALID, "fgh_facet_children: NULL argument");
-    std::lock_guard<std::mutex> g(const_cast<fgh_dataset*>(ds)->mu);
+    std::lock_guard<std::mutex> g(ds->mu);
     std::vector<FacetEnt> ents;
     if (int32_t rc = facet_enumerate(ds, root, max_depth, ents)) return rc;
     return facet_emit(ents, nullptr, out, cap, path_buf, path_cap, n_out, path_bytes_out);
