@@ -10,6 +10,7 @@
 #include <cstring>
 #include <memory>
 #include <mutex>
+#include <shared_mutex>
 #include <string>
 #include <thread>
 #include <unordered_map>
@@ -359,7 +360,17 @@ struct fgh_dataset {
     // same way: it keeps the segments it was opened on).
     std::shared_ptr<fg_index> index;
     uint32_t committed_docs = 0;  // n_docs of the snapshot in `index`
-    mutable std::mutex mu;
+    // dictionary entries the current snapshot knows, per field: ordinals are assigned in insertion order, so
+    // a term first seen after the last commit has an ordinal >= this and is planned as MISSING (an
+    // uncommitted document is invisible to the reference's searcher too). A dataset without a device
+    // context never commits: its dictionary is its state and everything in it is visible.
+    uint32_t committed_terms[3] = {0, 0, 0};
+    // writers (upsert, delete, commit, adopt) exclusive; planners, dictionary walks and snapshot grabs shared
+    mutable std::shared_mutex mu;
+    uint32_t lookup(uint32_t field, const char* s, size_t n) const {
+        const uint32_t o = f[field].dict.find(s, n);
+        return (o != FG_TERM_MISSING && ctx && o >= committed_terms[field]) ? FG_TERM_MISSING : o;
+    }
     FieldBuild f[3];
     std::vector<std::string> ids;
     std::unordered_map<std::string, uint32_t> id2doc;
@@ -383,11 +394,11 @@ extern "C" void fgh_dataset_destroy(fgh_dataset* ds) {
 extern "C" uint32_t fgh_dataset_num_docs(const fgh_dataset* ds) { return ds ? ds->n_docs : 0; }
 extern "C" fg_index* fgh_dataset_index(fgh_dataset* ds) {
     if (!ds) return nullptr;
-    std::lock_guard<std::mutex> g(ds->mu);
+    std::shared_lock<std::shared_mutex> g(ds->mu);
     return ds->index.get();
 }
 static std::shared_ptr<fg_index> current_snapshot(fgh_dataset* ds) {
-    std::lock_guard<std::mutex> g(ds->mu);
+    std::shared_lock<std::shared_mutex> g(ds->mu);
     return ds->index;
 }
 
@@ -415,7 +426,7 @@ static void delete_doc_locked(fgh_dataset* ds, const std::string& id) {
 
 extern "C" int32_t fgh_dataset_delete(fgh_dataset* ds, const char* id) {
     if (!ds || !id) return host_fail(FG_ERR_INVALID, "NULL argument");
-    std::lock_guard<std::mutex> g(ds->mu);
+    std::unique_lock<std::shared_mutex> g(ds->mu);
     if (ds->adopted) return host_fail(FG_ERR_UNSUPPORTED, "adopted datasets are immutable");
     delete_doc_locked(ds, id);
     return FG_OK;
@@ -435,7 +446,7 @@ extern "C" int32_t fgh_dataset_upsert(fgh_dataset* ds, const char* id, const cha
         if (!facets[i] || !facets[i][0]) return host_fail(FG_ERR_INVALID, "Facet at index %u cannot be empty", i);
         if (strlen(facets[i]) > 512) return host_fail(FG_ERR_INVALID, "Facet at index %u too long (max 512 characters)", i);
     }
-    std::lock_guard<std::mutex> g(ds->mu);
+    std::unique_lock<std::shared_mutex> g(ds->mu);
     if (ds->adopted) return host_fail(FG_ERR_UNSUPPORTED, "adopted datasets are immutable");
     delete_doc_locked(ds, id);  // delete_term(id) then add_document, src/db/document.rs:38-48
     const uint32_t doc = ds->n_docs++;
@@ -477,7 +488,7 @@ extern "C" int32_t fgh_dataset_upsert(fgh_dataset* ds, const char* id, const cha
 
 extern "C" int32_t fgh_dataset_commit(fgh_dataset* ds) {
     if (!ds) return host_fail(FG_ERR_INVALID, "NULL dataset");
-    std::lock_guard<std::mutex> g(ds->mu);
+    std::unique_lock<std::shared_mutex> g(ds->mu);
     if (ds->adopted) return FG_OK;
     if (!ds->ctx) return host_fail(FG_ERR_NO_DEVICE, "dataset has no device context (planning only)");
     std::vector<uint32_t> alive((ds->n_docs + 31) / 32, 0);
@@ -536,6 +547,7 @@ extern "C" int32_t fgh_dataset_commit(fgh_dataset* ds) {
     if (rc) return rc;
     ds->index.reset(nx, fg_index_release);
     ds->committed_docs = ds->n_docs;
+    for (int f = 0; f < 3; f++) ds->committed_terms[f] = fd[f].n_terms;
     ds->dirty = false;
     return FG_OK;
 }
@@ -544,7 +556,7 @@ extern "C" int32_t fgh_dataset_adopt(fgh_dataset* ds, const fg_index_desc* desc,
                                      const uint64_t* terms_bytes) {
     if (!ds || !desc) return host_fail(FG_ERR_INVALID, "NULL argument");
     if (desc->n_fields > 3) return host_fail(FG_ERR_INVALID, "adopt expects fields [text, name, facet]");
-    std::lock_guard<std::mutex> g(ds->mu);
+    std::unique_lock<std::shared_mutex> g(ds->mu);
     if (ds->ctx) {
         fg_index* nx = nullptr;
         int32_t rc = fg_index_upload(ds->ctx, desc, &nx);
@@ -563,6 +575,7 @@ extern "C" int32_t fgh_dataset_adopt(fgh_dataset* ds, const fg_index_desc* desc,
             p += l + 1;
         }
     }
+    for (uint32_t f = 0; f < 3; f++) ds->committed_terms[f] = f < desc->n_fields ? desc->fields[f].n_terms : 0;
     ds->adopted = true;
     ds->n_docs = desc->n_docs;
     ds->doc_base = desc->doc_id_base;
@@ -582,7 +595,7 @@ extern "C" int32_t fgh_dataset_doc_id(const fgh_dataset* ds, uint32_t doc, char*
 
 extern "C" uint32_t fgh_dataset_term_ord(const fgh_dataset* ds, uint32_t field, const char* token) {
     if (!ds || field > 2 || !token) return FG_TERM_MISSING;
-    return ds->f[field].dict.find(token, strlen(token));
+    return ds->lookup(field, token, strlen(token));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -842,6 +855,7 @@ int32_t plan_impl(const fgh_dataset* ds, const char* query, const char* const* f
 extern "C" int32_t fgh_plan(const fgh_dataset* ds, const char* query, const char* const* filters,
                             uint32_t n_filters, uint32_t page, uint32_t per_page, fgh_plan_t* out) {
     if (!ds || !out) return host_fail(FG_ERR_INVALID, "fgh_plan: NULL argument");
+    std::shared_lock<std::shared_mutex> g(ds->mu);  // the dictionaries must not grow under the planner
     return plan_impl(ds, query, filters, n_filters, page, per_page, out);
 }
 
@@ -908,8 +922,8 @@ bool plan_fast(const fgh_dataset* ds, const char* q, uint32_t page, uint32_t per
         cl.occur = conj ? FG_OCCUR_MUST : FG_OCCUR_SHOULD;
         cl.leaf_begin = (uint32_t)l.size();
         cl.n_leaves = 2;
-        l.push_back({FGH_FIELD_TEXT, ds->f[FGH_FIELD_TEXT].dict.find(low, words[i].n), 1.f});
-        l.push_back({FGH_FIELD_NAME, ds->f[FGH_FIELD_NAME].dict.find(low, words[i].n), 1.f});
+        l.push_back({FGH_FIELD_TEXT, ds->lookup(FGH_FIELD_TEXT, low, words[i].n), 1.f});
+        l.push_back({FGH_FIELD_NAME, ds->lookup(FGH_FIELD_NAME, low, words[i].n), 1.f});
         c.push_back(cl);
     }
     out.n_clauses = (uint32_t)(c.size() - c0);
@@ -918,6 +932,7 @@ bool plan_fast(const fgh_dataset* ds, const char* q, uint32_t page, uint32_t per
 
 void plan_batch(const fgh_dataset* ds, uint32_t n, const char* const* queries, const char* const* filters,
                 const uint32_t* filter_offsets, const uint32_t* pages, const uint32_t* per_pages, PlannedBatch& pb) {
+    std::shared_lock<std::shared_mutex> dict_lock(ds->mu);  // held for the worker threads too: the dictionaries must not grow under the planner
     pb.rc.assign(n, FG_OK);
     pb.q.resize(n);
     pb.offset.assign(n, 0);
@@ -1161,7 +1176,7 @@ extern "C" int32_t fgh_facet_children(const fgh_dataset* ds, const char* root, u
                                       fgh_facet_entry* out, uint32_t cap, char* path_buf, uint32_t path_cap,
                                       uint32_t* n_out, uint32_t* path_bytes_out) {
     if (!ds || (out && !path_buf)) return host_fail(FG_ERR_INVALID, "fgh_facet_children: NULL argument");
-    std::lock_guard<std::mutex> g(ds->mu);
+    std::shared_lock<std::shared_mutex> g(ds->mu);
     std::vector<FacetEnt> ents;
     if (int32_t rc = facet_enumerate(ds, root, max_depth, ents)) return rc;
     return facet_emit(ents, nullptr, out, cap, path_buf, path_cap, n_out, path_bytes_out);
@@ -1175,7 +1190,7 @@ extern "C" int32_t fgh_facet_counts(fgh_dataset* ds, const char* root, uint32_t 
     std::vector<std::string> keep;  // copies: the dictionary pool may grow once the lock is dropped
     std::shared_ptr<fg_index> snap;
     {
-        std::lock_guard<std::mutex> g(ds->mu);
+        std::shared_lock<std::shared_mutex> g(ds->mu);
         if (int32_t rc = facet_enumerate(ds, root, max_depth, ents)) return rc;
         snap = ds->index;
         keep.reserve(ents.size());

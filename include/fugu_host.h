@@ -48,7 +48,12 @@ void fgh_dataset_destroy(fgh_dataset* ds);
 int32_t fgh_dataset_upsert(fgh_dataset* ds, const char* id, const char* text, const char* name,
                            const char* const* facets, uint32_t n_facets);
 int32_t fgh_dataset_delete(fgh_dataset* ds, const char* id);
-/* Publish the pending state as a new device snapshot (swaps the fg_index; searches already running
+/* Visibility follows the reference's reader: searches, plans and facet counts see the state of the last
+ * commit. A document upserted since is invisible, and a term or facet that only such documents contain
+ * plans as FG_TERM_MISSING (an empty scorer), never as an error. Planning, searching and counting may run
+ * concurrently with upserts and commits (readers share the dataset's lock, writers take it exclusively).
+ *
+ * Publish the pending state as a new device snapshot (swaps the fg_index; searches already running
  * keep the snapshot they started on). Only deletes since the last commit: the new snapshot shares the
  * posting arrays of the old one and uploads just the alive bitset (fg_index_with_alive, SURVEY.md 8(f)
  * row f3). New documents: the CSR is rebuilt and uploaded whole (per-segment incremental upload is not

@@ -59,7 +59,7 @@ def _gpu_tests():
 FAST = {"test_config1_two_term_and", "test_golden_cases_through_dataset_search", "test_upsert_delete_snapshot_semantics",
         "test_gated_column_scan_equals_exhaustive", "test_facet_counts_golden_corpus_with_deletes",
         "test_delete_only_commit_refreshes_alive_bitset", "test_with_alive_shares_arrays_and_outlives_its_base",
-        "test_facet_counts_large_synthetic_with_facet_columns", "test_config4_three_term_and_with_deletes",
+        "test_facet_counts_large_synthetic_with_facet_columns", "test_uncommitted_documents_are_invisible", "test_config4_three_term_and_with_deletes",
         "test_config5_facet_filters", "test_edge_cases", "test_sharded_search_and_device_merge",
         "test_accounting_matches_oracle_definition", "test_many_leaf_union_in_hash_mode",
         "test_concurrent_callers_share_one_index"}

@@ -247,3 +247,29 @@ def test_synthetic_facet_dictionary_enumerates_on_cpu():
     assert ds.facet_children("/", 0) == sorted(paths, key=op._facet_sort_key)
     assert set(want) <= set(paths) and len(want) > 64
     ds.close()
+
+
+@pytest.mark.gpu
+def test_uncommitted_documents_are_invisible(ctx):
+    """A searcher only sees committed segments (src/db/document.rs:65, core.rs:86): a document upserted
+    but not committed changes no result, and a term that only it contains is an empty scorer, not an
+    error (its dictionary ordinal is beyond the snapshot's); after the commit both are visible."""
+    ds, ix = Dataset(ctx), op.PyIndex()
+    base = [("a", "alpha beta", ["/namespace/n1"]), ("b", "beta gamma", ["/namespace/n1"]), ("c", "alpha alpha", ["/namespace/n2"])]
+    ds.upsert([ObjectRecord(id=i, text=t, facets=f) for i, t, f in base])
+    for i, t, f in base:
+        ix.upsert(i, t, None, f)
+    ds.upsert([ObjectRecord(id="z", text="zeta alpha", facets=["/namespace/n9"])], commit=False)
+    assert ds.search("zeta") == [] and ds.search("zeta", ["/namespace/n9"]) == []
+    for q, fl in [("alpha", []), ("alpha zeta", []), ("beta", ["/namespace/n1"]), ("", [])]:
+        want, n_match = op.search(ix, q, fl, 0, 10)  # the twin has not seen "z"
+        got = ds.search(q, fl, 0, 10)
+        assert [r.doc for r in got] == [d for d, _ in want], (q, fl)
+    assert ds.facet_counts("/namespace", 1) == op.facet_collect(ix, "/namespace")
+    assert ds.plan("zeta").as_dict()["clauses"][0][1][0][1] == nat.FG_TERM_MISSING
+    ds.commit()
+    ix.upsert("z", "zeta alpha", None, ["/namespace/n9"])
+    assert [r.id for r in ds.search("zeta")] == ["z"]
+    _check_search(ds, ix, "alpha", [], tag="after commit")
+    assert ds.facet_counts("/namespace", 1) == op.facet_collect(ix, "/namespace")
+    ds.close()
