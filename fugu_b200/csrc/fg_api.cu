@@ -965,11 +965,18 @@ extern "C" int32_t fg_batch_prepare_ex(fg_index* ix, const fg_query_batch* qb, u
             const uint32_t lg = c ? 63u - (uint32_t)__builtin_clzll(c) : 0u;
             const uint32_t sub = (lg && ((c >> (lg - 1)) & 1u)) ? 1u : 0u;
             const uint32_t bk = std::min<uint32_t>(63u, lg * 2u + sub);
-            return items[i].cls * 64u + (63u - bk);
+            // Column-scan class: the FIRST work item of every query is queued ahead of all sibling items. An
+            // item's first window runs cold (the query's threshold is not known yet: fully scanned, no
+            // sparse-hit gating); siblings that start after a first item has published its threshold through
+            // qtheta are gated from their first window on. Items of one query have equal cost, so plain
+            // heavy-first order would start them all at once, all cold.
+            uint32_t group = items[i].cls;
+            if (group == 4u && items[i].slot != dq[items[i].query].item_begin) group = (uint32_t)NCLS;
+            return group * 64u + (63u - bk);
         };
-        uint32_t hist[NCLS * 64 + 1] = {0};
+        uint32_t hist[(NCLS + 1) * 64 + 1] = {0};
         for (size_t i = 0; i < items.size(); i++) hist[bucket(i) + 1]++;
-        for (int i = 0; i < NCLS * 64; i++) hist[i + 1] += hist[i];
+        for (int i = 0; i < (NCLS + 1) * 64; i++) hist[i + 1] += hist[i];
         for (size_t i = 0; i < items.size(); i++) sorted[hist[bucket(i)]++] = items[i];
     }
     uint32_t class_count[NCLS] = {};
