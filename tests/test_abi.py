@@ -68,3 +68,16 @@ def test_product_never_imports_the_oracle():
     for f in ("_native.py", "synth.py", "dataset.py", "__init__.py"):
         src = open(os.path.join(pkg, f)).read()
         assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f
+
+
+def test_product_never_loads_the_emulated_library():
+    """tests/emu/libfugu_emu.so (the kernel sources under a SIMT emulation) is test infrastructure: no
+    product module, the bench or the driver entry points may name it, and the library the product loads
+    is the nvcc build next to the package."""
+    for f in ("bench.py", "__graft_entry__.py", "fugu_b200/_native.py", "fugu_b200/dataset.py", "fugu_b200/synth.py", "fugu_b200/__init__.py"):
+        src = open(os.path.join(ROOT, f)).read()
+        assert "libfugu_emu" not in src and "tests/emu" not in src and "FG_EMULATE" not in src, f
+    assert nat.LIB_PATH == os.path.join(ROOT, "fugu_b200", "libfugu_gpu.so")
+    # the product build defines nothing of the emulation: FG_EMULATE comes from tests/emu/cuda_runtime.h alone
+    mk = open(os.path.join(ROOT, "Makefile")).read()
+    assert "FG_EMULATE" not in mk and "tests/emu" not in mk
