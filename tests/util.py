@@ -104,6 +104,13 @@ def check_batch_against_oracle(index: nat.Index, desc: nat.HostIndexDesc, batch:
     for qi in range(batch.n_queries):  # float atomics: the two runs may differ in the last bit
         n = int(g_n[qi])
         check_topk(h_hits[qi, :n], g_hits[qi, :n], int(batch.q["k"][qi]), ctx=f"host-vs-device query {qi}")
+    # the TopDocs form (no match counts, no bitmap): the only form in which the column scan may gate windows
+    # on sparse hits and skip docs that cannot reach the top-k; it must answer exactly like the counting form
+    t_hits, t_n, t_c = index.search(batch, want_counts=False)
+    assert t_c is None and np.array_equal(t_n, o_n), f"TopDocs form: n_hits differ for queries {np.nonzero(t_n != o_n)[0][:10]}"
+    for qi in range(batch.n_queries):
+        n = int(o_n[qi])
+        check_topk(t_hits[qi, :n], o_hits[qi, :n], int(batch.q["k"][qi]), ctx=f"TopDocs form (gated column scan), query {qi}")
     # deterministic mode: two executions are bit-identical
     d1 = gpu_search_device(index, batch, flags=nat.FG_EXEC_DETERMINISTIC)
     d2 = gpu_search_device(index, batch, flags=nat.FG_EXEC_DETERMINISTIC)
