@@ -6,19 +6,21 @@ PROFILE ?= 0
 ifeq ($(PROFILE),1)
 EXTRA := -DFG_PROFILE_PHASES
 endif
-NVFLAGS := $(EXTRA) -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC,-Wall,-Wno-unused-function -Iinclude
+NVFLAGS := $(EXTRA) -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC,-Wall,-Wno-unused-function -Iinclude -Ifugu_b200/csrc
 CSRC := fugu_b200/csrc
 
 all: fugu_b200/libfugu_gpu.so fugu_b200/synth/libfugu_synth.so oracle/liboracle.so
 
-$(CSRC)/fg_kernels.o: $(CSRC)/fg_kernels.cu $(CSRC)/fg_internal.h
+$(CSRC)/fg_kernels.o: $(CSRC)/fg_kernels.cu $(CSRC)/fg_internal.h $(CSRC)/fg_device.h $(CSRC)/fg_ptx.h
+	$(NVCC) $(NVFLAGS) -Xptxas -v -c $< -o $@
+$(CSRC)/fg_lead.o: $(CSRC)/fg_lead.cu $(CSRC)/fg_internal.h $(CSRC)/fg_device.h $(CSRC)/fg_ptx.h
 	$(NVCC) $(NVFLAGS) -Xptxas -v -c $< -o $@
 $(CSRC)/fg_api.o: $(CSRC)/fg_api.cu $(CSRC)/fg_internal.h $(CSRC)/fg_error.h $(CSRC)/fg_pool.h include/fugu_gpu.h
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 $(CSRC)/fg_host.o: $(CSRC)/fg_host.cpp $(CSRC)/fg_error.h $(CSRC)/fg_pool.h $(CSRC)/fg_unicode_tables.h include/fugu_gpu.h include/fugu_host.h
 	$(CXX) -O2 -std=c++17 -fPIC -Wall -Iinclude -c $< -o $@
 
-fugu_b200/libfugu_gpu.so: $(CSRC)/fg_kernels.o $(CSRC)/fg_api.o $(CSRC)/fg_host.o
+fugu_b200/libfugu_gpu.so: $(CSRC)/fg_kernels.o $(CSRC)/fg_lead.o $(CSRC)/fg_api.o $(CSRC)/fg_host.o
 	$(NVCC) -shared $(ARCH) -o $@ $^ -lpthread
 
 fugu_b200/synth/libfugu_synth.so: fugu_b200/synth/synth.cpp

@@ -14,7 +14,6 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libfugu_gpu.so")
-LIB_PATH = os.environ.get("FG_LIB", LIB_PATH)  # dev: alternative builds of the same library
 
 FG_OK = 0
 FG_ERR_INVALID = -1
@@ -33,6 +32,7 @@ FG_EXEC_DETERMINISTIC = 2
 FG_EXEC_COUNTERS = 4
 FG_EXEC_NO_PRUNE = 8
 FG_PREP_NO_COLUMNS = 1
+FG_PREP_LEGACY = 2
 
 
 class FgError(RuntimeError):
@@ -106,6 +106,9 @@ class BatchStats(C.Structure):
         ("merge_kernel_ms", C.c_float),
         ("colscan_chunks", C.c_uint64),
         ("colscan_chunks_skipped", C.c_uint64),
+        ("bytes_meta", C.c_uint64),
+        ("lead_blocks", C.c_uint64),
+        ("lead_blocks_seen", C.c_uint64),
     ]
 
 

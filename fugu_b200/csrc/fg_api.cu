@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -104,7 +105,15 @@ struct fg_ctx {
     // kernels of batch i (fg_batch_submit / fgh_search_batch pipeline host work under device work)
     cudaStream_t up = nullptr;
     std::vector<std::pair<void*, size_t>> hpool;  // page-locked staging blocks for asynchronous result copies
+    // development switches, read ONCE when the context is created (never per request)
+    bool env_legacy = false;      // FG_LEGACY=1: lower every plan for the round-1 window kernels (fg_kernels.cu)
+    bool env_no_columns = false;  // FG_NO_COLUMNS=1
+    bool env_no_prune = false;    // FG_NO_PRUNE=1: exhaustive evaluation (A/B runs; results are identical)
+    bool env_timing = false;      // FG_TIMING=1
+    bool env_prof = false;        // FG_PROF=1
+    uint32_t lead_par_blocks = 256, lead_max_par = 16, lead_chunk = 64;
 };
+static uint64_t env_u64_early(const char* name, uint64_t dflt);
 
 static cudaError_t pinned_alloc(fg_ctx* c, void** out, size_t bytes) {
     bytes = std::max<size_t>((bytes + 4095) & ~(size_t)4095, 4096);
@@ -178,6 +187,14 @@ extern "C" int32_t fg_ctx_create(int32_t device, fg_ctx** out) {
     fg_ctx* c = new fg_ctx();
     c->device = device;
     c->n_sms = pr.multiProcessorCount;
+    c->env_legacy = env_u64_early("FG_LEGACY", 0) != 0;
+    c->env_no_columns = getenv("FG_NO_COLUMNS") != nullptr;
+    c->env_no_prune = getenv("FG_NO_PRUNE") != nullptr;
+    c->env_timing = getenv("FG_TIMING") != nullptr;
+    c->env_prof = getenv("FG_PROF") != nullptr;
+    c->lead_par_blocks = (uint32_t)std::max<uint64_t>(1, env_u64_early("FG_LEAD_PAR_BLOCKS", 256));
+    c->lead_max_par = (uint32_t)std::max<uint64_t>(1, env_u64_early("FG_LEAD_MAX_PAR", 16));
+    c->lead_chunk = (uint32_t)std::max<uint64_t>(1, env_u64_early("FG_LEAD_CHUNK", 64));
     CU(cudaStreamCreateWithFlags(&c->own, cudaStreamNonBlocking));
     c->stream = c->own;
     for (int i = 0; i < NCLS - 1; i++) {
@@ -222,6 +239,8 @@ struct TermInfo {
     int32_t col;     // dense tf column of the term (index into fg_index::d_cols) or -1
     float idf_w;     // idf(df_global, N) * (1 + K1): the leaf weight before the boost (one logf per term at upload,
                      // not one per leaf per query in the lowering)
+    float max_factor;  // max over the term's postings of tf / (tf + norm): weight * max_factor bounds the leaf's score
+    uint32_t top_off, top_n;  // the term's top_n largest block maxima, descending, at fg_index::topbm[top_off ..]
 };
 struct HostField {
     uint32_t flags = 0;
@@ -253,7 +272,11 @@ struct fg_index {
     const uint8_t* d_cols = nullptr;
     uint64_t col_stride = 0;
     uint32_t n_cols = 0;
+    // per term with at least TOP_MIN_BLOCKS blocks: its largest block maxima (descending, at most TOP_MAX). The
+    // k-th of them is a lower bound of the k-th best score of any pure union containing the term.
+    std::shared_ptr<std::vector<float>> topbm;
 };
+static constexpr uint32_t TOP_MIN_BLOCKS = 4, TOP_MAX = 128;
 
 static uint64_t env_u64_early(const char* name, uint64_t dflt) {
     const char* e = getenv(name);
@@ -352,6 +375,8 @@ extern "C" int32_t fg_index_upload(fg_ctx* ctx, const fg_index_desc* d, fg_index
             ti.blk_begin = (uint32_t)n_blocks;
             ti.bytes = 0;
             ti.col = -1;
+            ti.max_factor = 0.f;
+            ti.top_off = ti.top_n = 0;
             n_blocks += ti.n_blocks;
             n_postings += n;
         }
@@ -484,6 +509,59 @@ extern "C" int32_t fg_index_upload(fg_ctx* ctx, const fg_index_desc* d, fg_index
     ix->dev.doc_base = d->doc_id_base;
     ix->dev.n_alive = d->alive_bitset ? count_alive(d->alive_bitset, d->n_docs) : d->n_docs;
 
+    // ---- block-max metadata (tantivy stores the block-max fieldnorm/tf pair in its skip entries, A.7) ----
+    // One f32 per block: the largest tf / (tf + norm(doc)) of its postings, computed on the device with the
+    // scoring path's own arithmetic (so weight * bmax >= every score of the block, exactly). The host keeps
+    // each term's maximum and its largest block maxima for the MaxScore bounds of the lowering.
+    {
+        float* d_bmax = nullptr;
+        CU(cudaMalloc((void**)&d_bmax, std::max<size_t>(n_blocks * 4, 16)));
+        ix->arena->allocs.push_back(d_bmax);
+        ix->info.device_bytes += n_blocks * 4;
+        ix->dev.bmax = d_bmax;
+        ix->dev.n_docs = d->n_docs;
+        for (uint32_t f = 0; f < d->n_fields; f++) {
+            const HostField& hf = ix->fields[f];
+            if (hf.terms.empty()) continue;
+            const uint32_t b0 = hf.terms.front().blk_begin, b1 = hf.terms.back().blk_begin + hf.terms.back().n_blocks;
+            launch_blockmax(ix->dev, b0, b1, (hf.flags & FG_FIELD_HAS_FIELDNORMS) ? (int)f : -1, hf.cnorm, d_bmax, ctx->stream);
+        }
+        CU(cudaGetLastError());
+        std::vector<float> bm(n_blocks);
+        CU(cudaMemcpyAsync(bm.data(), d_bmax, n_blocks * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        auto top = std::make_shared<std::vector<float>>();
+        // offsets first (serial), then the per-term selection in parallel
+        uint64_t top_total = 0;
+        for (uint32_t f = 0; f < d->n_fields; f++)
+            for (auto& ti : ix->fields[f].terms)
+                if (ti.n_blocks >= TOP_MIN_BLOCKS) {
+                    ti.top_off = (uint32_t)top_total;
+                    ti.top_n = std::min<uint32_t>(ti.n_blocks, TOP_MAX);
+                    top_total += ti.top_n;
+                }
+        if (top_total > 0xFFFFFFF0ull) return fail(FG_ERR_UNSUPPORTED, "block-max table too large");
+        top->resize(top_total);
+        for (uint32_t f = 0; f < d->n_fields; f++) {
+            HostField& hf = ix->fields[f];
+            parallel_for(hf.n_terms, T, [&](uint64_t a, uint64_t b, int) {
+                std::vector<float> tmp;
+                for (uint64_t t = a; t < b; t++) {
+                    TermInfo& ti = hf.terms[t];
+                    const float* v = bm.data() + ti.blk_begin;
+                    float mx = 0.f;
+                    for (uint32_t i = 0; i < ti.n_blocks; i++) mx = std::max(mx, v[i]);
+                    ti.max_factor = mx;
+                    if (!ti.top_n) continue;
+                    tmp.assign(v, v + ti.n_blocks);
+                    std::partial_sort(tmp.begin(), tmp.begin() + ti.top_n, tmp.end(), std::greater<float>());
+                    std::copy(tmp.begin(), tmp.begin() + ti.top_n, top->begin() + ti.top_off);
+                }
+            });
+        }
+        ix->topbm = top;
+    }
+
     // ---- dense tf columns -----------------------------------------------------------------
     // A term that occurs in at least 1/FG_COL_DIV of the shard's docs additionally gets a dense
     // column: one byte per doc holding its term frequency (0 = absent). Leaves on such terms skip
@@ -615,6 +693,15 @@ struct fg_batch {
     size_t out_sz = 0;
     uint32_t sub_k_stride = 0;
     bool sub_counts = false;
+    // lead-driven evaluation (fg_lead.cu): the default lowering
+    bool lead = false;
+    LQuery* l_queries = nullptr;
+    LLeaf* l_leaves = nullptr;
+    LItem* l_items = nullptr;
+    uint32_t* l_state = nullptr;   // [1 work | n_cursors | qtheta n_queries | qcount n_queries | qmatch n_queries]
+    uint32_t n_cursors = 0;
+    uint64_t partial_entries = 0;
+    size_t lsz[4] = {0, 0, 0, 0};
 };
 
 static double now_ms() {
@@ -638,6 +725,8 @@ extern "C" void fg_batch_release(fg_batch* b) {
         pool_free(c, b->d_stats, b->sz[5]); pool_free(c, b->d_qtheta, b->sz[6]);
         pool_free(c, b->d_out, b->out_sz);
         pinned_free(c, b->h_out, b->out_sz);
+        pool_free(c, b->l_queries, b->lsz[0]); pool_free(c, b->l_leaves, b->lsz[1]); pool_free(c, b->l_items, b->lsz[2]);
+        pool_free(c, b->l_state, b->lsz[3]);
     }
     for (auto& e : b->ev) if (e) cudaEventDestroy(e);
     if (b->ev_up) cudaEventDestroy(b->ev_up);
@@ -646,13 +735,322 @@ extern "C" void fg_batch_release(fg_batch* b) {
 }
 
 
+
+// ------------------------------------------------------------------------------------------
+// plan lowering for the lead-driven kernels (fg_lead.cu; the scheme is described in fg_internal.h)
+// ------------------------------------------------------------------------------------------
+static inline uint32_t host_sortable(float f) {
+    uint32_t b;
+    memcpy(&b, &f, 4);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+static int32_t prepare_lead(fg_index* ix, const fg_query_batch* qb, uint32_t prep_flags, fg_batch** out) {
+    fg_ctx* ctx = ix->ctx;
+    const bool use_cols = !(prep_flags & FG_PREP_NO_COLUMNS) && ix->n_cols && !ctx->env_no_columns;
+    const uint32_t PAR_BLOCKS = ctx->lead_par_blocks, MAX_PAR = ctx->lead_max_par, CHUNK = ctx->lead_chunk;
+    constexpr int MAXC = 40;
+    struct CRec { uint32_t occur, begin, count; uint64_t df; };
+    struct Part {
+        std::vector<LLeaf> leaves;
+        std::vector<LItem> items;       // cursor = index of the (query, lead) pair inside this part
+        std::vector<uint32_t> item_key; // sort key: lead index, then list length
+        std::vector<uint32_t> q_items;  // items per query of this part
+        uint32_t n_cursors = 0, kmax = 1;
+        uint64_t sum_k = 0;
+        int32_t rc = FG_OK;
+        std::string err;
+    };
+    std::vector<LQuery> lq(qb->n_queries);
+    auto lfail = [](Part& o, int32_t code, const char* fmt, ...) -> int32_t {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof(buf), fmt, ap);
+        va_end(ap);
+        o.rc = code;
+        o.err = buf;
+        return code;
+    };
+    const std::vector<float>& topbm = *ix->topbm;
+    const bool has_deletes = ix->dev.alive != nullptr;
+    auto lower_range = [&](uint32_t q_begin, uint32_t q_end, Part& o) -> int32_t {
+        LLeaf tmp[LMAX_LEAVES * 2];
+        uint32_t tdf[LMAX_LEAVES * 2];   // top table of each temp leaf: offset, count
+        uint32_t ttop[LMAX_LEAVES * 2], ttopn[LMAX_LEAVES * 2];
+        CRec crec[MAXC];
+        o.q_items.assign(q_end - q_begin, 0);
+        o.leaves.reserve((size_t)((uint64_t)qb->n_leaves * (q_end - q_begin) / std::max<uint32_t>(qb->n_queries, 1)) + 64);
+        for (uint32_t qi = q_begin; qi < q_end; qi++) {
+            const fg_query& q = qb->queries[qi];
+            LQuery& D = lq[qi];
+            memset(&D, 0, sizeof(D));
+            if (q.k == 0) return lfail(o, FG_ERR_INVALID, "query %u: k == 0 (TopDocs::with_limit requires limit >= 1)", qi);
+            if (q.k > 1024) return lfail(o, FG_ERR_UNSUPPORTED, "query %u: k = %u > 1024 not supported", qi, q.k);
+            if ((uint64_t)q.clause_begin + q.n_clauses > qb->n_clauses)
+                return lfail(o, FG_ERR_INVALID, "query %u: clause range out of bounds", qi);
+            o.kmax = std::max(o.kmax, q.k);
+            o.sum_k += q.k;
+            D.k = q.k;
+            D.leaf_begin = (uint32_t)o.leaves.size();
+            int nc = 0, nt = 0;
+            int must_idx[MAXC], n_must = 0, n_should = 0, n_not = 0;
+            float const_score = 0.f;
+            bool empty = false, has_all_only = false, positive = true;
+            for (uint32_t ci = 0; ci < q.n_clauses; ci++) {
+                const fg_clause& c = qb->clauses[q.clause_begin + ci];
+                if ((uint64_t)c.leaf_begin + c.n_leaves > qb->n_leaves)
+                    return lfail(o, FG_ERR_INVALID, "query %u: leaf range out of bounds", qi);
+                if (c.occur > FG_OCCUR_MUST_NOT) return lfail(o, FG_ERR_INVALID, "query %u: bad occur", qi);
+                CRec cr{c.occur, (uint32_t)nt, 0, 0};
+                bool all = false;
+                float all_boost = 0.f;
+                for (uint32_t li = 0; li < c.n_leaves; li++) {
+                    const fg_leaf& lf = qb->leaves[c.leaf_begin + li];
+                    if (lf.term_ord == FG_TERM_ALL) { all = true; all_boost += lf.boost; continue; }
+                    if (lf.term_ord == FG_TERM_MISSING) continue;
+                    if (lf.field >= ix->fields.size()) return lfail(o, FG_ERR_INVALID, "query %u: field %u out of range", qi, lf.field);
+                    const HostField& hf = ix->fields[lf.field];
+                    if (lf.term_ord >= hf.n_terms) return lfail(o, FG_ERR_INVALID, "query %u: term_ord out of range", qi);
+                    const TermInfo& ti = hf.terms[lf.term_ord];
+                    if (ti.df_global == 0 || ti.n_blocks == 0) continue;  // empty scorer (globally, or in this shard)
+                    if (nt >= LMAX_LEAVES * 2) return lfail(o, FG_ERR_UNSUPPORTED, "query %u: too many leaves", qi);
+                    LLeaf& L = tmp[nt];
+                    memset(&L, 0, sizeof(L));
+                    L.blk_begin = ti.blk_begin;
+                    L.n_blocks = ti.n_blocks;
+                    L.weight = lf.boost * ti.idf_w;
+                    L.cnorm = hf.cnorm;
+                    L.fn_field = (hf.flags & FG_FIELD_HAS_FIELDNORMS) ? (int32_t)lf.field : -1;
+                    L.df = ti.df_local;
+                    if (c.occur != FG_OCCUR_MUST_NOT) {
+                        if (!(L.weight >= 0.f)) positive = false;
+                        L.ub = L.weight * ti.max_factor;
+                    }
+                    if (use_cols && ti.col >= 0) L.col = ix->d_cols + (uint64_t)ti.col * ix->col_stride;
+                    ttop[nt] = ti.top_off;
+                    ttopn[nt] = ti.top_n;
+                    tdf[nt] = ti.df_local;
+                    nt++;
+                    cr.df += ti.df_local;
+                    cr.count++;
+                }
+                if (all) {
+                    if (c.occur == FG_OCCUR_MUST && cr.count == 0) { const_score += all_boost; has_all_only = true; continue; }
+                    return lfail(o, FG_ERR_UNSUPPORTED, "query %u: AllQuery leaf outside a Must clause is not supported", qi);
+                }
+                if (cr.count == 0) {
+                    if (c.occur == FG_OCCUR_MUST) empty = true;
+                    continue;
+                }
+                if (nc >= MAXC) return lfail(o, FG_ERR_UNSUPPORTED, "query %u: too many clauses", qi);
+                if (c.occur == FG_OCCUR_MUST) must_idx[n_must++] = nc;
+                else if (c.occur == FG_OCCUR_SHOULD) n_should++;
+                else n_not++;
+                crec[nc++] = cr;
+            }
+            D.const_score = const_score;
+            if (has_all_only && n_must == 0 && !empty) {
+                if (n_should == 0 && n_not == 0) {  // pure AllQuery: every alive doc, score = boost
+                    D.flags |= LQ_ALL;
+                    continue;
+                }
+                return lfail(o, FG_ERR_UNSUPPORTED, "query %u: AllQuery Must with only Should/MustNot siblings not supported", qi);
+            }
+            if (empty || (n_must == 0 && n_should == 0)) continue;
+            if (nt > LMAX_LEAVES) return lfail(o, FG_ERR_UNSUPPORTED, "query %u: %d live leaves > %d", qi, nt, LMAX_LEAVES);
+            // Must clauses by ascending Sum(df) = tantivy's Intersection order (stable insertion sort)
+            for (int i = 1; i < n_must; i++) {
+                const int x = must_idx[i];
+                int j = i - 1;
+                while (j >= 0 && crec[must_idx[j]].df > crec[x].df) { must_idx[j + 1] = must_idx[j]; j--; }
+                must_idx[j + 1] = x;
+            }
+            // ---- leads, by descending upper bound ----
+            int lead_src[LMAX_LEAVES], nl = 0;
+            if (n_must) {
+                const CRec& cr = crec[must_idx[0]];
+                for (uint32_t i = 0; i < cr.count; i++) lead_src[nl++] = (int)(cr.begin + i);
+            } else {
+                for (int ci = 0; ci < nc; ci++)
+                    if (crec[ci].occur == FG_OCCUR_SHOULD)
+                        for (uint32_t i = 0; i < crec[ci].count; i++) lead_src[nl++] = (int)(crec[ci].begin + i);
+            }
+            for (int i = 1; i < nl; i++) {
+                const int x = lead_src[i];
+                int j = i - 1;
+                while (j >= 0 && tmp[lead_src[j]].ub < tmp[x].ub) { lead_src[j + 1] = lead_src[j]; j--; }
+                lead_src[j + 1] = x;
+            }
+            const size_t l0 = o.leaves.size();
+            for (int i = 0; i < nl; i++) {
+                LLeaf L = tmp[lead_src[i]];
+                L.role = LR_LEAD;
+                o.leaves.push_back(L);
+            }
+            uint32_t n_req = 0, n_opt = 0;
+            for (int ci = 1; ci < n_must; ci++) {
+                const CRec& cr = crec[must_idx[ci]];
+                for (uint32_t i = 0; i < cr.count; i++) {
+                    LLeaf L = tmp[cr.begin + i];
+                    L.role = LR_REQ | ((uint32_t)ci << 8);
+                    o.leaves.push_back(L);
+                    n_req++;
+                }
+            }
+            if (n_must)
+                for (int ci = 0; ci < nc; ci++)
+                    if (crec[ci].occur == FG_OCCUR_SHOULD)
+                        for (uint32_t i = 0; i < crec[ci].count; i++) {
+                            LLeaf L = tmp[crec[ci].begin + i];
+                            L.role = LR_OPT;
+                            o.leaves.push_back(L);
+                            n_opt++;
+                        }
+            for (int ci = 0; ci < nc; ci++)
+                if (crec[ci].occur == FG_OCCUR_MUST_NOT)
+                    for (uint32_t i = 0; i < crec[ci].count; i++) {
+                        LLeaf L = tmp[crec[ci].begin + i];
+                        L.role = LR_NOT;
+                        L.ub = 0.f;
+                        o.leaves.push_back(L);
+                    }
+            D.n_leaves = (uint32_t)(o.leaves.size() - l0);
+            D.n_lead = (uint32_t)nl;
+            D.n_req = n_req;
+            D.n_opt = n_opt;
+            // rest of a lead = what a candidate of it can still collect: later leads + required + optional leaves
+            float tail = 0.f, total = 0.f;
+            for (uint32_t i = (uint32_t)nl; i < (uint32_t)nl + n_req + n_opt; i++) tail += o.leaves[l0 + i].ub;
+            total = tail;
+            for (int i = nl - 1; i >= 0; i--) {
+                o.leaves[l0 + i].rest = tail;
+                tail += o.leaves[l0 + i].ub;
+            }
+            total = tail;
+            D.slack = total * 1e-5f + 1e-30f;
+            if (positive) D.flags |= LQ_PRUNE;
+            // a lower bound of the k-th best score known before anything runs: the k-th largest block maximum of
+            // a lead of a pure union (k distinct docs reach it with that one leaf alone, the others only add)
+            if (positive && n_must == 0 && n_not == 0 && !has_deletes) {
+                float t0 = 0.f;
+                for (int i = 0; i < nl; i++) {
+                    const int sidx = lead_src[i];
+                    if (ttopn[sidx] >= q.k) t0 = std::max(t0, tmp[sidx].weight * topbm[ttop[sidx] + q.k - 1]);
+                }
+                if (t0 > 0.f) D.theta0 = host_sortable(t0);
+            }
+            // ---- work items: n_par copies per lead (one warp each) share a block cursor ----
+            uint32_t qitems = 0;
+            for (int i = 0; i < nl; i++) {
+                const uint32_t nb = o.leaves[l0 + i].n_blocks;
+                const uint32_t par = std::max<uint32_t>(1, std::min<uint32_t>(MAX_PAR, (nb + PAR_BLOCKS - 1) / PAR_BLOCKS));
+                const uint32_t lg = 31u - (uint32_t)__builtin_clz(nb | 1u);
+                for (uint32_t c = 0; c < par; c++) {
+                    o.items.push_back(LItem{qi, (uint32_t)i, o.n_cursors, CHUNK});
+                    o.item_key.push_back(std::min<uint32_t>((uint32_t)i, 15u) * 32u + (31u - lg));
+                }
+                o.n_cursors++;
+                qitems += par;
+            }
+            o.q_items[qi - q_begin] = qitems;
+        }
+        return FG_OK;
+    };
+    const int LT = (int)std::max<uint64_t>(1, std::min<uint64_t>({(uint64_t)HostPool::get().size(), 8, (uint64_t)qb->n_queries / 256 + 1}));
+    std::vector<Part> parts((size_t)LT);
+    HostPool::get().run(LT, [&](int t) {
+        lower_range((uint32_t)((uint64_t)qb->n_queries * t / LT), (uint32_t)((uint64_t)qb->n_queries * (t + 1) / LT), parts[t]);
+    });
+    for (auto& o : parts)
+        if (o.rc != FG_OK) return fail(o.rc, "%s", o.err.c_str());
+    // concatenate the parts: rebase leaf_begin / cursors, assign the partial regions
+    size_t nl_tot = 0, ni_tot = 0;
+    for (auto& o : parts) { nl_tot += o.leaves.size(); ni_tot += o.items.size(); }
+    std::vector<LLeaf> leaves;
+    leaves.reserve(nl_tot);
+    std::vector<LItem> items(ni_tot);
+    uint32_t kmax = 1, n_cursors = 0;
+    uint64_t sum_k = 0, part_entries = 0;
+    {
+        // counting sort of the items on (lead index, list length): every query's first lead is queued ahead of
+        // all second leads, and so on: a later (lower upper bound) lead mostly finds the threshold already set
+        uint32_t hist[16 * 32 + 1] = {0};
+        for (auto& o : parts)
+            for (uint32_t kx : o.item_key) hist[kx + 1]++;
+        for (int i = 0; i < 16 * 32; i++) hist[i + 1] += hist[i];
+        for (int t = 0; t < LT; t++) {
+            Part& o = parts[t];
+            const uint32_t lb = (uint32_t)leaves.size();
+            const uint32_t q0 = (uint32_t)((uint64_t)qb->n_queries * t / LT), q1 = (uint32_t)((uint64_t)qb->n_queries * (t + 1) / LT);
+            for (uint32_t qi = q0; qi < q1; qi++) {
+                LQuery& D = lq[qi];
+                D.leaf_begin += lb;
+                D.part_begin = (uint32_t)part_entries;
+                D.part_cap = o.q_items[qi - q0] * D.k;
+                part_entries += D.part_cap;
+            }
+            for (size_t i = 0; i < o.items.size(); i++) {
+                LItem it = o.items[i];
+                it.cursor += n_cursors;
+                items[hist[o.item_key[i]]++] = it;
+            }
+            leaves.insert(leaves.end(), o.leaves.begin(), o.leaves.end());
+            n_cursors += o.n_cursors;
+            kmax = std::max(kmax, o.kmax);
+            sum_k += o.sum_k;
+        }
+    }
+    if (part_entries > 0xFFFFFFF0ull) return fail(FG_ERR_UNSUPPORTED, "partial result lists exceed 2^32 entries");
+
+    CU(cudaSetDevice(ctx->device));
+    std::unique_ptr<fg_batch, void (*)(fg_batch*)> b(new fg_batch(), fg_batch_release);
+    b->ix = ix;
+    b->lead = true;
+    b->n_queries = qb->n_queries;
+    b->n_items = (uint32_t)items.size();
+    b->kcap = kmax;
+    b->ks = kmax <= 32 ? 1 : kmax <= 128 ? 4 : 32;
+    b->sum_k = sum_k;
+    b->n_cursors = n_cursors;
+    b->partial_entries = part_entries;
+    auto up = [&](const void* src, size_t bytes, void** dst, size_t* sz) -> int32_t {
+        *sz = std::max<size_t>(bytes, 16);
+        CU(pool_alloc(ctx, dst, *sz));
+        if (bytes) CU(cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, ctx->up));
+        return FG_OK;
+    };
+    int32_t rc;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    if ((rc = up(lq.data(), lq.size() * sizeof(LQuery), (void**)&b->l_queries, &b->lsz[0]))) return rc;
+    if ((rc = up(leaves.data(), leaves.size() * sizeof(LLeaf), (void**)&b->l_leaves, &b->lsz[1]))) return rc;
+    if ((rc = up(items.data(), items.size() * sizeof(LItem), (void**)&b->l_items, &b->lsz[2]))) return rc;
+    b->lsz[3] = ((size_t)1 + n_cursors + 3 * (size_t)b->n_queries) * 4 + 16;
+    CU(pool_alloc(ctx, (void**)&b->l_state, b->lsz[3]));
+    b->sz[3] = std::max<size_t>((size_t)part_entries * 8, 16);
+    CU(pool_alloc(ctx, (void**)&b->d_partial, b->sz[3]));
+    b->sz[5] = 16 * sizeof(unsigned long long);
+    CU(pool_alloc(ctx, (void**)&b->d_stats, b->sz[5]));
+    for (auto& e : b->ev) CU(cudaEventCreate(&e));
+    CU(cudaEventCreateWithFlags(&b->ev_up, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&b->ev_done, cudaEventDisableTiming));
+    CU(cudaEventRecord(b->ev_up, ctx->up));
+    CU(cudaStreamSynchronize(ctx->up));  // host vectors go out of scope (the compute stream is not touched)
+    *out = b.release();
+    return FG_OK;
+}
+
 extern "C" int32_t fg_batch_prepare(fg_index* ix, const fg_query_batch* qb, fg_batch** out) {
     return fg_batch_prepare_ex(ix, qb, 0, out);
 }
 
 extern "C" int32_t fg_batch_prepare_ex(fg_index* ix, const fg_query_batch* qb, uint32_t prep_flags, fg_batch** out) {
     if (!ix || !qb || !out) return fail(FG_ERR_INVALID, "fg_batch_prepare: NULL argument");
-    const bool use_cols = !(prep_flags & FG_PREP_NO_COLUMNS) && ix->n_cols && !getenv("FG_NO_COLUMNS");
+    *out = nullptr;
+    if (qb->n_queries && (!qb->queries || (qb->n_clauses && !qb->clauses) || (qb->n_leaves && !qb->leaves)))
+        return fail(FG_ERR_INVALID, "fg_batch_prepare: NULL arrays");
+    if (!(prep_flags & FG_PREP_LEGACY) && !ix->ctx->env_legacy) return prepare_lead(ix, qb, prep_flags, out);
+    const bool use_cols = !(prep_flags & FG_PREP_NO_COLUMNS) && ix->n_cols && !ix->ctx->env_no_columns;
     const uint64_t COL_COST_DIV = std::max<uint64_t>(1, env_u64("FG_COL_COST_DIV", 16));
     const uint64_t COL_COST_DIV_PHASES = std::max<uint64_t>(1, env_u64("FG_COL_COST_DIV_PHASES", 2));
     const uint64_t WINDOW_COST = env_u64("FG_WINDOW_COST", 4096);
@@ -1016,7 +1414,7 @@ extern "C" int32_t fg_batch_prepare_ex(fg_index* ix, const fg_query_batch* qb, u
     CU(cudaEventCreateWithFlags(&b->ev_done, cudaEventDisableTiming));
     CU(cudaEventRecord(b->ev_up, ctx->up));
     CU(cudaStreamSynchronize(ctx->up));  // host vectors go out of scope (the compute stream is not touched)
-    if (getenv("FG_TIMING"))
+    if (ctx->env_timing)
         fprintf(stderr, "[fg_batch_prepare] lowering %.2f ms, sort+upload %.2f ms (%zu items)\n", t_lower - t_begin, now_ms() - t_lower, items.size());
     *out = b.release();
     return FG_OK;
@@ -1033,6 +1431,52 @@ extern "C" int32_t fg_batch_execute(fg_batch* b, uint32_t flags, uint32_t k_stri
     cudaStream_t st = ctx->stream;
     CU(cudaStreamWaitEvent(st, b->ev_up, 0));
     CU(cudaMemsetAsync(b->d_stats, 0, 16 * sizeof(unsigned long long), st));
+    if (b->lead) {
+        if (flags & FG_EXEC_EXACT_ACCOUNTING)
+            return fail(FG_ERR_INVALID, "FG_EXEC_EXACT_ACCOUNTING needs a batch prepared with FG_PREP_LEGACY | FG_PREP_NO_COLUMNS");
+        LeadParams p{};
+        p.ix = ix->dev;
+        p.queries = b->l_queries;
+        p.leaves = b->l_leaves;
+        p.items = b->l_items;
+        p.n_items = b->n_items;
+        p.n_queries = b->n_queries;
+        p.work = b->l_state;
+        p.cursors = b->l_state + 1;
+        p.n_cursors = b->n_cursors;
+        p.qtheta = p.cursors + b->n_cursors;
+        p.qcount = p.qtheta + b->n_queries;
+        p.qmatch = p.qcount + b->n_queries;
+        p.partial = b->d_partial;
+        p.stats = b->d_stats;
+        p.match_bitmap = (uint32_t*)d_match_bitmap;
+        p.bitmap_words = (ix->n_docs + 31) / 32;
+        p.want_counts = d_match_count ? 1 : 0;
+        p.exhaustive = (d_match_count || d_match_bitmap || (flags & FG_EXEC_NO_PRUNE) || ctx->env_no_prune) ? 1 : 0;
+        p.acct = (flags & FG_EXEC_COUNTERS) ? 1 : 0;
+        CU(cudaEventRecord(b->ev[0], st));
+        launch_lead(p, b->ks, ctx->n_sms, st);
+        CU(cudaEventRecord(b->ev[1], st));
+        LeadMergeParams m{};
+        m.queries = b->l_queries;
+        m.n_queries = b->n_queries;
+        m.partial = b->d_partial;
+        m.qcount = p.qcount;
+        m.qmatch = p.qmatch;
+        m.k_stride = k_stride;
+        m.doc_base = ix->doc_base;
+        m.alive = ix->dev.alive;
+        m.n_docs = ix->n_docs;
+        m.n_alive = ix->dev.n_alive;
+        m.out_hits = d_hits;
+        m.out_n = (uint32_t*)d_n_hits;
+        m.out_count = (uint32_t*)d_match_count;
+        launch_lead_merge(m, b->ks, st);
+        CU(cudaEventRecord(b->ev[2], st));
+        b->n_launches = b->n_queries ? (b->n_items ? 3 : 2) : 0;
+        CU(cudaGetLastError());
+        return FG_OK;
+    }
     CU(cudaMemsetAsync(b->d_qtheta, 0, std::max<size_t>((size_t)b->n_queries * 4, 16), st));
     SearchParams p{};
     p.ix = ix->dev;
@@ -1051,8 +1495,8 @@ extern "C" int32_t fg_batch_execute(fg_batch* b, uint32_t flags, uint32_t k_stri
     p.want_counts = d_match_count ? 1 : 0;
     p.acct = (flags & (FG_EXEC_EXACT_ACCOUNTING | FG_EXEC_COUNTERS)) ? 1 : 0;
     p.qtheta = (flags & FG_EXEC_DETERMINISTIC) ? nullptr : b->d_qtheta;
-    p.no_prune = ((flags & FG_EXEC_NO_PRUNE) || getenv("FG_NO_PRUNE")) ? 1 : 0;
-    p.prof = getenv("FG_PROF") ? b->d_stats + 8 : nullptr;
+    p.no_prune = ((flags & FG_EXEC_NO_PRUNE) || ctx->env_no_prune) ? 1 : 0;
+    p.prof = ctx->env_prof ? b->d_stats + 8 : nullptr;
     CU(cudaEventRecord(b->ev[0], st));
     {
         // fork: class 0 on the main stream, classes 1..3 on side streams, join before the merge
@@ -1094,13 +1538,13 @@ extern "C" int32_t fg_batch_get_stats(fg_batch* b, fg_batch_stats* out) {
     if (!b || !out) return fail(FG_ERR_INVALID, "NULL argument");
     fg_ctx* ctx = b->ix->ctx;
     CU(cudaSetDevice(ctx->device));
-    unsigned long long h[5];
+    unsigned long long h[8];
     {
         std::lock_guard<std::mutex> g(ctx->mu);
         CU(cudaStreamSynchronize(ctx->stream));
         CU(cudaMemcpy(h, b->d_stats, sizeof(h), cudaMemcpyDeviceToHost));
     }
-    if (getenv("FG_PROF")) {
+    if (ctx->env_prof && !b->lead) {
         unsigned long long pr[8];
         cudaMemcpy(pr, b->d_stats + 8, sizeof(pr), cudaMemcpyDeviceToHost);
         const double ni = b->n_items ? (double)b->n_items : 1.0;
@@ -1112,6 +1556,9 @@ extern "C" int32_t fg_batch_get_stats(fg_batch* b, fg_batch_stats* out) {
     out->scored_postings = h[2];
     out->colscan_chunks = h[3];
     out->colscan_chunks_skipped = h[4];
+    out->bytes_meta = b->lead ? h[5] : 0;
+    out->lead_blocks = b->lead ? h[6] : 0;
+    out->lead_blocks_seen = b->lead ? h[7] : 0;
     out->n_work_items = b->n_items;
     out->n_launches = b->n_launches;
     out->n_queries = b->n_queries;
@@ -1127,7 +1574,7 @@ extern "C" int32_t fg_batch_get_stats(fg_batch* b, fg_batch_stats* out) {
 extern "C" int32_t fg_search_batch(fg_index* ix, const fg_query_batch* qb, uint32_t k_stride,
                                    fg_hit* out_hits, uint32_t* out_n_hits, uint32_t* out_match_count) {
     if (!ix || !qb || !out_hits || !out_n_hits) return fail(FG_ERR_INVALID, "fg_search_batch: NULL argument");
-    const bool timing = getenv("FG_TIMING") != nullptr;
+    const bool timing = ix->ctx->env_timing;
     const double t0 = now_ms();
     fg_batch* b = nullptr;
     int32_t rc = fg_batch_prepare(ix, qb, &b);

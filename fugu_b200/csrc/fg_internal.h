@@ -87,6 +87,7 @@ struct DevItem {
 
 struct DevIndex {
     const uint4* skip;
+    const float* bmax;   // per block: max over its postings of tf / (tf + norm(doc)) (block-max metadata)
     const uint8_t* blk;
     const uint8_t* fnorm[MAX_FIELDS];
     const float* cache;  // [MAX_FIELDS][256]
@@ -155,5 +156,92 @@ void launch_merge_gathered(const void* hits, const uint32_t* n, uint32_t n_ranks
                            uint32_t k, uint32_t k_stride, void* out_hits, uint32_t* out_n, int ks,
                            void* stream);
 int search_smem_bytes(int ks, bool pure);
+
+// ---- lead-driven evaluation (fg_lead.cu) ---------------------------------------------------------
+// A query is answered by walking some of its leaves as LEADS, block after block, and looking every
+// candidate doc of a lead block up in the query's other leaves (dense tf column byte, or skip-table
+// gallop + block decode). Leaves of a query are stored [leads | required | optional | excluded]:
+//   pure union      : every Should leaf is a lead, by descending upper bound ub = weight * max tf factor;
+//                     a candidate of lead i that also occurs in a lead j < i is dropped (lead j scores it)
+//   plan with Must  : the leaves of the Must clause with the smallest document frequency are the leads,
+//                     the other Must clauses are required lookups (ascending frequency), Should leaves
+//                     optional lookups, MustNot leaves excluding lookups.
+// MaxScore / block-max pruning (TopDocs form only; results are identical to exhaustive evaluation): a
+// lead is not walked at all once ub + rest < theta (theta = k-th best score known for the query), a
+// block is decoded only if weight * bmax[block] + rest >= theta, a candidate is looked up only while
+// its partial score + the upper bounds of the leaves not applied yet >= theta.
+constexpr int LMAX_LEAVES = 32;   // live leaves per query (16 words x [text, name])
+enum : uint32_t { LR_LEAD = 0, LR_REQ = 1, LR_OPT = 2, LR_NOT = 3 };
+struct LLeaf {
+    uint32_t blk_begin, n_blocks;
+    float weight;        // boost * idf * (1 + K1), GLOBAL statistics
+    float cnorm;         // constant BM25 norm of a field without fieldnorms
+    int32_t fn_field;    // fieldnorm field or -1
+    float ub;            // upper bound of this leaf's score contribution (0 for LR_NOT)
+    float rest;          // LR_LEAD: sum of ub over the later leads, required and optional leaves
+    uint32_t role;       // LR_* | clause index << 8 (required leaves of one Must clause share the index)
+    const uint8_t* col;  // dense tf column or nullptr
+    uint32_t df;         // local document frequency
+    uint32_t pad;
+};
+static_assert(sizeof(LLeaf) == 48, "LLeaf is uploaded as a flat array");
+constexpr uint32_t LQ_ALL = 1;    // pure AllQuery: first k alive docs, score = const_score
+constexpr uint32_t LQ_PRUNE = 2;  // every scoring weight is > 0: the upper bounds hold
+struct LQuery {
+    uint32_t leaf_begin, n_leaves, n_lead, n_req, n_opt;
+    uint32_t k;
+    uint32_t flags;
+    float const_score;   // Must AllQuery scores
+    float slack;         // added to an upper bound before it is compared with theta (f32 summation order)
+    uint32_t part_begin; // this query's region of the partial array
+    uint32_t part_cap;
+    uint32_t theta0;     // sortable f32 lower bound of the k-th best score known at lowering time, 0 = none
+};
+static_assert(sizeof(LQuery) == 48, "LQuery is uploaded as a flat array");
+struct LItem {
+    uint32_t query;
+    uint32_t lead;    // lead leaf (index inside the query) this item walks
+    uint32_t cursor;  // block cursor shared by the copies of this item (each copy is one warp)
+    uint32_t chunk;   // blocks claimed per step
+};
+struct LeadParams {
+    DevIndex ix;
+    const LQuery* queries;
+    const LLeaf* leaves;
+    const LItem* items;
+    uint32_t n_items;
+    uint32_t n_queries;
+    uint32_t* work;            // [1] next item (dynamic queue: items start in array order)
+    uint32_t* cursors;         // [n_cursors] next block of a (query, lead) pair
+    uint32_t n_cursors;
+    uint32_t* qtheta;          // [n_queries] sortable f32 threshold shared by all warps of a query
+    uint32_t* qcount;          // [n_queries] entries appended to the query's partial region
+    uint32_t* qmatch;          // [n_queries] matching docs (exhaustive form)
+    uint64_t* partial;
+    unsigned long long* stats; // [8]
+    uint32_t* match_bitmap;
+    uint32_t bitmap_words;
+    uint32_t exhaustive;       // visit every posting (match counts / bitmaps wanted, or pruning switched off)
+    uint32_t want_counts;
+    uint32_t acct;
+};
+struct LeadMergeParams {
+    const LQuery* queries;
+    uint32_t n_queries;
+    const uint64_t* partial;
+    const uint32_t* qcount;
+    const uint32_t* qmatch;
+    uint32_t k_stride;
+    uint32_t doc_base;
+    const uint32_t* alive;
+    uint32_t n_docs, n_alive;
+    void* out_hits;
+    uint32_t* out_n;
+    uint32_t* out_count;
+};
+void launch_lead(const LeadParams& p, int ks, int n_sms, void* stream);
+void launch_lead_merge(const LeadMergeParams& p, int ks, void* stream);
+// block-max metadata of the blocks [b0, b1) of one field (upload time)
+void launch_blockmax(const DevIndex& ix, uint32_t b0, uint32_t b1, int fn_field, float cnorm, float* bmax, void* stream);
 
 }  // namespace fg

@@ -1,0 +1,582 @@
+// Lead-driven evaluation of the fugu query hot path on sm_100a: what tantivy does inside
+// `searcher.search(&q, &TopDocs::with_limit(k))` (/root/reference/src/db/search.rs:162) -- posting
+// decode, Intersection / Union / RequiredOptional / Exclude, Bm25Weight, TopDocs with block-max pruning
+//  -- restructured for a GPU:
+//
+//   * every warp is autonomous: it takes work items from a global queue, walks the 128-posting blocks
+//     of ONE lead leaf of ONE query, and keeps its own top-k queue in registers. No CTA barriers, no
+//     shared accumulators, no atomics on scores: a document's score is summed by one lane, in leaf
+//     order, so results are bit-reproducible.
+//   * a lead block is decoded by the whole warp (4 postings per lane, warp prefix sum), its candidates
+//     are compacted and looked up in the query's other leaves: one byte load from a dense tf column, or
+//     a warp-cooperative gallop over the 16-byte skip entries (32 entries per step, ballot) followed by
+//     a decode of the target block into shared memory and a binary search per candidate.
+//   * MaxScore / block-max pruning (fg_internal.h): whole leads, blocks and candidates are skipped once
+//     the query's k-th best score (shared by all warps of the query through one global word) exceeds
+//     what they can still reach. Pruning never changes the result; it is off when the caller wants match
+//     counts or the matched doc-id set.
+#include <fg_ptx.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "fg_device.h"
+#include "fg_internal.h"
+
+namespace fg {
+
+using namespace dev;
+
+namespace {
+
+constexpr int LNT = 256;      // threads per CTA
+constexpr int LNW = LNT / 32; // warps per CTA
+constexpr int LC = 8;         // decoded lookup blocks cached per warp
+
+struct WarpShared {
+    LLeaf leaf[LMAX_LEAVES];
+    uint32_t cur[LMAX_LEAVES];   // per leaf: first block that can still hold a candidate of this item
+    uint32_t ctag[LC];           // global block index of the decoded block in cdocs[slot], EMPTY = none
+    uint32_t cdocs[LC][BLOCK];   // doc ids of a decoded lookup block, padded with 0xFFFFFFFF
+    uint32_t cand_doc[BLOCK];    // compacted candidates of the current lead block, ascending
+    uint32_t cand_val[BLOCK];    // their lead score (f32 bits), or the lead tf while required clauses come first
+};
+struct LeadShared {
+    float cache[MAX_FIELDS * 256];  // BM25 norm caches K1*(1-B+B*dl/avg) of every field, by fieldnorm id
+    WarpShared w[LNW];
+};
+
+// per-warp byte / posting counters (FG_EXEC_COUNTERS)
+struct Acct {
+    unsigned long long block_bytes = 0;   // payload + 16 B skip entry of every block decoded (lead or lookup)
+    unsigned long long meta_bytes = 0;    // block-max words and skip entries read while skipping
+    unsigned long long gathers = 0;       // 1-byte gathers: fieldnorm ids, column bytes, alive bits
+    unsigned long long lead_blocks = 0, lead_blocks_seen = 0;
+};
+
+// First block index in [from, n) whose last_doc >= target; n if there is none. Warp-collective
+// (uniform arguments): the next 32 skip entries first (the common case while candidates and blocks
+// advance together), then a 32-ary search over the rest of the list.
+__device__ __forceinline__ uint32_t seek(const uint4* __restrict__ sk, uint32_t n, uint32_t from, uint32_t target,
+                                         int lane, bool acct, Acct& A) {
+    if (from >= n) return n;
+    {
+        const uint32_t i = from + lane;
+        const bool ge = i >= n || __ldg(&sk[i].x) >= target;
+        const unsigned m = __ballot_sync(FULL, ge);
+        if (acct) A.meta_bytes += 4u * 32u;
+        if (m) return min(from + (uint32_t)__ffs(m) - 1u, n);
+    }
+    uint32_t lo = from + 32u, hi = n;  // blocks below lo end before target; block hi (if < n) does not
+    while (hi - lo > 32u) {
+        const uint32_t step = (hi - lo + 31u) / 32u;
+        const uint32_t i = lo + ((uint32_t)lane + 1u) * step - 1u;
+        const bool ge = i >= hi || __ldg(&sk[i].x) >= target;
+        const unsigned m = __ballot_sync(FULL, ge);
+        if (acct) A.meta_bytes += 4u * 32u;
+        if (!m) return hi;  // lane 31 probed block hi - 1 or beyond
+        const uint32_t f = (uint32_t)__ffs(m) - 1u;
+        const uint32_t nhi = min(lo + (f + 1u) * step - 1u, hi);
+        lo = lo + f * step;
+        hi = nhi;
+    }
+    const uint32_t i = lo + lane;
+    const bool ge = i >= hi || __ldg(&sk[i].x) >= target;
+    const unsigned m = __ballot_sync(FULL, ge);
+    if (acct) A.meta_bytes += 4u * 32u;
+    return m ? min(lo + (uint32_t)__ffs(m) - 1u, hi) : hi;
+}
+
+// tf of posting `pos` of the block described by skip entry e
+__device__ __forceinline__ uint32_t extract_tf(const uint8_t* __restrict__ blk, const uint4 e, uint32_t pos) {
+    const uint32_t bd = e.w & 63u, bt = (e.w >> 6) & 63u;
+    if (bt == 0) return 1u;
+    const uint32_t* wt = reinterpret_cast<const uint32_t*>(blk + (size_t)e.z * 16u) + 4u * bd;
+    const uint32_t bit = pos * bt, wi = bit >> 5, sh = bit & 31u;
+    const uint32_t lo = __ldg(wt + wi), hi = __ldg(wt + wi + 1);
+    const uint32_t m = bt >= 32u ? 0xFFFFFFFFu : ((1u << bt) - 1u);
+    return (__funnelshift_r(lo, hi, sh) & m) + 1u;
+}
+
+// doc ids of block (L, b) in the warp's lookup cache (decoded on a miss); 128 entries, ascending,
+// padded with 0xFFFFFFFF
+__device__ __forceinline__ const uint32_t* cached_block(const uint8_t* __restrict__ blk, WarpShared& W, int j,
+                                                        uint32_t gblock, const uint4 e, int lane, bool acct, Acct& A) {
+    const int slot = j & (LC - 1);
+    uint32_t* cd = W.cdocs[slot];
+    if (W.ctag[slot] != gblock) {  // uniform
+        const uint32_t bd = e.w & 63u, n = ((e.w >> 12) & 127u) + 1u;
+        const uint32_t* wd = reinterpret_cast<const uint32_t*>(blk + (size_t)e.z * 16u);
+        uint32_t g[4];
+        unpack4(wd, lane, bd, g);
+        g[1] += g[0]; g[2] += g[1]; g[3] += g[2];
+        const uint32_t off = warp_excl_scan(g[3], lane) + e.y + 4u * lane;
+        uint4 d;
+        d.x = 4u * lane + 0u < n ? off + g[0] + 0u : 0xFFFFFFFFu;
+        d.y = 4u * lane + 1u < n ? off + g[1] + 1u : 0xFFFFFFFFu;
+        d.z = 4u * lane + 2u < n ? off + g[2] + 2u : 0xFFFFFFFFu;
+        d.w = 4u * lane + 3u < n ? off + g[3] + 3u : 0xFFFFFFFFu;
+        __syncwarp();  // earlier searches in this slot are done
+        reinterpret_cast<uint4*>(cd)[lane] = d;
+        if (lane == 0) W.ctag[slot] = gblock;
+        __syncwarp();
+        if (acct) A.block_bytes += ((n * bd + 7u) >> 3) + 16u;
+    }
+    return cd;
+}
+
+// Term frequency of doc c in leaf L (0 = absent) for the lanes with `live`; candidates ascend with the
+// lane index. Warp-collective. need_tf = false: presence only (returns 1).
+__device__ __forceinline__ uint32_t probe(const LeadParams& p, WarpShared& W, int j, const LLeaf& L, uint32_t c,
+                                          bool live, bool need_tf, int lane, Acct& A) {
+    const unsigned m = __ballot_sync(FULL, live);
+    if (!m) return 0u;
+    const bool acct = p.acct != 0;
+    const uint4* __restrict__ sk = p.ix.skip + L.blk_begin;
+    const uint32_t cmin = __shfl_sync(FULL, c, __ffs(m) - 1), cmax = __shfl_sync(FULL, c, 31 - __clz((int)m));
+    uint32_t b = seek(sk, L.n_blocks, W.cur[j], cmin, lane, acct, A);
+    __syncwarp();
+    if (lane == 0) W.cur[j] = b;
+    __syncwarp();
+    uint32_t tf = 0u;
+    bool pend = live;
+    while (b < L.n_blocks) {
+        const uint4 e = __ldg(&sk[b]);
+        if (acct) A.meta_bytes += 16u;
+#ifdef FG_DEBUG_LEAD
+        if (lane == 0) printf("  probe leaf %d (blk_begin %u) b=%u e=[%u..%u] cmin=%u cmax=%u m=%08x\n", j, L.blk_begin, b, e.y, e.x, cmin, cmax, m);
+#endif
+        if (e.y > cmax) break;  // the block starts behind the last candidate
+        const bool inb = pend && c >= e.y && c <= e.x;
+        if (__any_sync(FULL, inb)) {
+            const uint32_t* cd = cached_block(p.ix.blk, W, j, L.blk_begin + b, e, lane, acct, A);
+            uint32_t pos = 0u;  // entries < c among the first 127
+#pragma unroll
+            for (uint32_t s = 64u; s; s >>= 1)
+                if (inb && cd[pos + s - 1u] < c) pos += s;
+#ifdef FG_DEBUG_LEAD
+            if (inb) printf("    lane %d c=%u pos=%u cd[pos]=%u\n", lane, c, pos, cd[pos]);
+#endif
+            if (inb && cd[pos] == c) {
+                tf = need_tf ? extract_tf(p.ix.blk, e, pos) : 1u;
+                if (acct && need_tf) A.block_bytes += 8u;
+            }
+        }
+        pend = pend && c > e.x;
+        const unsigned mp = __ballot_sync(FULL, pend);
+        if (!mp) break;
+        const uint32_t cn = __shfl_sync(FULL, c, __ffs(mp) - 1);
+        b = seek(sk, L.n_blocks, b + 1u, cn, lane, acct, A);
+    }
+    return tf;
+}
+
+template <int KS>
+__device__ __forceinline__ void run_item(const LeadParams& p, const LeadShared& S, WarpShared& W, const LItem item, int lane) {
+    const LQuery q = p.queries[item.query];
+    __syncwarp();
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(p.leaves + q.leaf_begin);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(W.leaf);
+        for (uint32_t i = lane; i < q.n_leaves * (uint32_t)(sizeof(LLeaf) / 4); i += 32) dst[i] = __ldg(src + i);
+        W.cur[lane] = 0u;
+        if (lane < LC) W.ctag[lane] = EMPTY;
+    }
+    __syncwarp();
+#ifdef FG_DEBUG_LEAD
+    if (lane == 0) printf("item q=%u lead=%u cursor=%u nleaves=%u leaf_begin=%u part_begin=%u L0.blk=%u L0.nb=%u L1.blk=%u L1.nb=%u\n", item.query, item.lead, item.cursor, q.n_leaves, q.leaf_begin, q.part_begin, W.leaf[0].blk_begin, W.leaf[0].n_blocks, W.leaf[1].blk_begin, W.leaf[1].n_blocks);
+#endif
+    const int k = (int)q.k;
+    const bool prune = !p.exhaustive && (q.flags & LQ_PRUNE);
+    const bool acct = p.acct != 0;
+    const LLeaf LD = W.leaf[item.lead];
+    const int n_lead = (int)q.n_lead, n_req = (int)q.n_req, n_opt = (int)q.n_opt, n_leaves = (int)q.n_leaves;
+    const int lead = (int)item.lead;
+    const bool has_req = n_req != 0;
+    const uint4* __restrict__ sk = p.ix.skip + LD.blk_begin;
+    const float* __restrict__ bmx = p.ix.bmax + LD.blk_begin;
+    const float slack = q.slack;
+    const float rest_s = LD.rest + slack;
+    const unsigned lt = (1u << lane) - 1u;
+    Acct A;
+
+    WarpTopK<KS> tk;
+    tk.init();
+    float theta = -INFINITY;  // a candidate needs score >= theta (ties are decided by the doc id in the queue)
+    uint32_t pub = 0u;        // sortable threshold this warp has seen or published
+    uint32_t n_match = 0u;
+
+    auto pull = [&]() {
+        if (prune) {
+            const uint32_t g = __ldcg(p.qtheta + item.query);
+            if (g > pub) {
+                pub = g;
+                theta = fmaxf(theta, unsortable(g));
+            }
+        }
+    };
+    auto norm_of = [&](const LLeaf& L, uint32_t c) -> float {
+        return L.fn_field >= 0 ? S.cache[L.fn_field * 256 + (int)__ldg(p.ix.fnorm[L.fn_field] + c)] : L.cnorm;
+    };
+    auto lookup = [&](int j, const LLeaf& L, uint32_t c, bool live, bool need_tf) -> uint32_t {
+        if (L.col) {
+            if (acct) A.gathers += (unsigned long long)__popc(__ballot_sync(FULL, live));
+            return live ? (uint32_t)__ldg(L.col + c) : 0u;
+        }
+        return probe(p, W, j, L, c, live, need_tf, lane, A);
+    };
+
+    // one round of up to 32 candidates, one per lane, ascending: c = doc, v = lead score bits or lead tf
+    auto evaluate = [&](bool live, uint32_t c, uint32_t v) {
+        float sc, rem = LD.rest;
+        if (has_req) {
+            sc = 0.f;
+            bool found = false;
+            uint32_t clause = W.leaf[n_lead].role >> 8;
+            for (int j = n_lead; j < n_lead + n_req; j++) {
+                const LLeaf& L = W.leaf[j];
+                const uint32_t cl = L.role >> 8;
+                if (cl != clause) {
+                    live = live && found;
+                    found = false;
+                    clause = cl;
+                    if (!__any_sync(FULL, live)) return;
+                }
+                const uint32_t tf = lookup(j, L, c, live, true);
+                if (tf) {
+                    sc += L.weight * tf_factor((float)tf, norm_of(L, c));
+                    found = true;
+                }
+                rem -= L.ub;
+            }
+            live = live && found;
+            if (!__any_sync(FULL, live)) return;
+            if (live) sc += LD.weight * tf_factor((float)v, norm_of(LD, c));
+            if (acct) A.gathers += (unsigned long long)__popc(__ballot_sync(FULL, live));
+            if (prune) live = live && (sc + rem + slack >= theta);
+        } else {
+            sc = __uint_as_float(v);
+        }
+        // a candidate that also occurs in an earlier lead was (or will be) scored by that lead's items
+        for (int j = 0; j < lead; j++) {
+            if (!__any_sync(FULL, live)) return;
+            const uint32_t tf = lookup(j, W.leaf[j], c, live, false);
+            live = live && tf == 0u;
+        }
+        // later leads, then optional leaves, add their scores
+        for (int j = lead + 1; j < n_lead + n_req + n_opt; j++) {
+            if (j == n_lead) {
+                j += n_req;
+                if (j >= n_lead + n_req + n_opt) break;
+            }
+            if (!__any_sync(FULL, live)) return;
+            const LLeaf& L = W.leaf[j];
+            const uint32_t tf = lookup(j, L, c, live, true);
+            if (tf) sc += L.weight * tf_factor((float)tf, norm_of(L, c));
+            rem -= L.ub;
+            if (prune) live = live && (sc + rem + slack >= theta);
+        }
+        for (int j = n_lead + n_req + n_opt; j < n_leaves; j++) {
+            if (!__any_sync(FULL, live)) return;
+            const uint32_t tf = lookup(j, W.leaf[j], c, live, false);
+            live = live && tf == 0u;
+        }
+        if (p.ix.alive) live = live && ((__ldg(p.ix.alive + (live ? (c >> 5) : 0u)) >> (c & 31u)) & 1u);
+        const unsigned mm = __ballot_sync(FULL, live);
+        if (!mm) return;
+        sc += q.const_score;
+        if (p.exhaustive) {
+            n_match += (uint32_t)__popc(mm);
+            if (p.match_bitmap && live)
+                atomicOr(p.match_bitmap + (size_t)item.query * p.bitmap_words + (c >> 5), 1u << (c & 31u));
+        }
+#ifdef FG_DEBUG_LEAD
+        if (live) printf("    q=%u offer doc %u score %f (lane %d)\n", item.query, c, sc, lane);
+#endif
+        tk.offer(live, make_key(sc, c), k, lane);
+        if (prune && tk.theta) {
+            const uint32_t own = (uint32_t)(tk.theta >> 32);
+            if (own > pub) {
+                pub = own;
+                theta = fmaxf(theta, unsortable(own));
+                if (lane == 0) atomicMax(p.qtheta + item.query, own);
+            }
+        }
+    };
+
+    auto process_block = [&](uint32_t b) {
+        const uint4 e = __ldg(&sk[b]);
+        const uint32_t bd = e.w & 63u, bt = (e.w >> 6) & 63u, n = ((e.w >> 12) & 127u) + 1u;
+        const uint32_t* wd = reinterpret_cast<const uint32_t*>(p.ix.blk + (size_t)e.z * 16u);
+        uint32_t g[4], t[4];
+        unpack4(wd, lane, bd, g);
+        unpack4(wd + 4 * bd, lane, bt, t);
+        g[1] += g[0]; g[2] += g[1]; g[3] += g[2];
+        const uint32_t off = warp_excl_scan(g[3], lane) + e.y + 4u * lane;
+        uint32_t d[4], val[4];
+        bool ok[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            d[j] = off + g[j] + (uint32_t)j;
+            ok[j] = 4u * lane + (uint32_t)j < n;
+        }
+        if (acct) {
+            A.block_bytes += ((n * bd + 7u) >> 3) + ((n * bt + 7u) >> 3) + 16u;
+            A.lead_blocks++;
+        }
+        if (!has_req) {
+            uint32_t id[4] = {0u, 0u, 0u, 0u};
+            if (LD.fn_field >= 0) {
+                const uint8_t* __restrict__ fn = p.ix.fnorm[LD.fn_field];
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    if (ok[j]) id[j] = __ldg(fn + d[j]);
+                if (acct) A.gathers += n;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const float nrm = LD.fn_field >= 0 ? S.cache[LD.fn_field * 256 + (int)id[j]] : LD.cnorm;
+                const float s = LD.weight * tf_factor((float)(t[j] + 1u), nrm);
+                if (prune) ok[j] = ok[j] && (s + rest_s >= theta);
+                val[j] = __float_as_uint(s);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; j++) val[j] = t[j] + 1u;
+        }
+        const unsigned m0 = __ballot_sync(FULL, ok[0]), m1 = __ballot_sync(FULL, ok[1]), m2 = __ballot_sync(FULL, ok[2]),
+                       m3 = __ballot_sync(FULL, ok[3]);
+        const uint32_t total = (uint32_t)(__popc(m0) + __popc(m1) + __popc(m2) + __popc(m3));
+        if (!total) return;
+        uint32_t pos = (uint32_t)(__popc(m0 & lt) + __popc(m1 & lt) + __popc(m2 & lt) + __popc(m3 & lt));
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (ok[j]) {
+                W.cand_doc[pos] = d[j];
+                W.cand_val[pos] = val[j];
+                pos++;
+            }
+        __syncwarp();
+        for (uint32_t r = 0; r < total; r += 32u) {
+            const bool live = r + lane < total;
+            const uint32_t c = live ? W.cand_doc[r + lane] : 0xFFFFFFFFu;
+            const uint32_t v = live ? W.cand_val[r + lane] : 0u;
+            evaluate(live, c, v);
+        }
+    };
+
+    pull();
+    bool dead = prune && LD.ub + rest_s < theta;  // this lead cannot contribute a hit any more
+    while (!dead) {
+        uint32_t b0 = 0u;
+        if (lane == 0) b0 = atomicAdd(p.cursors + item.cursor, item.chunk);
+        b0 = __shfl_sync(FULL, b0, 0);
+        if (b0 >= LD.n_blocks) break;
+        const uint32_t b1 = min(b0 + item.chunk, LD.n_blocks);
+        for (uint32_t g0 = b0; g0 < b1 && !dead; g0 += 32u) {
+            pull();
+            if (prune && LD.ub + rest_s < theta) {
+                dead = true;
+                break;
+            }
+            const uint32_t b = g0 + lane;
+            float bound = INFINITY;
+            if (prune && b < b1) bound = LD.weight * __ldg(bmx + b) + rest_s;
+            if (acct) {
+                A.lead_blocks_seen += min(32u, b1 - g0);
+                if (prune) A.meta_bytes += 4u * min(32u, b1 - g0);
+            }
+            unsigned m = __ballot_sync(FULL, b < b1 && bound >= theta);
+            while (m) {
+                const int src = __ffs(m) - 1;
+                m &= m - 1;
+                process_block(g0 + (uint32_t)src);
+                if (prune && m) m &= __ballot_sync(FULL, bound >= theta);  // the threshold may have risen
+            }
+        }
+    }
+
+    // append this warp's queue to the query's region of the partial array
+    {
+        // (the queue is sorted best first; ranks >= k are scratch)
+        uint32_t nz = 0u;
+#pragma unroll
+        for (int s = 0; s < KS; s++) nz += (uint32_t)__popc(__ballot_sync(FULL, tk.q[s] != 0 && s * 32 + lane < k));
+        if (nz) {
+            uint32_t base = 0u;
+            if (lane == 0) base = atomicAdd(p.qcount + item.query, nz);
+            base = __shfl_sync(FULL, base, 0) + q.part_begin;
+#pragma unroll
+            for (int s = 0; s < KS; s++) {
+                const bool wr = tk.q[s] != 0 && s * 32 + lane < k;
+                const unsigned mk = __ballot_sync(FULL, wr);
+                if (wr) p.partial[base + (uint32_t)__popc(mk & lt)] = tk.q[s];
+                base += (uint32_t)__popc(mk);
+            }
+        }
+        if (lane == 0) {
+            if (n_match) atomicAdd(p.qmatch + item.query, n_match);
+            if (acct && p.stats) {
+                atomicAdd(p.stats + 0, A.block_bytes);
+                atomicAdd(p.stats + 2, A.gathers);
+                atomicAdd(p.stats + 5, A.meta_bytes);
+                atomicAdd(p.stats + 6, A.lead_blocks);
+                atomicAdd(p.stats + 7, A.lead_blocks_seen);
+            }
+        }
+    }
+}
+
+template <int KS>
+__global__ void __launch_bounds__(LNT, KS <= 4 ? 3 : 1) lead_kernel(const LeadParams p) {
+    FG_DYN_SMEM(smem);
+    LeadShared& S = *reinterpret_cast<LeadShared*>(smem);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < MAX_FIELDS * 256; i += LNT) S.cache[i] = __ldg(p.ix.cache + i);
+    __syncthreads();
+    WarpShared& W = S.w[warp];
+    while (true) {
+        uint32_t it = 0u;
+        if (lane == 0) it = atomicAdd(p.work, 1u);
+        it = __shfl_sync(FULL, it, 0);
+        if (it >= p.n_items) break;
+        run_item<KS>(p, S, W, p.items[it], lane);
+    }
+}
+
+// resets the per-execution device state of a prepared batch
+__global__ void lead_init_kernel(const LeadParams p) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) *p.work = 0u;
+    if (i < p.n_cursors) p.cursors[i] = 0u;
+    if (i < p.n_queries) {
+        p.qtheta[i] = p.exhaustive ? 0u : p.queries[i].theta0;
+        p.qcount[i] = 0u;
+        p.qmatch[i] = 0u;
+    }
+}
+
+// one warp per query: the k best of the entries the lead warps appended
+template <int KS>
+__global__ void __launch_bounds__(128) lead_merge_kernel(const LeadMergeParams p) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t qi = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (qi >= p.n_queries) return;
+    const LQuery q = p.queries[qi];
+    const int k = (int)q.k;
+    uint2* out = reinterpret_cast<uint2*>(p.out_hits) + (size_t)qi * p.k_stride;
+    if (q.flags & LQ_ALL) {  // AllQuery: the first k alive docs (every score equals const_score)
+        uint32_t found = 0;
+        for (uint32_t base = 0; base < p.n_docs && found < (uint32_t)k; base += 32) {
+            const uint32_t d = base + lane;
+            const bool al = d < p.n_docs && (!p.alive || ((p.alive[d >> 5] >> (d & 31)) & 1u));
+            const unsigned m = __ballot_sync(FULL, al);
+            const uint32_t r = found + __popc(m & ((1u << lane) - 1u));
+            if (al && r < (uint32_t)k && r < p.k_stride) out[r] = make_uint2(__float_as_uint(q.const_score), d + p.doc_base);
+            found += __popc(m);
+        }
+        const uint32_t nh_all = min(min(found, (uint32_t)k), p.k_stride);
+        for (uint32_t r = nh_all + lane; r < p.k_stride; r += 32) out[r] = make_uint2(0u, 0xFFFFFFFFu);
+        if (lane == 0) {
+            p.out_n[qi] = nh_all;
+            if (p.out_count) p.out_count[qi] = p.n_alive;
+        }
+        return;
+    }
+    WarpTopK<KS> tk;
+    tk.init();
+    const uint64_t* src = p.partial + q.part_begin;
+    const uint32_t total = min(p.qcount[qi], q.part_cap);
+    for (uint32_t i0 = 0; i0 < total; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        const uint64_t c = i < total ? src[i] : 0;
+        tk.offer(c != 0, c, k, lane);
+    }
+    uint32_t nh = 0;
+#pragma unroll
+    for (int s = 0; s < KS; s++) {
+        const int r = s * 32 + lane;
+        const bool ok = r < k && tk.q[s] != 0;
+        if (r < (int)p.k_stride) {
+            uint2 h = make_uint2(0u, 0xFFFFFFFFu);
+            if (ok) {
+                h.x = __float_as_uint(unsortable((uint32_t)(tk.q[s] >> 32)));
+                h.y = ~(uint32_t)(tk.q[s] & 0xFFFFFFFFu) + p.doc_base;
+            }
+            out[r] = h;
+        }
+        nh += __popc(__ballot_sync(FULL, ok));
+    }
+    for (uint32_t r = KS * 32 + lane; r < p.k_stride; r += 32) out[r] = make_uint2(0u, 0xFFFFFFFFu);
+    if (lane == 0) {
+        p.out_n[qi] = nh;
+        if (p.out_count) p.out_count[qi] = p.qmatch[qi];
+    }
+}
+
+// block-max metadata: one warp per block, the same arithmetic as the scoring path
+__global__ void __launch_bounds__(256) blockmax_kernel(const DevIndex ix, uint32_t b0, uint32_t b1, int fn_field,
+                                                       float cnorm, float* bmax) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t b = b0 + blockIdx.x * 8u + (threadIdx.x >> 5);
+    if (b >= b1) return;
+    const uint4 e = __ldg(&ix.skip[b]);
+    const uint32_t bd = e.w & 63u, bt = (e.w >> 6) & 63u, n = ((e.w >> 12) & 127u) + 1u;
+    const uint32_t* wd = reinterpret_cast<const uint32_t*>(ix.blk + (size_t)e.z * 16u);
+    uint32_t g[4], t[4];
+    unpack4(wd, lane, bd, g);
+    unpack4(wd + 4 * bd, lane, bt, t);
+    g[1] += g[0]; g[2] += g[1]; g[3] += g[2];
+    const uint32_t off = warp_excl_scan(g[3], lane) + e.y + 4u * lane;
+    float best = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        if (4u * lane + (uint32_t)j < n) {
+            const uint32_t d = off + g[j] + (uint32_t)j;
+            const float nrm = fn_field >= 0 ? __ldg(ix.cache + fn_field * 256 + (int)__ldg(ix.fnorm[fn_field] + d)) : cnorm;
+            best = fmaxf(best, tf_factor((float)(t[j] + 1u), nrm));
+        }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) best = fmaxf(best, __shfl_xor_sync(FULL, best, o));
+    if (lane == 0) bmax[b] = best;
+}
+
+}  // namespace
+
+void launch_lead(const LeadParams& p, int ks, int n_sms, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (p.n_queries == 0) return;
+    const uint32_t n_init = max(max(p.n_cursors, p.n_queries), 1u);
+    FG_LAUNCH(lead_init_kernel, (n_init + 255) / 256, 256, 0, st, p);
+    if (p.n_items == 0) return;
+    const int smem = (int)sizeof(LeadShared);
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(lead_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(lead_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(lead_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        configured = true;
+    }
+    const unsigned per_sm = ks <= 4 ? 3u : 1u;
+    const unsigned grid = min((p.n_items + LNW - 1) / LNW, (unsigned)n_sms * per_sm);
+    if (ks <= 1) FG_LAUNCH(lead_kernel<1>, grid, LNT, smem, st, p);
+    else if (ks <= 4) FG_LAUNCH(lead_kernel<4>, grid, LNT, smem, st, p);
+    else FG_LAUNCH(lead_kernel<32>, grid, LNT, smem, st, p);
+}
+
+void launch_lead_merge(const LeadMergeParams& p, int ks, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (p.n_queries == 0) return;
+    const unsigned grid = (p.n_queries + 3) / 4;
+    if (ks <= 1) FG_LAUNCH(lead_merge_kernel<1>, grid, 128, 0, st, p);
+    else if (ks <= 4) FG_LAUNCH(lead_merge_kernel<4>, grid, 128, 0, st, p);
+    else FG_LAUNCH(lead_merge_kernel<32>, grid, 128, 0, st, p);
+}
+
+void launch_blockmax(const DevIndex& ix, uint32_t b0, uint32_t b1, int fn_field, float cnorm, float* bmax, void* stream) {
+    if (b1 <= b0) return;
+    FG_LAUNCH(blockmax_kernel, (b1 - b0 + 7) / 8, 256, 0, (cudaStream_t)stream, ix, b0, b1, fn_field, cnorm, bmax);
+}
+
+}  // namespace fg

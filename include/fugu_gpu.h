@@ -174,6 +174,10 @@ int32_t fg_batch_prepare(fg_index* index, const fg_query_batch* batch, fg_batch*
  * when the term has a dense tf column: the block path is what the algorithmic-byte definition
  *  and the exact-accounting counters are stated on. */
 #define FG_PREP_NO_COLUMNS 1u
+/* FG_PREP_LEGACY lowers the plan for the windowed accumulator kernels of round 1 (kept for A/B runs and for
+ * the exact algorithmic-byte accounting pass, which is defined on exhaustive block evaluation); the default
+ * lowering targets the lead-driven kernels (block-max / MaxScore pruning, skip-table gallop lookups). */
+#define FG_PREP_LEGACY 2u
 int32_t fg_batch_prepare_ex(fg_index* index, const fg_query_batch* batch, uint32_t prep_flags, fg_batch** out);
 void fg_batch_release(fg_batch* b);
 #define FG_EXEC_EXACT_ACCOUNTING 1u /* exact block-need test for the algorithmic-byte counters (slow) */
@@ -212,6 +216,11 @@ typedef struct {
     float merge_kernel_ms;    /* ... and of the per-query merge kernel */
     uint64_t colscan_chunks;         /* with FG_EXEC_COUNTERS: 256-doc chunks of windowed column-scan plans reached */
     uint64_t colscan_chunks_skipped; /* ... of which skipped because no doc in them could enter the top-k */
+    /* lead-driven kernels, with FG_EXEC_COUNTERS: bytes_blocks = payload + skip entry of every block decoded
+     * (lead or lookup), scored_postings = 1-byte gathers (fieldnorm ids, tf-column bytes), and: */
+    uint64_t bytes_meta;       /* block-max words and skip entries read while skipping / galloping */
+    uint64_t lead_blocks;      /* lead blocks decoded ... */
+    uint64_t lead_blocks_seen; /* ... of the lead blocks whose block maximum was tested */
 } fg_batch_stats;
 /* synchronises the stream and reads the device counters of the last fg_batch_execute */
 int32_t fg_batch_get_stats(fg_batch* b, fg_batch_stats* out);

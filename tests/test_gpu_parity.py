@@ -486,9 +486,9 @@ def test_multi_item_plans_forced_small_items(ctx, monkeypatch):
 
 
 def test_gated_column_scan_equals_exhaustive(ctx):
-    """Sparse-hit gating of the column scan (windows evaluated from their hit lists, chunks without a
-    streamed posting skipped once such docs cannot reach the top-k): identical results with the gate on,
-    off (FG_EXEC_NO_PRUNE) and from the oracle; the counters prove the gate engaged; deletes included."""
+    """Pruning never changes a result. Default lowering (lead-driven kernels): MaxScore / block-max pruning on
+    (TopDocs form) vs off (FG_EXEC_NO_PRUNE) vs the oracle, the counters prove blocks were skipped. Legacy
+    lowering (FG_PREP_LEGACY): sparse-hit gating of the column scan, same three-way check. Deletes included."""
     from oracle import orc
     from tests.util import DevBuf, check_topk
 
@@ -513,30 +513,36 @@ def test_gated_column_scan_equals_exhaustive(ctx):
         assert index.info().n_columns >= 40
         o_hits, o_n, _ = orc.search(desc, batch, threads=4)
         nq, ks = batch.n_queries, batch.kmax
-        res = {}
-        for name, flags in (("gated", nat.FG_EXEC_COUNTERS), ("exhaustive", nat.FG_EXEC_COUNTERS | nat.FG_EXEC_NO_PRUNE)):
-            d_hits, d_n = DevBuf((nq, ks, 2)), DevBuf(nq)
-            pb = index.prepare(batch)
-            pb.execute(d_hits.ptr, d_n.ptr, None, None, k_stride=ks, flags=flags)  # no match counts: the TopDocs form
-            st = pb.stats()
-            raw = d_hits.numpy().view(np.uint32).reshape(nq, ks, 2)
-            out = np.zeros((nq, ks), nat.HIT_DT)
-            out["score"], out["doc"] = raw[:, :, 0].view(np.float32), raw[:, :, 1]
-            res[name] = (out, d_n.numpy().view(np.uint32), st.colscan_chunks, st.colscan_chunks_skipped)
-            pb.close()
-        g, e = res["gated"], res["exhaustive"]
-        assert e[3] == 0 and g[2] == e[2] > 0
-        # how much is skipped depends on how fast the threshold warms up (work items of a query run one after
-        # the other under emulation, concurrently on a GPU): only require that the gate engaged
-        assert 0 < g[3] <= g[2], f"the gate skipped {g[3]} of {g[2]} chunks"
-        assert np.array_equal(g[1], o_n) and np.array_equal(e[1], o_n)
-        for qi in range(nq):
-            n = int(o_n[qi])
-            k = int(batch.q["k"][qi])
-            check_topk(g[0][qi, :n], o_hits[qi, :n], k, ctx=f"gated query {qi} {qs[qi]['query']}")
-            check_topk(e[0][qi, :n], o_hits[qi, :n], k, ctx=f"exhaustive query {qi}")
-            # same kernels, same operation order: gated and exhaustive agree far inside the oracle tolerance
-            check_topk(g[0][qi, :n], e[0][qi, :n], k, tol=1e-6, ctx=f"gated vs exhaustive query {qi}")
+        for prep in (0, nat.FG_PREP_LEGACY):
+            res = {}
+            for name, flags in (("gated", nat.FG_EXEC_COUNTERS), ("exhaustive", nat.FG_EXEC_COUNTERS | nat.FG_EXEC_NO_PRUNE)):
+                d_hits, d_n = DevBuf((nq, ks, 2)), DevBuf(nq)
+                pb = index.prepare(batch, prep)
+                pb.execute(d_hits.ptr, d_n.ptr, None, None, k_stride=ks, flags=flags)  # no match counts: the TopDocs form
+                st = pb.stats()
+                raw = d_hits.numpy().view(np.uint32).reshape(nq, ks, 2)
+                out = np.zeros((nq, ks), nat.HIT_DT)
+                out["score"], out["doc"] = raw[:, :, 0].view(np.float32), raw[:, :, 1]
+                if prep & nat.FG_PREP_LEGACY:
+                    res[name] = (out, d_n.numpy().view(np.uint32), st.colscan_chunks, st.colscan_chunks_skipped)
+                else:  # lead blocks whose block maximum was tested / of which skipped
+                    res[name] = (out, d_n.numpy().view(np.uint32), st.lead_blocks_seen, st.lead_blocks_seen - st.lead_blocks)
+                pb.close()
+            g, e = res["gated"], res["exhaustive"]
+            assert e[3] == 0 and e[2] > 0
+            if prep & nat.FG_PREP_LEGACY:
+                assert g[2] == e[2]
+            # how much is skipped depends on how fast the threshold warms up (work items of a query run one after
+            # the other under emulation, concurrently on a GPU): only require that the pruning engaged
+            assert 0 < g[3] <= g[2], f"pruning skipped {g[3]} of {g[2]}"
+            assert np.array_equal(g[1], o_n) and np.array_equal(e[1], o_n)
+            for qi in range(nq):
+                n = int(o_n[qi])
+                k = int(batch.q["k"][qi])
+                check_topk(g[0][qi, :n], o_hits[qi, :n], k, ctx=f"pruned query {qi} {qs[qi]['query']}")
+                check_topk(e[0][qi, :n], o_hits[qi, :n], k, ctx=f"exhaustive query {qi}")
+                # same kernels, same operation order: pruned and exhaustive agree far inside the oracle tolerance
+                check_topk(g[0][qi, :n], e[0][qi, :n], k, tol=1e-6, ctx=f"pruned vs exhaustive query {qi}")
         # with match counts every doc is visited and the counts are exact
         h_hits, h_n, h_c = index.search(batch)
         _, _, o_c = orc.search(desc, batch, threads=4)

@@ -64,8 +64,8 @@ def gpu_search_device(index: nat.Index, batch: nat.HostBatch, want_bitmap: bool 
                       prep_flags: int = 0):
     """Split-phase path with device buffers provided by torch; returns numpy results (+ stats).
     The byte counters are defined on the block path: accounting runs lower the plan without columns."""
-    if flags & (nat.FG_EXEC_EXACT_ACCOUNTING | nat.FG_EXEC_COUNTERS):
-        prep_flags |= nat.FG_PREP_NO_COLUMNS
+    if flags & nat.FG_EXEC_EXACT_ACCOUNTING:
+        prep_flags |= nat.FG_PREP_NO_COLUMNS | nat.FG_PREP_LEGACY
 
     ks = batch.kmax
     nq = batch.n_queries
@@ -128,6 +128,15 @@ def check_batch_against_oracle(index: nat.Index, desc: nat.HostIndexDesc, batch:
         for qi in range(batch.n_queries):
             n = int(o_n[qi])
             check_topk(b_hits[qi, :n], o_hits[qi, :n], int(batch.q["k"][qi]), ctx=f"block path, query {qi}")
+    # the windowed accumulator kernels of round 1 (FG_PREP_LEGACY; still used by the exact-accounting pass)
+    l_hits, l_n, l_c, l_bm, _ = gpu_search_device(index, batch, want_bitmap=bitmaps, prep_flags=nat.FG_PREP_LEGACY)
+    assert np.array_equal(l_c, o_c), f"legacy kernels: match counts differ for queries {np.nonzero(l_c != o_c)[0][:10]}"
+    assert np.array_equal(l_n, o_n)
+    if bitmaps:
+        assert np.array_equal(l_bm, o_bm), "legacy kernels: matched doc-id sets differ"
+    for qi in range(batch.n_queries):
+        n = int(o_n[qi])
+        check_topk(l_hits[qi, :n], o_hits[qi, :n], int(batch.q["k"][qi]), ctx=f"legacy kernels, query {qi}")
     bad = np.nonzero(g_c != o_c)[0]
     assert len(bad) == 0, f"match counts differ for queries {bad[:10]}: gpu {g_c[bad[:10]]} oracle {o_c[bad[:10]]}"
     assert np.array_equal(g_n, o_n), f"n_hits differ: {np.nonzero(g_n != o_n)[0][:10]}"
