@@ -133,6 +133,13 @@ def build_workload(args, rank: int, world: int):
     d0, d1 = cfg.n_docs * rank // world, cfg.n_docs * (rank + 1) // world
     fields = synth.build_fields(corpus, d0, d1)
     queries = synth.gen_queries(cfg)
+    flt = os.environ.get("FG_BENCH_FILTER")  # dev: time one query shape of the mix ("and", "or", "single"); never set by the driver
+    if flt:
+        def shape(q):
+            s = q["query"]
+            return "and" if " AND " in s else ("single" if " " not in s.strip() else "or")
+        queries = [q for q in queries if shape(q) == flt]
+        cfg = synth.Config(cfg=cfg.cfg, n_docs=cfg.n_docs, vocab=cfg.vocab, n_queries=len(queries), k=cfg.k, name_pct=cfg.name_pct, n_ns=cfg.n_ns)
     return cfg, corpus, fields, queries, d0, d1
 
 
@@ -147,13 +154,13 @@ def term_lists(corpus, cfg, n_fields):
     return terms
 
 
-def ncu_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum of the kernels of one step, from the committed
-    `ncu --set full` capture of this command (profiles/r01b_traffic.json, written by
-    tools/ncu_summary.py), or None."""
-    p = os.path.join(ROOT, "profiles", "r01b_traffic.json")
+def ncu_traffic(cfg_id: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the search kernel of one step, from the committed
+    `ncu --set full` capture of THIS round's build (profiles/r02_traffic.json, written by tools/ncu_summary.py
+    from the capture named in it), or None when no capture of this configuration is committed."""
+    p = os.path.join(ROOT, "profiles", "r02_traffic.json")
     try:
-        return json.load(open(p))["dram_bytes_per_step"]
+        return json.load(open(p))[f"C{cfg_id}"]["dram_bytes_per_step"]
     except Exception:
         return None
 
@@ -168,41 +175,25 @@ def peak_hbm():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def pruned_bytes_estimate(index, batch, n_local: int, skip_frac: float) -> float:
-    """Algorithmic bytes the column scan did NOT need: for every windowed column-scan plan (a pure union
-    with dense-tf-column leaves next to sparse leaves) the block bytes + fieldnorm gathers of its
-    column-term leaves, times the measured share of skipped 256-doc chunks."""
-    from fugu_b200 import _native as nat
-
-    if skip_frac <= 0:
-        return 0.0
-    is_col: dict = {}
-
-    def col_bytes(f, t):
-        key = (int(f), int(t))
-        if key not in is_col:
-            ti = index.term_info(key[0], key[1])
-            dense = ti["local_df"] * 16 >= n_local and ti["local_df"] >= 128  # fg_index_upload's rule for a dense tf column
-            is_col[key] = (ti["bytes"] + ti["local_df"]) if dense else 0  # block bytes + 1 B fieldnorm gather per posting
-        return is_col[key]
-
-    total = 0.0
-    for qi in range(batch.n_queries):
-        c0, nc = int(batch.q["clause_begin"][qi]), int(batch.q["n_clauses"][qi])
-        cl = batch.c[c0:c0 + nc]
-        if nc == 0 or (cl["occur"] != nat.FG_OCCUR_SHOULD).any():
-            continue  # only pure unions run in the column-scan kernel
-        cb = sparse = 0
-        for c in cl:
-            for lf in batch.l[int(c["leaf_begin"]):int(c["leaf_begin"]) + int(c["n_leaves"])]:
-                if int(lf["term_ord"]) >= 0xFFFFFFFE:
-                    continue  # missing term / AllQuery
-                b = col_bytes(lf["field"], lf["term_ord"])
-                cb += b
-                sparse += 0 if b else 1
-        if cb and sparse:
-            total += skip_frac * cb
-    return total
+def compare_topk(gs, gd, os_, od, k, tol=1e-5):
+    """None when the hit lists agree (scores rank-wise within tol, docs equal except inside runs of scores tied
+    within tolerance, a run cut at rank k may differ), else a description of the first difference."""
+    if len(gs) != len(os_):
+        return f"n_hits {len(gs)} != {len(os_)}"
+    n = len(os_)
+    for i in range(n):
+        a, b = float(gs[i]), float(os_[i])
+        if abs(a - b) > tol * max(abs(a), abs(b), 1e-30):
+            return f"rank {i}: score {a!r} vs {b!r}"
+    i = 0
+    while i < n:
+        j = i
+        while j + 1 < n and abs(float(os_[j + 1]) - float(os_[j])) <= 4 * tol * max(abs(float(os_[j])), 1e-30):
+            j += 1
+        if set(gd[i:j + 1].tolist()) != set(od[i:j + 1].tolist()) and not (j == n - 1 and n == k):
+            return f"ranks {i}..{j}: docs {sorted(gd[i:j + 1].tolist())} vs {sorted(od[i:j + 1].tolist())}"
+        i = j + 1
+    return None
 
 
 def run_reference(args):
@@ -405,24 +396,21 @@ def main():
             nat.merge_topk_device(ctx, g_hits.data_ptr(), g_n.data_ptr(), world, nq, k, k, f_hits.data_ptr(), f_n.data_ptr())
 
     # exact algorithmic-byte accounting pass (untimed). SURVEY.md 8(d) states the algorithmic bytes on
-    # the posting-block layout, so this pass lowers the plan WITHOUT dense tf columns (every leaf decoded
-    # from its blocks); the timed batch `pb` uses the columns.
-    pb_blocks = index.prepare(batch, nat.FG_PREP_NO_COLUMNS)
+    # exhaustive evaluation of the posting-block layout: this pass lowers the plan for the windowed kernels
+    # WITHOUT dense tf columns (FG_PREP_LEGACY | FG_PREP_NO_COLUMNS: every leaf decoded from its blocks).
+    pb_blocks = index.prepare(batch, nat.FG_PREP_NO_COLUMNS | nat.FG_PREP_LEGACY)
     pb_blocks.execute(d_hits.data_ptr(), d_n.data_ptr(), d_c.data_ptr(), None, k_stride=k, flags=nat.FG_EXEC_EXACT_ACCOUNTING)
     st = pb_blocks.stats()
     algo_bytes = st.bytes_blocks + st.scored_postings + 8 * st.sum_k
     pb_blocks.close()
-    # touched block bytes of the normal execution (columns on, coarse filter), counters on (untimed), in the
-    # timed configuration (no match counts unless FG_BENCH_COUNTS: counting forces every doc to be visited)
+    # bytes the timed configuration really touches ("if the implementation prunes, report touched
+    # bytes (kernel counters) and use min(algorithmic, touched)"): the same batch, counters on, untimed. Counted
+    # by the kernel: payload + skip entry of every block decoded (lead or lookup), block-max words and skip
+    # entries read while skipping / galloping, 1-byte gathers (fieldnorm ids, tf-column bytes), 8 B per hit.
     pb.execute(d_hits.data_ptr(), d_n.data_ptr(), d_c.data_ptr() if counts else None, None, k_stride=k, flags=nat.FG_EXEC_COUNTERS)
     st_touched = pb.stats()
-    # Pruning ("if the implementation prunes, report touched bytes"): the column scan skips
-    # the docs that no sparse-term posting touched once they cannot reach the top-k any more. The
-    # algorithmic bytes of the column-term leaves of those plans are discounted by the measured share of
-    # skipped 256-doc chunks (an estimate: the postings of a frequent term are spread evenly over doc ids).
-    skip_frac = (st_touched.colscan_chunks_skipped / st_touched.colscan_chunks) if st_touched.colscan_chunks else 0.0
-    pruned_bytes = pruned_bytes_estimate(index, batch, n_local, skip_frac)
-    touched_algo_bytes = max(0.0, float(algo_bytes) - pruned_bytes)
+    touched_bytes = st_touched.bytes_blocks + st_touched.bytes_meta + st_touched.scored_postings + 8 * st_touched.sum_k
+    touched_algo_bytes = float(min(algo_bytes, touched_bytes))
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -470,6 +458,48 @@ def main():
     st_timed = pb.stats()
     ms_per_step = total_ms / args.steps
     qps = nq / (ms_per_step * 1e-3)
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+
+    # ---- the same batch evaluated exhaustively (pruning off, every posting of every leaf visited): the pass
+    # on which algorithmic bytes == touched bytes; timed the same way, reported beside the pruned figures ----
+    exh_ms = []
+    for i in range(2 + min(args.steps, 5)):
+        if not args.no_flush:
+            flush_buf.fill_(i & 0xFF)
+        pb.execute(d_hits.data_ptr(), d_n.data_ptr(), None, None, k_stride=k, flags=nat.FG_EXEC_NO_PRUNE)
+        s2 = pb.stats()
+        if i >= 2:
+            exh_ms.append(s2.search_kernel_ms)
+    step()  # leave the buffers holding the result of the timed (pruned) configuration
+    torch.cuda.synchronize()
+
+    # ---- parity of the benchmarked configuration at the benchmarked size: the hits the timed path produced
+    # vs the oracle on the same batch (first PARITY_Q queries; scores within 1e-5 relative, same docs except
+    # inside ties) ----
+    parity = None
+    if rank == 0 and not args.no_cpu_baseline:
+        from oracle import orc  # checker only
+
+        pq = min(nq, int(os.environ.get("FG_BENCH_PARITY_Q", "1000")))
+        if world > 1:
+            full_fields = synth.build_fields(corpus, 0, cfg.n_docs)
+            pdesc = nat.HostIndexDesc(cfg.n_docs, full_fields)
+            got_hits, got_n = f_hits.cpu().numpy(), f_n.cpu().numpy().view(np.uint32)
+        else:
+            pdesc = desc
+            got_hits, got_n = d_hits.cpu().numpy(), d_n.cpu().numpy().view(np.uint32)
+        sub = nat.HostBatch.from_arrays(batch.q[:pq], batch.c, batch.l)
+        o_hits, o_n, _ = orc.search(pdesc, sub, threads=host_cores())
+        raw = got_hits.view(np.uint32).reshape(nq, k, 2)
+        failed, first = 0, None
+        for qi in range(pq):
+            msg = compare_topk(raw[qi, :, 0].view(np.float32)[:got_n[qi]], raw[qi, :, 1][:got_n[qi]],
+                               o_hits["score"][qi, :o_n[qi]], o_hits["doc"][qi, :o_n[qi]], int(batch.q["k"][qi]))
+            if msg:
+                failed += 1
+                first = first or f"query {qi} ({queries[qi]['query']!r}): {msg}"
+        parity = {"checked": pq, "failed": failed, "against": "oracle/oracle.cpp on the same batch and corpus",
+                  "tolerance": "scores 1e-5 relative, doc ids equal except inside ties", "first_failure": first}
 
     # ---- e2e through the blocking host-buffer ABI call ----
     e2e_times = []
@@ -492,7 +522,7 @@ def main():
         print("e2e_times ms", [round(x * 1e3, 2) for x in e2e_times], file=sys.stderr)
     if dist:
         e2e_s = float(xch.allreduce_cpu(np.array([e2e_s], np.float64), "max")[0])
-    lowered_bytes = nq * 48 + len(batch.l) * 64 + st_touched.n_work_items * 32
+    lowered_bytes = nq * 48 + len(batch.l) * 48 + st_touched.n_work_items * 16  # LQuery + LLeaf + LItem arrays
     out_bytes = nq * k * 8 + nq * 8
 
     def shutdown():
@@ -506,6 +536,7 @@ def main():
     peak, peak_src = peak_hbm()
     kms = float(np.mean(kern_ms)) if kern_ms else ms_per_step
     achieved = touched_algo_bytes / (kms * 1e-3) / 1e9  # this rank's launch; min(algorithmic, touched)
+    exh_kms = float(np.mean(exh_ms)) if exh_ms else kms
     line = {
         "metric": "queries_per_sec", "value": qps, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
@@ -513,30 +544,33 @@ def main():
         "config": workload_config(cfg, args, world),
         "posting_gbs": algo_total / (ms_per_step * 1e-3) / 1e9,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": ncu_traffic(), "peak_source": peak_src,
-                     "kernel": "one step's search kernels, launched concurrently and timed as one group: colscan_kernel (pure unions "
-                               "with a dense-tf-column leaf; ~3/4 of the step's instructions) + search_kernel x4 (dense/hash x pure/masked)",
-                     "kernel_ms": kms, "algorithmic_bytes_per_launch": int(touched_algo_bytes),
+                     "traffic": ncu_traffic(cfg.cfg), "peak_source": peak_src,
+                     "kernel": "lead_kernel (fg_lead.cu): one persistent launch per step walks the lead leaves block by block "
+                               "(bit-unpack + warp prefix sum), looks candidates up in the other leaves (tf-column byte or "
+                               "skip-table gallop + block decode), BM25, per-warp top-k; + lead_init_kernel, lead_merge_kernel",
+                     "kernel_ms": kms, "kernel_ms_min": float(np.min(kern_ms)), "kernel_ms_median": float(np.median(kern_ms)),
+                     "algorithmic_bytes_per_launch": int(touched_algo_bytes),
                      "bytes_per_query": touched_algo_bytes / nq,
-                     "exhaustive_bytes_per_launch": int(algo_bytes),
-                     "exhaustive_equivalent_gbs": algo_bytes / (kms * 1e-3) / 1e9,
-                     "pruning": {"colscan_chunks": int(st_touched.colscan_chunks),
-                                 "colscan_chunks_skipped": int(st_touched.colscan_chunks_skipped),
-                                 "pruned_bytes_estimate": int(pruned_bytes),
-                                 "note": "achieved uses exhaustive algorithmic bytes MINUS the bytes of column-term leaves in the "
-                                         "docs the column scan skipped (docs without a sparse-term posting once they cannot reach "
-                                         "the top-k); exhaustive_equivalent_gbs is the undiscounted figure"},
-                     "touched_block_bytes": int(st_touched.bytes_blocks), "redecode_bytes": int(st_touched.bytes_redecode),
-                     "note": "algorithmic bytes are counted on the posting-block layout by an untimed exact-accounting pass "
-                             "that evaluates every leaf from its blocks; the timed pass reads 1 B/doc dense tf columns for terms "
-                             "in >= 1/16 of the docs instead of their blocks. Index snapshot is %.0f MB in HBM incl. %.0f MB of "
-                             "columns (L2 is 126 MB); L2 is flushed before each timed step; traffic = ncu dram bytes of one C2 "
-                             "step (profiles/r01b_traffic.json, captured before sparse-hit gating was added to the column scan)" % (info.device_bytes / 1e6, info.column_bytes / 1e6)},
+                     "numerator": "min(algorithmic, touched) per SURVEY.md 8(d): the timed configuration prunes (MaxScore + "
+                                  "block-max), so the numerator is the bytes the kernel really read (device counters of an untimed "
+                                  "pass of the same batch)",
+                     "touched": {"block_bytes": int(st_touched.bytes_blocks), "meta_bytes": int(st_touched.bytes_meta),
+                                 "gather_bytes": int(st_touched.scored_postings), "hit_bytes": int(8 * st_touched.sum_k),
+                                 "lead_blocks_decoded": int(st_touched.lead_blocks), "lead_blocks_tested": int(st_touched.lead_blocks_seen)},
+                     "exhaustive": {"algorithmic_bytes_per_launch": int(algo_bytes), "kernel_ms": exh_kms,
+                                    "achieved": algo_bytes / (exh_kms * 1e-3) / 1e9, "frac": algo_bytes / (exh_kms * 1e-3) / 1e9 / peak,
+                                    "note": "the same batch with FG_EXEC_NO_PRUNE (every posting of every leaf visited, results "
+                                            "identical): algorithmic bytes of SURVEY.md 8(d) (exact-accounting pass on the block "
+                                            "layout) over this pass's own CUDA-event kernel time"},
+                     "note": "index snapshot is %.0f MB in HBM incl. %.0f MB of tf columns (L2 is 126 MB); L2 is flushed before "
+                             "each timed step" % (info.device_bytes / 1e6, info.column_bytes / 1e6)},
         "e2e": {"value": nq / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": int(lowered_bytes),
                 "d2h_bytes_per_step": int(out_bytes), "ms_per_step": e2e_s * 1e3,
                 "what": "fgh_search_batch: query strings (host) -> C++ planner -> plan lowering -> H2D plan -> kernels -> D2H hits "
                         "(host); requests of 4096 queries and more are pipelined in four chunks (10 / 30 / 30 / 30 %%); match counts %s" % ("on" if counts else "off (TopDocs does not count)")},
         "gpu_launches": int(st_timed.n_launches + (1 if world > 1 else 0)) * args.steps,
+        "parity": parity,
+        "ms_per_step_min": float(np.min(step_ms)), "ms_per_step_median": float(np.median(step_ms)),
         "clocks": clocks,
         "index": {"postings": int(info.n_postings), "blocks": int(info.n_blocks), "packed_bytes": int(info.packed_bytes),
                   "device_bytes": int(info.device_bytes), "upload_s": upload_s, "work_items": int(st_touched.n_work_items),
@@ -569,6 +603,9 @@ def main():
     sys.stdout.flush()
     os.write(json_fd, (json.dumps(line) + "\n").encode())
     shutdown()
+    if parity and parity["failed"]:
+        sys.stderr.write(f"bench.py: PARITY FAILURE on the benchmarked batch: {parity}\n")
+        sys.exit(3)
 
 
 if __name__ == "__main__":

@@ -77,7 +77,8 @@ class IndexInfo(C.Structure):
         ("n_fields", C.c_uint32),
         ("column_bytes", C.c_uint64),
         ("n_columns", C.c_uint32),
-        ("reserved", C.c_uint32),
+        ("n_bitmaps", C.c_uint32),
+        ("bitmap_bytes", C.c_uint64),
     ]
 
 

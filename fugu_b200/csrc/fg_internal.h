@@ -161,8 +161,9 @@ int search_smem_bytes(int ks, bool pure);
 // A query is answered by walking some of its leaves as LEADS, block after block, and looking every
 // candidate doc of a lead block up in the query's other leaves (dense tf column byte, or skip-table
 // gallop + block decode). Leaves of a query are stored [leads | required | optional | excluded]:
-//   pure union      : every Should leaf is a lead, by descending upper bound ub = weight * max tf factor;
-//                     a candidate of lead i that also occurs in a lead j < i is dropped (lead j scores it)
+//   pure union      : every Should leaf is a lead, shortest list first (ub = weight * max tf factor bounds a
+//                     leaf's contribution); a candidate of lead i that also occurs in a lead j < i is dropped
+//                     (lead j scores it)
 //   plan with Must  : the leaves of the Must clause with the smallest document frequency are the leads,
 //                     the other Must clauses are required lookups (ascending frequency), Should leaves
 //                     optional lookups, MustNot leaves excluding lookups.
@@ -181,10 +182,12 @@ struct LLeaf {
     float rest;          // LR_LEAD: sum of ub over the later leads, required and optional leaves
     uint32_t role;       // LR_* | clause index << 8 (required leaves of one Must clause share the index)
     const uint8_t* col;  // dense tf column or nullptr
+    const uint32_t* bits; // membership bitmap of the term (1 bit per doc) or nullptr; 8 words per 256-doc chunk
+    const uint32_t* rank; // with bits: number of postings before each 256-doc chunk
     uint32_t df;         // local document frequency
-    uint32_t pad;
+    uint32_t slot;       // lookup-cache slot of a leaf that is looked up by gallop + decode (running index over the query's such leaves)
 };
-static_assert(sizeof(LLeaf) == 48, "LLeaf is uploaded as a flat array");
+static_assert(sizeof(LLeaf) == 64, "LLeaf is uploaded as a flat array");
 constexpr uint32_t LQ_ALL = 1;    // pure AllQuery: first k alive docs, score = const_score
 constexpr uint32_t LQ_PRUNE = 2;  // every scoring weight is > 0: the upper bounds hold
 struct LQuery {
@@ -243,5 +246,9 @@ void launch_lead(const LeadParams& p, int ks, int n_sms, void* stream);
 void launch_lead_merge(const LeadMergeParams& p, int ks, void* stream);
 // block-max metadata of the blocks [b0, b1) of one field (upload time)
 void launch_blockmax(const DevIndex& ix, uint32_t b0, uint32_t b1, int fn_field, float cnorm, float* bmax, void* stream);
+// membership bitmaps + rank directories of selected terms (upload time): sel[i] = {global block, bitmap slot};
+// bits / rank are zeroed by the caller, stride_words is a multiple of 8
+void launch_bitmap_build(const DevIndex& ix, const uint2* sel, uint32_t n_sel, uint32_t* bits, uint64_t stride_words, void* stream);
+void launch_bitmap_rank(const uint32_t* bits, uint32_t* rank, uint32_t n_slots, uint64_t stride_words, void* stream);
 
 }  // namespace fg

@@ -30,15 +30,17 @@ namespace {
 
 constexpr int LNT = 256;      // threads per CTA
 constexpr int LNW = LNT / 32; // warps per CTA
-constexpr int LC = 8;         // decoded lookup blocks cached per warp
+constexpr int LC = 8;         // decoded lookup blocks cached per warp (slot = LLeaf::slot, assigned by the lowering)
+constexpr int CAND_CAP = BLOCK + 32;  // candidates wait here until a full round of 32 is available
 
 struct WarpShared {
     LLeaf leaf[LMAX_LEAVES];
-    uint32_t cur[LMAX_LEAVES];   // per leaf: first block that can still hold a candidate of this item
+    uint4 cure[LMAX_LEAVES];     // skip entry of block cur[j] (valid while cur[j] != EMPTY)
+    uint32_t cur[LMAX_LEAVES];   // per leaf: the block the last lookup ended in (lookups ascend), EMPTY = none yet
     uint32_t ctag[LC];           // global block index of the decoded block in cdocs[slot], EMPTY = none
     uint32_t cdocs[LC][BLOCK];   // doc ids of a decoded lookup block, padded with 0xFFFFFFFF
-    uint32_t cand_doc[BLOCK];    // compacted candidates of the current lead block, ascending
-    uint32_t cand_val[BLOCK];    // their lead score (f32 bits), or the lead tf while required clauses come first
+    uint32_t cand_doc[CAND_CAP]; // candidates that survived their lead block's bound test, ascending
+    uint32_t cand_val[CAND_CAP]; // their lead score (f32 bits), or the lead tf while required clauses come first
 };
 struct LeadShared {
     float cache[MAX_FIELDS * 256];  // BM25 norm caches K1*(1-B+B*dl/avg) of every field, by fieldnorm id
@@ -101,7 +103,7 @@ __device__ __forceinline__ uint32_t extract_tf(const uint8_t* __restrict__ blk, 
 // padded with 0xFFFFFFFF
 __device__ __forceinline__ const uint32_t* cached_block(const uint8_t* __restrict__ blk, WarpShared& W, int j,
                                                         uint32_t gblock, const uint4 e, int lane, bool acct, Acct& A) {
-    const int slot = j & (LC - 1);
+    const int slot = (int)W.leaf[j].slot & (LC - 1);
     uint32_t* cd = W.cdocs[slot];
     if (W.ctag[slot] != gblock) {  // uniform
         const uint32_t bd = e.w & 63u, n = ((e.w >> 12) & 127u) + 1u;
@@ -125,7 +127,10 @@ __device__ __forceinline__ const uint32_t* cached_block(const uint8_t* __restric
 }
 
 // Term frequency of doc c in leaf L (0 = absent) for the lanes with `live`; candidates ascend with the
-// lane index. Warp-collective. need_tf = false: presence only (returns 1).
+// lane index, and from one call to the next (per leaf). Warp-collective. need_tf = false: presence only.
+// The leaf's cursor (block index + its skip entry, in shared memory) makes the common cases cheap: the
+// candidates still fall into the block the previous call ended in (sparse list: no global load at all), or
+// into one of the next 32 blocks (one 4-byte load per lane + ballot).
 __device__ __forceinline__ uint32_t probe(const LeadParams& p, WarpShared& W, int j, const LLeaf& L, uint32_t c,
                                           bool live, bool need_tf, int lane, Acct& A) {
     const unsigned m = __ballot_sync(FULL, live);
@@ -133,32 +138,35 @@ __device__ __forceinline__ uint32_t probe(const LeadParams& p, WarpShared& W, in
     const bool acct = p.acct != 0;
     const uint4* __restrict__ sk = p.ix.skip + L.blk_begin;
     const uint32_t cmin = __shfl_sync(FULL, c, __ffs(m) - 1), cmax = __shfl_sync(FULL, c, 31 - __clz((int)m));
-    uint32_t b = seek(sk, L.n_blocks, W.cur[j], cmin, lane, acct, A);
-    __syncwarp();
-    if (lane == 0) W.cur[j] = b;
-    __syncwarp();
+    uint32_t b = W.cur[j];
+    uint4 e = W.cure[j];
+    if (b == EMPTY || e.x < cmin) {  // (uniform) the cursor's block ends before the first candidate
+        b = seek(sk, L.n_blocks, b == EMPTY ? 0u : b + 1u, cmin, lane, acct, A);
+        if (b < L.n_blocks) {
+            e = __ldg(&sk[b]);
+            if (acct) A.meta_bytes += 16u;
+        }
+    }
     uint32_t tf = 0u;
     bool pend = live;
     while (b < L.n_blocks) {
-        const uint4 e = __ldg(&sk[b]);
-        if (acct) A.meta_bytes += 16u;
-#ifdef FG_DEBUG_LEAD
-        if (lane == 0) printf("  probe leaf %d (blk_begin %u) b=%u e=[%u..%u] cmin=%u cmax=%u m=%08x\n", j, L.blk_begin, b, e.y, e.x, cmin, cmax, m);
-#endif
         if (e.y > cmax) break;  // the block starts behind the last candidate
         const bool inb = pend && c >= e.y && c <= e.x;
         if (__any_sync(FULL, inb)) {
             const uint32_t* cd = cached_block(p.ix.blk, W, j, L.blk_begin + b, e, lane, acct, A);
-            uint32_t pos = 0u;  // entries < c among the first 127
+            // sparse lists: most of the time no posting of the block lies between the first and the last candidate
+            const uint4 d4 = reinterpret_cast<const uint4*>(cd)[lane];
+            const bool inr = (d4.x >= cmin && d4.x <= cmax) || (d4.y >= cmin && d4.y <= cmax) ||
+                             (d4.z >= cmin && d4.z <= cmax) || (d4.w >= cmin && d4.w <= cmax);
+            if (__any_sync(FULL, inr)) {
+                uint32_t pos = 0u;  // entries < c among the first 127
 #pragma unroll
-            for (uint32_t s = 64u; s; s >>= 1)
-                if (inb && cd[pos + s - 1u] < c) pos += s;
-#ifdef FG_DEBUG_LEAD
-            if (inb) printf("    lane %d c=%u pos=%u cd[pos]=%u\n", lane, c, pos, cd[pos]);
-#endif
-            if (inb && cd[pos] == c) {
-                tf = need_tf ? extract_tf(p.ix.blk, e, pos) : 1u;
-                if (acct && need_tf) A.block_bytes += 8u;
+                for (uint32_t s = 64u; s; s >>= 1)
+                    if (inb && cd[pos + s - 1u] < c) pos += s;
+                if (inb && cd[pos] == c) {
+                    tf = need_tf ? extract_tf(p.ix.blk, e, pos) : 1u;
+                    if (acct && need_tf) A.block_bytes += 8u;
+                }
             }
         }
         pend = pend && c > e.x;
@@ -166,7 +174,17 @@ __device__ __forceinline__ uint32_t probe(const LeadParams& p, WarpShared& W, in
         if (!mp) break;
         const uint32_t cn = __shfl_sync(FULL, c, __ffs(mp) - 1);
         b = seek(sk, L.n_blocks, b + 1u, cn, lane, acct, A);
+        if (b < L.n_blocks) {
+            e = __ldg(&sk[b]);
+            if (acct) A.meta_bytes += 16u;
+        }
     }
+    __syncwarp();
+    if (lane == 0) {
+        W.cur[j] = b;
+        W.cure[j] = e;
+    }
+    __syncwarp();
     return tf;
 }
 
@@ -178,7 +196,7 @@ __device__ __forceinline__ void run_item(const LeadParams& p, const LeadShared& 
         const uint32_t* src = reinterpret_cast<const uint32_t*>(p.leaves + q.leaf_begin);
         uint32_t* dst = reinterpret_cast<uint32_t*>(W.leaf);
         for (uint32_t i = lane; i < q.n_leaves * (uint32_t)(sizeof(LLeaf) / 4); i += 32) dst[i] = __ldg(src + i);
-        W.cur[lane] = 0u;
+        W.cur[lane] = EMPTY;
         if (lane < LC) W.ctag[lane] = EMPTY;
     }
     __syncwarp();
@@ -194,7 +212,7 @@ __device__ __forceinline__ void run_item(const LeadParams& p, const LeadShared& 
     const bool has_req = n_req != 0;
     const uint4* __restrict__ sk = p.ix.skip + LD.blk_begin;
     const float* __restrict__ bmx = p.ix.bmax + LD.blk_begin;
-    const float slack = q.slack;
+    const float slack = q.slack + q.const_score;  // every bound below is compared with final scores, which include the constant
     const float rest_s = LD.rest + slack;
     const unsigned lt = (1u << lane) - 1u;
     Acct A;
@@ -204,6 +222,7 @@ __device__ __forceinline__ void run_item(const LeadParams& p, const LeadShared& 
     float theta = -INFINITY;  // a candidate needs score >= theta (ties are decided by the doc id in the queue)
     uint32_t pub = 0u;        // sortable threshold this warp has seen or published
     uint32_t n_match = 0u;
+    uint32_t ncand = 0u;      // candidates waiting in W.cand_* (< 32 between blocks)
 
     auto pull = [&]() {
         if (prune) {
@@ -221,6 +240,29 @@ __device__ __forceinline__ void run_item(const LeadParams& p, const LeadShared& 
         if (L.col) {
             if (acct) A.gathers += (unsigned long long)__popc(__ballot_sync(FULL, live));
             return live ? (uint32_t)__ldg(L.col + c) : 0u;
+        }
+        if (L.bits) {
+            // membership bit first (one 4-byte gather; most lookups miss); a hit finds its posting through the
+            // rank directory: position = postings before the doc, block = position / 128, tf from the block's tf stream
+            uint32_t tf = 0u;
+            if (live) {
+                const uint32_t wv = __ldg(L.bits + (c >> 5));
+                if ((wv >> (c & 31u)) & 1u) {
+                    tf = 1u;
+                    if (need_tf) {
+                        const uint32_t w0 = (c >> 8) << 3, wl = c >> 5;
+                        uint32_t r = __ldg(L.rank + (c >> 8)) + (uint32_t)__popc(wv & ((1u << (c & 31u)) - 1u));
+                        for (uint32_t w = w0; w < wl; w++) r += (uint32_t)__popc(__ldg(L.bits + w));
+                        const uint4 e = __ldg(p.ix.skip + L.blk_begin + (r >> 7));
+                        tf = extract_tf(p.ix.blk, e, r & 127u);
+                    }
+                }
+            }
+            if (acct) {
+                A.gathers += 4ull * (unsigned long long)__popc(__ballot_sync(FULL, live));
+                A.block_bytes += 56ull * (unsigned long long)__popc(__ballot_sync(FULL, tf != 0u && need_tf));
+            }
+            return tf;
         }
         return probe(p, W, j, L, c, live, need_tf, lane, A);
     };
@@ -255,6 +297,7 @@ __device__ __forceinline__ void run_item(const LeadParams& p, const LeadShared& 
             if (prune) live = live && (sc + rem + slack >= theta);
         } else {
             sc = __uint_as_float(v);
+            if (prune) live = live && (sc + rest_s >= theta);  // the threshold may have risen while the candidate waited
         }
         // a candidate that also occurs in an earlier lead was (or will be) scored by that lead's items
         for (int j = 0; j < lead; j++) {
@@ -347,8 +390,7 @@ __device__ __forceinline__ void run_item(const LeadParams& p, const LeadShared& 
                        m3 = __ballot_sync(FULL, ok[3]);
         const uint32_t total = (uint32_t)(__popc(m0) + __popc(m1) + __popc(m2) + __popc(m3));
         if (!total) return;
-        uint32_t pos = (uint32_t)(__popc(m0 & lt) + __popc(m1 & lt) + __popc(m2 & lt) + __popc(m3 & lt));
-        __syncwarp();
+        uint32_t pos = ncand + (uint32_t)(__popc(m0 & lt) + __popc(m1 & lt) + __popc(m2 & lt) + __popc(m3 & lt));
 #pragma unroll
         for (int j = 0; j < 4; j++)
             if (ok[j]) {
@@ -356,12 +398,36 @@ __device__ __forceinline__ void run_item(const LeadParams& p, const LeadShared& 
                 W.cand_val[pos] = val[j];
                 pos++;
             }
+        ncand += total;
         __syncwarp();
-        for (uint32_t r = 0; r < total; r += 32u) {
-            const bool live = r + lane < total;
-            const uint32_t c = live ? W.cand_doc[r + lane] : 0xFFFFFFFFu;
-            const uint32_t v = live ? W.cand_val[r + lane] : 0u;
-            evaluate(live, c, v);
+        // full rounds of 32 candidates; fewer than 32 wait for the survivors of the next blocks
+        uint32_t head = 0u;
+        while (ncand - head >= 32u) {
+            evaluate(true, W.cand_doc[head + lane], W.cand_val[head + lane]);
+            head += 32u;
+        }
+        if (head) {
+            const uint32_t left = ncand - head;
+            uint32_t cd0 = 0u, cv0 = 0u;
+            if ((uint32_t)lane < left) {
+                cd0 = W.cand_doc[head + lane];
+                cv0 = W.cand_val[head + lane];
+            }
+            __syncwarp();
+            if ((uint32_t)lane < left) {
+                W.cand_doc[lane] = cd0;
+                W.cand_val[lane] = cv0;
+            }
+            ncand = left;
+            __syncwarp();
+        }
+    };
+    auto flush = [&]() {  // the candidates still waiting (fewer than 32)
+        if (ncand) {
+            const bool live = (uint32_t)lane < ncand;
+            evaluate(live, live ? W.cand_doc[lane] : 0xFFFFFFFFu, live ? W.cand_val[lane] : 0u);
+            ncand = 0u;
+            __syncwarp();
         }
     };
 
@@ -395,6 +461,8 @@ __device__ __forceinline__ void run_item(const LeadParams& p, const LeadShared& 
             }
         }
     }
+
+    flush();
 
     // append this warp's queue to the query's region of the partial array
     {
@@ -542,7 +610,67 @@ __global__ void __launch_bounds__(256) blockmax_kernel(const DevIndex ix, uint32
     if (lane == 0) bmax[b] = best;
 }
 
+// membership bitmaps of the mid-frequency terms: one warp per selected block sets the bits of its 128 docs
+__global__ void __launch_bounds__(256) bitmap_build_kernel(const DevIndex ix, const uint2* __restrict__ sel, uint32_t n_sel,
+                                                           uint32_t* bits, uint64_t stride_words) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t i = blockIdx.x * 8u + (threadIdx.x >> 5);
+    if (i >= n_sel) return;
+    const uint2 sb = __ldg(&sel[i]);
+    const uint4 e = __ldg(&ix.skip[sb.x]);
+    const uint32_t bd = e.w & 63u, n = ((e.w >> 12) & 127u) + 1u;
+    const uint32_t* wd = reinterpret_cast<const uint32_t*>(ix.blk + (size_t)e.z * 16u);
+    uint32_t g[4];
+    unpack4(wd, lane, bd, g);
+    g[1] += g[0]; g[2] += g[1]; g[3] += g[2];
+    const uint32_t off = warp_excl_scan(g[3], lane) + e.y + 4u * lane;
+    uint32_t* dst = bits + (size_t)sb.y * stride_words;
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+        if (4u * lane + (uint32_t)j < n) {
+            const uint32_t d = off + g[j] + (uint32_t)j;
+            atomicOr(dst + (d >> 5), 1u << (d & 31u));
+        }
+}
+// rank directory: postings before each 256-doc chunk; one CTA per bitmap, tiles of 256 chunks
+__global__ void __launch_bounds__(256) bitmap_rank_kernel(const uint32_t* __restrict__ bits, uint32_t* rank, uint64_t stride_words) {
+    __shared__ uint32_t part[8];
+    __shared__ uint32_t carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t* src = bits + (size_t)blockIdx.x * stride_words;
+    uint32_t* dst = rank + (size_t)blockIdx.x * (stride_words / 8);
+    const uint32_t n_chunks = (uint32_t)(stride_words / 8);
+    if (tid == 0) carry = 0u;
+    __syncthreads();
+    for (uint32_t c0 = 0; c0 < n_chunks; c0 += 256u) {
+        const uint32_t c = c0 + (uint32_t)tid;
+        uint32_t cnt = 0u;
+        if (c < n_chunks) {
+            const uint4 a = reinterpret_cast<const uint4*>(src)[2 * (size_t)c], b = reinterpret_cast<const uint4*>(src)[2 * (size_t)c + 1];
+            cnt = (uint32_t)(__popc(a.x) + __popc(a.y) + __popc(a.z) + __popc(a.w) + __popc(b.x) + __popc(b.y) + __popc(b.z) + __popc(b.w));
+        }
+        const uint32_t ex = warp_excl_scan(cnt, lane);
+        if (lane == 31) part[warp] = ex + cnt;
+        __syncthreads();
+        uint32_t base = carry;
+        for (int w = 0; w < warp; w++) base += part[w];
+        if (c < n_chunks) dst[c] = base + ex;
+        __syncthreads();
+        if (tid == 255) carry = base + ex + cnt;
+        __syncthreads();
+    }
+}
+
 }  // namespace
+
+void launch_bitmap_build(const DevIndex& ix, const uint2* sel, uint32_t n_sel, uint32_t* bits, uint64_t stride_words, void* stream) {
+    if (!n_sel) return;
+    FG_LAUNCH(bitmap_build_kernel, (n_sel + 7) / 8, 256, 0, (cudaStream_t)stream, ix, sel, n_sel, bits, stride_words);
+}
+void launch_bitmap_rank(const uint32_t* bits, uint32_t* rank, uint32_t n_slots, uint64_t stride_words, void* stream) {
+    if (!n_slots) return;
+    FG_LAUNCH(bitmap_rank_kernel, n_slots, 256, 0, (cudaStream_t)stream, bits, rank, stride_words);
+}
 
 void launch_lead(const LeadParams& p, int ks, int n_sms, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;

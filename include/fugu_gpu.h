@@ -106,7 +106,8 @@ typedef struct {
     uint32_t n_fields;
     uint64_t column_bytes;  /* dense tf columns of the most frequent terms (1 B per doc per column) */
     uint32_t n_columns;
-    uint32_t reserved;
+    uint32_t n_bitmaps;     /* membership bitmaps (+ rank directories) of the mid-frequency terms */
+    uint64_t bitmap_bytes;
 } fg_index_info;
 int32_t fg_index_get_info(const fg_index* index, fg_index_info* out);
 /* document frequency / layout of one term (host copy of the term table) */

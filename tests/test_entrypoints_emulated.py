@@ -28,10 +28,11 @@ def test_bench_main_emits_one_complete_json_line():
     assert d["metric"] == "queries_per_sec" and d["n_gpus"] == 1 and d["steps"] == 2 and d["value"] > 0
     assert "workload" in d["config"] and "model" not in d["config"]
     rf = d["roofline"]
-    for key in ("bound", "achieved", "peak", "unit", "frac", "traffic", "pruning", "exhaustive_bytes_per_launch"):
+    for key in ("bound", "achieved", "peak", "unit", "frac", "traffic", "touched", "exhaustive"):
         assert key in rf, key
-    assert rf["bound"] == "hbm" and 0 < rf["algorithmic_bytes_per_launch"] <= rf["exhaustive_bytes_per_launch"]
-    assert rf["pruning"]["colscan_chunks"] >= rf["pruning"]["colscan_chunks_skipped"] >= 0
+    assert rf["bound"] == "hbm" and 0 < rf["algorithmic_bytes_per_launch"] <= rf["exhaustive"]["algorithmic_bytes_per_launch"]
+    assert rf["touched"]["lead_blocks_tested"] >= rf["touched"]["lead_blocks_decoded"] > 0
+    assert d["parity"]["checked"] > 0 and d["parity"]["failed"] == 0, d["parity"]
     assert abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-12
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] > 0 and "sample" in cb

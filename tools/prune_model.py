@@ -18,6 +18,8 @@ sys.path.insert(0, ".")
 from fugu_b200 import synth  # noqa: E402
 
 K1, B = 1.2, 0.75
+import os
+ORDER = os.environ.get("ORDER", "df")
 
 
 def fn_table():
@@ -49,7 +51,7 @@ def main():
         caches.append((K1 * (1 - B + B * tab / avg)).astype(np.float32))
     qs = synth.gen_queries(cfg)
     k = cfg.k
-    tot_exh = tot_touch = tot_lead_blocks = 0
+    tot_exh = tot_touch = tot_lead_blocks = tot_cand = 0
     by_shape = {}
     for q in qs:
         s = q["query"]
@@ -105,7 +107,7 @@ def main():
                 touch += int(keep.sum()) * 128
                 tot_lead_blocks += nb
         else:
-            leaves = sorted([l for cl in clauses for l in cl], key=lambda l: -float(l[2] * l[3].max()))
+            leaves = sorted([l for cl in clauses for l in cl], key=lambda l: (len(l[0]) if ORDER == "df" else -float(l[2] * l[3].max())))
             ubs = [float(l[2] * l[3].max()) for l in leaves]
             touch = 0
             for i, (docs, sc, w, fac) in enumerate(leaves):
@@ -119,11 +121,15 @@ def main():
                 keep = bm + rest >= theta * (1 - 1e-6)
                 touch += int(keep.sum()) * 128
                 tot_lead_blocks += nb
+                surv = (pad.reshape(nb, 128)[keep] + rest >= theta * (1 - 1e-6)) & (pad.reshape(nb, 128)[keep] > 0)
+                tot_cand += int(surv.sum())
+                cand_q = cand_q + int(surv.sum()) if 'cand_q' in dir() else int(surv.sum())
         tot_exh += exh
         tot_touch += touch
         key = ("AND" if conj else "OR", len(words))
         a = by_shape.setdefault(key, [0, 0, 0])
         a[0] += 1; a[1] += exh; a[2] += touch
+    print(f"OR candidates surviving the per-posting bound (best-case theta): {tot_cand:,}")
     print(f"queries {len(qs)}  exhaustive postings {tot_exh:,}  touched (best-case theta) {tot_touch:,}  ratio {tot_touch / max(tot_exh, 1):.3f}")
     for key in sorted(by_shape):
         n, e, t = by_shape[key]
