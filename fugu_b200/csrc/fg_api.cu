@@ -111,7 +111,7 @@ struct fg_ctx {
     bool env_no_prune = false;    // FG_NO_PRUNE=1: exhaustive evaluation (A/B runs; results are identical)
     bool env_timing = false;      // FG_TIMING=1
     bool env_prof = false;        // FG_PROF=1
-    uint32_t lead_par_blocks = 16, lead_max_par = 64, lead_chunk = 16;
+    uint32_t lead_par_blocks = 16, lead_max_par = 64, lead_chunk = 16, lead_round4 = 1;
 };
 static uint64_t env_u64_early(const char* name, uint64_t dflt);
 
@@ -195,6 +195,7 @@ extern "C" int32_t fg_ctx_create(int32_t device, fg_ctx** out) {
     c->lead_par_blocks = (uint32_t)std::max<uint64_t>(1, env_u64_early("FG_LEAD_PAR_BLOCKS", 16));
     c->lead_max_par = (uint32_t)std::max<uint64_t>(1, env_u64_early("FG_LEAD_MAX_PAR", 64));
     c->lead_chunk = (uint32_t)std::max<uint64_t>(1, env_u64_early("FG_LEAD_CHUNK", 16));
+    c->lead_round4 = (uint32_t)env_u64_early("FG_LEAD_ROUND4", 1);
     CU(cudaStreamCreateWithFlags(&c->own, cudaStreamNonBlocking));
     c->stream = c->own;
     for (int i = 0; i < NCLS - 1; i++) {
@@ -629,7 +630,7 @@ extern "C" int32_t fg_index_upload(fg_ctx* ctx, const fg_index_desc* d, fg_index
     // gather, and only a hit goes on to its posting (rank -> block, position -> tf stream). Built on the device
     // from the posting blocks. 180 GB of HBM3e pays for it: n_docs/8 * 1.125 bytes per term.
     {
-        const uint64_t bm_min_df = env_u64_early("FG_BITMAP_MIN_DF", 1024);
+        const uint64_t bm_min_df = env_u64_early("FG_BITMAP_MIN_DF", 512);
         const uint64_t budget = env_u64_early("FG_BITMAP_MAX_MB", 16384) << 20;
         const uint64_t stride_words = (((uint64_t)d->n_docs + 255) / 256) * 8 + 8;
         const uint64_t per_term = stride_words * 4 + stride_words / 2;
@@ -1001,6 +1002,12 @@ static int32_t prepare_lead(fg_index* ix, const fg_query_batch* qb, uint32_t pre
             }
             total = tail;
             D.slack = total * 1e-5f + 1e-30f;
+            {
+                const float ubt = total * 1.0001f + const_score;  // no score of this query lies above it
+                uint32_t bits;
+                memcpy(&bits, &ubt, 4);
+                D.hist_base = ubt > 0.f ? std::max<uint32_t>(bits >> LHIST_SHIFT, (uint32_t)LHIST_B) : (uint32_t)LHIST_B;
+            }
             if (positive) D.flags |= LQ_PRUNE;
             // a lower bound of the k-th best score known before anything runs: the k-th largest block maximum of
             // a lead of a pure union (k distinct docs reach it with that one leaf alone, the others only add)
@@ -1099,7 +1106,7 @@ static int32_t prepare_lead(fg_index* ix, const fg_query_batch* qb, uint32_t pre
     if ((rc = up(lq.data(), lq.size() * sizeof(LQuery), (void**)&b->l_queries, &b->lsz[0]))) return rc;
     if ((rc = up(leaves.data(), leaves.size() * sizeof(LLeaf), (void**)&b->l_leaves, &b->lsz[1]))) return rc;
     if ((rc = up(items.data(), items.size() * sizeof(LItem), (void**)&b->l_items, &b->lsz[2]))) return rc;
-    b->lsz[3] = ((size_t)1 + n_cursors + 3 * (size_t)b->n_queries) * 4 + 16;
+    b->lsz[3] = ((size_t)4 + n_cursors + (3 + (size_t)LHIST_B) * (size_t)b->n_queries) * 4 + 32;
     CU(pool_alloc(ctx, (void**)&b->l_state, b->lsz[3]));
     b->sz[3] = std::max<size_t>((size_t)part_entries * 8, 16);
     CU(pool_alloc(ctx, (void**)&b->d_partial, b->sz[3]));
@@ -1521,6 +1528,9 @@ extern "C" int32_t fg_batch_execute(fg_batch* b, uint32_t flags, uint32_t k_stri
         p.qtheta = p.cursors + b->n_cursors;
         p.qcount = p.qtheta + b->n_queries;
         p.qmatch = p.qcount + b->n_queries;
+        p.qhist = b->l_state + (((size_t)1 + b->n_cursors + 3 * (size_t)b->n_queries + 3) & ~(size_t)3);  // 16-byte aligned
+        p.exhaustive = (d_match_count || d_match_bitmap || (flags & FG_EXEC_NO_PRUNE) || ctx->env_no_prune) ? 1 : 0;
+        if (!p.exhaustive) CU(cudaMemsetAsync(p.qhist, 0, (size_t)b->n_queries * LHIST_B * 4, st));
         p.partial = b->d_partial;
         p.stats = b->d_stats;
         p.match_bitmap = (uint32_t*)d_match_bitmap;
@@ -1528,6 +1538,7 @@ extern "C" int32_t fg_batch_execute(fg_batch* b, uint32_t flags, uint32_t k_stri
         p.want_counts = d_match_count ? 1 : 0;
         p.exhaustive = (d_match_count || d_match_bitmap || (flags & FG_EXEC_NO_PRUNE) || ctx->env_no_prune) ? 1 : 0;
         p.acct = (flags & FG_EXEC_COUNTERS) ? 1 : 0;
+        p.round4 = ctx->lead_round4;
         CU(cudaEventRecord(b->ev[0], st));
         launch_lead(p, b->ks, ctx->n_sms, st);
         CU(cudaEventRecord(b->ev[1], st));

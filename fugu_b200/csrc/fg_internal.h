@@ -172,6 +172,8 @@ int search_smem_bytes(int ks, bool pure);
 // block is decoded only if weight * bmax[block] + rest >= theta, a candidate is looked up only while
 // its partial score + the upper bounds of the leaves not applied yet >= theta.
 constexpr int LMAX_LEAVES = 32;   // live leaves per query (16 words x [text, name])
+constexpr int LHIST_B = 128;
+constexpr int LHIST_SHIFT = 17;
 enum : uint32_t { LR_LEAD = 0, LR_REQ = 1, LR_OPT = 2, LR_NOT = 3 };
 struct LLeaf {
     uint32_t blk_begin, n_blocks;
@@ -199,8 +201,15 @@ struct LQuery {
     uint32_t part_begin; // this query's region of the partial array
     uint32_t part_cap;
     uint32_t theta0;     // sortable f32 lower bound of the k-th best score known at lowering time, 0 = none
+    uint32_t hist_base;  // (f32 bits of the query's total upper bound) >> LHIST_SHIFT: top bucket of its score histogram
+    uint32_t pad[3];
 };
-static_assert(sizeof(LQuery) == 48, "LQuery is uploaded as a flat array");
+static_assert(sizeof(LQuery) == 64, "LQuery is uploaded as a flat array");
+// Shared threshold of a query: every warp adds the score of each hit it accepts to a per-query histogram
+// (global atomics; a document is offered exactly once across all warps). Bucket = the score's f32 bits
+// >> LHIST_SHIFT (sign, exponent, 6 mantissa bits: 64 buckets per octave, exact and monotone), relative to
+// the bucket of the query's total upper bound; LHIST_B buckets cover the two octaves below it. The lower edge
+// of the highest bucket at which the counts from the top reach k is a lower bound of the k-th best score.
 struct LItem {
     uint32_t query;
     uint32_t lead;    // lead leaf (index inside the query) this item walks
@@ -220,6 +229,7 @@ struct LeadParams {
     uint32_t* qtheta;          // [n_queries] sortable f32 threshold shared by all warps of a query
     uint32_t* qcount;          // [n_queries] entries appended to the query's partial region
     uint32_t* qmatch;          // [n_queries] matching docs (exhaustive form)
+    uint32_t* qhist;           // [n_queries][LHIST_B] score histogram of the accepted hits (pruned form)
     uint64_t* partial;
     unsigned long long* stats; // [8]
     uint32_t* match_bitmap;
@@ -227,6 +237,7 @@ struct LeadParams {
     uint32_t exhaustive;       // visit every posting (match counts / bitmaps wanted, or pruning switched off)
     uint32_t want_counts;
     uint32_t acct;
+    uint32_t round4;           // evaluate candidates 128 at a time (4 per lane) instead of 32
 };
 struct LeadMergeParams {
     const LQuery* queries;
@@ -247,7 +258,7 @@ void launch_lead_merge(const LeadMergeParams& p, int ks, void* stream);
 // block-max metadata of the blocks [b0, b1) of one field (upload time)
 void launch_blockmax(const DevIndex& ix, uint32_t b0, uint32_t b1, int fn_field, float cnorm, float* bmax, void* stream);
 // membership bitmaps + rank directories of selected terms (upload time): sel[i] = {global block, bitmap slot};
-// bits / rank are zeroed by the caller, stride_words is a multiple of 8
+// bits is zeroed by the caller, stride_words is a multiple of 8
 void launch_bitmap_build(const DevIndex& ix, const uint2* sel, uint32_t n_sel, uint32_t* bits, uint64_t stride_words, void* stream);
 void launch_bitmap_rank(const uint32_t* bits, uint32_t* rank, uint32_t n_slots, uint64_t stride_words, void* stream);
 

@@ -19,6 +19,8 @@
 #include <math.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "fg_device.h"
 #include "fg_internal.h"
 
@@ -30,8 +32,9 @@ namespace {
 
 constexpr int LNT = 256;      // threads per CTA
 constexpr int LNW = LNT / 32; // warps per CTA
-constexpr int LC = 8;         // decoded lookup blocks cached per warp (slot = LLeaf::slot, assigned by the lowering)
-constexpr int CAND_CAP = BLOCK + 32;  // candidates wait here until a full round of 32 is available
+constexpr int LC = 4;         // decoded lookup blocks cached per warp (slot = LLeaf::slot, assigned by the lowering)
+constexpr int ROUND = 128;            // candidates evaluated together: 4 per lane (4 independent gathers in flight per lookup)
+constexpr int CAND_CAP = 2 * BLOCK;   // candidates wait here until a full round is available
 
 struct WarpShared {
     LLeaf leaf[LMAX_LEAVES];
@@ -52,6 +55,7 @@ struct Acct {
     unsigned long long block_bytes = 0;   // payload + 16 B skip entry of every block decoded (lead or lookup)
     unsigned long long meta_bytes = 0;    // block-max words and skip entries read while skipping
     unsigned long long gathers = 0;       // 1-byte gathers: fieldnorm ids, column bytes, alive bits
+    unsigned long long gathers_l = 0, block_bytes_l = 0;  // the same, counted per lane (summed over the warp at the end)
     unsigned long long lead_blocks = 0, lead_blocks_seen = 0;
 };
 
@@ -200,14 +204,11 @@ __device__ __forceinline__ void run_item(const LeadParams& p, const LeadShared& 
         if (lane < LC) W.ctag[lane] = EMPTY;
     }
     __syncwarp();
-#ifdef FG_DEBUG_LEAD
-    if (lane == 0) printf("item q=%u lead=%u cursor=%u nleaves=%u leaf_begin=%u part_begin=%u L0.blk=%u L0.nb=%u L1.blk=%u L1.nb=%u\n", item.query, item.lead, item.cursor, q.n_leaves, q.leaf_begin, q.part_begin, W.leaf[0].blk_begin, W.leaf[0].n_blocks, W.leaf[1].blk_begin, W.leaf[1].n_blocks);
-#endif
     const int k = (int)q.k;
     const bool prune = !p.exhaustive && (q.flags & LQ_PRUNE);
     const bool acct = p.acct != 0;
     const LLeaf LD = W.leaf[item.lead];
-    const int n_lead = (int)q.n_lead, n_req = (int)q.n_req, n_opt = (int)q.n_opt, n_leaves = (int)q.n_leaves;
+    const int n_lead = (int)q.n_lead, n_req = (int)q.n_req, n_leaves = (int)q.n_leaves;
     const int lead = (int)item.lead;
     const bool has_req = n_req != 0;
     const uint4* __restrict__ sk = p.ix.skip + LD.blk_begin;
@@ -222,247 +223,328 @@ __device__ __forceinline__ void run_item(const LeadParams& p, const LeadShared& 
     float theta = -INFINITY;  // a candidate needs score >= theta (ties are decided by the doc id in the queue)
     uint32_t pub = 0u;        // sortable threshold this warp has seen or published
     uint32_t n_match = 0u;
-    uint32_t ncand = 0u;      // candidates waiting in W.cand_* (< 32 between blocks)
+    uint32_t ncand = 0u;      // candidates waiting in W.cand_* (fewer than a round between blocks)
 
-    auto pull = [&]() {
-        if (prune) {
-            const uint32_t g = __ldcg(p.qtheta + item.query);
-            if (g > pub) {
-                pub = g;
-                theta = fmaxf(theta, unsortable(g));
-            }
-        }
-    };
     auto norm_of = [&](const LLeaf& L, uint32_t c) -> float {
         return L.fn_field >= 0 ? S.cache[L.fn_field * 256 + (int)__ldg(p.ix.fnorm[L.fn_field] + c)] : L.cnorm;
     };
-    auto lookup = [&](int j, const LLeaf& L, uint32_t c, bool live, bool need_tf) -> uint32_t {
-        if (L.col) {
-            if (acct) A.gathers += (unsigned long long)__popc(__ballot_sync(FULL, live));
-            return live ? (uint32_t)__ldg(L.col + c) : 0u;
+
+    // ---- state of the block walk: chunk [g0 .. b1) claimed from the lead's cursor, current group of 32 blocks ----
+    uint32_t g0 = 0u, b1 = 0u;
+    unsigned m = 0u;     // blocks of the current group still to decode
+    uint4 eg = make_uint4(0u, 0u, 0u, 0u);  // this lane's skip entry of the group
+    float bound = INFINITY;                 // ... and its block's upper bound
+    bool fin = false;    // nothing left to decode (list exhausted, or the lead cannot contribute a hit any more)
+    {
+        if (prune) {
+            const uint32_t g = __ldcg(p.qtheta + item.query);
+            if (g > pub) { pub = g; theta = fmaxf(theta, unsortable(g)); }
         }
-        if (L.bits) {
-            // membership bit first (one 4-byte gather; most lookups miss); a hit finds its posting through the
-            // rank directory: position = postings before the doc, block = position / 128, tf from the block's tf stream
-            uint32_t tf = 0u;
-            if (live) {
-                const uint32_t wv = __ldg(L.bits + (c >> 5));
-                if ((wv >> (c & 31u)) & 1u) {
-                    tf = 1u;
-                    if (need_tf) {
-                        const uint32_t w0 = (c >> 8) << 3, wl = c >> 5;
-                        uint32_t r = __ldg(L.rank + (c >> 8)) + (uint32_t)__popc(wv & ((1u << (c & 31u)) - 1u));
-                        for (uint32_t w = w0; w < wl; w++) r += (uint32_t)__popc(__ldg(L.bits + w));
-                        const uint4 e = __ldg(p.ix.skip + L.blk_begin + (r >> 7));
-                        tf = extract_tf(p.ix.blk, e, r & 127u);
+        fin = prune && LD.ub + rest_s < theta;
+    }
+
+    while (true) {
+        // ================= next block to decode, if any =================
+        bool have = false;
+        uint4 e = make_uint4(0u, 0u, 0u, 0u);
+        while (!fin && !have) {
+            if (prune && m) m &= __ballot_sync(FULL, bound >= theta);  // the threshold may have risen
+            if (m) {
+                const int src = __ffs(m) - 1;
+                m &= m - 1;
+                e.x = __shfl_sync(FULL, eg.x, src);
+                e.y = __shfl_sync(FULL, eg.y, src);
+                e.z = __shfl_sync(FULL, eg.z, src);
+                e.w = __shfl_sync(FULL, eg.w, src);
+                have = true;
+                break;
+            }
+            if (g0 >= b1) {  // claim the next chunk of the lead
+                uint32_t c0 = 0u;
+                if (lane == 0) c0 = atomicAdd(p.cursors + item.cursor, item.chunk);
+                c0 = __shfl_sync(FULL, c0, 0);
+                if (c0 >= LD.n_blocks) { fin = true; break; }
+                g0 = c0;
+                b1 = min(c0 + item.chunk, LD.n_blocks);
+            }
+            if (prune) {
+                const uint32_t g = __ldcg(p.qtheta + item.query);
+                if (g > pub) { pub = g; theta = fmaxf(theta, unsortable(g)); }
+                if (LD.ub + rest_s < theta) { fin = true; break; }
+            }
+            const uint32_t b = g0 + lane;
+            bound = INFINITY;
+            if (b < b1) eg = __ldg(&sk[b]);  // the group's skip entries: one coalesced request, independent of the bound load
+            if (prune && b < b1) bound = LD.weight * __ldg(bmx + b) + rest_s;
+            if (acct) {
+                A.lead_blocks_seen += min(32u, b1 - g0);
+                A.meta_bytes += (prune ? 20u : 16u) * min(32u, b1 - g0);
+            }
+            m = __ballot_sync(FULL, b < b1 && bound >= theta);
+            if ((m >> lane) & 1u) {  // payloads of the blocks that will be decoded: on their way while earlier ones are processed
+                const uint8_t* pp = p.ix.blk + (size_t)eg.z * 16u;
+                prefetch_l2(pp);
+                if (((eg.w & 63u) + ((eg.w >> 6) & 63u)) > 8u) prefetch_l2(pp + 128);
+            }
+            g0 += 32u;
+        }
+
+        // ================= decode the lead block, keep the postings that can still reach the top-k =================
+        if (have) {
+            const uint32_t bd = e.w & 63u, bt = (e.w >> 6) & 63u, n = ((e.w >> 12) & 127u) + 1u;
+            const uint32_t* wd = reinterpret_cast<const uint32_t*>(p.ix.blk + (size_t)e.z * 16u);
+            uint32_t g[4], t[4];
+            unpack4(wd, lane, bd, g);
+            unpack4(wd + 4 * bd, lane, bt, t);
+            g[1] += g[0]; g[2] += g[1]; g[3] += g[2];
+            const uint32_t off = warp_excl_scan(g[3], lane) + e.y + 4u * lane;
+            uint32_t d[4], val[4];
+            bool ok[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                d[j] = off + g[j] + (uint32_t)j;
+                ok[j] = 4u * lane + (uint32_t)j < n;
+            }
+            if (acct) {
+                A.block_bytes += ((n * bd + 7u) >> 3) + ((n * bt + 7u) >> 3) + 16u;
+                A.lead_blocks++;
+            }
+            if (!has_req) {
+                uint32_t id[4] = {0u, 0u, 0u, 0u};
+                if (LD.fn_field >= 0) {
+                    const uint8_t* __restrict__ fn = p.ix.fnorm[LD.fn_field];
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                        if (ok[j]) id[j] = __ldg(fn + d[j]);
+                    if (acct) A.gathers += n;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const float nrm = LD.fn_field >= 0 ? S.cache[LD.fn_field * 256 + (int)id[j]] : LD.cnorm;
+                    const float s = LD.weight * tf_factor((float)(t[j] + 1u), nrm);
+                    if (prune) ok[j] = ok[j] && (s + rest_s >= theta);
+                    val[j] = __float_as_uint(s);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; j++) val[j] = t[j] + 1u;  // required clauses first: the lead is scored for the survivors only
+            }
+            const unsigned m0 = __ballot_sync(FULL, ok[0]), m1 = __ballot_sync(FULL, ok[1]), m2 = __ballot_sync(FULL, ok[2]),
+                           m3 = __ballot_sync(FULL, ok[3]);
+            const uint32_t total = (uint32_t)(__popc(m0) + __popc(m1) + __popc(m2) + __popc(m3));
+            if (total) {
+                uint32_t pos = ncand + (uint32_t)(__popc(m0 & lt) + __popc(m1 & lt) + __popc(m2 & lt) + __popc(m3 & lt));
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    if (ok[j]) {
+                        W.cand_doc[pos] = d[j];
+                        W.cand_val[pos] = val[j];
+                        pos++;
+                    }
+                ncand += total;
+                __syncwarp();
+            }
+        }
+
+        // ================= evaluate a round of candidates =================
+        // A full round (128: 4 per lane, so every lookup has 4 independent gathers in flight) as soon as it is there;
+        // whatever is left when the walk ends. Candidate 32*r + lane of the round belongs to this lane: every r is an
+        // ascending run over the lanes (what probe() needs).
+        if (ncand >= (uint32_t)ROUND || (fin && ncand)) {
+            const uint32_t cnt = min(ncand, (uint32_t)ROUND);
+            const int nr = (int)((cnt + 31u) >> 5);  // rows in use (uniform): rows >= nr are skipped
+            uint32_t c[4], v[4], tf[4], lv = 0u;
+            float sc[4];
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                const uint32_t idx = 32u * r + lane;
+                c[r] = 0xFFFFFFFFu;
+                v[r] = 0u;
+                sc[r] = 0.f;
+                tf[r] = 0u;
+                if (idx < cnt) {
+                    lv |= 1u << r;
+                    c[r] = W.cand_doc[idx];
+                    v[r] = W.cand_val[idx];
+                }
+            }
+            float rem = LD.rest;
+            if (!has_req) {
+#pragma unroll
+                for (int r = 0; r < 4; r++) {
+                    sc[r] = __uint_as_float(v[r]);
+                    // (the threshold may have risen while the candidate waited)
+                    if (prune && !(sc[r] + rest_s >= theta)) lv &= ~(1u << r);
+                }
+            }
+            // The other leaves in evaluation order: required clauses (a candidate must occur in every one), the earlier
+            // leads (a candidate that occurs in one is scored by that lead's items: dropped here), the later leads and
+            // the optional leaves (add their scores), the excluded leaves (drop on a hit).
+            uint32_t found = 0u, clause = has_req ? (W.leaf[n_lead].role >> 8) : 0u;
+            const int n_steps = n_leaves - 1;
+            for (int s = 0; s <= n_steps; s++) {
+                if (has_req && s == n_req) {  // all required clauses seen: close the last one, score the lead
+                    lv &= found;
+#pragma unroll
+                    for (int r = 0; r < 4; r++)
+                        if ((lv >> r) & 1u) {
+                            sc[r] += LD.weight * tf_factor((float)v[r], norm_of(LD, c[r]));
+                            if (prune && !(sc[r] + rem + slack >= theta)) lv &= ~(1u << r);
+                        }
+                    if (acct) A.gathers_l += (unsigned long long)__popc(lv);
+                }
+                if (s == n_steps || !__any_sync(FULL, lv)) break;
+                int j, mode;  // mode 0 required, 1 drop on hit, 2 add
+                if (s < n_req) { j = n_lead + s; mode = 0; }
+                else {
+                    const int s2 = s - n_req;
+                    if (s2 < lead) { j = s2; mode = 1; }
+                    else if (s2 < n_lead - 1) { j = s2 + 1; mode = 2; }
+                    else { j = s2 + 1 + n_req; mode = j < n_lead + n_req + (int)q.n_opt ? 2 : 1; }
+                }
+                const LLeaf& L = W.leaf[j];
+                if (mode == 0) {
+                    const uint32_t cl = L.role >> 8;
+                    if (cl != clause) {
+                        lv &= found;
+                        found = 0u;
+                        clause = cl;
+                        if (!__any_sync(FULL, lv)) break;
+                    }
+                }
+                const bool need_tf = mode != 1;
+                // ---- term frequencies of the candidates in leaf j (0 = absent) ----
+                if (L.col) {  // dense tf column: one byte per doc
+#pragma unroll
+                    for (int r = 0; r < 4; r++) tf[r] = ((lv >> r) & 1u) ? (uint32_t)__ldg(L.col + c[r]) : 0u;
+                    if (acct) A.gathers_l += (unsigned long long)__popc(lv);
+                } else if (L.bits) {
+                    // membership bit first (one 4-byte gather per candidate, all in flight together; most lookups miss); a hit
+                    // finds its posting through the rank directory: position = postings before the doc, block = position / 128
+                    uint32_t wv[4];
+#pragma unroll
+                    for (int r = 0; r < 4; r++) wv[r] = ((lv >> r) & 1u) ? __ldg(L.bits + (c[r] >> 5)) : 0u;
+#pragma unroll
+                    for (int r = 0; r < 4; r++) {
+                        tf[r] = (wv[r] >> (c[r] & 31u)) & 1u;
+                        if (tf[r] && need_tf) {
+                            const uint32_t w0 = (c[r] >> 8) << 3, wl = c[r] >> 5;
+                            uint32_t rk = __ldg(L.rank + (c[r] >> 8)) + (uint32_t)__popc(wv[r] & ((1u << (c[r] & 31u)) - 1u));
+                            for (uint32_t w = w0; w < wl; w++) rk += (uint32_t)__popc(__ldg(L.bits + w));
+                            const uint4 e2 = __ldg(p.ix.skip + L.blk_begin + (rk >> 7));
+                            tf[r] = extract_tf(p.ix.blk, e2, rk & 127u);
+                            if (acct) A.block_bytes_l += 56ull;
+                        }
+                    }
+                    if (acct) A.gathers_l += 4ull * (unsigned long long)__popc(lv);
+                } else {
+#pragma unroll 1
+                    for (int r = 0; r < nr; r++) {
+                        const uint32_t cr = r == 0 ? c[0] : r == 1 ? c[1] : r == 2 ? c[2] : c[3];
+                        const uint32_t t1 = probe(p, W, j, L, cr, ((lv >> r) & 1u) != 0u, need_tf, lane, A);
+                        if (r == 0) tf[0] = t1; else if (r == 1) tf[1] = t1; else if (r == 2) tf[2] = t1; else tf[3] = t1;
+                    }
+                }
+                // ---- what a hit means ----
+                if (mode == 1) {
+#pragma unroll
+                    for (int r = 0; r < 4; r++)
+                        if (tf[r]) lv &= ~(1u << r);
+                } else {
+                    rem -= L.ub;
+#pragma unroll
+                    for (int r = 0; r < 4; r++) {
+                        if (tf[r]) {
+                            sc[r] += L.weight * tf_factor((float)tf[r], norm_of(L, c[r]));
+                            found |= 1u << r;
+                        }
+                        if (mode == 2 && prune && !(sc[r] + rem + slack >= theta)) lv &= ~(1u << r);
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < 4; r++) tf[r] = 0u;
+            }
+            if (p.ix.alive) {
+#pragma unroll
+                for (int r = 0; r < 4; r++)
+                    if (((lv >> r) & 1u) && !((__ldg(p.ix.alive + (c[r] >> 5)) >> (c[r] & 31u)) & 1u)) lv &= ~(1u << r);
+            }
+            if (__any_sync(FULL, lv)) {
+                uint32_t* hq = p.qhist + (size_t)item.query * LHIST_B;
+#pragma unroll 1
+                for (int r = 0; r < nr; r++) {
+                    const uint32_t cr = r == 0 ? c[0] : r == 1 ? c[1] : r == 2 ? c[2] : c[3];
+                    const float sr = (r == 0 ? sc[0] : r == 1 ? sc[1] : r == 2 ? sc[2] : sc[3]) + q.const_score;
+                    const bool live = ((lv >> r) & 1u) != 0u;
+                    if (p.exhaustive) {
+                        n_match += (uint32_t)__popc(__ballot_sync(FULL, live));
+                        if (p.match_bitmap && live)
+                            atomicOr(p.match_bitmap + (size_t)item.query * p.bitmap_words + (cr >> 5), 1u << (cr & 31u));
+                    }
+                    tk.offer(live, make_key(sr, cr), k, lane);
+                    if (prune && live) {  // the query-wide histogram of accepted scores (fg_internal.h)
+                        int idx = (int)(__float_as_uint(sr) >> LHIST_SHIFT) - (int)q.hist_base + (LHIST_B - 1);
+                        idx = sr > 0.f ? min(max(idx, 0), LHIST_B - 1) : 0;
+                        atomicAdd(hq + idx, 1u);
+                    }
+                }
+                if (prune) {
+                    // this warp's own k-th best, and the k-th best the histogram proves for the whole query
+                    uint32_t best = tk.theta ? (uint32_t)(tk.theta >> 32) : 0u;
+                    __syncwarp();
+                    const uint4 h4 = __ldcg(reinterpret_cast<const uint4*>(hq) + lane);  // buckets 4*lane .. 4*lane+3
+                    const uint32_t mine = h4.x + h4.y + h4.z + h4.w;
+                    uint32_t above = mine;  // inclusive suffix sum over the lanes
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t y = __shfl_down_sync(FULL, above, o);
+                        if (lane + o < 32) above += y;
+                    }
+                    above -= mine;  // counts in the buckets above this lane's
+                    int hit = -1;   // highest bucket of this lane at which the count from the top reaches k
+                    uint32_t acc = above + h4.w;
+                    if (acc >= (uint32_t)k) hit = 4 * lane + 3;
+                    else if ((acc += h4.z) >= (uint32_t)k) hit = 4 * lane + 2;
+                    else if ((acc += h4.y) >= (uint32_t)k) hit = 4 * lane + 1;
+                    else if ((acc += h4.x) >= (uint32_t)k) hit = 4 * lane;
+#pragma unroll
+                    for (int o = 16; o; o >>= 1) hit = max(hit, __shfl_xor_sync(FULL, hit, o));
+                    if (hit > 0) {  // bucket 0 collects everything below the window: no bound
+                        const float edge = __uint_as_float((q.hist_base - (uint32_t)(LHIST_B - 1) + (uint32_t)hit) << LHIST_SHIFT);
+                        best = max(best, sortable(edge));
+                    }
+                    if (best > pub) {
+                        pub = best;
+                        theta = fmaxf(theta, unsortable(best));
+                        if (lane == 0) atomicMax(p.qtheta + item.query, best);
                     }
                 }
             }
-            if (acct) {
-                A.gathers += 4ull * (unsigned long long)__popc(__ballot_sync(FULL, live));
-                A.block_bytes += 56ull * (unsigned long long)__popc(__ballot_sync(FULL, tf != 0u && need_tf));
-            }
-            return tf;
-        }
-        return probe(p, W, j, L, c, live, need_tf, lane, A);
-    };
-
-    // one round of up to 32 candidates, one per lane, ascending: c = doc, v = lead score bits or lead tf
-    auto evaluate = [&](bool live, uint32_t c, uint32_t v) {
-        float sc, rem = LD.rest;
-        if (has_req) {
-            sc = 0.f;
-            bool found = false;
-            uint32_t clause = W.leaf[n_lead].role >> 8;
-            for (int j = n_lead; j < n_lead + n_req; j++) {
-                const LLeaf& L = W.leaf[j];
-                const uint32_t cl = L.role >> 8;
-                if (cl != clause) {
-                    live = live && found;
-                    found = false;
-                    clause = cl;
-                    if (!__any_sync(FULL, live)) return;
+            // candidates behind the round move to the front
+            const uint32_t left = ncand - cnt;
+            if (left) {
+                uint32_t cd0[4], cv0[4];
+#pragma unroll
+                for (int r = 0; r < 4; r++) {
+                    const uint32_t idx = 32u * r + lane;
+                    cd0[r] = idx < left ? W.cand_doc[cnt + idx] : 0u;
+                    cv0[r] = idx < left ? W.cand_val[cnt + idx] : 0u;
                 }
-                const uint32_t tf = lookup(j, L, c, live, true);
-                if (tf) {
-                    sc += L.weight * tf_factor((float)tf, norm_of(L, c));
-                    found = true;
+                __syncwarp();
+#pragma unroll
+                for (int r = 0; r < 4; r++) {
+                    const uint32_t idx = 32u * r + lane;
+                    if (idx < left) {
+                        W.cand_doc[idx] = cd0[r];
+                        W.cand_val[idx] = cv0[r];
+                    }
                 }
-                rem -= L.ub;
-            }
-            live = live && found;
-            if (!__any_sync(FULL, live)) return;
-            if (live) sc += LD.weight * tf_factor((float)v, norm_of(LD, c));
-            if (acct) A.gathers += (unsigned long long)__popc(__ballot_sync(FULL, live));
-            if (prune) live = live && (sc + rem + slack >= theta);
-        } else {
-            sc = __uint_as_float(v);
-            if (prune) live = live && (sc + rest_s >= theta);  // the threshold may have risen while the candidate waited
-        }
-        // a candidate that also occurs in an earlier lead was (or will be) scored by that lead's items
-        for (int j = 0; j < lead; j++) {
-            if (!__any_sync(FULL, live)) return;
-            const uint32_t tf = lookup(j, W.leaf[j], c, live, false);
-            live = live && tf == 0u;
-        }
-        // later leads, then optional leaves, add their scores
-        for (int j = lead + 1; j < n_lead + n_req + n_opt; j++) {
-            if (j == n_lead) {
-                j += n_req;
-                if (j >= n_lead + n_req + n_opt) break;
-            }
-            if (!__any_sync(FULL, live)) return;
-            const LLeaf& L = W.leaf[j];
-            const uint32_t tf = lookup(j, L, c, live, true);
-            if (tf) sc += L.weight * tf_factor((float)tf, norm_of(L, c));
-            rem -= L.ub;
-            if (prune) live = live && (sc + rem + slack >= theta);
-        }
-        for (int j = n_lead + n_req + n_opt; j < n_leaves; j++) {
-            if (!__any_sync(FULL, live)) return;
-            const uint32_t tf = lookup(j, W.leaf[j], c, live, false);
-            live = live && tf == 0u;
-        }
-        if (p.ix.alive) live = live && ((__ldg(p.ix.alive + (live ? (c >> 5) : 0u)) >> (c & 31u)) & 1u);
-        const unsigned mm = __ballot_sync(FULL, live);
-        if (!mm) return;
-        sc += q.const_score;
-        if (p.exhaustive) {
-            n_match += (uint32_t)__popc(mm);
-            if (p.match_bitmap && live)
-                atomicOr(p.match_bitmap + (size_t)item.query * p.bitmap_words + (c >> 5), 1u << (c & 31u));
-        }
-#ifdef FG_DEBUG_LEAD
-        if (live) printf("    q=%u offer doc %u score %f (lane %d)\n", item.query, c, sc, lane);
-#endif
-        tk.offer(live, make_key(sc, c), k, lane);
-        if (prune && tk.theta) {
-            const uint32_t own = (uint32_t)(tk.theta >> 32);
-            if (own > pub) {
-                pub = own;
-                theta = fmaxf(theta, unsortable(own));
-                if (lane == 0) atomicMax(p.qtheta + item.query, own);
-            }
-        }
-    };
-
-    auto process_block = [&](uint32_t b) {
-        const uint4 e = __ldg(&sk[b]);
-        const uint32_t bd = e.w & 63u, bt = (e.w >> 6) & 63u, n = ((e.w >> 12) & 127u) + 1u;
-        const uint32_t* wd = reinterpret_cast<const uint32_t*>(p.ix.blk + (size_t)e.z * 16u);
-        uint32_t g[4], t[4];
-        unpack4(wd, lane, bd, g);
-        unpack4(wd + 4 * bd, lane, bt, t);
-        g[1] += g[0]; g[2] += g[1]; g[3] += g[2];
-        const uint32_t off = warp_excl_scan(g[3], lane) + e.y + 4u * lane;
-        uint32_t d[4], val[4];
-        bool ok[4];
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            d[j] = off + g[j] + (uint32_t)j;
-            ok[j] = 4u * lane + (uint32_t)j < n;
-        }
-        if (acct) {
-            A.block_bytes += ((n * bd + 7u) >> 3) + ((n * bt + 7u) >> 3) + 16u;
-            A.lead_blocks++;
-        }
-        if (!has_req) {
-            uint32_t id[4] = {0u, 0u, 0u, 0u};
-            if (LD.fn_field >= 0) {
-                const uint8_t* __restrict__ fn = p.ix.fnorm[LD.fn_field];
-#pragma unroll
-                for (int j = 0; j < 4; j++)
-                    if (ok[j]) id[j] = __ldg(fn + d[j]);
-                if (acct) A.gathers += n;
-            }
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const float nrm = LD.fn_field >= 0 ? S.cache[LD.fn_field * 256 + (int)id[j]] : LD.cnorm;
-                const float s = LD.weight * tf_factor((float)(t[j] + 1u), nrm);
-                if (prune) ok[j] = ok[j] && (s + rest_s >= theta);
-                val[j] = __float_as_uint(s);
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < 4; j++) val[j] = t[j] + 1u;
-        }
-        const unsigned m0 = __ballot_sync(FULL, ok[0]), m1 = __ballot_sync(FULL, ok[1]), m2 = __ballot_sync(FULL, ok[2]),
-                       m3 = __ballot_sync(FULL, ok[3]);
-        const uint32_t total = (uint32_t)(__popc(m0) + __popc(m1) + __popc(m2) + __popc(m3));
-        if (!total) return;
-        uint32_t pos = ncand + (uint32_t)(__popc(m0 & lt) + __popc(m1 & lt) + __popc(m2 & lt) + __popc(m3 & lt));
-#pragma unroll
-        for (int j = 0; j < 4; j++)
-            if (ok[j]) {
-                W.cand_doc[pos] = d[j];
-                W.cand_val[pos] = val[j];
-                pos++;
-            }
-        ncand += total;
-        __syncwarp();
-        // full rounds of 32 candidates; fewer than 32 wait for the survivors of the next blocks
-        uint32_t head = 0u;
-        while (ncand - head >= 32u) {
-            evaluate(true, W.cand_doc[head + lane], W.cand_val[head + lane]);
-            head += 32u;
-        }
-        if (head) {
-            const uint32_t left = ncand - head;
-            uint32_t cd0 = 0u, cv0 = 0u;
-            if ((uint32_t)lane < left) {
-                cd0 = W.cand_doc[head + lane];
-                cv0 = W.cand_val[head + lane];
-            }
-            __syncwarp();
-            if ((uint32_t)lane < left) {
-                W.cand_doc[lane] = cd0;
-                W.cand_val[lane] = cv0;
             }
             ncand = left;
             __syncwarp();
         }
-    };
-    auto flush = [&]() {  // the candidates still waiting (fewer than 32)
-        if (ncand) {
-            const bool live = (uint32_t)lane < ncand;
-            evaluate(live, live ? W.cand_doc[lane] : 0xFFFFFFFFu, live ? W.cand_val[lane] : 0u);
-            ncand = 0u;
-            __syncwarp();
-        }
-    };
-
-    pull();
-    bool dead = prune && LD.ub + rest_s < theta;  // this lead cannot contribute a hit any more
-    while (!dead) {
-        uint32_t b0 = 0u;
-        if (lane == 0) b0 = atomicAdd(p.cursors + item.cursor, item.chunk);
-        b0 = __shfl_sync(FULL, b0, 0);
-        if (b0 >= LD.n_blocks) break;
-        const uint32_t b1 = min(b0 + item.chunk, LD.n_blocks);
-        for (uint32_t g0 = b0; g0 < b1 && !dead; g0 += 32u) {
-            pull();
-            if (prune && LD.ub + rest_s < theta) {
-                dead = true;
-                break;
-            }
-            const uint32_t b = g0 + lane;
-            float bound = INFINITY;
-            if (prune && b < b1) bound = LD.weight * __ldg(bmx + b) + rest_s;
-            if (acct) {
-                A.lead_blocks_seen += min(32u, b1 - g0);
-                if (prune) A.meta_bytes += 4u * min(32u, b1 - g0);
-            }
-            unsigned m = __ballot_sync(FULL, b < b1 && bound >= theta);
-            while (m) {
-                const int src = __ffs(m) - 1;
-                m &= m - 1;
-                process_block(g0 + (uint32_t)src);
-                if (prune && m) m &= __ballot_sync(FULL, bound >= theta);  // the threshold may have risen
-            }
-        }
+        if (fin && !ncand) break;
     }
-
-    flush();
 
     // append this warp's queue to the query's region of the partial array
     {
@@ -482,11 +564,18 @@ __device__ __forceinline__ void run_item(const LeadParams& p, const LeadShared& 
                 base += (uint32_t)__popc(mk);
             }
         }
+        if (acct) {  // lane-local counters: sum over the warp
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                A.gathers_l += __shfl_xor_sync(FULL, A.gathers_l, o);
+                A.block_bytes_l += __shfl_xor_sync(FULL, A.block_bytes_l, o);
+            }
+        }
         if (lane == 0) {
             if (n_match) atomicAdd(p.qmatch + item.query, n_match);
             if (acct && p.stats) {
-                atomicAdd(p.stats + 0, A.block_bytes);
-                atomicAdd(p.stats + 2, A.gathers);
+                atomicAdd(p.stats + 0, A.block_bytes + A.block_bytes_l);
+                atomicAdd(p.stats + 2, A.gathers + A.gathers_l);
                 atomicAdd(p.stats + 5, A.meta_bytes);
                 atomicAdd(p.stats + 6, A.lead_blocks);
                 atomicAdd(p.stats + 7, A.lead_blocks_seen);

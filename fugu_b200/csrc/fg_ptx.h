@@ -32,6 +32,9 @@ __device__ __forceinline__ uint32_t smem_atomic_inc(uint32_t* p) {
     return r;
 }
 
+// start bringing the 128-byte line at p into L2 (no register, no fault on a bad address)
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // ---- 1-D bulk copies global -> shared memory (TMA engine, SASS UBLKCP) guarded by an mbarrier ----
 // A posting block's payload is 16*(bd+bt) contiguous bytes, 16-byte aligned: one bulk copy stages it.
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

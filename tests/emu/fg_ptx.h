@@ -15,6 +15,8 @@ template <int J>
 inline uint32_t prmt_byte(uint32_t w, uint32_t magic) { return __byte_perm(w, magic, 0x7650u | (uint32_t)J); }
 inline uint32_t smem_atomic_inc(uint32_t* p) { return atomicAdd(p, 1u); }
 
+inline void prefetch_l2(const void*) {}
+
 // mbarrier + bulk copy: the copy completes at once; the barrier word counts completed phases
 inline void mbar_init(uint64_t* bar, uint32_t) { *bar = 0; }
 inline void fence_mbar_init() {}
