@@ -21,7 +21,7 @@ $(CSRC)/fg_host.o: $(CSRC)/fg_host.cpp $(CSRC)/fg_error.h $(CSRC)/fg_pool.h $(CS
 	$(CXX) -O2 -std=c++17 -fPIC -Wall -Iinclude -c $< -o $@
 
 fugu_b200/libfugu_gpu.so: $(CSRC)/fg_kernels.o $(CSRC)/fg_lead.o $(CSRC)/fg_api.o $(CSRC)/fg_host.o
-	$(NVCC) -shared $(ARCH) -o $@ $^ -lpthread
+	$(NVCC) -shared $(ARCH) -o $@ $^ -lpthread -ldl
 
 fugu_b200/synth/libfugu_synth.so: fugu_b200/synth/synth.cpp
 	$(CXX) -O3 -march=x86-64-v2 -std=c++17 -shared -fPIC -pthread -o $@ $<

@@ -344,18 +344,29 @@ def main():
             os.environ.setdefault("GLOO_SOCKET_IFNAME", "lo")
             dist.init_process_group("gloo")
     xch = Exchange(dist, torch, dev, mode=xmode) if dist else None
-    EXCHANGE_NOTE["mode"] = ("NCCL all_gather_into_tensor + on-device merge" if xch.mode == "nccl" else
+    EXCHANGE_NOTE["mode"] = ("inside the library: fg_batch_execute_sharded = local top-k -> ncclAllGather (one fused launch) -> on-device merge"
+                             if xch.mode == "nccl" else
                              "host-memory (gloo) all-gather + on-device merge (FG_BENCH_EXCHANGE=gloo)") if xch else "none"
 
+    ctx = nat.Context(local_rank)
+    comm = None
+    if world > 1 and xch.mode == "nccl":
+        # the library's own communicator (fg_comm): rank 0's id travels over the launcher's process group once
+        ids = [nat.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        comm = nat.Comm(ctx, rank, world, ids[0])
     cfg, corpus, fields, queries, d0, d1 = build_workload(args, rank, world)
     n_local = d1 - d0
     if world > 1:
         # global statistics (tantivy computes N, df and total_num_tokens over all segments, A.4)
         for f in fields:
-            f["global_doc_freq"] = xch.allreduce_cpu(np.diff(f["term_offsets"]).astype(np.int64)).astype(np.uint32)
-            f["total_num_tokens"] = int(xch.allreduce_cpu(np.array([f["total_num_tokens"]], np.int64))[0])
+            if comm:
+                f["global_doc_freq"] = comm.allreduce_sum(np.diff(f["term_offsets"]).astype(np.uint32))
+                f["total_num_tokens"] = int(comm.allreduce_sum(np.array([f["total_num_tokens"]], np.uint64))[0])
+            else:
+                f["global_doc_freq"] = xch.allreduce_cpu(np.diff(f["term_offsets"]).astype(np.int64)).astype(np.uint32)
+                f["total_num_tokens"] = int(xch.allreduce_cpu(np.array([f["total_num_tokens"]], np.int64))[0])
     desc = nat.HostIndexDesc(n_local, fields, doc_id_base=d0, global_n_docs=cfg.n_docs)
-    ctx = nat.Context(local_rank)
     # a real (non-default) stream: the legacy default stream's handle is 0, which fg_ctx_set_stream
     # reads as "use the context's own stream"; events below are recorded on this same stream
     stream = torch.cuda.Stream(dev)
@@ -389,6 +400,9 @@ def main():
     counts = bool(os.environ.get("FG_BENCH_COUNTS"))  # TopDocs::with_limit does not count matches: off by default
 
     def step():
+        if comm:  # one call: local top-k -> NCCL all-gather -> merge, all inside the library
+            pb.execute_sharded(comm, f_hits.data_ptr(), f_n.data_ptr(), k_stride=k)
+            return
         pb.execute(d_hits.data_ptr(), d_n.data_ptr(), d_c.data_ptr() if counts else None, None, k_stride=k)
         if world > 1:
             xch.all_gather(g_hits, d_hits)
@@ -508,12 +522,20 @@ def main():
             xch.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        h_hits, h_n, h_c, _ = ds.search_batch(qset, want_counts=counts)  # fgh_search_batch: strings -> plan -> H2D -> kernels -> D2H
-        if world > 1:
-            xch.all_gather(g_hits, torch.from_numpy(h_hits.view(np.int32).reshape(nq, k, 2)).to(dev))
-            xch.all_gather(g_n, torch.from_numpy(h_n.view(np.int32)).to(dev))
-            nat.merge_topk_device(ctx, g_hits.data_ptr(), g_n.data_ptr(), world, nq, k, k, f_hits.data_ptr(), f_n.data_ptr())
+        if comm:
+            # strings (host) -> planner -> lowering -> H2D -> kernels -> NCCL all-gather -> merge -> D2H (host)
+            eb, _ = ds.plan_batch(qset)
+            epb = index.prepare(eb)
+            epb.execute_sharded(comm, f_hits.data_ptr(), f_n.data_ptr(), k_stride=k)
             f_hits.cpu(); f_n.cpu()
+            epb.close()
+        else:
+            h_hits, h_n, h_c, _ = ds.search_batch(qset, want_counts=counts)  # fgh_search_batch: strings -> plan -> H2D -> kernels -> D2H
+            if world > 1:
+                xch.all_gather(g_hits, torch.from_numpy(h_hits.view(np.int32).reshape(nq, k, 2)).to(dev))
+                xch.all_gather(g_n, torch.from_numpy(h_n.view(np.int32)).to(dev))
+                nat.merge_topk_device(ctx, g_hits.data_ptr(), g_n.data_ptr(), world, nq, k, k, f_hits.data_ptr(), f_n.data_ptr())
+                f_hits.cpu(); f_n.cpu()
         dt = time.perf_counter() - t0
         if it >= 2:
             e2e_times.append(dt)
@@ -526,6 +548,8 @@ def main():
     out_bytes = nq * k * 8 + nq * 8
 
     def shutdown():
+        if comm:
+            comm.close()
         if dist:
             dist.destroy_process_group()
 

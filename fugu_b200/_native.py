@@ -33,6 +33,7 @@ FG_EXEC_COUNTERS = 4
 FG_EXEC_NO_PRUNE = 8
 FG_PREP_NO_COLUMNS = 1
 FG_PREP_LEGACY = 2
+FG_PREP_PER_QUERY_STATUS = 4
 
 
 class FgError(RuntimeError):
@@ -125,6 +126,8 @@ ABI_SYMBOLS = [
     "fg_ctx_synchronize", "fg_index_upload", "fg_index_release", "fg_index_with_alive", "fg_index_get_info",
     "fg_index_term_info", "fg_search_batch", "fg_batch_prepare", "fg_batch_prepare_ex", "fg_batch_release",
     "fg_batch_execute", "fg_batch_submit", "fg_batch_collect", "fg_batch_get_stats", "fg_merge_topk_device", "fg_fieldnorm_to_id",
+    "fg_comm_unique_id", "fg_comm_create", "fg_comm_destroy", "fg_comm_allreduce_sum_u64", "fg_comm_allreduce_sum_u32",
+    "fg_batch_execute_sharded", "fg_batch_query_status",
     "fg_id_to_fieldnorm", "fg_bm25_idf",
 ]
 
@@ -159,12 +162,20 @@ def lib() -> C.CDLL:
     L.fg_batch_prepare.argtypes = [vp, C.POINTER(QueryBatch), C.POINTER(vp)]
     L.fg_batch_prepare_ex.argtypes = [vp, C.POINTER(QueryBatch), u32, C.POINTER(vp)]
     L.fg_batch_release.argtypes = [vp]
+    L.fg_batch_query_status.argtypes = [vp, vp]
     L.fg_batch_release.restype = None
     L.fg_batch_execute.argtypes = [vp, u32, u32, vp, vp, vp, vp]
     L.fg_batch_submit.argtypes = [vp, u32, u32, i32]
     L.fg_batch_collect.argtypes = [vp, vp, vp, vp]
     L.fg_batch_get_stats.argtypes = [vp, C.POINTER(BatchStats)]
     L.fg_merge_topk_device.argtypes = [vp, vp, vp, u32, u32, u32, u32, vp, vp]
+    L.fg_comm_unique_id.argtypes = [vp]
+    L.fg_comm_create.argtypes = [vp, i32, i32, vp, C.POINTER(vp)]
+    L.fg_comm_destroy.argtypes = [vp]
+    L.fg_comm_destroy.restype = None
+    L.fg_comm_allreduce_sum_u64.argtypes = [vp, vp, C.c_size_t]
+    L.fg_comm_allreduce_sum_u32.argtypes = [vp, vp, C.c_size_t]
+    L.fg_batch_execute_sharded.argtypes = [vp, vp, u32, u32, vp, vp]
     L.fg_fieldnorm_to_id.argtypes = [u32]
     L.fg_fieldnorm_to_id.restype = C.c_uint8
     L.fg_id_to_fieldnorm.argtypes = [C.c_uint8]
@@ -338,6 +349,10 @@ class PreparedBatch:
         check(lib().fg_batch_execute(self.h, flags, k_stride or self.kmax, C.c_void_p(d_hits), C.c_void_p(d_n),
                                      C.c_void_p(d_count or 0), C.c_void_p(d_bitmap or 0)))
 
+    def execute_sharded(self, comm: "Comm", d_hits: int, d_n: int, k_stride: int | None = None, flags: int = 0) -> None:
+        """fg_batch_execute_sharded: local top-k -> NCCL all-gather -> on-device merge; global result on every rank."""
+        check(lib().fg_batch_execute_sharded(self.h, comm.h, flags, k_stride or self.kmax, C.c_void_p(d_hits), C.c_void_p(d_n)))
+
     def submit(self, k_stride: int | None = None, want_counts: bool = True, flags: int = 0) -> None:
         """fg_batch_submit: launch + queue the device->host copy of the results; returns at once."""
         self._sub = (k_stride or self.kmax, want_counts)
@@ -352,6 +367,11 @@ class PreparedBatch:
         check(lib().fg_batch_collect(self.h, _ptr(hits), _ptr(n), _ptr(cnt)))
         return hits, n, cnt
 
+    def query_status(self) -> np.ndarray:
+        st = np.zeros(self.n_queries, np.int32)
+        check(lib().fg_batch_query_status(self.h, st.ctypes.data))
+        return st
+
     def stats(self) -> BatchStats:
         s = BatchStats()
         check(lib().fg_batch_get_stats(self.h, C.byref(s)))
@@ -360,6 +380,37 @@ class PreparedBatch:
     def close(self) -> None:
         if self.h:
             lib().fg_batch_release(self.h)
+            self.h = C.c_void_p()
+
+
+FG_COMM_ID_BYTES = 128
+
+
+def comm_unique_id() -> bytes:
+    buf = C.create_string_buffer(FG_COMM_ID_BYTES)
+    check(lib().fg_comm_unique_id(buf))
+    return buf.raw
+
+
+class Comm:
+    """fg_comm: this rank's end of the NCCL communicator the library exchanges per-shard top-k lists over."""
+
+    def __init__(self, ctx: Context, rank: int, world: int, unique_id: bytes):
+        assert len(unique_id) == FG_COMM_ID_BYTES
+        self.h = C.c_void_p()
+        self.rank, self.world = rank, world
+        check(lib().fg_comm_create(ctx.h, rank, world, C.c_char_p(unique_id), C.byref(self.h)))
+
+    def allreduce_sum(self, a: np.ndarray) -> np.ndarray:
+        """in-place sum over all ranks of a uint32 / uint64 host array (collective)"""
+        assert a.flags["C_CONTIGUOUS"] and a.dtype in (np.uint32, np.uint64)
+        f = lib().fg_comm_allreduce_sum_u64 if a.dtype == np.uint64 else lib().fg_comm_allreduce_sum_u32
+        check(f(self.h, a.ctypes.data, a.size))
+        return a
+
+    def close(self) -> None:
+        if self.h:
+            lib().fg_comm_destroy(self.h)
             self.h = C.c_void_p()
 
 

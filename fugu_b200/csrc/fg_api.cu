@@ -3,6 +3,8 @@
 // batch execution. No CPU evaluation path exists here: without a CUDA device every compute entry
 // point returns FG_ERR_NO_DEVICE.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
 #include <time.h>
 
 #include <algorithm>
@@ -169,6 +171,7 @@ static void pool_free(fg_ctx* c, void* p, size_t bytes) {
     }
 }
 
+extern "C" void fg_ctx_destroy(fg_ctx* c);
 extern "C" int32_t fg_ctx_create(int32_t device, fg_ctx** out) {
     if (!out) return fail(FG_ERR_INVALID, "fg_ctx_create: out is NULL");
     *out = nullptr;
@@ -184,7 +187,8 @@ extern "C" int32_t fg_ctx_create(int32_t device, fg_ctx** out) {
     if (pr.major < 10)
         return fail(FG_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only",
                     device, pr.major, pr.minor);
-    fg_ctx* c = new fg_ctx();
+    std::unique_ptr<fg_ctx, void (*)(fg_ctx*)> guard(new fg_ctx(), fg_ctx_destroy);  // a failing call below must not leak streams / events
+    fg_ctx* c = guard.get();
     c->device = device;
     c->n_sms = pr.multiProcessorCount;
     c->env_legacy = env_u64_early("FG_LEGACY", 0) != 0;
@@ -204,7 +208,7 @@ extern "C" int32_t fg_ctx_create(int32_t device, fg_ctx** out) {
     }
     CU(cudaEventCreateWithFlags(&c->fork_ev, cudaEventDisableTiming));
     CU(cudaStreamCreateWithFlags(&c->up, cudaStreamNonBlocking));
-    *out = c;
+    *out = guard.release();
     return FG_OK;
 }
 extern "C" void fg_ctx_destroy(fg_ctx* c) {
@@ -763,6 +767,8 @@ struct fg_batch {
     uint32_t n_cursors = 0;
     uint64_t partial_entries = 0;
     size_t lsz[4] = {0, 0, 0, 0};
+    std::vector<int32_t> qstatus;  // FG_PREP_PER_QUERY_STATUS: per-query lowering status
+    std::string first_bad;
 };
 
 static double now_ms() {
@@ -823,6 +829,9 @@ static int32_t prepare_lead(fg_index* ix, const fg_query_batch* qb, uint32_t pre
         std::string err;
     };
     std::vector<LQuery> lq(qb->n_queries);
+    const bool per_query = (prep_flags & FG_PREP_PER_QUERY_STATUS) != 0;
+    std::vector<int32_t> qstatus(per_query ? qb->n_queries : 0, FG_OK);
+    std::string first_bad;  // (written by the thread that owns the query's part; read after the join)
     auto lfail = [](Part& o, int32_t code, const char* fmt, ...) -> int32_t {
         char buf[512];
         va_list ap;
@@ -841,10 +850,11 @@ static int32_t prepare_lead(fg_index* ix, const fg_query_batch* qb, uint32_t pre
         CRec crec[MAXC];
         o.q_items.assign(q_end - q_begin, 0);
         o.leaves.reserve((size_t)((uint64_t)qb->n_leaves * (q_end - q_begin) / std::max<uint32_t>(qb->n_queries, 1)) + 64);
-        for (uint32_t qi = q_begin; qi < q_end; qi++) {
+        auto lower_query = [&](uint32_t qi) -> int32_t {
             const fg_query& q = qb->queries[qi];
             LQuery& D = lq[qi];
             memset(&D, 0, sizeof(D));
+            D.k = 1;
             if (q.k == 0) return lfail(o, FG_ERR_INVALID, "query %u: k == 0 (TopDocs::with_limit requires limit >= 1)", qi);
             if (q.k > 1024) return lfail(o, FG_ERR_UNSUPPORTED, "query %u: k = %u > 1024 not supported", qi, q.k);
             if ((uint64_t)q.clause_begin + q.n_clauses > qb->n_clauses)
@@ -871,7 +881,9 @@ static int32_t prepare_lead(fg_index* ix, const fg_query_batch* qb, uint32_t pre
                     if (lf.term_ord == FG_TERM_MISSING) continue;
                     if (lf.field >= ix->fields.size()) return lfail(o, FG_ERR_INVALID, "query %u: field %u out of range", qi, lf.field);
                     const HostField& hf = ix->fields[lf.field];
-                    if (lf.term_ord >= hf.n_terms) return lfail(o, FG_ERR_INVALID, "query %u: term_ord out of range", qi);
+                    // a term the planner's dictionary learned after this snapshot was taken (a commit raced the request):
+                    // the snapshot does not contain it -- an empty scorer, like an uncommitted document in the reference
+                    if (lf.term_ord >= hf.n_terms) continue;
                     const TermInfo& ti = hf.terms[lf.term_ord];
                     if (ti.df_global == 0 || ti.n_blocks == 0) continue;  // empty scorer (globally, or in this shard)
                     if (nt >= LMAX_LEAVES * 2) return lfail(o, FG_ERR_UNSUPPORTED, "query %u: too many leaves", qi);
@@ -916,11 +928,11 @@ static int32_t prepare_lead(fg_index* ix, const fg_query_batch* qb, uint32_t pre
             if (has_all_only && n_must == 0 && !empty) {
                 if (n_should == 0 && n_not == 0) {  // pure AllQuery: every alive doc, score = boost
                     D.flags |= LQ_ALL;
-                    continue;
+                    return FG_OK;
                 }
                 return lfail(o, FG_ERR_UNSUPPORTED, "query %u: AllQuery Must with only Should/MustNot siblings not supported", qi);
             }
-            if (empty || (n_must == 0 && n_should == 0)) continue;
+            if (empty || (n_must == 0 && n_should == 0)) return FG_OK;
             if (nt > LMAX_LEAVES) return lfail(o, FG_ERR_UNSUPPORTED, "query %u: %d live leaves > %d", qi, nt, LMAX_LEAVES);
             // Must clauses by ascending Sum(df) = tantivy's Intersection order (stable insertion sort)
             for (int i = 1; i < n_must; i++) {
@@ -1035,10 +1047,25 @@ static int32_t prepare_lead(fg_index* ix, const fg_query_batch* qb, uint32_t pre
                 qitems += par;
             }
             o.q_items[qi - q_begin] = qitems;
+            return FG_OK;
+        };
+        for (uint32_t qi = q_begin; qi < q_end; qi++) {
+            const int32_t rc = lower_query(qi);
+            if (rc == FG_OK) continue;
+            if (!per_query) return rc;
+            // FG_PREP_PER_QUERY_STATUS: the offender becomes an empty query, its siblings are answered
+            qstatus[qi] = rc;
+            if (first_bad.empty()) first_bad = o.err;
+            o.rc = FG_OK;
+            LQuery& D = lq[qi];
+            memset(&D, 0, sizeof(D));
+            D.k = 1;
+            D.leaf_begin = (uint32_t)o.leaves.size();
         }
         return FG_OK;
     };
-    const int LT = (int)std::max<uint64_t>(1, std::min<uint64_t>({(uint64_t)HostPool::get().size(), 8, (uint64_t)qb->n_queries / 256 + 1}));
+    const double t_begin = now_ms();
+    const int LT = (int)std::max<uint64_t>(1, std::min<uint64_t>({(uint64_t)HostPool::get().size(), 16, (uint64_t)qb->n_queries / 96 + 1}));
     std::vector<Part> parts((size_t)LT);
     HostPool::get().run(LT, [&](int t) {
         lower_range((uint32_t)((uint64_t)qb->n_queries * t / LT), (uint32_t)((uint64_t)qb->n_queries * (t + 1) / LT), parts[t]);
@@ -1083,6 +1110,7 @@ static int32_t prepare_lead(fg_index* ix, const fg_query_batch* qb, uint32_t pre
         }
     }
     if (part_entries > 0xFFFFFFF0ull) return fail(FG_ERR_UNSUPPORTED, "partial result lists exceed 2^32 entries");
+    const double t_lowered = now_ms();
 
     CU(cudaSetDevice(ctx->device));
     std::unique_ptr<fg_batch, void (*)(fg_batch*)> b(new fg_batch(), fg_batch_release);
@@ -1095,6 +1123,8 @@ static int32_t prepare_lead(fg_index* ix, const fg_query_batch* qb, uint32_t pre
     b->sum_k = sum_k;
     b->n_cursors = n_cursors;
     b->partial_entries = part_entries;
+    b->qstatus.swap(qstatus);
+    b->first_bad.swap(first_bad);
     auto up = [&](const void* src, size_t bytes, void** dst, size_t* sz) -> int32_t {
         *sz = std::max<size_t>(bytes, 16);
         CU(pool_alloc(ctx, dst, *sz));
@@ -1117,6 +1147,9 @@ static int32_t prepare_lead(fg_index* ix, const fg_query_batch* qb, uint32_t pre
     CU(cudaEventCreateWithFlags(&b->ev_done, cudaEventDisableTiming));
     CU(cudaEventRecord(b->ev_up, ctx->up));
     CU(cudaStreamSynchronize(ctx->up));  // host vectors go out of scope (the compute stream is not touched)
+    if (ctx->env_timing)
+        fprintf(stderr, "[prepare_lead] lowering %.2f ms (%d threads), alloc + upload %.2f ms (%zu items, %zu leaves)\n", t_lowered - t_begin, LT,
+                now_ms() - t_lowered, items.size(), leaves.size());
     *out = b.release();
     return FG_OK;
 }
@@ -1216,7 +1249,7 @@ extern "C" int32_t fg_batch_prepare_ex(fg_index* ix, const fg_query_batch* qb, u
                     if (lf.term_ord == FG_TERM_MISSING) continue;
                     if (lf.field >= ix->fields.size()) return lfail(o, FG_ERR_INVALID, "query %u: field %u out of range", qi, lf.field);
                     const HostField& hf = ix->fields[lf.field];
-                    if (lf.term_ord >= hf.n_terms) return lfail(o, FG_ERR_INVALID, "query %u: term_ord out of range", qi);
+                    if (lf.term_ord >= hf.n_terms) continue;  // not in this snapshot's dictionary (see prepare_lead)
                     const TermInfo& ti = hf.terms[lf.term_ord];
                     if (ti.df_global == 0 || ti.n_blocks == 0) continue;  // empty scorer (globally, or in this shard)
                     if (nt >= MAXT) return lfail(o, FG_ERR_UNSUPPORTED, "query %u: too many leaves", qi);
@@ -1619,6 +1652,14 @@ extern "C" int32_t fg_batch_execute(fg_batch* b, uint32_t flags, uint32_t k_stri
     return FG_OK;
 }
 
+extern "C" int32_t fg_batch_query_status(const fg_batch* b, int32_t* out_status) {
+    if (!b || !out_status) return fail(FG_ERR_INVALID, "fg_batch_query_status: NULL argument");
+    for (uint32_t i = 0; i < b->n_queries; i++) out_status[i] = i < b->qstatus.size() ? b->qstatus[i] : FG_OK;
+    for (int32_t st : b->qstatus)
+        if (st != FG_OK) { fail(st, "%s", b->first_bad.c_str()); break; }  // fg_last_error() describes the first offender
+    return FG_OK;
+}
+
 extern "C" int32_t fg_batch_get_stats(fg_batch* b, fg_batch_stats* out) {
     if (!b || !out) return fail(FG_ERR_INVALID, "NULL argument");
     fg_ctx* ctx = b->ix->ctx;
@@ -1662,7 +1703,10 @@ extern "C" int32_t fg_search_batch(fg_index* ix, const fg_query_batch* qb, uint3
     const bool timing = ix->ctx->env_timing;
     const double t0 = now_ms();
     fg_batch* b = nullptr;
-    int32_t rc = fg_batch_prepare(ix, qb, &b);
+    // match counts need every matching document visited: the windowed accumulator kernels are the exhaustive engine;
+    // the TopDocs form (no counts) runs on the lead-driven kernels, which prune
+    int32_t rc = out_match_count ? fg_batch_prepare_ex(ix, qb, FG_PREP_LEGACY, &b) : FG_ERR_UNSUPPORTED;
+    if (rc) rc = fg_batch_prepare(ix, qb, &b);
     const double t1 = now_ms();
     if (rc) return rc;
     std::unique_ptr<fg_batch, void (*)(fg_batch*)> guard(b, fg_batch_release);
@@ -1743,6 +1787,172 @@ extern "C" int32_t fg_merge_topk_device(fg_ctx* ctx, const void* d_hits, const v
     std::lock_guard<std::mutex> g(ctx->mu);
     launch_merge_gathered(d_hits, (const uint32_t*)d_n, n_ranks, n_queries, k, k_stride, d_out_hits,
                           (uint32_t*)d_out_n, k <= 32 ? 1 : k <= 128 ? 4 : 32, ctx->stream);
+    CU(cudaGetLastError());
+    return FG_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// multi-GPU, one process per GPU: NCCL communicator + sharded execution
+// ------------------------------------------------------------------------------------------
+namespace {
+// NCCL is loaded on first use (dlopen): a single-GPU host never needs the library, and a host that already
+// carries an NCCL (torch's bundled copy has the same soname) shares it instead of getting a second one.
+struct NcclApi {
+    void* h = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    std::string err;
+};
+NcclApi& nccl_api() {
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+            api.h = dlopen(name, RTLD_NOW | RTLD_LOCAL);
+            if (api.h) break;
+        }
+        if (!api.h) { api.err = std::string("cannot load libnccl.so.2: ") + dlerror(); return; }
+        auto sym = [&](const char* n) -> void* {
+            void* p = dlsym(api.h, n);
+            if (!p && api.err.empty()) api.err = std::string("libnccl lacks ") + n;
+            return p;
+        };
+        api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId");
+        api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
+        api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
+        api.AllGather = (decltype(api.AllGather))sym("ncclAllGather");
+        api.AllReduce = (decltype(api.AllReduce))sym("ncclAllReduce");
+        api.GroupStart = (decltype(api.GroupStart))sym("ncclGroupStart");
+        api.GroupEnd = (decltype(api.GroupEnd))sym("ncclGroupEnd");
+        api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
+    });
+    return api;
+}
+}  // namespace
+#define NC(call)                                                                                          \
+    do {                                                                                                  \
+        ncclResult_t r_ = (call);                                                                         \
+        if (r_ != ncclSuccess)                                                                            \
+            return fail(FG_ERR_CUDA, "%s failed: %s (%s:%d)", #call, nccl_api().GetErrorString(r_), __FILE__, __LINE__); \
+    } while (0)
+
+struct fg_comm {
+    fg_ctx* ctx = nullptr;
+    ncclComm_t comm = nullptr;
+    int rank = 0, world = 1;
+    void* d_local = nullptr;    // this shard's [hits n*k_stride | n_hits n]
+    void* d_gather = nullptr;   // [world][hits] then [world][n_hits]
+    size_t local_sz = 0, gather_sz = 0;
+    void* d_tmp = nullptr;      // all-reduce staging
+    size_t tmp_sz = 0;
+};
+
+extern "C" int32_t fg_comm_unique_id(void* out_id) {
+    if (!out_id) return fail(FG_ERR_INVALID, "fg_comm_unique_id: NULL argument");
+    NcclApi& n = nccl_api();
+    if (!n.err.empty()) return fail(FG_ERR_UNSUPPORTED, "%s", n.err.c_str());
+    static_assert(sizeof(ncclUniqueId) == FG_COMM_ID_BYTES, "FG_COMM_ID_BYTES");
+    ncclUniqueId id;
+    NC(n.GetUniqueId(&id));
+    memcpy(out_id, &id, sizeof(id));
+    return FG_OK;
+}
+extern "C" int32_t fg_comm_create(fg_ctx* ctx, int32_t rank, int32_t n_ranks, const void* id, fg_comm** out) {
+    if (!ctx || !id || !out || n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(FG_ERR_INVALID, "fg_comm_create: bad argument");
+    *out = nullptr;
+    NcclApi& n = nccl_api();
+    if (!n.err.empty()) return fail(FG_ERR_UNSUPPORTED, "%s", n.err.c_str());
+    CU(cudaSetDevice(ctx->device));
+    ncclUniqueId uid;
+    memcpy(&uid, id, sizeof(uid));
+    std::unique_ptr<fg_comm> c(new fg_comm());
+    c->ctx = ctx;
+    c->rank = rank;
+    c->world = n_ranks;
+    NC(n.CommInitRank(&c->comm, n_ranks, uid, rank));
+    *out = c.release();
+    return FG_OK;
+}
+extern "C" void fg_comm_destroy(fg_comm* c) {
+    if (!c) return;
+    cudaSetDevice(c->ctx->device);
+    cudaStreamSynchronize(c->ctx->stream);
+    if (c->comm) nccl_api().CommDestroy(c->comm);
+    cudaFree(c->d_local);
+    cudaFree(c->d_gather);
+    cudaFree(c->d_tmp);
+    delete c;
+}
+static int32_t comm_allreduce(fg_comm* c, void* values, size_t n, size_t elem, ncclDataType_t dt) {
+    if (!c || (n && !values)) return fail(FG_ERR_INVALID, "fg_comm_allreduce: NULL argument");
+    if (n == 0) return FG_OK;
+    fg_ctx* ctx = c->ctx;
+    CU(cudaSetDevice(ctx->device));
+    std::lock_guard<std::mutex> g(ctx->mu);
+    if (c->tmp_sz < n * elem) {
+        cudaFree(c->d_tmp);
+        c->d_tmp = nullptr;
+        c->tmp_sz = 0;
+        CU(cudaMalloc(&c->d_tmp, n * elem));
+        c->tmp_sz = n * elem;
+    }
+    CU(cudaMemcpyAsync(c->d_tmp, values, n * elem, cudaMemcpyHostToDevice, ctx->stream));
+    NC(nccl_api().AllReduce(c->d_tmp, c->d_tmp, n, dt, ncclSum, c->comm, ctx->stream));
+    CU(cudaMemcpyAsync(values, c->d_tmp, n * elem, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return FG_OK;
+}
+extern "C" int32_t fg_comm_allreduce_sum_u64(fg_comm* c, uint64_t* v, size_t n) { return comm_allreduce(c, v, n, 8, ncclUint64); }
+extern "C" int32_t fg_comm_allreduce_sum_u32(fg_comm* c, uint32_t* v, size_t n) { return comm_allreduce(c, v, n, 4, ncclUint32); }
+
+extern "C" int32_t fg_batch_execute_sharded(fg_batch* b, fg_comm* c, uint32_t flags, uint32_t k_stride, void* d_hits, void* d_n_hits) {
+    if (!b || !c || !d_hits || !d_n_hits) return fail(FG_ERR_INVALID, "fg_batch_execute_sharded: NULL argument");
+    fg_ctx* ctx = b->ix->ctx;
+    if (ctx != c->ctx) return fail(FG_ERR_INVALID, "fg_batch_execute_sharded: the batch and the communicator belong to different contexts");
+    if (k_stride < b->kcap) return fail(FG_ERR_INVALID, "k_stride %u < max k %u", k_stride, b->kcap);
+    CU(cudaSetDevice(ctx->device));
+    const size_t nq = b->n_queries;
+    if (nq == 0) return FG_OK;
+    const size_t hits_b = nq * k_stride * sizeof(fg_hit), n_b = nq * 4, local = hits_b + n_b;
+    {
+        std::lock_guard<std::mutex> g(ctx->mu);
+        if (c->local_sz < local) {
+            CU(cudaStreamSynchronize(ctx->stream));
+            cudaFree(c->d_local);
+            cudaFree(c->d_gather);
+            c->d_local = c->d_gather = nullptr;
+            c->local_sz = c->gather_sz = 0;
+            CU(cudaMalloc(&c->d_local, local));
+            CU(cudaMalloc(&c->d_gather, local * c->world));
+            c->local_sz = local;
+            c->gather_sz = local * c->world;
+        }
+    }
+    char* dl = (char*)c->d_local;
+    char* dg = (char*)c->d_gather;
+    int32_t rc = fg_batch_execute(b, flags, k_stride, dl, dl + hits_b, nullptr, nullptr);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    cudaStream_t st = ctx->stream;
+    NcclApi& n = nccl_api();
+    // one fused NCCL launch: the hit lists and their lengths of every shard
+    NC(n.GroupStart());
+    NC(n.AllGather(dl, dg, hits_b, ncclUint8, c->comm, st));
+    NC(n.AllGather(dl + hits_b, dg + hits_b * c->world, n_b, ncclUint8, c->comm, st));
+    NC(n.GroupEnd());
+    const void* qrec = b->lead ? (const void*)b->l_queries : (const void*)b->d_queries;
+    const uint32_t q_words = b->lead ? sizeof(LQuery) / 4 : sizeof(DevQuery) / 4;
+    const uint32_t k_word = b->lead ? offsetof(LQuery, k) / 4 : offsetof(DevQuery, k) / 4;
+    launch_merge_ranks(dg, (const uint32_t*)(dg + hits_b * c->world), (uint32_t)c->world, (uint32_t)nq, qrec, q_words, k_word, k_stride,
+                       d_hits, (uint32_t*)d_n_hits, b->ks, st);
+    CU(cudaEventRecord(b->ev[2], st));
+    b->n_launches += 2;
     CU(cudaGetLastError());
     return FG_OK;
 }

@@ -940,7 +940,7 @@ void plan_batch(const fgh_dataset* ds, uint32_t n, const char* const* queries, c
     const char* e = getenv("FG_HOST_THREADS");
     if (e) hw = (unsigned)atoi(e);
     // the fast path plans ~3M requests/s per thread; a thread costs ~30 us to start
-    const int T = (int)std::max(1u, std::min<unsigned>({hw ? hw : 4u, (unsigned)fg::HostPool::get().size(), 8u, n / 256 + 1}));
+    const int T = (int)std::max(1u, std::min<unsigned>({hw ? hw : 4u, (unsigned)fg::HostPool::get().size(), 16u, n / 96 + 1}));
     struct Part { std::vector<fg_clause> c; std::vector<fg_leaf> l; std::vector<std::string> errs; uint32_t a, b; };
     std::vector<Part> parts((size_t)T);
     auto work = [&](int t) {
@@ -1066,8 +1066,23 @@ extern "C" int32_t fgh_search_batch(fgh_dataset* ds, uint32_t n, const char* con
         qb.clauses = C.pb.c.data();
         qb.leaves = C.pb.l.data();
         const double t1 = now_ms();
-        int32_t r = fg_batch_prepare(snap.get(), &qb, &C.batch);
+        // The TopDocs form (no match counts: what the reference's collector does) runs on the lead-driven kernels,
+        // which prune; match counts need every matching document visited, which is what the windowed accumulator
+        // kernels do best (FG_PREP_LEGACY). A query the device path cannot take fails alone, not its siblings.
+        int32_t r = FG_ERR_UNSUPPORTED;
+        if (out_match_count) r = fg_batch_prepare_ex(snap.get(), &qb, FG_PREP_LEGACY, &C.batch);
+        if (r) r = fg_batch_prepare_ex(snap.get(), &qb, FG_PREP_PER_QUERY_STATUS, &C.batch);
         if (r) return r;
+        {
+            std::vector<int32_t> qs(m);
+            fg_batch_query_status(C.batch, qs.data());
+            for (uint32_t j = 0; j < m; j++)
+                if (qs[j] != FG_OK && C.pb.rc[j] == FG_OK) {
+                    C.pb.rc[j] = qs[j];
+                    if (status) status[C.a + j] = qs[j];
+                    else return qs[j];  // single-status callers see the first failure (message set by fg_batch_query_status)
+                }
+        }
         const double t2 = now_ms();
         // match counts are optional: the reference's TopDocs collector does not count (src/db/search.rs:162)
         r = fg_batch_submit(C.batch, 0, C.pb.kmax, out_match_count ? 1 : 0);

@@ -255,6 +255,9 @@ struct LeadMergeParams {
 };
 void launch_lead(const LeadParams& p, int ks, int n_sms, void* stream);
 void launch_lead_merge(const LeadMergeParams& p, int ks, void* stream);
+// merge of all-gathered per-rank lists with per-query k (word k_word of the q_words-word query records at qrec)
+void launch_merge_ranks(const void* hits, const uint32_t* n, uint32_t n_ranks, uint32_t n_queries, const void* qrec, uint32_t q_words,
+                        uint32_t k_word, uint32_t k_stride, void* out_hits, uint32_t* out_n, int ks, void* stream);
 // block-max metadata of the blocks [b0, b1) of one field (upload time)
 void launch_blockmax(const DevIndex& ix, uint32_t b0, uint32_t b1, int fn_field, float cnorm, float* bmax, void* stream);
 // membership bitmaps + rank directories of selected terms (upload time): sel[i] = {global block, bitmap slot};

@@ -671,6 +671,50 @@ __global__ void __launch_bounds__(128) lead_merge_kernel(const LeadMergeParams p
     }
 }
 
+// one warp per query: merge the all-gathered per-rank top-k lists; the query's k is read from the
+// batch's query array (word k_word of a record of q_words words)
+template <int KS>
+__global__ void __launch_bounds__(128) merge_ranks_kernel(const uint2* __restrict__ hits, const uint32_t* __restrict__ n, uint32_t n_ranks,
+                                                          uint32_t n_queries, const uint32_t* __restrict__ qrec, uint32_t q_words,
+                                                          uint32_t k_word, uint32_t k_stride, uint2* out_hits, uint32_t* out_n) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t qi = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (qi >= n_queries) return;
+    const int k = (int)min(__ldg(qrec + (size_t)qi * q_words + k_word), k_stride);
+    WarpTopK<KS> tk;
+    tk.init();
+    for (uint32_t r = 0; r < n_ranks; r++) {
+        const uint32_t cnt = min(n[(size_t)r * n_queries + qi], k_stride);
+        const uint2* src = hits + ((size_t)r * n_queries + qi) * k_stride;
+        for (uint32_t i0 = 0; i0 < cnt; i0 += 32) {
+            const uint32_t i = i0 + lane;
+            uint64_t c = 0;
+            if (i < cnt) {
+                const uint2 h = src[i];
+                c = make_key(__uint_as_float(h.x), h.y);
+            }
+            tk.offer(c != 0, c, k, lane);
+        }
+    }
+    uint32_t nh = 0;
+#pragma unroll
+    for (int s = 0; s < KS; s++) {
+        const int r = s * 32 + lane;
+        const bool ok = r < k && tk.q[s] != 0;
+        if (r < (int)k_stride) {
+            uint2 h = make_uint2(0u, 0xFFFFFFFFu);
+            if (ok) {
+                h.x = __float_as_uint(unsortable((uint32_t)(tk.q[s] >> 32)));
+                h.y = ~(uint32_t)(tk.q[s] & 0xFFFFFFFFu);
+            }
+            out_hits[(size_t)qi * k_stride + r] = h;
+        }
+        nh += __popc(__ballot_sync(FULL, ok));
+    }
+    for (uint32_t r = KS * 32 + lane; r < k_stride; r += 32) out_hits[(size_t)qi * k_stride + r] = make_uint2(0u, 0xFFFFFFFFu);
+    if (lane == 0) out_n[qi] = nh;
+}
+
 // block-max metadata: one warp per block, the same arithmetic as the scoring path
 __global__ void __launch_bounds__(256) blockmax_kernel(const DevIndex ix, uint32_t b0, uint32_t b1, int fn_field,
                                                        float cnorm, float* bmax) {
@@ -789,6 +833,22 @@ void launch_lead_merge(const LeadMergeParams& p, int ks, void* stream) {
     if (ks <= 1) FG_LAUNCH(lead_merge_kernel<1>, grid, 128, 0, st, p);
     else if (ks <= 4) FG_LAUNCH(lead_merge_kernel<4>, grid, 128, 0, st, p);
     else FG_LAUNCH(lead_merge_kernel<32>, grid, 128, 0, st, p);
+}
+
+void launch_merge_ranks(const void* hits, const uint32_t* n, uint32_t n_ranks, uint32_t n_queries, const void* qrec, uint32_t q_words,
+                        uint32_t k_word, uint32_t k_stride, void* out_hits, uint32_t* out_n, int ks, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_queries == 0) return;
+    const unsigned grid = (n_queries + 3) / 4;
+    if (ks <= 1)
+        FG_LAUNCH(merge_ranks_kernel<1>, grid, 128, 0, st, (const uint2*)hits, n, n_ranks, n_queries, (const uint32_t*)qrec, q_words, k_word,
+                  k_stride, (uint2*)out_hits, out_n);
+    else if (ks <= 4)
+        FG_LAUNCH(merge_ranks_kernel<4>, grid, 128, 0, st, (const uint2*)hits, n, n_ranks, n_queries, (const uint32_t*)qrec, q_words, k_word,
+                  k_stride, (uint2*)out_hits, out_n);
+    else
+        FG_LAUNCH(merge_ranks_kernel<32>, grid, 128, 0, st, (const uint2*)hits, n, n_ranks, n_queries, (const uint32_t*)qrec, q_words, k_word,
+                  k_stride, (uint2*)out_hits, out_n);
 }
 
 void launch_blockmax(const DevIndex& ix, uint32_t b0, uint32_t b1, int fn_field, float cnorm, float* bmax, void* stream) {

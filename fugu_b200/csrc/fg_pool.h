@@ -47,7 +47,7 @@ private:
     HostPool() : pid_(getpid()) {
         unsigned hw = std::thread::hardware_concurrency();
         if (const char* e = getenv("FG_HOST_THREADS")) hw = (unsigned)atoi(e);
-        const int n = (int)std::max(1u, std::min(hw ? hw : 4u, 8u));
+        const int n = (int)std::max(1u, std::min(hw ? hw : 4u, 16u));
         for (int i = 1; i < n; i++) workers_.emplace_back([this] { loop(); });
     }
     ~HostPool() {
@@ -56,7 +56,11 @@ private:
             stop_ = true;
         }
         cv_.notify_all();
-        for (auto& t : workers_) t.join();
+        // a fork()ed child inherits the std::thread objects but not the threads: joining them there never returns
+        for (auto& t : workers_) {
+            if (getpid() == pid_) t.join();
+            else t.detach();
+        }
     }
     void loop() {
         unsigned long long seen = 0;

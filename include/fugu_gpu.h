@@ -179,8 +179,15 @@ int32_t fg_batch_prepare(fg_index* index, const fg_query_batch* batch, fg_batch*
  * the exact algorithmic-byte accounting pass, which is defined on exhaustive block evaluation); the default
  * lowering targets the lead-driven kernels (block-max / MaxScore pruning, skip-table gallop lookups). */
 #define FG_PREP_LEGACY 2u
+/* FG_PREP_PER_QUERY_STATUS: a query the device path cannot take (k == 0, k > 1024, more than 32 live leaves, a plan
+ * node outside the supported shapes) does not fail the batch: it becomes an empty query (0 hits) and its status is
+ * reported by fg_batch_query_status; the other queries of the batch are answered. Without the flag the first such
+ * query fails the call (default lowering only; FG_PREP_LEGACY batches always fail as a whole). */
+#define FG_PREP_PER_QUERY_STATUS 4u
 int32_t fg_batch_prepare_ex(fg_index* index, const fg_query_batch* batch, uint32_t prep_flags, fg_batch** out);
 void fg_batch_release(fg_batch* b);
+/* per-query lowering status of a prepared batch, [n_queries] (all FG_OK unless FG_PREP_PER_QUERY_STATUS was given) */
+int32_t fg_batch_query_status(const fg_batch* b, int32_t* out_status);
 #define FG_EXEC_EXACT_ACCOUNTING 1u /* exact block-need test for the algorithmic-byte counters (slow) */
 #define FG_EXEC_COUNTERS 4u         /* maintain bytes_blocks / bytes_redecode / scored_postings (cheap) */
 #define FG_EXEC_NO_PRUNE 8u         /* column scan: visit every 256-doc chunk even when the query's k-th best score
@@ -233,6 +240,27 @@ int32_t fg_batch_get_stats(fg_batch* b, fg_batch_stats* out);
 int32_t fg_merge_topk_device(fg_ctx* ctx, const void* d_gathered_hits, const void* d_gathered_n,
                              uint32_t n_ranks, uint32_t n_queries, uint32_t k, uint32_t k_stride,
                              void* d_out_hits, void* d_out_n);
+
+/* ---- multi-GPU, one process per GPU --------------------------------------------
+ * Documents are sharded by contiguous doc-id range; rank r uploads its shard with doc_id_base = first doc of the
+ * shard and the GLOBAL statistics (global_n_docs, global_doc_freq, total_num_tokens), so weights and norm caches
+ * are identical on every rank. One exchange per batch, inside the library: local top-k -> ncclAllGather of the
+ * per-shard lists over NVLink -> on-device select of the k best per query (score desc, global doc id asc). Every
+ * rank ends up with the global result. The communicator is NCCL's (libnccl.so.2, loaded on first use); the host
+ * distributes the 128-byte id of rank 0 to the other ranks by whatever transport it has (the reference is a
+ * single-process server, src/main.rs:11: there is no transport to mirror). */
+typedef struct fg_comm fg_comm;
+#define FG_COMM_ID_BYTES 128
+int32_t fg_comm_unique_id(void* out_id);
+int32_t fg_comm_create(fg_ctx* ctx, int32_t rank, int32_t n_ranks, const void* id, fg_comm** out);
+void fg_comm_destroy(fg_comm* comm);
+/* sum over all ranks, in place, HOST buffers (global statistics at upload time); collective */
+int32_t fg_comm_allreduce_sum_u64(fg_comm* comm, uint64_t* values, size_t n);
+int32_t fg_comm_allreduce_sum_u32(fg_comm* comm, uint32_t* values, size_t n);
+/* Collective: executes the prepared batch on this rank's shard, all-gathers the per-shard lists and merges them.
+ * d_hits [n_queries*k_stride] fg_hit and d_n_hits [n_queries] are DEVICE pointers receiving the GLOBAL result on
+ * every rank; asynchronous on the context's stream. Every rank must pass a batch prepared from the same queries. */
+int32_t fg_batch_execute_sharded(fg_batch* b, fg_comm* comm, uint32_t flags, uint32_t k_stride, void* d_hits, void* d_n_hits);
 
 /* ---- scoring helpers shared with the host planner (tantivy fieldnorm / Bm25Weight) ---------- */
 uint8_t fg_fieldnorm_to_id(uint32_t num_tokens);

@@ -470,6 +470,44 @@ def test_async_submit_collect_and_pipelined_requests(ctx):
     ds.close()
 
 
+def test_search_while_commits_land(ctx):
+    """A search that runs while another thread upserts + commits must not fail (the planner resolved
+    terms against a dictionary newer than the snapshot it executed on and the lowering rejected the ordinals).
+    Terms a snapshot does not know are empty scorers; a long query fails alone, not its siblings."""
+    import threading
+
+    from fugu_b200.dataset import Dataset, ObjectRecord
+
+    ds = Dataset(ctx)
+    ds.upsert([ObjectRecord(id=f"d{i}", text=f"alpha beta common{i % 7} w{i}") for i in range(200)], commit=True)
+    stop, errors = threading.Event(), []
+
+    def searcher():
+        try:
+            while not stop.is_set():
+                for q in ("alpha beta", "common3 OR fresh17", "fresh3 AND alpha", "w5 w6 w7"):
+                    ds.search(q, [], 0, 10)
+                h, n, c, st = ds.search_batch(["alpha", "fresh1 fresh2", "beta AND common1"], None, 0, 10, want_counts=False)
+                assert (st == 0).all()
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    th = [threading.Thread(target=searcher) for _ in range(3)]
+    for x in th:
+        x.start()
+    for r in range(25):
+        ds.upsert([ObjectRecord(id=f"n{r}_{i}", text=f"alpha fresh{r} fresh{i} newterm{r}x{i}") for i in range(20)], commit=True)
+    stop.set()
+    for x in th:
+        x.join()
+    assert not errors, errors[:3]
+    # one query over the leaf limit fails alone
+    long_q = " ".join(f"w{i}" for i in range(1, 40))  # 39 words x 2 fields > 32 live leaves
+    h, n, c, st = ds.search_batch(["alpha beta", long_q, "beta"], None, 0, 10, want_counts=False)
+    assert st[0] == 0 and st[2] == 0 and st[1] == nat.FG_ERR_UNSUPPORTED and n[0] > 0 and n[1] == 0 and n[2] > 0
+    ds.close()
+
+
 def test_multi_item_plans_forced_small_items(ctx, monkeypatch):
     """Work-item boundaries: with tiny item sizes every query is cut into many doc-id ranges (16-aligned
     cuts, blocks straddling two items, streamed leaves starting mid-list, per-item partial top-k lists and
