@@ -591,7 +591,7 @@ def main():
         "e2e": {"value": nq / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": int(lowered_bytes),
                 "d2h_bytes_per_step": int(out_bytes), "ms_per_step": e2e_s * 1e3,
                 "what": "fgh_search_batch: query strings (host) -> C++ planner -> plan lowering -> H2D plan -> kernels -> D2H hits "
-                        "(host); requests of 4096 queries and more are pipelined in four chunks (10 / 30 / 30 / 30 %%); match counts %s" % ("on" if counts else "off (TopDocs does not count)")},
+                        "(host); requests of 3072 queries and more are pipelined in two chunks (20 / 80 %%); match counts %s" % ("on" if counts else "off (TopDocs does not count)")},
         "gpu_launches": int(st_timed.n_launches + (1 if world > 1 else 0)) * args.steps,
         "parity": parity,
         "ms_per_step_min": float(np.min(step_ms)), "ms_per_step_median": float(np.median(step_ms)),

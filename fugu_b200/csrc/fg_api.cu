@@ -88,8 +88,10 @@ static const float K1 = 1.2f, B = 0.75f;
 // ------------------------------------------------------------------------------------------
 // context
 // ------------------------------------------------------------------------------------------
+struct LeadScratch;
 struct fg_ctx {
     int device = 0;
+    std::vector<std::unique_ptr<LeadScratch>> lead_scratch;  // reusable host vectors of the plan lowering (under pool_mu)
     cudaStream_t own = nullptr;
     cudaStream_t stream = nullptr;
     std::mutex mu;
@@ -767,6 +769,9 @@ struct fg_batch {
     uint32_t n_cursors = 0;
     uint64_t partial_entries = 0;
     size_t lsz[4] = {0, 0, 0, 0};
+    void* d_plan = nullptr;        // one device block [LQuery | LLeaf | LItem] (l_queries / l_leaves / l_items point into it)
+    void* h_plan = nullptr;        // its page-locked source (kept until release: the upload is asynchronous)
+    size_t plan_sz = 0;
     std::vector<int32_t> qstatus;  // FG_PREP_PER_QUERY_STATUS: per-query lowering status
     std::string first_bad;
 };
@@ -792,7 +797,9 @@ extern "C" void fg_batch_release(fg_batch* b) {
         pool_free(c, b->d_stats, b->sz[5]); pool_free(c, b->d_qtheta, b->sz[6]);
         pool_free(c, b->d_out, b->out_sz);
         pinned_free(c, b->h_out, b->out_sz);
-        pool_free(c, b->l_queries, b->lsz[0]); pool_free(c, b->l_leaves, b->lsz[1]); pool_free(c, b->l_items, b->lsz[2]);
+        if (b->ev_up) cudaEventSynchronize(b->ev_up);  // the plan upload reads h_plan
+        pool_free(c, b->d_plan, b->plan_sz);
+        pinned_free(c, b->h_plan, b->plan_sz);
         pool_free(c, b->l_state, b->lsz[3]);
     }
     for (auto& e : b->ev) if (e) cudaEventDestroy(e);
@@ -806,6 +813,42 @@ extern "C" void fg_batch_release(fg_batch* b) {
 // ------------------------------------------------------------------------------------------
 // plan lowering for the lead-driven kernels (fg_lead.cu; the scheme is described in fg_internal.h)
 // ------------------------------------------------------------------------------------------
+constexpr int LKEYS = 16 * 32;  // item sort keys: lead index (clamped to 15), then list length (log2)
+struct LeadPart {
+    std::vector<LLeaf> leaves;
+    std::vector<LItem> items;       // cursor = index of the (query, lead) pair inside this part
+    std::vector<uint32_t> item_key; // sort key: lead index, then list length
+    std::vector<uint32_t> q_items;  // items per query of this part
+    uint32_t key_count[LKEYS];
+    uint32_t n_cursors = 0, kmax = 1;
+    uint64_t sum_k = 0;
+    int32_t rc = FG_OK;
+    std::string err;
+    void reset() {
+        leaves.clear(); items.clear(); item_key.clear(); q_items.clear();
+        memset(key_count, 0, sizeof(key_count));
+        n_cursors = 0; kmax = 1; sum_k = 0; rc = FG_OK; err.clear();
+    }
+};
+struct LeadScratch {
+    std::vector<LeadPart> parts;
+    std::vector<LQuery> lq;
+};
+static std::unique_ptr<LeadScratch> take_scratch(fg_ctx* c) {
+    std::lock_guard<std::mutex> g(c->pool_mu);
+    if (!c->lead_scratch.empty()) {
+        std::unique_ptr<LeadScratch> s = std::move(c->lead_scratch.back());
+        c->lead_scratch.pop_back();
+        return s;
+    }
+    return std::unique_ptr<LeadScratch>(new LeadScratch());
+}
+static void give_scratch(fg_ctx* c, std::unique_ptr<LeadScratch> s) {
+    if (!s) return;
+    std::lock_guard<std::mutex> g(c->pool_mu);
+    if (c->lead_scratch.size() < 8) c->lead_scratch.push_back(std::move(s));
+}
+
 static inline uint32_t host_sortable(float f) {
     uint32_t b;
     memcpy(&b, &f, 4);
@@ -818,17 +861,16 @@ static int32_t prepare_lead(fg_index* ix, const fg_query_batch* qb, uint32_t pre
     const uint32_t PAR_BLOCKS = ctx->lead_par_blocks, MAX_PAR = ctx->lead_max_par, CHUNK = ctx->lead_chunk;
     constexpr int MAXC = 40;
     struct CRec { uint32_t occur, begin, count; uint64_t df; };
-    struct Part {
-        std::vector<LLeaf> leaves;
-        std::vector<LItem> items;       // cursor = index of the (query, lead) pair inside this part
-        std::vector<uint32_t> item_key; // sort key: lead index, then list length
-        std::vector<uint32_t> q_items;  // items per query of this part
-        uint32_t n_cursors = 0, kmax = 1;
-        uint64_t sum_k = 0;
-        int32_t rc = FG_OK;
-        std::string err;
-    };
-    std::vector<LQuery> lq(qb->n_queries);
+    using Part = LeadPart;
+    // scratch vectors are recycled through the context: fresh multi-megabyte vectors cost more in page faults than the
+    // lowering itself
+    std::unique_ptr<LeadScratch> scratch = take_scratch(ctx);
+    struct Giveback {
+        fg_ctx* c; std::unique_ptr<LeadScratch>& s;
+        ~Giveback() { give_scratch(c, std::move(s)); }
+    } giveback{ctx, scratch};
+    std::vector<LQuery>& lq = scratch->lq;
+    lq.resize(qb->n_queries);
     const bool per_query = (prep_flags & FG_PREP_PER_QUERY_STATUS) != 0;
     std::vector<int32_t> qstatus(per_query ? qb->n_queries : 0, FG_OK);
     std::string first_bad;  // (written by the thread that owns the query's part; read after the join)
@@ -848,6 +890,7 @@ static int32_t prepare_lead(fg_index* ix, const fg_query_batch* qb, uint32_t pre
         LLeaf tmp[LMAX_LEAVES * 2];
         uint32_t ttop[LMAX_LEAVES * 2], ttopn[LMAX_LEAVES * 2];
         CRec crec[MAXC];
+        o.reset();
         o.q_items.assign(q_end - q_begin, 0);
         o.leaves.reserve((size_t)((uint64_t)qb->n_leaves * (q_end - q_begin) / std::max<uint32_t>(qb->n_queries, 1)) + 64);
         auto lower_query = [&](uint32_t qi) -> int32_t {
@@ -1041,7 +1084,9 @@ static int32_t prepare_lead(fg_index* ix, const fg_query_batch* qb, uint32_t pre
                 const uint32_t lg = 31u - (uint32_t)__builtin_clz(nb | 1u);
                 for (uint32_t c = 0; c < par; c++) {
                     o.items.push_back(LItem{qi, (uint32_t)i, o.n_cursors, CHUNK});
-                    o.item_key.push_back(std::min<uint32_t>((uint32_t)i, 15u) * 32u + (31u - lg));
+                    const uint32_t key = std::min<uint32_t>((uint32_t)i, 15u) * 32u + (31u - lg);
+                    o.item_key.push_back(key);
+                    o.key_count[key]++;
                 }
                 o.n_cursors++;
                 qitems += par;
@@ -1066,58 +1111,57 @@ static int32_t prepare_lead(fg_index* ix, const fg_query_batch* qb, uint32_t pre
     };
     const double t_begin = now_ms();
     const int LT = (int)std::max<uint64_t>(1, std::min<uint64_t>({(uint64_t)HostPool::get().size(), 16, (uint64_t)qb->n_queries / 96 + 1}));
-    std::vector<Part> parts((size_t)LT);
-    HostPool::get().run(LT, [&](int t) {
-        lower_range((uint32_t)((uint64_t)qb->n_queries * t / LT), (uint32_t)((uint64_t)qb->n_queries * (t + 1) / LT), parts[t]);
-    });
-    for (auto& o : parts)
-        if (o.rc != FG_OK) return fail(o.rc, "%s", o.err.c_str());
-    // concatenate the parts: rebase leaf_begin / cursors, assign the partial regions
-    size_t nl_tot = 0, ni_tot = 0;
-    for (auto& o : parts) { nl_tot += o.leaves.size(); ni_tot += o.items.size(); }
-    std::vector<LLeaf> leaves;
-    leaves.reserve(nl_tot);
-    std::vector<LItem> items(ni_tot);
-    uint32_t kmax = 1, n_cursors = 0;
-    uint64_t sum_k = 0, part_entries = 0;
+    std::vector<Part>& parts = scratch->parts;
+    if ((int)parts.size() < LT) parts.resize((size_t)LT);
+    auto q_lo = [&](int t) { return (uint32_t)((uint64_t)qb->n_queries * t / LT); };
+    HostPool::get().run(LT, [&](int t) { lower_range(q_lo(t), q_lo(t + 1), parts[t]); });
+    for (int t = 0; t < LT; t++)
+        if (parts[t].rc != FG_OK) return fail(parts[t].rc, "%s", parts[t].err.c_str());
+    // ---- layout of the concatenated plan: per-part bases, item positions by sort key, partial regions ----
+    // Items are ordered by (lead index, list length): every query's first lead is queued ahead of all second leads,
+    // and so on: a later lead mostly finds the query's threshold already set.
+    std::vector<uint32_t> leaf_base((size_t)LT + 1, 0), cur_base((size_t)LT + 1, 0);
+    std::vector<uint32_t> key_start((size_t)LT * LKEYS);
+    uint32_t kmax = 1;
+    uint64_t sum_k = 0, part_entries = 0, ni_tot = 0;
+    for (int t = 0; t < LT; t++) {
+        leaf_base[t + 1] = leaf_base[t] + (uint32_t)parts[t].leaves.size();
+        cur_base[t + 1] = cur_base[t] + parts[t].n_cursors;
+        kmax = std::max(kmax, parts[t].kmax);
+        sum_k += parts[t].sum_k;
+        ni_tot += parts[t].items.size();
+    }
     {
-        // counting sort of the items on (lead index, list length): every query's first lead is queued ahead of
-        // all second leads, and so on: a later (lower upper bound) lead mostly finds the threshold already set
-        uint32_t hist[16 * 32 + 1] = {0};
-        for (auto& o : parts)
-            for (uint32_t kx : o.item_key) hist[kx + 1]++;
-        for (int i = 0; i < 16 * 32; i++) hist[i + 1] += hist[i];
-        for (int t = 0; t < LT; t++) {
-            Part& o = parts[t];
-            const uint32_t lb = (uint32_t)leaves.size();
-            const uint32_t q0 = (uint32_t)((uint64_t)qb->n_queries * t / LT), q1 = (uint32_t)((uint64_t)qb->n_queries * (t + 1) / LT);
-            for (uint32_t qi = q0; qi < q1; qi++) {
-                LQuery& D = lq[qi];
-                D.leaf_begin += lb;
-                D.part_begin = (uint32_t)part_entries;
-                D.part_cap = o.q_items[qi - q0] * D.k;
-                part_entries += D.part_cap;
+        uint32_t run = 0;
+        for (int key = 0; key < LKEYS; key++)
+            for (int t = 0; t < LT; t++) {
+                key_start[(size_t)t * LKEYS + key] = run;
+                run += parts[t].key_count[key];
             }
-            for (size_t i = 0; i < o.items.size(); i++) {
-                LItem it = o.items[i];
-                it.cursor += n_cursors;
-                items[hist[o.item_key[i]]++] = it;
-            }
-            leaves.insert(leaves.end(), o.leaves.begin(), o.leaves.end());
-            n_cursors += o.n_cursors;
-            kmax = std::max(kmax, o.kmax);
-            sum_k += o.sum_k;
+    }
+    for (int t = 0; t < LT; t++) {
+        const uint32_t q0 = q_lo(t), q1 = q_lo(t + 1);
+        for (uint32_t qi = q0; qi < q1; qi++) {
+            LQuery& D = lq[qi];
+            D.leaf_begin += leaf_base[t];
+            D.part_begin = (uint32_t)part_entries;
+            D.part_cap = parts[t].q_items[qi - q0] * D.k;
+            part_entries += D.part_cap;
         }
     }
-    if (part_entries > 0xFFFFFFF0ull) return fail(FG_ERR_UNSUPPORTED, "partial result lists exceed 2^32 entries");
-    const double t_lowered = now_ms();
+    if (part_entries > 0xFFFFFFF0ull || ni_tot > 0xFFFFFFF0ull) return fail(FG_ERR_UNSUPPORTED, "partial result lists exceed 2^32 entries");
+    const uint32_t n_cursors = cur_base[LT];
+    const size_t nl_tot = leaf_base[LT];
+    const size_t off_leaves = ((size_t)qb->n_queries * sizeof(LQuery) + 255) & ~(size_t)255;
+    const size_t off_items = (off_leaves + nl_tot * sizeof(LLeaf) + 255) & ~(size_t)255;
+    const size_t plan_bytes = off_items + ni_tot * sizeof(LItem) + 256;
 
     CU(cudaSetDevice(ctx->device));
     std::unique_ptr<fg_batch, void (*)(fg_batch*)> b(new fg_batch(), fg_batch_release);
     b->ix = ix;
     b->lead = true;
     b->n_queries = qb->n_queries;
-    b->n_items = (uint32_t)items.size();
+    b->n_items = (uint32_t)ni_tot;
     b->kcap = kmax;
     b->ks = kmax <= 32 ? 1 : kmax <= 128 ? 4 : 32;
     b->sum_k = sum_k;
@@ -1125,17 +1169,29 @@ static int32_t prepare_lead(fg_index* ix, const fg_query_batch* qb, uint32_t pre
     b->partial_entries = part_entries;
     b->qstatus.swap(qstatus);
     b->first_bad.swap(first_bad);
-    auto up = [&](const void* src, size_t bytes, void** dst, size_t* sz) -> int32_t {
-        *sz = std::max<size_t>(bytes, 16);
-        CU(pool_alloc(ctx, dst, *sz));
-        if (bytes) CU(cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, ctx->up));
-        return FG_OK;
-    };
-    int32_t rc;
+    // the plan is assembled in page-locked memory (one block, one asynchronous copy) by the same worker threads
+    b->plan_sz = plan_bytes;
+    CU(pinned_alloc(ctx, &b->h_plan, plan_bytes));
+    char* hp = (char*)b->h_plan;
+    if (qb->n_queries) memcpy(hp, lq.data(), (size_t)qb->n_queries * sizeof(LQuery));
+    HostPool::get().run(LT, [&](int t) {
+        Part& o = parts[t];
+        if (!o.leaves.empty()) memcpy(hp + off_leaves + (size_t)leaf_base[t] * sizeof(LLeaf), o.leaves.data(), o.leaves.size() * sizeof(LLeaf));
+        LItem* items = reinterpret_cast<LItem*>(hp + off_items);
+        uint32_t* pos = key_start.data() + (size_t)t * LKEYS;
+        for (size_t i = 0; i < o.items.size(); i++) {
+            LItem it = o.items[i];
+            it.cursor += cur_base[t];
+            items[pos[o.item_key[i]]++] = it;
+        }
+    });
+    const double t_lowered = now_ms();
     std::lock_guard<std::mutex> g(ctx->mu);
-    if ((rc = up(lq.data(), lq.size() * sizeof(LQuery), (void**)&b->l_queries, &b->lsz[0]))) return rc;
-    if ((rc = up(leaves.data(), leaves.size() * sizeof(LLeaf), (void**)&b->l_leaves, &b->lsz[1]))) return rc;
-    if ((rc = up(items.data(), items.size() * sizeof(LItem), (void**)&b->l_items, &b->lsz[2]))) return rc;
+    CU(pool_alloc(ctx, &b->d_plan, plan_bytes));
+    CU(cudaMemcpyAsync(b->d_plan, b->h_plan, plan_bytes, cudaMemcpyHostToDevice, ctx->up));
+    b->l_queries = reinterpret_cast<LQuery*>((char*)b->d_plan);
+    b->l_leaves = reinterpret_cast<LLeaf*>((char*)b->d_plan + off_leaves);
+    b->l_items = reinterpret_cast<LItem*>((char*)b->d_plan + off_items);
     b->lsz[3] = ((size_t)4 + n_cursors + (3 + (size_t)LHIST_B) * (size_t)b->n_queries) * 4 + 32;
     CU(pool_alloc(ctx, (void**)&b->l_state, b->lsz[3]));
     b->sz[3] = std::max<size_t>((size_t)part_entries * 8, 16);
@@ -1145,11 +1201,10 @@ static int32_t prepare_lead(fg_index* ix, const fg_query_batch* qb, uint32_t pre
     for (auto& e : b->ev) CU(cudaEventCreate(&e));
     CU(cudaEventCreateWithFlags(&b->ev_up, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&b->ev_done, cudaEventDisableTiming));
-    CU(cudaEventRecord(b->ev_up, ctx->up));
-    CU(cudaStreamSynchronize(ctx->up));  // host vectors go out of scope (the compute stream is not touched)
+    CU(cudaEventRecord(b->ev_up, ctx->up));  // (the page-locked block lives as long as the batch: no wait here)
     if (ctx->env_timing)
-        fprintf(stderr, "[prepare_lead] lowering %.2f ms (%d threads), alloc + upload %.2f ms (%zu items, %zu leaves)\n", t_lowered - t_begin, LT,
-                now_ms() - t_lowered, items.size(), leaves.size());
+        fprintf(stderr, "[prepare_lead] lowering + assembly %.2f ms (%d threads), alloc + upload %.2f ms (%llu items, %zu leaves)\n", t_lowered - t_begin, LT,
+                now_ms() - t_lowered, (unsigned long long)ni_tot, nl_tot);
     *out = b.release();
     return FG_OK;
 }

@@ -1018,11 +1018,11 @@ extern "C" int32_t fgh_search_batch(fgh_dataset* ds, uint32_t n, const char* con
     // Large requests are cut into a few chunks and pipelined: while the device evaluates chunk i
     // (fg_batch_submit returns at once) this thread parses, plans and lowers chunk i+1, so the host
     // side of the call hides under the kernels instead of adding to them.
-    // Chunk count: measured with two chunks (20 % / 80 %) on a B200, the device sat idle while the host
-    // planned the second chunk (e2e = host time of the whole request + kernels of the last chunk: 2.0 + 0.8 x
-    // 3.4 ms for 5000 queries). Four chunks (10 / 30 / 30 / 30 %) leave only the last 30 % of the kernels
-    // outside the host's shadow; each chunk still holds > 1000 queries (about two waves of work items).
-    uint32_t nch = n >= 4096 ? 4u : (n >= 3072 ? 2u : 1u);
+    // Chunk count (measured on a B200, 5000-query C2 batch, round 2): planning + lowering of the whole request takes
+    // ~0.9 ms on 16 host threads, the kernels ~1.5 ms. One chunk: 2.4 ms; two chunks (20 % / 80 %): 2.3 ms; three:
+    // 2.5 ms; four: 2.9 ms -- every extra chunk costs the device more (smaller launches fill it worse) than the
+    // overlap gains once the host side is this short.
+    uint32_t nch = n >= 3072 ? 2u : 1u;
     if (const char* e = getenv("FG_PIPELINE_CHUNKS")) nch = (uint32_t)std::max(1, atoi(e));
     nch = std::max<uint32_t>(1, std::min(nch, n));
     double first_frac = 1.0 / nch;
