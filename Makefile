@@ -26,8 +26,9 @@ fugu_b200/libfugu_gpu.so: $(CSRC)/fg_kernels.o $(CSRC)/fg_lead.o $(CSRC)/fg_api.
 fugu_b200/synth/libfugu_synth.so: fugu_b200/synth/synth.cpp
 	$(CXX) -O3 -march=x86-64-v2 -std=c++17 -shared -fPIC -pthread -o $@ $<
 
-oracle/liboracle.so: oracle/oracle.cpp
-	$(CXX) -O3 -std=c++17 -shared -fPIC -pthread -o $@ $<
+oracle/liboracle.so: oracle/oracle.cpp oracle/orc.py
+	python -c 'import sys; sys.path.insert(0, "."); from oracle import orc; orc.build()'
+	@touch $@
 
 clean:
 	rm -f $(CSRC)/*.o fugu_b200/libfugu_gpu.so fugu_b200/synth/libfugu_synth.so oracle/liboracle.so

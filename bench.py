@@ -40,13 +40,20 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--docs", type=int, default=1_000_000)
-    ap.add_argument("--vocab", type=int, default=200_000)
-    ap.add_argument("--queries", type=int, default=5_000)
-    ap.add_argument("--cfg", type=int, default=2)
+    ap.add_argument("--docs", type=int, default=None, help="default: the configuration's size (SURVEY.md 8(d))")
+    ap.add_argument("--vocab", type=int, default=None)
+    ap.add_argument("--queries", type=int, default=None)
+    ap.add_argument("--cfg", type=int, default=2, help="BASELINE.json configuration 1..5 (2 = the metric's 1-GPU configuration)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
-    return ap.parse_args()
+    a = ap.parse_args()
+    from fugu_b200 import synth
+
+    base = synth.CONFIGS[a.cfg]
+    a.docs = a.docs or base.n_docs
+    a.vocab = a.vocab or base.vocab
+    a.queries = a.queries or base.n_queries
+    return a
 
 
 def env_rank():
@@ -441,6 +448,8 @@ def main():
     # ranks disagree by one step).
     t_step = max((time.perf_counter() - t_w) / max(args.warmup, 1), 1e-4)
     n_hold = int(min(2000, max(1, round(1.0 / t_step)))) if args.warmup else 100
+    if os.environ.get("FG_BENCH_HOLD"):  # dev (profiling runs under ncu): fewer untimed hold steps
+        n_hold = int(os.environ["FG_BENCH_HOLD"])
     if dist:
         n_hold = int(xch.allreduce_cpu(np.array([n_hold], np.int64), "max")[0])
     for _ in range(n_hold):

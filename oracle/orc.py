@@ -18,18 +18,43 @@ LIB = os.path.join(_HERE, "liboracle.so")
 _lib = None
 
 
+def _cpu_signature() -> str:
+    """model + ISA flags of the host CPU: liboracle.so is built with -march=native, so a library built on another
+    machine (the build container vs the GPU box) is rebuilt where it runs"""
+    import hashlib
+
+    sig = ""
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith(("model name", "flags")):
+                sig += line
+                if line.startswith("flags"):
+                    break
+    except OSError:
+        pass
+    return hashlib.sha1(sig.encode()).hexdigest()[:16]
+
+
 def build() -> None:
     src = os.path.join(_HERE, "oracle.cpp")
-    if os.path.exists(LIB) and os.path.getmtime(LIB) >= os.path.getmtime(src):
+    mark = os.path.join(_HERE, ".built_for")
+    sig = _cpu_signature()
+    try:
+        fresh = os.path.getmtime(LIB) >= os.path.getmtime(src) and open(mark).read().strip() == sig
+    except OSError:
+        fresh = False
+    if fresh:
         return
-    subprocess.check_call(["g++", "-O3", "-std=c++17", "-shared", "-fPIC", "-pthread", "-o", LIB, src])
+    tmp = LIB + f".tmp{os.getpid()}"
+    subprocess.check_call(["g++", "-O3", "-march=native", "-std=c++17", "-shared", "-fPIC", "-pthread", "-o", tmp, src])
+    os.replace(tmp, LIB)
+    open(mark, "w").write(sig)
 
 
 def lib():
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB):
-            build()
+        build()  # no-op when the library is current and was built for this CPU
         L = C.CDLL(LIB)
         vp, u32, u64, i32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int32
         L.orc_fieldnorm_to_id.argtypes = [u32]

@@ -52,7 +52,7 @@ def _gpu_tests():
     return out
 
 
-# The default CPU run keeps the emulated part to about three minutes: the tests below cover every kernel
+# The default CPU run keeps the emulated part to a few minutes: the tests below cover every kernel
 # class, the column-scan windows with gating and hit lists, deletes, snapshot refresh,
 # shards + device merge, concurrent callers, facets and the Dataset front-end. FG_EMU_FULL=1 runs all
 # `-m gpu` tests under emulation (32 minutes on 8 cores for the whole suite, deep pagination alone 19).
@@ -61,7 +61,7 @@ FAST = {"test_config1_two_term_and", "test_golden_cases_through_dataset_search",
         "test_delete_only_commit_refreshes_alive_bitset", "test_with_alive_shares_arrays_and_outlives_its_base",
         "test_facet_counts_large_synthetic_with_facet_columns", "test_uncommitted_documents_are_invisible", "test_config4_three_term_and_with_deletes",
         "test_config5_facet_filters", "test_edge_cases", "test_sharded_search_and_device_merge",
-        "test_accounting_matches_oracle_definition", "test_many_leaf_union_in_hash_mode",
+        "test_accounting_matches_oracle_definition",
         "test_concurrent_callers_share_one_index", "test_search_while_commits_land"}
 
 
