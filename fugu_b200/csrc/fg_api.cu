@@ -115,7 +115,7 @@ struct fg_ctx {
     bool env_no_prune = false;    // FG_NO_PRUNE=1: exhaustive evaluation (A/B runs; results are identical)
     bool env_timing = false;      // FG_TIMING=1
     bool env_prof = false;        // FG_PROF=1
-    uint32_t lead_par_blocks = 16, lead_max_par = 64, lead_chunk = 16, lead_round4 = 1;
+    uint32_t lead_par_blocks = 16, lead_max_par = 64, lead_chunk = 16, lead_tma = 0;
 };
 static uint64_t env_u64_early(const char* name, uint64_t dflt);
 
@@ -201,7 +201,7 @@ extern "C" int32_t fg_ctx_create(int32_t device, fg_ctx** out) {
     c->lead_par_blocks = (uint32_t)std::max<uint64_t>(1, env_u64_early("FG_LEAD_PAR_BLOCKS", 16));
     c->lead_max_par = (uint32_t)std::max<uint64_t>(1, env_u64_early("FG_LEAD_MAX_PAR", 64));
     c->lead_chunk = (uint32_t)std::max<uint64_t>(1, env_u64_early("FG_LEAD_CHUNK", 16));
-    c->lead_round4 = (uint32_t)env_u64_early("FG_LEAD_ROUND4", 1);
+    c->lead_tma = (uint32_t)env_u64_early("FG_LEAD_TMA", 0);
     CU(cudaStreamCreateWithFlags(&c->own, cudaStreamNonBlocking));
     c->stream = c->own;
     for (int i = 0; i < NCLS - 1; i++) {
@@ -1626,7 +1626,7 @@ extern "C" int32_t fg_batch_execute(fg_batch* b, uint32_t flags, uint32_t k_stri
         p.want_counts = d_match_count ? 1 : 0;
         p.exhaustive = (d_match_count || d_match_bitmap || (flags & FG_EXEC_NO_PRUNE) || ctx->env_no_prune) ? 1 : 0;
         p.acct = (flags & FG_EXEC_COUNTERS) ? 1 : 0;
-        p.round4 = ctx->lead_round4;
+        p.tma = ctx->lead_tma;
         CU(cudaEventRecord(b->ev[0], st));
         launch_lead(p, b->ks, ctx->n_sms, st);
         CU(cudaEventRecord(b->ev[1], st));

@@ -142,5 +142,40 @@ __device__ __forceinline__ void unpack4(const uint32_t* __restrict__ w, int lane
     }
 }
 
+// the same from a payload staged in shared memory (plain loads; the staging slot is padded by one word)
+__device__ __forceinline__ void unpack4_smem(const uint32_t* w, int lane, uint32_t b, uint32_t v[4]) {
+    if (b == 0) {
+        v[0] = v[1] = v[2] = v[3] = 0;
+        return;
+    }
+    const uint32_t bit0 = (uint32_t)lane * 4u * b;
+    if (b <= 8) {
+        const uint32_t wi = bit0 >> 5, sh = bit0 & 31;
+        const uint32_t x = __funnelshift_r(w[wi], w[wi + 1], sh);
+        const uint32_t m = (1u << b) - 1u;
+        v[0] = x & m;
+        v[1] = (x >> b) & m;
+        v[2] = (x >> (2 * b)) & m;
+        v[3] = (x >> (3 * b)) & m;
+    } else if (b <= 16) {
+        const uint32_t wi = bit0 >> 5, sh = bit0 & 31;
+        const uint32_t w0 = w[wi], w1 = w[wi + 1], w2 = w[wi + 2];
+        const uint32_t x0 = __funnelshift_r(w0, w1, sh), x1 = __funnelshift_r(w1, w2, sh);
+        const uint32_t m = (1u << b) - 1u;
+        v[0] = x0 & m;
+        v[1] = __funnelshift_r(x0, x1, b) & m;
+        v[2] = __funnelshift_rc(x0, x1, 2 * b) & m;
+        v[3] = 3 * b >= 32 ? (x1 >> (3 * b - 32)) & m : __funnelshift_r(x0, x1, 3 * b) & m;
+    } else {
+        const uint32_t m = b >= 32 ? 0xFFFFFFFFu : ((1u << b) - 1u);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t bp = bit0 + j * b;
+            const uint32_t wi = bp >> 5, sh = bp & 31;
+            v[j] = __funnelshift_r(w[wi], w[wi + 1], sh) & m;
+        }
+    }
+}
+
 }  // namespace dev
 }  // namespace fg

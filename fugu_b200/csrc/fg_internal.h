@@ -237,7 +237,7 @@ struct LeadParams {
     uint32_t exhaustive;       // visit every posting (match counts / bitmaps wanted, or pruning switched off)
     uint32_t want_counts;
     uint32_t acct;
-    uint32_t round4;           // evaluate candidates 128 at a time (4 per lane) instead of 32
+    uint32_t tma;              // stage lead-block payloads in shared memory with 1-D bulk copies (cp.async.bulk)
 };
 struct LeadMergeParams {
     const LQuery* queries;

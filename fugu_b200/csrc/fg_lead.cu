@@ -32,9 +32,13 @@ namespace {
 
 constexpr int LNT = 256;      // threads per CTA
 constexpr int LNW = LNT / 32; // warps per CTA
-constexpr int LC = 4;         // decoded lookup blocks cached per warp (slot = LLeaf::slot, assigned by the lowering)
+#ifndef FG_LEAD_LC
+#define FG_LEAD_LC 4
+#endif
+constexpr int LC = FG_LEAD_LC;  // decoded lookup blocks cached per warp (slot = LLeaf::slot, assigned by the lowering)
 constexpr int ROUND = 128;            // candidates evaluated together: 4 per lane (4 independent gathers in flight per lookup)
 constexpr int CAND_CAP = 2 * BLOCK;   // candidates wait here until a full round is available
+constexpr int STAGE_BYTES = 512;      // staged payload capacity per slot: bd + bt <= 32 bits per posting
 
 struct WarpShared {
     LLeaf leaf[LMAX_LEAVES];
@@ -45,10 +49,30 @@ struct WarpShared {
     uint32_t cand_doc[CAND_CAP]; // candidates that survived their lead block's bound test, ascending
     uint32_t cand_val[CAND_CAP]; // their lead score (f32 bits), or the lead tf while required clauses come first
 };
+// Only in the kernel variant that stages lead-block payloads with 1-D bulk copies (TMA engine): two slots per warp, the
+// copy of the next block to decode is in flight while the current one is processed; payloads above STAGE_BYTES are
+// read with plain loads instead. (Kept out of WarpShared: shared memory the default variant does not use would only
+// shrink its L1.)
+struct StageShared {
+    uint32_t stage[2][STAGE_BYTES / 4 + 4];
+    uint64_t bar[2];
+    uint32_t bar_parity;  // bit s: parity of the phase the next wait on bar[s] needs (carried from item to item)
+    uint32_t pad_[3];
+};
 struct LeadShared {
+#ifndef FG_LEAD_GLOBAL_CACHE
     float cache[MAX_FIELDS * 256];  // BM25 norm caches K1*(1-B+B*dl/avg) of every field, by fieldnorm id
+#endif
     WarpShared w[LNW];
 };
+#ifdef FG_LEAD_GLOBAL_CACHE
+#define NORM_CACHE(S, p, i) __ldg((p).ix.cache + (i))
+#else
+#define NORM_CACHE(S, p, i) (S).cache[(i)]
+#endif
+#ifndef FG_LEAD_MINB
+#define FG_LEAD_MINB 3
+#endif
 
 // per-warp byte / posting counters (FG_EXEC_COUNTERS)
 struct Acct {
@@ -192,8 +216,8 @@ __device__ __forceinline__ uint32_t probe(const LeadParams& p, WarpShared& W, in
     return tf;
 }
 
-template <int KS>
-__device__ __forceinline__ void run_item(const LeadParams& p, const LeadShared& S, WarpShared& W, const LItem item, int lane) {
+template <int KS, bool TMA>
+__device__ __forceinline__ void run_item(const LeadParams& p, const LeadShared& S, WarpShared& W, StageShared& G, const LItem item, int lane) {
     const LQuery q = p.queries[item.query];
     __syncwarp();
     {
@@ -226,7 +250,7 @@ __device__ __forceinline__ void run_item(const LeadParams& p, const LeadShared& 
     uint32_t ncand = 0u;      // candidates waiting in W.cand_* (fewer than a round between blocks)
 
     auto norm_of = [&](const LLeaf& L, uint32_t c) -> float {
-        return L.fn_field >= 0 ? S.cache[L.fn_field * 256 + (int)__ldg(p.ix.fnorm[L.fn_field] + c)] : L.cnorm;
+        return L.fn_field >= 0 ? NORM_CACHE(S, p, L.fn_field * 256 + (int)__ldg(p.ix.fnorm[L.fn_field] + c)) : L.cnorm;
     };
 
     // ---- state of the block walk: chunk [g0 .. b1) claimed from the lead's cursor, current group of 32 blocks ----
@@ -243,6 +267,31 @@ __device__ __forceinline__ void run_item(const LeadParams& p, const LeadShared& 
         fin = prune && LD.ub + rest_s < theta;
     }
 
+    // ---- payload staging (p.tma): slot state is uniform across the warp ----
+    uint32_t st_blk[2] = {EMPTY, EMPTY};  // payload offset (off16) staged or in flight in each slot
+    uint32_t st_par = TMA ? G.bar_parity : 0u;  // bit s: parity of the phase the next wait on slot s needs
+    uint32_t st_pend = 0u;                // bit s: a copy into slot s was issued and not waited for yet
+    auto stage_wait = [&](int sl) {
+        if ((st_pend >> sl) & 1u) {
+            mbar_wait(&G.bar[sl], (st_par >> sl) & 1u);
+            st_par ^= 1u << sl;
+            st_pend &= ~(1u << sl);
+        }
+    };
+    auto stage_issue = [&](int sl, const uint4 e2) {
+        const uint32_t bytes = 16u * ((e2.w & 63u) + ((e2.w >> 6) & 63u));
+        stage_wait(sl);  // (a slot is re-armed only after its previous copy has landed)
+        __syncwarp();
+        if (lane == 0) bulk_g2s(G.stage[sl], p.ix.blk + (size_t)e2.z * 16u, bytes, &G.bar[sl]);
+        st_blk[sl] = e2.z;
+        st_pend |= 1u << sl;
+    };
+    auto stageable = [&](const uint4 e2) -> bool {
+        const uint32_t wsum = (e2.w & 63u) + ((e2.w >> 6) & 63u);
+        return TMA && wsum != 0u && wsum * 16u <= (uint32_t)STAGE_BYTES;
+    };
+    int st_cur = 0;  // slot the next decode reads from
+
     while (true) {
         // ================= next block to decode, if any =================
         bool have = false;
@@ -257,6 +306,21 @@ __device__ __forceinline__ void run_item(const LeadParams& p, const LeadShared& 
                 e.z = __shfl_sync(FULL, eg.z, src);
                 e.w = __shfl_sync(FULL, eg.w, src);
                 have = true;
+                if (TMA && stageable(e)) {
+                    if (st_blk[st_cur] != e.z) {
+                        if (st_blk[st_cur ^ 1] == e.z) st_cur ^= 1;  // staged ahead by the previous block
+                        else stage_issue(st_cur, e);
+                    }
+                    if (m) {  // the block after this one (unless the threshold drops it): its copy runs under this block's work
+                        const int nsrc = __ffs(m) - 1;
+                        uint4 ne;
+                        ne.x = __shfl_sync(FULL, eg.x, nsrc);
+                        ne.y = __shfl_sync(FULL, eg.y, nsrc);
+                        ne.z = __shfl_sync(FULL, eg.z, nsrc);
+                        ne.w = __shfl_sync(FULL, eg.w, nsrc);
+                        if (stageable(ne) && st_blk[st_cur ^ 1] != ne.z) stage_issue(st_cur ^ 1, ne);
+                    }
+                }
                 break;
             }
             if (g0 >= b1) {  // claim the next chunk of the lead
@@ -292,10 +356,19 @@ __device__ __forceinline__ void run_item(const LeadParams& p, const LeadShared& 
         // ================= decode the lead block, keep the postings that can still reach the top-k =================
         if (have) {
             const uint32_t bd = e.w & 63u, bt = (e.w >> 6) & 63u, n = ((e.w >> 12) & 127u) + 1u;
-            const uint32_t* wd = reinterpret_cast<const uint32_t*>(p.ix.blk + (size_t)e.z * 16u);
             uint32_t g[4], t[4];
-            unpack4(wd, lane, bd, g);
-            unpack4(wd + 4 * bd, lane, bt, t);
+            if (TMA && stageable(e)) {  // (uniform) the payload was staged in shared memory by a bulk copy
+                stage_wait(st_cur);
+                const uint32_t* wd = G.stage[st_cur];
+                unpack4_smem(wd, lane, bd, g);
+                unpack4_smem(wd + 4 * bd, lane, bt, t);
+                st_blk[st_cur] = EMPTY;  // (the slot may be re-armed as soon as every lane has read it: __syncwarp in stage_issue)
+                st_cur ^= 1;
+            } else {
+                const uint32_t* wd = reinterpret_cast<const uint32_t*>(p.ix.blk + (size_t)e.z * 16u);
+                unpack4(wd, lane, bd, g);
+                unpack4(wd + 4 * bd, lane, bt, t);
+            }
             g[1] += g[0]; g[2] += g[1]; g[3] += g[2];
             const uint32_t off = warp_excl_scan(g[3], lane) + e.y + 4u * lane;
             uint32_t d[4], val[4];
@@ -320,7 +393,7 @@ __device__ __forceinline__ void run_item(const LeadParams& p, const LeadShared& 
                 }
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
-                    const float nrm = LD.fn_field >= 0 ? S.cache[LD.fn_field * 256 + (int)id[j]] : LD.cnorm;
+                    const float nrm = LD.fn_field >= 0 ? NORM_CACHE(S, p, LD.fn_field * 256 + (int)id[j]) : LD.cnorm;
                     const float s = LD.weight * tf_factor((float)(t[j] + 1u), nrm);
                     if (prune) ok[j] = ok[j] && (s + rest_s >= theta);
                     val[j] = __float_as_uint(s);
@@ -546,6 +619,13 @@ __device__ __forceinline__ void run_item(const LeadParams& p, const LeadShared& 
         if (fin && !ncand) break;
     }
 
+    if (TMA) {
+        stage_wait(0);
+        stage_wait(1);
+        __syncwarp();
+        if (lane == 0) G.bar_parity = st_par;
+    }
+
     // append this warp's queue to the query's region of the partial array
     {
         // (the queue is sorted best first; ranks >= k are scratch)
@@ -584,20 +664,32 @@ __device__ __forceinline__ void run_item(const LeadParams& p, const LeadShared& 
     }
 }
 
-template <int KS>
-__global__ void __launch_bounds__(LNT, KS <= 4 ? 3 : 1) lead_kernel(const LeadParams p) {
+template <int KS, bool TMA>
+__global__ void __launch_bounds__(LNT, KS <= 1 ? FG_LEAD_MINB : (KS <= 4 ? 3 : 1)) lead_kernel(const LeadParams p) {
     FG_DYN_SMEM(smem);
     LeadShared& S = *reinterpret_cast<LeadShared*>(smem);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#ifndef FG_LEAD_GLOBAL_CACHE
     for (int i = tid; i < MAX_FIELDS * 256; i += LNT) S.cache[i] = __ldg(p.ix.cache + i);
     __syncthreads();
+#endif
     WarpShared& W = S.w[warp];
+    StageShared& G = reinterpret_cast<StageShared*>(smem + sizeof(LeadShared))[TMA ? warp : 0];  // (present only when TMA)
+    if (TMA) {
+        if (lane == 0) {
+            mbar_init(&G.bar[0], 1u);
+            mbar_init(&G.bar[1], 1u);
+            fence_mbar_init();
+            G.bar_parity = 0u;
+        }
+        __syncwarp();
+    }
     while (true) {
         uint32_t it = 0u;
         if (lane == 0) it = atomicAdd(p.work, 1u);
         it = __shfl_sync(FULL, it, 0);
         if (it >= p.n_items) break;
-        run_item<KS>(p, S, W, p.items[it], lane);
+        run_item<KS, TMA>(p, S, W, G, p.items[it], lane);
     }
 }
 
@@ -811,19 +903,30 @@ void launch_lead(const LeadParams& p, int ks, int n_sms, void* stream) {
     const uint32_t n_init = max(max(p.n_cursors, p.n_queries), 1u);
     FG_LAUNCH(lead_init_kernel, (n_init + 255) / 256, 256, 0, st, p);
     if (p.n_items == 0) return;
-    const int smem = (int)sizeof(LeadShared);
+    const int smem = (int)sizeof(LeadShared) + (p.tma ? (int)(LNW * sizeof(StageShared)) : 0);
     static bool configured = false;
     if (!configured) {
-        cudaFuncSetAttribute(lead_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        cudaFuncSetAttribute(lead_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        cudaFuncSetAttribute(lead_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        const int s0 = (int)sizeof(LeadShared), s1 = s0 + (int)(LNW * sizeof(StageShared));
+        cudaFuncSetAttribute(lead_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s0);
+        cudaFuncSetAttribute(lead_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s0);
+        cudaFuncSetAttribute(lead_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s0);
+        cudaFuncSetAttribute(lead_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1);
+        cudaFuncSetAttribute(lead_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s1);
         configured = true;
     }
-    const unsigned per_sm = ks <= 4 ? 3u : 1u;
+    const unsigned per_sm = ks <= 1 ? (unsigned)FG_LEAD_MINB : (ks <= 4 ? 3u : 1u);
     const unsigned grid = min((p.n_items + LNW - 1) / LNW, (unsigned)n_sms * per_sm);
-    if (ks <= 1) FG_LAUNCH(lead_kernel<1>, grid, LNT, smem, st, p);
-    else if (ks <= 4) FG_LAUNCH(lead_kernel<4>, grid, LNT, smem, st, p);
-    else FG_LAUNCH(lead_kernel<32>, grid, LNT, smem, st, p);
+    // p.tma (FG_LEAD_TMA=1): the variant that stages lead-block payloads with 1-D bulk copies -- measured 9 % slower
+    // than plain loads of L2-prefetched payloads on the C2 mix (profiles/r02_tma_ab.txt), so it is not the default
+    if (ks <= 1) {
+        if (p.tma) FG_LAUNCH((lead_kernel<1, true>), grid, LNT, smem, st, p);
+        else FG_LAUNCH((lead_kernel<1, false>), grid, LNT, smem, st, p);
+    } else if (ks <= 4) {
+        if (p.tma) FG_LAUNCH((lead_kernel<4, true>), grid, LNT, smem, st, p);
+        else FG_LAUNCH((lead_kernel<4, false>), grid, LNT, smem, st, p);
+    } else {
+        FG_LAUNCH((lead_kernel<32, false>), grid, LNT, (int)sizeof(LeadShared), st, p);
+    }
 }
 
 void launch_lead_merge(const LeadMergeParams& p, int ks, void* stream) {

@@ -62,7 +62,7 @@ FAST = {"test_config1_two_term_and", "test_golden_cases_through_dataset_search",
         "test_facet_counts_large_synthetic_with_facet_columns", "test_uncommitted_documents_are_invisible", "test_config4_three_term_and_with_deletes",
         "test_config5_facet_filters", "test_edge_cases", "test_sharded_search_and_device_merge",
         "test_accounting_matches_oracle_definition",
-        "test_concurrent_callers_share_one_index", "test_search_while_commits_land"}
+        "test_concurrent_callers_share_one_index", "test_search_while_commits_land", "test_bulk_copy_staged_variant_equals_default"}
 
 
 @pytest.mark.parametrize("fn", _gpu_tests())

@@ -508,6 +508,23 @@ def test_search_while_commits_land(ctx):
     ds.close()
 
 
+def test_bulk_copy_staged_variant_equals_default(ctx, monkeypatch):
+    """FG_LEAD_TMA=1 selects the kernel variant that stages lead-block payloads in shared memory with 1-D bulk
+    copies (cp.async.bulk + mbarrier, two slots per warp): same results as the default (plain loads)."""
+    monkeypatch.setenv("FG_LEAD_TMA", "1")
+    c2 = nat.Context(0)  # the switch is read when a context is created
+    try:
+        cfg = synth.Config(cfg=2, n_docs=30_000, vocab=6_000, n_queries=200, k=10, name_pct=10)
+        corpus = synth.Corpus.for_config(cfg)
+        desc = nat.HostIndexDesc(cfg.n_docs, synth.build_fields(corpus, 0, cfg.n_docs))
+        index = nat.Index(c2, desc)
+        batch = plan_queries(synth.gen_queries(cfg), vocab=cfg.vocab, n_text_fields=2)
+        check_batch_against_oracle(index, desc, batch, legacy=False)
+        index.close()
+    finally:
+        c2.close()
+
+
 def test_multi_item_plans_forced_small_items(ctx, monkeypatch):
     """Work-item boundaries: with tiny item sizes every query is cut into many doc-id ranges (16-aligned
     cuts, blocks straddling two items, streamed leaves starting mid-list, per-item partial top-k lists and

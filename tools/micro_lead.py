@@ -11,6 +11,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from fugu_b200 import _native as nat  # noqa: E402
 from fugu_b200 import synth  # noqa: E402
 
+if os.environ.get("MICRO_LIB"):  # dev: time another build of the library
+    nat.LIB_PATH = os.environ["MICRO_LIB"]
+
 
 def main():
     cfgn = int(sys.argv[1]) if len(sys.argv) > 1 else 2
