@@ -36,6 +36,7 @@ constexpr int LNW = LNT / 32; // warps per CTA
 #define FG_LEAD_LC 4
 #endif
 constexpr int LC = FG_LEAD_LC;  // decoded lookup blocks cached per warp (slot = LLeaf::slot, assigned by the lowering)
+static_assert(LC % 4 == 0, "WarpShared::cdocs must stay 16-byte aligned");
 constexpr int ROUND = 128;            // candidates evaluated together: 4 per lane (4 independent gathers in flight per lookup)
 constexpr int CAND_CAP = 2 * BLOCK;   // candidates wait here until a full round is available
 constexpr int STAGE_BYTES = 512;      // staged payload capacity per slot: bd + bt <= 32 bits per posting
@@ -60,16 +61,11 @@ struct StageShared {
     uint32_t pad_[3];
 };
 struct LeadShared {
-#ifndef FG_LEAD_GLOBAL_CACHE
-    float cache[MAX_FIELDS * 256];  // BM25 norm caches K1*(1-B+B*dl/avg) of every field, by fieldnorm id
-#endif
     WarpShared w[LNW];
 };
-#ifdef FG_LEAD_GLOBAL_CACHE
+// The BM25 norm caches K1*(1-B+B*dl/avg) (1 KB per field, by fieldnorm id) are read from global memory: they live in
+// L1, and 8 KB less shared memory per CTA is 24 KB more L1 per SM for the lookups' gathers (measured: -4 % step time).
 #define NORM_CACHE(S, p, i) __ldg((p).ix.cache + (i))
-#else
-#define NORM_CACHE(S, p, i) (S).cache[(i)]
-#endif
 #ifndef FG_LEAD_MINB
 #define FG_LEAD_MINB 3
 #endif
@@ -669,10 +665,6 @@ __global__ void __launch_bounds__(LNT, KS <= 1 ? FG_LEAD_MINB : (KS <= 4 ? 3 : 1
     FG_DYN_SMEM(smem);
     LeadShared& S = *reinterpret_cast<LeadShared*>(smem);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-#ifndef FG_LEAD_GLOBAL_CACHE
-    for (int i = tid; i < MAX_FIELDS * 256; i += LNT) S.cache[i] = __ldg(p.ix.cache + i);
-    __syncthreads();
-#endif
     WarpShared& W = S.w[warp];
     StageShared& G = reinterpret_cast<StageShared*>(smem + sizeof(LeadShared))[TMA ? warp : 0];  // (present only when TMA)
     if (TMA) {
