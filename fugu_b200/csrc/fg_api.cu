@@ -858,7 +858,7 @@ static inline uint32_t host_sortable(float f) {
 static int32_t prepare_lead(fg_index* ix, const fg_query_batch* qb, uint32_t prep_flags, fg_batch** out) {
     fg_ctx* ctx = ix->ctx;
     const bool use_cols = !(prep_flags & FG_PREP_NO_COLUMNS) && !ctx->env_no_columns;  // tf columns and membership bitmaps
-    const uint32_t PAR_BLOCKS = ctx->lead_par_blocks, MAX_PAR = ctx->lead_max_par, CHUNK = ctx->lead_chunk;
+    const uint32_t PAR_BLOCKS = ctx->lead_par_blocks, MAX_PAR = ctx->lead_max_par;
     constexpr int MAXC = 40;
     struct CRec { uint32_t occur, begin, count; uint64_t df; };
     using Part = LeadPart;
@@ -1074,22 +1074,43 @@ static int32_t prepare_lead(fg_index* ix, const fg_query_batch* qb, uint32_t pre
                 }
                 if (t0 > 0.f) D.theta0 = host_sortable(t0);
             }
-            // ---- work items: n_par copies per lead (one warp each) share a block cursor ----
+            // ---- work items ----
+            // Short leads that follow one another share one item (one warp walks them in order); a long lead gets an item
+            // of its own in `par` copies (one warp each) that share its block cursor. (A lead that cannot contribute a hit
+            // given the threshold known at lowering time still gets its place: whether the execution may prune is decided
+            // per execution; in the pruned form such a lead ends at its first threshold test.)
             uint32_t qitems = 0;
-            for (int i = 0; i < nl; i++) {
-                const uint32_t nb = o.leaves[l0 + i].n_blocks;
-                // (every copy appends up to k hits to the query's partial region: fewer copies for deep pages)
-                const uint32_t max_par = std::max<uint32_t>(4, std::min<uint32_t>(MAX_PAR, 4096u / q.k));
-                const uint32_t par = std::max<uint32_t>(1, std::min<uint32_t>(max_par, (nb + PAR_BLOCKS - 1) / PAR_BLOCKS));
-                const uint32_t lg = 31u - (uint32_t)__builtin_clz(nb | 1u);
+            const float bound_slack = D.slack + const_score;
+            int i = 0;
+            while (i < nl) {
+                const LLeaf& L0 = o.leaves[l0 + i];
+                const uint32_t nb = L0.n_blocks;
+                uint32_t par = 1, lg = 31u - (uint32_t)__builtin_clz(nb | 1u);
+                int j = i + 1;
+                if (nb > PAR_BLOCKS) {
+                    // (every copy appends up to k hits to the query's partial region: fewer copies for deep pages)
+                    const uint32_t max_par = std::max<uint32_t>(4, std::min<uint32_t>(MAX_PAR, 4096u / q.k));
+                    par = std::max<uint32_t>(1, std::min<uint32_t>(max_par, (nb + PAR_BLOCKS - 1) / PAR_BLOCKS));
+                } else {
+                    uint32_t sum = nb;
+                    while (j < nl && sum + o.leaves[l0 + j].n_blocks <= PAR_BLOCKS) {
+                        sum += o.leaves[l0 + j].n_blocks;
+                        j++;
+                    }
+                    lg = 31u - (uint32_t)__builtin_clz(sum | 1u);
+                }
+                const uint32_t key = std::min<uint32_t>((uint32_t)i, 15u) * 32u + (31u - lg);
+                float item_bound = -INFINITY;  // (only meaningful when the bounds hold: LQ_PRUNE)
+                for (int l = i; l < j; l++) item_bound = std::max(item_bound, o.leaves[l0 + l].ub + o.leaves[l0 + l].rest + bound_slack);
+                if (!positive) item_bound = INFINITY;
                 for (uint32_t c = 0; c < par; c++) {
-                    o.items.push_back(LItem{qi, (uint32_t)i, o.n_cursors, CHUNK});
-                    const uint32_t key = std::min<uint32_t>((uint32_t)i, 15u) * 32u + (31u - lg);
+                    o.items.push_back(LItem{qi, (uint32_t)i | ((uint32_t)j << 16), o.n_cursors, item_bound});
                     o.item_key.push_back(key);
                     o.key_count[key]++;
                 }
-                o.n_cursors++;
+                o.n_cursors += (uint32_t)(j - i);
                 qitems += par;
+                i = j;
             }
             o.q_items[qi - q_begin] = qitems;
             return FG_OK;
@@ -1627,6 +1648,7 @@ extern "C" int32_t fg_batch_execute(fg_batch* b, uint32_t flags, uint32_t k_stri
         p.exhaustive = (d_match_count || d_match_bitmap || (flags & FG_EXEC_NO_PRUNE) || ctx->env_no_prune) ? 1 : 0;
         p.acct = (flags & FG_EXEC_COUNTERS) ? 1 : 0;
         p.tma = ctx->lead_tma;
+        p.chunk = ctx->lead_chunk;
         CU(cudaEventRecord(b->ev[0], st));
         launch_lead(p, b->ks, ctx->n_sms, st);
         CU(cudaEventRecord(b->ev[1], st));

@@ -212,9 +212,11 @@ static_assert(sizeof(LQuery) == 64, "LQuery is uploaded as a flat array");
 // of the highest bucket at which the counts from the top reach k is a lower bound of the k-th best score.
 struct LItem {
     uint32_t query;
-    uint32_t lead;    // lead leaf (index inside the query) this item walks
-    uint32_t cursor;  // block cursor shared by the copies of this item (each copy is one warp)
-    uint32_t chunk;   // blocks claimed per step
+    uint32_t lead;    // lead leaves this item walks, one after the other: [lead & 0xFFFF, lead >> 16) (indices inside the query)
+    uint32_t cursor;  // block cursor of the first of them (the following leads use the following cursors); shared by
+                      // the copies of the item (each copy is one warp)
+    float bound;      // no document this item can offer scores above it (max over its leads of ub + rest + slack): an
+                      // item whose bound is below the query's threshold is skipped before its plan is even loaded
 };
 struct LeadParams {
     DevIndex ix;
@@ -237,6 +239,7 @@ struct LeadParams {
     uint32_t exhaustive;       // visit every posting (match counts / bitmaps wanted, or pruning switched off)
     uint32_t want_counts;
     uint32_t acct;
+    uint32_t chunk;            // blocks of a lead a warp claims per step
     uint32_t tma;              // stage lead-block payloads in shared memory with 1-D bulk copies (cp.async.bulk)
 };
 struct LeadMergeParams {

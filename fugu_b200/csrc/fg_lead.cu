@@ -227,14 +227,9 @@ __device__ __forceinline__ void run_item(const LeadParams& p, const LeadShared& 
     const int k = (int)q.k;
     const bool prune = !p.exhaustive && (q.flags & LQ_PRUNE);
     const bool acct = p.acct != 0;
-    const LLeaf LD = W.leaf[item.lead];
     const int n_lead = (int)q.n_lead, n_req = (int)q.n_req, n_leaves = (int)q.n_leaves;
-    const int lead = (int)item.lead;
     const bool has_req = n_req != 0;
-    const uint4* __restrict__ sk = p.ix.skip + LD.blk_begin;
-    const float* __restrict__ bmx = p.ix.bmax + LD.blk_begin;
     const float slack = q.slack + q.const_score;  // every bound below is compared with final scores, which include the constant
-    const float rest_s = LD.rest + slack;
     const unsigned lt = (1u << lane) - 1u;
     Acct A;
 
@@ -248,20 +243,6 @@ __device__ __forceinline__ void run_item(const LeadParams& p, const LeadShared& 
     auto norm_of = [&](const LLeaf& L, uint32_t c) -> float {
         return L.fn_field >= 0 ? NORM_CACHE(S, p, L.fn_field * 256 + (int)__ldg(p.ix.fnorm[L.fn_field] + c)) : L.cnorm;
     };
-
-    // ---- state of the block walk: chunk [g0 .. b1) claimed from the lead's cursor, current group of 32 blocks ----
-    uint32_t g0 = 0u, b1 = 0u;
-    unsigned m = 0u;     // blocks of the current group still to decode
-    uint4 eg = make_uint4(0u, 0u, 0u, 0u);  // this lane's skip entry of the group
-    float bound = INFINITY;                 // ... and its block's upper bound
-    bool fin = false;    // nothing left to decode (list exhausted, or the lead cannot contribute a hit any more)
-    {
-        if (prune) {
-            const uint32_t g = __ldcg(p.qtheta + item.query);
-            if (g > pub) { pub = g; theta = fmaxf(theta, unsortable(g)); }
-        }
-        fin = prune && LD.ub + rest_s < theta;
-    }
 
     // ---- payload staging (p.tma): slot state is uniform across the warp ----
     uint32_t st_blk[2] = {EMPTY, EMPTY};  // payload offset (off16) staged or in flight in each slot
@@ -287,6 +268,37 @@ __device__ __forceinline__ void run_item(const LeadParams& p, const LeadShared& 
         return TMA && wsum != 0u && wsum * 16u <= (uint32_t)STAGE_BYTES;
     };
     int st_cur = 0;  // slot the next decode reads from
+
+    // An item walks the leads [lead0, lead1) of its query one after the other (short lists share an item: the per-item
+    // cost -- plan fetch, threshold, result append -- is paid once, and the threshold the early leads establish is
+    // already in this warp's queue when the later ones start); a long lead has an item of its own, in several copies.
+    const int lead0 = (int)(item.lead & 0xFFFFu), lead1 = (int)(item.lead >> 16);
+    for (int lead = lead0; lead < lead1; lead++) {
+    const LLeaf LD = W.leaf[lead];
+    const uint4* __restrict__ sk = p.ix.skip + LD.blk_begin;
+    const float* __restrict__ bmx = p.ix.bmax + LD.blk_begin;
+    const float rest_s = LD.rest + slack;
+    uint32_t* const cursor = p.cursors + item.cursor + (uint32_t)(lead - lead0);
+    if (lead != lead0) {  // the lookups of the next lead start from the front of every list again
+        __syncwarp();
+        W.cur[lane] = EMPTY;
+        __syncwarp();
+    }
+
+    // ---- state of the block walk: chunk [g0 .. b1) claimed from the lead's cursor, current group of 32 blocks ----
+    uint32_t g0 = 0u, b1 = 0u;
+    unsigned m = 0u;     // blocks of the current group still to decode
+    uint4 eg = make_uint4(0u, 0u, 0u, 0u);  // this lane's skip entry of the group
+    float bound = INFINITY;                 // ... and its block's upper bound
+    bool fin = false;    // nothing left to decode (list exhausted, or the lead cannot contribute a hit any more)
+    {
+        if (prune) {
+            const uint32_t g = __ldcg(p.qtheta + item.query);
+            if (g > pub) { pub = g; theta = fmaxf(theta, unsortable(g)); }
+        }
+        fin = prune && LD.ub + rest_s < theta;
+    }
+
 
     while (true) {
         // ================= next block to decode, if any =================
@@ -321,11 +333,11 @@ __device__ __forceinline__ void run_item(const LeadParams& p, const LeadShared& 
             }
             if (g0 >= b1) {  // claim the next chunk of the lead
                 uint32_t c0 = 0u;
-                if (lane == 0) c0 = atomicAdd(p.cursors + item.cursor, item.chunk);
+                if (lane == 0) c0 = atomicAdd(cursor, p.chunk);
                 c0 = __shfl_sync(FULL, c0, 0);
                 if (c0 >= LD.n_blocks) { fin = true; break; }
                 g0 = c0;
-                b1 = min(c0 + item.chunk, LD.n_blocks);
+                b1 = min(c0 + p.chunk, LD.n_blocks);
             }
             if (prune) {
                 const uint32_t g = __ldcg(p.qtheta + item.query);
@@ -614,6 +626,7 @@ __device__ __forceinline__ void run_item(const LeadParams& p, const LeadShared& 
         }
         if (fin && !ncand) break;
     }
+    }  // leads of the item
 
     if (TMA) {
         stage_wait(0);
@@ -676,12 +689,18 @@ __global__ void __launch_bounds__(LNT, KS <= 1 ? FG_LEAD_MINB : (KS <= 4 ? 3 : 1
         }
         __syncwarp();
     }
+    // The work queue hands out ONE item per atomic, in array order: items are sorted by lead index, so a query's short
+    // leads have run -- and set its threshold -- before its long leads start. (Claiming 4 items per atomic was measured:
+    // the first wave then reaches 4x deeper into the array, later leads start cold, 80 % more blocks get decoded.)
     while (true) {
         uint32_t it = 0u;
         if (lane == 0) it = atomicAdd(p.work, 1u);
         it = __shfl_sync(FULL, it, 0);
         if (it >= p.n_items) break;
-        run_item<KS, TMA>(p, S, W, G, p.items[it], lane);
+        const LItem item = p.items[it];
+        // pruned form: an item none of whose documents can reach the query's current threshold costs two loads
+        if (!p.exhaustive && item.bound < unsortable(__ldcg(p.qtheta + item.query))) continue;
+        run_item<KS, TMA>(p, S, W, G, item, lane);
     }
 }
 
