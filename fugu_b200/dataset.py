@@ -129,6 +129,31 @@ class ObjectRecord:
                 out.append(f"/namespace/{self.namespace}/data/{self.data_type}")
         return out
 
+    def validate(self) -> None:
+        """ObjectRecord::validate, src/object.rs:31-78: raises ValueError with the reference's message. (Lengths are
+        byte lengths, as Rust's `String::len`.)"""
+        if not self.id:
+            raise ValueError("Object ID cannot be empty")
+        if len(self.id.encode()) > 256:
+            raise ValueError("Object ID too long (max 256 characters)")
+        if not self.text:
+            raise ValueError("Object text cannot be empty")
+        if len(self.text.encode()) > 10000:
+            raise ValueError("Text too long (max 10000 characters)")
+        if self.namespace is not None:
+            if not self.namespace or "/" in self.namespace or " " in self.namespace:
+                raise ValueError("Invalid namespace format")
+            if len(self.namespace.encode()) > 128:
+                raise ValueError("Namespace too long (max 128 characters)")
+        if self.facets is not None:
+            if len(self.facets) > 100:
+                raise ValueError("Too many facets (max 100 per object)")
+            for i, f in enumerate(self.facets):
+                if not f:
+                    raise ValueError(f"Facet at index {i} cannot be empty")
+                if len(f.encode()) > 512:
+                    raise ValueError(f"Facet at index {i} too long (max 512 characters)")
+
     def name(self) -> str | None:
         """metadata.name when it is a string (src/db/document.rs:131-139)."""
         if self.metadata and isinstance(self.metadata.get("name"), str):
@@ -169,10 +194,18 @@ def all_facet_paths(rec: ObjectRecord) -> list[str]:
 
 @dataclass
 class FuguSearchResult:
-    """src/db/search.rs:20-27 (text/metadata/facets hydration stays with the caller's doc store)."""
+    """src/db/search.rs:20-27. `text` / `metadata` / `facets` are filled by Dataset.search from the host-side record
+    table (hydration never touches the device); `doc` is the device's doc id."""
     id: str
     score: float
     doc: int = -1
+    text: str = ""
+    metadata: dict | None = None
+    facets: list[str] | None = None
+
+    def to_json(self) -> dict:
+        """serde field order of FuguSearchResult"""
+        return {"id": self.id, "score": self.score, "text": self.text, "metadata": self.metadata, "facets": self.facets}
 
 
 @dataclass
@@ -274,11 +307,15 @@ class Dataset:
         self.h = C.c_void_p()
         nat.check(_L().fgh_dataset_create(ctx.h if ctx is not None else None, C.byref(self.h)))
         self._keep = None
+        # hit hydration (convert_doc_to_search_result, src/db/search.rs:534-590): id -> the stored fields of the
+        # record, in host memory (row f1: a side table instead of a doc-store block decompress per hit)
+        self._records: dict[str, ObjectRecord] = {}
 
     # ---- ingest -------------------------------------------------------------------------
     def upsert(self, records: list[ObjectRecord], commit: bool = True) -> None:
         L = _L()
         for r in records:
+            self._records[r.id] = r
             facets = [f.encode() for f in all_facet_paths(r)]
             arr = (C.c_char_p * max(len(facets), 1))(*facets)
             nm = r.name()
@@ -288,6 +325,7 @@ class Dataset:
             self.commit()
 
     def delete(self, id_: str, commit: bool = True) -> None:
+        self._records.pop(id_, None)
         nat.check(_L().fgh_dataset_delete(self.h, id_.encode()))
         if commit:
             self.commit()
@@ -360,7 +398,16 @@ class Dataset:
         cnt = C.c_uint32()
         nat.check(_L().fgh_search(self.h, query.encode(), arr, len(filters), page, per_page, hits.ctypes.data,
                                   C.byref(n), C.byref(cnt)))
-        return [FuguSearchResult(self.doc_id(int(h["doc"])), float(h["score"]), int(h["doc"])) for h in hits[:n.value]]
+        return [self._hydrate(self.doc_id(int(h["doc"])), float(h["score"]), int(h["doc"])) for h in hits[:n.value]]
+
+    def _hydrate(self, id_: str, score: float, doc: int) -> FuguSearchResult:
+        """convert_doc_to_search_result (src/db/search.rs:534-590) from the host-side record table: stored text,
+        parsed metadata, the document's facet values (None when it has none)."""
+        r = self._records.get(id_)
+        if r is None:  # adopted (synthetic) corpora keep no records
+            return FuguSearchResult(id_, score, doc)
+        facets = all_facet_paths(r)
+        return FuguSearchResult(id_, score, doc, text=r.text, metadata=r.metadata, facets=facets or None)
 
     def search_batch(self, queries, filters: list[list[str]] | None = None, page: int = 0, per_page: int = 20,
                      want_counts: bool = True):

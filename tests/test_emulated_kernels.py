@@ -39,9 +39,10 @@ def ctx():
 def _gpu_tests():
     import tests.test_facets as tf
     import tests.test_gpu_parity as gp
+    import tests.test_handlers as th
 
     out = []
-    for mod in (gp, tf):
+    for mod in (gp, tf, th):
         for name in sorted(dir(mod)):
             fn = getattr(mod, name)
             if not name.startswith("test_") or not callable(fn):
@@ -62,7 +63,9 @@ FAST = {"test_config1_two_term_and", "test_golden_cases_through_dataset_search",
         "test_facet_counts_large_synthetic_with_facet_columns", "test_uncommitted_documents_are_invisible", "test_config4_three_term_and_with_deletes",
         "test_config5_facet_filters", "test_edge_cases", "test_sharded_search_and_device_merge",
         "test_accounting_matches_oracle_definition",
-        "test_concurrent_callers_share_one_index", "test_search_while_commits_land", "test_bulk_copy_staged_variant_equals_default"}
+        "test_concurrent_callers_share_one_index", "test_search_while_commits_land", "test_bulk_copy_staged_variant_equals_default",
+        "test_search_endpoint_shape_defaults_and_hydration", "test_query_json_post_namespace_text_flags_and_clamp", "test_get_front_ends",
+        "test_object_record_validate_messages"}
 
 
 @pytest.mark.parametrize("fn", _gpu_tests())

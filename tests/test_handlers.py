@@ -1,0 +1,112 @@
+"""The reference's search front-ends (src/server/handlers/search.rs:27-301,350-402) mirrored in
+fugu_b200/handlers.py on top of the GPU Dataset: JSON shapes, defaults, namespace selection, per_page clamp,
+"text" stripping, hydration (id, score, text, metadata, facets: src/db/search.rs:20-27,534-590) and
+ObjectRecord::validate (src/object.rs:31-78). -m gpu; the same functions run under the SIMT emulation on CPU."""
+import pytest
+
+from fugu_b200 import _native as nat
+from fugu_b200 import handlers as H
+from fugu_b200.dataset import Dataset, ObjectRecord
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = nat.Context(0)
+    yield c
+    c.close()
+
+
+def _state(ctx):
+    main, other = Dataset(ctx), Dataset(ctx)
+    recs = [ObjectRecord(id=f"doc{i}", text=f"alpha beta gamma{i % 3} filler{i}", metadata={"name": f"report {i}", "kind": "memo"},
+                         namespace="acme", organization=f"org{i % 2}", data_type="note") for i in range(30)]
+    recs.append(ObjectRecord(id="plain", text="alpha only here", facets=["/custom/path", "nolead/slash"]))
+    main.upsert(recs, commit=True)
+    other.upsert([ObjectRecord(id="o1", text="alpha in the other namespace")], commit=True)
+    return H.AppState(datasets={"fugu_db": main, "second": other}, default_namespace="fugu_db"), main, other
+
+
+def test_search_endpoint_shape_defaults_and_hydration(ctx):
+    state, main, other = _state(ctx)
+    code, out = H.search_endpoint(state, {"query": "alpha"})
+    assert code == 200 and list(out) == ["status", "query", "filters", "page", "per_page", "total", "results"]
+    assert out["status"] == "success" and out["page"] == 0 and out["per_page"] == 20 and out["filters"] == []
+    assert out["total"] == len(out["results"]) == 20  # 31 docs match, default per_page 20, no clamp in this handler
+    r = out["results"][0]
+    assert list(r) == ["id", "score", "text", "metadata", "facets"] and isinstance(r["score"], float)
+    byid = {x["id"]: x for x in out["results"]}
+    assert byid["plain"]["text"] == "alpha only here" and byid["plain"]["metadata"] is None
+    assert byid["plain"]["facets"] == ["/custom/path", "/nolead/slash"]  # explicit facets, normalised (document.rs:277-312)
+    some = next(x for x in out["results"] if x["id"].startswith("doc"))
+    assert some["metadata"]["kind"] == "memo" and "/namespace/acme" in some["facets"] and some["text"].startswith("alpha beta")
+    # pagination object, filters (facet Must group), page 1
+    code, out = H.search_endpoint(state, {"query": "alpha", "filters": ["/namespace/acme/organization/org1"], "page": {"page": 1, "per_page": 5}})
+    assert code == 200 and out["page"] == 1 and out["per_page"] == 5 and out["total"] == 5
+    assert all("/namespace/acme/organization/org1" in x["facets"] for x in out["results"])
+    # per_page = 0 is an error here (TopDocs::with_limit(0) panics in the reference): HTTP 500 shape
+    code, out = H.search_endpoint(state, {"query": "alpha", "page": {"per_page": 0}})
+    assert code == 500 and out["status"] == "error" and out["error"].startswith("Search failed:")
+    # POST /search only ever searches the default dataset (handlers/search.rs:169)
+    assert all(x["id"] != "o1" for x in H.search_endpoint(state, {"query": "alpha", "page": {"per_page": 100}})[1]["results"])
+    state.default_namespace = "missing"
+    assert H.search_endpoint(state, {"query": "alpha"}) == (500, {"status": "error", "error": "Default dataset not found"})
+    main.close(); other.close()
+
+
+def test_query_json_post_namespace_text_flags_and_clamp(ctx):
+    state, main, other = _state(ctx)
+    code, out = H.query_json_post(state, {"query": "alpha"})
+    assert code == 200 and list(out) == ["results", "total", "page", "per_page", "query", "includes_data_objects",
+                                         "targeting_conversations_or_organizations"]
+    assert out["per_page"] == 20 and out["total"] == 20 and out["query"] == "alpha"
+    assert all("text" not in r for r in out["results"])  # stripped by default (:264-272)
+    assert out["includes_data_objects"] is True and out["targeting_conversations_or_organizations"] is False
+    # namespace from the body (:256-257)
+    code, out = H.query_json_post(state, {"query": "alpha", "namespace": "second", "text": True})
+    assert code == 200 and [r["id"] for r in out["results"]] == ["o1"] and out["results"][0]["text"].startswith("alpha in")
+    # url flag wins, disagreement is reported (:221-236)
+    code, out = H.query_json_post(state, {"query": "alpha", "text": True}, url_text=False)
+    assert "developer_message" in out and all("text" not in r for r in out["results"])
+    # perform_search clamp: per_page 0 or > 100 -> 20 (:370-374)
+    for pp in (0, 101, 5000):
+        code, out = H.query_json_post(state, {"query": "alpha", "page": {"per_page": pp}})
+        assert code == 200 and out["per_page"] == 20
+    code, out = H.query_json_post(state, {"query": "alpha", "page": {"per_page": 100}})
+    assert out["per_page"] == 100 and out["total"] == 31
+    # conversation / organization filters flip include_data's default (:241-248)
+    code, out = H.query_json_post(state, {"query": "alpha", "filters": ["namespace/acme/organization/org0"]})
+    assert out["targeting_conversations_or_organizations"] is True and out["includes_data_objects"] is False and out["total"] == 15
+    code, out = H.query_json_post(state, {"query": "alpha", "namespace": "nope"})
+    assert code == 500 and out == {"error": "Search failed: Namespace 'nope' not found"}
+    main.close(); other.close()
+
+
+def test_get_front_ends(ctx):
+    state, main, other = _state(ctx)
+    code, out = H.query_text_get(state, "alpha", limit=7)
+    assert code == 200 and out["per_page"] == 7 and out["total"] == 7 and all("text" not in r for r in out["results"])
+    code, out = H.query_text_get(state, "alpha", text=True, namespace="second")
+    assert [r["id"] for r in out["results"]] == ["o1"] and "text" in out["results"][0]
+    code, out = H.query_text_path(state, "alpha%20AND%20gamma1")
+    assert code == 200 and out["query"] == "alpha AND gamma1" and out["total"] == 10 and out["per_page"] == 20
+    assert H.query_text_path(state, "%ff%fe")[0] == 400
+    main.close(); other.close()
+
+
+def test_object_record_validate_messages(ctx):
+    ok = ObjectRecord(id="a", text="t")
+    ok.validate()
+    for rec, msg in [(ObjectRecord(id="", text="t"), "Object ID cannot be empty"),
+                     (ObjectRecord(id="x" * 257, text="t"), "Object ID too long (max 256 characters)"),
+                     (ObjectRecord(id="a", text=""), "Object text cannot be empty"),
+                     (ObjectRecord(id="a", text="y" * 10001), "Text too long (max 10000 characters)"),
+                     (ObjectRecord(id="a", text="t", namespace="a b"), "Invalid namespace format"),
+                     (ObjectRecord(id="a", text="t", namespace="n" * 129), "Namespace too long (max 128 characters)"),
+                     (ObjectRecord(id="a", text="t", facets=["f"] * 101), "Too many facets (max 100 per object)"),
+                     (ObjectRecord(id="a", text="t", facets=["ok", ""]), "Facet at index 1 cannot be empty"),
+                     (ObjectRecord(id="a", text="t", facets=["z" * 513]), "Facet at index 0 too long (max 512 characters)")]:
+        with pytest.raises(ValueError) as e:
+            rec.validate()
+        assert str(e.value) == msg
