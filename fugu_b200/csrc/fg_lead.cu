@@ -293,7 +293,8 @@ __device__ __forceinline__ void run_item(const LeadParams& p, const LeadShared& 
     bool fin = false;    // nothing left to decode (list exhausted, or the lead cannot contribute a hit any more)
     {
         if (prune) {
-            const uint32_t g = __ldcg(p.qtheta + item.query);
+            // (one lane's view of the shared threshold for the whole warp: two lanes may see different values)
+            const uint32_t g = __shfl_sync(FULL, __ldcg(p.qtheta + item.query), 0);
             if (g > pub) { pub = g; theta = fmaxf(theta, unsortable(g)); }
         }
         fin = prune && LD.ub + rest_s < theta;
@@ -340,7 +341,7 @@ __device__ __forceinline__ void run_item(const LeadParams& p, const LeadShared& 
                 b1 = min(c0 + p.chunk, LD.n_blocks);
             }
             if (prune) {
-                const uint32_t g = __ldcg(p.qtheta + item.query);
+                const uint32_t g = __shfl_sync(FULL, __ldcg(p.qtheta + item.query), 0);
                 if (g > pub) { pub = g; theta = fmaxf(theta, unsortable(g)); }
                 if (LD.ub + rest_s < theta) { fin = true; break; }
             }
@@ -699,7 +700,8 @@ __global__ void __launch_bounds__(LNT, KS <= 1 ? FG_LEAD_MINB : (KS <= 4 ? 3 : 1
         if (it >= p.n_items) break;
         const LItem item = p.items[it];
         // pruned form: an item none of whose documents can reach the query's current threshold costs two loads
-        if (!p.exhaustive && item.bound < unsortable(__ldcg(p.qtheta + item.query))) continue;
+        // (decided by lane 0 for the warp: the threshold may move between two lanes' loads)
+        if (__shfl_sync(FULL, (int)(!p.exhaustive && item.bound < unsortable(__ldcg(p.qtheta + item.query))), 0)) continue;
         run_item<KS, TMA>(p, S, W, G, item, lane);
     }
 }

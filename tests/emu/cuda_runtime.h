@@ -88,6 +88,7 @@ extern Fiber* g_cur;
 extern Cta g_cta;
 extern unsigned long long g_progress;
 void yield();
+extern const char* g_kernel_name;
 void launch(unsigned grid, unsigned block, size_t smem, const std::function<void()>& body);
 void die(const char* what);
 inline unsigned char* dyn_smem() { return g_cta.dyn; }

@@ -76,6 +76,7 @@ static void fiber_main() {
     die("resumed a finished fiber");
 }
 
+const char* g_kernel_name = "?";
 void launch(unsigned grid, unsigned block, size_t smem, const std::function<void()>& body) {
     std::lock_guard<std::recursive_mutex> lock(g_launch_mu);
     if (g_cur) die("nested launch");
@@ -141,7 +142,7 @@ void launch(unsigned grid, unsigned block, size_t smem, const std::function<void
             }
             g_cur = nullptr;
             if (live && g_progress == before) {
-                fprintf(stderr, "fgemu: deadlock in block %u: %u threads wait for a barrier or a warp collective that cannot complete\n", b, live);
+                fprintf(stderr, "fgemu: deadlock in kernel %s, block %u: %u threads wait for a barrier or a warp collective that cannot complete\n", g_kernel_name, b, live);
                 for (unsigned w = 0; w < block / 32; w++)
                     fprintf(stderr, "  warp %u: arrived %08x drained %08x draining %d\n", w, g_cta.warps[w].arrived, g_cta.warps[w].drained, g_cta.warps[w].draining);
                 fprintf(stderr, "  barrier: %u of %u arrived\n", g_cta.bar_arrived, g_cta.live);

@@ -5,7 +5,7 @@
 #include "cuda_runtime.h"
 
 #define FG_DYN_SMEM(name) unsigned char* name = fgemu::dyn_smem()
-#define FG_LAUNCH(kernel, grid, block, smem, stream, ...) fgemu::launch((grid), (block), (smem), [&]() { kernel(__VA_ARGS__); })
+#define FG_LAUNCH(kernel, grid, block, smem, stream, ...) (fgemu::g_kernel_name = #kernel, fgemu::launch((grid), (block), (smem), [&]() { kernel(__VA_ARGS__); }))
 #define FG_MAGIC_2P23(m) m = 0x4B000000u
 
 namespace fg {
