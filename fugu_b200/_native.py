@@ -14,6 +14,10 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libfugu_gpu.so")
+# the host library (include/fugu_host.h: planner, tokenizer, dataset builder); contains no CUDA code and
+# binds the device library on first use. None = libfugu_host.so next to LIB_PATH, or LIB_PATH itself when
+# that directory has no separate host library (a monolithic build exports both ABIs).
+HOST_LIB_PATH = None
 
 FG_OK = 0
 FG_ERR_INVALID = -1
@@ -189,6 +193,32 @@ def lib() -> C.CDLL:
 def check(rc: int) -> None:
     if rc != FG_OK:
         raise FgError(rc, lib().fg_last_error().decode("utf-8", "replace"))
+
+
+_host_lib = None
+
+
+def host_lib() -> C.CDLL:
+    """Load libfugu_host.so (no CUDA code is mapped by this call)."""
+    global _host_lib
+    if _host_lib is not None:
+        return _host_lib
+    path = HOST_LIB_PATH
+    if path is None:
+        path = os.path.join(os.path.dirname(LIB_PATH), "libfugu_host.so")
+        if not os.path.exists(path):
+            path = LIB_PATH
+    if not os.path.exists(path):
+        raise ImportError(f"{path} is missing: build it with `make` or `python -c 'import __graft_entry__ as g; g.build()'`.")
+    _host_lib = C.CDLL(path)
+    _host_lib.fgh_last_error.restype = C.c_char_p
+    return _host_lib
+
+
+def hcheck(rc: int) -> None:
+    """status of an fgh_* call (include/fugu_host.h)"""
+    if rc != FG_OK:
+        raise FgError(rc, host_lib().fgh_last_error().decode("utf-8", "replace"))
 
 
 def _ptr(a):

@@ -4,7 +4,10 @@
 // A.1/A.2 (tantivy 0.24.1 side, upstream-recalled). No search arithmetic happens here: every
 // search goes to the device through fg_search_batch.
 #include <algorithm>
+#include <chrono>
+#include <condition_variable>
 #include <cstdarg>
+#include <deque>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -17,14 +20,114 @@
 #include <vector>
 
 #include "../../include/fugu_host.h"
+#include <dlfcn.h>
 #include <time.h>
-#include "fg_error.h"
 #include "fg_pool.h"
 #include "fg_unicode_tables.h"
 
-using fg::host_fail;
-
+// ------------------------------------------------------------------------------------------
+// errors, and the device library behind this one
+// ------------------------------------------------------------------------------------------
+// libfugu_host.so (this file) contains no CUDA code and does not link against libfugu_gpu.so: planning,
+// tokenising and the dataset builder work in a process that never touches a GPU (the reference arm of the
+// bench, a GPU-less build of the Rust host). The device entry points are bound on first use: from the
+// library this code is linked into when that one exports them (a monolithic build), else from
+// libfugu_gpu.so in the directory of libfugu_host.so. Without them every call that needs the device
+// fails with FG_ERR_NO_DEVICE.
 namespace {
+
+thread_local char g_herr[512] = "";
+int32_t host_fail(int32_t code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_herr, sizeof(g_herr), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+struct DevApi {
+#define FGH_DEV_FN(name) decltype(&::name) name = nullptr
+    FGH_DEV_FN(fg_last_error);
+    FGH_DEV_FN(fg_index_upload);
+    FGH_DEV_FN(fg_index_release);
+    FGH_DEV_FN(fg_index_with_alive);
+    FGH_DEV_FN(fg_index_term_info);
+    FGH_DEV_FN(fg_search_batch);
+    FGH_DEV_FN(fg_batch_prepare_ex);
+    FGH_DEV_FN(fg_batch_query_status);
+    FGH_DEV_FN(fg_batch_submit);
+    FGH_DEV_FN(fg_batch_collect);
+    FGH_DEV_FN(fg_batch_release);
+#undef FGH_DEV_FN
+    bool ok = false;
+    std::string why;
+};
+
+const DevApi& dev_api() {
+    static const DevApi api = [] {
+        DevApi a;
+        Dl_info self;
+        memset(&self, 0, sizeof(self));
+        std::string own = dladdr((const void*)&host_fail, &self) && self.dli_fname ? self.dli_fname : "";
+        void* h = own.empty() ? nullptr : dlopen(own.c_str(), RTLD_NOW | RTLD_LOCAL);
+        if (!h || !dlsym(h, "fg_batch_prepare_ex")) {
+            const size_t slash = own.rfind('/');
+            const std::string sibling = (slash == std::string::npos ? std::string("") : own.substr(0, slash + 1)) + "libfugu_gpu.so";
+            h = dlopen(sibling.c_str(), RTLD_NOW | RTLD_LOCAL);
+            if (!h) {
+                const char* e = dlerror();
+                a.why = "device library " + sibling + " cannot be loaded (" + (e ? e : "?") + "); there is no CPU fallback";
+                return a;
+            }
+        }
+        bool all = true;
+#define FGH_DEV_BIND(name) all = ((a.name = reinterpret_cast<decltype(a.name)>(dlsym(h, #name))) != nullptr) && all
+        FGH_DEV_BIND(fg_last_error);
+        FGH_DEV_BIND(fg_index_upload);
+        FGH_DEV_BIND(fg_index_release);
+        FGH_DEV_BIND(fg_index_with_alive);
+        FGH_DEV_BIND(fg_index_term_info);
+        FGH_DEV_BIND(fg_search_batch);
+        FGH_DEV_BIND(fg_batch_prepare_ex);
+        FGH_DEV_BIND(fg_batch_query_status);
+        FGH_DEV_BIND(fg_batch_submit);
+        FGH_DEV_BIND(fg_batch_collect);
+        FGH_DEV_BIND(fg_batch_release);
+#undef FGH_DEV_BIND
+        a.ok = all;
+        if (!all) a.why = "the device library does not export the fugu_gpu.h entry points this host library needs (version mismatch)";
+        return a;
+    }();
+    return api;
+}
+// status of a device-library call: on failure its message becomes this library's (fgh_last_error)
+int32_t D(int32_t rc) {
+    if (rc != FG_OK) {
+        const char* m = dev_api().fg_last_error ? dev_api().fg_last_error() : "";
+        snprintf(g_herr, sizeof(g_herr), "%s", m ? m : "");
+    }
+    return rc;
+}
+#define DEV_OR_FAIL()                                                                  \
+    do {                                                                               \
+        if (!dev_api().ok) return host_fail(FG_ERR_NO_DEVICE, "%s", dev_api().why.c_str()); \
+    } while (0)
+
+// tantivy's fieldnorm code (Lucene SmallFloat, 24 exact values, then 3 mantissa bits per
+// power of two): the largest id whose decoded value is <= n. fg_fieldnorm_to_id of the device library
+// computes the same table; it is repeated here so that building documents needs no device library.
+uint8_t fieldnorm_id(uint32_t n) {
+    static const std::vector<uint64_t> table = [] {
+        std::vector<uint64_t> t(256);
+        for (uint32_t id = 0; id < 256; id++) {
+            if (id < 24) { t[id] = id; continue; }
+            const uint32_t m = (id - 24) & 7u, e = (id - 24) >> 3;
+            t[id] = 24u + (e == 0 ? (uint64_t)m : ((uint64_t)(m | 8u) << (e - 1)));
+        }
+        return t;
+    }();
+    return (uint8_t)((std::upper_bound(table.begin(), table.end(), (uint64_t)n) - table.begin()) - 1);
+}
 
 // ------------------------------------------------------------------------------------------
 // A.1 default analyzer: SimpleTokenizer -> RemoveLongFilter(40) -> LowerCaser
@@ -381,6 +484,8 @@ struct fgh_dataset {
     uint32_t doc_base = 0;
 };
 
+extern "C" const char* fgh_last_error(void) { return g_herr; }
+
 extern "C" int32_t fgh_dataset_create(fg_ctx* ctx, fgh_dataset** out) {
     if (!out) return host_fail(FG_ERR_INVALID, "fgh_dataset_create: out is NULL");
     *out = new fgh_dataset();
@@ -501,9 +606,10 @@ extern "C" int32_t fgh_dataset_commit(fgh_dataset* ds) {
     if (ds->index && ds->committed_docs == ds->n_docs && !getenv("FG_NO_INCREMENTAL")) {
         // only deletes since the last commit: the postings are unchanged, refresh the alive bitset
         fg_index* nx = nullptr;
-        int32_t rc = fg_index_with_alive(ds->index.get(), any_dead ? alive.data() : nullptr, &nx);
+        DEV_OR_FAIL();
+        int32_t rc = D(dev_api().fg_index_with_alive(ds->index.get(), any_dead ? alive.data() : nullptr, &nx));
         if (rc) return rc;
-        ds->index.reset(nx, fg_index_release);
+        ds->index.reset(nx, dev_api().fg_index_release);
         ds->dirty = false;
         return FG_OK;
     }
@@ -530,7 +636,7 @@ extern "C" int32_t fgh_dataset_commit(fgh_dataset* ds) {
         fd[f].doc_ids = c[f].docs.data();
         if (f != (int)FGH_FIELD_FACET) {
             c[f].fn.resize(ds->n_docs);
-            for (uint32_t d = 0; d < ds->n_docs; d++) c[f].fn[d] = fg_fieldnorm_to_id(fb.doc_len[d]);
+            for (uint32_t d = 0; d < ds->n_docs; d++) c[f].fn[d] = fieldnorm_id(fb.doc_len[d]);
             fd[f].flags = FG_FIELD_HAS_FIELDNORMS | FG_FIELD_HAS_FREQS;
             fd[f].fieldnorm_ids = c[f].fn.data();
             fd[f].term_freqs = c[f].tfs.data();
@@ -543,9 +649,10 @@ extern "C" int32_t fgh_dataset_commit(fgh_dataset* ds) {
     desc.fields = fd;
     desc.alive_bitset = any_dead ? alive.data() : nullptr;
     fg_index* nx = nullptr;
-    int32_t rc = fg_index_upload(ds->ctx, &desc, &nx);
+    DEV_OR_FAIL();
+    int32_t rc = D(dev_api().fg_index_upload(ds->ctx, &desc, &nx));
     if (rc) return rc;
-    ds->index.reset(nx, fg_index_release);
+    ds->index.reset(nx, dev_api().fg_index_release);
     ds->committed_docs = ds->n_docs;
     for (int f = 0; f < 3; f++) ds->committed_terms[f] = fd[f].n_terms;
     ds->dirty = false;
@@ -559,9 +666,10 @@ extern "C" int32_t fgh_dataset_adopt(fgh_dataset* ds, const fg_index_desc* desc,
     std::unique_lock<std::shared_mutex> g(ds->mu);
     if (ds->ctx) {
         fg_index* nx = nullptr;
-        int32_t rc = fg_index_upload(ds->ctx, desc, &nx);
+        DEV_OR_FAIL();
+        int32_t rc = D(dev_api().fg_index_upload(ds->ctx, desc, &nx));
         if (rc) return rc;
-        ds->index.reset(nx, fg_index_release);
+        ds->index.reset(nx, dev_api().fg_index_release);
     }
     for (uint32_t f = 0; f < desc->n_fields; f++) {
         ds->f[f] = FieldBuild();
@@ -955,7 +1063,7 @@ void plan_batch(const fgh_dataset* ds, uint32_t n, const char* const* queries, c
             if (f1 == f0 && plan_fast(ds, queries[i], page, pp, P.c, P.l, pb.q[i], pb.offset[i])) continue;
             pb.rc[i] = plan_impl(ds, queries[i], filters ? filters + f0 : nullptr, f1 - f0, page, pp, &plan);
             const bool bad = pb.rc[i] != FG_OK;
-            if (bad) P.errs[i - P.a] = fg_last_error();
+            if (bad) P.errs[i - P.a] = g_herr;
             pb.q[i].k = bad ? 1 : plan.k;
             pb.q[i].clause_begin = (uint32_t)P.c.size();
             pb.q[i].n_clauses = bad ? 0 : plan.n_clauses;
@@ -1033,7 +1141,7 @@ extern "C" int32_t fgh_search_batch(fgh_dataset* ds, uint32_t n, const char* con
     std::vector<Chunk> ch(nch);
     struct Cleanup {
         std::vector<Chunk>& c;
-        ~Cleanup() { for (auto& x : c) if (x.batch) fg_batch_release(x.batch); }
+        ~Cleanup() { for (auto& x : c) if (x.batch) dev_api().fg_batch_release(x.batch); }
     } cleanup{ch};
     const bool timing = getenv("FG_TIMING") != nullptr;
     auto now_ms = []() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
@@ -1070,12 +1178,12 @@ extern "C" int32_t fgh_search_batch(fgh_dataset* ds, uint32_t n, const char* con
         // which prune; match counts need every matching document visited, which is what the windowed accumulator
         // kernels do best (FG_PREP_LEGACY). A query the device path cannot take fails alone, not its siblings.
         int32_t r = FG_ERR_UNSUPPORTED;
-        if (out_match_count) r = fg_batch_prepare_ex(snap.get(), &qb, FG_PREP_LEGACY, &C.batch);
-        if (r) r = fg_batch_prepare_ex(snap.get(), &qb, FG_PREP_PER_QUERY_STATUS, &C.batch);
+        if (out_match_count) r = D(dev_api().fg_batch_prepare_ex(snap.get(), &qb, FG_PREP_LEGACY, &C.batch));
+        if (r) r = D(dev_api().fg_batch_prepare_ex(snap.get(), &qb, FG_PREP_PER_QUERY_STATUS, &C.batch));
         if (r) return r;
         {
             std::vector<int32_t> qs(m);
-            fg_batch_query_status(C.batch, qs.data());
+            D(dev_api().fg_batch_query_status(C.batch, qs.data()));
             for (uint32_t j = 0; j < m; j++)
                 if (qs[j] != FG_OK && C.pb.rc[j] == FG_OK) {
                     C.pb.rc[j] = qs[j];
@@ -1085,7 +1193,7 @@ extern "C" int32_t fgh_search_batch(fgh_dataset* ds, uint32_t n, const char* con
         }
         const double t2 = now_ms();
         // match counts are optional: the reference's TopDocs collector does not count (src/db/search.rs:162)
-        r = fg_batch_submit(C.batch, 0, C.pb.kmax, out_match_count ? 1 : 0);
+        r = D(dev_api().fg_batch_submit(C.batch, 0, C.pb.kmax, out_match_count ? 1 : 0));
         if (r) return r;
         t_plan += t1 - t0; t_prep += t2 - t1; t_sub += now_ms() - t2;
     }
@@ -1098,7 +1206,7 @@ extern "C" int32_t fgh_search_batch(fgh_dataset* ds, uint32_t n, const char* con
         hits.resize((size_t)m * kmax);
         nh.resize(m);
         cnt.resize(m);
-        int32_t r = fg_batch_collect(C.batch, hits.data(), nh.data(), out_match_count ? cnt.data() : nullptr);
+        int32_t r = D(dev_api().fg_batch_collect(C.batch, hits.data(), nh.data(), out_match_count ? cnt.data() : nullptr));
         if (r) return r;
         for (uint32_t j = 0; j < m; j++) {
             const uint32_t qi = C.a + j;
@@ -1122,6 +1230,141 @@ extern "C" int32_t fgh_search(fgh_dataset* ds, const char* query, const char* co
     const uint32_t offs[2] = {0, n_filters};
     return fgh_search_batch(ds, 1, &query, filters, offs, &page, &per_page, per_page, out_hits, out_n,
                             out_match_count, nullptr);
+}
+
+// ------------------------------------------------------------------------------------------
+// micro-batcher
+// ------------------------------------------------------------------------------------------
+// The HTTP API answers one query per request (search_endpoint, /root/reference/src/server/handlers/search.rs:152;
+// query_json_post :210), each on its own tokio worker thread inside Dataset::search; the device wants thousands
+// of queries per launch. fgh_batcher_search is what such a thread calls instead of fgh_search: the request is
+// queued, a dispatcher thread gathers what has arrived -- everything that queued up while the previous batch was
+// on the device, or, when the device is idle, whatever arrives within `max_wait_us` of the first request, up to
+// `max_batch` -- and answers it with ONE fgh_search_batch; every caller wakes up with its own page. A request the
+// device path cannot take fails alone with its own status (the caller keeps tantivy for it).
+struct fgh_batcher {
+    struct Req {
+        const char* query;
+        const char* const* filters;
+        uint32_t n_filters, page, per_page;
+        fg_hit* out_hits;
+        uint32_t* out_n;
+        int32_t rc = FG_OK;
+        std::string err;
+        bool done = false;
+        std::chrono::steady_clock::time_point t_in;
+    };
+    fgh_dataset* ds = nullptr;
+    uint32_t max_batch = 4096, max_wait_us = 200;
+    std::mutex mu;
+    std::condition_variable cv_in, cv_out;
+    std::deque<Req*> queue;
+    bool stop = false;
+    std::thread worker;
+    fgh_batcher_stats st{};
+
+    void run() {
+        std::vector<Req*> reqs;
+        std::vector<const char*> qs, fl;
+        std::vector<uint32_t> foff, pages, pps, nh;
+        std::vector<int32_t> status;
+        std::vector<fg_hit> hits;
+        std::unique_lock<std::mutex> g(mu);
+        while (true) {
+            cv_in.wait(g, [&] { return stop || !queue.empty(); });
+            if (queue.empty()) return;  // stop requested and nothing pending
+            // device idle: give concurrent callers a short window to join the first request's batch
+            const auto deadline = queue.front()->t_in + std::chrono::microseconds(max_wait_us);
+            while (!stop && queue.size() < max_batch && std::chrono::steady_clock::now() < deadline) cv_in.wait_until(g, deadline);
+            reqs.clear();
+            while (!queue.empty() && reqs.size() < max_batch) { reqs.push_back(queue.front()); queue.pop_front(); }
+            g.unlock();
+            const uint32_t n = (uint32_t)reqs.size();
+            qs.resize(n); pages.resize(n); pps.resize(n); nh.assign(n, 0); status.assign(n, FG_OK);
+            fl.clear(); foff.assign(n + 1, 0);
+            uint32_t stride = 1;
+            for (uint32_t i = 0; i < n; i++) {
+                const Req& r = *reqs[i];
+                qs[i] = r.query;
+                pages[i] = r.page;
+                pps[i] = r.per_page;
+                stride = std::max(stride, r.per_page);
+                for (uint32_t f = 0; f < r.n_filters; f++) fl.push_back(r.filters[f]);
+                foff[i + 1] = (uint32_t)fl.size();
+            }
+            hits.resize((size_t)n * stride);
+            const int32_t rc = fgh_search_batch(ds, n, qs.data(), fl.empty() ? nullptr : fl.data(), foff.data(), pages.data(), pps.data(), stride,
+                                                hits.data(), nh.data(), nullptr, status.data());
+            const std::string batch_err = rc ? g_herr : "";
+            const auto t_done = std::chrono::steady_clock::now();
+            g.lock();
+            st.n_batches++;
+            st.n_requests += n;
+            st.max_batch_seen = std::max<uint64_t>(st.max_batch_seen, n);
+            for (uint32_t i = 0; i < n; i++) {
+                Req& r = *reqs[i];
+                st.wait_us_total += (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(t_done - r.t_in).count();
+                if (rc) { r.rc = rc; r.err = batch_err; }
+                else if (status[i]) { r.rc = status[i]; r.err = "query not evaluated on the device path (status " + std::to_string(status[i]) + ")"; }
+                else {
+                    memcpy(r.out_hits, hits.data() + (size_t)i * stride, (size_t)nh[i] * sizeof(fg_hit));
+                    *r.out_n = nh[i];
+                }
+                r.done = true;
+            }
+            cv_out.notify_all();
+        }
+    }
+};
+
+extern "C" int32_t fgh_batcher_create(fgh_dataset* ds, uint32_t max_batch, uint32_t max_wait_us, fgh_batcher** out) {
+    if (!ds || !out) return host_fail(FG_ERR_INVALID, "fgh_batcher_create: NULL argument");
+    fgh_batcher* b = new fgh_batcher();
+    b->ds = ds;
+    b->max_batch = max_batch ? max_batch : 4096;
+    b->max_wait_us = max_wait_us;
+    b->worker = std::thread([b] { b->run(); });
+    *out = b;
+    return FG_OK;
+}
+extern "C" void fgh_batcher_destroy(fgh_batcher* b) {
+    if (!b) return;
+    {
+        std::lock_guard<std::mutex> g(b->mu);
+        b->stop = true;  // requests already queued are still answered
+    }
+    b->cv_in.notify_all();
+    if (b->worker.joinable()) b->worker.join();
+    delete b;
+}
+extern "C" int32_t fgh_batcher_search(fgh_batcher* b, const char* query, const char* const* filters, uint32_t n_filters,
+                                      uint32_t page, uint32_t per_page, fg_hit* out_hits, uint32_t* out_n) {
+    if (!b || !out_hits || !out_n) return host_fail(FG_ERR_INVALID, "fgh_batcher_search: NULL argument");
+    if (per_page == 0) return host_fail(FG_ERR_INVALID, "per_page == 0: TopDocs::with_limit panics on a zero limit");
+    fgh_batcher::Req r;
+    r.query = query ? query : "";
+    r.filters = filters;
+    r.n_filters = filters ? n_filters : 0;
+    r.page = page;
+    r.per_page = per_page;
+    r.out_hits = out_hits;
+    r.out_n = out_n;
+    *out_n = 0;
+    r.t_in = std::chrono::steady_clock::now();
+    std::unique_lock<std::mutex> g(b->mu);
+    if (b->stop) return host_fail(FG_ERR_INVALID, "fgh_batcher_search: the batcher is shutting down");
+    b->queue.push_back(&r);
+    b->cv_in.notify_one();
+    b->cv_out.wait(g, [&] { return r.done; });
+    g.unlock();
+    if (r.rc) return host_fail(r.rc, "%s", r.err.c_str());
+    return FG_OK;
+}
+extern "C" int32_t fgh_batcher_get_stats(fgh_batcher* b, fgh_batcher_stats* out) {
+    if (!b || !out) return host_fail(FG_ERR_INVALID, "fgh_batcher_get_stats: NULL argument");
+    std::lock_guard<std::mutex> g(b->mu);
+    *out = b->st;
+    return FG_OK;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1219,7 +1462,7 @@ extern "C" int32_t fgh_facet_counts(fgh_dataset* ds, const char* root, uint32_t 
         // assigned in insertion order): they count 0 docs, like an uncommitted document in the reference
         std::vector<FacetEnt> kept;
         for (auto& e : ents)
-            if (fg_index_term_info(snap.get(), FGH_FIELD_FACET, e.ord, nullptr, nullptr, nullptr, nullptr) == FG_OK) kept.push_back(e);
+            if (dev_api().fg_index_term_info(snap.get(), FGH_FIELD_FACET, e.ord, nullptr, nullptr, nullptr, nullptr) == FG_OK) kept.push_back(e);
         ents.swap(kept);
     }
     // one single-leaf query per facet: its match count is the number of ALIVE docs that carry the
@@ -1243,7 +1486,7 @@ extern "C" int32_t fgh_facet_counts(fgh_dataset* ds, const char* root, uint32_t 
         qb.leaves = l.data();
         std::vector<fg_hit> hits(n);
         std::vector<uint32_t> nh(n), cnt(n);
-        if (int32_t rc = fg_search_batch(snap.get(), &qb, 1, hits.data(), nh.data(), cnt.data())) return rc;
+        if (int32_t rc = D(dev_api().fg_search_batch(snap.get(), &qb, 1, hits.data(), nh.data(), cnt.data()))) return rc;
         for (uint32_t i = 0; i < n; i++) counts[i] = cnt[i];
     }
     return facet_emit(ents, &counts, out, cap, path_buf, path_cap, n_out, path_bytes_out);

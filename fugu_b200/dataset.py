@@ -49,17 +49,18 @@ class Plan(C.Structure):
 
 
 HOST_SYMBOLS = [
-    "fgh_dataset_create", "fgh_dataset_destroy", "fgh_dataset_upsert", "fgh_dataset_delete", "fgh_dataset_commit",
+    "fgh_last_error", "fgh_dataset_create", "fgh_dataset_destroy", "fgh_dataset_upsert", "fgh_dataset_delete", "fgh_dataset_commit",
     "fgh_dataset_adopt", "fgh_dataset_num_docs", "fgh_dataset_index", "fgh_dataset_doc_id", "fgh_dataset_term_ord",
     "fgh_tokenize", "fgh_plan", "fgh_plan_batch", "fgh_search", "fgh_search_batch",
     "fgh_facet_children", "fgh_facet_counts",
+    "fgh_batcher_create", "fgh_batcher_destroy", "fgh_batcher_search", "fgh_batcher_get_stats",
 ]
 _bound = False
 
 
 def _L():
     global _bound
-    L = nat.lib()
+    L = nat.host_lib()
     if not _bound:
         vp, u32, i32 = C.c_void_p, C.c_uint32, C.c_int32
         cpp = C.POINTER(C.c_char_p)
@@ -84,6 +85,11 @@ def _L():
         L.fgh_search_batch.argtypes = [vp, u32, cpp, cpp, vp, vp, vp, u32, vp, vp, vp, vp]
         for fn in (L.fgh_facet_children, L.fgh_facet_counts):
             fn.argtypes = [vp, C.c_char_p, u32, vp, u32, vp, u32, C.POINTER(u32), C.POINTER(u32)]
+        L.fgh_batcher_create.argtypes = [vp, u32, u32, C.POINTER(vp)]
+        L.fgh_batcher_destroy.argtypes = [vp]
+        L.fgh_batcher_destroy.restype = None
+        L.fgh_batcher_search.argtypes = [vp, C.c_char_p, cpp, u32, u32, u32, vp, C.POINTER(u32)]
+        L.fgh_batcher_get_stats.argtypes = [vp, vp]
         _bound = True
     return L
 
@@ -305,7 +311,7 @@ class Dataset:
     def __init__(self, ctx: nat.Context | None):
         self.ctx = ctx
         self.h = C.c_void_p()
-        nat.check(_L().fgh_dataset_create(ctx.h if ctx is not None else None, C.byref(self.h)))
+        nat.hcheck(_L().fgh_dataset_create(ctx.h if ctx is not None else None, C.byref(self.h)))
         self._keep = None
         # hit hydration (convert_doc_to_search_result, src/db/search.rs:534-590): id -> the stored fields of the
         # record, in host memory (row f1: a side table instead of a doc-store block decompress per hit)
@@ -319,19 +325,19 @@ class Dataset:
             facets = [f.encode() for f in all_facet_paths(r)]
             arr = (C.c_char_p * max(len(facets), 1))(*facets)
             nm = r.name()
-            nat.check(L.fgh_dataset_upsert(self.h, r.id.encode(), r.text.encode(), None if nm is None else nm.encode(),
+            nat.hcheck(L.fgh_dataset_upsert(self.h, r.id.encode(), r.text.encode(), None if nm is None else nm.encode(),
                                            arr, len(facets)))
         if commit:
             self.commit()
 
     def delete(self, id_: str, commit: bool = True) -> None:
         self._records.pop(id_, None)
-        nat.check(_L().fgh_dataset_delete(self.h, id_.encode()))
+        nat.hcheck(_L().fgh_dataset_delete(self.h, id_.encode()))
         if commit:
             self.commit()
 
     def commit(self) -> None:
-        nat.check(_L().fgh_dataset_commit(self.h))
+        nat.hcheck(_L().fgh_dataset_commit(self.h))
 
     def adopt(self, desc: nat.HostIndexDesc, terms: list[list[str] | None]) -> None:
         """Adopt a pre-built CSR (synthetic corpora) + per-field term dictionaries."""
@@ -342,7 +348,7 @@ class Dataset:
         for i, bf in enumerate(bufs):
             arr[i] = None if bf is None else C.cast(bf, C.c_char_p)
         sizes = (C.c_uint64 * n)(*[0 if b is None else len(b) for b in blobs])
-        nat.check(_L().fgh_dataset_adopt(self.h, C.byref(desc.desc), arr, sizes))
+        nat.hcheck(_L().fgh_dataset_adopt(self.h, C.byref(desc.desc), arr, sizes))
         self._keep = (desc, bufs)
 
     # ---- introspection ------------------------------------------------------------------
@@ -362,7 +368,7 @@ class Dataset:
         filters = filters or []
         arr = (C.c_char_p * max(len(filters), 1))(*[f.encode() for f in filters])
         p = Plan()
-        nat.check(_L().fgh_plan(self.h, query.encode(), arr, len(filters), page, per_page, C.byref(p)))
+        nat.hcheck(_L().fgh_plan(self.h, query.encode(), arr, len(filters), page, per_page, C.byref(p)))
         return p
 
     def plan_batch(self, queries, filters: list[list[str]] | None = None, page: int = 0, per_page: int = 20):
@@ -374,7 +380,7 @@ class Dataset:
         l = np.zeros(max(n * MAX_PLAN_LEAVES, 1), nat.LEAF_DT)
         nc, nl = C.c_uint32(), C.c_uint32()
         status = np.zeros(n, np.int32)
-        nat.check(_L().fgh_plan_batch(self.h, n, qs.qarr, qs.farr, None if qs.foffs is None else qs.foffs.ctypes.data,
+        nat.hcheck(_L().fgh_plan_batch(self.h, n, qs.qarr, qs.farr, None if qs.foffs is None else qs.foffs.ctypes.data,
                                       qs.pages.ctypes.data, qs.pps.ctypes.data, q.ctypes.data, c.ctypes.data, len(c),
                                       l.ctypes.data, len(l), C.byref(nc), C.byref(nl), status.ctypes.data))
         return nat.HostBatch.from_arrays(q, c[:nc.value].copy(), l[:nl.value].copy()), status
@@ -396,7 +402,7 @@ class Dataset:
         hits = np.zeros(max(per_page, 1), nat.HIT_DT)
         n = C.c_uint32()
         cnt = C.c_uint32()
-        nat.check(_L().fgh_search(self.h, query.encode(), arr, len(filters), page, per_page, hits.ctypes.data,
+        nat.hcheck(_L().fgh_search(self.h, query.encode(), arr, len(filters), page, per_page, hits.ctypes.data,
                                   C.byref(n), C.byref(cnt)))
         return [self._hydrate(self.doc_id(int(h["doc"])), float(h["score"]), int(h["doc"])) for h in hits[:n.value]]
 
@@ -419,7 +425,7 @@ class Dataset:
         nh = np.zeros(n, np.uint32)
         cnt = np.zeros(n, np.uint32) if want_counts else None
         status = np.zeros(n, np.int32)
-        nat.check(_L().fgh_search_batch(self.h, n, qs.qarr, qs.farr, None if qs.foffs is None else qs.foffs.ctypes.data,
+        nat.hcheck(_L().fgh_search_batch(self.h, n, qs.qarr, qs.farr, None if qs.foffs is None else qs.foffs.ctypes.data,
                                         qs.pages.ctypes.data, qs.pps.ctypes.data, per_page, hits.ctypes.data, nh.ctypes.data,
                                         None if cnt is None else cnt.ctypes.data, status.ctypes.data))
         return hits, nh, cnt, status
@@ -428,10 +434,10 @@ class Dataset:
     def _facets(self, fn, root: str, max_depth: int) -> list[tuple[str, int, int]]:
         n, nb = C.c_uint32(), C.c_uint32()
         r = root.encode()
-        nat.check(fn(self.h, r, max_depth, None, 0, None, 0, C.byref(n), C.byref(nb)))  # size query
+        nat.hcheck(fn(self.h, r, max_depth, None, 0, None, 0, C.byref(n), C.byref(nb)))  # size query
         ents = np.zeros(max(n.value, 1), FACET_ENTRY_DT)
         buf = C.create_string_buffer(max(nb.value, 1))
-        nat.check(fn(self.h, r, max_depth, ents.ctypes.data, len(ents), buf, len(buf), C.byref(n), C.byref(nb)))
+        nat.hcheck(fn(self.h, r, max_depth, ents.ctypes.data, len(ents), buf, len(buf), C.byref(n), C.byref(nb)))
         raw = buf.raw
         return [(raw[int(e["path_off"]):int(e["path_off"]) + int(e["path_len"])].decode(), int(e["count"]), int(e["depth"]))
                 for e in ents[:n.value]]
@@ -494,6 +500,39 @@ class Dataset:
     def close(self) -> None:
         if self.h:
             _L().fgh_dataset_destroy(self.h)
+            self.h = C.c_void_p()
+
+
+class Batcher:
+    """Micro-batcher for single-query traffic (include/fugu_host.h fgh_batcher_*): `search`
+    has Dataset.search's contract and may be called from any number of threads (one per in-flight HTTP request,
+    src/server/handlers/search.rs:152); concurrent calls are answered together by one batched device call."""
+
+    def __init__(self, ds: Dataset, max_batch: int = 4096, max_wait_us: int = 200):
+        self.ds = ds
+        self.h = C.c_void_p()
+        nat.hcheck(_L().fgh_batcher_create(ds.h, max_batch, max_wait_us, C.byref(self.h)))
+
+    def search_raw(self, query: str, filters: list[str] | None = None, page: int = 0, per_page: int = 20) -> np.ndarray:
+        filters = filters or []
+        arr = (C.c_char_p * max(len(filters), 1))(*[f.encode() for f in filters])
+        hits = np.zeros(max(per_page, 1), nat.HIT_DT)
+        n = C.c_uint32()
+        nat.hcheck(_L().fgh_batcher_search(self.h, query.encode(), arr, len(filters), page, per_page, hits.ctypes.data, C.byref(n)))
+        return hits[:n.value]
+
+    def search(self, query: str, filters: list[str] | None = None, page: int = 0, per_page: int = 20) -> list[FuguSearchResult]:
+        return [self.ds._hydrate(self.ds.doc_id(int(h["doc"])), float(h["score"]), int(h["doc"]))
+                for h in self.search_raw(query, filters, page, per_page)]
+
+    def stats(self) -> dict:
+        st = np.zeros(4, np.uint64)
+        nat.hcheck(_L().fgh_batcher_get_stats(self.h, st.ctypes.data))
+        return {"n_requests": int(st[0]), "n_batches": int(st[1]), "max_batch_seen": int(st[2]), "wait_us_total": int(st[3])}
+
+    def close(self) -> None:
+        if self.h:
+            _L().fgh_batcher_destroy(self.h)
             self.h = C.c_void_p()
 
 

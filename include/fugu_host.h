@@ -18,7 +18,14 @@
  * Hit hydration (searcher.doc + convert_doc_to_search_result, src/db/search.rs:172-207,534-590) is
  * reduced to the doc -> id side table; stored fields stay with the caller.
  *
- * Same error convention as fugu_gpu.h (int32 status, fg_last_error()).
+ * Same error convention as fugu_gpu.h: int32 status, and fgh_last_error() returns the thread-local message of
+ * the last failing fgh_* call on this thread (a failure inside the device library is passed through).
+ *
+ * Two libraries: libfugu_host.so (this header; plain C++, no CUDA code, no link-time dependency on the device
+ * library) and libfugu_gpu.so (fugu_gpu.h). The host library binds the device entry points on first use, from
+ * libfugu_gpu.so in its own directory; a process that only plans, tokenises or builds documents (the reference
+ * arm of the bench, a GPU-less build of the Rust host) never maps any CUDA code. Calls that need the device
+ * fail with FG_ERR_NO_DEVICE when the device library or a CUDA device is missing: there is no CPU fallback.
  */
 #ifndef FUGU_HOST_H
 #define FUGU_HOST_H
@@ -35,6 +42,8 @@ extern "C" {
 #define FGH_FIELD_FACET 2u
 
 typedef struct fgh_dataset fgh_dataset;
+
+const char* fgh_last_error(void);
 
 /* ctx may be NULL: the dataset then only plans (fgh_plan / fgh_tokenize work, searches fail). */
 int32_t fgh_dataset_create(fg_ctx* ctx, fgh_dataset** out);
@@ -120,6 +129,28 @@ int32_t fgh_search_batch(fgh_dataset* ds, uint32_t n, const char* const* queries
                          const uint32_t* pages /* or NULL = 0 */, const uint32_t* per_pages /* or NULL = 20 */,
                          uint32_t per_page_stride, fg_hit* out_hits, uint32_t* out_n,
                          uint32_t* out_match_count, int32_t* status);
+
+/* ---- micro-batcher ----------------------------------------------------
+ * The reference's HTTP API is one query per request (search_endpoint, src/server/handlers/search.rs:152;
+ * query_json_post :210), each request blocking its own worker thread in Dataset::search (src/db/search.rs:74).
+ * fgh_batcher_search has fgh_search's contract (same page semantics, same errors, blocking, callable from any
+ * number of threads) but answers concurrent callers together: a dispatcher thread takes everything that queued
+ * up while the previous batch was on the device -- or, when idle, what arrives within max_wait_us of the first
+ * request, at most max_batch (0 = 4096) -- through ONE fgh_search_batch. A request the device path does not
+ * evaluate fails alone (its own FG_ERR_*), its siblings are answered. out_hits must hold per_page entries.
+ * fgh_batcher_destroy answers what is queued, then stops the dispatcher; no call may be made after it. */
+typedef struct fgh_batcher fgh_batcher;
+typedef struct {
+    uint64_t n_requests;     /* requests answered */
+    uint64_t n_batches;      /* fgh_search_batch calls they were answered with */
+    uint64_t max_batch_seen;
+    uint64_t wait_us_total;  /* sum over requests of (answered - queued) */
+} fgh_batcher_stats;
+int32_t fgh_batcher_create(fgh_dataset* ds, uint32_t max_batch, uint32_t max_wait_us, fgh_batcher** out);
+void fgh_batcher_destroy(fgh_batcher* b);
+int32_t fgh_batcher_search(fgh_batcher* b, const char* query, const char* const* filters, uint32_t n_filters,
+                           uint32_t page, uint32_t per_page, fg_hit* out_hits, uint32_t* out_n);
+int32_t fgh_batcher_get_stats(fgh_batcher* b, fgh_batcher_stats* out);
 
 /* ---- facet counting -------------------------------------------------
  * Mirrors `FacetCollector::for_field("facet")` + `add_facet(root)` run over `AllQuery`

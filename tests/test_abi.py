@@ -19,13 +19,45 @@ def _declared(header):
 
 
 def test_exports_every_declared_symbol():
-    L = nat.lib()
-    names = _declared("fugu_gpu.h") + _declared("fugu_host.h")
-    assert len(names) >= 30
-    for n in names:
-        assert hasattr(L, n), f"{n} declared in include/ but not exported by libfugu_gpu.so"
-    assert sorted(nat.ABI_SYMBOLS) == _declared("fugu_gpu.h")
-    assert sorted(dsm.HOST_SYMBOLS) == _declared("fugu_host.h")
+    L, H = nat.lib(), nat.host_lib()
+    dev_names, host_names = _declared("fugu_gpu.h"), _declared("fugu_host.h")
+    assert len(dev_names) + len(host_names) >= 30
+    for n in dev_names:
+        assert hasattr(L, n), f"{n} declared in include/fugu_gpu.h but not exported by libfugu_gpu.so"
+    for n in host_names:
+        assert hasattr(H, n), f"{n} declared in include/fugu_host.h but not exported by libfugu_host.so"
+    assert sorted(nat.ABI_SYMBOLS) == dev_names
+    assert sorted(dsm.HOST_SYMBOLS) == host_names
+
+
+def test_host_library_maps_no_cuda_code():
+    """libfugu_host.so (planner, tokenizer, dataset builder) neither contains nor links CUDA code, and exports
+    nothing of the device ABI: a process that only plans (the bench's reference arm, a GPU-less Rust build)
+    maps no CUDA library. Checked in a fresh interpreter: planning works and /proc/self/maps stays clean."""
+    import subprocess
+    import sys
+
+    host = os.path.join(ROOT, "fugu_b200", "libfugu_host.so")
+    needed = subprocess.run(["objdump", "-p", host], capture_output=True, text=True).stdout
+    assert "libcudart" not in needed and "libcuda" not in needed and "libfugu_gpu" not in needed and "libnccl" not in needed
+    syms = subprocess.run(["nm", "-D", "--defined-only", host], capture_output=True, text=True).stdout
+    exported = sorted(ln.split()[-1] for ln in syms.splitlines() if " T " in ln)
+    assert exported and all(n.startswith("fgh_") for n in exported), exported
+    dev = subprocess.run(["nm", "-D", "--defined-only", os.path.join(ROOT, "fugu_b200", "libfugu_gpu.so")], capture_output=True, text=True).stdout
+    assert " T fgh_" not in dev  # the device library carries no host-layer code
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "from fugu_b200 import dataset as dsm\n"
+        "ds = dsm.Dataset(None)\n"
+        "ds.upsert([dsm.ObjectRecord(id='a', text='hello world')], commit=False)\n"
+        "assert ds.plan('hello AND world').n_clauses == 2\n"
+        "assert dsm.tokenize('Hello, World') == ['hello', 'world']\n"
+        "maps = open('/proc/self/maps').read()\n"
+        "assert 'libfugu_host.so' in maps\n"
+        "assert 'libfugu_gpu' not in maps and 'libcudart' not in maps and 'libcuda.so' not in maps, 'CUDA code mapped'\n"
+        "print('clean')\n" % ROOT)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "clean" in r.stdout, r.stdout + r.stderr
 
 
 def test_abi_struct_sizes():

@@ -26,14 +26,14 @@ EMU_DIR = os.path.join(ROOT, "tests", "emu")
 @pytest.fixture(scope="module")
 def ctx():
     subprocess.check_call(["make", "-s", "-j4", "-C", EMU_DIR])
-    saved = (nat.LIB_PATH, nat._lib, dsm._bound, util.EMULATED)
-    nat.LIB_PATH, nat._lib, dsm._bound, util.EMULATED = os.path.join(EMU_DIR, "libfugu_emu.so"), None, False, True
+    saved = (nat.LIB_PATH, nat._lib, nat._host_lib, dsm._bound, util.EMULATED)
+    nat.LIB_PATH, nat._lib, nat._host_lib, dsm._bound, util.EMULATED = os.path.join(EMU_DIR, "libfugu_emu.so"), None, None, False, True
     c = nat.Context(0)
     try:
         yield c
     finally:
         c.close()
-        nat.LIB_PATH, nat._lib, dsm._bound, util.EMULATED = saved
+        nat.LIB_PATH, nat._lib, nat._host_lib, dsm._bound, util.EMULATED = saved
 
 
 def _gpu_tests():
@@ -65,7 +65,7 @@ FAST = {"test_config1_two_term_and", "test_golden_cases_through_dataset_search",
         "test_accounting_matches_oracle_definition",
         "test_concurrent_callers_share_one_index", "test_search_while_commits_land", "test_bulk_copy_staged_variant_equals_default",
         "test_search_endpoint_shape_defaults_and_hydration", "test_query_json_post_namespace_text_flags_and_clamp", "test_get_front_ends",
-        "test_object_record_validate_messages"}
+        "test_object_record_validate_messages", "test_micro_batcher_concurrent_single_query_requests"}
 
 
 @pytest.mark.parametrize("fn", _gpu_tests())

@@ -110,3 +110,48 @@ def test_object_record_validate_messages(ctx):
         with pytest.raises(ValueError) as e:
             rec.validate()
         assert str(e.value) == msg
+
+
+def test_micro_batcher_concurrent_single_query_requests(ctx):
+    """Row f2: many threads, one query each (the HTTP API's shape, handlers/search.rs:152), answered through the
+    micro-batcher: every caller gets exactly what a direct Dataset.search returns, requests are really batched,
+    a request the device path does not take fails alone."""
+    import threading
+
+    from fugu_b200.dataset import Batcher
+
+    state, main, other = _state(ctx)
+    queries = [("alpha", [], 0, 20), ("beta AND gamma1", [], 0, 5), ("report", ["namespace/acme"], 0, 10), ("filler7 OR filler9", [], 0, 20),
+               ("alpha", [], 1, 10), ("nosuchterm", [], 0, 20), ("alpha beta", ["/namespace/acme/organization/org1"], 0, 7)]
+    want = [[(r.id, r.score) for r in main.search(q, f, p, pp)] for q, f, p, pp in queries]
+    b = Batcher(main, max_batch=64, max_wait_us=20000)
+    n_threads, got, errs = 24, {}, {}
+    start = threading.Barrier(n_threads)
+
+    def worker(t):
+        q, f, p, pp = queries[t % len(queries)]
+        start.wait()
+        try:
+            got[t] = [(r.id, r.score) for r in b.search(q, f, p, pp)]
+            if t == 3:  # a phrase query is not evaluated on the device: this caller alone gets the error
+                try:
+                    b.search('"alpha beta"')
+                    errs[t] = "phrase query was answered"
+                except nat.FgError as e:
+                    if e.code != nat.FG_ERR_UNSUPPORTED:
+                        errs[t] = f"wrong code {e.code}"
+        except Exception as e:  # noqa: BLE001
+            errs[t] = repr(e)
+
+    th = [threading.Thread(target=worker, args=(t,)) for t in range(n_threads)]
+    for x in th:
+        x.start()
+    for x in th:
+        x.join()
+    st = b.stats()
+    b.close()
+    assert not errs, errs
+    for t in range(n_threads):
+        assert got[t] == want[t % len(queries)], (t, queries[t % len(queries)])
+    assert st["n_requests"] == n_threads + 1 and st["n_batches"] < st["n_requests"] and st["max_batch_seen"] >= 2, st
+    main.close(); other.close()
