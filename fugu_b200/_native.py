@@ -84,6 +84,7 @@ class IndexInfo(C.Structure):
         ("n_columns", C.c_uint32),
         ("n_bitmaps", C.c_uint32),
         ("bitmap_bytes", C.c_uint64),
+        ("appended_bytes_h2d", C.c_uint64),
     ]
 
 
@@ -127,7 +128,7 @@ HIT_DT = np.dtype([("score", "<f4"), ("doc", "<u4")])
 # every symbol include/fugu_gpu.h declares (tests check the .so exports all of them)
 ABI_SYMBOLS = [
     "fg_last_error", "fg_version", "fg_ctx_create", "fg_ctx_destroy", "fg_ctx_set_stream",
-    "fg_ctx_synchronize", "fg_index_upload", "fg_index_release", "fg_index_with_alive", "fg_index_get_info",
+    "fg_ctx_synchronize", "fg_index_upload", "fg_index_release", "fg_index_with_alive", "fg_index_append", "fg_index_get_info",
     "fg_index_term_info", "fg_search_batch", "fg_batch_prepare", "fg_batch_prepare_ex", "fg_batch_release",
     "fg_batch_execute", "fg_batch_submit", "fg_batch_collect", "fg_batch_get_stats", "fg_merge_topk_device", "fg_fieldnorm_to_id",
     "fg_comm_unique_id", "fg_comm_create", "fg_comm_destroy", "fg_comm_allreduce_sum_u64", "fg_comm_allreduce_sum_u32",
@@ -160,6 +161,7 @@ def lib() -> C.CDLL:
     L.fg_index_release.argtypes = [vp]
     L.fg_index_release.restype = None
     L.fg_index_with_alive.argtypes = [vp, vp, C.POINTER(vp)]
+    L.fg_index_append.argtypes = [vp, C.POINTER(IndexDesc), vp, C.POINTER(vp)]
     L.fg_index_get_info.argtypes = [vp, C.POINTER(IndexInfo)]
     L.fg_index_term_info.argtypes = [vp, u32, u32, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32), C.POINTER(u64)]
     L.fg_search_batch.argtypes = [vp, C.POINTER(QueryBatch), u32, vp, vp, vp]
@@ -336,6 +338,15 @@ class Index:
         bits = None if alive_bitset is None else np.ascontiguousarray(alive_bitset, dtype=np.uint32)
         assert bits is None or len(bits) == (self.n_docs + 31) // 32
         check(lib().fg_index_with_alive(self.h, _ptr(bits), C.byref(nx.h)))
+        return nx
+
+    def append(self, segment: HostIndexDesc, alive_bitset: np.ndarray | None = None) -> "Index":
+        """fg_index_append: this snapshot + one new segment (its docs get the ids after this snapshot's)."""
+        nx = Index.__new__(Index)
+        nx.ctx, nx.n_docs, nx.h = self.ctx, self.n_docs + segment.n_docs, C.c_void_p()
+        bits = None if alive_bitset is None else np.ascontiguousarray(alive_bitset, dtype=np.uint32)
+        assert bits is None or len(bits) == (nx.n_docs + 31) // 32
+        check(lib().fg_index_append(self.h, C.byref(segment.desc), _ptr(bits), C.byref(nx.h)))
         return nx
 
     def info(self) -> IndexInfo:

@@ -342,6 +342,63 @@ extern "C" void fg_index_release(fg_index* ix) {
     delete ix;  // drops this snapshot's share of the arena
 }
 
+// One f32 per block: the largest tf / (tf + norm(doc)) of its postings, computed on the device with the
+// scoring path's own arithmetic (so weight * bmax >= every score of the block, exactly). The host keeps
+// each term's maximum and its largest block maxima for the MaxScore bounds of the lowering.
+// Needs ix->dev.{skip, blk, fnorm, cache} and the term table; allocates ix->dev.bmax in the snapshot's arena.
+static int32_t compute_block_max(fg_index* ix, uint64_t n_blocks, int T) {
+    fg_ctx* ctx = ix->ctx;
+    const uint32_t n_fields = (uint32_t)ix->fields.size();
+    float* d_bmax = nullptr;
+    CU(cudaMalloc((void**)&d_bmax, std::max<size_t>(n_blocks * 4, 16)));
+    ix->arena->allocs.push_back(d_bmax);
+    ix->info.device_bytes += n_blocks * 4;
+    ix->dev.bmax = d_bmax;
+    for (uint32_t f = 0; f < n_fields; f++) {
+        const HostField& hf = ix->fields[f];
+        if (hf.terms.empty()) continue;
+        const uint32_t b0 = hf.terms.front().blk_begin, b1 = hf.terms.back().blk_begin + hf.terms.back().n_blocks;
+        launch_blockmax(ix->dev, b0, b1, (hf.flags & FG_FIELD_HAS_FIELDNORMS) ? (int)f : -1, hf.cnorm, d_bmax, ctx->stream);
+    }
+    CU(cudaGetLastError());
+    std::vector<float> bm(n_blocks);
+    CU(cudaMemcpyAsync(bm.data(), d_bmax, n_blocks * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    auto top = std::make_shared<std::vector<float>>();
+    // offsets first (serial), then the per-term selection in parallel
+    uint64_t top_total = 0;
+    for (uint32_t f = 0; f < n_fields; f++)
+        for (auto& ti : ix->fields[f].terms) {
+            ti.top_off = ti.top_n = 0;
+            if (ti.n_blocks >= TOP_MIN_BLOCKS) {
+                ti.top_off = (uint32_t)top_total;
+                ti.top_n = std::min<uint32_t>(ti.n_blocks, TOP_MAX);
+                top_total += ti.top_n;
+            }
+        }
+    if (top_total > 0xFFFFFFF0ull) return fail(FG_ERR_UNSUPPORTED, "block-max table too large");
+    top->resize(top_total);
+    for (uint32_t f = 0; f < n_fields; f++) {
+        HostField& hf = ix->fields[f];
+        parallel_for(hf.n_terms, T, [&](uint64_t a, uint64_t b, int) {
+            std::vector<float> tmp;
+            for (uint64_t t = a; t < b; t++) {
+                TermInfo& ti = hf.terms[t];
+                const float* v = bm.data() + ti.blk_begin;
+                float mx = 0.f;
+                for (uint32_t i = 0; i < ti.n_blocks; i++) mx = std::max(mx, v[i]);
+                ti.max_factor = mx;
+                if (!ti.top_n) continue;
+                tmp.assign(v, v + ti.n_blocks);
+                std::partial_sort(tmp.begin(), tmp.begin() + ti.top_n, tmp.end(), std::greater<float>());
+                std::copy(tmp.begin(), tmp.begin() + ti.top_n, top->begin() + ti.top_off);
+            }
+        });
+    }
+    ix->topbm = top;
+    return FG_OK;
+}
+
 extern "C" int32_t fg_index_upload(fg_ctx* ctx, const fg_index_desc* d, fg_index** out) {
     if (!ctx || !d || !out) return fail(FG_ERR_INVALID, "fg_index_upload: NULL argument");
     *out = nullptr;
@@ -524,57 +581,7 @@ extern "C" int32_t fg_index_upload(fg_ctx* ctx, const fg_index_desc* d, fg_index
     ix->dev.n_alive = d->alive_bitset ? count_alive(d->alive_bitset, d->n_docs) : d->n_docs;
 
     // ---- block-max metadata (tantivy stores the block-max fieldnorm/tf pair in its skip entries, A.7) ----
-    // One f32 per block: the largest tf / (tf + norm(doc)) of its postings, computed on the device with the
-    // scoring path's own arithmetic (so weight * bmax >= every score of the block, exactly). The host keeps
-    // each term's maximum and its largest block maxima for the MaxScore bounds of the lowering.
-    {
-        float* d_bmax = nullptr;
-        CU(cudaMalloc((void**)&d_bmax, std::max<size_t>(n_blocks * 4, 16)));
-        ix->arena->allocs.push_back(d_bmax);
-        ix->info.device_bytes += n_blocks * 4;
-        ix->dev.bmax = d_bmax;
-        ix->dev.n_docs = d->n_docs;
-        for (uint32_t f = 0; f < d->n_fields; f++) {
-            const HostField& hf = ix->fields[f];
-            if (hf.terms.empty()) continue;
-            const uint32_t b0 = hf.terms.front().blk_begin, b1 = hf.terms.back().blk_begin + hf.terms.back().n_blocks;
-            launch_blockmax(ix->dev, b0, b1, (hf.flags & FG_FIELD_HAS_FIELDNORMS) ? (int)f : -1, hf.cnorm, d_bmax, ctx->stream);
-        }
-        CU(cudaGetLastError());
-        std::vector<float> bm(n_blocks);
-        CU(cudaMemcpyAsync(bm.data(), d_bmax, n_blocks * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaStreamSynchronize(ctx->stream));
-        auto top = std::make_shared<std::vector<float>>();
-        // offsets first (serial), then the per-term selection in parallel
-        uint64_t top_total = 0;
-        for (uint32_t f = 0; f < d->n_fields; f++)
-            for (auto& ti : ix->fields[f].terms)
-                if (ti.n_blocks >= TOP_MIN_BLOCKS) {
-                    ti.top_off = (uint32_t)top_total;
-                    ti.top_n = std::min<uint32_t>(ti.n_blocks, TOP_MAX);
-                    top_total += ti.top_n;
-                }
-        if (top_total > 0xFFFFFFF0ull) return fail(FG_ERR_UNSUPPORTED, "block-max table too large");
-        top->resize(top_total);
-        for (uint32_t f = 0; f < d->n_fields; f++) {
-            HostField& hf = ix->fields[f];
-            parallel_for(hf.n_terms, T, [&](uint64_t a, uint64_t b, int) {
-                std::vector<float> tmp;
-                for (uint64_t t = a; t < b; t++) {
-                    TermInfo& ti = hf.terms[t];
-                    const float* v = bm.data() + ti.blk_begin;
-                    float mx = 0.f;
-                    for (uint32_t i = 0; i < ti.n_blocks; i++) mx = std::max(mx, v[i]);
-                    ti.max_factor = mx;
-                    if (!ti.top_n) continue;
-                    tmp.assign(v, v + ti.n_blocks);
-                    std::partial_sort(tmp.begin(), tmp.begin() + ti.top_n, tmp.end(), std::greater<float>());
-                    std::copy(tmp.begin(), tmp.begin() + ti.top_n, top->begin() + ti.top_off);
-                }
-            });
-        }
-        ix->topbm = top;
-    }
+    if ((rc = compute_block_max(ix.get(), n_blocks, T))) return rc;
 
     // ---- dense tf columns -----------------------------------------------------------------
     // A term that occurs in at least 1/FG_COL_DIV of the shard's docs additionally gets a dense
@@ -730,6 +737,377 @@ extern "C" int32_t fg_index_with_alive(fg_index* base, const uint32_t* alive_bit
         ix->dev.n_alive = count_alive(alive_bitset, base->n_docs);
         ix->info.device_bytes += bytes;
     }
+    *out = ix.release();
+    return FG_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// snapshot append: base snapshot + one new segment -> new snapshot
+// ------------------------------------------------------------------------------------------
+// The reference commits on every ingest call (src/db/document.rs:65,97); tantivy then adds one new segment and
+// leaves the old ones alone. The equivalent here: the new documents take the doc ids after the base's (a new
+// tantivy segment's doc-id base is the sum of the earlier max_docs too), so every posting list only grows at its
+// tail. Only the segment's own postings cross PCIe; everything else is rebuilt from what is already in HBM:
+//   * full blocks of the base keep their payload bytes and offsets (one device-to-device copy of the payload
+//     region); a term's partial last block is decoded on the device, merged with the term's new postings on the
+//     host and re-encoded together with them behind the old payload;
+//   * skip entries are laid out anew (terms stay contiguous) by a range-copy kernel + the new blocks' entries;
+//   * N and the average field length change, so norm caches, idf weights and the block-max metadata of EVERY
+//     block are recomputed (blockmax_kernel over the whole payload: HBM speed);
+//   * fieldnorm ids, dense tf columns and membership bitmaps are extended in place of being rebuilt: old part
+//     copied on the device, the new documents' part uploaded / built from the new blocks.
+// Which terms own a column or a bitmap is decided at full uploads only (a term crossing a threshold later is
+// served from its blocks until the next one; a column term whose new tf exceeds a byte loses its column).
+namespace {
+struct NewBlocks {  // new blocks of one touched term, encoded on the host
+    std::vector<SkipEntry> skips;
+    std::vector<uint32_t> words;  // payload, 4 * (bd + bt) words per block
+};
+void encode_postings(const uint32_t* docs, const uint32_t* tfs, uint32_t n, uint32_t first_base, NewBlocks& out) {
+    uint32_t prev_plus1 = first_base;
+    uint32_t gaps[BLOCK], tfm[BLOCK];
+    for (uint32_t i0 = 0; i0 < n; i0 += BLOCK) {
+        const uint32_t m = std::min<uint32_t>(BLOCK, n - i0);
+        uint32_t gor = 0, tor = 0, p = prev_plus1;
+        for (uint32_t i = 0; i < m; i++) {
+            gaps[i] = docs[i0 + i] - p;
+            p = docs[i0 + i] + 1;
+            tfm[i] = tfs ? tfs[i0 + i] - 1 : 0;
+            gor |= gaps[i];
+            tor |= tfm[i];
+        }
+        const uint32_t bd = bits_of(gor), bt = bits_of(tor);
+        SkipEntry e;
+        e.last_doc = docs[i0 + m - 1];
+        e.first_base = prev_plus1;
+        e.off16 = (uint32_t)(out.words.size() / 4);  // relative to the term's first new block; rebased by the caller
+        e.packed = pack_meta(bd, bt, m);
+        out.skips.push_back(e);
+        const size_t w0 = out.words.size();
+        out.words.resize(w0 + 4 * (size_t)(bd + bt), 0);
+        pack_stream(out.words.data() + w0, gaps, m, bd);
+        pack_stream(out.words.data() + w0 + 4 * bd, tfm, m, bt);
+        prev_plus1 = p;
+    }
+}
+}  // namespace
+
+extern "C" int32_t fg_index_append(fg_index* base, const fg_index_desc* seg, const uint32_t* alive_bitset, fg_index** out) {
+    if (!base || !seg || !out) return fail(FG_ERR_INVALID, "fg_index_append: NULL argument");
+    *out = nullptr;
+    if (seg->n_fields != base->fields.size() || !seg->fields) return fail(FG_ERR_INVALID, "fg_index_append: the segment must have the base's %zu fields", base->fields.size());
+    if (base->global_n_docs != base->n_docs || base->doc_base != 0 || seg->global_n_docs || seg->doc_id_base)
+        return fail(FG_ERR_UNSUPPORTED, "fg_index_append: sharded snapshots (global statistics) are rebuilt with fg_index_upload");
+    if ((uint64_t)base->n_docs + seg->n_docs > 0xFFFFFFF0ull) return fail(FG_ERR_UNSUPPORTED, "too many docs");
+    fg_ctx* ctx = base->ctx;
+    CU(cudaSetDevice(ctx->device));
+    std::call_once(g_fn_once, fn_init);
+    const int T = host_threads();
+    const uint32_t n_old = base->n_docs, n_seg = seg->n_docs, n_new = n_old + n_seg, n_fields = seg->n_fields;
+    for (uint32_t f = 0; f < n_fields; f++) {
+        const fg_field_desc& fd = seg->fields[f];
+        const HostField& bf = base->fields[f];
+        if (fd.flags != bf.flags) return fail(FG_ERR_INVALID, "field %u: flags differ from the base snapshot", f);
+        if (fd.n_terms < bf.n_terms) return fail(FG_ERR_INVALID, "field %u: the segment's dictionary must extend the base's (%u < %u terms)", f, fd.n_terms, bf.n_terms);
+        if (fd.n_terms && (!fd.term_offsets || (fd.term_offsets[fd.n_terms] && !fd.doc_ids))) return fail(FG_ERR_INVALID, "field %u: term_offsets/doc_ids NULL", f);
+        if ((fd.flags & FG_FIELD_HAS_FIELDNORMS) && !fd.fieldnorm_ids && n_seg) return fail(FG_ERR_INVALID, "field %u: HAS_FIELDNORMS but fieldnorm_ids NULL", f);
+    }
+    std::unique_ptr<fg_index, void (*)(fg_index*)> ix(new fg_index(), fg_index_release);
+    ix->ctx = ctx;
+    ix->arena = std::make_shared<DeviceArena>();
+    ix->arena->device = ctx->device;
+    ix->n_docs = n_new;
+    ix->doc_base = 0;
+    ix->global_n_docs = n_new;
+    ix->fields.resize(n_fields);
+    auto dev_alloc = [&](size_t bytes, void** dst) -> int32_t {
+        void* p = nullptr;
+        CU(cudaMalloc(&p, std::max<size_t>(bytes, 16)));
+        ix->arena->allocs.push_back(p);
+        ix->info.device_bytes += bytes;
+        *dst = p;
+        return FG_OK;
+    };
+    int32_t rc;
+
+    // ---- term table of the new snapshot; which blocks of the base are kept, which are decoded for the host ----
+    struct Touched { uint32_t f, t, old_last_block /* global, EMPTY32 = the term is new */, tail, list_idx; };
+    constexpr uint32_t EMPTY32 = 0xFFFFFFFFu;
+    std::vector<Touched> touched;
+    std::vector<uint32_t> decode_list;  // global block indices of the base handed to tail_decode_kernel
+    uint64_t n_blocks = 0, n_postings = 0;
+    for (uint32_t f = 0; f < n_fields; f++) {
+        const fg_field_desc& fd = seg->fields[f];
+        const HostField& bf = base->fields[f];
+        HostField& hf = ix->fields[f];
+        hf.flags = fd.flags;
+        hf.n_terms = fd.n_terms;
+        hf.total_tokens = bf.total_tokens + fd.total_num_tokens;
+        hf.terms.resize(fd.n_terms);
+        for (uint32_t t = 0; t < fd.n_terms; t++) {
+            if (fd.term_offsets[t + 1] < fd.term_offsets[t]) return fail(FG_ERR_INVALID, "field %u: term_offsets not monotone at %u", f, t);
+            const uint64_t add = fd.term_offsets[t + 1] - fd.term_offsets[t];
+            if (add > n_seg) return fail(FG_ERR_INVALID, "field %u term %u: df > n_docs of the segment", f, t);
+            TermInfo ti{};
+            const TermInfo* old = t < bf.n_terms ? &bf.terms[t] : nullptr;
+            const uint32_t old_df = old ? old->df_local : 0;
+            ti.df_local = ti.df_global = old_df + (uint32_t)add;
+            ti.n_blocks = (ti.df_local + BLOCK - 1) / BLOCK;
+            ti.blk_begin = (uint32_t)n_blocks;
+            ti.col = old ? old->col : -1;
+            ti.bm = old ? old->bm : -1;
+            ti.idf_w = fg_bm25_idf(ti.df_global, n_new) * (1.0f + K1);
+            if (n_blocks + ti.n_blocks > 0xFFFFFFF0ull) return fail(FG_ERR_UNSUPPORTED, "too many blocks");
+            n_blocks += ti.n_blocks;
+            n_postings += ti.df_local;
+            if (add) {
+                Touched x{f, t, EMPTY32, old_df % BLOCK, EMPTY32};
+                if (old && old->n_blocks) {
+                    x.old_last_block = old->blk_begin + old->n_blocks - 1;
+                    x.list_idx = (uint32_t)decode_list.size();
+                    decode_list.push_back(x.old_last_block);
+                }
+                touched.push_back(x);
+            }
+            hf.terms[t] = ti;
+        }
+    }
+
+    // ---- last blocks of the touched terms: (last_doc, first_base) and, for partial ones, their postings ----
+    std::vector<uint32_t> h_meta(2 * decode_list.size()), h_docs((size_t)BLOCK * decode_list.size()), h_tfs((size_t)BLOCK * decode_list.size());
+    if (!decode_list.empty()) {
+        uint32_t *d_list = nullptr, *d_meta = nullptr, *d_docs = nullptr, *d_tfs = nullptr;
+        const size_t nl = decode_list.size();
+        CU(cudaMalloc((void**)&d_list, nl * 4));
+        CU(cudaMalloc((void**)&d_meta, nl * 8));
+        CU(cudaMalloc((void**)&d_docs, nl * BLOCK * 4));
+        CU(cudaMalloc((void**)&d_tfs, nl * BLOCK * 4));
+        cudaMemcpyAsync(d_list, decode_list.data(), nl * 4, cudaMemcpyHostToDevice, ctx->stream);
+        launch_tail_decode(base->dev, d_list, (uint32_t)nl, d_meta, d_docs, d_tfs, ctx->stream);
+        cudaMemcpyAsync(h_meta.data(), d_meta, nl * 8, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaMemcpyAsync(h_docs.data(), d_docs, nl * BLOCK * 4, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaMemcpyAsync(h_tfs.data(), d_tfs, nl * BLOCK * 4, cudaMemcpyDeviceToHost, ctx->stream);
+        const cudaError_t e1 = cudaStreamSynchronize(ctx->stream);
+        cudaFree(d_list); cudaFree(d_meta); cudaFree(d_docs); cudaFree(d_tfs);
+        CU(e1);
+    }
+
+    // ---- encode the new blocks of every touched term (parallel): old partial tail + the segment's postings ----
+    std::vector<NewBlocks> enc(touched.size());
+    std::vector<int> bad(T, 0);
+    parallel_for(touched.size(), T, [&](uint64_t a, uint64_t b, int tix) {
+        std::vector<uint32_t> docs, tfs;
+        for (uint64_t i = a; i < b; i++) {
+            const Touched& x = touched[i];
+            const fg_field_desc& fd = seg->fields[x.f];
+            const bool freqs = (fd.flags & FG_FIELD_HAS_FREQS) && fd.term_freqs;
+            const uint64_t o = fd.term_offsets[x.t];
+            const uint32_t add = (uint32_t)(fd.term_offsets[x.t + 1] - o);
+            docs.clear(); tfs.clear();
+            uint32_t first_base = 0;
+            if (x.list_idx != EMPTY32) {
+                first_base = h_meta[2 * x.list_idx] + 1;  // behind the base's last posting ...
+                if (x.tail) {                              // ... unless its partial last block is re-encoded with the new ones
+                    first_base = h_meta[2 * x.list_idx + 1];
+                    docs.assign(h_docs.begin() + (size_t)x.list_idx * BLOCK, h_docs.begin() + (size_t)x.list_idx * BLOCK + x.tail);
+                    tfs.assign(h_tfs.begin() + (size_t)x.list_idx * BLOCK, h_tfs.begin() + (size_t)x.list_idx * BLOCK + x.tail);
+                }
+            }
+            uint32_t prev = EMPTY32;
+            for (uint32_t j = 0; j < add; j++) {
+                const uint32_t dl = fd.doc_ids[o + j], tf = freqs ? fd.term_freqs[o + j] : 1u;
+                if (dl >= n_seg || (prev != EMPTY32 && dl <= prev) || tf == 0) { bad[tix] = 1; break; }
+                prev = dl;
+                docs.push_back(n_old + dl);
+                tfs.push_back(tf);
+            }
+            if (bad[tix]) break;
+            encode_postings(docs.data(), freqs ? tfs.data() : nullptr, (uint32_t)docs.size(), first_base, enc[i]);
+        }
+    });
+    for (int t = 0; t < T; t++)
+        if (bad[t]) return fail(FG_ERR_INVALID, "segment postings must be strictly ascending, < n_docs of the segment, with tf >= 1");
+
+    // ---- layout: payload of the new blocks behind the base's, skip entries term by term ----
+    const uint64_t old_payload16 = base->info.packed_bytes / 16;
+    uint64_t off16 = old_payload16;
+    std::vector<uint32_t> new_words;
+    std::vector<SkipEntry> new_skips;          // compact: the new blocks of the touched terms, in term order
+    std::vector<uint3> old_ranges, new_ranges;  // {src_begin, dst_begin, count} for copy_ranges_kernel
+    {
+        size_t ti_touched = 0;
+        for (uint32_t f = 0; f < n_fields; f++) {
+            const HostField& bf = base->fields[f];
+            HostField& hf = ix->fields[f];
+            for (uint32_t t = 0; t < hf.n_terms; t++) {
+                TermInfo& ti = hf.terms[t];
+                const TermInfo* old = t < bf.n_terms ? &bf.terms[t] : nullptr;
+                const bool is_touched = ti_touched < touched.size() && touched[ti_touched].f == f && touched[ti_touched].t == t;
+                uint32_t kept = old ? old->n_blocks : 0;
+                if (is_touched && touched[ti_touched].tail) kept--;  // the partial last block is re-encoded
+                if (kept) old_ranges.push_back(make_uint3(old->blk_begin, ti.blk_begin, kept));
+                uint64_t bytes = old ? old->bytes : 0;
+                if (is_touched) {
+                    NewBlocks& nb = enc[ti_touched];
+                    if (kept + nb.skips.size() != ti.n_blocks) return fail(FG_ERR_CUDA, "fg_index_append: internal block count mismatch (field %u term %u)", f, t);
+                    new_ranges.push_back(make_uint3((uint32_t)new_skips.size(), ti.blk_begin + kept, (uint32_t)nb.skips.size()));
+                    for (SkipEntry e : nb.skips) {
+                        e.off16 += (uint32_t)off16;
+                        new_skips.push_back(e);
+                    }
+                    if (off16 + nb.words.size() / 4 > 0xFFFFFFFFull) return fail(FG_ERR_UNSUPPORTED, "packed payload exceeds 64 GiB");
+                    off16 += nb.words.size() / 4;
+                    new_words.insert(new_words.end(), nb.words.begin(), nb.words.end());
+                    bytes += nb.words.size() * 4 + nb.skips.size() * 16;  // (the replaced partial block's bytes stay counted: dead payload)
+                    ti_touched++;
+                }
+                ti.bytes = bytes;
+            }
+        }
+    }
+    const uint64_t payload = off16 * 16;
+
+    // ---- device arrays ----
+    uint8_t* d_blk = nullptr;
+    uint4* d_skip = nullptr;
+    if ((rc = dev_alloc(payload + 64, (void**)&d_blk))) return rc;
+    if ((rc = dev_alloc(n_blocks * sizeof(SkipEntry), (void**)&d_skip))) return rc;
+    CU(cudaMemcpyAsync(d_blk, base->dev.blk, old_payload16 * 16, cudaMemcpyDeviceToDevice, ctx->stream));
+    CU(cudaMemsetAsync(d_blk + payload, 0, 64, ctx->stream));
+    if (!new_words.empty()) CU(cudaMemcpyAsync(d_blk + old_payload16 * 16, new_words.data(), new_words.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    {
+        uint3 *d_r0 = nullptr, *d_r1 = nullptr;
+        uint4* d_ns = nullptr;
+        CU(cudaMalloc((void**)&d_r0, std::max<size_t>(old_ranges.size() * sizeof(uint3), 16)));
+        CU(cudaMalloc((void**)&d_r1, std::max<size_t>(new_ranges.size() * sizeof(uint3), 16)));
+        CU(cudaMalloc((void**)&d_ns, std::max<size_t>(new_skips.size() * sizeof(SkipEntry), 16)));
+        if (!old_ranges.empty()) cudaMemcpyAsync(d_r0, old_ranges.data(), old_ranges.size() * sizeof(uint3), cudaMemcpyHostToDevice, ctx->stream);
+        if (!new_ranges.empty()) cudaMemcpyAsync(d_r1, new_ranges.data(), new_ranges.size() * sizeof(uint3), cudaMemcpyHostToDevice, ctx->stream);
+        if (!new_skips.empty()) cudaMemcpyAsync(d_ns, new_skips.data(), new_skips.size() * sizeof(SkipEntry), cudaMemcpyHostToDevice, ctx->stream);
+        launch_copy_ranges(base->dev.skip, d_skip, d_r0, (uint32_t)old_ranges.size(), ctx->stream);
+        launch_copy_ranges(d_ns, d_skip, d_r1, (uint32_t)new_ranges.size(), ctx->stream);
+        const cudaError_t e1 = cudaStreamSynchronize(ctx->stream);
+        cudaFree(d_r0); cudaFree(d_r1); cudaFree(d_ns);
+        CU(e1);
+        CU(cudaGetLastError());
+    }
+    ix->dev.skip = d_skip;
+    ix->dev.blk = d_blk;
+
+    // norm caches from the new statistics
+    std::vector<float> cache((size_t)MAX_FIELDS * 256, 0.f);
+    for (uint32_t f = 0; f < n_fields; f++) {
+        const float avg = (float)ix->fields[f].total_tokens / (float)ix->global_n_docs;
+        for (int i = 0; i < 256; i++) cache[f * 256 + i] = K1 * (1.0f - B + B * (float)g_fn_table[i] / avg);
+        ix->fields[f].cnorm = cache[f * 256 + fg_fieldnorm_to_id(1)];
+    }
+    float* d_cache = nullptr;
+    if ((rc = dev_alloc(cache.size() * 4, (void**)&d_cache))) return rc;
+    CU(cudaMemcpyAsync(d_cache, cache.data(), cache.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    ix->dev.cache = d_cache;
+    // fieldnorm ids: the base's on the device, the segment's from the host
+    for (uint32_t f = 0; f < n_fields; f++) {
+        ix->dev.fnorm[f] = nullptr;
+        if (!(seg->fields[f].flags & FG_FIELD_HAS_FIELDNORMS)) continue;
+        const size_t padded = ((size_t)n_new + 15) / 16 * 16 + 16;
+        uint8_t* p = nullptr;
+        if ((rc = dev_alloc(padded, (void**)&p))) return rc;
+        CU(cudaMemsetAsync(p, 0, padded, ctx->stream));
+        if (n_old) CU(cudaMemcpyAsync(p, base->dev.fnorm[f], n_old, cudaMemcpyDeviceToDevice, ctx->stream));
+        if (n_seg) CU(cudaMemcpyAsync(p + n_old, seg->fields[f].fieldnorm_ids, n_seg, cudaMemcpyHostToDevice, ctx->stream));
+        ix->dev.fnorm[f] = p;
+    }
+    ix->dev.alive = nullptr;
+    ix->dev.n_docs = n_new;
+    ix->dev.doc_base = 0;
+    ix->dev.n_alive = n_new;
+    if (alive_bitset) {
+        const size_t bytes = ((size_t)n_new + 31) / 32 * 4, padded = (bytes + 16 + 15) & ~(size_t)15;
+        uint32_t* p = nullptr;
+        if ((rc = dev_alloc(padded, (void**)&p))) return rc;
+        CU(cudaMemsetAsync(p, 0, padded, ctx->stream));
+        CU(cudaMemcpyAsync(p, alive_bitset, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        ix->dev.alive = p;
+        ix->dev.n_alive = count_alive(alive_bitset, n_new);
+    }
+    CU(cudaStreamSynchronize(ctx->stream));  // (host staging vectors above may go out of use)
+
+    // block maxima of every block under the new norms, per-term maxima and top tables
+    if ((rc = compute_block_max(ix.get(), n_blocks, T))) return rc;
+
+    // ---- dense tf columns: the base's columns, extended by the segment's docs ----
+    if (base->n_cols) {
+        const uint64_t stride = (((uint64_t)n_new + 15) & ~(uint64_t)15) + 16;
+        uint8_t* d_cols = nullptr;
+        if ((rc = dev_alloc((size_t)base->n_cols * stride, (void**)&d_cols))) return rc;
+        CU(cudaMemsetAsync(d_cols, 0, (size_t)base->n_cols * stride, ctx->stream));
+        if (n_old) CU(cudaMemcpy2DAsync(d_cols, stride, base->d_cols, base->col_stride, n_old, base->n_cols, cudaMemcpyDeviceToDevice, ctx->stream));
+        std::vector<uint8_t> part((size_t)base->n_cols * std::max<uint32_t>(n_seg, 1), 0);
+        for (uint32_t f = 0; f < n_fields; f++) {
+            const fg_field_desc& fd = seg->fields[f];
+            const bool freqs = (fd.flags & FG_FIELD_HAS_FREQS) && fd.term_freqs;
+            for (uint32_t t = 0; t < base->fields[f].n_terms; t++) {
+                TermInfo& ti = ix->fields[f].terms[t];
+                if (ti.col < 0) continue;
+                const uint64_t o = fd.term_offsets[t], add = fd.term_offsets[t + 1] - o;
+                uint8_t* col = part.data() + (size_t)ti.col * n_seg;
+                for (uint64_t j = 0; j < add; j++) {
+                    const uint32_t tf = freqs ? fd.term_freqs[o + j] : 1u;
+                    if (tf > 255) { ti.col = -1; break; }  // a byte no longer holds every tf: the term is served from its blocks
+                    col[fd.doc_ids[o + j]] = (uint8_t)tf;
+                }
+            }
+        }
+        if (n_seg) CU(cudaMemcpy2DAsync(d_cols + n_old, stride, part.data(), n_seg, n_seg, base->n_cols, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        ix->d_cols = d_cols;
+        ix->col_stride = stride;
+        ix->n_cols = base->n_cols;
+    }
+    ix->info.n_columns = ix->n_cols;
+    ix->info.column_bytes = ix->n_cols * ix->col_stride;
+
+    // ---- membership bitmaps: old bits copied, the new blocks' docs set, rank directories rebuilt ----
+    if (base->n_bitmaps) {
+        const uint64_t stride_words = (((uint64_t)n_new + 255) / 256) * 8 + 8;
+        const size_t bits_bytes = (size_t)base->n_bitmaps * stride_words * 4, rank_bytes = (size_t)base->n_bitmaps * (stride_words / 8) * 4;
+        uint32_t *d_bits = nullptr, *d_rank = nullptr;
+        if ((rc = dev_alloc(bits_bytes, (void**)&d_bits))) return rc;
+        if ((rc = dev_alloc(rank_bytes, (void**)&d_rank))) return rc;
+        CU(cudaMemsetAsync(d_bits, 0, bits_bytes, ctx->stream));
+        const uint64_t old_used_words = std::min<uint64_t>(base->bm_stride_words, stride_words);
+        CU(cudaMemcpy2DAsync(d_bits, stride_words * 4, base->d_bits, base->bm_stride_words * 4, old_used_words * 4, base->n_bitmaps, cudaMemcpyDeviceToDevice, ctx->stream));
+        std::vector<uint2> sel;
+        for (size_t i = 0; i < touched.size(); i++) {
+            const TermInfo& ti = ix->fields[touched[i].f].terms[touched[i].t];
+            if (ti.bm < 0) continue;
+            const uint32_t nnew = (uint32_t)enc[i].skips.size();
+            for (uint32_t b = ti.n_blocks - nnew; b < ti.n_blocks; b++) sel.push_back(make_uint2(ti.blk_begin + b, (uint32_t)ti.bm));
+        }
+        uint2* d_sel = nullptr;
+        CU(cudaMalloc((void**)&d_sel, std::max<size_t>(sel.size() * sizeof(uint2), 16)));
+        if (!sel.empty()) cudaMemcpyAsync(d_sel, sel.data(), sel.size() * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream);
+        launch_bitmap_build(ix->dev, d_sel, (uint32_t)sel.size(), d_bits, stride_words, ctx->stream);
+        launch_bitmap_rank(d_bits, d_rank, base->n_bitmaps, stride_words, ctx->stream);
+        const cudaError_t e1 = cudaStreamSynchronize(ctx->stream);
+        cudaFree(d_sel);
+        CU(e1);
+        CU(cudaGetLastError());
+        ix->d_bits = d_bits;
+        ix->d_rank = d_rank;
+        ix->bm_stride_words = stride_words;
+        ix->n_bitmaps = base->n_bitmaps;
+        ix->info.bitmap_bytes = (uint64_t)ix->n_bitmaps * (stride_words * 4 + stride_words / 2);
+    }
+    ix->info.n_bitmaps = ix->n_bitmaps;
+    ix->info.n_postings = n_postings;
+    ix->info.n_blocks = n_blocks;
+    ix->info.packed_bytes = payload;
+    ix->info.skip_bytes = n_blocks * 16;
+    ix->info.n_docs = n_new;
+    ix->info.n_fields = n_fields;
+    ix->info.appended_bytes_h2d = new_words.size() * 4 + new_skips.size() * sizeof(SkipEntry) + (old_ranges.size() + new_ranges.size()) * sizeof(uint3) +
+                                  (uint64_t)n_seg * (ix->n_cols + 2) + decode_list.size() * 4;
     *out = ix.release();
     return FG_OK;
 }

@@ -51,6 +51,7 @@ struct DevApi {
     FGH_DEV_FN(fg_index_upload);
     FGH_DEV_FN(fg_index_release);
     FGH_DEV_FN(fg_index_with_alive);
+    FGH_DEV_FN(fg_index_append);
     FGH_DEV_FN(fg_index_term_info);
     FGH_DEV_FN(fg_search_batch);
     FGH_DEV_FN(fg_batch_prepare_ex);
@@ -86,6 +87,7 @@ const DevApi& dev_api() {
         FGH_DEV_BIND(fg_index_upload);
         FGH_DEV_BIND(fg_index_release);
         FGH_DEV_BIND(fg_index_with_alive);
+        FGH_DEV_BIND(fg_index_append);
         FGH_DEV_BIND(fg_index_term_info);
         FGH_DEV_BIND(fg_search_batch);
         FGH_DEV_BIND(fg_batch_prepare_ex);
@@ -463,6 +465,8 @@ struct fgh_dataset {
     // same way: it keeps the segments it was opened on).
     std::shared_ptr<fg_index> index;
     uint32_t committed_docs = 0;  // n_docs of the snapshot in `index`
+    uint32_t full_docs = 0;       // n_docs of the last snapshot built by a full upload (appends since: committed_docs - full_docs)
+    uint64_t n_appends = 0, n_full_uploads = 0;
     // dictionary entries the current snapshot knows, per field: ordinals are assigned in insertion order, so
     // a term first seen after the last commit has an ordinal >= this and is planned as MISSING (an
     // uncommitted document is invisible to the reference's searcher too). A dataset without a device
@@ -617,6 +621,57 @@ extern "C" int32_t fgh_dataset_commit(fgh_dataset* ds) {
     Csr c[3];
     fg_field_desc fd[3];
     memset(fd, 0, sizeof(fd));
+    // New documents since the last commit: hand over only them, as one new segment (fg_index_append: the postings
+    // already in HBM stay there). Like tantivy's merge policy, a full rebuild follows once the appended part has
+    // outgrown the part that was built whole (it re-decides which terms own tf columns / membership bitmaps).
+    if (ds->index && ds->committed_docs && ds->n_docs > ds->committed_docs && (uint64_t)ds->n_docs <= 2ull * ds->full_docs &&
+        !getenv("FG_NO_INCREMENTAL")) {
+        DEV_OR_FAIL();
+        const uint32_t d0 = ds->committed_docs, ns = ds->n_docs - d0;
+        for (int f = 0; f < 3; f++) {
+            FieldBuild& fb = ds->f[f];
+            c[f].off.resize(fb.postings.size() + 1);
+            uint64_t n = 0;
+            for (size_t t = 0; t < fb.postings.size(); t++) {
+                c[f].off[t] = n;
+                const auto& pl = fb.postings[t];
+                auto it = std::lower_bound(pl.begin(), pl.end(), std::make_pair(d0, 0u));
+                for (; it != pl.end(); ++it) {
+                    c[f].docs.push_back(it->first - d0);
+                    c[f].tfs.push_back(it->second);
+                    n++;
+                }
+            }
+            c[f].off[fb.postings.size()] = n;
+            uint64_t seg_tokens = 0;
+            for (uint32_t d = d0; d < ds->n_docs; d++) seg_tokens += fb.doc_len[d];
+            fd[f].n_terms = (uint32_t)fb.postings.size();
+            fd[f].total_num_tokens = seg_tokens;
+            fd[f].term_offsets = c[f].off.data();
+            fd[f].doc_ids = c[f].docs.data();
+            if (f != (int)FGH_FIELD_FACET) {
+                c[f].fn.resize(ns);
+                for (uint32_t d = 0; d < ns; d++) c[f].fn[d] = fieldnorm_id(fb.doc_len[d0 + d]);
+                fd[f].flags = FG_FIELD_HAS_FIELDNORMS | FG_FIELD_HAS_FREQS;
+                fd[f].fieldnorm_ids = c[f].fn.data();
+                fd[f].term_freqs = c[f].tfs.data();
+            }
+        }
+        fg_index_desc seg;
+        memset(&seg, 0, sizeof(seg));
+        seg.n_docs = ns;
+        seg.n_fields = 3;
+        seg.fields = fd;
+        fg_index* nx = nullptr;
+        int32_t rc = D(dev_api().fg_index_append(ds->index.get(), &seg, any_dead ? alive.data() : nullptr, &nx));
+        if (rc) return rc;
+        ds->index.reset(nx, dev_api().fg_index_release);
+        ds->committed_docs = ds->n_docs;
+        for (int f = 0; f < 3; f++) ds->committed_terms[f] = fd[f].n_terms;
+        ds->dirty = false;
+        ds->n_appends++;
+        return FG_OK;
+    }
     for (int f = 0; f < 3; f++) {
         FieldBuild& fb = ds->f[f];
         c[f].off.resize(fb.postings.size() + 1);
@@ -654,8 +709,18 @@ extern "C" int32_t fgh_dataset_commit(fgh_dataset* ds) {
     if (rc) return rc;
     ds->index.reset(nx, dev_api().fg_index_release);
     ds->committed_docs = ds->n_docs;
+    ds->full_docs = ds->n_docs;
+    ds->n_full_uploads++;
     for (int f = 0; f < 3; f++) ds->committed_terms[f] = fd[f].n_terms;
     ds->dirty = false;
+    return FG_OK;
+}
+
+extern "C" int32_t fgh_dataset_commit_counts(const fgh_dataset* ds, uint64_t* n_full_uploads, uint64_t* n_appends) {
+    if (!ds) return host_fail(FG_ERR_INVALID, "NULL dataset");
+    std::shared_lock<std::shared_mutex> g(ds->mu);
+    if (n_full_uploads) *n_full_uploads = ds->n_full_uploads;
+    if (n_appends) *n_appends = ds->n_appends;
     return FG_OK;
 }
 

@@ -268,4 +268,9 @@ void launch_blockmax(const DevIndex& ix, uint32_t b0, uint32_t b1, int fn_field,
 void launch_bitmap_build(const DevIndex& ix, const uint2* sel, uint32_t n_sel, uint32_t* bits, uint64_t stride_words, void* stream);
 void launch_bitmap_rank(const uint32_t* bits, uint32_t* rank, uint32_t n_slots, uint64_t stride_words, void* stream);
 
+// snapshot append (fg_index_append): decode the listed blocks for the host (out_meta[2i] = last_doc, [2i+1] = first_base;
+// out_docs / out_tfs 128 slots per block), and copy ranges {src_begin, dst_begin, count} of 16-byte skip entries
+void launch_tail_decode(const DevIndex& ix, const uint32_t* blocks, uint32_t n_list, uint32_t* out_meta, uint32_t* out_docs, uint32_t* out_tfs, void* stream);
+void launch_copy_ranges(const void* src, void* dst, const void* ranges, uint32_t n_ranges, void* stream);
+
 }  // namespace fg

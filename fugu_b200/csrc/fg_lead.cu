@@ -899,7 +899,51 @@ __global__ void __launch_bounds__(256) bitmap_rank_kernel(const uint32_t* __rest
     }
 }
 
+// ---- snapshot append (fg_index_append) ----
+// one warp per listed block: its skip entry's (last_doc, first_base) and its decoded postings (doc ids and tfs,
+// 128 slots each; slots >= n undefined) go to a staging buffer the host reads back
+__global__ void __launch_bounds__(256) tail_decode_kernel(const DevIndex ix, const uint32_t* __restrict__ blocks, uint32_t n_list,
+                                                          uint32_t* out_meta, uint32_t* out_docs, uint32_t* out_tfs) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t i = blockIdx.x * 8u + (threadIdx.x >> 5);
+    if (i >= n_list) return;
+    const uint4 e = __ldg(&ix.skip[__ldg(blocks + i)]);
+    const uint32_t bd = e.w & 63u, bt = (e.w >> 6) & 63u;
+    const uint32_t* wd = reinterpret_cast<const uint32_t*>(ix.blk + (size_t)e.z * 16u);
+    uint32_t g[4], t[4];
+    unpack4(wd, lane, bd, g);
+    unpack4(wd + 4 * bd, lane, bt, t);
+    g[1] += g[0]; g[2] += g[1]; g[3] += g[2];
+    const uint32_t off = warp_excl_scan(g[3], lane) + e.y + 4u * lane;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        out_docs[(size_t)i * BLOCK + 4u * lane + j] = off + g[j] + (uint32_t)j;
+        out_tfs[(size_t)i * BLOCK + 4u * lane + j] = t[j] + 1u;
+    }
+    if (lane == 0) {
+        out_meta[2 * i] = e.x;
+        out_meta[2 * i + 1] = e.y;
+    }
+}
+// one warp per range {src_begin, dst_begin, count}: dst[dst_begin + j] = src[src_begin + j] (16-byte entries)
+__global__ void __launch_bounds__(256) copy_ranges_kernel(const uint4* __restrict__ src, uint4* dst, const uint3* __restrict__ ranges, uint32_t n_ranges) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t i = blockIdx.x * 8u + (threadIdx.x >> 5);
+    if (i >= n_ranges) return;
+    const uint3 r = ranges[i];
+    for (uint32_t j = lane; j < r.z; j += 32u) dst[r.y + j] = __ldg(&src[r.x + j]);
+}
+
 }  // namespace
+
+void launch_tail_decode(const DevIndex& ix, const uint32_t* blocks, uint32_t n_list, uint32_t* out_meta, uint32_t* out_docs, uint32_t* out_tfs, void* stream) {
+    if (!n_list) return;
+    FG_LAUNCH(tail_decode_kernel, (n_list + 7) / 8, 256, 0, (cudaStream_t)stream, ix, blocks, n_list, out_meta, out_docs, out_tfs);
+}
+void launch_copy_ranges(const void* src, void* dst, const void* ranges, uint32_t n_ranges, void* stream) {
+    if (!n_ranges) return;
+    FG_LAUNCH(copy_ranges_kernel, (n_ranges + 7) / 8, 256, 0, (cudaStream_t)stream, (const uint4*)src, (uint4*)dst, (const uint3*)ranges, n_ranges);
+}
 
 void launch_bitmap_build(const DevIndex& ix, const uint2* sel, uint32_t n_sel, uint32_t* bits, uint64_t stride_words, void* stream) {
     if (!n_sel) return;

@@ -49,7 +49,7 @@ class Plan(C.Structure):
 
 
 HOST_SYMBOLS = [
-    "fgh_last_error", "fgh_dataset_create", "fgh_dataset_destroy", "fgh_dataset_upsert", "fgh_dataset_delete", "fgh_dataset_commit",
+    "fgh_last_error", "fgh_dataset_create", "fgh_dataset_destroy", "fgh_dataset_upsert", "fgh_dataset_delete", "fgh_dataset_commit", "fgh_dataset_commit_counts",
     "fgh_dataset_adopt", "fgh_dataset_num_docs", "fgh_dataset_index", "fgh_dataset_doc_id", "fgh_dataset_term_ord",
     "fgh_tokenize", "fgh_plan", "fgh_plan_batch", "fgh_search", "fgh_search_batch",
     "fgh_facet_children", "fgh_facet_counts",
@@ -70,6 +70,7 @@ def _L():
         L.fgh_dataset_upsert.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_char_p, cpp, u32]
         L.fgh_dataset_delete.argtypes = [vp, C.c_char_p]
         L.fgh_dataset_commit.argtypes = [vp]
+        L.fgh_dataset_commit_counts.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.fgh_dataset_adopt.argtypes = [vp, C.POINTER(nat.IndexDesc), cpp, C.POINTER(C.c_uint64)]
         L.fgh_dataset_num_docs.argtypes = [vp]
         L.fgh_dataset_num_docs.restype = u32
@@ -338,6 +339,12 @@ class Dataset:
 
     def commit(self) -> None:
         nat.hcheck(_L().fgh_dataset_commit(self.h))
+
+    def commit_counts(self) -> tuple[int, int]:
+        """(snapshots built by a full upload, snapshots built by appending a segment)"""
+        a, b = C.c_uint64(), C.c_uint64()
+        nat.hcheck(_L().fgh_dataset_commit_counts(self.h, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
 
     def adopt(self, desc: nat.HostIndexDesc, terms: list[list[str] | None]) -> None:
         """Adopt a pre-built CSR (synthetic corpora) + per-field term dictionaries."""

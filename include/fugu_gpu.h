@@ -95,6 +95,20 @@ void fg_index_release(fg_index* index);
  * counting deleted docs, as tantivy's do until a merge. `base` and the derived snapshot are released
  * independently, in any order; the shared arrays are freed with the last of them. */
 int32_t fg_index_with_alive(fg_index* base, const uint32_t* alive_bitset, fg_index** out);
+/* Snapshot refresh after a commit that added documents (DocumentOperations::upsert / add + commit,
+ * src/db/document.rs:23-67,97): `segment` describes ONLY the new documents, the way a new
+ * tantivy segment would (doc ids 0..segment->n_docs local to the segment; they become base.n_docs + id, as a new
+ * segment's doc-id base is the sum of the earlier max_docs). Its fields are the base's, in the same order with the
+ * same flags; its term ordinals extend the base's dictionary (ordinals < the base's n_terms mean the same terms, new
+ * terms follow); total_num_tokens counts the segment's tokens; global_doc_freq / global_n_docs / doc_id_base must be
+ * NULL / 0 (single-shard snapshots only). `alive_bitset` covers base.n_docs + segment->n_docs docs (NULL = all alive).
+ * Only the segment's postings, fieldnorm ids and column bytes cross PCIe: full blocks of the base keep their payload
+ * (copied device to device), each touched term's partial last block is re-encoded with its new postings, and norm
+ * caches, idf weights and the block-max metadata of every block are recomputed on the device for the new N and
+ * average field length, so the result scores exactly like a full fg_index_upload of the whole corpus. Terms keep the
+ * lookup structures (tf column / membership bitmap) they had; membership is re-decided by the next full upload.
+ * `base` is not modified and is released independently. */
+int32_t fg_index_append(fg_index* base, const fg_index_desc* segment, const uint32_t* alive_bitset, fg_index** out);
 
 typedef struct {
     uint64_t n_postings;
@@ -108,6 +122,7 @@ typedef struct {
     uint32_t n_columns;
     uint32_t n_bitmaps;     /* membership bitmaps (+ rank directories) of the mid-frequency terms */
     uint64_t bitmap_bytes;
+    uint64_t appended_bytes_h2d; /* fg_index_append: bytes that crossed PCIe to build this snapshot (0 after a full upload) */
 } fg_index_info;
 int32_t fg_index_get_info(const fg_index* index, fg_index_info* out);
 /* document frequency / layout of one term (host copy of the term table) */

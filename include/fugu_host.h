@@ -65,9 +65,13 @@ int32_t fgh_dataset_delete(fgh_dataset* ds, const char* id);
  * Publish the pending state as a new device snapshot (swaps the fg_index; searches already running
  * keep the snapshot they started on). Only deletes since the last commit: the new snapshot shares the
  * posting arrays of the old one and uploads just the alive bitset (fg_index_with_alive, SURVEY.md 8(f)
- * row f3). New documents: the CSR is rebuilt and uploaded whole (per-segment incremental upload is not
- * implemented). Nothing pending: no-op. */
+ * row f3). New documents: only they are handed over, as one new segment (fg_index_append: the postings already
+ * in HBM stay there, the derived structures are rebuilt on the device); once the appended part has outgrown the
+ * part that was uploaded whole, the next commit rebuilds the snapshot from scratch (tantivy merges segments on a
+ * similar schedule). Nothing pending: no-op. */
 int32_t fgh_dataset_commit(fgh_dataset* ds);
+/* how the snapshots of this dataset were built so far: full uploads / appended segments */
+int32_t fgh_dataset_commit_counts(const fgh_dataset* ds, uint64_t* n_full_uploads, uint64_t* n_appends);
 
 /* Alternative to upsert+commit for large pre-built corpora: adopt a flat CSR (uploaded as is) plus
  * the term dictionaries needed for planning. `terms[f]` = n_terms NUL-terminated strings packed

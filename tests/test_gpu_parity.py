@@ -605,3 +605,81 @@ def test_gated_column_scan_equals_exhaustive(ctx):
         _, _, o_c = orc.search(desc, batch, threads=4)
         assert np.array_equal(h_c, o_c)
         index.close()
+
+
+def test_index_append_equals_full_upload(ctx, monkeypatch):
+    """Row f3: a snapshot grown by fg_index_append (base + two segments, with deletes in the last one) answers exactly
+    like the oracle on the whole corpus -- every engine, lead exhaustive / pruned / block path / window kernels -- and
+    only the segments' bytes cross PCIe. Small column / bitmap thresholds so that the base owns both kinds of lookup
+    structures and their extension is exercised (terms keep the structure they had)."""
+    monkeypatch.setenv("FG_BITMAP_MIN_DF", "64")
+    cfg = synth.Config(cfg=2, n_docs=30_000, vocab=3_000, n_queries=240, k=10, name_pct=10)
+    corpus = synth.Corpus.for_config(cfg)
+    cuts = [0, 17_003, 24_130, cfg.n_docs]  # (not multiples of 128 / 256 / 32: partial blocks, chunks and bitset words)
+    whole = nat.HostIndexDesc(cfg.n_docs, synth.build_fields(corpus, 0, cfg.n_docs))
+    batch = plan_queries(synth.gen_queries(cfg), vocab=cfg.vocab, n_text_fields=2)
+    base = nat.Index(ctx, nat.HostIndexDesc(cuts[1], synth.build_fields(corpus, 0, cuts[1])))
+    assert base.info().n_columns > 0 and base.info().n_bitmaps > 0
+    seg1 = nat.HostIndexDesc(cuts[2] - cuts[1], synth.build_fields(corpus, cuts[1], cuts[2]))
+    mid = base.append(seg1)
+    # the intermediate snapshot is a complete index of the first two parts
+    part = nat.HostIndexDesc(cuts[2], synth.build_fields(corpus, 0, cuts[2]))
+    check_batch_against_oracle(mid, part, batch, legacy=False)
+    # second segment, with deletes (an upsert is delete + add, src/db/document.rs:38-48)
+    rng = np.random.default_rng(5)
+    alive = np.full((cfg.n_docs + 31) // 32, 0xFFFFFFFF, np.uint32)
+    for d in rng.choice(cfg.n_docs, 900, replace=False):
+        alive[d >> 5] &= ~np.uint32(1 << (d & 31))
+    seg2 = nat.HostIndexDesc(cuts[3] - cuts[2], synth.build_fields(corpus, cuts[2], cuts[3]))
+    full = mid.append(seg2, alive)
+    whole_alive = nat.HostIndexDesc(cfg.n_docs, synth.build_fields(corpus, 0, cfg.n_docs), alive_bitset=alive)
+    check_batch_against_oracle(full, whole_alive, batch)
+    i_full, i_ref = full.info(), nat.Index(ctx, whole).info()
+    assert i_full.n_postings == i_ref.n_postings and i_full.n_blocks == i_ref.n_blocks and i_full.n_docs == cfg.n_docs
+    # what crossed PCIe for the last segment (a fifth of the corpus: its blocks, re-encoded tail blocks, column bytes)
+    # against what a full upload reads from the host (8 B per posting of the flat CSR)
+    assert 0 < i_full.appended_bytes_h2d < 8 * i_ref.n_postings // 4
+    # the base is untouched and still answers for its own docs
+    check_batch_against_oracle(base, nat.HostIndexDesc(cuts[1], synth.build_fields(corpus, 0, cuts[1])), batch, legacy=False)
+    for ix in (base, mid, full):
+        ix.close()
+
+
+def test_dataset_commits_append_segments(ctx):
+    """fgh_dataset_commit hands new documents over as a segment (fg_index_append) instead of re-uploading the corpus;
+    results equal those of a dataset built in one go, and the python twin's; a rebuild follows once the appended part
+    outgrows the part uploaded whole."""
+    from fugu_b200.dataset import Dataset, ObjectRecord
+    from oracle import oracle_py as op
+
+    words = ["alpha", "beta", "gamma", "delta", "omega", "sigma", "kappa", "theta"]
+    def rec(i):
+        text = " ".join(words[(i * 7 + j * j) % len(words)] for j in range(3 + i % 5)) + f" uniq{i}"
+        return ObjectRecord(id=f"d{i}", text=text, metadata={"name": f"{words[i % 8]} report"}, namespace="ns%d" % (i % 3))
+    inc, one, ix = Dataset(ctx), Dataset(ctx), op.PyIndex()
+    n = 700
+    for a, b in [(0, 400), (400, 520), (520, 521), (521, 700)]:
+        inc.upsert([rec(i) for i in range(a, b)], commit=True)
+    inc.upsert([rec(3)], commit=False)      # an upsert of an existing id: delete + append
+    inc.delete("d10")
+    inc.commit()
+    one.upsert([rec(i) for i in range(n)] + [rec(3)], commit=False)
+    one.delete("d10")
+    one.commit()
+    for i in list(range(n)) + [3]:
+        r = rec(i)
+        ix.upsert(r.id, r.text, name=r.metadata["name"], facets=[f"/namespace/{r.namespace}"])
+    ix.delete("d10")
+    assert inc.commit_counts() == (1, 4) and one.commit_counts() == (1, 0)
+    for q, f in [("alpha", []), ("beta AND gamma", []), ("omega sigma report", []), ("uniq3", []), ("uniq10", []), ("kappa", ["namespace/ns1"]),
+                 ("theta -alpha", []), ("", ["namespace/ns2"])]:
+        a, b = inc.search(q, f, 0, 25), one.search(q, f, 0, 25)
+        assert [r.id for r in a] == [r.id for r in b], (q, f)
+        for x, y in zip(a, b):
+            assert abs(x.score - y.score) <= 1e-6 * max(abs(y.score), 1e-30), (q, x, y)
+        want, _ = op.search(ix, q, f, 0, 25)
+        assert [r.id for r in a] == [ix.ids[d] for d, _ in want], (q, f)
+    # doubling the corpus since the last full upload triggers a rebuild
+    inc.upsert([rec(i) for i in range(n, 2 * n + 200)], commit=True)
+    assert inc.commit_counts()[0] == 2
+    inc.close(); one.close()
