@@ -1150,6 +1150,8 @@ struct fg_batch {
     void* d_plan = nullptr;        // one device block [LQuery | LLeaf | LItem] (l_queries / l_leaves / l_items point into it)
     void* h_plan = nullptr;        // its page-locked source (kept until release: the upload is asynchronous)
     size_t plan_sz = 0;
+    uint64_t* d_sel = nullptr;     // deep-page batches (ks == 0): scratch of lead_select_kernel
+    size_t sel_sz = 0;
     std::vector<int32_t> qstatus;  // FG_PREP_PER_QUERY_STATUS: per-query lowering status
     std::string first_bad;
 };
@@ -1179,6 +1181,7 @@ extern "C" void fg_batch_release(fg_batch* b) {
         pool_free(c, b->d_plan, b->plan_sz);
         pinned_free(c, b->h_plan, b->plan_sz);
         pool_free(c, b->l_state, b->lsz[3]);
+        pool_free(c, b->d_sel, b->sel_sz);
     }
     for (auto& e : b->ev) if (e) cudaEventDestroy(e);
     if (b->ev_up) cudaEventDestroy(b->ev_up);
@@ -1277,7 +1280,6 @@ static int32_t prepare_lead(fg_index* ix, const fg_query_batch* qb, uint32_t pre
             memset(&D, 0, sizeof(D));
             D.k = 1;
             if (q.k == 0) return lfail(o, FG_ERR_INVALID, "query %u: k == 0 (TopDocs::with_limit requires limit >= 1)", qi);
-            if (q.k > 1024) return lfail(o, FG_ERR_UNSUPPORTED, "query %u: k = %u > 1024 not supported", qi, q.k);
             if ((uint64_t)q.clause_begin + q.n_clauses > qb->n_clauses)
                 return lfail(o, FG_ERR_INVALID, "query %u: clause range out of bounds", qi);
             o.kmax = std::max(o.kmax, q.k);
@@ -1425,6 +1427,11 @@ static int32_t prepare_lead(fg_index* ix, const fg_query_batch* qb, uint32_t pre
             D.n_lead = (uint32_t)nl;
             D.n_req = n_req;
             D.n_opt = n_opt;
+            {
+                uint64_t ld = 0;  // a document is offered at most once, by one of the leads
+                for (int i = 0; i < nl; i++) ld += o.leaves[l0 + i].df;
+                D.lead_docs = (uint32_t)std::min<uint64_t>(ld, ix->n_docs);
+            }
             // rest of a lead = what a candidate of it can still collect: later leads + required + optional leaves
             float tail = 0.f, total = 0.f;
             for (uint32_t i = (uint32_t)nl; i < (uint32_t)nl + n_req + n_opt; i++) tail += o.leaves[l0 + i].ub;
@@ -1522,7 +1529,7 @@ static int32_t prepare_lead(fg_index* ix, const fg_query_batch* qb, uint32_t pre
     std::vector<uint32_t> leaf_base((size_t)LT + 1, 0), cur_base((size_t)LT + 1, 0);
     std::vector<uint32_t> key_start((size_t)LT * LKEYS);
     uint32_t kmax = 1;
-    uint64_t sum_k = 0, part_entries = 0, ni_tot = 0;
+    uint64_t sum_k = 0, part_entries = 0, ni_tot = 0, sel_entries = 0;
     for (int t = 0; t < LT; t++) {
         leaf_base[t + 1] = leaf_base[t] + (uint32_t)parts[t].leaves.size();
         cur_base[t + 1] = cur_base[t] + parts[t].n_cursors;
@@ -1543,12 +1550,24 @@ static int32_t prepare_lead(fg_index* ix, const fg_query_batch* qb, uint32_t pre
         for (uint32_t qi = q0; qi < q1; qi++) {
             LQuery& D = lq[qi];
             D.leaf_begin += leaf_base[t];
-            D.part_begin = (uint32_t)part_entries;
-            D.part_cap = parts[t].q_items[qi - q0] * D.k;
+            D.part_begin = (uint32_t)std::min<uint64_t>(part_entries, 0xFFFFFFFFull);
+            if (kmax > 1024) {
+                // deep pages: the warps append every accepted hit (no per-warp queue); at most lead_docs of them exist.
+                // A scratch region for the selected page follows (lead_select_kernel sorts it: power of two).
+                D.part_cap = D.lead_docs;
+                uint64_t cap2 = 1;
+                while (cap2 < std::min<uint64_t>(D.k, D.part_cap)) cap2 <<= 1;
+                D.sel_begin = (uint32_t)std::min<uint64_t>(sel_entries, 0xFFFFFFFFull);
+                sel_entries += cap2;
+            } else {
+                D.part_cap = parts[t].q_items[qi - q0] * D.k;
+            }
             part_entries += D.part_cap;
         }
     }
-    if (part_entries > 0xFFFFFFF0ull || ni_tot > 0xFFFFFFF0ull) return fail(FG_ERR_UNSUPPORTED, "partial result lists exceed 2^32 entries");
+    // (deep pages share a batch with other queries at the price of list space for all of them: callers batch them apart)
+    if (part_entries > 0x7FFFFFF0ull || sel_entries > 0x7FFFFFF0ull || ni_tot > 0xFFFFFFF0ull)
+        return fail(FG_ERR_UNSUPPORTED, "partial result lists exceed 2^31 entries%s", kmax > 1024 ? " (a batch with a page limit above 1024 keeps every match of every query: send deep pages in batches of their own)" : "");
     const uint32_t n_cursors = cur_base[LT];
     const size_t nl_tot = leaf_base[LT];
     const size_t off_leaves = ((size_t)qb->n_queries * sizeof(LQuery) + 255) & ~(size_t)255;
@@ -1562,7 +1581,7 @@ static int32_t prepare_lead(fg_index* ix, const fg_query_batch* qb, uint32_t pre
     b->n_queries = qb->n_queries;
     b->n_items = (uint32_t)ni_tot;
     b->kcap = kmax;
-    b->ks = kmax <= 32 ? 1 : kmax <= 128 ? 4 : 32;
+    b->ks = kmax <= 32 ? 1 : kmax <= 128 ? 4 : kmax <= 1024 ? 32 : 0;  // 0: deep pages (append + select)
     b->sum_k = sum_k;
     b->n_cursors = n_cursors;
     b->partial_entries = part_entries;
@@ -1597,6 +1616,10 @@ static int32_t prepare_lead(fg_index* ix, const fg_query_batch* qb, uint32_t pre
     CU(pool_alloc(ctx, (void**)&b->d_partial, b->sz[3]));
     b->sz[5] = 16 * sizeof(unsigned long long);
     CU(pool_alloc(ctx, (void**)&b->d_stats, b->sz[5]));
+    if (sel_entries) {
+        b->sel_sz = (size_t)sel_entries * 8;
+        CU(pool_alloc(ctx, (void**)&b->d_sel, b->sel_sz));
+    }
     for (auto& e : b->ev) CU(cudaEventCreate(&e));
     CU(cudaEventCreateWithFlags(&b->ev_up, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&b->ev_done, cudaEventDisableTiming));
@@ -1679,7 +1702,7 @@ extern "C" int32_t fg_batch_prepare_ex(fg_index* ix, const fg_query_batch* qb, u
         for (uint32_t qi = q_begin; qi < q_end; qi++) {
             const fg_query& q = qb->queries[qi];
             if (q.k == 0) return lfail(o, FG_ERR_INVALID, "query %u: k == 0 (TopDocs::with_limit requires limit >= 1)", qi);
-            if (q.k > 1024) return lfail(o, FG_ERR_UNSUPPORTED, "query %u: k = %u > 1024 not supported", qi, q.k);
+            if (q.k > 1024) return lfail(o, FG_ERR_UNSUPPORTED, "query %u: k = %u > 1024: deep pages run on the lead-driven kernels (default lowering)", qi, q.k);
             if ((uint64_t)q.clause_begin + q.n_clauses > qb->n_clauses)
                 return lfail(o, FG_ERR_INVALID, "query %u: clause range out of bounds", qi);
             kmax = std::max(kmax, q.k);
@@ -2044,6 +2067,7 @@ extern "C" int32_t fg_batch_execute(fg_batch* b, uint32_t flags, uint32_t k_stri
         m.out_hits = d_hits;
         m.out_n = (uint32_t*)d_n_hits;
         m.out_count = (uint32_t*)d_match_count;
+        m.sel = b->d_sel;
         launch_lead_merge(m, b->ks, st);
         CU(cudaEventRecord(b->ev[2], st));
         b->n_launches = b->n_queries ? (b->n_items ? 3 : 2) : 0;
@@ -2370,6 +2394,7 @@ extern "C" int32_t fg_batch_execute_sharded(fg_batch* b, fg_comm* c, uint32_t fl
     if (!b || !c || !d_hits || !d_n_hits) return fail(FG_ERR_INVALID, "fg_batch_execute_sharded: NULL argument");
     fg_ctx* ctx = b->ix->ctx;
     if (ctx != c->ctx) return fail(FG_ERR_INVALID, "fg_batch_execute_sharded: the batch and the communicator belong to different contexts");
+    if (b->lead && b->ks == 0) return fail(FG_ERR_UNSUPPORTED, "fg_batch_execute_sharded: page limits above 1024 are not merged across shards");
     if (k_stride < b->kcap) return fail(FG_ERR_INVALID, "k_stride %u < max k %u", k_stride, b->kcap);
     CU(cudaSetDevice(ctx->device));
     const size_t nq = b->n_queries;

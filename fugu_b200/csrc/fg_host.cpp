@@ -1188,6 +1188,51 @@ extern "C" int32_t fgh_search_batch(fgh_dataset* ds, uint32_t n, const char* con
     const std::shared_ptr<fg_index> snap = current_snapshot(ds);  // held until the results are collected
     if (!snap) return host_fail(ds->ctx ? FG_ERR_INVALID : FG_ERR_NO_DEVICE, "dataset has no device snapshot (commit first)");
     if (n == 0) return FG_OK;
+    // Deep pages (limit = page*per_page + per_page above 1024; handlers/search.rs:370-374 clamps per_page, not page) are
+    // evaluated without per-warp queues: every match above the running threshold is kept and the page is selected
+    // afterwards, which costs list space for every query of the batch they are in. They are rare: answer each one in a
+    // batch of its own and the rest together.
+    if (n > 1) {
+        std::vector<uint32_t> deep, rest;
+        for (uint32_t i = 0; i < n; i++) {
+            const uint64_t limit = (uint64_t)(pages ? pages[i] : 0) * (per_pages ? per_pages[i] : 20) + (per_pages ? per_pages[i] : 20);
+            (limit > 1024 ? deep : rest).push_back(i);
+        }
+        if (!deep.empty()) {
+            auto sub = [&](const std::vector<uint32_t>& idx) -> int32_t {
+                const uint32_t m = (uint32_t)idx.size();
+                if (!m) return FG_OK;
+                std::vector<const char*> q(m), f;
+                std::vector<uint32_t> fo(m + 1, 0), pg(m), pp(m), nh(m), cnt(m);
+                std::vector<int32_t> st(m, FG_OK);
+                std::vector<fg_hit> hits((size_t)m * stride);
+                for (uint32_t j = 0; j < m; j++) {
+                    const uint32_t i = idx[j];
+                    q[j] = queries[i];
+                    pg[j] = pages ? pages[i] : 0;
+                    pp[j] = per_pages ? per_pages[i] : 20;
+                    if (filter_offsets)
+                        for (uint32_t x = filter_offsets[i]; x < filter_offsets[i + 1]; x++) f.push_back(filters[x]);
+                    fo[j + 1] = (uint32_t)f.size();
+                }
+                const int32_t rc = fgh_search_batch(ds, m, q.data(), f.empty() ? nullptr : f.data(), fo.data(), pg.data(), pp.data(), stride, hits.data(),
+                                                    nh.data(), out_match_count ? cnt.data() : nullptr, status ? st.data() : nullptr);
+                if (rc) return rc;
+                for (uint32_t j = 0; j < m; j++) {
+                    const uint32_t i = idx[j];
+                    memcpy(out_hits + (size_t)i * stride, hits.data() + (size_t)j * stride, (size_t)nh[j] * sizeof(fg_hit));
+                    out_n[i] = nh[j];
+                    if (out_match_count) out_match_count[i] = cnt[j];
+                    if (status) status[i] = st[j];
+                }
+                return FG_OK;
+            };
+            if (int32_t rc = sub(rest)) return rc;
+            for (uint32_t i : deep)
+                if (int32_t rc = sub(std::vector<uint32_t>{i})) return rc;
+            return FG_OK;
+        }
+    }
     // Large requests are cut into a few chunks and pipelined: while the device evaluates chunk i
     // (fg_batch_submit returns at once) this thread parses, plans and lowers chunk i+1, so the host
     // side of the call hides under the kernels instead of adding to them.

@@ -202,7 +202,9 @@ struct LQuery {
     uint32_t part_cap;
     uint32_t theta0;     // sortable f32 lower bound of the k-th best score known at lowering time, 0 = none
     uint32_t hist_base;  // (f32 bits of the query's total upper bound) >> LHIST_SHIFT: top bucket of its score histogram
-    uint32_t pad[3];
+    uint32_t sel_begin;  // deep-page batches (k > 1024): this query's region of the selection scratch (next power of two >= min(k, part_cap) keys)
+    uint32_t lead_docs;  // min(sum of the leads' document frequencies, n_docs): no more documents are ever offered
+    uint32_t pad[1];
 };
 static_assert(sizeof(LQuery) == 64, "LQuery is uploaded as a flat array");
 // Shared threshold of a query: every warp adds the score of each hit it accepts to a per-query histogram
@@ -255,6 +257,7 @@ struct LeadMergeParams {
     void* out_hits;
     uint32_t* out_n;
     uint32_t* out_count;
+    uint64_t* sel;  // deep-page batches: selection scratch (LQuery::sel_begin)
 };
 void launch_lead(const LeadParams& p, int ks, int n_sms, void* stream);
 void launch_lead_merge(const LeadMergeParams& p, int ks, void* stream);

@@ -233,7 +233,9 @@ __device__ __forceinline__ void run_item(const LeadParams& p, const LeadShared& 
     const unsigned lt = (1u << lane) - 1u;
     Acct A;
 
-    WarpTopK<KS> tk;
+    // KS == 0 (deep pages, k > 1024): no register queue -- every accepted hit is appended to the query's partial region
+    // right away (the histogram threshold still prunes) and lead_select_kernel picks the k best afterwards
+    WarpTopK<(KS > 0 ? KS : 1)> tk;
     tk.init();
     float theta = -INFINITY;  // a candidate needs score >= theta (ties are decided by the doc id in the queue)
     uint32_t pub = 0u;        // sortable threshold this warp has seen or published
@@ -563,7 +565,17 @@ __device__ __forceinline__ void run_item(const LeadParams& p, const LeadShared& 
                         if (p.match_bitmap && live)
                             atomicOr(p.match_bitmap + (size_t)item.query * p.bitmap_words + (cr >> 5), 1u << (cr & 31u));
                     }
-                    tk.offer(live, make_key(sr, cr), k, lane);
+                    if (KS == 0) {
+                        const unsigned mk = __ballot_sync(FULL, live);
+                        if (mk) {
+                            uint32_t base = 0u;
+                            if (lane == 0) base = atomicAdd(p.qcount + item.query, (uint32_t)__popc(mk));
+                            base = __shfl_sync(FULL, base, 0) + (uint32_t)__popc(mk & lt);
+                            if (live && base < q.part_cap) p.partial[q.part_begin + base] = make_key(sr, cr);
+                        }
+                    } else {
+                        tk.offer(live, make_key(sr, cr), k, lane);
+                    }
                     if (prune && live) {  // the query-wide histogram of accepted scores (fg_internal.h)
                         int idx = (int)(__float_as_uint(sr) >> LHIST_SHIFT) - (int)q.hist_base + (LHIST_B - 1);
                         idx = sr > 0.f ? min(max(idx, 0), LHIST_B - 1) : 0;
@@ -572,7 +584,7 @@ __device__ __forceinline__ void run_item(const LeadParams& p, const LeadShared& 
                 }
                 if (prune) {
                     // this warp's own k-th best, and the k-th best the histogram proves for the whole query
-                    uint32_t best = tk.theta ? (uint32_t)(tk.theta >> 32) : 0u;
+                    uint32_t best = (KS > 0 && tk.theta) ? (uint32_t)(tk.theta >> 32) : 0u;
                     __syncwarp();
                     const uint4 h4 = __ldcg(reinterpret_cast<const uint4*>(hq) + lane);  // buckets 4*lane .. 4*lane+3
                     const uint32_t mine = h4.x + h4.y + h4.z + h4.w;
@@ -642,7 +654,7 @@ __device__ __forceinline__ void run_item(const LeadParams& p, const LeadShared& 
         uint32_t nz = 0u;
 #pragma unroll
         for (int s = 0; s < KS; s++) nz += (uint32_t)__popc(__ballot_sync(FULL, tk.q[s] != 0 && s * 32 + lane < k));
-        if (nz) {
+        if (KS > 0 && nz) {
             uint32_t base = 0u;
             if (lane == 0) base = atomicAdd(p.qcount + item.query, nz);
             base = __shfl_sync(FULL, base, 0) + q.part_begin;
@@ -676,6 +688,7 @@ __device__ __forceinline__ void run_item(const LeadParams& p, const LeadShared& 
 
 template <int KS, bool TMA>
 __global__ void __launch_bounds__(LNT, KS <= 1 ? FG_LEAD_MINB : (KS <= 4 ? 3 : 1)) lead_kernel(const LeadParams p) {
+    static_assert(KS > 0 || !TMA, "the deep-page variant is built without payload staging");
     FG_DYN_SMEM(smem);
     LeadShared& S = *reinterpret_cast<LeadShared*>(smem);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -771,6 +784,115 @@ __global__ void __launch_bounds__(128) lead_merge_kernel(const LeadMergeParams p
     }
     for (uint32_t r = KS * 32 + lane; r < p.k_stride; r += 32) out[r] = make_uint2(0u, 0xFFFFFFFFu);
     if (lane == 0) {
+        p.out_n[qi] = nh;
+        if (p.out_count) p.out_count[qi] = p.qmatch[qi];
+    }
+}
+
+// Deep pages (k > 1024, any page * per_page + per_page the handler lets through: /root/reference/src/db/search.rs:154-160):
+// the lead warps appended every accepted hit to the query's partial region. One CTA per query: radix select of the
+// k-th largest 64-bit key (most significant byte first; keys are distinct, the doc id is part of them), compaction of
+// the k keys at or above it into the query's scratch region, bitonic sort there (padded to a power of two), page out.
+__global__ void __launch_bounds__(256) lead_select_kernel(const LeadMergeParams p) {
+    __shared__ uint32_t hist[256];
+    __shared__ uint64_t s_prefix;
+    __shared__ uint32_t s_remaining, s_cnt;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const uint32_t qi = blockIdx.x;
+    const LQuery q = p.queries[qi];
+    uint2* out = reinterpret_cast<uint2*>(p.out_hits) + (size_t)qi * p.k_stride;
+    if (q.flags & LQ_ALL) {  // (uniform) AllQuery: the first k alive docs, every score equals const_score
+        if (tid >= 32) return;
+        uint32_t found = 0;
+        for (uint32_t base = 0; base < p.n_docs && found < q.k; base += 32) {
+            const uint32_t d = base + lane;
+            const bool al = d < p.n_docs && (!p.alive || ((p.alive[d >> 5] >> (d & 31)) & 1u));
+            const unsigned m = __ballot_sync(FULL, al);
+            const uint32_t r = found + __popc(m & ((1u << lane) - 1u));
+            if (al && r < q.k && r < p.k_stride) out[r] = make_uint2(__float_as_uint(q.const_score), d + p.doc_base);
+            found += __popc(m);
+        }
+        const uint32_t nh_all = min(min(found, q.k), p.k_stride);
+        for (uint32_t r = nh_all + lane; r < p.k_stride; r += 32) out[r] = make_uint2(0u, 0xFFFFFFFFu);
+        if (lane == 0) {
+            p.out_n[qi] = nh_all;
+            if (p.out_count) p.out_count[qi] = p.n_alive;
+        }
+        return;
+    }
+    const uint64_t* src = p.partial + q.part_begin;
+    const uint32_t total = min(p.qcount[qi], q.part_cap);
+    const uint32_t k = min(min(q.k, total), p.k_stride);
+    uint64_t* sel = p.sel + q.sel_begin;
+    uint32_t cap2 = 1u;
+    while (cap2 < k) cap2 <<= 1;
+    uint64_t T = 0;  // the k-th largest key
+    if (total > k) {
+        uint64_t prefix = 0;
+        uint32_t remaining = k;
+        for (int shift = 56; shift >= 0; shift -= 8) {
+            hist[tid] = 0u;
+            __syncthreads();
+            for (uint32_t i = tid; i < total; i += 256u) {
+                const uint64_t key = src[i];
+                if (shift == 56 || (key >> (shift + 8)) == prefix) atomicAdd(&hist[(uint32_t)(key >> shift) & 255u], 1u);
+            }
+            __syncthreads();
+            if (tid == 0) {
+                uint32_t acc = 0u;
+                int d = 255;
+                for (; d > 0; d--) {
+                    if (acc + hist[d] >= remaining) break;
+                    acc += hist[d];
+                }
+                s_prefix = (prefix << 8) | (uint64_t)d;
+                s_remaining = remaining - acc;
+            }
+            __syncthreads();
+            prefix = s_prefix;
+            remaining = s_remaining;
+            __syncthreads();
+        }
+        T = prefix;
+    }
+    if (tid == 0) s_cnt = 0u;
+    __syncthreads();
+    for (uint32_t i = tid; i < total; i += 256u) {
+        const uint64_t key = src[i];
+        if (key >= T && key != 0) {
+            const uint32_t pos = atomicAdd(&s_cnt, 1u);
+            if (pos < cap2) sel[pos] = key;
+        }
+    }
+    __syncthreads();
+    const uint32_t n_sel = min(s_cnt, cap2);
+    for (uint32_t i = n_sel + tid; i < cap2; i += 256u) sel[i] = 0;
+    __syncthreads();
+    for (uint32_t size = 2u; size <= cap2; size <<= 1) {
+        for (uint32_t stride = size >> 1; stride; stride >>= 1) {
+            for (uint32_t i = tid; i < cap2 / 2u; i += 256u) {
+                const uint32_t pos = 2u * i - (i & (stride - 1u));
+                const bool desc = (pos & size) == 0u;
+                const uint64_t a = sel[pos], b = sel[pos + stride];
+                if ((a < b) == desc) {
+                    sel[pos] = b;
+                    sel[pos + stride] = a;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    const uint32_t nh = min(n_sel, k);
+    for (uint32_t r = tid; r < p.k_stride; r += 256u) {
+        uint2 h = make_uint2(0u, 0xFFFFFFFFu);
+        if (r < nh) {
+            const uint64_t key = sel[r];
+            h.x = __float_as_uint(unsortable((uint32_t)(key >> 32)));
+            h.y = ~(uint32_t)(key & 0xFFFFFFFFu) + p.doc_base;
+        }
+        out[r] = h;
+    }
+    if (tid == 0) {
         p.out_n[qi] = nh;
         if (p.out_count) p.out_count[qi] = p.qmatch[qi];
     }
@@ -964,6 +1086,7 @@ void launch_lead(const LeadParams& p, int ks, int n_sms, void* stream) {
     static bool configured = false;
     if (!configured) {
         const int s0 = (int)sizeof(LeadShared), s1 = s0 + (int)(LNW * sizeof(StageShared));
+        cudaFuncSetAttribute(lead_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s0);
         cudaFuncSetAttribute(lead_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s0);
         cudaFuncSetAttribute(lead_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s0);
         cudaFuncSetAttribute(lead_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s0);
@@ -975,7 +1098,9 @@ void launch_lead(const LeadParams& p, int ks, int n_sms, void* stream) {
     const unsigned grid = min((p.n_items + LNW - 1) / LNW, (unsigned)n_sms * per_sm);
     // p.tma (FG_LEAD_TMA=1): the variant that stages lead-block payloads with 1-D bulk copies -- measured 9 % slower
     // than plain loads of L2-prefetched payloads on the C2 mix (profiles/r02_tma_ab.txt), so it is not the default
-    if (ks <= 1) {
+    if (ks == 0) {
+        FG_LAUNCH((lead_kernel<0, false>), grid, LNT, (int)sizeof(LeadShared), st, p);
+    } else if (ks <= 1) {
         if (p.tma) FG_LAUNCH((lead_kernel<1, true>), grid, LNT, smem, st, p);
         else FG_LAUNCH((lead_kernel<1, false>), grid, LNT, smem, st, p);
     } else if (ks <= 4) {
@@ -990,7 +1115,8 @@ void launch_lead_merge(const LeadMergeParams& p, int ks, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (p.n_queries == 0) return;
     const unsigned grid = (p.n_queries + 3) / 4;
-    if (ks <= 1) FG_LAUNCH(lead_merge_kernel<1>, grid, 128, 0, st, p);
+    if (ks == 0) FG_LAUNCH(lead_select_kernel, p.n_queries, 256, 0, st, p);
+    else if (ks <= 1) FG_LAUNCH(lead_merge_kernel<1>, grid, 128, 0, st, p);
     else if (ks <= 4) FG_LAUNCH(lead_merge_kernel<4>, grid, 128, 0, st, p);
     else FG_LAUNCH(lead_merge_kernel<32>, grid, 128, 0, st, p);
 }

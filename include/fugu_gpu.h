@@ -194,7 +194,11 @@ int32_t fg_batch_prepare(fg_index* index, const fg_query_batch* batch, fg_batch*
  * the exact algorithmic-byte accounting pass, which is defined on exhaustive block evaluation); the default
  * lowering targets the lead-driven kernels (block-max / MaxScore pruning, skip-table gallop lookups). */
 #define FG_PREP_LEGACY 2u
-/* FG_PREP_PER_QUERY_STATUS: a query the device path cannot take (k == 0, k > 1024, more than 32 live leaves, a plan
+/* Page limits: k <= 1024 is served from per-warp register queues (the common case); a batch whose largest k exceeds 1024
+ * (deep pages: src/db/search.rs:154-160 puts no bound on page * per_page) keeps every match above the running threshold
+ * of every query in it and selects the pages afterwards (radix select + sort on the device): exact, any k, but list
+ * space grows with the number of matches, so callers send deep pages in batches of their own (fgh_search_batch does).
+ * FG_PREP_PER_QUERY_STATUS: a query the device path cannot take (k == 0, more than 32 live leaves, a plan
  * node outside the supported shapes) does not fail the batch: it becomes an empty query (0 hits) and its status is
  * reported by fg_batch_query_status; the other queries of the batch are answered. Without the flag the first such
  * query fails the call (default lowering only; FG_PREP_LEGACY batches always fail as a whole). */

@@ -295,6 +295,44 @@ def test_deep_pagination_k_up_to_1024(ctx):
     index.close()
 
 
+def test_deep_pagination_beyond_1024(ctx):
+    """The reference puts no bound on page * per_page (src/db/search.rs:154-160; handlers/search.rs:370-374 clamps only
+    per_page): limits above 1024 run without per-warp queues (append + radix select + sort). k = 1500 / 5000 / 40000
+    (more than there are matches for most queries), through the device ABI in a batch of their own, and through
+    fgh_search_batch mixed with ordinary pages."""
+    from tests import util
+
+    small = util.EMULATED  # (CPU suite time)
+    cfg = synth.Config(cfg=2, n_docs=6_000 if small else 30_000, vocab=1_000 if small else 5_000, n_queries=12 if small else 24, k=10, name_pct=10)
+    corpus, desc, index = _setup(ctx, cfg)
+    qs = synth.gen_queries(cfg)
+    for i, q in enumerate(qs):
+        q["k"] = (1500, 5000, 40_000)[i % 3]
+    batch = plan_queries(qs, vocab=cfg.vocab, n_text_fields=2)
+    check_batch_against_oracle(index, desc, batch, bitmaps=False, legacy=False)
+    index.close()
+    # host layer: page 30 of 100 per page (limit 3100) next to first pages, one request
+    from fugu_b200.dataset import Dataset, QuerySet
+
+    ds = Dataset(ctx)
+    words = [f"w{i + 1}" for i in range(cfg.vocab)]
+    ds.adopt(desc, [words, words])
+    strings = [q["query"] for q in qs[:12]]
+    pages = [30 if i % 4 == 0 else 0 for i in range(12)]
+    deep = QuerySet(strings, None, 0, 100)
+    deep.pages[:] = np.array(pages, np.uint32)
+    hits, nh, cnt, status = ds.search_batch(deep, want_counts=False)
+    assert (status == 0).all()
+    for i, s_ in enumerate(strings):
+        one = ds.search_batch(QuerySet([s_], None, pages[i], 100), want_counts=False)
+        assert nh[i] == one[1][0] and np.array_equal(hits[i, :nh[i]], one[0][0, :nh[i]]), (i, s_)
+        # the page is rows [offset, offset + per_page) of the full ranking
+        allr = ds.search_batch(QuerySet([s_], None, 0, 100 * (pages[i] + 1)), want_counts=False)
+        want = allr[0][0, 100 * pages[i]:allr[1][0]]
+        assert nh[i] == len(want) and np.array_equal(hits[i, :nh[i]]["doc"], want["doc"]), (i, s_)
+    ds.close()
+
+
 def test_concurrent_callers_share_one_index(ctx):
     """The ABI is thread-safe and re-entrant (axum handlers call Dataset::search concurrently,
     src/server/server_main.rs:50): 8 host threads hammer one snapshot; every result equals the
