@@ -115,7 +115,7 @@ struct fg_ctx {
     bool env_no_prune = false;    // FG_NO_PRUNE=1: exhaustive evaluation (A/B runs; results are identical)
     bool env_timing = false;      // FG_TIMING=1
     bool env_prof = false;        // FG_PROF=1
-    uint32_t lead_par_blocks = 16, lead_max_par = 64, lead_chunk = 16, lead_tma = 0;
+    uint32_t lead_par_blocks = 16, lead_max_par = 64, lead_chunk = 16, lead_tma = 0, lead_chunk_req = 48, lead_par_blocks_req = 2, lead_max_par_req = 1024, lead_union_work = 32;
 };
 static uint64_t env_u64_early(const char* name, uint64_t dflt);
 
@@ -201,6 +201,10 @@ extern "C" int32_t fg_ctx_create(int32_t device, fg_ctx** out) {
     c->lead_par_blocks = (uint32_t)std::max<uint64_t>(1, env_u64_early("FG_LEAD_PAR_BLOCKS", 16));
     c->lead_max_par = (uint32_t)std::max<uint64_t>(1, env_u64_early("FG_LEAD_MAX_PAR", 64));
     c->lead_chunk = (uint32_t)std::max<uint64_t>(1, env_u64_early("FG_LEAD_CHUNK", 16));
+    c->lead_chunk_req = (uint32_t)std::max<uint64_t>(1, env_u64_early("FG_LEAD_REQ_WORK", 48));
+    c->lead_par_blocks_req = (uint32_t)std::max<uint64_t>(1, env_u64_early("FG_LEAD_PAR_BLOCKS_REQ", 2));
+    c->lead_max_par_req = (uint32_t)std::max<uint64_t>(1, env_u64_early("FG_LEAD_MAX_PAR_REQ", 1024));
+    c->lead_union_work = (uint32_t)std::max<uint64_t>(1, env_u64_early("FG_LEAD_UNION_WORK", 32));
     c->lead_tma = (uint32_t)env_u64_early("FG_LEAD_TMA", 0);
     CU(cudaStreamCreateWithFlags(&c->own, cudaStreamNonBlocking));
     c->stream = c->own;
@@ -1239,7 +1243,7 @@ static inline uint32_t host_sortable(float f) {
 static int32_t prepare_lead(fg_index* ix, const fg_query_batch* qb, uint32_t prep_flags, fg_batch** out) {
     fg_ctx* ctx = ix->ctx;
     const bool use_cols = !(prep_flags & FG_PREP_NO_COLUMNS) && !ctx->env_no_columns;  // tf columns and membership bitmaps
-    const uint32_t PAR_BLOCKS = ctx->lead_par_blocks, MAX_PAR = ctx->lead_max_par;
+    const uint32_t PAR_BLOCKS_UNION = ctx->lead_par_blocks, MAX_PAR = ctx->lead_max_par;
     constexpr int MAXC = 40;
     struct CRec { uint32_t occur, begin, count; uint64_t df; };
     using Part = LeadPart;
@@ -1466,6 +1470,10 @@ static int32_t prepare_lead(fg_index* ix, const fg_query_batch* qb, uint32_t pre
             // per execution; in the pruned form such a lead ends at its first threshold test.)
             uint32_t qitems = 0;
             const float bound_slack = D.slack + const_score;
+            // (required clauses: every posting of a lead block is looked up in them -- a block is a whole round of dependent
+            // gathers, so such leads are shared out among warps in much smaller pieces than the mostly skipped blocks of a pruned union)
+            const uint32_t PAR_BLOCKS = n_req ? std::min<uint32_t>(PAR_BLOCKS_UNION, std::max<uint32_t>(2u, ctx->lead_chunk_req / n_req))
+                                              : std::min<uint32_t>(PAR_BLOCKS_UNION, std::max<uint32_t>(2u, ctx->lead_union_work / std::max<uint32_t>(1u, D.n_leaves - 1)));
             int i = 0;
             while (i < nl) {
                 const LLeaf& L0 = o.leaves[l0 + i];
@@ -1474,7 +1482,8 @@ static int32_t prepare_lead(fg_index* ix, const fg_query_batch* qb, uint32_t pre
                 int j = i + 1;
                 if (nb > PAR_BLOCKS) {
                     // (every copy appends up to k hits to the query's partial region: fewer copies for deep pages)
-                    const uint32_t max_par = std::max<uint32_t>(4, std::min<uint32_t>(MAX_PAR, 4096u / q.k));
+                    const uint32_t max_par = n_req ? std::max<uint32_t>(4, std::min<uint32_t>(ctx->lead_max_par_req, 16384u / q.k))
+                                                   : std::max<uint32_t>(4, std::min<uint32_t>(MAX_PAR, 4096u / q.k));
                     par = std::max<uint32_t>(1, std::min<uint32_t>(max_par, (nb + PAR_BLOCKS - 1) / PAR_BLOCKS));
                 } else {
                     uint32_t sum = nb;
@@ -2050,6 +2059,9 @@ extern "C" int32_t fg_batch_execute(fg_batch* b, uint32_t flags, uint32_t k_stri
         p.acct = (flags & FG_EXEC_COUNTERS) ? 1 : 0;
         p.tma = ctx->lead_tma;
         p.chunk = ctx->lead_chunk;
+        p.chunk_req = ctx->lead_chunk_req;
+        p.union_work = ctx->lead_union_work;
+        p.prof = (ctx->env_prof && p.acct) ? 1u : 0u;
         CU(cudaEventRecord(b->ev[0], st));
         launch_lead(p, b->ks, ctx->n_sms, st);
         CU(cudaEventRecord(b->ev[1], st));
@@ -2148,6 +2160,16 @@ extern "C" int32_t fg_batch_get_stats(fg_batch* b, fg_batch_stats* out) {
         std::lock_guard<std::mutex> g(ctx->mu);
         CU(cudaStreamSynchronize(ctx->stream));
         CU(cudaMemcpy(h, b->d_stats, sizeof(h), cudaMemcpyDeviceToHost));
+    }
+    if (ctx->env_prof && b->lead) {
+        unsigned long long pr[8];
+        cudaMemcpy(pr, b->d_stats + 8, sizeof(pr), cudaMemcpyDeviceToHost);
+        if (pr[4]) {
+            const double start = (double)~pr[5], first_idle = (double)~pr[2] - start, done = (double)pr[3] - start;
+            fprintf(stderr, "[prof lead] warps %llu: kernel %.1f us, first warp out of work at %.1f us, busy share %.1f %% of warp-time, longest item %.1f us, "
+                            "mean busy per warp %.1f us\n", pr[4], done * 1e-3, first_idle * 1e-3, 100.0 * (double)pr[0] / ((double)pr[4] * done),
+                    (double)pr[1] * 1e-3, (double)pr[0] / (double)pr[4] * 1e-3);
+        }
     }
     if (ctx->env_prof && !b->lead) {
         unsigned long long pr[8];

@@ -242,7 +242,10 @@ struct LeadParams {
     uint32_t want_counts;
     uint32_t acct;
     uint32_t chunk;            // blocks of a lead a warp claims per step
+    uint32_t chunk_req;        // plans with required clauses: chunk = min(chunk, max(2, chunk_req / required leaves))
+    uint32_t union_work;       // unions: chunk = min(chunk, max(2, union_work / (n_leaves - 1)))
     uint32_t tma;              // stage lead-block payloads in shared memory with 1-D bulk copies (cp.async.bulk)
+    uint32_t prof;             // dev tool: per-warp busy time / longest item into stats[8..13]
 };
 struct LeadMergeParams {
     const LQuery* queries;

@@ -213,7 +213,7 @@ __device__ __forceinline__ uint32_t probe(const LeadParams& p, WarpShared& W, in
 }
 
 template <int KS, bool TMA>
-__device__ __forceinline__ void run_item(const LeadParams& p, const LeadShared& S, WarpShared& W, StageShared& G, const LItem item, int lane) {
+__device__ __forceinline__ void run_item(const LeadParams& p, const LeadShared& S, WarpShared& W, StageShared& G, const LItem item, const uint32_t theta_seen, int lane) {
     const LQuery q = p.queries[item.query];
     __syncwarp();
     {
@@ -239,6 +239,10 @@ __device__ __forceinline__ void run_item(const LeadParams& p, const LeadShared& 
     tk.init();
     float theta = -INFINITY;  // a candidate needs score >= theta (ties are decided by the doc id in the queue)
     uint32_t pub = 0u;        // sortable threshold this warp has seen or published
+    if (prune && theta_seen) {  // the value the caller read for its item-level test
+        pub = theta_seen;
+        theta = unsortable(theta_seen);
+    }
     uint32_t n_match = 0u;
     uint32_t ncand = 0u;      // candidates waiting in W.cand_* (fewer than a round between blocks)
 
@@ -275,6 +279,10 @@ __device__ __forceinline__ void run_item(const LeadParams& p, const LeadShared& 
     // cost -- plan fetch, threshold, result append -- is paid once, and the threshold the early leads establish is
     // already in this warp's queue when the later ones start); a long lead has an item of its own, in several copies.
     const int lead0 = (int)(item.lead & 0xFFFFu), lead1 = (int)(item.lead >> 16);
+    // blocks claimed per step: a plan with required clauses evaluates a full round of lookups per lead block (every
+    // posting is a candidate), so its leads are shared out in small steps; a pruned union mostly skips blocks
+    // (an unpruned union block costs a round of lookups in each of the other leaves: the step shrinks with their number)
+    const uint32_t chunk = has_req ? min(p.chunk, max(2u, p.chunk_req / (uint32_t)n_req)) : min(p.chunk, max(2u, p.union_work / (uint32_t)max(1, n_leaves - 1)));
     for (int lead = lead0; lead < lead1; lead++) {
     const LLeaf LD = W.leaf[lead];
     const uint4* __restrict__ sk = p.ix.skip + LD.blk_begin;
@@ -294,7 +302,7 @@ __device__ __forceinline__ void run_item(const LeadParams& p, const LeadShared& 
     float bound = INFINITY;                 // ... and its block's upper bound
     bool fin = false;    // nothing left to decode (list exhausted, or the lead cannot contribute a hit any more)
     {
-        if (prune) {
+        if (prune && lead != lead0) {  // (the first lead starts from the value read with the item)
             // (one lane's view of the shared threshold for the whole warp: two lanes may see different values)
             const uint32_t g = __shfl_sync(FULL, __ldcg(p.qtheta + item.query), 0);
             if (g > pub) { pub = g; theta = fmaxf(theta, unsortable(g)); }
@@ -335,12 +343,13 @@ __device__ __forceinline__ void run_item(const LeadParams& p, const LeadShared& 
                 break;
             }
             if (g0 >= b1) {  // claim the next chunk of the lead
+                if (b1 >= LD.n_blocks && b1 != 0u) { fin = true; break; }  // (this warp took the list's last chunk)
                 uint32_t c0 = 0u;
-                if (lane == 0) c0 = atomicAdd(cursor, p.chunk);
+                if (lane == 0) c0 = atomicAdd(cursor, chunk);
                 c0 = __shfl_sync(FULL, c0, 0);
                 if (c0 >= LD.n_blocks) { fin = true; break; }
                 g0 = c0;
-                b1 = min(c0 + p.chunk, LD.n_blocks);
+                b1 = min(c0 + chunk, LD.n_blocks);
             }
             if (prune) {
                 const uint32_t g = __shfl_sync(FULL, __ldcg(p.qtheta + item.query), 0);
@@ -706,6 +715,10 @@ __global__ void __launch_bounds__(LNT, KS <= 1 ? FG_LEAD_MINB : (KS <= 4 ? 3 : 1
     // The work queue hands out ONE item per atomic, in array order: items are sorted by lead index, so a query's short
     // leads have run -- and set its threshold -- before its long leads start. (Claiming 4 items per atomic was measured:
     // the first wave then reaches 4x deeper into the array, later leads start cold, 80 % more blocks get decoded.)
+    // dev tool (FG_PROF + FG_EXEC_COUNTERS): busy time of the warps, longest item, when the first warp ran out of work
+    const bool prof = p.prof != 0u;
+    unsigned long long t_busy = 0ull, t_longest = 0ull;
+    if (prof && lane == 0) atomicMax(p.stats + 13, ~global_timer_ns());  // (complement: the earliest start wins)
     while (true) {
         uint32_t it = 0u;
         if (lane == 0) it = atomicAdd(p.work, 1u);
@@ -713,9 +726,24 @@ __global__ void __launch_bounds__(LNT, KS <= 1 ? FG_LEAD_MINB : (KS <= 4 ? 3 : 1
         if (it >= p.n_items) break;
         const LItem item = p.items[it];
         // pruned form: an item none of whose documents can reach the query's current threshold costs two loads
-        // (decided by lane 0 for the warp: the threshold may move between two lanes' loads)
-        if (__shfl_sync(FULL, (int)(!p.exhaustive && item.bound < unsortable(__ldcg(p.qtheta + item.query))), 0)) continue;
-        run_item<KS, TMA>(p, S, W, G, item, lane);
+        // (lane 0's view for the whole warp: the threshold may move between two lanes' loads)
+        const uint32_t th = p.exhaustive ? 0u : __shfl_sync(FULL, __ldcg(p.qtheta + item.query), 0);
+        if (!p.exhaustive && item.bound < unsortable(th)) continue;
+        const unsigned long long t0 = prof ? global_timer_ns() : 0ull;
+        run_item<KS, TMA>(p, S, W, G, item, th, lane);
+        if (prof) {
+            const unsigned long long dt = global_timer_ns() - t0;
+            t_busy += dt;
+            t_longest = max(t_longest, dt);
+        }
+    }
+    if (prof && lane == 0) {
+        const unsigned long long t = global_timer_ns();
+        atomicAdd(p.stats + 8, t_busy);
+        atomicMax(p.stats + 9, t_longest);
+        atomicMax(p.stats + 10, ~t);  // first warp out of work
+        atomicMax(p.stats + 11, t);   // last warp done
+        atomicAdd(p.stats + 12, 1ull);
     }
 }
 

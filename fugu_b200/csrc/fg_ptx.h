@@ -11,6 +11,12 @@
 
 namespace fg {
 
+// nanosecond timer shared by all SMs (dev tool: per-item timing of the lead kernel)
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 // 1 / x with MUFU.RCP (<= 1 ulp; callers keep x >= 0.3)
 __device__ __forceinline__ float rcp_approx(float x) {
     float r;

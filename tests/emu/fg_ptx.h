@@ -10,6 +10,7 @@
 
 namespace fg {
 
+inline unsigned long long global_timer_ns() { return 0ull; }
 inline float rcp_approx(float x) { return 1.0f / x; }
 template <int J>
 inline uint32_t prmt_byte(uint32_t w, uint32_t magic) { return __byte_perm(w, magic, 0x7650u | (uint32_t)J); }

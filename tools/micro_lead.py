@@ -32,13 +32,27 @@ def main():
     print(f"corpus+upload {time.time() - t0:.1f}s", flush=True)
     qs_all = synth.gen_queries(cfg)
 
+    n_col = index.info().n_columns  # text terms w1 .. w<n_col> own a dense tf column (ranks by descending df)
+
     def shape(q):
         s = q["query"]
         return "and" if " AND " in s else ("single" if " " not in s.strip() else "or")
 
+    def has_col(q):
+        return any(w.startswith("w") and w[1:].isdigit() and int(w[1:]) <= n_col for w in q["query"].split())
+
+    def pick(sh):
+        if sh == "all":
+            return qs_all
+        if sh.endswith("_col"):
+            return [q for q in qs_all if shape(q) == sh[:-4] and has_col(q)]
+        if sh.endswith("_nocol"):
+            return [q for q in qs_all if shape(q) == sh[:-6] and not has_col(q)]
+        return [q for q in qs_all if shape(q) == sh]
+
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     for sh in shapes:
-        qs = qs_all if sh == "all" else [q for q in qs_all if shape(q) == sh]
+        qs = pick(sh)
         batch = synth.lower_queries(qs, vocab=cfg.vocab, n_text_fields=len(fields))
         n, k = batch.n_queries, batch.kmax
         d_hits = torch.zeros((n, k, 2), dtype=torch.int32, device="cuda")
