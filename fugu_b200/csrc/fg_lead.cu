@@ -246,8 +246,20 @@ __device__ __forceinline__ void run_item(const LeadParams& p, const LeadShared& 
     uint32_t n_match = 0u;
     uint32_t ncand = 0u;      // candidates waiting in W.cand_* (fewer than a round between blocks)
 
-    auto norm_of = [&](const LLeaf& L, uint32_t c) -> float {
-        return L.fn_field >= 0 ? NORM_CACHE(S, p, L.fn_field * 256 + (int)__ldg(p.ix.fnorm[L.fn_field] + c)) : L.cnorm;
+    // BM25 norms of the candidates selected by `mask` (bit r = row r) in leaf L's field: the four fieldnorm gathers are
+    // issued together (rows outside the mask read doc 0: no branch between the loads), then the cache lookups
+    auto norms4 = [&](const LLeaf& L, const uint32_t (&cc)[4], uint32_t mask, float (&out)[4]) {
+        if (L.fn_field >= 0) {
+            const uint8_t* __restrict__ fn = p.ix.fnorm[L.fn_field];
+            uint32_t id[4];
+#pragma unroll
+            for (int r = 0; r < 4; r++) id[r] = __ldg(fn + (((mask >> r) & 1u) ? cc[r] : 0u));
+#pragma unroll
+            for (int r = 0; r < 4; r++) out[r] = NORM_CACHE(S, p, L.fn_field * 256 + (int)id[r]);
+        } else {
+#pragma unroll
+            for (int r = 0; r < 4; r++) out[r] = L.cnorm;
+        }
     };
 
     // ---- payload staging (p.tma): slot state is uniform across the warp ----
@@ -478,10 +490,12 @@ __device__ __forceinline__ void run_item(const LeadParams& p, const LeadShared& 
             for (int s = 0; s <= n_steps; s++) {
                 if (has_req && s == n_req) {  // all required clauses seen: close the last one, score the lead
                     lv &= found;
+                    float nl[4];
+                    norms4(LD, c, lv, nl);
 #pragma unroll
                     for (int r = 0; r < 4; r++)
                         if ((lv >> r) & 1u) {
-                            sc[r] += LD.weight * tf_factor((float)v[r], norm_of(LD, c[r]));
+                            sc[r] += LD.weight * tf_factor((float)v[r], nl[r]);
                             if (prune && !(sc[r] + rem + slack >= theta)) lv &= ~(1u << r);
                         }
                     if (acct) A.gathers_l += (unsigned long long)__popc(lv);
@@ -518,15 +532,49 @@ __device__ __forceinline__ void run_item(const LeadParams& p, const LeadShared& 
 #pragma unroll
                     for (int r = 0; r < 4; r++) wv[r] = ((lv >> r) & 1u) ? __ldg(L.bits + (c[r] >> 5)) : 0u;
 #pragma unroll
-                    for (int r = 0; r < 4; r++) {
-                        tf[r] = (wv[r] >> (c[r] & 31u)) & 1u;
-                        if (tf[r] && need_tf) {
-                            const uint32_t w0 = (c[r] >> 8) << 3, wl = c[r] >> 5;
-                            uint32_t rk = __ldg(L.rank + (c[r] >> 8)) + (uint32_t)__popc(wv[r] & ((1u << (c[r] & 31u)) - 1u));
-                            for (uint32_t w = w0; w < wl; w++) rk += (uint32_t)__popc(__ldg(L.bits + w));
-                            const uint4 e2 = __ldg(p.ix.skip + L.blk_begin + (rk >> 7));
-                            tf[r] = extract_tf(p.ix.blk, e2, rk & 127u);
-                            if (acct) A.block_bytes_l += 56ull;
+                    for (int r = 0; r < 4; r++) tf[r] = (wv[r] >> (c[r] & 31u)) & 1u;
+                    if (need_tf && __any_sync(FULL, (tf[0] | tf[1] | tf[2] | tf[3]) != 0u)) {
+                        // The hits' postings, all rows in step (each stage's loads of the four rows are in flight together;
+                        // rows without a hit read element 0 of everything: no branch between the loads):
+                        // rank directory + the words of the doc's 256-doc chunk before its own (same 32-byte sector as wv)
+                        uint32_t rk[4];
+#pragma unroll
+                        for (int r = 0; r < 4; r++) rk[r] = __ldg(L.rank + (tf[r] ? (c[r] >> 8) : 0u));
+#pragma unroll
+                        for (int r = 0; r < 4; r++) {
+                            const uint32_t ch = tf[r] ? (c[r] >> 8) : 0u, wi = tf[r] ? ((c[r] >> 5) & 7u) : 0u;
+                            const uint4 a = __ldg(reinterpret_cast<const uint4*>(L.bits) + 2u * ch), b = __ldg(reinterpret_cast<const uint4*>(L.bits) + 2u * ch + 1u);
+                            uint32_t n = (uint32_t)__popc(wv[r] & ((1u << (c[r] & 31u)) - 1u));
+                            n += wi > 0u ? (uint32_t)__popc(a.x) : 0u;
+                            n += wi > 1u ? (uint32_t)__popc(a.y) : 0u;
+                            n += wi > 2u ? (uint32_t)__popc(a.z) : 0u;
+                            n += wi > 3u ? (uint32_t)__popc(a.w) : 0u;
+                            n += wi > 4u ? (uint32_t)__popc(b.x) : 0u;
+                            n += wi > 5u ? (uint32_t)__popc(b.y) : 0u;
+                            n += wi > 6u ? (uint32_t)__popc(b.z) : 0u;
+                            rk[r] = tf[r] ? rk[r] + n : 0u;
+                        }
+                        // position -> block (rank / 128) -> its skip entry -> the two words of the tf stream holding the value
+                        uint4 e2[4];
+#pragma unroll
+                        for (int r = 0; r < 4; r++) e2[r] = __ldg(p.ix.skip + L.blk_begin + (rk[r] >> 7));
+                        uint32_t lo[4], hi[4];
+#pragma unroll
+                        for (int r = 0; r < 4; r++) {
+                            const uint32_t bd = e2[r].w & 63u, bt = (e2[r].w >> 6) & 63u;
+                            const uint32_t* wt = reinterpret_cast<const uint32_t*>(p.ix.blk + (size_t)e2[r].z * 16u) + 4u * bd;
+                            const uint32_t bit = (rk[r] & 127u) * bt;
+                            lo[r] = __ldg(wt + (bit >> 5));
+                            hi[r] = __ldg(wt + (bit >> 5) + 1);
+                        }
+#pragma unroll
+                        for (int r = 0; r < 4; r++) {
+                            const uint32_t bt = (e2[r].w >> 6) & 63u, sh = ((rk[r] & 127u) * bt) & 31u;
+                            const uint32_t m = bt >= 32u ? 0xFFFFFFFFu : ((1u << bt) - 1u);
+                            if (tf[r]) {
+                                tf[r] = (__funnelshift_r(lo[r], hi[r], sh) & m) + 1u;
+                                if (acct) A.block_bytes_l += 56ull;
+                            }
                         }
                     }
                     if (acct) A.gathers_l += 4ull * (unsigned long long)__popc(lv);
@@ -545,14 +593,18 @@ __device__ __forceinline__ void run_item(const LeadParams& p, const LeadShared& 
                         if (tf[r]) lv &= ~(1u << r);
                 } else {
                     rem -= L.ub;
+                    const uint32_t hitm = (tf[0] ? 1u : 0u) | (tf[1] ? 2u : 0u) | (tf[2] ? 4u : 0u) | (tf[3] ? 8u : 0u);
+                    if (__any_sync(FULL, hitm != 0u)) {
+                        float nl[4];
+                        norms4(L, c, hitm, nl);
 #pragma unroll
-                    for (int r = 0; r < 4; r++) {
-                        if (tf[r]) {
-                            sc[r] += L.weight * tf_factor((float)tf[r], norm_of(L, c[r]));
-                            found |= 1u << r;
-                        }
-                        if (mode == 2 && prune && !(sc[r] + rem + slack >= theta)) lv &= ~(1u << r);
+                        for (int r = 0; r < 4; r++)
+                            if (tf[r]) sc[r] += L.weight * tf_factor((float)tf[r], nl[r]);
+                        found |= hitm;
                     }
+#pragma unroll
+                    for (int r = 0; r < 4; r++)
+                        if (mode == 2 && prune && !(sc[r] + rem + slack >= theta)) lv &= ~(1u << r);
                 }
 #pragma unroll
                 for (int r = 0; r < 4; r++) tf[r] = 0u;
