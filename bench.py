@@ -536,12 +536,9 @@ def main():
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         if comm:
-            # strings (host) -> planner -> lowering -> H2D -> kernels -> NCCL all-gather -> merge -> D2H (host)
-            eb, _ = ds.plan_batch(qset)
-            epb = index.prepare(eb)
-            epb.execute_sharded(comm, f_hits.data_ptr(), f_n.data_ptr(), k_stride=k)
-            f_hits.cpu(); f_n.cpu()
-            epb.close()
+            # fgh_search_batch_sharded (collective): strings (host) -> planning shared by the ranks -> lowering for this
+            # shard -> H2D -> kernels -> NCCL all-gather -> merge -> D2H (host), pipelined in chunks like the 1-GPU call
+            e_hits, e_n, e_status = ds.search_batch_sharded(comm, qset)
         else:
             h_hits, h_n, h_c, _ = ds.search_batch(qset, want_counts=counts)  # fgh_search_batch: strings -> plan -> H2D -> kernels -> D2H
             if world > 1:
@@ -553,6 +550,11 @@ def main():
         if it >= 2:
             e2e_times.append(dt)
     e2e_s = float(np.mean(e2e_times))
+    if comm and rank == 0:  # the end-to-end call must return what the timed device path produced
+        ref_h, ref_n = f_hits.cpu().numpy().view(np.uint32).reshape(nq, k, 2), f_n.cpu().numpy().view(np.uint32)
+        assert (e_status == 0).all() and np.array_equal(e_n, ref_n), "fgh_search_batch_sharded: hit counts differ from the device path"
+        for qi in range(nq):
+            assert np.array_equal(e_hits[qi, :e_n[qi]]["doc"], ref_h[qi, :ref_n[qi], 1]), f"fgh_search_batch_sharded: query {qi} differs"
     if os.environ.get("FG_TIMING"):
         print("e2e_times ms", [round(x * 1e3, 2) for x in e2e_times], file=sys.stderr)
     if dist:
@@ -607,8 +609,11 @@ def main():
                              "each timed step" % (info.device_bytes / 1e6, info.column_bytes / 1e6)},
         "e2e": {"value": nq / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": int(lowered_bytes),
                 "d2h_bytes_per_step": int(out_bytes), "ms_per_step": e2e_s * 1e3,
-                "what": "fgh_search_batch: query strings (host) -> C++ planner -> plan lowering -> H2D plan -> kernels -> D2H hits "
-                        "(host); requests of 3072 queries and more are pipelined in two chunks (20 / 80 %%); match counts %s" % ("on" if counts else "off (TopDocs does not count)")},
+                "what": ("fgh_search_batch_sharded (collective): query strings (host) -> planning shared by the ranks (all-gather of the "
+                         "plans) -> lowering for this shard -> H2D -> kernels -> NCCL all-gather + merge -> D2H (host), two pipelined chunks"
+                         if comm else
+                         "fgh_search_batch: query strings (host) -> C++ planner -> plan lowering -> H2D plan -> kernels -> D2H hits "
+                         "(host); requests of 3072 queries and more are pipelined in two chunks (35 / 65 %%); match counts %s" % ("on" if counts else "off (TopDocs does not count)"))},
         "gpu_launches": int(st_timed.n_launches + (1 if world > 1 else 0)) * args.steps,
         "parity": parity,
         "ms_per_step_min": float(np.min(step_ms)), "ms_per_step_median": float(np.median(step_ms)),

@@ -132,7 +132,7 @@ ABI_SYMBOLS = [
     "fg_index_term_info", "fg_search_batch", "fg_batch_prepare", "fg_batch_prepare_ex", "fg_batch_release",
     "fg_batch_execute", "fg_batch_submit", "fg_batch_collect", "fg_batch_get_stats", "fg_merge_topk_device", "fg_fieldnorm_to_id",
     "fg_comm_unique_id", "fg_comm_create", "fg_comm_destroy", "fg_comm_allreduce_sum_u64", "fg_comm_allreduce_sum_u32",
-    "fg_batch_execute_sharded", "fg_batch_query_status",
+    "fg_batch_execute_sharded", "fg_batch_query_status", "fg_batch_submit_sharded", "fg_comm_info", "fg_comm_allgather_bytes",
     "fg_id_to_fieldnorm", "fg_bm25_idf",
 ]
 
@@ -182,6 +182,9 @@ def lib() -> C.CDLL:
     L.fg_comm_allreduce_sum_u64.argtypes = [vp, vp, C.c_size_t]
     L.fg_comm_allreduce_sum_u32.argtypes = [vp, vp, C.c_size_t]
     L.fg_batch_execute_sharded.argtypes = [vp, vp, u32, u32, vp, vp]
+    L.fg_batch_submit_sharded.argtypes = [vp, vp, u32, u32]
+    L.fg_comm_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32)]
+    L.fg_comm_allgather_bytes.argtypes = [vp, vp, C.c_size_t, vp]
     L.fg_fieldnorm_to_id.argtypes = [u32]
     L.fg_fieldnorm_to_id.restype = C.c_uint8
     L.fg_id_to_fieldnorm.argtypes = [C.c_uint8]

@@ -2263,6 +2263,31 @@ extern "C" int32_t fg_batch_submit(fg_batch* b, uint32_t flags, uint32_t k_strid
     return FG_OK;
 }
 
+// fg_batch_submit for a sharded index: local top-k -> all-gather -> merge inside the library, then the device->host copy
+// of the GLOBAL result into the batch's staging; fg_batch_collect hands it out. Collective.
+extern "C" int32_t fg_batch_submit_sharded(fg_batch* b, fg_comm* comm, uint32_t flags, uint32_t k_stride) {
+    if (!b || !comm) return fail(FG_ERR_INVALID, "fg_batch_submit_sharded: NULL argument");
+    if (k_stride < b->kcap) return fail(FG_ERR_INVALID, "k_stride %u < max k %u", k_stride, b->kcap);
+    if (b->d_out) return fail(FG_ERR_INVALID, "fg_batch_submit_sharded: batch already submitted");
+    fg_ctx* ctx = b->ix->ctx;
+    CU(cudaSetDevice(ctx->device));
+    const size_t nq = b->n_queries;
+    b->sub_k_stride = k_stride;
+    b->sub_counts = false;
+    if (nq == 0) return FG_OK;
+    const size_t hits_b = nq * k_stride * sizeof(fg_hit);
+    b->out_sz = hits_b + 2 * nq * 4;
+    CU(pool_alloc(ctx, &b->d_out, b->out_sz));
+    CU(pinned_alloc(ctx, &b->h_out, b->out_sz));
+    char* d = (char*)b->d_out;
+    int32_t rc = fg_batch_execute_sharded(b, comm, flags, k_stride, d, d + hits_b);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    CU(cudaMemcpyAsync(b->h_out, b->d_out, hits_b + nq * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaEventRecord(b->ev_done, ctx->stream));
+    return FG_OK;
+}
+
 extern "C" int32_t fg_batch_collect(fg_batch* b, fg_hit* out_hits, uint32_t* out_n_hits, uint32_t* out_match_count) {
     if (!b || !out_hits || !out_n_hits) return fail(FG_ERR_INVALID, "fg_batch_collect: NULL argument");
     const size_t nq = b->n_queries;
@@ -2389,6 +2414,37 @@ extern "C" void fg_comm_destroy(fg_comm* c) {
     cudaFree(c->d_gather);
     cudaFree(c->d_tmp);
     delete c;
+}
+extern "C" int32_t fg_comm_info(const fg_comm* c, int32_t* rank, int32_t* n_ranks) {
+    if (!c) return fail(FG_ERR_INVALID, "fg_comm_info: NULL communicator");
+    if (rank) *rank = c->rank;
+    if (n_ranks) *n_ranks = c->world;
+    return FG_OK;
+}
+// all-gather of `bytes` bytes per rank, HOST buffers (staged through the device like the all-reduce); collective
+extern "C" int32_t fg_comm_allgather_bytes(fg_comm* c, const void* send, size_t bytes, void* recv) {
+    if (!c || (bytes && (!send || !recv))) return fail(FG_ERR_INVALID, "fg_comm_allgather_bytes: NULL argument");
+    if (bytes == 0) return FG_OK;
+    fg_ctx* ctx = c->ctx;
+    CU(cudaSetDevice(ctx->device));
+    std::lock_guard<std::mutex> g(ctx->mu);
+    const size_t need = bytes * ((size_t)c->world + 1);
+    if (c->tmp_sz < need) {
+        CU(cudaStreamSynchronize(ctx->stream));
+        cudaFree(c->d_tmp);
+        c->d_tmp = nullptr;
+        c->tmp_sz = 0;
+        CU(cudaMalloc(&c->d_tmp, need + (need >> 1)));
+        c->tmp_sz = need + (need >> 1);
+    }
+    char* d_send = (char*)c->d_tmp;
+    char* d_recv = d_send + bytes;
+    cudaStream_t st = ctx->stream;
+    CU(cudaMemcpyAsync(d_send, send, bytes, cudaMemcpyHostToDevice, st));
+    NC(nccl_api().AllGather(d_send, d_recv, bytes, ncclUint8, c->comm, st));
+    CU(cudaMemcpyAsync(recv, d_recv, bytes * c->world, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return FG_OK;
 }
 static int32_t comm_allreduce(fg_comm* c, void* values, size_t n, size_t elem, ncclDataType_t dt) {
     if (!c || (n && !values)) return fail(FG_ERR_INVALID, "fg_comm_allreduce: NULL argument");

@@ -57,6 +57,9 @@ struct DevApi {
     FGH_DEV_FN(fg_batch_prepare_ex);
     FGH_DEV_FN(fg_batch_query_status);
     FGH_DEV_FN(fg_batch_submit);
+    FGH_DEV_FN(fg_batch_submit_sharded);
+    FGH_DEV_FN(fg_comm_info);
+    FGH_DEV_FN(fg_comm_allgather_bytes);
     FGH_DEV_FN(fg_batch_collect);
     FGH_DEV_FN(fg_batch_release);
 #undef FGH_DEV_FN
@@ -93,6 +96,9 @@ const DevApi& dev_api() {
         FGH_DEV_BIND(fg_batch_prepare_ex);
         FGH_DEV_BIND(fg_batch_query_status);
         FGH_DEV_BIND(fg_batch_submit);
+        FGH_DEV_BIND(fg_batch_submit_sharded);
+        FGH_DEV_BIND(fg_comm_info);
+        FGH_DEV_BIND(fg_comm_allgather_bytes);
         FGH_DEV_BIND(fg_batch_collect);
         FGH_DEV_BIND(fg_batch_release);
 #undef FGH_DEV_BIND
@@ -1179,11 +1185,79 @@ extern "C" int32_t fgh_plan_batch(const fgh_dataset* ds, uint32_t n, const char*
     return FG_OK;
 }
 
-extern "C" int32_t fgh_search_batch(fgh_dataset* ds, uint32_t n, const char* const* queries,
-                                    const char* const* filters, const uint32_t* filter_offsets,
-                                    const uint32_t* pages, const uint32_t* per_pages, uint32_t stride,
-                                    fg_hit* out_hits, uint32_t* out_n, uint32_t* out_match_count,
-                                    int32_t* status) {
+namespace {
+// Sharded datasets (one process per GPU, fg_comm): every rank is handed the same request. Planning does not depend on
+// the shard (term ordinals and statistics are global), so each rank plans 1/n_ranks of the queries and the plans are
+// all-gathered (two small collectives: sizes, then the padded arrays); lowering is per shard.
+int32_t plan_batch_shared(const fgh_dataset* ds, fg_comm* comm, uint32_t n, const char* const* queries, const char* const* filters,
+                          const uint32_t* filter_offsets, const uint32_t* pages, const uint32_t* per_pages, PlannedBatch& pb) {
+    int32_t rank = 0, world = 1;
+    if (comm) D(dev_api().fg_comm_info(comm, &rank, &world));
+    if (world <= 1 || n < (uint32_t)world * 32u) {
+        plan_batch(ds, n, queries, filters, filter_offsets, pages, per_pages, pb);
+        return FG_OK;
+    }
+    const uint32_t a = (uint32_t)((uint64_t)n * rank / world), b = (uint32_t)((uint64_t)n * (rank + 1) / world);
+    PlannedBatch mine;
+    plan_batch(ds, b - a, queries + a, filters, filter_offsets ? filter_offsets + a : nullptr, pages ? pages + a : nullptr,
+               per_pages ? per_pages + a : nullptr, mine);
+    struct Hdr { uint32_t nq, nc, nl; int32_t first_err; };
+    const Hdr h{b - a, (uint32_t)mine.c.size(), (uint32_t)mine.l.size(), mine.first_err};
+    std::vector<Hdr> hs((size_t)world);
+    if (int32_t rc = D(dev_api().fg_comm_allgather_bytes(comm, &h, sizeof(h), hs.data()))) return rc;
+    uint32_t mq = 0, mc = 0, ml = 0;
+    for (const Hdr& x : hs) { mq = std::max(mq, x.nq); mc = std::max(mc, x.nc); ml = std::max(ml, x.nl); }
+    // one fixed-size record per rank: [queries | offsets | status | clauses | leaves], padded to the largest rank
+    const size_t o_off = (size_t)mq * sizeof(fg_query), o_rc = o_off + (size_t)mq * 4, o_c = o_rc + (size_t)mq * 4,
+                 o_l = o_c + (size_t)mc * sizeof(fg_clause), rec = ((o_l + (size_t)ml * sizeof(fg_leaf)) + 15) & ~(size_t)15;
+    std::vector<char> send(rec, 0), recv(rec * (size_t)world);
+    if (h.nq) {
+        memcpy(send.data(), mine.q.data(), (size_t)h.nq * sizeof(fg_query));
+        memcpy(send.data() + o_off, mine.offset.data(), (size_t)h.nq * 4);
+        memcpy(send.data() + o_rc, mine.rc.data(), (size_t)h.nq * 4);
+    }
+    if (h.nc) memcpy(send.data() + o_c, mine.c.data(), (size_t)h.nc * sizeof(fg_clause));
+    if (h.nl) memcpy(send.data() + o_l, mine.l.data(), (size_t)h.nl * sizeof(fg_leaf));
+    if (int32_t rc = D(dev_api().fg_comm_allgather_bytes(comm, send.data(), rec, recv.data()))) return rc;
+    pb.q.clear(); pb.c.clear(); pb.l.clear(); pb.offset.clear(); pb.rc.clear();
+    pb.kmax = 1;
+    pb.first_err = FG_OK;
+    for (int r = 0; r < world; r++) {
+        const char* p = recv.data() + rec * (size_t)r;
+        const Hdr& x = hs[(size_t)r];
+        const uint32_t cb = (uint32_t)pb.c.size(), lb = (uint32_t)pb.l.size();
+        const fg_query* q = reinterpret_cast<const fg_query*>(p);
+        const uint32_t* off = reinterpret_cast<const uint32_t*>(p + o_off);
+        const int32_t* rc = reinterpret_cast<const int32_t*>(p + o_rc);
+        const fg_clause* c = reinterpret_cast<const fg_clause*>(p + o_c);
+        const fg_leaf* l = reinterpret_cast<const fg_leaf*>(p + o_l);
+        for (uint32_t i = 0; i < x.nq; i++) {
+            fg_query qq = q[i];
+            qq.clause_begin += cb;
+            pb.q.push_back(qq);
+            pb.offset.push_back(off[i]);
+            pb.rc.push_back(rc[i]);
+            pb.kmax = std::max(pb.kmax, qq.k);
+        }
+        for (uint32_t i = 0; i < x.nc; i++) {
+            fg_clause cc = c[i];
+            cc.leaf_begin += lb;
+            pb.c.push_back(cc);
+        }
+        pb.l.insert(pb.l.end(), l, l + x.nl);
+        if (x.first_err && !pb.first_err) {
+            pb.first_err = x.first_err;
+            pb.first_msg = r == rank ? mine.first_msg : std::string("a query of the request failed to plan (planned by rank ") + std::to_string(r) + ")";
+        }
+    }
+    return FG_OK;
+}
+
+int32_t search_batch_impl(fgh_dataset* ds, fg_comm* comm, uint32_t n, const char* const* queries,
+                          const char* const* filters, const uint32_t* filter_offsets,
+                          const uint32_t* pages, const uint32_t* per_pages, uint32_t stride,
+                          fg_hit* out_hits, uint32_t* out_n, uint32_t* out_match_count,
+                          int32_t* status) {
     if (!ds || (n && (!queries || !out_hits || !out_n))) return host_fail(FG_ERR_INVALID, "fgh_search_batch: NULL argument");
     const std::shared_ptr<fg_index> snap = current_snapshot(ds);  // held until the results are collected
     if (!snap) return host_fail(ds->ctx ? FG_ERR_INVALID : FG_ERR_NO_DEVICE, "dataset has no device snapshot (commit first)");
@@ -1192,7 +1266,7 @@ extern "C" int32_t fgh_search_batch(fgh_dataset* ds, uint32_t n, const char* con
     // evaluated without per-warp queues: every match above the running threshold is kept and the page is selected
     // afterwards, which costs list space for every query of the batch they are in. They are rare: answer each one in a
     // batch of its own and the rest together.
-    if (n > 1) {
+    if (n > 1 && !comm) {
         std::vector<uint32_t> deep, rest;
         for (uint32_t i = 0; i < n; i++) {
             const uint64_t limit = (uint64_t)(pages ? pages[i] : 0) * (per_pages ? per_pages[i] : 20) + (per_pages ? per_pages[i] : 20);
@@ -1215,8 +1289,8 @@ extern "C" int32_t fgh_search_batch(fgh_dataset* ds, uint32_t n, const char* con
                         for (uint32_t x = filter_offsets[i]; x < filter_offsets[i + 1]; x++) f.push_back(filters[x]);
                     fo[j + 1] = (uint32_t)f.size();
                 }
-                const int32_t rc = fgh_search_batch(ds, m, q.data(), f.empty() ? nullptr : f.data(), fo.data(), pg.data(), pp.data(), stride, hits.data(),
-                                                    nh.data(), out_match_count ? cnt.data() : nullptr, status ? st.data() : nullptr);
+                const int32_t rc = search_batch_impl(ds, nullptr, m, q.data(), f.empty() ? nullptr : f.data(), fo.data(), pg.data(), pp.data(), stride, hits.data(),
+                                                     nh.data(), out_match_count ? cnt.data() : nullptr, status ? st.data() : nullptr);
                 if (rc) return rc;
                 for (uint32_t j = 0; j < m; j++) {
                     const uint32_t i = idx[j];
@@ -1249,6 +1323,16 @@ extern "C" int32_t fgh_search_batch(fgh_dataset* ds, uint32_t n, const char* con
     if (const char* e = getenv("FG_PIPELINE_FIRST")) first_frac = std::min(0.9, std::max(0.05, atof(e)));
     struct Chunk { uint32_t a, b; PlannedBatch pb; fg_batch* batch = nullptr; };
     std::vector<Chunk> ch(nch);
+    // Sharded: the whole request is planned first, shared among the ranks (the exchange of the plans is a collective on
+    // the context's stream: between chunks it would queue up behind the previous chunk's kernels); the chunks then only
+    // lower and submit.
+    PlannedBatch whole;
+    const bool planned_whole = comm != nullptr;
+    if (planned_whole) {
+        if (int32_t prc = plan_batch_shared(ds, comm, n, queries, filters, filter_offsets, pages, per_pages, whole)) return prc;
+        if (status) memcpy(status, whole.rc.data(), n * sizeof(int32_t));
+        if (whole.first_err && !status) return host_fail(whole.first_err, "%s", whole.first_msg.c_str());
+    }
     struct Cleanup {
         std::vector<Chunk>& c;
         ~Cleanup() { for (auto& x : c) if (x.batch) dev_api().fg_batch_release(x.batch); }
@@ -1271,18 +1355,30 @@ extern "C" int32_t fgh_search_batch(fgh_dataset* ds, uint32_t n, const char* con
         C.a = cut(i);
         C.b = cut(i + 1);
         const uint32_t m = C.b - C.a;
-        plan_batch(ds, m, queries + C.a, filters, filter_offsets ? filter_offsets + C.a : nullptr,
-                   pages ? pages + C.a : nullptr, per_pages ? per_pages + C.a : nullptr, C.pb);
-        if (status) memcpy(status + C.a, C.pb.rc.data(), m * sizeof(int32_t));
-        if (C.pb.first_err && !status) return host_fail(C.pb.first_err, "%s", C.pb.first_msg.c_str());  // single-status callers see the first failure
         fg_query_batch qb;
         memset(&qb, 0, sizeof(qb));
         qb.n_queries = m;
-        qb.n_clauses = (uint32_t)C.pb.c.size();
-        qb.n_leaves = (uint32_t)C.pb.l.size();
-        qb.queries = C.pb.q.data();
-        qb.clauses = C.pb.c.data();
-        qb.leaves = C.pb.l.data();
+        if (planned_whole) {  // a slice of the request's plan (its queries index the request's clause / leaf arrays)
+            C.pb.rc.assign(whole.rc.begin() + C.a, whole.rc.begin() + C.b);
+            C.pb.offset.assign(whole.offset.begin() + C.a, whole.offset.begin() + C.b);
+            C.pb.kmax = 1;
+            for (uint32_t j = C.a; j < C.b; j++) C.pb.kmax = std::max(C.pb.kmax, whole.q[j].k);
+            qb.n_clauses = (uint32_t)whole.c.size();
+            qb.n_leaves = (uint32_t)whole.l.size();
+            qb.queries = whole.q.data() + C.a;
+            qb.clauses = whole.c.data();
+            qb.leaves = whole.l.data();
+        } else {
+            plan_batch(ds, m, queries + C.a, filters, filter_offsets ? filter_offsets + C.a : nullptr,
+                       pages ? pages + C.a : nullptr, per_pages ? per_pages + C.a : nullptr, C.pb);
+            if (status) memcpy(status + C.a, C.pb.rc.data(), m * sizeof(int32_t));
+            if (C.pb.first_err && !status) return host_fail(C.pb.first_err, "%s", C.pb.first_msg.c_str());  // single-status callers see the first failure
+            qb.n_clauses = (uint32_t)C.pb.c.size();
+            qb.n_leaves = (uint32_t)C.pb.l.size();
+            qb.queries = C.pb.q.data();
+            qb.clauses = C.pb.c.data();
+            qb.leaves = C.pb.l.data();
+        }
         const double t1 = now_ms();
         // The TopDocs form (no match counts: what the reference's collector does) runs on the lead-driven kernels,
         // which prune; match counts need every matching document visited, which is what the windowed accumulator
@@ -1303,7 +1399,8 @@ extern "C" int32_t fgh_search_batch(fgh_dataset* ds, uint32_t n, const char* con
         }
         const double t2 = now_ms();
         // match counts are optional: the reference's TopDocs collector does not count (src/db/search.rs:162)
-        r = D(dev_api().fg_batch_submit(C.batch, 0, C.pb.kmax, out_match_count ? 1 : 0));
+        r = comm ? D(dev_api().fg_batch_submit_sharded(C.batch, comm, 0, C.pb.kmax))
+                 : D(dev_api().fg_batch_submit(C.batch, 0, C.pb.kmax, out_match_count ? 1 : 0));
         if (r) return r;
         t_plan += t1 - t0; t_prep += t2 - t1; t_sub += now_ms() - t2;
     }
@@ -1332,6 +1429,24 @@ extern "C" int32_t fgh_search_batch(fgh_dataset* ds, uint32_t n, const char* con
         fprintf(stderr, "[fgh_search_batch] n=%u chunks=%u: plan %.2f prepare %.2f submit %.2f | all submitted at %.2f, done at %.2f ms\n",
                 n, nch, t_plan, t_prep, t_sub, t_submitted - t_start, now_ms() - t_start);
     return FG_OK;
+}
+
+}  // namespace
+
+extern "C" int32_t fgh_search_batch(fgh_dataset* ds, uint32_t n, const char* const* queries,
+                                    const char* const* filters, const uint32_t* filter_offsets,
+                                    const uint32_t* pages, const uint32_t* per_pages, uint32_t stride,
+                                    fg_hit* out_hits, uint32_t* out_n, uint32_t* out_match_count,
+                                    int32_t* status) {
+    return search_batch_impl(ds, nullptr, n, queries, filters, filter_offsets, pages, per_pages, stride, out_hits, out_n, out_match_count, status);
+}
+
+extern "C" int32_t fgh_search_batch_sharded(fgh_dataset* ds, fg_comm* comm, uint32_t n, const char* const* queries,
+                                            const char* const* filters, const uint32_t* filter_offsets,
+                                            const uint32_t* pages, const uint32_t* per_pages, uint32_t stride,
+                                            fg_hit* out_hits, uint32_t* out_n, int32_t* status) {
+    if (!comm) return host_fail(FG_ERR_INVALID, "fgh_search_batch_sharded: NULL communicator");
+    return search_batch_impl(ds, comm, n, queries, filters, filter_offsets, pages, per_pages, stride, out_hits, out_n, nullptr, status);
 }
 
 extern "C" int32_t fgh_search(fgh_dataset* ds, const char* query, const char* const* filters, uint32_t n_filters,

@@ -51,7 +51,7 @@ class Plan(C.Structure):
 HOST_SYMBOLS = [
     "fgh_last_error", "fgh_dataset_create", "fgh_dataset_destroy", "fgh_dataset_upsert", "fgh_dataset_delete", "fgh_dataset_commit", "fgh_dataset_commit_counts",
     "fgh_dataset_adopt", "fgh_dataset_num_docs", "fgh_dataset_index", "fgh_dataset_doc_id", "fgh_dataset_term_ord",
-    "fgh_tokenize", "fgh_plan", "fgh_plan_batch", "fgh_search", "fgh_search_batch",
+    "fgh_tokenize", "fgh_plan", "fgh_plan_batch", "fgh_search", "fgh_search_batch", "fgh_search_batch_sharded",
     "fgh_facet_children", "fgh_facet_counts",
     "fgh_batcher_create", "fgh_batcher_destroy", "fgh_batcher_search", "fgh_batcher_get_stats",
 ]
@@ -84,6 +84,7 @@ def _L():
         L.fgh_plan_batch.argtypes = [vp, u32, cpp, cpp, vp, vp, vp, vp, vp, u32, vp, u32, C.POINTER(u32), C.POINTER(u32), vp]
         L.fgh_search.argtypes = [vp, C.c_char_p, cpp, u32, u32, u32, vp, vp, vp]
         L.fgh_search_batch.argtypes = [vp, u32, cpp, cpp, vp, vp, vp, u32, vp, vp, vp, vp]
+        L.fgh_search_batch_sharded.argtypes = [vp, vp, u32, cpp, cpp, vp, vp, vp, u32, vp, vp, vp]
         for fn in (L.fgh_facet_children, L.fgh_facet_counts):
             fn.argtypes = [vp, C.c_char_p, u32, vp, u32, vp, u32, C.POINTER(u32), C.POINTER(u32)]
         L.fgh_batcher_create.argtypes = [vp, u32, u32, C.POINTER(vp)]
@@ -436,6 +437,19 @@ class Dataset:
                                         qs.pages.ctypes.data, qs.pps.ctypes.data, per_page, hits.ctypes.data, nh.ctypes.data,
                                         None if cnt is None else cnt.ctypes.data, status.ctypes.data))
         return hits, nh, cnt, status
+
+    def search_batch_sharded(self, comm, queries, filters: list[list[str]] | None = None, page: int = 0, per_page: int = 20):
+        """Collective form for doc-id-range shards (one process per GPU): (hits[n, per_page], n_hits[n], status[n]) of
+        the GLOBAL result on every rank."""
+        qs = queries if isinstance(queries, QuerySet) else QuerySet(queries, filters, page, per_page)
+        n, per_page = qs.n, qs.per_page
+        hits = np.zeros((n, per_page), nat.HIT_DT)
+        nh = np.zeros(n, np.uint32)
+        status = np.zeros(n, np.int32)
+        nat.hcheck(_L().fgh_search_batch_sharded(self.h, comm.h, n, qs.qarr, qs.farr, None if qs.foffs is None else qs.foffs.ctypes.data,
+                                                qs.pages.ctypes.data, qs.pps.ctypes.data, per_page, hits.ctypes.data, nh.ctypes.data,
+                                                status.ctypes.data))
+        return hits, nh, status
 
     # ---- facets (src/db/facet.rs) -----------------------------------------------------------
     def _facets(self, fn, root: str, max_depth: int) -> list[tuple[str, int, int]]:

@@ -280,6 +280,13 @@ int32_t fg_comm_allreduce_sum_u32(fg_comm* comm, uint32_t* values, size_t n);
  * d_hits [n_queries*k_stride] fg_hit and d_n_hits [n_queries] are DEVICE pointers receiving the GLOBAL result on
  * every rank; asynchronous on the context's stream. Every rank must pass a batch prepared from the same queries. */
 int32_t fg_batch_execute_sharded(fg_batch* b, fg_comm* comm, uint32_t flags, uint32_t k_stride, void* d_hits, void* d_n_hits);
+/* fg_batch_submit for a sharded index (collective): local top-k -> all-gather -> merge, then the device->host copy of
+ * the GLOBAL result into the batch's staging; returns at once, fg_batch_collect (out_match_count NULL) hands it out. */
+int32_t fg_batch_submit_sharded(fg_batch* b, fg_comm* comm, uint32_t flags, uint32_t k_stride);
+int32_t fg_comm_info(const fg_comm* comm, int32_t* rank, int32_t* n_ranks);
+/* all-gather of `bytes` bytes per rank between HOST buffers (recv holds n_ranks * bytes, in rank order); collective.
+ * The host layer shares the planning of a request among the ranks with it. */
+int32_t fg_comm_allgather_bytes(fg_comm* comm, const void* send, size_t bytes, void* recv);
 
 /* ---- scoring helpers shared with the host planner (tantivy fieldnorm / Bm25Weight) ---------- */
 uint8_t fg_fieldnorm_to_id(uint32_t num_tokens);

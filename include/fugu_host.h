@@ -134,6 +134,18 @@ int32_t fgh_search_batch(fgh_dataset* ds, uint32_t n, const char* const* queries
                          uint32_t per_page_stride, fg_hit* out_hits, uint32_t* out_n,
                          uint32_t* out_match_count, int32_t* status);
 
+/* The same request against a dataset whose documents are sharded over several GPUs, one process per GPU
+ * (fg_comm in fugu_gpu.h): a COLLECTIVE call -- every rank passes the same queries and gets the
+ * same, global, result. The ranks share the planning (each plans 1/n_ranks of the request, the plans are
+ * all-gathered), every rank lowers the plan for its own shard, and each pipeline chunk ends in the library's fused
+ * exchange (local top-k -> ncclAllGather -> merge). Match counts are not available; a request with a page limit
+ * above 1024 fails with FG_ERR_UNSUPPORTED (deep pages are not merged across shards). The dataset must have been adopted from this rank's shard with the
+ * GLOBAL statistics (fgh_dataset_adopt with fg_index_desc.global_*). */
+int32_t fgh_search_batch_sharded(fgh_dataset* ds, fg_comm* comm, uint32_t n, const char* const* queries,
+                                 const char* const* filters, const uint32_t* filter_offsets, const uint32_t* pages,
+                                 const uint32_t* per_pages, uint32_t per_page_stride, fg_hit* out_hits,
+                                 uint32_t* out_n, int32_t* status);
+
 /* ---- micro-batcher ----------------------------------------------------
  * The reference's HTTP API is one query per request (search_endpoint, src/server/handlers/search.rs:152;
  * query_json_post :210), each request blocking its own worker thread in Dataset::search (src/db/search.rs:74).
