@@ -13,6 +13,8 @@
 //   A.5 boolean scorers (TermScorer, BufferedUnionScorer with a 4096-doc horizon, Intersection
 //                        ordered by cost with leap-frog seeks, RequiredOptionalScorer, Exclude)
 //   A.6 TopDocs         (TopNComputer: 2k buffer + median truncation; score desc, doc asc)
+//   A.5 pruning         (orc_search_batch_pruned: block maxima for unions of plain term scorers, the shape tantivy hands
+//                        to block-max WAND; results identical to the exhaustive scorers, tests/test_oracle_golden.py)
 // and is anchored on hand-computed known-answer vectors under tests/golden/ plus a second,
 // independently written pure-Python twin (oracle/oracle_py.py).
 //
@@ -397,6 +399,131 @@ int run_query(const Index& ix, const fg_query_batch& qb, uint32_t qi, uint32_t k
     return FG_OK;
 }
 
+// ---- block-max pruning for unions of plain term scorers (A.5: BooleanWeight hands a Should-only query whose
+// children are all TermScorers to block-max WAND instead of the buffered union; fugu's two default fields make a
+// single-word query such a union, (text:w OR name:w), while a multi-word query is a union of unions and keeps the
+// buffered union). tantivy's index stores the block-max (fieldnorm id, tf) pair of every 128-doc block in its skip
+// entries; the equivalent here is built once per index (orc_blockmax_build) and only the TopDocs form uses it
+// (counting visits every match). Restated as MaxScore with block maxima: same result set and scores as the exhaustive
+// evaluation (scores are summed in leaf order either way).
+struct BlockMax {
+    // per field: offset of each term's first block in `factor`, then one float per 128 postings = the largest
+    // tf / (tf + cache[fieldnorm id]) of the block under the index's statistics
+    std::vector<std::vector<uint64_t>> term_block0;
+    std::vector<std::vector<float>> factor;
+};
+constexpr size_t PBLOCK = 128;
+
+struct PrunedLeaf {
+    const uint32_t* docs;
+    const uint32_t* tfs;
+    const uint8_t* fn;
+    size_t n, i = 0;
+    const float* bmax;  // per block of 128 postings
+    float w, gmax;      // weight, largest possible score of the list
+    Bm25 bm;
+    uint8_t const_id;
+    float score_at(size_t j) const { return bm.score(fn ? fn[docs[j]] : const_id, tfs ? tfs[j] : 1u); }
+};
+
+bool prunable(const fg_query_batch& qb, const fg_query& q) {
+    if (q.n_clauses == 0) return false;
+    uint32_t multi = 0;
+    for (uint32_t ci = 0; ci < q.n_clauses; ci++) {
+        const fg_clause& c = qb.clauses[q.clause_begin + ci];
+        if (c.occur != FG_OCCUR_SHOULD) return false;
+        for (uint32_t li = 0; li < c.n_leaves; li++)
+            if (qb.leaves[c.leaf_begin + li].term_ord == FG_TERM_ALL || !(qb.leaves[c.leaf_begin + li].boost > 0.f)) return false;
+        if (c.n_leaves > 1) multi++;
+    }
+    // one clause of several leaves (a bare word over the default fields) or several single-leaf clauses: every child of
+    // the top-level union is a term scorer. A clause of several leaves next to other clauses is a union inside a union.
+    return multi == 0 || q.n_clauses == 1;
+}
+
+int run_query_pruned(const Index& ix, const BlockMax& bmx, const fg_query_batch& qb, uint32_t qi, uint32_t k_stride, fg_hit* hits, uint32_t* n_hits) {
+    const fg_query& q = qb.queries[qi];
+    if (q.k == 0) return FG_ERR_INVALID;
+    std::vector<PrunedLeaf> L;
+    for (uint32_t ci = 0; ci < q.n_clauses; ci++) {
+        const fg_clause& c = qb.clauses[q.clause_begin + ci];
+        for (uint32_t li = 0; li < c.n_leaves; li++) {
+            const fg_leaf& lf = qb.leaves[c.leaf_begin + li];
+            if (lf.term_ord == FG_TERM_MISSING) continue;
+            const fg_field_desc& f = ix.fields[lf.field];
+            const uint64_t a = f.term_offsets[lf.term_ord], b = f.term_offsets[lf.term_ord + 1];
+            const uint64_t gdf = f.global_doc_freq ? f.global_doc_freq[lf.term_ord] : (b - a);
+            if (gdf == 0 || a == b) continue;
+            const bool freqs = (f.flags & FG_FIELD_HAS_FREQS) && f.term_freqs;
+            const bool norms = (f.flags & FG_FIELD_HAS_FIELDNORMS) && f.fieldnorm_ids;
+            PrunedLeaf p{f.doc_ids + a, freqs ? f.term_freqs + a : nullptr, norms ? f.fieldnorm_ids : nullptr, (size_t)(b - a), 0,
+                         bmx.factor[lf.field].data() + bmx.term_block0[lf.field][lf.term_ord], 0.f, 0.f,
+                         Bm25(lf.boost, gdf, ix.global_n_docs, f.total_num_tokens), fieldnorm_to_id(1)};
+            p.w = p.bm.weight;
+            float mx = 0.f;
+            for (size_t blk = 0; blk < (p.n + PBLOCK - 1) / PBLOCK; blk++) mx = std::max(mx, p.bmax[blk]);
+            p.gmax = p.w * mx * 1.00001f;  // (bounds carry a relative slack: the block maxima were computed in another expression order)
+            L.push_back(p);
+        }
+    }
+    const size_t m = L.size();
+    // MaxScore over the lists, shortest first: list i offers the docs none of the shorter lists holds (those are scored
+    // when their list is walked), looked up in the longer ones; a block of list i is skipped when
+    // w_i * bmax_i(block) + the maxima of the longer lists cannot reach the threshold. The hit collector does not depend
+    // on the order docs arrive in ((score, doc) decides), and a doc's score is summed in leaf order as the union does.
+    std::vector<size_t> order(m);
+    for (size_t i = 0; i < m; i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](size_t x, size_t y) { return L[x].n < L[y].n; });
+    TopN top(q.k);
+    std::vector<size_t> cur(m);
+    std::vector<float> part(m);
+    for (size_t oi = 0; oi < m; oi++) {
+        PrunedLeaf& P = L[order[oi]];
+        float rest = 0.f;
+        for (size_t oj = oi + 1; oj < m; oj++) rest += L[order[oj]].gmax;
+        for (size_t j = 0; j < m; j++) cur[j] = 0;
+        const size_t nblk = (P.n + PBLOCK - 1) / PBLOCK;
+        for (size_t blk = 0; blk < nblk; blk++) {
+            if (top.has_thr && P.w * P.bmax[blk] * 1.00001f + rest < top.thr.score) continue;
+            const size_t e = std::min(P.n, (blk + 1) * PBLOCK);
+            for (size_t x = blk * PBLOCK; x < e; x++) {
+                const uint32_t d = P.docs[x];
+                bool owned = false;  // a shorter list holds d
+                for (size_t oj = 0; oj < m; oj++) part[order[oj]] = 0.f;
+                for (size_t oj = 0; oj < m && !owned; oj++) {
+                    if (oj == oi) { part[order[oi]] = P.score_at(x); continue; }
+                    PrunedLeaf& Q = L[order[oj]];
+                    size_t& c = cur[order[oj]];
+                    // gallop from the cursor (docs of P ascend)
+                    size_t step = 1, lo = c, hi = c;
+                    while (hi < Q.n && Q.docs[hi] < d) { lo = hi; hi = std::min(Q.n, hi + step); step <<= 1; }
+                    c = (size_t)(std::lower_bound(Q.docs + lo, Q.docs + hi, d) - Q.docs);
+                    if (c < Q.n && Q.docs[c] == d) {
+                        if (oj < oi) owned = true;
+                        else part[order[oj]] = Q.score_at(c);
+                    }
+                }
+                if (owned || !ix.is_alive(d)) continue;
+                float sc = 0.f;
+                for (size_t j = 0; j < m; j++) sc += part[j];  // (absent leaves add +0: the sum equals the union's)
+                top.push(sc, d);
+            }
+        }
+    }
+    std::vector<Hit> r = top.finish();
+    const uint32_t n = (uint32_t)std::min<size_t>(r.size(), k_stride);
+    for (uint32_t i = 0; i < n; i++) {
+        hits[(size_t)qi * k_stride + i].score = r[i].score;
+        hits[(size_t)qi * k_stride + i].doc = r[i].doc + ix.doc_base;
+    }
+    for (uint32_t i = n; i < k_stride; i++) {
+        hits[(size_t)qi * k_stride + i].score = 0.f;
+        hits[(size_t)qi * k_stride + i].doc = 0xFFFFFFFFu;
+    }
+    n_hits[qi] = n;
+    return FG_OK;
+}
+
 Index make_index(const fg_index_desc* d) {
     Index ix;
     ix.n_docs = d->n_docs;
@@ -540,6 +667,79 @@ int32_t orc_search_batch(const fg_index_desc* d, const fg_query_batch* qb, uint3
             uint32_t qi = next.fetch_add(1);
             if (qi >= qb->n_queries) break;
             int r = run_query(ix, *qb, qi, k_stride, hits, n_hits, counts, match_bitmap, words);
+            if (r != FG_OK) rc.store(r);
+        }
+    };
+    if (n_threads <= 1) work();
+    else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < n_threads; t++) th.emplace_back(work);
+        for (auto& t : th) t.join();
+    }
+    return rc.load();
+}
+
+// Block-max metadata of an index (what tantivy keeps in its skip entries): built once, released with orc_blockmax_free.
+void* orc_blockmax_build(const fg_index_desc* d, int32_t n_threads) {
+    Index ix = make_index(d);
+    BlockMax* bm = new BlockMax();
+    bm->term_block0.resize(ix.fields.size());
+    bm->factor.resize(ix.fields.size());
+    for (size_t f = 0; f < ix.fields.size(); f++) {
+        const fg_field_desc& fd = ix.fields[f];
+        std::vector<uint64_t>& b0 = bm->term_block0[f];
+        b0.resize((size_t)fd.n_terms + 1);
+        uint64_t nb = 0;
+        for (uint32_t t = 0; t < fd.n_terms; t++) {
+            b0[t] = nb;
+            nb += (fd.term_offsets[t + 1] - fd.term_offsets[t] + PBLOCK - 1) / PBLOCK;
+        }
+        b0[fd.n_terms] = nb;
+        bm->factor[f].assign(nb, 0.f);
+        if (!fd.n_terms) continue;
+        const bool freqs = (fd.flags & FG_FIELD_HAS_FREQS) && fd.term_freqs;
+        const bool norms = (fd.flags & FG_FIELD_HAS_FIELDNORMS) && fd.fieldnorm_ids;
+        const Bm25 unit(1.0f, 1, ix.global_n_docs, fd.total_num_tokens);  // (only its norm cache is used)
+        const uint8_t cid = fieldnorm_to_id(1);
+        std::atomic<uint32_t> next(0);
+        auto work = [&]() {
+            while (true) {
+                const uint32_t t0 = next.fetch_add(256);
+                if (t0 >= fd.n_terms) break;
+                for (uint32_t t = t0; t < std::min(fd.n_terms, t0 + 256); t++) {
+                    const uint64_t a = fd.term_offsets[t], b = fd.term_offsets[t + 1];
+                    for (uint64_t i = a; i < b; i++) {
+                        const float tf = (float)(freqs ? fd.term_freqs[i] : 1u);
+                        const float fac = tf / (tf + unit.cache[norms ? fd.fieldnorm_ids[fd.doc_ids[i]] : cid]);
+                        float& slot = bm->factor[f][b0[t] + (i - a) / PBLOCK];
+                        slot = std::max(slot, fac);
+                    }
+                }
+            }
+        };
+        std::vector<std::thread> th;
+        for (int t = 1; t < std::max(1, n_threads); t++) th.emplace_back(work);
+        work();
+        for (auto& t : th) t.join();
+    }
+    return bm;
+}
+void orc_blockmax_free(void* h) { delete (BlockMax*)h; }
+
+// The TopDocs form with block-max pruning where tantivy prunes (unions whose children are all term scorers); every other
+// query runs the exhaustive scorers of orc_search_batch. No match counts (pruning does not visit every match).
+int32_t orc_search_batch_pruned(const fg_index_desc* d, const void* blockmax, const fg_query_batch* qb, uint32_t k_stride,
+                                fg_hit* hits, uint32_t* n_hits, int32_t n_threads) {
+    Index ix = make_index(d);
+    const BlockMax& bm = *(const BlockMax*)blockmax;
+    std::atomic<uint32_t> next(0);
+    std::atomic<int32_t> rc(FG_OK);
+    auto work = [&]() {
+        while (true) {
+            uint32_t qi = next.fetch_add(1);
+            if (qi >= qb->n_queries) break;
+            int r = prunable(*qb, qb->queries[qi]) ? run_query_pruned(ix, bm, *qb, qi, k_stride, hits, n_hits)
+                                                   : run_query(ix, *qb, qi, k_stride, hits, n_hits, nullptr, nullptr, 0);
             if (r != FG_OK) rc.store(r);
         }
     };

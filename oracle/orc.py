@@ -69,8 +69,40 @@ def lib():
         L.orc_search_batch.restype = i32
         L.orc_algorithmic_bytes.argtypes = [C.POINTER(nat.IndexDesc), C.POINTER(nat.QueryBatch), vp, vp, i32]
         L.orc_algorithmic_bytes.restype = i32
+        L.orc_blockmax_build.argtypes = [C.POINTER(nat.IndexDesc), i32]
+        L.orc_blockmax_build.restype = vp
+        L.orc_blockmax_free.argtypes = [vp]
+        L.orc_blockmax_free.restype = None
+        L.orc_search_batch_pruned.argtypes = [C.POINTER(nat.IndexDesc), vp, C.POINTER(nat.QueryBatch), u32, vp, vp, i32]
+        L.orc_search_batch_pruned.restype = i32
         _lib = L
     return _lib
+
+
+class BlockMax:
+    """Block-max metadata of an index (tantivy keeps it in its skip entries): built once per corpus, used by
+    search_pruned."""
+
+    def __init__(self, desc: nat.HostIndexDesc, threads: int = 1):
+        self.desc = desc
+        self.h = lib().orc_blockmax_build(C.byref(desc.desc), threads)
+
+    def close(self):
+        if self.h:
+            lib().orc_blockmax_free(self.h)
+            self.h = None
+
+
+def search_pruned(bm: BlockMax, batch: nat.HostBatch, k_stride: int | None = None, threads: int = 1):
+    """TopDocs form with block-max pruning where tantivy prunes (unions of plain term scorers, e.g. a single word over
+    the two default fields); exhaustive scorers elsewhere. Returns (hits, n_hits)."""
+    ks = k_stride or batch.kmax
+    hits = np.zeros((batch.n_queries, ks), nat.HIT_DT)
+    n = np.zeros(batch.n_queries, np.uint32)
+    rc = lib().orc_search_batch_pruned(C.byref(bm.desc.desc), bm.h, C.byref(batch.batch), ks, hits.ctypes.data, n.ctypes.data, threads)
+    if rc != 0:
+        raise nat.FgError(rc, "oracle")
+    return hits, n
 
 
 def search(desc: nat.HostIndexDesc, batch: nat.HostBatch, k_stride: int | None = None, threads: int = 1,
