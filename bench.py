@@ -629,7 +629,7 @@ def main():
     if not args.no_cpu_baseline:
         from oracle import orc  # cpu_baseline leg: the one place bench.py may run the oracle (as the measured CPU arm)
 
-        odesc = nat.HostIndexDesc(n_local, fields, doc_id_base=d0, global_n_docs=cfg.n_docs) if world > 1 else desc
+        odesc = pdesc  # the whole corpus at every N (at N > 1 rank 0 rebuilt it for the parity check): comparable across N
         cores = host_cores()
         ns = min(nq, 5000)
         sub, _ = ds.plan_batch(QuerySet([q["query"] for q in queries[:ns]], [q["filters"] for q in queries[:ns]], 0, cfg.k))
@@ -649,7 +649,7 @@ def main():
         dt1 = time.perf_counter() - t0
         line["cpu_baseline"] = {"value": ns / best, "unit": "queries/s", "cores": cores, "kind": "port",
                                 "single_thread_qps": max(1, ns // 10) / dt1,
-                                "sample": f"first {ns} queries of the batch on rank 0's shard, best of 3, oracle C++ -O3 -march=native "
+                                "sample": f"first {ns} queries of the batch on the whole corpus, best of 3, oracle C++ -O3 -march=native "
                                           f"(restatement of tantivy 0.24.1 semantics: DAAT scorers; block-max pruning for unions of plain term "
                                           f"scorers, where tantivy runs block-max WAND), {cores} threads; cpu: {cpu_model()}"}
     sys.stdout.flush()

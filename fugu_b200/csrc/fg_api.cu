@@ -1623,7 +1623,7 @@ static int32_t prepare_lead(fg_index* ix, const fg_query_batch* qb, uint32_t pre
     CU(pool_alloc(ctx, (void**)&b->l_state, b->lsz[3]));
     b->sz[3] = std::max<size_t>((size_t)part_entries * 8, 16);
     CU(pool_alloc(ctx, (void**)&b->d_partial, b->sz[3]));
-    b->sz[5] = 16 * sizeof(unsigned long long);
+    b->sz[5] = 32 * sizeof(unsigned long long);
     CU(pool_alloc(ctx, (void**)&b->d_stats, b->sz[5]));
     if (sel_entries) {
         b->sel_sz = (size_t)sel_entries * 8;
@@ -2030,7 +2030,7 @@ extern "C" int32_t fg_batch_execute(fg_batch* b, uint32_t flags, uint32_t k_stri
     std::lock_guard<std::mutex> g(ctx->mu);
     cudaStream_t st = ctx->stream;
     CU(cudaStreamWaitEvent(st, b->ev_up, 0));
-    CU(cudaMemsetAsync(b->d_stats, 0, 16 * sizeof(unsigned long long), st));
+    CU(cudaMemsetAsync(b->d_stats, 0, (b->lead ? 32 : 16) * sizeof(unsigned long long), st));
     if (b->lead) {
         if (flags & FG_EXEC_EXACT_ACCOUNTING)
             return fail(FG_ERR_INVALID, "FG_EXEC_EXACT_ACCOUNTING needs a batch prepared with FG_PREP_LEGACY | FG_PREP_NO_COLUMNS");
@@ -2162,8 +2162,15 @@ extern "C" int32_t fg_batch_get_stats(fg_batch* b, fg_batch_stats* out) {
         CU(cudaMemcpy(h, b->d_stats, sizeof(h), cudaMemcpyDeviceToHost));
     }
     if (ctx->env_prof && b->lead) {
-        unsigned long long pr[8];
+        unsigned long long pr[8], ph[8];
         cudaMemcpy(pr, b->d_stats + 8, sizeof(pr), cudaMemcpyDeviceToHost);
+        cudaMemcpy(ph, b->d_stats + 16, sizeof(ph), cudaMemcpyDeviceToHost);
+        unsigned long long ph_tot = 0;
+        for (int i = 0; i < 8; i++) ph_tot += ph[i];
+        if (ph_tot)  // (only a library built with make PROFILE=1 fills these)
+            fprintf(stderr, "[prof lead phases] %% of warp busy time: plan load %.1f, block walk %.1f, decode %.1f, lookups %.1f, scoring %.1f, "
+                            "top-k + histogram %.1f, append %.1f, other %.1f\n", 100.0 * ph[0] / ph_tot, 100.0 * ph[1] / ph_tot, 100.0 * ph[2] / ph_tot,
+                    100.0 * ph[3] / ph_tot, 100.0 * ph[4] / ph_tot, 100.0 * ph[5] / ph_tot, 100.0 * ph[6] / ph_tot, 100.0 * ph[7] / ph_tot);
         if (pr[4]) {
             const double start = (double)~pr[5], first_idle = (double)~pr[2] - start, done = (double)pr[3] - start;
             fprintf(stderr, "[prof lead] warps %llu: kernel %.1f us, first warp out of work at %.1f us, busy share %.1f %% of warp-time, longest item %.1f us, "

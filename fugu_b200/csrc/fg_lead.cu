@@ -79,6 +79,18 @@ struct Acct {
     unsigned long long lead_blocks = 0, lead_blocks_seen = 0;
 };
 
+// dev tool (make PROFILE=1): time of a warp per phase of run_item, summed into stats[16 + phase] (ns) by lane 0
+#ifdef FG_PROFILE_PHASES
+#define PH_DECL unsigned long long ph_t = global_timer_ns(), ph_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+#define PH_MARK(i) do { const unsigned long long t_ = global_timer_ns(); ph_acc[i] += t_ - ph_t; ph_t = t_; } while (0)
+#define PH_FLUSH() do { if (lane == 0 && p.stats) { for (int i_ = 0; i_ < 8; i_++) atomicAdd(p.stats + 16 + i_, ph_acc[i_]); } } while (0)
+#else
+#define PH_DECL
+#define PH_MARK(i)
+#define PH_FLUSH()
+#endif
+enum { PH_PLAN = 0, PH_WALK = 1, PH_DECODE = 2, PH_LOOKUP = 3, PH_SCORE = 4, PH_TOPK = 5, PH_APPEND = 6, PH_OTHER = 7 };
+
 // First block index in [from, n) whose last_doc >= target; n if there is none. Warp-collective
 // (uniform arguments): the next 32 skip entries first (the common case while candidates and blocks
 // advance together), then a 32-ary search over the rest of the list.
@@ -214,6 +226,7 @@ __device__ __forceinline__ uint32_t probe(const LeadParams& p, WarpShared& W, in
 
 template <int KS, bool TMA>
 __device__ __forceinline__ void run_item(const LeadParams& p, const LeadShared& S, WarpShared& W, StageShared& G, const LItem item, const uint32_t theta_seen, int lane) {
+    PH_DECL;
     const LQuery q = p.queries[item.query];
     __syncwarp();
     {
@@ -224,6 +237,7 @@ __device__ __forceinline__ void run_item(const LeadParams& p, const LeadShared& 
         if (lane < LC) W.ctag[lane] = EMPTY;
     }
     __syncwarp();
+    PH_MARK(PH_PLAN);
     const int k = (int)q.k;
     const bool prune = !p.exhaustive && (q.flags & LQ_PRUNE);
     const bool acct = p.acct != 0;
@@ -385,6 +399,7 @@ __device__ __forceinline__ void run_item(const LeadParams& p, const LeadShared& 
             g0 += 32u;
         }
 
+        PH_MARK(PH_WALK);
         // ================= decode the lead block, keep the postings that can still reach the top-k =================
         if (have) {
             const uint32_t bd = e.w & 63u, bt = (e.w >> 6) & 63u, n = ((e.w >> 12) & 127u) + 1u;
@@ -451,6 +466,7 @@ __device__ __forceinline__ void run_item(const LeadParams& p, const LeadShared& 
             }
         }
 
+        PH_MARK(PH_DECODE);
         // ================= evaluate a round of candidates =================
         // A full round (128: 4 per lane, so every lookup has 4 independent gathers in flight) as soon as it is there;
         // whatever is left when the walk ends. Candidate 32*r + lane of the round belongs to this lane: every r is an
@@ -586,6 +602,7 @@ __device__ __forceinline__ void run_item(const LeadParams& p, const LeadShared& 
                         if (r == 0) tf[0] = t1; else if (r == 1) tf[1] = t1; else if (r == 2) tf[2] = t1; else tf[3] = t1;
                     }
                 }
+                PH_MARK(PH_LOOKUP);
                 // ---- what a hit means ----
                 if (mode == 1) {
 #pragma unroll
@@ -608,7 +625,9 @@ __device__ __forceinline__ void run_item(const LeadParams& p, const LeadShared& 
                 }
 #pragma unroll
                 for (int r = 0; r < 4; r++) tf[r] = 0u;
+                PH_MARK(PH_SCORE);
             }
+            PH_MARK(PH_SCORE);
             if (p.ix.alive) {
 #pragma unroll
                 for (int r = 0; r < 4; r++)
@@ -675,6 +694,7 @@ __device__ __forceinline__ void run_item(const LeadParams& p, const LeadShared& 
                     }
                 }
             }
+            PH_MARK(PH_TOPK);
             // candidates behind the round move to the front
             const uint32_t left = ncand - cnt;
             if (left) {
@@ -709,6 +729,7 @@ __device__ __forceinline__ void run_item(const LeadParams& p, const LeadShared& 
         if (lane == 0) G.bar_parity = st_par;
     }
 
+    PH_MARK(PH_OTHER);
     // append this warp's queue to the query's region of the partial array
     {
         // (the queue is sorted best first; ranks >= k are scratch)
@@ -745,6 +766,8 @@ __device__ __forceinline__ void run_item(const LeadParams& p, const LeadShared& 
             }
         }
     }
+    PH_MARK(PH_APPEND);
+    PH_FLUSH();
 }
 
 template <int KS, bool TMA>

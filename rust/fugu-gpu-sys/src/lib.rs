@@ -103,8 +103,34 @@ extern "C" {
     pub fn fg_fieldnorm_to_id(num_tokens: u32) -> u8;
     pub fn fg_id_to_fieldnorm(id: u8) -> u32;
     pub fn fg_bm25_idf(doc_freq: u64, doc_count: u64) -> f32;
+    // snapshot refresh after a commit that added documents: only the new segment crosses PCIe
+    pub fn fg_index_append(base: *mut fg_index, segment: *const fg_index_desc, alive_bitset: *const u32, out: *mut *mut fg_index) -> i32;
+    // sharded submit (collective), communicator info, host-buffer all-gather (shared planning)
+    pub fn fg_batch_submit_sharded(b: *mut fg_batch, comm: *mut fg_comm, flags: u32, k_stride: u32) -> i32;
+    pub fn fg_comm_info(comm: *const fg_comm, rank: *mut i32, n_ranks: *mut i32) -> i32;
+    pub fn fg_comm_allgather_bytes(comm: *mut fg_comm, send: *const c_void, bytes: usize, recv: *mut c_void) -> i32;
+}
 
-    // include/fugu_host.h: the planning half of Dataset::search + a batched search entry
+#[repr(C)] #[derive(Clone, Copy, Default)]
+pub struct fgh_batcher_stats { pub n_requests: u64, pub n_batches: u64, pub max_batch_seen: u64, pub wait_us_total: u64 }
+opaque!(fgh_batcher);
+
+// libfugu_host.so: no CUDA code; device entry points are bound on first use (FG_ERR_NO_DEVICE when they are missing)
+#[link(name = "fugu_host")]
+extern "C" {
+    pub fn fgh_last_error() -> *const c_char;
+    pub fn fgh_dataset_commit_counts(ds: *const fgh_dataset, n_full_uploads: *mut u64, n_appends: *mut u64) -> i32;
+    pub fn fgh_search_batch_sharded(ds: *mut fgh_dataset, comm: *mut fg_comm, n: u32, queries: *const *const c_char,
+                                    filters: *const *const c_char, filter_offsets: *const u32, pages: *const u32,
+                                    per_pages: *const u32, stride: u32, out_hits: *mut fg_hit, out_n: *mut u32, status: *mut i32) -> i32;
+    // micro-batcher for the one-query-per-request handlers (src/server/handlers/search.rs:152): blocking, any thread
+    pub fn fgh_batcher_create(ds: *mut fgh_dataset, max_batch: u32, max_wait_us: u32, out: *mut *mut fgh_batcher) -> i32;
+    pub fn fgh_batcher_destroy(b: *mut fgh_batcher);
+    pub fn fgh_batcher_search(b: *mut fgh_batcher, query: *const c_char, filters: *const *const c_char, n_filters: u32,
+                              page: u32, per_page: u32, out_hits: *mut fg_hit, out_n: *mut u32) -> i32;
+    pub fn fgh_batcher_get_stats(b: *mut fgh_batcher, out: *mut fgh_batcher_stats) -> i32;
+
+    // include/fugu_host.h (libfugu_host.so): the planning half of Dataset::search + a batched search entry
     pub fn fgh_dataset_create(ctx: *mut fg_ctx, out: *mut *mut fgh_dataset) -> i32;
     pub fn fgh_dataset_destroy(ds: *mut fgh_dataset);
     pub fn fgh_dataset_upsert(ds: *mut fgh_dataset, id: *const c_char, text: *const c_char, name: *const c_char,

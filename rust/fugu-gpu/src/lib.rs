@@ -23,6 +23,7 @@ impl std::error::Error for GpuError {}
 
 pub(crate) fn check(rc: i32) -> Result<(), GpuError> {
     if rc == sys::FG_OK { return Ok(()); }
+    // (calls into libfugu_host.so report through fgh_last_error, which also carries device-library failures)
     let message = unsafe { CStr::from_ptr(sys::fg_last_error()) }.to_string_lossy().into_owned();
     Err(GpuError { code: rc, message })
 }
