@@ -358,17 +358,11 @@ static int32_t compute_block_max(fg_index* ix, uint64_t n_blocks, int T) {
     ix->arena->allocs.push_back(d_bmax);
     ix->info.device_bytes += n_blocks * 4;
     ix->dev.bmax = d_bmax;
-    // (tf, fieldnorm id) of every posting slot, written by the same pass (DevIndex::tfn)
-    uint16_t* d_tfn = nullptr;
-    CU(cudaMalloc((void**)&d_tfn, std::max<size_t>(n_blocks * BLOCK * sizeof(uint16_t), 16) + 16));
-    ix->arena->allocs.push_back(d_tfn);
-    ix->info.device_bytes += n_blocks * BLOCK * sizeof(uint16_t);
-    ix->dev.tfn = d_tfn;
     for (uint32_t f = 0; f < n_fields; f++) {
         const HostField& hf = ix->fields[f];
         if (hf.terms.empty()) continue;
         const uint32_t b0 = hf.terms.front().blk_begin, b1 = hf.terms.back().blk_begin + hf.terms.back().n_blocks;
-        launch_blockmax(ix->dev, b0, b1, (hf.flags & FG_FIELD_HAS_FIELDNORMS) ? (int)f : -1, hf.cnorm, d_bmax, d_tfn, ctx->stream);
+        launch_blockmax(ix->dev, b0, b1, (hf.flags & FG_FIELD_HAS_FIELDNORMS) ? (int)f : -1, hf.cnorm, d_bmax, ctx->stream);
     }
     CU(cudaGetLastError());
     std::vector<float> bm(n_blocks);

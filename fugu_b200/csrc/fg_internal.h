@@ -88,9 +88,6 @@ struct DevItem {
 struct DevIndex {
     const uint4* skip;
     const float* bmax;   // per block: max over its postings of tf / (tf + norm(doc)) (block-max metadata)
-    const uint16_t* tfn; // per posting slot (128 per block, slot = block * 128 + position): tf | fieldnorm id << 8; tf byte 0 =
-                         // the term frequency does not fit a byte (read it from the block). What a scorer needs about a
-                         // posting in one 2-byte load: a lead block's 128 slots are one coalesced 256-byte row
     const uint8_t* blk;
     const uint8_t* fnorm[MAX_FIELDS];
     const float* cache;  // [MAX_FIELDS][256]
@@ -270,8 +267,8 @@ void launch_lead_merge(const LeadMergeParams& p, int ks, void* stream);
 // merge of all-gathered per-rank lists with per-query k (word k_word of the q_words-word query records at qrec)
 void launch_merge_ranks(const void* hits, const uint32_t* n, uint32_t n_ranks, uint32_t n_queries, const void* qrec, uint32_t q_words,
                         uint32_t k_word, uint32_t k_stride, void* out_hits, uint32_t* out_n, int ks, void* stream);
-// block-max metadata and (tf, fieldnorm id) slots of the blocks [b0, b1) of one field (upload time)
-void launch_blockmax(const DevIndex& ix, uint32_t b0, uint32_t b1, int fn_field, float cnorm, float* bmax, uint16_t* tfn, void* stream);
+// block-max metadata of the blocks [b0, b1) of one field (upload time)
+void launch_blockmax(const DevIndex& ix, uint32_t b0, uint32_t b1, int fn_field, float cnorm, float* bmax, void* stream);
 // membership bitmaps + rank directories of selected terms (upload time): sel[i] = {global block, bitmap slot};
 // bits is zeroed by the caller, stride_words is a multiple of 8
 void launch_bitmap_build(const DevIndex& ix, const uint2* sel, uint32_t n_sel, uint32_t* bits, uint64_t stride_words, void* stream);

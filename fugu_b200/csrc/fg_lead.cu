@@ -1047,7 +1047,7 @@ __global__ void __launch_bounds__(128) merge_ranks_kernel(const uint2* __restric
 
 // block-max metadata: one warp per block, the same arithmetic as the scoring path
 __global__ void __launch_bounds__(256) blockmax_kernel(const DevIndex ix, uint32_t b0, uint32_t b1, int fn_field,
-                                                       float cnorm, float* bmax, uint16_t* tfn) {
+                                                       float cnorm, float* bmax) {
     const int lane = threadIdx.x & 31;
     const uint32_t b = b0 + blockIdx.x * 8u + (threadIdx.x >> 5);
     if (b >= b1) return;
@@ -1060,19 +1060,14 @@ __global__ void __launch_bounds__(256) blockmax_kernel(const DevIndex ix, uint32
     g[1] += g[0]; g[2] += g[1]; g[3] += g[2];
     const uint32_t off = warp_excl_scan(g[3], lane) + e.y + 4u * lane;
     float best = 0.f;
-    uint32_t slot[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
     for (int j = 0; j < 4; j++) {
         if (4u * lane + (uint32_t)j < n) {
             const uint32_t d = off + g[j] + (uint32_t)j;
-            const uint32_t id = fn_field >= 0 ? (uint32_t)__ldg(ix.fnorm[fn_field] + d) : 0u;
-            const float nrm = fn_field >= 0 ? __ldg(ix.cache + fn_field * 256 + (int)id) : cnorm;
+            const float nrm = fn_field >= 0 ? __ldg(ix.cache + fn_field * 256 + (int)__ldg(ix.fnorm[fn_field] + d)) : cnorm;
             best = fmaxf(best, tf_factor((float)(t[j] + 1u), nrm));
-            slot[j] = (t[j] + 1u <= 255u ? t[j] + 1u : 0u) | (id << 8);
         }
     }
-    // the block's 128 (tf, fieldnorm id) slots: one 8-byte store per lane (slots behind the last posting are 0)
-    reinterpret_cast<uint2*>(tfn + ((size_t)b << 7))[lane] = make_uint2(slot[0] | (slot[1] << 16), slot[2] | (slot[3] << 16));
 #pragma unroll
     for (int o = 16; o; o >>= 1) best = fmaxf(best, __shfl_xor_sync(FULL, best, o));
     if (lane == 0) bmax[b] = best;
@@ -1245,9 +1240,9 @@ void launch_merge_ranks(const void* hits, const uint32_t* n, uint32_t n_ranks, u
                   k_stride, (uint2*)out_hits, out_n);
 }
 
-void launch_blockmax(const DevIndex& ix, uint32_t b0, uint32_t b1, int fn_field, float cnorm, float* bmax, uint16_t* tfn, void* stream) {
+void launch_blockmax(const DevIndex& ix, uint32_t b0, uint32_t b1, int fn_field, float cnorm, float* bmax, void* stream) {
     if (b1 <= b0) return;
-    FG_LAUNCH(blockmax_kernel, (b1 - b0 + 7) / 8, 256, 0, (cudaStream_t)stream, ix, b0, b1, fn_field, cnorm, bmax, tfn);
+    FG_LAUNCH(blockmax_kernel, (b1 - b0 + 7) / 8, 256, 0, (cudaStream_t)stream, ix, b0, b1, fn_field, cnorm, bmax);
 }
 
 }  // namespace fg
