@@ -563,7 +563,7 @@ def main():
         print("e2e_times ms", [round(x * 1e3, 2) for x in e2e_times], file=sys.stderr)
     if dist:
         e2e_s = float(xch.allreduce_cpu(np.array([e2e_s], np.float64), "max")[0])
-    lowered_bytes = nq * 48 + len(batch.l) * 48 + st_touched.n_work_items * 16  # LQuery + LLeaf + LItem arrays
+    lowered_bytes = st_touched.plan_bytes  # the lowered plan as uploaded: LQuery + LLeaf arrays + work-item records
     out_bytes = nq * k * 8 + nq * 8
 
     def shutdown():

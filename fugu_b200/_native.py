@@ -116,6 +116,7 @@ class BatchStats(C.Structure):
         ("bytes_meta", C.c_uint64),
         ("lead_blocks", C.c_uint64),
         ("lead_blocks_seen", C.c_uint64),
+        ("plan_bytes", C.c_uint64),
     ]
 
 

@@ -1151,7 +1151,7 @@ struct fg_batch {
     uint32_t n_cursors = 0;
     uint64_t partial_entries = 0;
     size_t lsz[4] = {0, 0, 0, 0};
-    void* d_plan = nullptr;        // one device block [LQuery | LLeaf | LItem] (l_queries / l_leaves / l_items point into it)
+    void* d_plan = nullptr;        // one device block [LQuery | LLeaf | LItemRec] (l_queries / l_leaves point into it; l_items is expanded from the records on the device)
     void* h_plan = nullptr;        // its page-locked source (kept until release: the upload is asynchronous)
     size_t plan_sz = 0;
     uint64_t* d_sel = nullptr;     // deep-page batches (ks == 0): scratch of lead_select_kernel
@@ -1185,6 +1185,7 @@ extern "C" void fg_batch_release(fg_batch* b) {
         pool_free(c, b->d_plan, b->plan_sz);
         pinned_free(c, b->h_plan, b->plan_sz);
         pool_free(c, b->l_state, b->lsz[3]);
+        pool_free(c, b->l_items, b->lsz[2]);
         pool_free(c, b->d_sel, b->sel_sz);
     }
     for (auto& e : b->ev) if (e) cudaEventDestroy(e);
@@ -1201,8 +1202,10 @@ extern "C" void fg_batch_release(fg_batch* b) {
 constexpr int LKEYS = 16 * 32;  // item sort keys: lead index (clamped to 15), then list length (log2)
 struct LeadPart {
     std::vector<LLeaf> leaves;
-    std::vector<LItem> items;       // cursor = index of the (query, lead) pair inside this part
+    std::vector<LItem> items;       // one per (query, lead group); cursor = index of the (query, lead) pair inside this part
     std::vector<uint32_t> item_key; // sort key: lead index, then list length
+    std::vector<uint32_t> item_copies;  // copies of the item in the queue (a long lead is walked by several warps)
+    uint64_t n_item_copies = 0;
     std::vector<uint32_t> q_items;  // items per query of this part
     uint32_t key_count[LKEYS];
     uint32_t n_cursors = 0, kmax = 1;
@@ -1210,9 +1213,9 @@ struct LeadPart {
     int32_t rc = FG_OK;
     std::string err;
     void reset() {
-        leaves.clear(); items.clear(); item_key.clear(); q_items.clear();
+        leaves.clear(); items.clear(); item_key.clear(); item_copies.clear(); q_items.clear();
         memset(key_count, 0, sizeof(key_count));
-        n_cursors = 0; kmax = 1; sum_k = 0; rc = FG_OK; err.clear();
+        n_cursors = 0; kmax = 1; sum_k = 0; rc = FG_OK; err.clear(); n_item_copies = 0;
     }
 };
 struct LeadScratch {
@@ -1497,11 +1500,11 @@ static int32_t prepare_lead(fg_index* ix, const fg_query_batch* qb, uint32_t pre
                 float item_bound = -INFINITY;  // (only meaningful when the bounds hold: LQ_PRUNE)
                 for (int l = i; l < j; l++) item_bound = std::max(item_bound, o.leaves[l0 + l].ub + o.leaves[l0 + l].rest + bound_slack);
                 if (!positive) item_bound = INFINITY;
-                for (uint32_t c = 0; c < par; c++) {
-                    o.items.push_back(LItem{qi, (uint32_t)i | ((uint32_t)j << 16), o.n_cursors, item_bound});
-                    o.item_key.push_back(key);
-                    o.key_count[key]++;
-                }
+                o.items.push_back(LItem{qi, (uint32_t)i | ((uint32_t)j << 16), o.n_cursors, item_bound});
+                o.item_key.push_back(key);
+                o.item_copies.push_back(par);
+                o.key_count[key] += par;
+                o.n_item_copies += par;
                 o.n_cursors += (uint32_t)(j - i);
                 qitems += par;
                 i = j;
@@ -1538,13 +1541,14 @@ static int32_t prepare_lead(fg_index* ix, const fg_query_batch* qb, uint32_t pre
     std::vector<uint32_t> leaf_base((size_t)LT + 1, 0), cur_base((size_t)LT + 1, 0);
     std::vector<uint32_t> key_start((size_t)LT * LKEYS);
     uint32_t kmax = 1;
-    uint64_t sum_k = 0, part_entries = 0, ni_tot = 0, sel_entries = 0;
+    uint64_t sum_k = 0, part_entries = 0, ni_tot = 0, nrec_tot = 0, sel_entries = 0;
     for (int t = 0; t < LT; t++) {
         leaf_base[t + 1] = leaf_base[t] + (uint32_t)parts[t].leaves.size();
         cur_base[t + 1] = cur_base[t] + parts[t].n_cursors;
         kmax = std::max(kmax, parts[t].kmax);
         sum_k += parts[t].sum_k;
-        ni_tot += parts[t].items.size();
+        ni_tot += parts[t].n_item_copies;
+        nrec_tot += parts[t].items.size();
     }
     {
         uint32_t run = 0;
@@ -1580,8 +1584,11 @@ static int32_t prepare_lead(fg_index* ix, const fg_query_batch* qb, uint32_t pre
     const uint32_t n_cursors = cur_base[LT];
     const size_t nl_tot = leaf_base[LT];
     const size_t off_leaves = ((size_t)qb->n_queries * sizeof(LQuery) + 255) & ~(size_t)255;
-    const size_t off_items = (off_leaves + nl_tot * sizeof(LLeaf) + 255) & ~(size_t)255;
-    const size_t plan_bytes = off_items + ni_tot * sizeof(LItem) + 256;
+    // uploaded: [LQuery | LLeaf | LItemRec]; the item array itself (one entry per copy) is written on the device
+    const size_t off_recs = (off_leaves + nl_tot * sizeof(LLeaf) + 255) & ~(size_t)255;
+    const size_t plan_bytes = off_recs + nrec_tot * sizeof(LItemRec) + 256;
+    std::vector<uint32_t> rec_base((size_t)LT + 1, 0);
+    for (int t = 0; t < LT; t++) rec_base[t + 1] = rec_base[t] + (uint32_t)parts[t].items.size();
 
     CU(cudaSetDevice(ctx->device));
     std::unique_ptr<fg_batch, void (*)(fg_batch*)> b(new fg_batch(), fg_batch_release);
@@ -1604,12 +1611,13 @@ static int32_t prepare_lead(fg_index* ix, const fg_query_batch* qb, uint32_t pre
     HostPool::get().run(LT, [&](int t) {
         Part& o = parts[t];
         if (!o.leaves.empty()) memcpy(hp + off_leaves + (size_t)leaf_base[t] * sizeof(LLeaf), o.leaves.data(), o.leaves.size() * sizeof(LLeaf));
-        LItem* items = reinterpret_cast<LItem*>(hp + off_items);
+        LItemRec* recs = reinterpret_cast<LItemRec*>(hp + off_recs) + rec_base[t];  // (sequential writes: the queue order is in `dst`)
         uint32_t* pos = key_start.data() + (size_t)t * LKEYS;
         for (size_t i = 0; i < o.items.size(); i++) {
-            LItem it = o.items[i];
-            it.cursor += cur_base[t];
-            items[pos[o.item_key[i]]++] = it;
+            LItemRec r{o.items[i], pos[o.item_key[i]], o.item_copies[i]};
+            r.item.cursor += cur_base[t];
+            pos[o.item_key[i]] += o.item_copies[i];
+            recs[i] = r;
         }
     });
     const double t_lowered = now_ms();
@@ -1618,7 +1626,9 @@ static int32_t prepare_lead(fg_index* ix, const fg_query_batch* qb, uint32_t pre
     CU(cudaMemcpyAsync(b->d_plan, b->h_plan, plan_bytes, cudaMemcpyHostToDevice, ctx->up));
     b->l_queries = reinterpret_cast<LQuery*>((char*)b->d_plan);
     b->l_leaves = reinterpret_cast<LLeaf*>((char*)b->d_plan + off_leaves);
-    b->l_items = reinterpret_cast<LItem*>((char*)b->d_plan + off_items);
+    b->lsz[2] = std::max<size_t>(ni_tot * sizeof(LItem), 16);
+    CU(pool_alloc(ctx, (void**)&b->l_items, b->lsz[2]));
+    launch_expand_items(reinterpret_cast<const LItemRec*>((char*)b->d_plan + off_recs), (uint32_t)nrec_tot, b->l_items, ctx->up);
     b->lsz[3] = ((size_t)4 + n_cursors + (3 + (size_t)LHIST_B) * (size_t)b->n_queries) * 4 + 32;
     CU(pool_alloc(ctx, (void**)&b->l_state, b->lsz[3]));
     b->sz[3] = std::max<size_t>((size_t)part_entries * 8, 16);
@@ -2194,6 +2204,7 @@ extern "C" int32_t fg_batch_get_stats(fg_batch* b, fg_batch_stats* out) {
     out->lead_blocks = b->lead ? h[6] : 0;
     out->lead_blocks_seen = b->lead ? h[7] : 0;
     out->n_work_items = b->n_items;
+    out->plan_bytes = b->plan_sz;
     out->n_launches = b->n_launches;
     out->n_queries = b->n_queries;
     out->sum_k = b->sum_k;

@@ -220,6 +220,18 @@ struct LItem {
     float bound;      // no document this item can offer scores above it (max over its leads of ub + rest + slack): an
                       // item whose bound is below the query's threshold is skipped before its plan is even loaded
 };
+// Work items as the host writes them: one record per (query, lead group) with the number of copies the queue holds of it
+// (a long lead is walked by several warps sharing its block cursor) and the position of the first copy in the device's
+// item array; expand_items_kernel writes the copies. (A 5000-query C2 batch has 183 k items but 28 k records: the host
+// neither writes nor uploads the copies.)
+struct LItemRec {
+    LItem item;
+    uint32_t dst;     // index of the first copy in the item array
+    uint32_t copies;
+};
+static_assert(sizeof(LItemRec) == 24, "LItemRec is uploaded as a flat array");
+void launch_expand_items(const LItemRec* recs, uint32_t n_recs, LItem* items, void* stream);
+
 struct LeadParams {
     DevIndex ix;
     const LQuery* queries;

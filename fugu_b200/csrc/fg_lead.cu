@@ -1124,6 +1124,16 @@ __global__ void __launch_bounds__(256) bitmap_rank_kernel(const uint32_t* __rest
     }
 }
 
+// one warp per item record: the copies of the item, at their place in the queue
+__global__ void __launch_bounds__(256) expand_items_kernel(const LItemRec* __restrict__ recs, uint32_t n_recs, LItem* items) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t i = blockIdx.x * 8u + (threadIdx.x >> 5);
+    if (i >= n_recs) return;
+    const LItemRec r = recs[i];
+    const uint4 v = make_uint4(r.item.query, r.item.lead, r.item.cursor, __float_as_uint(r.item.bound));
+    for (uint32_t c = lane; c < r.copies; c += 32u) reinterpret_cast<uint4*>(items)[r.dst + c] = v;
+}
+
 // ---- snapshot append (fg_index_append) ----
 // one warp per listed block: its skip entry's (last_doc, first_base) and its decoded postings (doc ids and tfs,
 // 128 slots each; slots >= n undefined) go to a staging buffer the host reads back
@@ -1161,6 +1171,10 @@ __global__ void __launch_bounds__(256) copy_ranges_kernel(const uint4* __restric
 
 }  // namespace
 
+void launch_expand_items(const LItemRec* recs, uint32_t n_recs, LItem* items, void* stream) {
+    if (!n_recs) return;
+    FG_LAUNCH(expand_items_kernel, (n_recs + 7) / 8, 256, 0, (cudaStream_t)stream, recs, n_recs, items);
+}
 void launch_tail_decode(const DevIndex& ix, const uint32_t* blocks, uint32_t n_list, uint32_t* out_meta, uint32_t* out_docs, uint32_t* out_tfs, void* stream) {
     if (!n_list) return;
     FG_LAUNCH(tail_decode_kernel, (n_list + 7) / 8, 256, 0, (cudaStream_t)stream, ix, blocks, n_list, out_meta, out_docs, out_tfs);

@@ -248,6 +248,7 @@ typedef struct {
     uint64_t bytes_meta;       /* block-max words and skip entries read while skipping / galloping */
     uint64_t lead_blocks;      /* lead blocks decoded ... */
     uint64_t lead_blocks_seen; /* ... of the lead blocks whose block maximum was tested */
+    uint64_t plan_bytes;       /* bytes of the lowered plan fg_batch_prepare uploaded (queries, leaves, work-item records) */
 } fg_batch_stats;
 /* synchronises the stream and reads the device counters of the last fg_batch_execute */
 int32_t fg_batch_get_stats(fg_batch* b, fg_batch_stats* out);
