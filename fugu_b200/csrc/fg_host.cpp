@@ -440,6 +440,27 @@ struct TermDict {
         }
         return FG_TERM_MISSING;
     }
+    // find() with the hash already computed (one word is looked up in several dictionaries), and a prefetch of the
+    // slot the probe will start at: the planner issues the prefetches of all words of a query before it resolves any
+    // (a lookup is three dependent cache misses: table slot, entry, pooled string)
+    void prefetch_slot(uint64_t hv) const {
+        if (!table.empty()) __builtin_prefetch(&table[hv & (table.size() - 1)]);
+    }
+    void prefetch_entry(uint64_t hv) const {
+        if (table.empty()) return;
+        const uint32_t t = table[hv & (table.size() - 1)];
+        if (t) __builtin_prefetch(&ents[t - 1]);
+    }
+    uint32_t find_hashed(uint64_t hv, const char* s, size_t n) const {
+        if (table.empty()) return FG_TERM_MISSING;
+        size_t m = table.size() - 1, h = hv & m;
+        while (table[h]) {
+            const Ent& e = ents[table[h] - 1];
+            if (e.len == n && memcmp(pool.data() + e.off, s, n) == 0) return e.ord;
+            h = (h + 1) & m;
+        }
+        return FG_TERM_MISSING;
+    }
     void insert(const char* s, size_t n, uint32_t ord) {
         if ((ents.size() + 1) * 2 > table.size()) rehash((ents.size() + 1) * 4);
         ents.push_back({(uint64_t)pool.size(), (uint32_t)n, ord});
@@ -482,6 +503,10 @@ struct fgh_dataset {
     mutable std::shared_mutex mu;
     uint32_t lookup(uint32_t field, const char* s, size_t n) const {
         const uint32_t o = f[field].dict.find(s, n);
+        return (o != FG_TERM_MISSING && ctx && o >= committed_terms[field]) ? FG_TERM_MISSING : o;
+    }
+    uint32_t lookup_hashed(uint32_t field, uint64_t hv, const char* s, size_t n) const {
+        const uint32_t o = f[field].dict.find_hashed(hv, s, n);
         return (o != FG_TERM_MISSING && ctx && o >= committed_terms[field]) ? FG_TERM_MISSING : o;
     }
     FieldBuild f[3];
@@ -1091,18 +1116,32 @@ bool plan_fast(const fgh_dataset* ds, const char* q, uint32_t page, uint32_t per
     out.k = (uint32_t)limit;
     out.clause_begin = (uint32_t)c0;
     offset = page * per_page;
-    char low[40];
-    for (int i = 0; i < nw; i += conj ? 2 : 1) {
+    // lower-case all words and hash them first, start the table-slot loads of both dictionaries for every word, then
+    // the entry loads, and only then resolve: the cache misses of a query's lookups overlap instead of queueing up
+    char low[16][40];
+    uint64_t hv[16];
+    const int step = conj ? 2 : 1;
+    const TermDict &dt = ds->f[FGH_FIELD_TEXT].dict, &dn = ds->f[FGH_FIELD_NAME].dict;
+    for (int i = 0; i < nw; i += step) {
         for (uint32_t j = 0; j < words[i].n; j++) {
             const char ch = words[i].p[j];
-            low[j] = (ch >= 'A' && ch <= 'Z') ? (char)(ch + 32) : ch;
+            low[i][j] = (ch >= 'A' && ch <= 'Z') ? (char)(ch + 32) : ch;
         }
+        hv[i] = TermDict::hash(low[i], words[i].n);
+        dt.prefetch_slot(hv[i]);
+        dn.prefetch_slot(hv[i]);
+    }
+    for (int i = 0; i < nw; i += step) {
+        dt.prefetch_entry(hv[i]);
+        dn.prefetch_entry(hv[i]);
+    }
+    for (int i = 0; i < nw; i += step) {
         fg_clause cl;
         cl.occur = conj ? FG_OCCUR_MUST : FG_OCCUR_SHOULD;
         cl.leaf_begin = (uint32_t)l.size();
         cl.n_leaves = 2;
-        l.push_back({FGH_FIELD_TEXT, ds->lookup(FGH_FIELD_TEXT, low, words[i].n), 1.f});
-        l.push_back({FGH_FIELD_NAME, ds->lookup(FGH_FIELD_NAME, low, words[i].n), 1.f});
+        l.push_back({FGH_FIELD_TEXT, ds->lookup_hashed(FGH_FIELD_TEXT, hv[i], low[i], words[i].n), 1.f});
+        l.push_back({FGH_FIELD_NAME, ds->lookup_hashed(FGH_FIELD_NAME, hv[i], low[i], words[i].n), 1.f});
         c.push_back(cl);
     }
     out.n_clauses = (uint32_t)(c.size() - c0);
@@ -1149,18 +1188,47 @@ void plan_batch(const fgh_dataset* ds, uint32_t n, const char* const* queries, c
             }
         }
     };
+    static const bool timing = getenv("FG_TIMING") != nullptr;
+    timespec ts0, ts1, ts2;
+    if (timing) clock_gettime(CLOCK_MONOTONIC, &ts0);
     fg::HostPool::get().run(T, work);
-    // concatenate the per-thread parts (clause / leaf indices become global)
+    if (timing) clock_gettime(CLOCK_MONOTONIC, &ts1);
+    // concatenate the per-thread parts (clause / leaf indices become global): offsets first, then every thread copies its own part
+    std::vector<uint32_t> cb((size_t)T + 1, 0), lb((size_t)T + 1, 0);
     for (int t = 0; t < T; t++) {
+        cb[t + 1] = cb[t] + (uint32_t)parts[t].c.size();
+        lb[t + 1] = lb[t] + (uint32_t)parts[t].l.size();
+    }
+    pb.c.resize(cb[T]);
+    pb.l.resize(lb[T]);
+    std::vector<uint32_t> kmax_t((size_t)T, 1);
+    fg::HostPool::get().run(T, [&](int t) {
         Part& P = parts[t];
-        const uint32_t cb = (uint32_t)pb.c.size(), lb = (uint32_t)pb.l.size();
-        for (auto cl : P.c) { cl.leaf_begin += lb; pb.c.push_back(cl); }
-        pb.l.insert(pb.l.end(), P.l.begin(), P.l.end());
-        for (uint32_t i = P.a; i < P.b; i++) {
-            pb.q[i].clause_begin += cb;
-            pb.kmax = std::max(pb.kmax, pb.q[i].k);
-            if (pb.rc[i] != FG_OK && !pb.first_err) { pb.first_err = pb.rc[i]; pb.first_msg = P.errs[i - P.a]; }
+        fg_clause* dc = pb.c.data() + cb[t];
+        for (size_t i = 0; i < P.c.size(); i++) {
+            fg_clause cl = P.c[i];
+            cl.leaf_begin += lb[t];
+            dc[i] = cl;
         }
+        if (!P.l.empty()) memcpy(pb.l.data() + lb[t], P.l.data(), P.l.size() * sizeof(fg_leaf));
+        uint32_t km = 1;
+        for (uint32_t i = P.a; i < P.b; i++) {
+            pb.q[i].clause_begin += cb[t];
+            km = std::max(km, pb.q[i].k);
+        }
+        kmax_t[t] = km;
+    });
+    for (int t = 0; t < T; t++) {
+        pb.kmax = std::max(pb.kmax, kmax_t[t]);
+        if (pb.first_err) continue;
+        Part& P = parts[t];
+        for (uint32_t i = P.a; i < P.b; i++)
+            if (pb.rc[i] != FG_OK) { pb.first_err = pb.rc[i]; pb.first_msg = P.errs[i - P.a]; break; }
+    }
+    if (timing) {
+        clock_gettime(CLOCK_MONOTONIC, &ts2);
+        fprintf(stderr, "[plan_batch] n=%u threads=%d: parallel %.3f ms, concatenation %.3f ms\n", n, T,
+                (ts1.tv_sec - ts0.tv_sec) * 1e3 + (ts1.tv_nsec - ts0.tv_nsec) * 1e-6, (ts2.tv_sec - ts1.tv_sec) * 1e3 + (ts2.tv_nsec - ts1.tv_nsec) * 1e-6);
     }
 }
 }  // namespace
