@@ -1269,24 +1269,50 @@ int32_t plan_batch_shared(const fgh_dataset* ds, fg_comm* comm, uint32_t n, cons
     PlannedBatch mine;
     plan_batch(ds, b - a, queries + a, filters, filter_offsets ? filter_offsets + a : nullptr, pages ? pages + a : nullptr,
                per_pages ? per_pages + a : nullptr, mine);
-    struct Hdr { uint32_t nq, nc, nl; int32_t first_err; };
-    const Hdr h{b - a, (uint32_t)mine.c.size(), (uint32_t)mine.l.size(), mine.first_err};
+    // One collective in the common case: every rank sends a fixed-size record sized for plain word queries (<= 4 clauses
+    // and 8 leaves per query) with its array lengths in a header; a rank whose plans do not fit says so in the header
+    // and all ranks repeat the exchange with records sized for the largest rank.
+    struct Hdr { uint32_t nq, nc, nl; int32_t first_err; uint32_t overflow, pad[3]; };
+    const uint32_t mq = (n + (uint32_t)world - 1) / (uint32_t)world;
     std::vector<Hdr> hs((size_t)world);
-    if (int32_t rc = D(dev_api().fg_comm_allgather_bytes(comm, &h, sizeof(h), hs.data()))) return rc;
-    uint32_t mq = 0, mc = 0, ml = 0;
-    for (const Hdr& x : hs) { mq = std::max(mq, x.nq); mc = std::max(mc, x.nc); ml = std::max(ml, x.nl); }
-    // one fixed-size record per rank: [queries | offsets | status | clauses | leaves], padded to the largest rank
-    const size_t o_off = (size_t)mq * sizeof(fg_query), o_rc = o_off + (size_t)mq * 4, o_c = o_rc + (size_t)mq * 4,
-                 o_l = o_c + (size_t)mc * sizeof(fg_clause), rec = ((o_l + (size_t)ml * sizeof(fg_leaf)) + 15) & ~(size_t)15;
-    std::vector<char> send(rec, 0), recv(rec * (size_t)world);
-    if (h.nq) {
-        memcpy(send.data(), mine.q.data(), (size_t)h.nq * sizeof(fg_query));
-        memcpy(send.data() + o_off, mine.offset.data(), (size_t)h.nq * 4);
-        memcpy(send.data() + o_rc, mine.rc.data(), (size_t)h.nq * 4);
+    std::vector<char> send, recv;
+    size_t o_off = 0, o_rc = 0, o_c = 0, o_l = 0, rec = 0;
+    auto exchange = [&](uint32_t mc, uint32_t ml) -> int32_t {
+        // record: [header | queries | offsets | status | clauses | leaves], padded to the capacities
+        const size_t o_q = sizeof(Hdr);
+        o_off = o_q + (size_t)mq * sizeof(fg_query);
+        o_rc = o_off + (size_t)mq * 4;
+        o_c = o_rc + (size_t)mq * 4;
+        o_l = o_c + (size_t)mc * sizeof(fg_clause);
+        rec = ((o_l + (size_t)ml * sizeof(fg_leaf)) + 15) & ~(size_t)15;
+        send.assign(rec, 0);
+        recv.resize(rec * (size_t)world);
+        Hdr h{b - a, (uint32_t)mine.c.size(), (uint32_t)mine.l.size(), mine.first_err, 0u, {0u, 0u, 0u}};
+        h.overflow = (h.nc > mc || h.nl > ml) ? 1u : 0u;
+        memcpy(send.data(), &h, sizeof(h));
+        if (!h.overflow) {
+            if (h.nq) {
+                memcpy(send.data() + o_q, mine.q.data(), (size_t)h.nq * sizeof(fg_query));
+                memcpy(send.data() + o_off, mine.offset.data(), (size_t)h.nq * 4);
+                memcpy(send.data() + o_rc, mine.rc.data(), (size_t)h.nq * 4);
+            }
+            if (h.nc) memcpy(send.data() + o_c, mine.c.data(), (size_t)h.nc * sizeof(fg_clause));
+            if (h.nl) memcpy(send.data() + o_l, mine.l.data(), (size_t)h.nl * sizeof(fg_leaf));
+        }
+        if (int32_t rc = D(dev_api().fg_comm_allgather_bytes(comm, send.data(), rec, recv.data()))) return rc;
+        for (int r = 0; r < world; r++) memcpy(&hs[(size_t)r], recv.data() + rec * (size_t)r, sizeof(Hdr));
+        return FG_OK;
+    };
+    static const bool force_small = getenv("FG_PLAN_EXCHANGE_SMALL") != nullptr;  // dev: exercise the repeat path
+    if (int32_t rc = exchange(force_small ? 1u : 4u * mq, force_small ? 1u : 8u * mq)) return rc;
+    {
+        bool any_overflow = false;
+        uint32_t mc = 0, ml = 0;
+        for (const Hdr& x : hs) { any_overflow = any_overflow || x.overflow; mc = std::max(mc, x.nc); ml = std::max(ml, x.nl); }
+        if (any_overflow)  // (every rank sees the same headers: all of them repeat)
+            if (int32_t rc = exchange(mc, ml)) return rc;
     }
-    if (h.nc) memcpy(send.data() + o_c, mine.c.data(), (size_t)h.nc * sizeof(fg_clause));
-    if (h.nl) memcpy(send.data() + o_l, mine.l.data(), (size_t)h.nl * sizeof(fg_leaf));
-    if (int32_t rc = D(dev_api().fg_comm_allgather_bytes(comm, send.data(), rec, recv.data()))) return rc;
+    const size_t o_q = sizeof(Hdr);
     pb.q.clear(); pb.c.clear(); pb.l.clear(); pb.offset.clear(); pb.rc.clear();
     pb.kmax = 1;
     pb.first_err = FG_OK;
@@ -1294,7 +1320,7 @@ int32_t plan_batch_shared(const fgh_dataset* ds, fg_comm* comm, uint32_t n, cons
         const char* p = recv.data() + rec * (size_t)r;
         const Hdr& x = hs[(size_t)r];
         const uint32_t cb = (uint32_t)pb.c.size(), lb = (uint32_t)pb.l.size();
-        const fg_query* q = reinterpret_cast<const fg_query*>(p);
+        const fg_query* q = reinterpret_cast<const fg_query*>(p + o_q);
         const uint32_t* off = reinterpret_cast<const uint32_t*>(p + o_off);
         const int32_t* rc = reinterpret_cast<const int32_t*>(p + o_rc);
         const fg_clause* c = reinterpret_cast<const fg_clause*>(p + o_c);

@@ -35,7 +35,9 @@ for r in rows[2:]:
             lines.append(f"    {'sectors per global-load request (32 B sectors; 4 = a fully coalesced 32-bit warp load)':90s} {s_ / q_:16.2f}")
     for c in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
         i = H.index(c)
-        dram += float(r[i]) * scale.get(U[i], 1.0)
+        v = float(r[i])
+        if v == v:  # (a kernel whose metric passes were cut short reports nan)
+            dram += v * scale.get(U[i], 1.0)
 n_launch = len([r for r in rows[2:] if len(r) == len(H)])
 open(out + ".txt", "w").write("\n".join(lines) + f"\n\nDRAM bytes (read + write) over the {n_launch} captured launches: {dram:.0f}\n")
 if key:
