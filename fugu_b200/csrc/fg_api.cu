@@ -115,7 +115,7 @@ struct fg_ctx {
     bool env_no_prune = false;    // FG_NO_PRUNE=1: exhaustive evaluation (A/B runs; results are identical)
     bool env_timing = false;      // FG_TIMING=1
     bool env_prof = false;        // FG_PROF=1
-    uint32_t lead_par_blocks = 16, lead_max_par = 64, lead_chunk = 16, lead_tma = 0, lead_chunk_req = 48, lead_par_blocks_req = 2, lead_max_par_req = 1024, lead_union_work = 32;
+    uint32_t lead_par_blocks = 16, lead_max_par = 64, lead_chunk = 16, lead_tma = 0, lead_chunk_req = 48, lead_max_par_req = 1024, lead_union_work = 32;
 };
 static uint64_t env_u64_early(const char* name, uint64_t dflt);
 
@@ -202,7 +202,6 @@ extern "C" int32_t fg_ctx_create(int32_t device, fg_ctx** out) {
     c->lead_max_par = (uint32_t)std::max<uint64_t>(1, env_u64_early("FG_LEAD_MAX_PAR", 64));
     c->lead_chunk = (uint32_t)std::max<uint64_t>(1, env_u64_early("FG_LEAD_CHUNK", 16));
     c->lead_chunk_req = (uint32_t)std::max<uint64_t>(1, env_u64_early("FG_LEAD_REQ_WORK", 48));
-    c->lead_par_blocks_req = (uint32_t)std::max<uint64_t>(1, env_u64_early("FG_LEAD_PAR_BLOCKS_REQ", 2));
     c->lead_max_par_req = (uint32_t)std::max<uint64_t>(1, env_u64_early("FG_LEAD_MAX_PAR_REQ", 1024));
     c->lead_union_work = (uint32_t)std::max<uint64_t>(1, env_u64_early("FG_LEAD_UNION_WORK", 32));
     c->lead_tma = (uint32_t)env_u64_early("FG_LEAD_TMA", 0);
@@ -763,6 +762,12 @@ extern "C" int32_t fg_index_with_alive(fg_index* base, const uint32_t* alive_bit
 // Which terms own a column or a bitmap is decided at full uploads only (a term crossing a threshold later is
 // served from its blocks until the next one; a column term whose new tf exceeds a byte loses its column).
 namespace {
+struct DevTmp {  // scratch device buffer of a build step: freed on every path out of the scope
+    void* p = nullptr;
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, std::max<size_t>(bytes, 16)); }
+    template <class T> T* as() const { return static_cast<T*>(p); }
+    ~DevTmp() { if (p) cudaFree(p); }
+};
 struct NewBlocks {  // new blocks of one touched term, encoded on the host
     std::vector<SkipEntry> skips;
     std::vector<uint32_t> words;  // payload, 4 * (bd + bt) words per block
@@ -880,20 +885,19 @@ extern "C" int32_t fg_index_append(fg_index* base, const fg_index_desc* seg, con
     // ---- last blocks of the touched terms: (last_doc, first_base) and, for partial ones, their postings ----
     std::vector<uint32_t> h_meta(2 * decode_list.size()), h_docs((size_t)BLOCK * decode_list.size()), h_tfs((size_t)BLOCK * decode_list.size());
     if (!decode_list.empty()) {
-        uint32_t *d_list = nullptr, *d_meta = nullptr, *d_docs = nullptr, *d_tfs = nullptr;
+        DevTmp t_list, t_meta, t_docs, t_tfs;
         const size_t nl = decode_list.size();
-        CU(cudaMalloc((void**)&d_list, nl * 4));
-        CU(cudaMalloc((void**)&d_meta, nl * 8));
-        CU(cudaMalloc((void**)&d_docs, nl * BLOCK * 4));
-        CU(cudaMalloc((void**)&d_tfs, nl * BLOCK * 4));
-        cudaMemcpyAsync(d_list, decode_list.data(), nl * 4, cudaMemcpyHostToDevice, ctx->stream);
-        launch_tail_decode(base->dev, d_list, (uint32_t)nl, d_meta, d_docs, d_tfs, ctx->stream);
-        cudaMemcpyAsync(h_meta.data(), d_meta, nl * 8, cudaMemcpyDeviceToHost, ctx->stream);
-        cudaMemcpyAsync(h_docs.data(), d_docs, nl * BLOCK * 4, cudaMemcpyDeviceToHost, ctx->stream);
-        cudaMemcpyAsync(h_tfs.data(), d_tfs, nl * BLOCK * 4, cudaMemcpyDeviceToHost, ctx->stream);
-        const cudaError_t e1 = cudaStreamSynchronize(ctx->stream);
-        cudaFree(d_list); cudaFree(d_meta); cudaFree(d_docs); cudaFree(d_tfs);
-        CU(e1);
+        CU(t_list.alloc(nl * 4));
+        CU(t_meta.alloc(nl * 8));
+        CU(t_docs.alloc(nl * BLOCK * 4));
+        CU(t_tfs.alloc(nl * BLOCK * 4));
+        CU(cudaMemcpyAsync(t_list.p, decode_list.data(), nl * 4, cudaMemcpyHostToDevice, ctx->stream));
+        launch_tail_decode(base->dev, t_list.as<uint32_t>(), (uint32_t)nl, t_meta.as<uint32_t>(), t_docs.as<uint32_t>(), t_tfs.as<uint32_t>(), ctx->stream);
+        CU(cudaMemcpyAsync(h_meta.data(), t_meta.p, nl * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(h_docs.data(), t_docs.p, nl * BLOCK * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(h_tfs.data(), t_tfs.p, nl * BLOCK * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        CU(cudaGetLastError());
     }
 
     // ---- encode the new blocks of every touched term (parallel): old partial tail + the segment's postings ----
@@ -980,19 +984,16 @@ extern "C" int32_t fg_index_append(fg_index* base, const fg_index_desc* seg, con
     CU(cudaMemsetAsync(d_blk + payload, 0, 64, ctx->stream));
     if (!new_words.empty()) CU(cudaMemcpyAsync(d_blk + old_payload16 * 16, new_words.data(), new_words.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
     {
-        uint3 *d_r0 = nullptr, *d_r1 = nullptr;
-        uint4* d_ns = nullptr;
-        CU(cudaMalloc((void**)&d_r0, std::max<size_t>(old_ranges.size() * sizeof(uint3), 16)));
-        CU(cudaMalloc((void**)&d_r1, std::max<size_t>(new_ranges.size() * sizeof(uint3), 16)));
-        CU(cudaMalloc((void**)&d_ns, std::max<size_t>(new_skips.size() * sizeof(SkipEntry), 16)));
-        if (!old_ranges.empty()) cudaMemcpyAsync(d_r0, old_ranges.data(), old_ranges.size() * sizeof(uint3), cudaMemcpyHostToDevice, ctx->stream);
-        if (!new_ranges.empty()) cudaMemcpyAsync(d_r1, new_ranges.data(), new_ranges.size() * sizeof(uint3), cudaMemcpyHostToDevice, ctx->stream);
-        if (!new_skips.empty()) cudaMemcpyAsync(d_ns, new_skips.data(), new_skips.size() * sizeof(SkipEntry), cudaMemcpyHostToDevice, ctx->stream);
-        launch_copy_ranges(base->dev.skip, d_skip, d_r0, (uint32_t)old_ranges.size(), ctx->stream);
-        launch_copy_ranges(d_ns, d_skip, d_r1, (uint32_t)new_ranges.size(), ctx->stream);
-        const cudaError_t e1 = cudaStreamSynchronize(ctx->stream);
-        cudaFree(d_r0); cudaFree(d_r1); cudaFree(d_ns);
-        CU(e1);
+        DevTmp t_r0, t_r1, t_ns;
+        CU(t_r0.alloc(old_ranges.size() * sizeof(uint3)));
+        CU(t_r1.alloc(new_ranges.size() * sizeof(uint3)));
+        CU(t_ns.alloc(new_skips.size() * sizeof(SkipEntry)));
+        if (!old_ranges.empty()) CU(cudaMemcpyAsync(t_r0.p, old_ranges.data(), old_ranges.size() * sizeof(uint3), cudaMemcpyHostToDevice, ctx->stream));
+        if (!new_ranges.empty()) CU(cudaMemcpyAsync(t_r1.p, new_ranges.data(), new_ranges.size() * sizeof(uint3), cudaMemcpyHostToDevice, ctx->stream));
+        if (!new_skips.empty()) CU(cudaMemcpyAsync(t_ns.p, new_skips.data(), new_skips.size() * sizeof(SkipEntry), cudaMemcpyHostToDevice, ctx->stream));
+        launch_copy_ranges(base->dev.skip, d_skip, t_r0.p, (uint32_t)old_ranges.size(), ctx->stream);
+        launch_copy_ranges(t_ns.p, d_skip, t_r1.p, (uint32_t)new_ranges.size(), ctx->stream);
+        CU(cudaStreamSynchronize(ctx->stream));
         CU(cudaGetLastError());
     }
     ix->dev.skip = d_skip;
@@ -1088,14 +1089,12 @@ extern "C" int32_t fg_index_append(fg_index* base, const fg_index_desc* seg, con
             const uint32_t nnew = (uint32_t)enc[i].skips.size();
             for (uint32_t b = ti.n_blocks - nnew; b < ti.n_blocks; b++) sel.push_back(make_uint2(ti.blk_begin + b, (uint32_t)ti.bm));
         }
-        uint2* d_sel = nullptr;
-        CU(cudaMalloc((void**)&d_sel, std::max<size_t>(sel.size() * sizeof(uint2), 16)));
-        if (!sel.empty()) cudaMemcpyAsync(d_sel, sel.data(), sel.size() * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream);
-        launch_bitmap_build(ix->dev, d_sel, (uint32_t)sel.size(), d_bits, stride_words, ctx->stream);
+        DevTmp t_sel;
+        CU(t_sel.alloc(sel.size() * sizeof(uint2)));
+        if (!sel.empty()) CU(cudaMemcpyAsync(t_sel.p, sel.data(), sel.size() * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream));
+        launch_bitmap_build(ix->dev, t_sel.as<uint2>(), (uint32_t)sel.size(), d_bits, stride_words, ctx->stream);
         launch_bitmap_rank(d_bits, d_rank, base->n_bitmaps, stride_words, ctx->stream);
-        const cudaError_t e1 = cudaStreamSynchronize(ctx->stream);
-        cudaFree(d_sel);
-        CU(e1);
+        CU(cudaStreamSynchronize(ctx->stream));
         CU(cudaGetLastError());
         ix->d_bits = d_bits;
         ix->d_rank = d_rank;

@@ -493,6 +493,8 @@ struct fgh_dataset {
     std::shared_ptr<fg_index> index;
     uint32_t committed_docs = 0;  // n_docs of the snapshot in `index`
     uint32_t full_docs = 0;       // n_docs of the last snapshot built by a full upload (appends since: committed_docs - full_docs)
+    uint64_t version = 0;         // bumped by every upsert / delete (a commit detects changes made while it was building)
+    std::mutex commit_mu;         // commits serialize among themselves (they hold `mu` only to capture and to publish)
     uint64_t n_appends = 0, n_full_uploads = 0;
     // dictionary entries the current snapshot knows, per field: ordinals are assigned in insertion order, so
     // a term first seen after the last commit has an ordinal >= this and is planned as MISSING (an
@@ -561,6 +563,7 @@ static void delete_doc_locked(fgh_dataset* ds, const std::string& id) {
         ds->alive[it->second] = 0;
         ds->id2doc.erase(it);
         ds->dirty = true;
+        ds->version++;
     }
 }
 
@@ -623,42 +626,44 @@ extern "C" int32_t fgh_dataset_upsert(fgh_dataset* ds, const char* id, const cha
         for (auto& k : keys) fb.postings[fb.term(k)].emplace_back(doc, 1u);
     }
     ds->dirty = true;
+    ds->version++;
     return FG_OK;
 }
 
 extern "C" int32_t fgh_dataset_commit(fgh_dataset* ds) {
     if (!ds) return host_fail(FG_ERR_INVALID, "NULL dataset");
+    // Three phases, so that searches (and upserts) are not held up by the device work of a commit -- tantivy's commit does
+    // not stall its searchers either: (1) under the dataset's lock, capture what the new snapshot will contain (the CSR of
+    // the new segment / of everything, the alive bits); (2) without the lock, build the snapshot on the device; (3) under
+    // the lock again, publish it. Commits serialize among themselves. Documents upserted during (2) stay invisible
+    // (their doc ids and term ordinals lie beyond the captured counts) and keep the dataset dirty.
+    std::lock_guard<std::mutex> one_commit(ds->commit_mu);
     std::unique_lock<std::shared_mutex> g(ds->mu);
     if (ds->adopted) return FG_OK;
     if (!ds->ctx) return host_fail(FG_ERR_NO_DEVICE, "dataset has no device context (planning only)");
-    std::vector<uint32_t> alive((ds->n_docs + 31) / 32, 0);
+    if (ds->index && !ds->dirty) return FG_OK;  // nothing changed since the last commit
+    const uint32_t n_docs = ds->n_docs;
+    const uint64_t version = ds->version;
+    const std::shared_ptr<fg_index> base = ds->index;
+    std::vector<uint32_t> alive((n_docs + 31) / 32, 0);
     bool any_dead = false;
-    for (uint32_t d = 0; d < ds->n_docs; d++) {
+    for (uint32_t d = 0; d < n_docs; d++) {
         if (ds->alive[d]) alive[d >> 5] |= 1u << (d & 31);
         else any_dead = true;
     }
-    if (ds->index && !ds->dirty) return FG_OK;  // nothing changed since the last commit
-    if (ds->index && ds->committed_docs == ds->n_docs && !getenv("FG_NO_INCREMENTAL")) {
-        // only deletes since the last commit: the postings are unchanged, refresh the alive bitset
-        fg_index* nx = nullptr;
-        DEV_OR_FAIL();
-        int32_t rc = D(dev_api().fg_index_with_alive(ds->index.get(), any_dead ? alive.data() : nullptr, &nx));
-        if (rc) return rc;
-        ds->index.reset(nx, dev_api().fg_index_release);
-        ds->dirty = false;
-        return FG_OK;
-    }
+    const bool incremental = base && !getenv("FG_NO_INCREMENTAL");
+    enum { ALIVE_ONLY, APPEND, FULL } mode = FULL;
+    if (incremental && ds->committed_docs == n_docs) mode = ALIVE_ONLY;  // only deletes since the last commit
+    // New documents since the last commit: hand over only them, as one new segment (fg_index_append: the postings
+    // already in HBM stay there). Like tantivy's merge policy, a full rebuild follows once the appended part has
+    // outgrown the part that was built whole (it re-decides which terms own tf columns / membership bitmaps).
+    else if (incremental && ds->committed_docs && n_docs > ds->committed_docs && (uint64_t)n_docs <= 2ull * ds->full_docs) mode = APPEND;
     struct Csr { std::vector<uint64_t> off; std::vector<uint32_t> docs, tfs; std::vector<uint8_t> fn; };
     Csr c[3];
     fg_field_desc fd[3];
     memset(fd, 0, sizeof(fd));
-    // New documents since the last commit: hand over only them, as one new segment (fg_index_append: the postings
-    // already in HBM stay there). Like tantivy's merge policy, a full rebuild follows once the appended part has
-    // outgrown the part that was built whole (it re-decides which terms own tf columns / membership bitmaps).
-    if (ds->index && ds->committed_docs && ds->n_docs > ds->committed_docs && (uint64_t)ds->n_docs <= 2ull * ds->full_docs &&
-        !getenv("FG_NO_INCREMENTAL")) {
-        DEV_OR_FAIL();
-        const uint32_t d0 = ds->committed_docs, ns = ds->n_docs - d0;
+    const uint32_t d0 = mode == APPEND ? ds->committed_docs : 0u, ns = n_docs - d0;  // docs [d0, n_docs) are handed over
+    if (mode != ALIVE_ONLY) {
         for (int f = 0; f < 3; f++) {
             FieldBuild& fb = ds->f[f];
             c[f].off.resize(fb.postings.size() + 1);
@@ -666,7 +671,7 @@ extern "C" int32_t fgh_dataset_commit(fgh_dataset* ds) {
             for (size_t t = 0; t < fb.postings.size(); t++) {
                 c[f].off[t] = n;
                 const auto& pl = fb.postings[t];
-                auto it = std::lower_bound(pl.begin(), pl.end(), std::make_pair(d0, 0u));
+                auto it = d0 ? std::lower_bound(pl.begin(), pl.end(), std::make_pair(d0, 0u)) : pl.begin();
                 for (; it != pl.end(); ++it) {
                     c[f].docs.push_back(it->first - d0);
                     c[f].tfs.push_back(it->second);
@@ -674,10 +679,10 @@ extern "C" int32_t fgh_dataset_commit(fgh_dataset* ds) {
                 }
             }
             c[f].off[fb.postings.size()] = n;
-            uint64_t seg_tokens = 0;
-            for (uint32_t d = d0; d < ds->n_docs; d++) seg_tokens += fb.doc_len[d];
+            uint64_t tokens = 0;
+            for (uint32_t d = d0; d < n_docs; d++) tokens += fb.doc_len[d];
             fd[f].n_terms = (uint32_t)fb.postings.size();
-            fd[f].total_num_tokens = seg_tokens;
+            fd[f].total_num_tokens = tokens;  // (of the docs handed over: the whole corpus for a full upload)
             fd[f].term_offsets = c[f].off.data();
             fd[f].doc_ids = c[f].docs.data();
             if (f != (int)FGH_FIELD_FACET) {
@@ -688,62 +693,40 @@ extern "C" int32_t fgh_dataset_commit(fgh_dataset* ds) {
                 fd[f].term_freqs = c[f].tfs.data();
             }
         }
-        fg_index_desc seg;
-        memset(&seg, 0, sizeof(seg));
-        seg.n_docs = ns;
-        seg.n_fields = 3;
-        seg.fields = fd;
-        fg_index* nx = nullptr;
-        int32_t rc = D(dev_api().fg_index_append(ds->index.get(), &seg, any_dead ? alive.data() : nullptr, &nx));
-        if (rc) return rc;
-        ds->index.reset(nx, dev_api().fg_index_release);
-        ds->committed_docs = ds->n_docs;
-        for (int f = 0; f < 3; f++) ds->committed_terms[f] = fd[f].n_terms;
-        ds->dirty = false;
-        ds->n_appends++;
-        return FG_OK;
     }
-    for (int f = 0; f < 3; f++) {
-        FieldBuild& fb = ds->f[f];
-        c[f].off.resize(fb.postings.size() + 1);
-        uint64_t n = 0;
-        for (size_t t = 0; t < fb.postings.size(); t++) { c[f].off[t] = n; n += fb.postings[t].size(); }
-        c[f].off[fb.postings.size()] = n;
-        c[f].docs.resize(n);
-        c[f].tfs.resize(n);
-        for (size_t t = 0; t < fb.postings.size(); t++)
-            for (size_t i = 0; i < fb.postings[t].size(); i++) {
-                c[f].docs[c[f].off[t] + i] = fb.postings[t][i].first;
-                c[f].tfs[c[f].off[t] + i] = fb.postings[t][i].second;
-            }
-        fd[f].n_terms = (uint32_t)fb.postings.size();
-        fd[f].total_num_tokens = fb.total_tokens;
-        fd[f].term_offsets = c[f].off.data();
-        fd[f].doc_ids = c[f].docs.data();
-        if (f != (int)FGH_FIELD_FACET) {
-            c[f].fn.resize(ds->n_docs);
-            for (uint32_t d = 0; d < ds->n_docs; d++) c[f].fn[d] = fieldnorm_id(fb.doc_len[d]);
-            fd[f].flags = FG_FIELD_HAS_FIELDNORMS | FG_FIELD_HAS_FREQS;
-            fd[f].fieldnorm_ids = c[f].fn.data();
-            fd[f].term_freqs = c[f].tfs.data();
+    g.unlock();
+
+    // ---- device work, no lock held ----
+    DEV_OR_FAIL();
+    fg_index* nx = nullptr;
+    int32_t rc;
+    if (mode == ALIVE_ONLY) {
+        rc = D(dev_api().fg_index_with_alive(base.get(), any_dead ? alive.data() : nullptr, &nx));
+    } else {
+        fg_index_desc desc;
+        memset(&desc, 0, sizeof(desc));
+        desc.n_docs = ns;
+        desc.n_fields = 3;
+        desc.fields = fd;
+        if (mode == APPEND) {
+            rc = D(dev_api().fg_index_append(base.get(), &desc, any_dead ? alive.data() : nullptr, &nx));
+        } else {
+            desc.alive_bitset = any_dead ? alive.data() : nullptr;
+            rc = D(dev_api().fg_index_upload(ds->ctx, &desc, &nx));
         }
     }
-    fg_index_desc desc;
-    memset(&desc, 0, sizeof(desc));
-    desc.n_docs = ds->n_docs;
-    desc.n_fields = 3;
-    desc.fields = fd;
-    desc.alive_bitset = any_dead ? alive.data() : nullptr;
-    fg_index* nx = nullptr;
-    DEV_OR_FAIL();
-    int32_t rc = D(dev_api().fg_index_upload(ds->ctx, &desc, &nx));
     if (rc) return rc;
+
+    // ---- publish ----
+    g.lock();
     ds->index.reset(nx, dev_api().fg_index_release);
-    ds->committed_docs = ds->n_docs;
-    ds->full_docs = ds->n_docs;
-    ds->n_full_uploads++;
-    for (int f = 0; f < 3; f++) ds->committed_terms[f] = fd[f].n_terms;
-    ds->dirty = false;
+    if (mode != ALIVE_ONLY) {
+        ds->committed_docs = n_docs;
+        for (int f = 0; f < 3; f++) ds->committed_terms[f] = fd[f].n_terms;
+        if (mode == APPEND) ds->n_appends++;
+        else { ds->full_docs = n_docs; ds->n_full_uploads++; }
+    }
+    ds->dirty = ds->version != version;  // something was upserted / deleted while the snapshot was being built
     return FG_OK;
 }
 

@@ -68,7 +68,9 @@ int32_t fgh_dataset_delete(fgh_dataset* ds, const char* id);
  * row f3). New documents: only they are handed over, as one new segment (fg_index_append: the postings already
  * in HBM stay there, the derived structures are rebuilt on the device); once the appended part has outgrown the
  * part that was uploaded whole, the next commit rebuilds the snapshot from scratch (tantivy merges segments on a
- * similar schedule). Nothing pending: no-op. */
+ * similar schedule). Nothing pending: no-op. Searches, plans and upserts are not held up while the snapshot is
+ * built on the device (the dataset's lock is taken only to capture the pending state and to publish the result);
+ * commits serialize among themselves; what is upserted while a commit runs becomes visible with the next one. */
 int32_t fgh_dataset_commit(fgh_dataset* ds);
 /* how the snapshots of this dataset were built so far: full uploads / appended segments */
 int32_t fgh_dataset_commit_counts(const fgh_dataset* ds, uint64_t* n_full_uploads, uint64_t* n_appends);
