@@ -118,6 +118,7 @@ struct fg_ctx {
     uint32_t lead_par_blocks = 16, lead_max_par = 64, lead_chunk = 16, lead_tma = 0, lead_chunk_req = 48, lead_max_par_req = 1024, lead_union_work = 32;
 };
 static uint64_t env_u64_early(const char* name, uint64_t dflt);
+static double now_ms();
 
 static cudaError_t pinned_alloc(fg_ctx* c, void** out, size_t bytes) {
     bytes = std::max<size_t>((bytes + 4095) & ~(size_t)4095, 4096);
@@ -821,6 +822,18 @@ extern "C" int32_t fg_index_append(fg_index* base, const fg_index_desc* seg, con
         if (fd.n_terms && (!fd.term_offsets || (fd.term_offsets[fd.n_terms] && !fd.doc_ids))) return fail(FG_ERR_INVALID, "field %u: term_offsets/doc_ids NULL", f);
         if ((fd.flags & FG_FIELD_HAS_FIELDNORMS) && !fd.fieldnorm_ids && n_seg) return fail(FG_ERR_INVALID, "field %u: HAS_FIELDNORMS but fieldnorm_ids NULL", f);
     }
+    double t_mark = now_ms();
+    std::string t_log;
+#define APPEND_MARK(label)                                                        \
+    do {                                                                          \
+        if (ctx->env_timing) {                                                    \
+            char b_[96];                                                          \
+            const double t_ = now_ms();                                           \
+            snprintf(b_, sizeof(b_), " %s %.1f", label, t_ - t_mark);             \
+            t_log += b_;                                                          \
+            t_mark = t_;                                                          \
+        }                                                                         \
+    } while (0)
     std::unique_ptr<fg_index, void (*)(fg_index*)> ix(new fg_index(), fg_index_release);
     ix->ctx = ctx;
     ix->arena = std::make_shared<DeviceArena>();
@@ -843,7 +856,8 @@ extern "C" int32_t fg_index_append(fg_index* base, const fg_index_desc* seg, con
     struct Touched { uint32_t f, t, old_last_block /* global, EMPTY32 = the term is new */, tail, list_idx; };
     constexpr uint32_t EMPTY32 = 0xFFFFFFFFu;
     std::vector<Touched> touched;
-    std::vector<uint32_t> decode_list;  // global block indices of the base handed to tail_decode_kernel
+    std::vector<uint32_t> decode_list;  // global block indices of the base handed to tail_decode_kernel: postings wanted ...
+    std::vector<uint32_t> meta_list;    // ... and those of which only the skip entry's (last_doc, first_base) is needed
     uint64_t n_blocks = 0, n_postings = 0;
     for (uint32_t f = 0; f < n_fields; f++) {
         const fg_field_desc& fd = seg->fields[f];
@@ -861,7 +875,12 @@ extern "C" int32_t fg_index_append(fg_index* base, const fg_index_desc* seg, con
             const TermInfo* old = t < bf.n_terms ? &bf.terms[t] : nullptr;
             const uint32_t old_df = old ? old->df_local : 0;
             ti.df_local = ti.df_global = old_df + (uint32_t)add;
-            ti.n_blocks = (ti.df_local + BLOCK - 1) / BLOCK;
+            // A bitmap term finds a hit's posting through its rank (block = rank / 128): every block of it but the last
+            // stays full, so its partial last block is re-encoded together with the new postings. Any other term keeps
+            // its blocks as they are and gets new blocks behind them (a partial block in the middle of a list is fine
+            // for the block walk, the gallop and the block maxima; the next full upload packs the list again).
+            const uint32_t tail = (old && add && old->bm >= 0) ? old_df % BLOCK : 0u;
+            ti.n_blocks = (old ? old->n_blocks : 0u) - (tail ? 1u : 0u) + (uint32_t)((tail + add + BLOCK - 1) / BLOCK);
             ti.blk_begin = (uint32_t)n_blocks;
             ti.col = old ? old->col : -1;
             ti.bm = old ? old->bm : -1;
@@ -870,11 +889,12 @@ extern "C" int32_t fg_index_append(fg_index* base, const fg_index_desc* seg, con
             n_blocks += ti.n_blocks;
             n_postings += ti.df_local;
             if (add) {
-                Touched x{f, t, EMPTY32, old_df % BLOCK, EMPTY32};
+                Touched x{f, t, EMPTY32, tail, EMPTY32};
                 if (old && old->n_blocks) {
                     x.old_last_block = old->blk_begin + old->n_blocks - 1;
-                    x.list_idx = (uint32_t)decode_list.size();
-                    decode_list.push_back(x.old_last_block);
+                    std::vector<uint32_t>& list = tail ? decode_list : meta_list;  // postings wanted, or just (last_doc, first_base)
+                    x.list_idx = (uint32_t)list.size();
+                    list.push_back(x.old_last_block);
                 }
                 touched.push_back(x);
             }
@@ -882,6 +902,7 @@ extern "C" int32_t fg_index_append(fg_index* base, const fg_index_desc* seg, con
         }
     }
 
+    APPEND_MARK("term table");
     // ---- last blocks of the touched terms: (last_doc, first_base) and, for partial ones, their postings ----
     std::vector<uint32_t> h_meta(2 * decode_list.size()), h_docs((size_t)BLOCK * decode_list.size()), h_tfs((size_t)BLOCK * decode_list.size());
     if (!decode_list.empty()) {
@@ -899,7 +920,20 @@ extern "C" int32_t fg_index_append(fg_index* base, const fg_index_desc* seg, con
         CU(cudaStreamSynchronize(ctx->stream));
         CU(cudaGetLastError());
     }
+    std::vector<uint32_t> h_meta2(2 * meta_list.size());
+    if (!meta_list.empty()) {
+        DevTmp t_list, t_meta;
+        const size_t nl = meta_list.size();
+        CU(t_list.alloc(nl * 4));
+        CU(t_meta.alloc(nl * 8));
+        CU(cudaMemcpyAsync(t_list.p, meta_list.data(), nl * 4, cudaMemcpyHostToDevice, ctx->stream));
+        launch_tail_decode(base->dev, t_list.as<uint32_t>(), (uint32_t)nl, t_meta.as<uint32_t>(), nullptr, nullptr, ctx->stream);
+        CU(cudaMemcpyAsync(h_meta2.data(), t_meta.p, nl * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        CU(cudaGetLastError());
+    }
 
+    APPEND_MARK("tail decode");
     // ---- encode the new blocks of every touched term (parallel): old partial tail + the segment's postings ----
     std::vector<NewBlocks> enc(touched.size());
     std::vector<int> bad(T, 0);
@@ -914,8 +948,9 @@ extern "C" int32_t fg_index_append(fg_index* base, const fg_index_desc* seg, con
             docs.clear(); tfs.clear();
             uint32_t first_base = 0;
             if (x.list_idx != EMPTY32) {
-                first_base = h_meta[2 * x.list_idx] + 1;  // behind the base's last posting ...
-                if (x.tail) {                              // ... unless its partial last block is re-encoded with the new ones
+                if (!x.tail) {
+                    first_base = h_meta2[2 * x.list_idx] + 1;  // behind the base's last posting
+                } else {                                       // the partial last block is re-encoded with the new postings
                     first_base = h_meta[2 * x.list_idx + 1];
                     docs.assign(h_docs.begin() + (size_t)x.list_idx * BLOCK, h_docs.begin() + (size_t)x.list_idx * BLOCK + x.tail);
                     tfs.assign(h_tfs.begin() + (size_t)x.list_idx * BLOCK, h_tfs.begin() + (size_t)x.list_idx * BLOCK + x.tail);
@@ -936,11 +971,18 @@ extern "C" int32_t fg_index_append(fg_index* base, const fg_index_desc* seg, con
     for (int t = 0; t < T; t++)
         if (bad[t]) return fail(FG_ERR_INVALID, "segment postings must be strictly ascending, < n_docs of the segment, with tf >= 1");
 
+    APPEND_MARK("encode");
     // ---- layout: payload of the new blocks behind the base's, skip entries term by term ----
     const uint64_t old_payload16 = base->info.packed_bytes / 16;
     uint64_t off16 = old_payload16;
     std::vector<uint32_t> new_words;
     std::vector<SkipEntry> new_skips;          // compact: the new blocks of the touched terms, in term order
+    {
+        size_t nw = 0, nsk = 0;
+        for (const NewBlocks& nb : enc) { nw += nb.words.size(); nsk += nb.skips.size(); }
+        new_words.reserve(nw);
+        new_skips.reserve(nsk);
+    }
     std::vector<uint3> old_ranges, new_ranges;  // {src_begin, dst_begin, count} for copy_ranges_kernel
     {
         size_t ti_touched = 0;
@@ -975,6 +1017,7 @@ extern "C" int32_t fg_index_append(fg_index* base, const fg_index_desc* seg, con
     }
     const uint64_t payload = off16 * 16;
 
+    APPEND_MARK("layout");
     // ---- device arrays ----
     uint8_t* d_blk = nullptr;
     uint4* d_skip = nullptr;
@@ -1037,9 +1080,11 @@ extern "C" int32_t fg_index_append(fg_index* base, const fg_index_desc* seg, con
     }
     CU(cudaStreamSynchronize(ctx->stream));  // (host staging vectors above may go out of use)
 
+    APPEND_MARK("payload + skip + norms + alive");
     // block maxima of every block under the new norms, per-term maxima and top tables
     if ((rc = compute_block_max(ix.get(), n_blocks, T))) return rc;
 
+    APPEND_MARK("block maxima");
     // ---- dense tf columns: the base's columns, extended by the segment's docs ----
     if (base->n_cols) {
         const uint64_t stride = (((uint64_t)n_new + 15) & ~(uint64_t)15) + 16;
@@ -1072,6 +1117,7 @@ extern "C" int32_t fg_index_append(fg_index* base, const fg_index_desc* seg, con
     ix->info.n_columns = ix->n_cols;
     ix->info.column_bytes = ix->n_cols * ix->col_stride;
 
+    APPEND_MARK("columns");
     // ---- membership bitmaps: old bits copied, the new blocks' docs set, rank directories rebuilt ----
     if (base->n_bitmaps) {
         const uint64_t stride_words = (((uint64_t)n_new + 255) / 256) * 8 + 8;
@@ -1102,6 +1148,7 @@ extern "C" int32_t fg_index_append(fg_index* base, const fg_index_desc* seg, con
         ix->n_bitmaps = base->n_bitmaps;
         ix->info.bitmap_bytes = (uint64_t)ix->n_bitmaps * (stride_words * 4 + stride_words / 2);
     }
+    APPEND_MARK("bitmaps");
     ix->info.n_bitmaps = ix->n_bitmaps;
     ix->info.n_postings = n_postings;
     ix->info.n_blocks = n_blocks;
@@ -1109,8 +1156,10 @@ extern "C" int32_t fg_index_append(fg_index* base, const fg_index_desc* seg, con
     ix->info.skip_bytes = n_blocks * 16;
     ix->info.n_docs = n_new;
     ix->info.n_fields = n_fields;
+    if (ctx->env_timing) fprintf(stderr, "[fg_index_append] ms:%s\n", t_log.c_str());
+#undef APPEND_MARK
     ix->info.appended_bytes_h2d = new_words.size() * 4 + new_skips.size() * sizeof(SkipEntry) + (old_ranges.size() + new_ranges.size()) * sizeof(uint3) +
-                                  (uint64_t)n_seg * (ix->n_cols + 2) + decode_list.size() * 4;
+                                  (uint64_t)n_seg * (ix->n_cols + 2) + (decode_list.size() + meta_list.size()) * 4;
     *out = ix.release();
     return FG_OK;
 }

@@ -1143,6 +1143,11 @@ __global__ void __launch_bounds__(256) tail_decode_kernel(const DevIndex ix, con
     const uint32_t i = blockIdx.x * 8u + (threadIdx.x >> 5);
     if (i >= n_list) return;
     const uint4 e = __ldg(&ix.skip[__ldg(blocks + i)]);
+    if (lane == 0) {
+        out_meta[2 * i] = e.x;
+        out_meta[2 * i + 1] = e.y;
+    }
+    if (!out_docs) return;  // (uniform) only the skip entry was asked for
     const uint32_t bd = e.w & 63u, bt = (e.w >> 6) & 63u;
     const uint32_t* wd = reinterpret_cast<const uint32_t*>(ix.blk + (size_t)e.z * 16u);
     uint32_t g[4], t[4];
@@ -1154,10 +1159,6 @@ __global__ void __launch_bounds__(256) tail_decode_kernel(const DevIndex ix, con
     for (int j = 0; j < 4; j++) {
         out_docs[(size_t)i * BLOCK + 4u * lane + j] = off + g[j] + (uint32_t)j;
         out_tfs[(size_t)i * BLOCK + 4u * lane + j] = t[j] + 1u;
-    }
-    if (lane == 0) {
-        out_meta[2 * i] = e.x;
-        out_meta[2 * i + 1] = e.y;
     }
 }
 // one warp per range {src_begin, dst_begin, count}: dst[dst_begin + j] = src[src_begin + j] (16-byte entries)

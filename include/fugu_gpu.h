@@ -102,8 +102,9 @@ int32_t fg_index_with_alive(fg_index* base, const uint32_t* alive_bitset, fg_ind
  * same flags; its term ordinals extend the base's dictionary (ordinals < the base's n_terms mean the same terms, new
  * terms follow); total_num_tokens counts the segment's tokens; global_doc_freq / global_n_docs / doc_id_base must be
  * NULL / 0 (single-shard snapshots only). `alive_bitset` covers base.n_docs + segment->n_docs docs (NULL = all alive).
- * Only the segment's postings, fieldnorm ids and column bytes cross PCIe: full blocks of the base keep their payload
- * (copied device to device), each touched term's partial last block is re-encoded with its new postings, and norm
+ * Only the segment's postings, fieldnorm ids and column bytes cross PCIe: the blocks of the base keep their payload
+ * (copied device to device), new blocks go behind them (a bitmap term's partial last block is re-encoded with its new
+ * postings so that every block of it but the last stays full), and norm
  * caches, idf weights and the block-max metadata of every block are recomputed on the device for the new N and
  * average field length, so the result scores exactly like a full fg_index_upload of the whole corpus. Terms keep the
  * lookup structures (tf column / membership bitmap) they had; membership is re-decided by the next full upload.

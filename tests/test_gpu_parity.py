@@ -678,7 +678,8 @@ def test_index_append_equals_full_upload(ctx, monkeypatch):
     whole_alive = nat.HostIndexDesc(cfg.n_docs, synth.build_fields(corpus, 0, cfg.n_docs), alive_bitset=alive)
     check_batch_against_oracle(full, whole_alive, batch)
     i_full, i_ref = full.info(), nat.Index(ctx, whole).info()
-    assert i_full.n_postings == i_ref.n_postings and i_full.n_blocks == i_ref.n_blocks and i_full.n_docs == cfg.n_docs
+    # (only bitmap terms have their partial last block re-encoded; other terms get new blocks behind their old ones)
+    assert i_full.n_postings == i_ref.n_postings and i_full.n_blocks >= i_ref.n_blocks and i_full.n_docs == cfg.n_docs
     # what crossed PCIe for the last segment (a fifth of the corpus: its blocks, re-encoded tail blocks, column bytes)
     # against what a full upload reads from the host (8 B per posting of the flat CSR)
     assert 0 < i_full.appended_bytes_h2d < 8 * i_ref.n_postings // 4
