@@ -50,6 +50,10 @@ def main():
             return [q for q in qs_all if shape(q) == sh[:-6] and not has_col(q)]
         return [q for q in qs_all if shape(q) == sh]
 
+    if os.environ.get("SORT_QUERIES"):  # experiment: queries that lead with the same (rarest) terms next to each other
+        def ranks(q):
+            return sorted((int(w[1:]) for w in q["query"].split() if w.startswith("w") and w[1:].isdigit()), reverse=True)
+        qs_all = sorted(qs_all, key=ranks)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     for sh in shapes:
         qs = pick(sh)
