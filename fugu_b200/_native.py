@@ -130,7 +130,7 @@ HIT_DT = np.dtype([("score", "<f4"), ("doc", "<u4")])
 ABI_SYMBOLS = [
     "fg_last_error", "fg_version", "fg_ctx_create", "fg_ctx_destroy", "fg_ctx_set_stream",
     "fg_ctx_synchronize", "fg_index_upload", "fg_index_release", "fg_index_with_alive", "fg_index_append", "fg_index_get_info",
-    "fg_index_term_info", "fg_search_batch", "fg_batch_prepare", "fg_batch_prepare_ex", "fg_batch_release",
+    "fg_index_term_info", "fg_search_batch", "fg_search_union_of", "fg_batch_prepare", "fg_batch_prepare_ex", "fg_batch_release",
     "fg_batch_execute", "fg_batch_submit", "fg_batch_collect", "fg_batch_get_stats", "fg_merge_topk_device", "fg_fieldnorm_to_id",
     "fg_comm_unique_id", "fg_comm_create", "fg_comm_destroy", "fg_comm_allreduce_sum_u64", "fg_comm_allreduce_sum_u32",
     "fg_batch_execute_sharded", "fg_batch_query_status", "fg_batch_submit_sharded", "fg_comm_info", "fg_comm_allgather_bytes",
@@ -166,6 +166,7 @@ def lib() -> C.CDLL:
     L.fg_index_get_info.argtypes = [vp, C.POINTER(IndexInfo)]
     L.fg_index_term_info.argtypes = [vp, u32, u32, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32), C.POINTER(u64)]
     L.fg_search_batch.argtypes = [vp, C.POINTER(QueryBatch), u32, vp, vp, vp]
+    L.fg_search_union_of.argtypes = [vp, C.POINTER(QueryBatch), u32, vp, C.POINTER(u32), C.POINTER(u32)]
     L.fg_batch_prepare.argtypes = [vp, C.POINTER(QueryBatch), C.POINTER(vp)]
     L.fg_batch_prepare_ex.argtypes = [vp, C.POINTER(QueryBatch), u32, C.POINTER(vp)]
     L.fg_batch_release.argtypes = [vp]
@@ -371,6 +372,14 @@ class Index:
         cnt = np.zeros(batch.n_queries, np.uint32) if want_counts else None
         check(lib().fg_search_batch(self.h, C.byref(batch.batch), ks, _ptr(hits), _ptr(n), _ptr(cnt)))
         return hits, n, cnt
+
+    def search_union_of(self, disjuncts: HostBatch, k: int):
+        """fg_search_union_of: the batch's queries are the Should children (boolean queries themselves) of ONE query.
+        Returns (hits[n], match_count)."""
+        hits = np.zeros(max(k, 1), HIT_DT)
+        n, cnt = C.c_uint32(), C.c_uint32()
+        check(lib().fg_search_union_of(self.h, C.byref(disjuncts.batch), k, _ptr(hits), C.byref(n), C.byref(cnt)))
+        return hits[:n.value], int(cnt.value)
 
     def prepare(self, batch: HostBatch, prep_flags: int = 0) -> "PreparedBatch":
         return PreparedBatch(self, batch, prep_flags)

@@ -1203,6 +1203,10 @@ struct fg_batch {
     void* h_plan = nullptr;        // its page-locked source (kept until release: the upload is asynchronous)
     size_t plan_sz = 0;
     uint64_t* d_sel = nullptr;     // deep-page batches (ks == 0): scratch of lead_select_kernel
+    uint32_t combine_k = 0;        // fg_search_union_of: the queries are the disjuncts of ONE query with this page limit
+    uint64_t* d_comb = nullptr;    // ... and its two scratch arrays of comb_cap2 keys
+    uint32_t comb_cap2 = 0;
+    size_t comb_sz = 0;
     size_t sel_sz = 0;
     std::vector<int32_t> qstatus;  // FG_PREP_PER_QUERY_STATUS: per-query lowering status
     std::string first_bad;
@@ -1235,6 +1239,7 @@ extern "C" void fg_batch_release(fg_batch* b) {
         pool_free(c, b->l_state, b->lsz[3]);
         pool_free(c, b->l_items, b->lsz[2]);
         pool_free(c, b->d_sel, b->sel_sz);
+        pool_free(c, b->d_comb, b->comb_sz);
     }
     for (auto& e : b->ev) if (e) cudaEventDestroy(e);
     if (b->ev_up) cudaEventDestroy(b->ev_up);
@@ -2081,7 +2086,7 @@ extern "C" int32_t fg_batch_prepare_ex(fg_index* ix, const fg_query_batch* qb, u
 extern "C" int32_t fg_batch_execute(fg_batch* b, uint32_t flags, uint32_t k_stride, void* d_hits,
                                     void* d_n_hits, void* d_match_count, void* d_match_bitmap) {
     if (!b || !d_hits || !d_n_hits) return fail(FG_ERR_INVALID, "fg_batch_execute: NULL argument");
-    if (k_stride < b->kcap) return fail(FG_ERR_INVALID, "k_stride %u < max k %u", k_stride, b->kcap);
+    if (!b->combine_k && k_stride < b->kcap) return fail(FG_ERR_INVALID, "k_stride %u < max k %u", k_stride, b->kcap);
     fg_index* ix = b->ix;
     fg_ctx* ctx = ix->ctx;
     CU(cudaSetDevice(ctx->device));
@@ -2138,7 +2143,8 @@ extern "C" int32_t fg_batch_execute(fg_batch* b, uint32_t flags, uint32_t k_stri
         m.out_n = (uint32_t*)d_n_hits;
         m.out_count = (uint32_t*)d_match_count;
         m.sel = b->d_sel;
-        launch_lead_merge(m, b->ks, st);
+        if (b->combine_k) launch_lead_combine(m, b->combine_k, b->d_comb, b->d_comb + b->comb_cap2, b->comb_cap2, st);
+        else launch_lead_merge(m, b->ks, st);
         CU(cudaEventRecord(b->ev[2], st));
         b->n_launches = b->n_queries ? (b->n_items ? 3 : 2) : 0;
         CU(cudaGetLastError());
@@ -2303,6 +2309,55 @@ extern "C" int32_t fg_search_batch(fg_index* ix, const fg_query_batch* qb, uint3
     CU(cudaStreamSynchronize(ctx->stream));
     if (timing)
         fprintf(stderr, "[fg_search_batch] prepare %.2f ms, alloc+execute+d2h %.2f ms (n=%zu)\n", t1 - t0, now_ms() - t1, nq);
+    return FG_OK;
+}
+
+// One query whose Should children are boolean queries themselves (tantivy: BooleanQuery of BooleanQuerys, e.g.
+// `(a AND b) OR (c AND d)`): the batch's queries are its disjuncts. Every disjunct is evaluated exhaustively by the
+// lead-driven kernels in the deep-page form (all matches kept), lead_combine_kernel sums the scores per document and
+// selects the page. The disjuncts' own k is ignored.
+extern "C" int32_t fg_search_union_of(fg_index* ix, const fg_query_batch* disjuncts, uint32_t k, fg_hit* out_hits, uint32_t* out_n_hits,
+                                      uint32_t* out_match_count) {
+    if (!ix || !disjuncts || !out_hits || !out_n_hits) return fail(FG_ERR_INVALID, "fg_search_union_of: NULL argument");
+    if (k == 0) return fail(FG_ERR_INVALID, "k == 0 (TopDocs::with_limit requires limit >= 1)");
+    if (disjuncts->n_queries == 0 || disjuncts->n_queries > 64) return fail(FG_ERR_INVALID, "fg_search_union_of: 1 to 64 disjuncts");
+    std::vector<fg_query> qs(disjuncts->queries, disjuncts->queries + disjuncts->n_queries);
+    for (fg_query& q : qs) q.k = 0x7FFFFFFFu;  // every match of every disjunct: no per-warp queue, no threshold
+    fg_query_batch qb = *disjuncts;
+    qb.queries = qs.data();
+    fg_batch* b = nullptr;
+    int32_t rc = prepare_lead(ix, &qb, 0, &b);
+    if (rc) return rc;
+    std::unique_ptr<fg_batch, void (*)(fg_batch*)> guard(b, fg_batch_release);
+    fg_ctx* ctx = ix->ctx;
+    CU(cudaSetDevice(ctx->device));
+    uint64_t cap2 = 1;
+    while (cap2 < std::max<uint64_t>(b->partial_entries, 1)) cap2 <<= 1;
+    if (cap2 > 0x40000000ull) return fail(FG_ERR_UNSUPPORTED, "fg_search_union_of: the disjuncts match too many documents");
+    b->combine_k = k;
+    b->comb_cap2 = (uint32_t)cap2;
+    b->comb_sz = (size_t)cap2 * 16;
+    CU(pool_alloc(ctx, (void**)&b->d_comb, b->comb_sz));
+    const uint32_t k_stride = (uint32_t)std::min<uint64_t>(k, std::max<uint64_t>(b->partial_entries, 1));
+    void *d_hits = nullptr, *d_n = nullptr;
+    struct Guard {
+        fg_ctx* c; void* p = nullptr; size_t sz = 0;
+        ~Guard() { if (p) { cudaStreamSynchronize(c->stream); pool_free(c, p, sz); } }
+    } g1{ctx}, g2{ctx};
+    CU(pool_alloc(ctx, &d_hits, (size_t)k_stride * sizeof(fg_hit)));
+    g1.p = d_hits; g1.sz = (size_t)k_stride * sizeof(fg_hit);
+    CU(pool_alloc(ctx, &d_n, 2 * sizeof(uint32_t)));
+    g2.p = d_n; g2.sz = 2 * sizeof(uint32_t);
+    // (match counts come from the combine step itself: distinct documents over all disjuncts)
+    rc = fg_batch_execute(b, 0, k_stride, d_hits, d_n, out_match_count ? (char*)d_n + 4 : nullptr, nullptr);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    uint32_t h_n[2] = {0, 0};
+    CU(cudaMemcpyAsync(h_n, d_n, sizeof(h_n), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(out_hits, d_hits, (size_t)k_stride * sizeof(fg_hit), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    *out_n_hits = h_n[0];
+    if (out_match_count) *out_match_count = h_n[1];
     return FG_OK;
 }
 

@@ -892,41 +892,14 @@ __global__ void __launch_bounds__(128) lead_merge_kernel(const LeadMergeParams p
     }
 }
 
-// Deep pages (k > 1024, any page * per_page + per_page the handler lets through: /root/reference/src/db/search.rs:154-160):
-// the lead warps appended every accepted hit to the query's partial region. One CTA per query: radix select of the
-// k-th largest 64-bit key (most significant byte first; keys are distinct, the doc id is part of them), compaction of
-// the k keys at or above it into the query's scratch region, bitonic sort there (padded to a power of two), page out.
-__global__ void __launch_bounds__(256) lead_select_kernel(const LeadMergeParams p) {
-    __shared__ uint32_t hist[256];
-    __shared__ uint64_t s_prefix;
-    __shared__ uint32_t s_remaining, s_cnt;
-    const int tid = threadIdx.x, lane = tid & 31;
-    const uint32_t qi = blockIdx.x;
-    const LQuery q = p.queries[qi];
-    uint2* out = reinterpret_cast<uint2*>(p.out_hits) + (size_t)qi * p.k_stride;
-    if (q.flags & LQ_ALL) {  // (uniform) AllQuery: the first k alive docs, every score equals const_score
-        if (tid >= 32) return;
-        uint32_t found = 0;
-        for (uint32_t base = 0; base < p.n_docs && found < q.k; base += 32) {
-            const uint32_t d = base + lane;
-            const bool al = d < p.n_docs && (!p.alive || ((p.alive[d >> 5] >> (d & 31)) & 1u));
-            const unsigned m = __ballot_sync(FULL, al);
-            const uint32_t r = found + __popc(m & ((1u << lane) - 1u));
-            if (al && r < q.k && r < p.k_stride) out[r] = make_uint2(__float_as_uint(q.const_score), d + p.doc_base);
-            found += __popc(m);
-        }
-        const uint32_t nh_all = min(min(found, q.k), p.k_stride);
-        for (uint32_t r = nh_all + lane; r < p.k_stride; r += 32) out[r] = make_uint2(0u, 0xFFFFFFFFu);
-        if (lane == 0) {
-            p.out_n[qi] = nh_all;
-            if (p.out_count) p.out_count[qi] = p.n_alive;
-        }
-        return;
-    }
-    const uint64_t* src = p.partial + q.part_begin;
-    const uint32_t total = min(p.qcount[qi], q.part_cap);
-    const uint32_t k = min(min(q.k, total), p.k_stride);
-    uint64_t* sel = p.sel + q.sel_begin;
+// CTA-wide (256 threads): the k best of `total` distinct 64-bit keys at src (0 = empty slot), sorted, written as hits to
+// out[0 .. k_stride) (padded); returns the number of hits. sel = scratch of the next power of two >= k keys.
+__device__ uint32_t select_page(const uint64_t* src, uint32_t total, uint32_t k_want, uint64_t* sel, uint2* out, uint32_t k_stride,
+                                uint32_t doc_base, uint32_t* hist, uint64_t* s_prefix_p, uint32_t* s_remaining_p, uint32_t* s_cnt_p) {
+    const int tid = threadIdx.x;
+    uint64_t& s_prefix = *s_prefix_p;
+    uint32_t &s_remaining = *s_remaining_p, &s_cnt = *s_cnt_p;
+    const uint32_t k = min(k_want, k_stride);
     uint32_t cap2 = 1u;
     while (cap2 < k) cap2 <<= 1;
     uint64_t T = 0;  // the k-th largest key
@@ -986,18 +959,119 @@ __global__ void __launch_bounds__(256) lead_select_kernel(const LeadMergeParams 
         }
     }
     const uint32_t nh = min(n_sel, k);
-    for (uint32_t r = tid; r < p.k_stride; r += 256u) {
+    for (uint32_t r = tid; r < k_stride; r += 256u) {
         uint2 h = make_uint2(0u, 0xFFFFFFFFu);
         if (r < nh) {
             const uint64_t key = sel[r];
             h.x = __float_as_uint(unsortable((uint32_t)(key >> 32)));
-            h.y = ~(uint32_t)(key & 0xFFFFFFFFu) + p.doc_base;
+            h.y = ~(uint32_t)(key & 0xFFFFFFFFu) + doc_base;
         }
         out[r] = h;
     }
+    return nh;
+}
+
+// Deep pages (k > 1024, any page * per_page + per_page the handler lets through: /root/reference/src/db/search.rs:154-160):
+// the lead warps appended every accepted hit to the query's partial region. One CTA per query: radix select of the
+// k-th largest 64-bit key (most significant byte first; keys are distinct, the doc id is part of them), compaction of
+// the k keys at or above it into the query's scratch region, bitonic sort there (padded to a power of two), page out.
+__global__ void __launch_bounds__(256) lead_select_kernel(const LeadMergeParams p) {
+    __shared__ uint32_t hist[256];
+    __shared__ uint64_t s_prefix;
+    __shared__ uint32_t s_remaining, s_cnt;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const uint32_t qi = blockIdx.x;
+    const LQuery q = p.queries[qi];
+    uint2* out = reinterpret_cast<uint2*>(p.out_hits) + (size_t)qi * p.k_stride;
+    if (q.flags & LQ_ALL) {  // (uniform) AllQuery: the first k alive docs, every score equals const_score
+        if (tid >= 32) return;
+        uint32_t found = 0;
+        for (uint32_t base = 0; base < p.n_docs && found < q.k; base += 32) {
+            const uint32_t d = base + lane;
+            const bool al = d < p.n_docs && (!p.alive || ((p.alive[d >> 5] >> (d & 31)) & 1u));
+            const unsigned m = __ballot_sync(FULL, al);
+            const uint32_t r = found + __popc(m & ((1u << lane) - 1u));
+            if (al && r < q.k && r < p.k_stride) out[r] = make_uint2(__float_as_uint(q.const_score), d + p.doc_base);
+            found += __popc(m);
+        }
+        const uint32_t nh_all = min(min(found, q.k), p.k_stride);
+        for (uint32_t r = nh_all + lane; r < p.k_stride; r += 32) out[r] = make_uint2(0u, 0xFFFFFFFFu);
+        if (lane == 0) {
+            p.out_n[qi] = nh_all;
+            if (p.out_count) p.out_count[qi] = p.n_alive;
+        }
+        return;
+    }
+    const uint64_t* src = p.partial + q.part_begin;
+    const uint32_t total = min(p.qcount[qi], q.part_cap);
+    const uint32_t nh = select_page(src, total, min(q.k, total), p.sel + q.sel_begin, out, p.k_stride, p.doc_base, hist, &s_prefix, &s_remaining, &s_cnt);
     if (tid == 0) {
         p.out_n[qi] = nh;
         if (p.out_count) p.out_count[qi] = p.qmatch[qi];
+    }
+}
+
+// fg_search_union_of: the queries of the batch are the DISJUNCTS of one query (tantivy: a BooleanQuery whose Should
+// children are themselves boolean queries, e.g. `(a AND b) OR (c AND d)`; a document's score is the sum of the scores of
+// the disjuncts it matches). The lead warps appended every match of every disjunct (deep-page form, no pruning: k is
+// unbounded). One CTA: gather the m lists as (~doc, score) entries, bitonic sort (equal docs become neighbours, in a
+// value-determined order), one combined key per run of equal docs (scores summed in run order), then the ordinary
+// page selection over the combined keys. a, b: scratch of cap2 keys each (cap2 = power of two >= all matches).
+__global__ void __launch_bounds__(256) lead_combine_kernel(const LeadMergeParams p, uint32_t k, uint64_t* a, uint64_t* b, uint32_t cap2) {
+    __shared__ uint32_t hist[256];
+    __shared__ uint64_t s_prefix;
+    __shared__ uint32_t s_remaining, s_cnt, s_fill, s_runs;
+    const int tid = threadIdx.x;
+    if (tid == 0) s_fill = 0u, s_runs = 0u;
+    __syncthreads();
+    for (uint32_t j = 0; j < p.n_queries; j++) {
+        const LQuery q = p.queries[j];
+        const uint64_t* src = p.partial + q.part_begin;
+        const uint32_t cnt = min(p.qcount[j], q.part_cap), base = s_fill;
+        for (uint32_t i = tid; i < cnt; i += 256u) {
+            const uint64_t key = src[i];
+            if (base + i < cap2) a[base + i] = (key << 32) | (key >> 32);  // (~doc) above sortable(score)
+        }
+        __syncthreads();
+        if (tid == 0) s_fill = min(base + cnt, cap2);
+        __syncthreads();
+    }
+    const uint32_t n = s_fill;
+    for (uint32_t i = n + tid; i < cap2; i += 256u) a[i] = 0;
+    __syncthreads();
+    for (uint32_t size = 2u; size <= cap2; size <<= 1) {
+        for (uint32_t stride = size >> 1; stride; stride >>= 1) {
+            for (uint32_t i = tid; i < cap2 / 2u; i += 256u) {
+                const uint32_t pos = 2u * i - (i & (stride - 1u));
+                const bool desc = (pos & size) == 0u;
+                const uint64_t x = a[pos], y = a[pos + stride];
+                if ((x < y) == desc) {
+                    a[pos] = y;
+                    a[pos + stride] = x;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // runs of equal docs -> one key each (at the run's first position; 0 elsewhere)
+    for (uint32_t i = tid; i < cap2; i += 256u) {
+        uint64_t outk = 0;
+        const uint64_t e = i < n ? a[i] : 0;
+        if (e != 0 && (i == 0 || (a[i - 1] >> 32) != (e >> 32))) {
+            float sum = 0.f;
+            for (uint32_t t = i; t < n && (a[t] >> 32) == (e >> 32); t++) sum += unsortable((uint32_t)(a[t] & 0xFFFFFFFFu));
+            outk = ((uint64_t)sortable(sum) << 32) | (e >> 32);
+            atomicAdd(&s_runs, 1u);
+        }
+        b[i] = outk;
+    }
+    __syncthreads();
+    const uint32_t n_runs = s_runs;
+    const uint32_t nh = select_page(b, cap2, min(k, n_runs), a, reinterpret_cast<uint2*>(p.out_hits), p.k_stride, p.doc_base, hist, &s_prefix,
+                                    &s_remaining, &s_cnt);
+    if (tid == 0) {
+        p.out_n[0] = nh;
+        if (p.out_count) p.out_count[0] = n_runs;
     }
 }
 
@@ -1237,6 +1311,10 @@ void launch_lead_merge(const LeadMergeParams& p, int ks, void* stream) {
     else if (ks <= 1) FG_LAUNCH(lead_merge_kernel<1>, grid, 128, 0, st, p);
     else if (ks <= 4) FG_LAUNCH(lead_merge_kernel<4>, grid, 128, 0, st, p);
     else FG_LAUNCH(lead_merge_kernel<32>, grid, 128, 0, st, p);
+}
+
+void launch_lead_combine(const LeadMergeParams& p, uint32_t k, uint64_t* a, uint64_t* b, uint32_t cap2, void* stream) {
+    FG_LAUNCH(lead_combine_kernel, 1, 256, 0, (cudaStream_t)stream, p, k, a, b, cap2);
 }
 
 void launch_merge_ranks(const void* hits, const uint32_t* n, uint32_t n_ranks, uint32_t n_queries, const void* qrec, uint32_t q_words,

@@ -183,6 +183,15 @@ typedef struct {
 int32_t fg_search_batch(fg_index* index, const fg_query_batch* batch, uint32_t k_stride,
                         fg_hit* out_hits, uint32_t* out_n_hits, uint32_t* out_match_count);
 
+/* One query whose Should children are boolean queries themselves -- tantivy: a BooleanQuery of BooleanQuerys, what the
+ * QueryParser builds for `(a AND b) OR (c AND d)` or `a OR (b AND c)` (src/db/search.rs:118): the queries of `disjuncts`
+ * (1 to 64; each a one-level plan as above; their own k is ignored) are the children; a document matches when any of them
+ * matches and scores the SUM of the scores of those that do. Every disjunct is evaluated on the device with all its matches
+ * kept, a combine step sums per document and selects the page. out_hits holds min(k, matches) entries (caller-allocated for k);
+ * out_match_count (may be NULL) = distinct matching documents. Blocking, host buffers. */
+int32_t fg_search_union_of(fg_index* index, const fg_query_batch* disjuncts, uint32_t k, fg_hit* out_hits,
+                           uint32_t* out_n_hits, uint32_t* out_match_count);
+
 /* ---- split-phase form (batches resident in HBM; CUDA-event timing; multi-GPU merge) --------- */
 typedef struct fg_batch fg_batch;
 /* lowers the plan (weights from GLOBAL statistics, work items) and uploads it to the device */

@@ -679,6 +679,37 @@ int32_t orc_search_batch(const fg_index_desc* d, const fg_query_batch* qb, uint3
     return rc.load();
 }
 
+// One query whose Should children are the batch's queries (each a one-level plan): tantivy's BooleanQuery of boolean
+// queries, e.g. `(a AND b) OR (c AND d)`. complex_scorer builds each child's scorer and puts them under the buffered
+// union (A.5): a document matches when any child matches and scores the sum of the matching children.
+int32_t orc_search_union_of(const fg_index_desc* d, const fg_query_batch* disjuncts, uint32_t k, fg_hit* hits, uint32_t* n_hits,
+                            uint32_t* match_count) {
+    if (k == 0) return FG_ERR_INVALID;
+    Index ix = make_index(d);
+    std::vector<std::unique_ptr<Scorer>> kids;
+    for (uint32_t qi = 0; qi < disjuncts->n_queries; qi++) {
+        BuiltQuery bq = build(ix, *disjuncts, disjuncts->queries[qi]);
+        if (bq.unsupported) return FG_ERR_UNSUPPORTED;
+        kids.push_back(std::move(bq.scorer));
+    }
+    std::unique_ptr<Scorer> u = make_union(std::move(kids));
+    TopN top(k);
+    uint32_t cnt = 0;
+    for (uint32_t doc = u->doc(); doc != TERMINATED; doc = u->advance()) {
+        if (!ix.is_alive(doc)) continue;
+        cnt++;
+        top.push(u->score(), doc);
+    }
+    std::vector<Hit> r = top.finish();
+    for (size_t i = 0; i < r.size(); i++) {
+        hits[i].score = r[i].score;
+        hits[i].doc = r[i].doc + ix.doc_base;
+    }
+    *n_hits = (uint32_t)r.size();
+    if (match_count) *match_count = cnt;
+    return FG_OK;
+}
+
 // Block-max metadata of an index (what tantivy keeps in its skip entries): built once, released with orc_blockmax_free.
 void* orc_blockmax_build(const fg_index_desc* d, int32_t n_threads) {
     Index ix = make_index(d);

@@ -69,6 +69,8 @@ def lib():
         L.orc_search_batch.restype = i32
         L.orc_algorithmic_bytes.argtypes = [C.POINTER(nat.IndexDesc), C.POINTER(nat.QueryBatch), vp, vp, i32]
         L.orc_algorithmic_bytes.restype = i32
+        L.orc_search_union_of.argtypes = [C.POINTER(nat.IndexDesc), C.POINTER(nat.QueryBatch), u32, vp, C.POINTER(u32), C.POINTER(u32)]
+        L.orc_search_union_of.restype = i32
         L.orc_blockmax_build.argtypes = [C.POINTER(nat.IndexDesc), i32]
         L.orc_blockmax_build.restype = vp
         L.orc_blockmax_free.argtypes = [vp]
@@ -126,3 +128,13 @@ def algorithmic_bytes(desc: nat.HostIndexDesc, batch: nat.HostBatch, threads: in
     rc = lib().orc_algorithmic_bytes(C.byref(desc.desc), C.byref(batch.batch), b.ctypes.data, s.ctypes.data, threads)
     assert rc == 0
     return b, s
+
+
+def search_union_of(desc: nat.HostIndexDesc, disjuncts: nat.HostBatch, k: int):
+    """One query whose Should children are the batch's queries (BooleanQuery of boolean queries). Returns (hits, count)."""
+    hits = np.zeros(max(k, 1), nat.HIT_DT)
+    n, cnt = C.c_uint32(), C.c_uint32()
+    rc = lib().orc_search_union_of(C.byref(desc.desc), C.byref(disjuncts.batch), k, hits.ctypes.data, C.byref(n), C.byref(cnt))
+    if rc != 0:
+        raise nat.FgError(rc, "oracle")
+    return hits[:n.value], int(cnt.value)

@@ -727,3 +727,31 @@ def test_dataset_commits_append_segments(ctx):
     inc.upsert([rec(i) for i in range(n, 2 * n + 200)], commit=True)
     assert inc.commit_counts()[0] == 2
     inc.close(); one.close()
+
+
+def test_union_of_boolean_queries(ctx):
+    """fg_search_union_of: one query whose Should children are boolean queries themselves -- `(a AND b) OR (c AND d)`,
+    `a OR (b AND c)`, a conjunction with an excluded term next to a plain union -- against the oracle's union of the
+    children's scorers: same docs, scores within 1e-5, same match counts; pages of 10, 100 and 3000."""
+    from oracle import orc
+    from tests.util import check_topk
+
+    cfg = synth.Config(cfg=2, n_docs=30_000, vocab=3_000, n_queries=8, k=10, name_pct=10)
+    corpus, desc, index = _setup(ctx, cfg)
+    S, M, N = nat.FG_OCCUR_SHOULD, nat.FG_OCCUR_MUST, nat.FG_OCCUR_MUST_NOT
+    W = lambda t: [(0, t, 1.0), (1, t, 1.0)]  # a bare word over the default fields [text, name]
+    cases = [
+        [[(M, W(3)), (M, W(40))], [(M, W(7)), (M, W(120))]],                       # (a AND b) OR (c AND d)
+        [[(S, W(900))], [(M, W(1)), (M, W(2)), (M, W(5))]],                         # a OR (b AND c AND d)
+        [[(S, W(300)), (S, W(45))], [(M, W(10)), (N, W(0))], [(M, W(60)), (M, W(61))]],  # (a b) OR (c -d) OR (e AND f)
+        [[(M, W(2500)), (M, W(2900))], [(M, W(2999)), (M, W(2998))]],               # rare terms: few or no matches
+        [[(M, [(0, 0, 1.0)]), (M, [(0, 1, 2.0)])], [(S, [(0, 0, 0.5)])]],           # overlapping disjuncts, boosts
+    ]
+    for ci, disj in enumerate(cases):
+        batch = nat.HostBatch([{"k": 1, "clauses": cl} for cl in disj])
+        for k in (10, 100, 3000):
+            o_hits, o_cnt = orc.search_union_of(desc, batch, k)
+            g_hits, g_cnt = index.search_union_of(batch, k)
+            assert g_cnt == o_cnt and len(g_hits) == len(o_hits), (ci, k, g_cnt, o_cnt, len(g_hits), len(o_hits))
+            check_topk(g_hits, o_hits, k, ctx=f"union-of case {ci}, k = {k}")
+    index.close()
