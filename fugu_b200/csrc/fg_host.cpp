@@ -54,6 +54,7 @@ struct DevApi {
     FGH_DEV_FN(fg_index_append);
     FGH_DEV_FN(fg_index_term_info);
     FGH_DEV_FN(fg_search_batch);
+    FGH_DEV_FN(fg_search_union_of);
     FGH_DEV_FN(fg_batch_prepare_ex);
     FGH_DEV_FN(fg_batch_query_status);
     FGH_DEV_FN(fg_batch_submit);
@@ -93,6 +94,7 @@ const DevApi& dev_api() {
         FGH_DEV_BIND(fg_index_append);
         FGH_DEV_BIND(fg_index_term_info);
         FGH_DEV_BIND(fg_search_batch);
+        FGH_DEV_BIND(fg_search_union_of);
         FGH_DEV_BIND(fg_batch_prepare_ex);
         FGH_DEV_BIND(fg_batch_query_status);
         FGH_DEV_BIND(fg_batch_submit);
@@ -892,6 +894,36 @@ void flatten(const LNode& n, int occ, std::vector<FlatClause>& out, int depth) {
     throw ParseError{"nested boolean (OR of AND groups / negated groups) is not evaluated on the device", true};
 }
 
+// A union (every child Should) some of whose children are boolean queries of their own: each such child must flatten to
+// one level by itself; the plain children (words, unions of words) together form one more child. tantivy builds exactly
+// this tree -- BooleanQuery[(Should, BooleanQuery[..]), ..] -- and sums the scores of the children that match.
+bool all_kids_should(const LNode& n) {
+    if (n.is_group) return false;
+    for (auto& k : n.kids)
+        if (k.first != O_SHOULD) return false;
+    return true;
+}
+// (a union inside the union -- `x OR (a AND b) y` parses as ((x OR (a AND b)) y) -- is the same union: its children join)
+void collect_union_children(const LNode& n, std::vector<FlatClause>& plain, std::vector<std::vector<FlatClause>>& nested) {
+    for (auto& k : n.kids) {
+        if (k.second.is_group || all_should_groups(k.second)) flatten(k.second, O_SHOULD, plain, 1);
+        else if (all_kids_should(k.second)) collect_union_children(k.second, plain, nested);
+        else {
+            std::vector<FlatClause> sub;
+            flatten(k.second, O_SHOULD, sub, 0);  // (throws when the child itself is nested)
+            nested.push_back(std::move(sub));
+        }
+    }
+}
+bool split_disjuncts(const LNode& root, std::vector<std::vector<FlatClause>>& out) {
+    if (!all_kids_should(root)) return false;  // a Must / MustNot sibling of a nested group: deeper than this form
+    std::vector<FlatClause> plain;
+    collect_union_children(root, plain, out);
+    if (out.empty()) return false;
+    if (!plain.empty()) out.insert(out.begin(), std::move(plain));
+    return out.size() <= 64;
+}
+
 // parse_filters + build_facet_query, src/db/search.rs:221-324
 void facet_group(const fgh_dataset* ds, const char* const* filters, uint32_t n, Group& g, bool& any_term) {
     for (uint32_t i = 0; i < n; i++) {
@@ -928,6 +960,7 @@ int32_t plan_impl(const fgh_dataset* ds, const char* query, const char* const* f
     for (char c : q) if (!isspace((unsigned char)c)) blank = false;
 
     std::vector<FlatClause> flat;
+    std::vector<std::vector<FlatClause>> disjuncts;  // nested query: the children of the top-level union (fgh_plan_t::n_disjuncts)
     Planner pl(ds);
     bool text_all = false;
     float text_all_boost = 1.f;
@@ -950,7 +983,15 @@ int32_t plan_impl(const fgh_dataset* ds, const char* query, const char* const* f
                 root = pl.lower(a, 1.f);
             }
             if (root.is_group && root.g.all && root.g.leaves.empty()) { text_all = true; text_all_boost = root.g.all_boost; }
-            else flatten(root, O_SHOULD, flat, 0);
+            else {
+                try {
+                    flatten(root, O_SHOULD, flat, 0);
+                } catch (ParseError& e) {
+                    // not one level: a union whose children are one-level boolean queries? (`(a AND b) OR (c AND d)`)
+                    flat.clear();
+                    if (!e.unsupported || !split_disjuncts(root, disjuncts)) throw;
+                }
+            }
         }
     } catch (ParseError& e) {
         return host_fail(e.unsupported ? FG_ERR_UNSUPPORTED : FG_ERR_INVALID, "query '%s': %s", q.c_str(), e.msg.c_str());
@@ -962,6 +1003,8 @@ int32_t plan_impl(const fgh_dataset* ds, const char* query, const char* const* f
         std::string f = filters[i] ? filters[i] : "";
         if (!(!f.empty() && f.front() == '*' && f.back() == '*')) n_nonwild++;
     }
+    if (n_nonwild && !disjuncts.empty())  // Must(text_query) AND Must(facet_query): the facet group would have to score once, not once per child
+        return host_fail(FG_ERR_UNSUPPORTED, "query '%s': a nested boolean query combined with facet filters is not evaluated on the device", q.c_str());
     if (n_nonwild) {
         Group fg_;
         bool any = false;
@@ -1007,6 +1050,23 @@ int32_t plan_impl(const fgh_dataset* ds, const char* query, const char* const* f
         }
     } else if (text_all) {
         out->is_all = 1;
+    }
+    if (!disjuncts.empty()) {
+        out->n_disjuncts = (uint32_t)disjuncts.size();
+        for (size_t d = 0; d < disjuncts.size(); d++)
+            for (auto& c : disjuncts[d]) {
+                if (out->n_clauses >= FGH_MAX_PLAN_CLAUSES) return host_fail(FG_ERR_UNSUPPORTED, "too many clauses");
+                if (c.g.all) return host_fail(FG_ERR_UNSUPPORTED, "'*' inside a nested boolean query");
+                fg_clause& oc = out->clauses[out->n_clauses++];
+                oc.occur = (c.occ == O_MUST ? FG_OCCUR_MUST : c.occ == O_NOT ? FG_OCCUR_MUST_NOT : FG_OCCUR_SHOULD) | ((uint32_t)(d + 1) << FGH_DISJUNCT_SHIFT);
+                oc.leaf_begin = out->n_leaves;
+                for (auto& l : c.g.leaves) {
+                    if (out->n_leaves >= FGH_MAX_PLAN_LEAVES) return host_fail(FG_ERR_UNSUPPORTED, "too many leaves");
+                    out->leaves[out->n_leaves++] = l;
+                }
+                oc.n_leaves = out->n_leaves - oc.leaf_begin;
+            }
+        return FG_OK;
     }
     if (out->is_all) {
         out->n_clauses = 1;
@@ -1057,6 +1117,9 @@ struct PlannedBatch {
     uint32_t kmax = 1;
     int32_t first_err = FG_OK;
     std::string first_msg;
+    // nested queries (fgh_plan_t::n_disjuncts): (index in the batch, plan); the flat batch holds an empty query in their
+    // place, the search path answers them with fg_search_union_of
+    std::vector<std::pair<uint32_t, fgh_plan_t>> composites;
 };
 
 // Fast path for the overwhelmingly common request shape: no filters, only ASCII alphanumeric
@@ -1132,7 +1195,8 @@ bool plan_fast(const fgh_dataset* ds, const char* q, uint32_t page, uint32_t per
 }
 
 void plan_batch(const fgh_dataset* ds, uint32_t n, const char* const* queries, const char* const* filters,
-                const uint32_t* filter_offsets, const uint32_t* pages, const uint32_t* per_pages, PlannedBatch& pb) {
+                const uint32_t* filter_offsets, const uint32_t* pages, const uint32_t* per_pages, PlannedBatch& pb,
+                bool keep_composites = false) {
     std::shared_lock<std::shared_mutex> dict_lock(ds->mu);  // held for the worker threads too: the dictionaries must not grow under the planner
     pb.rc.assign(n, FG_OK);
     pb.q.resize(n);
@@ -1142,7 +1206,8 @@ void plan_batch(const fgh_dataset* ds, uint32_t n, const char* const* queries, c
     if (e) hw = (unsigned)atoi(e);
     // the fast path plans ~3M requests/s per thread; a thread costs ~30 us to start
     const int T = (int)std::max(1u, std::min<unsigned>({hw ? hw : 4u, (unsigned)fg::HostPool::get().size(), 16u, n / 96 + 1}));
-    struct Part { std::vector<fg_clause> c; std::vector<fg_leaf> l; std::vector<std::string> errs; uint32_t a, b; };
+    struct Part { std::vector<fg_clause> c; std::vector<fg_leaf> l; std::vector<std::string> errs; uint32_t a, b;
+                  std::vector<std::pair<uint32_t, fgh_plan_t>> comp; };
     std::vector<Part> parts((size_t)T);
     auto work = [&](int t) {
         Part& P = parts[t];
@@ -1155,6 +1220,17 @@ void plan_batch(const fgh_dataset* ds, uint32_t n, const char* const* queries, c
             const uint32_t page = pages ? pages[i] : 0, pp = per_pages ? per_pages[i] : 20;
             if (f1 == f0 && plan_fast(ds, queries[i], page, pp, P.c, P.l, pb.q[i], pb.offset[i])) continue;
             pb.rc[i] = plan_impl(ds, queries[i], filters ? filters + f0 : nullptr, f1 - f0, page, pp, &plan);
+            if (pb.rc[i] == FG_OK && plan.n_disjuncts) {
+                if (keep_composites) {  // answered apart (fg_search_union_of): an empty query holds its place in the flat batch
+                    P.comp.emplace_back(i, plan);
+                    pb.q[i].k = 1;
+                    pb.q[i].clause_begin = (uint32_t)P.c.size();
+                    pb.q[i].n_clauses = 0;
+                    pb.offset[i] = plan.offset;
+                    continue;
+                }
+                pb.rc[i] = host_fail(FG_ERR_UNSUPPORTED, "query '%s': a nested boolean query does not fit a flat fg_query_batch (use fgh_plan / fgh_search)", queries[i]);
+            }
             const bool bad = pb.rc[i] != FG_OK;
             if (bad) P.errs[i - P.a] = g_herr;
             pb.q[i].k = bad ? 1 : plan.k;
@@ -1201,7 +1277,9 @@ void plan_batch(const fgh_dataset* ds, uint32_t n, const char* const* queries, c
         }
         kmax_t[t] = km;
     });
+    pb.composites.clear();
     for (int t = 0; t < T; t++) {
+        pb.composites.insert(pb.composites.end(), parts[t].comp.begin(), parts[t].comp.end());
         pb.kmax = std::max(pb.kmax, kmax_t[t]);
         if (pb.first_err) continue;
         Part& P = parts[t];
@@ -1447,7 +1525,7 @@ int32_t search_batch_impl(fgh_dataset* ds, fg_comm* comm, uint32_t n, const char
             qb.leaves = whole.l.data();
         } else {
             plan_batch(ds, m, queries + C.a, filters, filter_offsets ? filter_offsets + C.a : nullptr,
-                       pages ? pages + C.a : nullptr, per_pages ? per_pages + C.a : nullptr, C.pb);
+                       pages ? pages + C.a : nullptr, per_pages ? per_pages + C.a : nullptr, C.pb, /*keep_composites=*/true);
             if (status) memcpy(status + C.a, C.pb.rc.data(), m * sizeof(int32_t));
             if (C.pb.first_err && !status) return host_fail(C.pb.first_err, "%s", C.pb.first_msg.c_str());  // single-status callers see the first failure
             qb.n_clauses = (uint32_t)C.pb.c.size();
@@ -1500,6 +1578,41 @@ int32_t search_batch_impl(fgh_dataset* ds, fg_comm* comm, uint32_t n, const char
             for (uint32_t x = 0; x < take; x++) out_hits[(size_t)qi * stride + x] = hits[(size_t)j * kmax + off + x];
             out_n[qi] = take;
             if (out_match_count) out_match_count[qi] = bad ? 0 : cnt[j];
+        }
+        // nested queries of the chunk: one fg_search_union_of each (their children are the disjuncts of the plan)
+        for (const auto& cp : C.pb.composites) {
+            const uint32_t qi = C.a + cp.first;
+            const fgh_plan_t& P = cp.second;
+            std::vector<fg_query> dq;
+            std::vector<fg_clause> dc(P.clauses, P.clauses + P.n_clauses);
+            for (uint32_t ci = 0; ci < P.n_clauses; ci++) {
+                const uint32_t d = dc[ci].occur >> FGH_DISJUNCT_SHIFT;
+                dc[ci].occur &= (1u << FGH_DISJUNCT_SHIFT) - 1u;
+                if (dq.size() < d) dq.push_back(fg_query{1u, ci, 0u});
+                dq.back().n_clauses++;
+            }
+            fg_query_batch qb;
+            memset(&qb, 0, sizeof(qb));
+            qb.n_queries = (uint32_t)dq.size();
+            qb.n_clauses = P.n_clauses;
+            qb.n_leaves = P.n_leaves;
+            qb.queries = dq.data();
+            qb.clauses = dc.data();
+            qb.leaves = P.leaves;
+            std::vector<fg_hit> page(P.k);
+            uint32_t n_page = 0, n_match = 0;
+            const int32_t rc = D(dev_api().fg_search_union_of(snap.get(), &qb, P.k, page.data(), &n_page, out_match_count ? &n_match : nullptr));
+            if (rc) {
+                if (!status) return rc;
+                status[qi] = rc;
+                out_n[qi] = 0;
+                continue;
+            }
+            const uint32_t pp = per_pages ? per_pages[qi] : 20;
+            const uint32_t take = n_page > P.offset ? std::min(n_page - P.offset, std::min(pp, stride)) : 0;  // skip(offset).take(per_page)
+            for (uint32_t x = 0; x < take; x++) out_hits[(size_t)qi * stride + x] = page[P.offset + x];
+            out_n[qi] = take;
+            if (out_match_count) out_match_count[qi] = n_match;
         }
     }
     if (timing)

@@ -36,16 +36,19 @@ class _Clause(C.Structure):
 class Plan(C.Structure):
     _fields_ = [("k", C.c_uint32), ("offset", C.c_uint32), ("n_clauses", C.c_uint32), ("n_leaves", C.c_uint32),
                 ("is_all", C.c_uint32), ("used_fallback", C.c_uint32),
-                ("clauses", _Clause * MAX_PLAN_CLAUSES), ("leaves", _Leaf * MAX_PLAN_LEAVES)]
+                ("clauses", _Clause * MAX_PLAN_CLAUSES), ("leaves", _Leaf * MAX_PLAN_LEAVES), ("n_disjuncts", C.c_uint32)]
 
     def as_dict(self) -> dict:
         cl = []
         for i in range(self.n_clauses):
             c = self.clauses[i]
-            cl.append((int(c.occur), [(int(self.leaves[j].field), int(self.leaves[j].term_ord), float(self.leaves[j].boost))
-                                      for j in range(c.leaf_begin, c.leaf_begin + c.n_leaves)]))
-        return {"k": int(self.k), "offset": int(self.offset), "is_all": bool(self.is_all),
-                "used_fallback": bool(self.used_fallback), "clauses": cl}
+            cl.append((int(c.occur) & 0xFF, [(int(self.leaves[j].field), int(self.leaves[j].term_ord), float(self.leaves[j].boost))
+                                             for j in range(c.leaf_begin, c.leaf_begin + c.n_leaves)]))
+        d = {"k": int(self.k), "offset": int(self.offset), "is_all": bool(self.is_all),
+             "used_fallback": bool(self.used_fallback), "clauses": cl}
+        if self.n_disjuncts:  # nested query: which child of the top-level union each clause belongs to (1-based)
+            d["disjunct_of_clause"] = [int(self.clauses[i].occur) >> 8 for i in range(self.n_clauses)]
+        return d
 
 
 HOST_SYMBOLS = [

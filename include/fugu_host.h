@@ -105,10 +105,17 @@ typedef struct {
     uint32_t used_fallback; /* parse_query failed and the escaped retry was used (src/db/search.rs:120-125) */
     fg_clause clauses[FGH_MAX_PLAN_CLAUSES];
     fg_leaf leaves[FGH_MAX_PLAN_LEAVES];
+    /* Nested query (a union whose children are boolean queries themselves, e.g. `(a AND b) OR (c AND d)`, `a OR (b AND c)`):
+     * the number of children; clause i then belongs to child `clauses[i].occur >> FGH_DISJUNCT_SHIFT` (1-based; the
+     * clauses of a child are contiguous, the plain words of the top level form one child) and the low bits hold its
+     * occur. Such a plan is answered with fg_search_union_of (fgh_search / fgh_search_batch do that by themselves);
+     * fg_batch_prepare rejects its clauses. 0 = an ordinary one-level plan. */
+    uint32_t n_disjuncts;
 } fgh_plan_t;
+#define FGH_DISJUNCT_SHIFT 8
 /* FG_ERR_INVALID = parse error even after the fallback (the reference returns Err -> HTTP 500);
- * FG_ERR_UNSUPPORTED = valid tantivy query the device path does not evaluate (phrase, range,
- * fuzzy, true OR-of-AND trees). */
+ * FG_ERR_UNSUPPORTED = valid tantivy query the device path does not evaluate (phrase, range, fuzzy, boolean
+ * trees nested deeper than a union of one-level boolean queries, nested queries combined with facet filters). */
 int32_t fgh_plan(const fgh_dataset* ds, const char* query, const char* const* filters,
                  uint32_t n_filters, uint32_t page, uint32_t per_page, fgh_plan_t* out);
 

@@ -66,7 +66,8 @@ FAST = {"test_config1_two_term_and", "test_golden_cases_through_dataset_search",
         "test_concurrent_callers_share_one_index", "test_search_while_commits_land", "test_bulk_copy_staged_variant_equals_default",
         "test_search_endpoint_shape_defaults_and_hydration", "test_query_json_post_namespace_text_flags_and_clamp", "test_get_front_ends",
         "test_object_record_validate_messages", "test_micro_batcher_concurrent_single_query_requests",
-        "test_dataset_commits_append_segments", "test_deep_pagination_beyond_1024", "test_union_of_boolean_queries"}
+        "test_dataset_commits_append_segments", "test_deep_pagination_beyond_1024", "test_union_of_boolean_queries",
+        "test_nested_boolean_queries_through_dataset_search"}
 
 
 @pytest.mark.parametrize("fn", _gpu_tests())

@@ -155,3 +155,47 @@ def test_micro_batcher_concurrent_single_query_requests(ctx):
         assert got[t] == want[t % len(queries)], (t, queries[t % len(queries)])
     assert st["n_requests"] == n_threads + 1 and st["n_batches"] < st["n_requests"] and st["max_batch_seen"] >= 2, st
     main.close(); other.close()
+
+
+def test_nested_boolean_queries_through_dataset_search(ctx):
+    """`(a AND b) OR (c AND d)` and friends through Dataset.search / the batched call / the micro-batcher: planned as a
+    union of boolean queries and answered by fg_search_union_of. Expected: a document matches when any child matches and
+    scores the sum of the children it matches -- recomputed here from complete result lists of the children searched on
+    their own (the children themselves are checked against the oracle elsewhere)."""
+    from fugu_b200.dataset import Batcher, QuerySet
+
+    state, main, other = _state(ctx)
+    every = 1000  # more than the corpus: complete result lists
+
+    def expected(children, page, per_page):
+        tot = {}
+        for ch in children:
+            for r in main.search(ch, [], 0, every):
+                tot[r.id] = tot.get(r.id, 0.0) + r.score
+        docid = {r.id: r.doc for ch in children for r in main.search(ch, [], 0, every)}
+        ranked = sorted(tot.items(), key=lambda kv: (-kv[1], docid[kv[0]]))
+        return ranked[page * per_page:(page + 1) * per_page]
+
+    cases = [("(alpha AND gamma1) OR (beta AND filler7)", ["alpha AND gamma1", "beta AND filler7"]),
+             ("filler3 OR (alpha AND gamma2)", ["filler3", "alpha AND gamma2"]),
+             ("(report AND gamma0) only filler9 OR (+alpha -beta)", ["only filler9", "report AND gamma0", "+alpha -beta"]),
+             ("(nosuchterm AND alpha) OR (beta AND nosuchterm)", ["nosuchterm AND alpha", "beta AND nosuchterm"])]
+    for q, children in cases:
+        assert "disjunct_of_clause" in main.plan(q).as_dict(), q
+        for page, pp in ((0, 20), (1, 7), (0, 100)):
+            got = [(r.id, r.score) for r in main.search(q, [], page, pp)]
+            want = expected(children, page, pp)
+            assert [g[0] for g in got] == [w[0] for w in want], (q, page, pp)
+            for (_, gs), (_, ws) in zip(got, want):
+                assert abs(gs - ws) <= 1e-5 * max(abs(ws), 1e-30), (q, gs, ws)
+    # in a batch next to ordinary queries, and through the micro-batcher
+    qs = ["alpha", cases[0][0], "beta AND gamma1", cases[1][0]]
+    hits, nh, cnt, status = main.search_batch(QuerySet(qs, None, 0, 20), want_counts=False)
+    assert (status == 0).all()
+    for i, q in enumerate(qs):
+        one = main.search(q, [], 0, 20)
+        assert nh[i] == len(one) and [int(h["doc"]) for h in hits[i, :nh[i]]] == [r.doc for r in one], q
+    b = Batcher(main, max_batch=16, max_wait_us=1000)
+    assert [r.id for r in b.search(cases[0][0], [], 0, 20)] == [r.id for r in main.search(cases[0][0], [], 0, 20)]
+    b.close()
+    main.close(); other.close()

@@ -89,7 +89,9 @@ def test_plan_errors_and_fallback(small):
     with pytest.raises(nat.FgError) as e:
         ds.plan("red", per_page=0)  # TopDocs::with_limit(0) panics
     assert e.value.code == nat.FG_ERR_INVALID
-    for q in ['"red apple"', "foo-bar", "apple~1", "[a TO b]", "red OR apple AND pie"]:
+    # (`red OR apple AND pie` = red OR (apple AND pie): a union of boolean queries, planned as disjuncts since round 2)
+    assert ds.plan("red OR apple AND pie").as_dict().get("disjunct_of_clause") == [1, 2, 2]
+    for q in ['"red apple"', "foo-bar", "apple~1", "[a TO b]", "red OR apple AND (pie OR (tart AND jam))"]:
         with pytest.raises(nat.FgError) as e:
             ds.plan(q)
         assert e.value.code == nat.FG_ERR_UNSUPPORTED, q
@@ -155,9 +157,38 @@ def test_fast_path_equals_general_parser(small):
         except nat.FgError as e:
             assert status[i] == e.code, q
             continue
+        if "disjunct_of_clause" in want:  # a nested query does not fit the flat batch fgh_plan_batch fills
+            assert status[i] == nat.FG_ERR_UNSUPPORTED, q
+            continue
         assert status[i] == 0, q
         got_k = int(batch.q["k"][i])
         cb, nc = int(batch.q["clause_begin"][i]), int(batch.q["n_clauses"][i])
         got = [(int(c["occur"]), [(int(l["field"]), int(l["term_ord"]), float(l["boost"]))
                                    for l in batch.l[c["leaf_begin"]:c["leaf_begin"] + c["n_leaves"]]]) for c in batch.c[cb:cb + nc]]
         assert got_k == want["k"] == 14 and got == want["clauses"], q
+
+
+def test_nested_union_of_boolean_queries_plans_as_disjuncts():
+    """`(a AND b) OR (c AND d)`, `a OR (b AND c)`: a union whose children are one-level boolean queries plans as
+    disjuncts (fgh_plan_t::n_disjuncts; answered by fg_search_union_of). Deeper nesting, a Must sibling of a nested
+    group, or facet filters next to it stay FG_ERR_UNSUPPORTED."""
+    from fugu_b200 import _native as nat
+    from fugu_b200.dataset import Dataset, ObjectRecord
+
+    ds = Dataset(None)
+    ds.upsert([ObjectRecord(id="x", text="alpha beta gamma delta omega", metadata={"name": "alpha"})], commit=False)
+    S, M, N = nat.FG_OCCUR_SHOULD, nat.FG_OCCUR_MUST, nat.FG_OCCUR_MUST_NOT
+    p = ds.plan("(alpha AND beta) OR (gamma AND delta)").as_dict()
+    assert p["disjunct_of_clause"] == [1, 1, 2, 2] and [c[0] for c in p["clauses"]] == [M, M, M, M]
+    assert all(len(c[1]) == 2 for c in p["clauses"])  # every word over [text, name]
+    p = ds.plan("omega OR (+alpha -beta) gamma").as_dict()
+    # plain words of the top level form the first child; then the nested group
+    assert p["disjunct_of_clause"] == [1, 1, 2, 2] and [c[0] for c in p["clauses"]] == [S, S, M, N]
+    assert "disjunct_of_clause" not in ds.plan("alpha AND beta").as_dict()
+    assert "disjunct_of_clause" not in ds.plan("alpha (beta gamma)").as_dict()
+    for q, f in (("alpha OR (beta AND (gamma OR (delta AND omega)))", []), ("+alpha (beta AND gamma)", []),
+                 ("(alpha AND beta) OR gamma", ["namespace/x"])):
+        with pytest.raises(nat.FgError) as e:
+            ds.plan(q, f)
+        assert e.value.code == nat.FG_ERR_UNSUPPORTED, q
+    ds.close()
