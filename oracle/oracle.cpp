@@ -158,6 +158,20 @@ struct UnionScorer : Scorer {
         offset = mn;
         cursor = 0;
         for (auto& s : subs) {
+            if (TermScorer* t = dynamic_cast<TermScorer*>(s.get())) {
+                // plain term scorer (the common child): the same loop on its arrays, without a virtual call per posting
+                // (tantivy's union is generic over its scorer type and gets the same effect from monomorphisation)
+                const uint64_t lim = (uint64_t)mn + HORIZON;
+                size_t i = t->i;
+                while (i < t->n && t->docs[i] < lim) {
+                    const uint32_t delta = t->docs[i] - mn;
+                    bits[delta >> 6] |= 1ull << (delta & 63);
+                    sums[delta] += t->bm.score(t->fn ? t->fn[t->docs[i]] : t->const_id, t->tfs ? t->tfs[i] : 1u);
+                    i++;
+                }
+                t->i = i;
+                continue;
+            }
             while (true) {
                 uint32_t d = s->doc();
                 if (d >= mn + HORIZON || d == TERMINATED) break;

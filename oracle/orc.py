@@ -45,8 +45,10 @@ def build() -> None:
         fresh = False
     if fresh:
         return
+    # -ffp-contract=off: tantivy is Rust, which never fuses a multiply and an add into an fma behind the programmer's back;
+    # it also keeps the oracle's own evaluation forms (exhaustive, pruned) bit-identical to each other
     tmp = LIB + f".tmp{os.getpid()}"
-    subprocess.check_call(["g++", "-O3", "-march=native", "-std=c++17", "-shared", "-fPIC", "-pthread", "-o", tmp, src])
+    subprocess.check_call(["g++", "-O3", "-march=native", "-ffp-contract=off", "-std=c++17", "-shared", "-fPIC", "-pthread", "-o", tmp, src])
     os.replace(tmp, LIB)
     open(mark, "w").write(sig)
 

@@ -59,11 +59,11 @@ def _gpu_tests():
 # `-m gpu` tests under emulation (32 minutes on 8 cores for the whole suite, deep pagination alone 19).
 FAST = {"test_config1_two_term_and", "test_golden_cases_through_dataset_search", "test_upsert_delete_snapshot_semantics",
         "test_gated_column_scan_equals_exhaustive", "test_facet_counts_golden_corpus_with_deletes",
-        "test_delete_only_commit_refreshes_alive_bitset", "test_with_alive_shares_arrays_and_outlives_its_base",
+        "test_delete_only_commit_refreshes_alive_bitset",
         "test_facet_counts_large_synthetic_with_facet_columns", "test_uncommitted_documents_are_invisible", "test_config4_three_term_and_with_deletes",
         "test_config5_facet_filters", "test_edge_cases", "test_sharded_search_and_device_merge",
         "test_accounting_matches_oracle_definition",
-        "test_concurrent_callers_share_one_index", "test_search_while_commits_land", "test_bulk_copy_staged_variant_equals_default",
+        "test_concurrent_callers_share_one_index", "test_search_while_commits_land",
         "test_search_endpoint_shape_defaults_and_hydration", "test_query_json_post_namespace_text_flags_and_clamp", "test_get_front_ends",
         "test_object_record_validate_messages", "test_micro_batcher_concurrent_single_query_requests",
         "test_dataset_commits_append_segments", "test_deep_pagination_beyond_1024", "test_union_of_boolean_queries",
