@@ -2226,15 +2226,16 @@ extern "C" int32_t fg_batch_get_stats(fg_batch* b, fg_batch_stats* out) {
         CU(cudaMemcpy(h, b->d_stats, sizeof(h), cudaMemcpyDeviceToHost));
     }
     if (ctx->env_prof && b->lead) {
-        unsigned long long pr[8], ph[8];
+        unsigned long long pr[8], ph[10];
         cudaMemcpy(pr, b->d_stats + 8, sizeof(pr), cudaMemcpyDeviceToHost);
         cudaMemcpy(ph, b->d_stats + 16, sizeof(ph), cudaMemcpyDeviceToHost);
         unsigned long long ph_tot = 0;
-        for (int i = 0; i < 8; i++) ph_tot += ph[i];
+        for (int i = 0; i < 10; i++) ph_tot += ph[i];
         if (ph_tot)  // (only a library built with make PROFILE=1 fills these)
             fprintf(stderr, "[prof lead phases] %% of warp busy time: plan load %.1f, block walk %.1f, decode %.1f, lookups %.1f, scoring %.1f, "
-                            "top-k + histogram %.1f, append %.1f, other %.1f\n", 100.0 * ph[0] / ph_tot, 100.0 * ph[1] / ph_tot, 100.0 * ph[2] / ph_tot,
-                    100.0 * ph[3] / ph_tot, 100.0 * ph[4] / ph_tot, 100.0 * ph[5] / ph_tot, 100.0 * ph[6] / ph_tot, 100.0 * ph[7] / ph_tot);
+                            "top-k + histogram %.1f, append %.1f, other %.1f; lookups by kind: tf column %.1f, bitmap %.1f, gallop + block %.1f\n", 100.0 * ph[0] / ph_tot, 100.0 * ph[1] / ph_tot, 100.0 * ph[2] / ph_tot,
+                    100.0 * (ph[3] + ph[8] + ph[9]) / ph_tot, 100.0 * ph[4] / ph_tot, 100.0 * ph[5] / ph_tot, 100.0 * ph[6] / ph_tot, 100.0 * ph[7] / ph_tot,
+                    100.0 * ph[3] / ph_tot, 100.0 * ph[8] / ph_tot, 100.0 * ph[9] / ph_tot);
         if (pr[4]) {
             const double start = (double)~pr[5], first_idle = (double)~pr[2] - start, done = (double)pr[3] - start;
             fprintf(stderr, "[prof lead] warps %llu: kernel %.1f us, first warp out of work at %.1f us, busy share %.1f %% of warp-time, longest item %.1f us, "

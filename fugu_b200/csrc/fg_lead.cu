@@ -81,15 +81,15 @@ struct Acct {
 
 // dev tool (make PROFILE=1): time of a warp per phase of run_item, summed into stats[16 + phase] (ns) by lane 0
 #ifdef FG_PROFILE_PHASES
-#define PH_DECL unsigned long long ph_t = global_timer_ns(), ph_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+#define PH_DECL unsigned long long ph_t = global_timer_ns(), ph_acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}
 #define PH_MARK(i) do { const unsigned long long t_ = global_timer_ns(); ph_acc[i] += t_ - ph_t; ph_t = t_; } while (0)
-#define PH_FLUSH() do { if (lane == 0 && p.stats) { for (int i_ = 0; i_ < 8; i_++) atomicAdd(p.stats + 16 + i_, ph_acc[i_]); } } while (0)
+#define PH_FLUSH() do { if (lane == 0 && p.stats) { for (int i_ = 0; i_ < 10; i_++) atomicAdd(p.stats + 16 + i_, ph_acc[i_]); } } while (0)
 #else
 #define PH_DECL
 #define PH_MARK(i)
 #define PH_FLUSH()
 #endif
-enum { PH_PLAN = 0, PH_WALK = 1, PH_DECODE = 2, PH_LOOKUP = 3, PH_SCORE = 4, PH_TOPK = 5, PH_APPEND = 6, PH_OTHER = 7 };
+enum { PH_PLAN = 0, PH_WALK = 1, PH_DECODE = 2, PH_LOOKUP = 3, PH_SCORE = 4, PH_TOPK = 5, PH_APPEND = 6, PH_OTHER = 7, PH_LOOKUP_BM = 8, PH_LOOKUP_PROBE = 9 };
 
 // First block index in [from, n) whose last_doc >= target; n if there is none. Warp-collective
 // (uniform arguments): the next 32 skip entries first (the common case while candidates and blocks
@@ -602,7 +602,7 @@ __device__ __forceinline__ void run_item(const LeadParams& p, const LeadShared& 
                         if (r == 0) tf[0] = t1; else if (r == 1) tf[1] = t1; else if (r == 2) tf[2] = t1; else tf[3] = t1;
                     }
                 }
-                PH_MARK(PH_LOOKUP);
+                PH_MARK(L.col ? PH_LOOKUP : (L.bits ? PH_LOOKUP_BM : PH_LOOKUP_PROBE));
                 // ---- what a hit means ----
                 if (mode == 1) {
 #pragma unroll
