@@ -115,6 +115,10 @@ struct fg_ctx {
     bool env_no_prune = false;    // FG_NO_PRUNE=1: exhaustive evaluation (A/B runs; results are identical)
     bool env_timing = false;      // FG_TIMING=1
     bool env_prof = false;        // FG_PROF=1
+    // fg_batch_submit alternates between these streams: the tail of one pipeline chunk's persistent kernel (warps running out of
+    // work) overlaps the start of the next chunk's instead of serialising behind it
+    cudaStream_t sub[2] = {nullptr, nullptr};
+    uint32_t sub_seq = 0, sub_streams = 2;
     uint32_t lead_par_blocks = 16, lead_max_par = 64, lead_chunk = 16, lead_tma = 0, lead_chunk_req = 48, lead_max_par_req = 1024, lead_union_work = 32;
 };
 static uint64_t env_u64_early(const char* name, uint64_t dflt);
@@ -214,6 +218,8 @@ extern "C" int32_t fg_ctx_create(int32_t device, fg_ctx** out) {
     }
     CU(cudaEventCreateWithFlags(&c->fork_ev, cudaEventDisableTiming));
     CU(cudaStreamCreateWithFlags(&c->up, cudaStreamNonBlocking));
+    c->sub_streams = (uint32_t)std::min<uint64_t>(2, env_u64_early("FG_SUBMIT_STREAMS", 2));
+    for (uint32_t i = 0; i < c->sub_streams; i++) CU(cudaStreamCreateWithFlags(&c->sub[i], cudaStreamNonBlocking));
     *out = guard.release();
     return FG_OK;
 }
@@ -226,6 +232,7 @@ extern "C" void fg_ctx_destroy(fg_ctx* c) {
     for (auto& b : c->pool) cudaFree(b.first);
     for (auto& b : c->hpool) cudaFreeHost(b.first);
     if (c->up) cudaStreamDestroy(c->up);
+    for (auto& st : c->sub) if (st) cudaStreamDestroy(st);
     delete c;
 }
 extern "C" int32_t fg_ctx_set_stream(fg_ctx* c, void* s) {
@@ -1203,6 +1210,7 @@ struct fg_batch {
     void* h_plan = nullptr;        // its page-locked source (kept until release: the upload is asynchronous)
     size_t plan_sz = 0;
     uint64_t* d_sel = nullptr;     // deep-page batches (ks == 0): scratch of lead_select_kernel
+    cudaStream_t exec_stream = nullptr;  // fg_batch_submit: the stream this batch runs on (null = the context's stream)
     uint32_t combine_k = 0;        // fg_search_union_of: the queries are the disjuncts of ONE query with this page limit
     uint64_t* d_comb = nullptr;    // ... and its two scratch arrays of comb_cap2 keys
     uint32_t comb_cap2 = 0;
@@ -1228,6 +1236,7 @@ extern "C" void fg_batch_release(fg_batch* b) {
     if (b->ix && b->ix->ctx) {
         fg_ctx* c = b->ix->ctx;
         cudaStreamSynchronize(c->stream);  // nothing in flight may still use the blocks we recycle
+        if (b->exec_stream) cudaStreamSynchronize(b->exec_stream);
         pool_free(c, b->d_queries, b->sz[0]); pool_free(c, b->d_leaves, b->sz[1]); pool_free(c, b->d_items, b->sz[2]);
         pool_free(c, b->d_partial, b->sz[3]); pool_free(c, b->d_partial_count, b->sz[4]);
         pool_free(c, b->d_stats, b->sz[5]); pool_free(c, b->d_qtheta, b->sz[6]);
@@ -2091,7 +2100,7 @@ extern "C" int32_t fg_batch_execute(fg_batch* b, uint32_t flags, uint32_t k_stri
     fg_ctx* ctx = ix->ctx;
     CU(cudaSetDevice(ctx->device));
     std::lock_guard<std::mutex> g(ctx->mu);
-    cudaStream_t st = ctx->stream;
+    cudaStream_t st = b->exec_stream ? b->exec_stream : ctx->stream;
     CU(cudaStreamWaitEvent(st, b->ev_up, 0));
     CU(cudaMemsetAsync(b->d_stats, 0, (b->lead ? 32 : 16) * sizeof(unsigned long long), st));
     if (b->lead) {
@@ -2377,11 +2386,16 @@ extern "C" int32_t fg_batch_submit(fg_batch* b, uint32_t flags, uint32_t k_strid
     CU(pool_alloc(ctx, &b->d_out, b->out_sz));
     CU(pinned_alloc(ctx, &b->h_out, b->out_sz));
     char* d = (char*)b->d_out;
+    if (b->lead && ctx->sub_streams) {  // (the window kernels share per-context side streams: they stay on the context's stream)
+        std::lock_guard<std::mutex> g(ctx->mu);
+        b->exec_stream = ctx->sub[ctx->sub_seq++ % ctx->sub_streams];
+    }
     int32_t rc = fg_batch_execute(b, flags, k_stride, d, d + hits_b, want_counts ? d + hits_b + nq * 4 : nullptr, nullptr);
     if (rc) return rc;
     std::lock_guard<std::mutex> g(ctx->mu);
-    CU(cudaMemcpyAsync(b->h_out, b->d_out, b->out_sz, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaEventRecord(b->ev_done, ctx->stream));
+    cudaStream_t st = b->exec_stream ? b->exec_stream : ctx->stream;
+    CU(cudaMemcpyAsync(b->h_out, b->d_out, b->out_sz, cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord(b->ev_done, st));
     return FG_OK;
 }
 

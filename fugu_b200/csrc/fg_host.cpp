@@ -1465,6 +1465,9 @@ int32_t search_batch_impl(fgh_dataset* ds, fg_comm* comm, uint32_t n, const char
     // Large requests are cut into a few chunks and pipelined: while the device evaluates chunk i
     // (fg_batch_submit returns at once) this thread parses, plans and lowers chunk i+1, so the host
     // side of the call hides under the kernels instead of adding to them.
+    // (fg_batch_submit alternates between two streams, so the tail of the first chunk's persistent kernel overlaps the start of
+    // the second's: 1.71 -> 1.55 ms per request; more chunks cost the host more than the overlap gains,
+    // profiles/r02h_e2e_submit_streams.txt.)
     // Chunk count (measured on a B200, 5000-query C2 batch, round 2): planning + lowering of the whole request takes
     // ~0.9 ms on 16 host threads, the kernels ~1.5 ms. One chunk: 2.4 ms; two chunks (20 % / 80 %): 2.3 ms; three:
     // 2.5 ms; four: 2.9 ms -- every extra chunk costs the device more (smaller launches fill it worse) than the

@@ -237,7 +237,9 @@ int32_t fg_batch_execute(fg_batch* b, uint32_t flags, uint32_t k_stride, void* d
  * fg_batch_collect blocks until the results have arrived and copies them into the caller's buffers
  * (same layout as fg_search_batch; out_match_count may be NULL, and must be when want_counts was 0).
  * A host thread can plan and prepare batch i+1 while batch i runs: fgh_search_batch pipelines large
- * requests this way. One submit per prepared batch. */
+ * requests this way. One submit per prepared batch. Submitted batches run on two internal streams in turn
+ * (FG_SUBMIT_STREAMS, read at fg_ctx_create; 0 = the context's stream): consecutive batches overlap on the device
+ * where one's persistent kernel runs out of work; each batch's results are ordered by its own fg_batch_collect. */
 int32_t fg_batch_submit(fg_batch* b, uint32_t flags, uint32_t k_stride, int32_t want_counts);
 int32_t fg_batch_collect(fg_batch* b, fg_hit* out_hits, uint32_t* out_n_hits, uint32_t* out_match_count);
 
