@@ -2416,11 +2416,16 @@ extern "C" int32_t fg_batch_submit_sharded(fg_batch* b, fg_comm* comm, uint32_t 
     CU(pool_alloc(ctx, &b->d_out, b->out_sz));
     CU(pinned_alloc(ctx, &b->h_out, b->out_sz));
     char* d = (char*)b->d_out;
+    if (b->lead && ctx->sub_streams) {  // as fg_batch_submit: consecutive chunks overlap (every rank submits in the same order)
+        std::lock_guard<std::mutex> g(ctx->mu);
+        b->exec_stream = ctx->sub[ctx->sub_seq++ % ctx->sub_streams];
+    }
     int32_t rc = fg_batch_execute_sharded(b, comm, flags, k_stride, d, d + hits_b);
     if (rc) return rc;
     std::lock_guard<std::mutex> g(ctx->mu);
-    CU(cudaMemcpyAsync(b->h_out, b->d_out, hits_b + nq * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaEventRecord(b->ev_done, ctx->stream));
+    cudaStream_t st = b->exec_stream ? b->exec_stream : ctx->stream;
+    CU(cudaMemcpyAsync(b->h_out, b->d_out, hits_b + nq * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord(b->ev_done, st));
     return FG_OK;
 }
 
@@ -2508,9 +2513,10 @@ struct fg_comm {
     fg_ctx* ctx = nullptr;
     ncclComm_t comm = nullptr;
     int rank = 0, world = 1;
-    void* d_local = nullptr;    // this shard's [hits n*k_stride | n_hits n]
-    void* d_gather = nullptr;   // [world][hits] then [world][n_hits]
-    size_t local_sz = 0, gather_sz = 0;
+    // exchange buffers, one set per stream a sharded batch may run on (0 = the context's stream, 1 / 2 = the submit streams):
+    void* d_local[3] = {nullptr, nullptr, nullptr};    // this shard's [hits n*k_stride | n_hits n]
+    void* d_gather[3] = {nullptr, nullptr, nullptr};   // [world][hits] then [world][n_hits]
+    size_t local_sz[3] = {0, 0, 0};
     void* d_tmp = nullptr;      // all-reduce staging
     size_t tmp_sz = 0;
 };
@@ -2546,8 +2552,11 @@ extern "C" void fg_comm_destroy(fg_comm* c) {
     cudaSetDevice(c->ctx->device);
     cudaStreamSynchronize(c->ctx->stream);
     if (c->comm) nccl_api().CommDestroy(c->comm);
-    cudaFree(c->d_local);
-    cudaFree(c->d_gather);
+    for (int i = 0; i < 3; i++) {
+        if (i && c->ctx->sub[i - 1]) cudaStreamSynchronize(c->ctx->sub[i - 1]);
+        cudaFree(c->d_local[i]);
+        cudaFree(c->d_gather[i]);
+    }
     cudaFree(c->d_tmp);
     delete c;
 }
@@ -2614,26 +2623,26 @@ extern "C" int32_t fg_batch_execute_sharded(fg_batch* b, fg_comm* c, uint32_t fl
     const size_t nq = b->n_queries;
     if (nq == 0) return FG_OK;
     const size_t hits_b = nq * k_stride * sizeof(fg_hit), n_b = nq * 4, local = hits_b + n_b;
+    cudaStream_t st = b->exec_stream ? b->exec_stream : ctx->stream;
+    const int slot = b->exec_stream == nullptr ? 0 : (b->exec_stream == ctx->sub[0] ? 1 : 2);
     {
         std::lock_guard<std::mutex> g(ctx->mu);
-        if (c->local_sz < local) {
-            CU(cudaStreamSynchronize(ctx->stream));
-            cudaFree(c->d_local);
-            cudaFree(c->d_gather);
-            c->d_local = c->d_gather = nullptr;
-            c->local_sz = c->gather_sz = 0;
-            CU(cudaMalloc(&c->d_local, local));
-            CU(cudaMalloc(&c->d_gather, local * c->world));
-            c->local_sz = local;
-            c->gather_sz = local * c->world;
+        if (c->local_sz[slot] < local) {
+            CU(cudaStreamSynchronize(st));
+            cudaFree(c->d_local[slot]);
+            cudaFree(c->d_gather[slot]);
+            c->d_local[slot] = c->d_gather[slot] = nullptr;
+            c->local_sz[slot] = 0;
+            CU(cudaMalloc(&c->d_local[slot], local));
+            CU(cudaMalloc(&c->d_gather[slot], local * c->world));
+            c->local_sz[slot] = local;
         }
     }
-    char* dl = (char*)c->d_local;
-    char* dg = (char*)c->d_gather;
+    char* dl = (char*)c->d_local[slot];
+    char* dg = (char*)c->d_gather[slot];
     int32_t rc = fg_batch_execute(b, flags, k_stride, dl, dl + hits_b, nullptr, nullptr);
     if (rc) return rc;
     std::lock_guard<std::mutex> g(ctx->mu);
-    cudaStream_t st = ctx->stream;
     NcclApi& n = nccl_api();
     // one fused NCCL launch: the hit lists and their lengths of every shard
     NC(n.GroupStart());
