@@ -754,4 +754,18 @@ def test_union_of_boolean_queries(ctx):
             g_hits, g_cnt = index.search_union_of(batch, k)
             assert g_cnt == o_cnt and len(g_hits) == len(o_hits), (ci, k, g_cnt, o_cnt, len(g_hits), len(o_hits))
             check_topk(g_hits, o_hits, k, ctx=f"union-of case {ci}, k = {k}")
+    # with deleted documents (an alive bitset on the same postings)
+    rng = np.random.default_rng(11)
+    alive = np.full((cfg.n_docs + 31) // 32, 0xFFFFFFFF, np.uint32)
+    for d in rng.choice(cfg.n_docs, 3000, replace=False):
+        alive[d >> 5] &= ~np.uint32(1 << (d & 31))
+    dead_ix = index.with_alive(alive)
+    dead_desc = nat.HostIndexDesc(cfg.n_docs, synth.build_fields(corpus, 0, cfg.n_docs), alive_bitset=alive)
+    for ci, disj in enumerate(cases[:3]):
+        batch = nat.HostBatch([{"k": 1, "clauses": cl} for cl in disj])
+        o_hits, o_cnt = orc.search_union_of(dead_desc, batch, 50)
+        g_hits, g_cnt = dead_ix.search_union_of(batch, 50)
+        assert g_cnt == o_cnt and len(g_hits) == len(o_hits), (ci, g_cnt, o_cnt)
+        check_topk(g_hits, o_hits, 50, ctx=f"union-of with deletes, case {ci}")
+    dead_ix.close()
     index.close()
