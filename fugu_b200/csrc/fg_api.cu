@@ -2519,6 +2519,8 @@ struct fg_comm {
     size_t local_sz[3] = {0, 0, 0};
     void* d_tmp = nullptr;      // all-reduce staging
     size_t tmp_sz = 0;
+    void* h_tmp = nullptr;      // page-locked staging of fg_comm_allgather_bytes ([send | recv x world])
+    size_t h_tmp_sz = 0;
 };
 
 extern "C" int32_t fg_comm_unique_id(void* out_id) {
@@ -2558,6 +2560,7 @@ extern "C" void fg_comm_destroy(fg_comm* c) {
         cudaFree(c->d_gather[i]);
     }
     cudaFree(c->d_tmp);
+    if (c->h_tmp) cudaFreeHost(c->h_tmp);
     delete c;
 }
 extern "C" int32_t fg_comm_info(const fg_comm* c, int32_t* rank, int32_t* n_ranks) {
@@ -2582,13 +2585,24 @@ extern "C" int32_t fg_comm_allgather_bytes(fg_comm* c, const void* send, size_t 
         CU(cudaMalloc(&c->d_tmp, need + (need >> 1)));
         c->tmp_sz = need + (need >> 1);
     }
+    if (c->h_tmp_sz < need) {  // page-locked staging: the copies run at bus speed and truly asynchronously
+        if (c->h_tmp) cudaFreeHost(c->h_tmp);
+        c->h_tmp = nullptr;
+        c->h_tmp_sz = 0;
+        CU(cudaHostAlloc(&c->h_tmp, need + (need >> 1), cudaHostAllocDefault));
+        c->h_tmp_sz = need + (need >> 1);
+    }
     char* d_send = (char*)c->d_tmp;
     char* d_recv = d_send + bytes;
+    char* h_send = (char*)c->h_tmp;
+    char* h_recv = h_send + bytes;
+    memcpy(h_send, send, bytes);
     cudaStream_t st = ctx->stream;
-    CU(cudaMemcpyAsync(d_send, send, bytes, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_send, h_send, bytes, cudaMemcpyHostToDevice, st));
     NC(nccl_api().AllGather(d_send, d_recv, bytes, ncclUint8, c->comm, st));
-    CU(cudaMemcpyAsync(recv, d_recv, bytes * c->world, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h_recv, d_recv, bytes * c->world, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    memcpy(recv, h_recv, bytes * c->world);
     return FG_OK;
 }
 static int32_t comm_allreduce(fg_comm* c, void* values, size_t n, size_t elem, ncclDataType_t dt) {

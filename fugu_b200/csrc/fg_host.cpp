@@ -1374,32 +1374,31 @@ int32_t plan_batch_shared(const fgh_dataset* ds, fg_comm* comm, uint32_t n, cons
             if (int32_t rc = exchange(mc, ml)) return rc;
     }
     const size_t o_q = sizeof(Hdr);
-    pb.q.clear(); pb.c.clear(); pb.l.clear(); pb.offset.clear(); pb.rc.clear();
+    // unpack: sizes first, then every rank's arrays with one copy each and a fix-up of the indices they carry
+    size_t tq = 0, tc = 0, tl = 0;
+    for (const Hdr& x : hs) { tq += x.nq; tc += x.nc; tl += x.nl; }
+    pb.q.resize(tq); pb.offset.resize(tq); pb.rc.resize(tq); pb.c.resize(tc); pb.l.resize(tl);
     pb.kmax = 1;
     pb.first_err = FG_OK;
+    size_t qb_ = 0, cb = 0, lb = 0;
     for (int r = 0; r < world; r++) {
         const char* p = recv.data() + rec * (size_t)r;
         const Hdr& x = hs[(size_t)r];
-        const uint32_t cb = (uint32_t)pb.c.size(), lb = (uint32_t)pb.l.size();
-        const fg_query* q = reinterpret_cast<const fg_query*>(p + o_q);
-        const uint32_t* off = reinterpret_cast<const uint32_t*>(p + o_off);
-        const int32_t* rc = reinterpret_cast<const int32_t*>(p + o_rc);
-        const fg_clause* c = reinterpret_cast<const fg_clause*>(p + o_c);
-        const fg_leaf* l = reinterpret_cast<const fg_leaf*>(p + o_l);
-        for (uint32_t i = 0; i < x.nq; i++) {
-            fg_query qq = q[i];
-            qq.clause_begin += cb;
-            pb.q.push_back(qq);
-            pb.offset.push_back(off[i]);
-            pb.rc.push_back(rc[i]);
-            pb.kmax = std::max(pb.kmax, qq.k);
+        if (x.nq) {
+            memcpy(pb.q.data() + qb_, p + o_q, (size_t)x.nq * sizeof(fg_query));
+            memcpy(pb.offset.data() + qb_, p + o_off, (size_t)x.nq * 4);
+            memcpy(pb.rc.data() + qb_, p + o_rc, (size_t)x.nq * 4);
+            for (size_t i = qb_; i < qb_ + x.nq; i++) {
+                pb.q[i].clause_begin += (uint32_t)cb;
+                pb.kmax = std::max(pb.kmax, pb.q[i].k);
+            }
         }
-        for (uint32_t i = 0; i < x.nc; i++) {
-            fg_clause cc = c[i];
-            cc.leaf_begin += lb;
-            pb.c.push_back(cc);
+        if (x.nc) {
+            memcpy(pb.c.data() + cb, p + o_c, (size_t)x.nc * sizeof(fg_clause));
+            for (size_t i = cb; i < cb + x.nc; i++) pb.c[i].leaf_begin += (uint32_t)lb;
         }
-        pb.l.insert(pb.l.end(), l, l + x.nl);
+        if (x.nl) memcpy(pb.l.data() + lb, p + o_l, (size_t)x.nl * sizeof(fg_leaf));
+        qb_ += x.nq; cb += x.nc; lb += x.nl;
         if (x.first_err && !pb.first_err) {
             pb.first_err = x.first_err;
             pb.first_msg = r == rank ? mine.first_msg : std::string("a query of the request failed to plan (planned by rank ") + std::to_string(r) + ")";
