@@ -203,6 +203,56 @@ def compare_topk(gs, gd, os_, od, k, tol=1e-5):
     return None
 
 
+def check_apart_sharded(ds, comm, queries, batch, pdesc, rank):
+    """N > 1: the requests the fused exchange does not take -- deep pages (limit above 1024) and nested boolean queries --
+    through the collective host call (every shard answers them alone, pages merged on the host). COLLECTIVE: every rank
+    calls; rank 0 checks: complete deep lists against the oracle's ranking of the unsharded corpus, the deep page as
+    rows of that list, a nested query (A) OR (B) against the oracle's union of A's and B's scorers."""
+    from fugu_b200 import _native as nat
+    from fugu_b200.dataset import QuerySet
+
+    nd, limit, pp = 8, 3100, 100
+    base = [q["query"] for q in queries[:80]]
+    nested = [f"({base[2 * i]}) OR ({base[2 * i + 1]})" for i in range(4)]
+    whole = QuerySet(base[:nd], None, 0, limit)                 # complete first 3100 of 8 queries
+    w_hits, w_n, w_st = ds.search_batch_sharded(comm, whole)
+    mixed = QuerySet(base + nested, None, 0, pp)                # ordinary pages + deep pages + nested, one request
+    mixed.pages[:nd] = limit // pp - 1
+    m_hits, m_n, m_st = ds.search_batch_sharded(comm, mixed)
+    if rank != 0:
+        return None
+    from oracle import orc  # checker only
+
+    failed, first = 0, None
+
+    def bad(msg):
+        nonlocal failed, first
+        failed += 1
+        first = first or msg
+
+    if not ((w_st == 0).all() and (m_st == 0).all()):
+        bad(f"status {w_st.tolist()} {m_st[m_st != 0].tolist()}")
+    q = batch.q[:nd].copy()
+    q["k"] = limit
+    o_hits, o_n, _ = orc.search(pdesc, nat.HostBatch.from_arrays(q, batch.c, batch.l), threads=host_cores())
+    for i in range(nd):
+        msg = compare_topk(w_hits[i, :w_n[i]]["score"], w_hits[i, :w_n[i]]["doc"], o_hits["score"][i, :o_n[i]], o_hits["doc"][i, :o_n[i]], limit)
+        if msg:
+            bad(f"deep list {i} ({base[i]!r}): {msg}")
+        want = w_hits[i, limit - pp:w_n[i]]
+        if m_n[i] != len(want) or not np.array_equal(m_hits[i, :m_n[i]], want):
+            bad(f"deep page {i} ({base[i]!r}) is not rows [{limit - pp}, {limit}) of the complete list")
+    for j, s_ in enumerate(nested):
+        children = nat.HostBatch.from_arrays(batch.q[[2 * j, 2 * j + 1]].copy(), batch.c, batch.l)
+        u_hits, _ = orc.search_union_of(pdesc, children, pp)   # the oracle's union of the two children's scorers
+        qi = len(base) + j
+        msg = compare_topk(m_hits[qi, :m_n[qi]]["score"], m_hits[qi, :m_n[qi]]["doc"], u_hits["score"], u_hits["doc"], pp)
+        if msg:
+            bad(f"nested {s_!r}: {msg}")
+    return {"checked": 2 * nd + len(nested), "failed": failed, "first_failure": first,
+            "what": "fgh_search_batch_sharded: deep lists vs oracle, deep pages as rows of them, nested (A) OR (B) vs the oracle's union of the children"}
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU path on the box's host cores. The real reference
     (Rust + tantivy 0.24.1) cannot be built here, so this is the oracle port (oracle/oracle.cpp)."""
@@ -559,6 +609,10 @@ def main():
         assert (e_status == 0).all() and np.array_equal(e_n, ref_n), "fgh_search_batch_sharded: hit counts differ from the device path"
         for qi in range(nq):
             assert np.array_equal(e_hits[qi, :e_n[qi]]["doc"], ref_h[qi, :ref_n[qi], 1]), f"fgh_search_batch_sharded: query {qi} differs"
+    apart_check = None
+    if comm and not args.no_cpu_baseline and len(queries) >= 80 and not any(q.get("filters") for q in queries[:80]) \
+            and not os.environ.get("FG_BENCH_NO_APART"):
+        apart_check = check_apart_sharded(ds, comm, queries, batch, pdesc if rank == 0 else None, rank)
     if os.environ.get("FG_TIMING"):
         print("e2e_times ms", [round(x * 1e3, 2) for x in e2e_times], file=sys.stderr)
     if dist:
@@ -620,6 +674,7 @@ def main():
                          "(host); requests of 3072 queries and more are pipelined in two chunks (35 / 65 %%); match counts %s" % ("on" if counts else "off (TopDocs does not count)"))},
         "gpu_launches": int(st_timed.n_launches + (1 if world > 1 else 0)) * args.steps,
         "parity": parity,
+        "parity_deep_and_nested_sharded": apart_check,
         "ms_per_step_min": float(np.min(step_ms)), "ms_per_step_median": float(np.median(step_ms)),
         "clocks": clocks,
         "index": {"postings": int(info.n_postings), "blocks": int(info.n_blocks), "packed_bytes": int(info.packed_bytes),
@@ -655,6 +710,9 @@ def main():
     sys.stdout.flush()
     os.write(json_fd, (json.dumps(line) + "\n").encode())
     shutdown()
+    if apart_check and apart_check["failed"]:
+        sys.stderr.write(f"bench.py: PARITY FAILURE of deep pages / nested queries across shards: {apart_check}\n")
+        sys.exit(3)
     if parity and parity["failed"]:
         sys.stderr.write(f"bench.py: PARITY FAILURE on the benchmarked batch: {parity}\n")
         sys.exit(3)

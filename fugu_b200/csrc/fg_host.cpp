@@ -1107,6 +1107,9 @@ extern "C" int32_t fgh_plan(const fgh_dataset* ds, const char* query, const char
 }
 
 namespace {
+// Internal per-query marker of the shared planner (never leaves the library): a nested boolean query, which a sharded
+// request answers apart (every shard evaluates it locally, the pages are merged on the host).
+constexpr int32_t RC_NESTED = 0x4E45;
 // plan n requests (multi-threaded) into one flat batch; failed plans become empty queries
 struct PlannedBatch {
     std::vector<fg_query> q;
@@ -1196,7 +1199,7 @@ bool plan_fast(const fgh_dataset* ds, const char* q, uint32_t page, uint32_t per
 
 void plan_batch(const fgh_dataset* ds, uint32_t n, const char* const* queries, const char* const* filters,
                 const uint32_t* filter_offsets, const uint32_t* pages, const uint32_t* per_pages, PlannedBatch& pb,
-                bool keep_composites = false) {
+                bool keep_composites = false, bool mark_composites = false) {
     std::shared_lock<std::shared_mutex> dict_lock(ds->mu);  // held for the worker threads too: the dictionaries must not grow under the planner
     pb.rc.assign(n, FG_OK);
     pb.q.resize(n);
@@ -1221,8 +1224,9 @@ void plan_batch(const fgh_dataset* ds, uint32_t n, const char* const* queries, c
             if (f1 == f0 && plan_fast(ds, queries[i], page, pp, P.c, P.l, pb.q[i], pb.offset[i])) continue;
             pb.rc[i] = plan_impl(ds, queries[i], filters ? filters + f0 : nullptr, f1 - f0, page, pp, &plan);
             if (pb.rc[i] == FG_OK && plan.n_disjuncts) {
-                if (keep_composites) {  // answered apart (fg_search_union_of): an empty query holds its place in the flat batch
-                    P.comp.emplace_back(i, plan);
+                if (keep_composites || mark_composites) {  // answered apart (fg_search_union_of): an empty query holds its place in the flat batch
+                    if (keep_composites) P.comp.emplace_back(i, plan);
+                    else pb.rc[i] = RC_NESTED;  // (sharded requests: every rank re-plans it for its own shard)
                     pb.q[i].k = 1;
                     pb.q[i].clause_begin = (uint32_t)P.c.size();
                     pb.q[i].n_clauses = 0;
@@ -1284,7 +1288,7 @@ void plan_batch(const fgh_dataset* ds, uint32_t n, const char* const* queries, c
         if (pb.first_err) continue;
         Part& P = parts[t];
         for (uint32_t i = P.a; i < P.b; i++)
-            if (pb.rc[i] != FG_OK) { pb.first_err = pb.rc[i]; pb.first_msg = P.errs[i - P.a]; break; }
+            if (pb.rc[i] != FG_OK && pb.rc[i] != RC_NESTED) { pb.first_err = pb.rc[i]; pb.first_msg = P.errs[i - P.a]; break; }
     }
     if (timing) {
         clock_gettime(CLOCK_MONOTONIC, &ts2);
@@ -1323,13 +1327,13 @@ int32_t plan_batch_shared(const fgh_dataset* ds, fg_comm* comm, uint32_t n, cons
     int32_t rank = 0, world = 1;
     if (comm) D(dev_api().fg_comm_info(comm, &rank, &world));
     if (world <= 1 || n < (uint32_t)world * 32u) {
-        plan_batch(ds, n, queries, filters, filter_offsets, pages, per_pages, pb);
+        plan_batch(ds, n, queries, filters, filter_offsets, pages, per_pages, pb, false, /*mark_composites=*/true);
         return FG_OK;
     }
     const uint32_t a = (uint32_t)((uint64_t)n * rank / world), b = (uint32_t)((uint64_t)n * (rank + 1) / world);
     PlannedBatch mine;
     plan_batch(ds, b - a, queries + a, filters, filter_offsets ? filter_offsets + a : nullptr, pages ? pages + a : nullptr,
-               per_pages ? per_pages + a : nullptr, mine);
+               per_pages ? per_pages + a : nullptr, mine, false, /*mark_composites=*/true);
     // One collective in the common case: every rank sends a fixed-size record sized for plain word queries (<= 4 clauses
     // and 8 leaves per query) with its array lengths in a header; a rank whose plans do not fit says so in the header
     // and all ranks repeat the exchange with records sized for the largest rank.
@@ -1411,6 +1415,105 @@ int32_t search_batch_impl(fgh_dataset* ds, fg_comm* comm, uint32_t n, const char
                           const char* const* filters, const uint32_t* filter_offsets,
                           const uint32_t* pages, const uint32_t* per_pages, uint32_t stride,
                           fg_hit* out_hits, uint32_t* out_n, uint32_t* out_match_count,
+                          int32_t* status);
+
+// TopDocs order (score descending, doc id ascending inside ties): what the device's 64-bit keys sort by.
+inline bool hit_before(const fg_hit& a, const fg_hit& b) { return a.score > b.score || (a.score == b.score && a.doc < b.doc); }
+
+// Merge per-shard result lists (each in TopDocs order, doc ids global and disjoint between shards) and cut the page
+// [offset, offset + per_page) out of the first `limit` hits of the merged order.
+uint32_t merge_shard_pages(const fg_hit* const* lists, const uint32_t* lens, uint32_t n_lists, uint64_t limit, uint64_t offset,
+                           uint32_t per_page, fg_hit* out) {
+    std::vector<fg_hit> all;
+    size_t total = 0;
+    for (uint32_t r = 0; r < n_lists; r++) total += lens[r];
+    all.reserve(total);
+    for (uint32_t r = 0; r < n_lists; r++) all.insert(all.end(), lists[r], lists[r] + lens[r]);
+    const size_t keep = (size_t)std::min<uint64_t>(limit, all.size());
+    std::partial_sort(all.begin(), all.begin() + keep, all.end(), hit_before);
+    if (offset >= keep) return 0;
+    const uint32_t take = (uint32_t)std::min<uint64_t>(keep - offset, per_page);
+    if (take) memcpy(out, all.data() + offset, (size_t)take * sizeof(fg_hit));
+    return take;
+}
+
+// Sharded requests, the queries the fused exchange does not take (deep pages, nested boolean queries): every rank
+// evaluates them on its own shard through the one-GPU path (statistics are global, so scores are final; a document
+// lives in exactly one shard, so a nested query's sums are complete there), then two collectives for all of them
+// together -- (status, length) per query, then the hit lists padded to the longest rank -- and every rank merges.
+// A shard cannot contribute more than `limit` hits to the first `limit` of the merged order.
+int32_t answer_apart_sharded(fgh_dataset* ds, fg_comm* comm, const std::vector<uint32_t>& apart, const char* const* queries,
+                             const char* const* filters, const uint32_t* filter_offsets, const uint32_t* pages,
+                             const uint32_t* per_pages, uint32_t stride, fg_hit* out_hits, uint32_t* out_n, int32_t* status) {
+    int32_t rank = 0, world = 1;
+    if (int32_t r = D(dev_api().fg_comm_info(comm, &rank, &world))) return r;
+    const uint32_t m = (uint32_t)apart.size();
+    struct Rec { int32_t st; uint32_t n; };
+    std::vector<Rec> mine(m), all((size_t)m * world);
+    std::vector<fg_hit> loc, buf;
+    std::vector<std::string> msgs(m);
+    const uint32_t local_docs = std::max(1u, ds->n_docs);
+    for (uint32_t j = 0; j < m; j++) {
+        const uint32_t i = apart[j];
+        const uint32_t page = pages ? pages[i] : 0, pp = per_pages ? per_pages[i] : 20;
+        const uint64_t limit = (uint64_t)page * pp + pp;
+        const uint32_t want = (uint32_t)std::min<uint64_t>(limit, local_docs), zero = 0;
+        const uint32_t f0 = filter_offsets ? filter_offsets[i] : 0, f1 = filter_offsets ? filter_offsets[i + 1] : 0;
+        const uint32_t fo[2] = {0, f1 - f0};
+        buf.resize(want);
+        uint32_t nh = 0;
+        int32_t st = FG_OK;
+        // (a hard failure is kept as this query's status: the collectives below must still be entered by every rank)
+        const int32_t rc = search_batch_impl(ds, nullptr, 1, queries + i, filters ? filters + f0 : nullptr, fo, &zero, &want, want,
+                                             buf.data(), &nh, nullptr, &st);
+        if (rc || st) { mine[j] = Rec{rc ? rc : st, 0u}; msgs[j] = g_herr; continue; }
+        mine[j] = Rec{FG_OK, nh};
+        loc.insert(loc.end(), buf.begin(), buf.begin() + nh);
+    }
+    if (int32_t r = D(dev_api().fg_comm_allgather_bytes(comm, mine.data(), (size_t)m * sizeof(Rec), all.data()))) return r;
+    std::vector<size_t> tot((size_t)world, 0);
+    size_t longest = 0;
+    for (int r = 0; r < world; r++) {
+        for (uint32_t j = 0; j < m; j++) tot[(size_t)r] += all[(size_t)r * m + j].n;
+        longest = std::max(longest, tot[(size_t)r]);
+    }
+    std::vector<fg_hit> gathered(longest * (size_t)world);
+    if (longest) {
+        loc.resize(longest, fg_hit{0.f, 0u});
+        if (int32_t r = D(dev_api().fg_comm_allgather_bytes(comm, loc.data(), longest * sizeof(fg_hit), gathered.data()))) return r;
+    }
+    std::vector<size_t> at((size_t)world, 0);  // start of query j's hits inside every rank's list
+    std::vector<const fg_hit*> lists((size_t)world);
+    std::vector<uint32_t> lens((size_t)world);
+    for (uint32_t j = 0; j < m; j++) {
+        const uint32_t i = apart[j];
+        int32_t st = FG_OK, bad_rank = -1;
+        for (int r = 0; r < world; r++) {
+            const Rec& x = all[(size_t)r * m + j];
+            if (x.st != FG_OK && st == FG_OK) { st = x.st; bad_rank = r; }
+            lists[(size_t)r] = gathered.data() + (size_t)r * longest + at[(size_t)r];
+            lens[(size_t)r] = x.n;
+            at[(size_t)r] += x.n;
+        }
+        out_n[i] = 0;
+        if (st != FG_OK) {
+            if (bad_rank == rank) host_fail(st, "%s", msgs[j].c_str());
+            else host_fail(st, "query '%s' failed on the shard of rank %d", queries[i], bad_rank);
+            if (!status) return st;
+            status[i] = st;
+            continue;
+        }
+        const uint32_t page = pages ? pages[i] : 0, pp = per_pages ? per_pages[i] : 20;
+        out_n[i] = merge_shard_pages(lists.data(), lens.data(), (uint32_t)world, (uint64_t)page * pp + pp, (uint64_t)page * pp,
+                                     std::min(pp, stride), out_hits + (size_t)i * stride);
+    }
+    return FG_OK;
+}
+
+int32_t search_batch_impl(fgh_dataset* ds, fg_comm* comm, uint32_t n, const char* const* queries,
+                          const char* const* filters, const uint32_t* filter_offsets,
+                          const uint32_t* pages, const uint32_t* per_pages, uint32_t stride,
+                          fg_hit* out_hits, uint32_t* out_n, uint32_t* out_match_count,
                           int32_t* status) {
     if (!ds || (n && (!queries || !out_hits || !out_n))) return host_fail(FG_ERR_INVALID, "fgh_search_batch: NULL argument");
     const std::shared_ptr<fg_index> snap = current_snapshot(ds);  // held until the results are collected
@@ -1484,9 +1587,23 @@ int32_t search_batch_impl(fgh_dataset* ds, fg_comm* comm, uint32_t n, const char
     // the context's stream: between chunks it would queue up behind the previous chunk's kernels); the chunks then only
     // lower and submit.
     PlannedBatch whole;
+    std::vector<uint32_t> apart;
     const bool planned_whole = comm != nullptr;
     if (planned_whole) {
         if (int32_t prc = plan_batch_shared(ds, comm, n, queries, filters, filter_offsets, pages, per_pages, whole)) return prc;
+        // Deep pages (limit above 1024) and nested boolean queries do not go through the fused exchange (its lists are
+        // k_stride wide; a nested query is several device queries): an empty query holds their place in the flat batch
+        // and answer_apart_sharded evaluates them per shard and merges the pages on the host.
+        for (uint32_t i = 0; i < n; i++) {
+            if (whole.rc[i] == RC_NESTED) {
+                whole.rc[i] = FG_OK;
+                apart.push_back(i);
+            } else if (whole.rc[i] == FG_OK && whole.q[i].k > 1024) {
+                whole.q[i].k = 1;
+                whole.q[i].n_clauses = 0;
+                apart.push_back(i);
+            }
+        }
         if (status) memcpy(status, whole.rc.data(), n * sizeof(int32_t));
         if (whole.first_err && !status) return host_fail(whole.first_err, "%s", whole.first_msg.c_str());
     }
@@ -1617,6 +1734,8 @@ int32_t search_batch_impl(fgh_dataset* ds, fg_comm* comm, uint32_t n, const char
             if (out_match_count) out_match_count[qi] = n_match;
         }
     }
+    if (!apart.empty())
+        if (int32_t r = answer_apart_sharded(ds, comm, apart, queries, filters, filter_offsets, pages, per_pages, stride, out_hits, out_n, status)) return r;
     if (timing)
         fprintf(stderr, "[fgh_search_batch] n=%u chunks=%u: plan %.2f prepare %.2f submit %.2f | all submitted at %.2f, done at %.2f ms\n",
                 n, nch, t_plan, t_prep, t_sub, t_submitted - t_start, now_ms() - t_start);
@@ -1639,6 +1758,12 @@ extern "C" int32_t fgh_search_batch_sharded(fgh_dataset* ds, fg_comm* comm, uint
                                             fg_hit* out_hits, uint32_t* out_n, int32_t* status) {
     if (!comm) return host_fail(FG_ERR_INVALID, "fgh_search_batch_sharded: NULL communicator");
     return search_batch_impl(ds, comm, n, queries, filters, filter_offsets, pages, per_pages, stride, out_hits, out_n, nullptr, status);
+}
+
+extern "C" uint32_t fgh_merge_shard_pages(const fg_hit* const* lists, const uint32_t* lens, uint32_t n_lists, uint32_t page,
+                                          uint32_t per_page, fg_hit* out_hits) {
+    if (!n_lists || !lists || !lens || !out_hits || !per_page) return 0;
+    return merge_shard_pages(lists, lens, n_lists, (uint64_t)page * per_page + per_page, (uint64_t)page * per_page, per_page, out_hits);
 }
 
 extern "C" int32_t fgh_search(fgh_dataset* ds, const char* query, const char* const* filters, uint32_t n_filters,

@@ -55,7 +55,7 @@ HOST_SYMBOLS = [
     "fgh_last_error", "fgh_dataset_create", "fgh_dataset_destroy", "fgh_dataset_upsert", "fgh_dataset_delete", "fgh_dataset_commit", "fgh_dataset_commit_counts",
     "fgh_dataset_adopt", "fgh_dataset_num_docs", "fgh_dataset_index", "fgh_dataset_doc_id", "fgh_dataset_term_ord",
     "fgh_tokenize", "fgh_plan", "fgh_plan_batch", "fgh_search", "fgh_search_batch", "fgh_search_batch_sharded",
-    "fgh_facet_children", "fgh_facet_counts",
+    "fgh_merge_shard_pages", "fgh_facet_children", "fgh_facet_counts",
     "fgh_batcher_create", "fgh_batcher_destroy", "fgh_batcher_search", "fgh_batcher_get_stats",
 ]
 _bound = False
@@ -88,6 +88,8 @@ def _L():
         L.fgh_search.argtypes = [vp, C.c_char_p, cpp, u32, u32, u32, vp, vp, vp]
         L.fgh_search_batch.argtypes = [vp, u32, cpp, cpp, vp, vp, vp, u32, vp, vp, vp, vp]
         L.fgh_search_batch_sharded.argtypes = [vp, vp, u32, cpp, cpp, vp, vp, vp, u32, vp, vp, vp]
+        L.fgh_merge_shard_pages.argtypes = [vp, vp, u32, u32, u32, vp]
+        L.fgh_merge_shard_pages.restype = u32
         for fn in (L.fgh_facet_children, L.fgh_facet_counts):
             fn.argtypes = [vp, C.c_char_p, u32, vp, u32, vp, u32, C.POINTER(u32), C.POINTER(u32)]
         L.fgh_batcher_create.argtypes = [vp, u32, u32, C.POINTER(vp)]
@@ -97,6 +99,18 @@ def _L():
         L.fgh_batcher_get_stats.argtypes = [vp, vp]
         _bound = True
     return L
+
+
+def merge_shard_pages(lists: list[np.ndarray], page: int, per_page: int) -> np.ndarray:
+    """fgh_merge_shard_pages: the page skip(page*per_page).take(per_page) of the merged order of per-shard result lists
+    (each in TopDocs order, global doc ids)."""
+    _L()
+    ls = [np.ascontiguousarray(x, nat.HIT_DT) for x in lists]
+    ptrs = (C.c_void_p * max(len(ls), 1))(*[x.ctypes.data for x in ls])
+    lens = np.array([len(x) for x in ls], np.uint32)
+    out = np.zeros(max(per_page, 1), nat.HIT_DT)
+    n = _L().fgh_merge_shard_pages(ptrs, lens.ctypes.data, len(ls), page, per_page, out.ctypes.data)
+    return out[:n]
 
 
 def tokenize(text: str) -> list[str]:

@@ -147,13 +147,23 @@ int32_t fgh_search_batch(fgh_dataset* ds, uint32_t n, const char* const* queries
  * (fg_comm in fugu_gpu.h): a COLLECTIVE call -- every rank passes the same queries and gets the
  * same, global, result. The ranks share the planning (each plans 1/n_ranks of the request, the plans are
  * all-gathered), every rank lowers the plan for its own shard, and each pipeline chunk ends in the library's fused
- * exchange (local top-k -> ncclAllGather -> merge). Match counts are not available; a request with a page limit
- * above 1024 fails with FG_ERR_UNSUPPORTED (deep pages are not merged across shards). The dataset must have been adopted from this rank's shard with the
- * GLOBAL statistics (fgh_dataset_adopt with fg_index_desc.global_*). */
+ * exchange (local top-k -> ncclAllGather -> merge). Match counts are not available. Requests the fused exchange does
+ * not take -- page limits above 1024 (the reference bounds per_page, not page: src/server/handlers/search.rs:370-374)
+ * and nested boolean queries -- are evaluated by every rank on its own shard through the one-GPU path and merged on
+ * the host (fgh_merge_shard_pages) after two collectives for all of them together. The dataset must have been
+ * adopted from this rank's shard with the GLOBAL statistics (fgh_dataset_adopt with fg_index_desc.global_*). */
 int32_t fgh_search_batch_sharded(fgh_dataset* ds, fg_comm* comm, uint32_t n, const char* const* queries,
                                  const char* const* filters, const uint32_t* filter_offsets, const uint32_t* pages,
                                  const uint32_t* per_pages, uint32_t per_page_stride, fg_hit* out_hits,
                                  uint32_t* out_n, int32_t* status);
+
+/* Merge of per-shard result lists on the host (a host that drives several shards from one process, or gathers the
+ * shards' lists itself, uses the same merge fgh_search_batch_sharded does): lists[r][0..lens[r]) is shard r's result
+ * in TopDocs order (score descending, doc id ascending inside ties; global doc ids, a document lives in one shard),
+ * each at least min(page*per_page + per_page, matches of the shard) long. Writes the page
+ * skip(page*per_page).take(per_page) of the merged order (src/db/search.rs:154-160, 210-211) and returns its length. */
+uint32_t fgh_merge_shard_pages(const fg_hit* const* lists, const uint32_t* lens, uint32_t n_lists, uint32_t page,
+                               uint32_t per_page, fg_hit* out_hits);
 
 /* ---- micro-batcher ----------------------------------------------------
  * The reference's HTTP API is one query per request (search_endpoint, src/server/handlers/search.rs:152;

@@ -126,6 +126,9 @@ extern "C" {
     pub fn fgh_search_batch_sharded(ds: *mut fgh_dataset, comm: *mut fg_comm, n: u32, queries: *const *const c_char,
                                     filters: *const *const c_char, filter_offsets: *const u32, pages: *const u32,
                                     per_pages: *const u32, stride: u32, out_hits: *mut fg_hit, out_n: *mut u32, status: *mut i32) -> i32;
+    // host-side merge of per-shard result lists (what fgh_search_batch_sharded uses for deep pages and nested queries)
+    pub fn fgh_merge_shard_pages(lists: *const *const fg_hit, lens: *const u32, n_lists: u32, page: u32, per_page: u32,
+                                 out_hits: *mut fg_hit) -> u32;
     // micro-batcher for the one-query-per-request handlers (src/server/handlers/search.rs:152): blocking, any thread
     pub fn fgh_batcher_create(ds: *mut fgh_dataset, max_batch: u32, max_wait_us: u32, out: *mut *mut fgh_batcher) -> i32;
     pub fn fgh_batcher_destroy(b: *mut fgh_batcher);

@@ -40,9 +40,10 @@ def _gpu_tests():
     import tests.test_facets as tf
     import tests.test_gpu_parity as gp
     import tests.test_handlers as th
+    import tests.test_sharded_host_call as sh
 
     out = []
-    for mod in (gp, tf, th):
+    for mod in (gp, tf, th, sh):
         for name in sorted(dir(mod)):
             fn = getattr(mod, name)
             if not name.startswith("test_") or not callable(fn):
@@ -67,7 +68,7 @@ FAST = {"test_config1_two_term_and", "test_golden_cases_through_dataset_search",
         "test_search_endpoint_shape_defaults_and_hydration", "test_query_json_post_namespace_text_flags_and_clamp", "test_get_front_ends",
         "test_object_record_validate_messages", "test_micro_batcher_concurrent_single_query_requests",
         "test_dataset_commits_append_segments", "test_deep_pagination_beyond_1024", "test_union_of_boolean_queries",
-        "test_nested_boolean_queries_through_dataset_search"}
+        "test_nested_boolean_queries_through_dataset_search", "test_shards_merged_on_the_host_equal_the_single_index"}
 
 
 @pytest.mark.parametrize("fn", _gpu_tests())

@@ -1,0 +1,137 @@
+"""Deep pages (limit above 1024) and nested boolean queries over doc-id-range shards: what fgh_search_batch_sharded
+does for the requests its fused exchange does not take -- every shard answers alone through the one-GPU path, the
+per-shard lists are merged on the host (fgh_merge_shard_pages). The reference bounds per_page, not page
+(/root/reference/src/server/handlers/search.rs:370-374; limit = page*per_page + per_page, src/db/search.rs:154-160)."""
+import numpy as np
+import pytest
+
+from fugu_b200 import _native as nat
+from fugu_b200 import synth
+from fugu_b200.dataset import Dataset, QuerySet, merge_shard_pages
+
+
+def _topdocs_order(h):
+    return h[np.lexsort((h["doc"], -h["score"].astype(np.float64)))]
+
+
+def test_merge_shard_pages_equals_global_order():
+    """CPU: the merged page == rows [page*per_page, +per_page) of the global TopDocs order (score desc, doc asc inside
+    ties), for lists cut at the limit, empty shards, pages past the end and heavy score ties."""
+    rng = np.random.default_rng(5)
+    for trial in range(40):
+        n, R = int(rng.integers(0, 4000)), int(rng.integers(1, 6))
+        allh = np.zeros(n, nat.HIT_DT)
+        allh["doc"] = rng.permutation(10 * n + 7)[:n]
+        allh["score"] = rng.integers(1, 12 if trial % 2 else 1 << 20, n).astype(np.float32) / 8  # odd trials: almost all tied
+        bounds = np.sort(rng.integers(0, 10 * n + 8, R - 1)).tolist()
+        shard_of = np.searchsorted(np.array(bounds, np.int64), allh["doc"], side="right") if R > 1 else np.zeros(n, np.int64)
+        page, pp = int(rng.integers(0, 40)), int(rng.integers(1, 150))
+        limit = page * pp + pp
+        lists = [_topdocs_order(allh[shard_of == r])[:limit] for r in range(R)]  # a shard sends at most `limit` hits
+        if trial % 5 == 0:
+            lists.append(np.zeros(0, nat.HIT_DT))
+        got = merge_shard_pages(lists, page, pp)
+        want = _topdocs_order(allh)[page * pp:limit]
+        assert len(got) == len(want) and np.array_equal(got, want), (trial, n, R, page, pp)
+    assert len(merge_shard_pages([], 0, 10)) == 0
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_collective_call_with_ranks_as_threads_emulated(world):
+    """CPU: fgh_search_batch_sharded with world_size 2 and 3 -- ranks are threads of one process over the emulated
+    library and an in-process NCCL stand-in (tests/emu/fake_nccl.cpp): shared planning, the fused exchange + merge,
+    and the per-shard answers of deep pages and nested queries, against the unsharded dataset. In a subprocess: the
+    stand-in must be mapped before any other libnccl.so.2 (torch's)."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.check_call(["make", "-s", "-j4", "-C", os.path.join(root, "tests", "emu")])
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "emu", "run_sharded_threads.py"), str(world)], cwd=root,
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and f"sharded x{world} OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+def _shards(ctx, cfg, R):
+    corpus = synth.Corpus.for_config(cfg)
+    whole = nat.HostIndexDesc(cfg.n_docs, synth.build_fields(corpus, 0, cfg.n_docs))
+    bounds = [cfg.n_docs * r // R for r in range(R + 1)]
+    shard_fields = [synth.build_fields(corpus, bounds[r], bounds[r + 1]) for r in range(R)]
+    for f in range(2):
+        gdf = sum(np.diff(sf[f]["term_offsets"]).astype(np.int64) for sf in shard_fields).astype(np.uint32)
+        tot = sum(sf[f]["total_num_tokens"] for sf in shard_fields)
+        for sf in shard_fields:
+            sf[f]["global_doc_freq"] = gdf
+            sf[f]["total_num_tokens"] = tot
+    words = [f"w{i + 1}" for i in range(cfg.vocab)]
+    one = Dataset(ctx)
+    one.adopt(whole, [words, words])
+    parts = []
+    for r in range(R):
+        d = Dataset(ctx)
+        d.adopt(nat.HostIndexDesc(bounds[r + 1] - bounds[r], shard_fields[r], doc_id_base=bounds[r], global_n_docs=cfg.n_docs), [words, words])
+        parts.append(d)
+    return one, parts
+
+
+STRINGS = ["w1 w2", "w3 AND w9", "w40", "w5 w17 w300", "(w1 AND w2) OR (w3 AND w4)", "w7 OR (w2 AND w11)",
+           "(w30 w45) OR (w10 AND w6)", "w900 w2", "(w2 AND w5) OR w999"]
+
+
+@pytest.mark.gpu
+def test_shards_merged_on_the_host_equal_the_single_index(ctx):
+    """Three shard snapshots with global statistics on one device: per-shard lists of the first `limit` hits, merged
+    by fgh_merge_shard_pages == the page of the unsharded dataset, for first pages, deep pages and nested queries."""
+    from tests import util
+
+    small = util.EMULATED
+    cfg = synth.Config(cfg=2, n_docs=6_000 if small else 40_000, vocab=1_000, n_queries=8, k=10, name_pct=10)
+    one, parts = _shards(ctx, cfg, 3)
+    for page, pp in ((0, 10), (30, 100), (2, 700)):
+        limit = page * pp + pp
+        want_h, want_n, _, st = one.search_batch(QuerySet(STRINGS, None, page, pp), want_counts=False)
+        assert (st == 0).all()
+        local = [d.search_batch(QuerySet(STRINGS, None, 0, limit), want_counts=False) for d in parts]
+        for qi, s_ in enumerate(STRINGS):
+            got = merge_shard_pages([h[qi, :n[qi]] for h, n, _, _ in local], page, pp)
+            w = want_h[qi, :want_n[qi]]
+            assert len(got) == len(w) and np.array_equal(got["doc"], w["doc"]), (s_, page, pp)
+            np.testing.assert_allclose(got["score"], w["score"], rtol=1e-6)
+    for d in parts + [one]:
+        d.close()
+
+
+@pytest.mark.gpu
+def test_collective_call_takes_deep_pages_and_nested_queries(ctx):
+    """fgh_search_batch_sharded on a one-rank communicator (the collectives run, over one rank): ordinary pages, deep
+    pages and nested queries in one request == fgh_search_batch. (The multi-rank case is checked by bench.py at
+    N > 1 against the oracle: `parity_deep_and_nested_sharded` in the bench line.)"""
+    import torch  # noqa: F401  (maps torch's libnccl.so.2, which the library then finds by name)
+
+    try:
+        comm = nat.Comm(ctx, 0, 1, nat.comm_unique_id())
+    except nat.FgError as e:
+        pytest.skip(f"no NCCL in this process: {e}")
+    cfg = synth.Config(cfg=2, n_docs=40_000, vocab=1_000, n_queries=8, k=10, name_pct=10)
+    one, parts = _shards(ctx, cfg, 1)
+    strings = STRINGS * 5
+    qs = QuerySet(strings, None, 0, 100)
+    qs.pages[::4] = 30  # limit 3100 for every fourth request
+    want_h, want_n, _, want_st = one.search_batch(qs, want_counts=False)
+    got_h, got_n, got_st = one.search_batch_sharded(comm, qs)
+    assert (want_st == 0).all() and (got_st == 0).all()
+    assert np.array_equal(got_n, want_n)
+    for qi in range(len(strings)):
+        assert np.array_equal(got_h[qi, :got_n[qi]], want_h[qi, :want_n[qi]]), (qi, strings[qi])
+    assert want_n[4] > 0 and want_n[0] > 0  # a nested query and a deep page really returned rows
+    comm.close()
+    for d in parts + [one]:
+        d.close()
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = nat.Context(0)
+    yield c
+    c.close()
