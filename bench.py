@@ -610,8 +610,9 @@ def main():
         for qi in range(nq):
             assert np.array_equal(e_hits[qi, :e_n[qi]]["doc"], ref_h[qi, :ref_n[qi], 1]), f"fgh_search_batch_sharded: query {qi} differs"
     apart_check = None
-    if comm and not args.no_cpu_baseline and len(queries) >= 80 and not any(q.get("filters") for q in queries[:80]) \
-            and not os.environ.get("FG_BENCH_NO_APART"):
+    if comm and len(queries) >= 80 and not any(q.get("filters") for q in queries[:80]) and not os.environ.get("FG_BENCH_NO_APART"):
+        if rank == 0 and args.no_cpu_baseline:  # (otherwise the parity check above has built the unsharded corpus)
+            pdesc = nat.HostIndexDesc(cfg.n_docs, synth.build_fields(corpus, 0, cfg.n_docs))
         apart_check = check_apart_sharded(ds, comm, queries, batch, pdesc if rank == 0 else None, rank)
     if os.environ.get("FG_TIMING"):
         print("e2e_times ms", [round(x * 1e3, 2) for x in e2e_times], file=sys.stderr)
