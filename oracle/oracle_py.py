@@ -10,7 +10,9 @@ from __future__ import annotations
 
 import math
 import re
-import unicodedata
+
+
+import regex
 
 import numpy as np
 
@@ -36,10 +38,13 @@ def fieldnorm_to_id(n: int) -> int:
 
 
 # ---- A.1 analyzer ----------------------------------------------------------------------------
+_ALNUM = regex.compile(r"[\p{Alphabetic}\p{N}]")
+
+
 def tokenize(text: str) -> list[str]:
     out, cur = [], []
     for ch in text + " ":
-        if unicodedata.category(ch)[0] in "LN":  # char::is_alphanumeric (minus Other_Alphabetic marks)
+        if ch.isascii() and ch.isalnum() or not ch.isascii() and _ALNUM.match(ch):  # char::is_alphanumeric = Alphabetic (incl. Other_Alphabetic marks) or N*
             cur.append(ch)
         else:
             if cur:

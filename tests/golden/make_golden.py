@@ -87,7 +87,10 @@ def main():
         bm.append({"df": df, "n_docs": n, "total_tokens": tot, "fieldnorm_id": fnid, "tf": tf, "boost": boost,
                    "idf": float(op.idf(df, n)), "score": float(w * (f32(tf) / (f32(tf) + norm)))})
     tok = [[s, op.tokenize(s)] for s in ["Hello, World!", "foo-bar_baz", "x" * 39 + " " + "y" * 40, "ÀÉÎõü straße İstanbul",
-                                         "d000000042 w17", "tab\tnew\nline", "日本語 テキスト 123", "a.b.c@d.com", "", "   "]]
+                                         "d000000042 w17", "tab\tnew\nline", "日本語 テキスト 123", "a.b.c@d.com", "", "   ",
+                                         # Other_Alphabetic marks (Rust's char::is_alphabetic counts them): Devanagari vowel signs stay, the
+                                         # virama splits; a combining acute splits; Arabic harakat stay; a Thai tone mark splits; Nl / No digits
+                                         "हिन्दी भाषा", "cafe\u0301 naïve", "كِتَاب جديد", "น้ำ ภาษาไทย", "Ⅻ ½ x²"]]
     json.dump({"fieldnorm": fn, "bm25": bm, "tokenizer": tok}, open(os.path.join(HERE, "formulas.json"), "w"), indent=1, ensure_ascii=False)
     # replay kit for a real fugu (POST /ingest body + POST /search bodies)
     with open(os.path.join(HERE, "replay_ingest.json"), "w") as f:
