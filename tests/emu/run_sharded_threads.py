@@ -74,6 +74,14 @@ def main(R: int) -> None:
                     if n[qi] != want_n[qi] or not np.array_equal(h[qi, :n[qi]]["doc"], want_h[qi, :want_n[qi]]["doc"]) \
                             or not np.allclose(h[qi, :n[qi]]["score"], want_h[qi, :want_n[qi]]["score"], rtol=1e-6):
                         errors.append(f"rank {r}: query {qi} {s_!r} page {pages[qi]}: {n[qi]} hits vs {want_n[qi]}")
+            # a small request (fewer than 32 queries per rank: every rank plans all of it, no plan exchange)
+            few = [0, 7, len(base), len(base) + 6, len(strings) - 2, len(strings) - 1]
+            q2 = QuerySet([strings[i] for i in few], None, 0, 100)
+            q2.pages[:] = pages[few]
+            h, n, st = ds.search_batch_sharded(comm, q2)
+            for j, qi in enumerate(few):
+                if st[j] != want_st[qi] or n[j] != want_n[qi] or not np.array_equal(h[j, :n[j]]["doc"], want_h[qi, :want_n[qi]]["doc"]):
+                    errors.append(f"rank {r}: small request, query {strings[qi]!r}: status {st[j]}, {n[j]} hits vs {want_n[qi]}")
             comm.close()
             ds.close()
             ctx.close()
