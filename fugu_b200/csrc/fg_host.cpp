@@ -883,6 +883,30 @@ void flatten(const LNode& n, int occ, std::vector<FlatClause>& out, int depth) {
         return;
     }
     if (occ == O_MUST || depth == 0) {
+        bool has_must = false;
+        for (auto& k : n.kids) has_must = has_must || k.first == O_MUST;
+        if (depth > 0 && !has_must) {
+            // Must(Bool[Should b.., MustNot c..]): without a Must child at least one Should child has to match, so lifted
+            // to this level the Should children are ONE Must group (a union whose scores add), not optional clauses
+            FlatClause m{O_MUST, {}};
+            bool any = false;
+            for (auto& k : n.kids) {
+                if (k.first != O_SHOULD) continue;
+                if (!(k.second.is_group || all_should_groups(k.second)))
+                    throw ParseError{"nested boolean (OR of AND groups / negated groups) is not evaluated on the device", true};
+                collect_groups(k.second, m.g);
+                any = true;
+            }
+            if (!any) throw ParseError{"a required group of only negated terms (matches nothing) is not evaluated on the device", true};
+            out.push_back(std::move(m));
+            for (auto& k : n.kids) {
+                if (k.first != O_NOT) continue;
+                if (!(k.second.is_group || all_should_groups(k.second)))
+                    throw ParseError{"nested boolean (OR of AND groups / negated groups) is not evaluated on the device", true};
+                flatten(k.second, O_NOT, out, depth + 1);
+            }
+            return;
+        }
         // Must(Bool[Must a, Should b, MustNot c]) == Must a, Should b, MustNot c at this level
         for (auto& k : n.kids) {
             if (k.second.is_group || all_should_groups(k.second)) flatten(k.second, k.first, out, depth + 1);

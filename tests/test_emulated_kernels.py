@@ -95,3 +95,16 @@ def test_shuffled_thread_schedule():
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-p", "no:cacheprovider", "-k", pick],
                        env=dict(os.environ, FGEMU_SEED="7"), cwd=ROOT, capture_output=True, text=True, timeout=1500)
     assert r.returncode == 0 and " passed" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("seed,n_queries,n_docs", [(1, 300, 400), (2, 300, 400), (3, 60, 6000)])
+def test_differential_fuzz_of_dataset_search(seed, n_queries, n_docs):
+    """Random query strings, filters and pages through Dataset.search on the emulated library vs the Python twin's tree
+    evaluation (tests/emu/run_fuzz_search.py): every answered request gives the twin's page; only FG_ERR_UNSUPPORTED
+    may be refused. 400 documents: tf columns and block lookups; 6000: membership bitmaps too."""
+    import sys
+
+    subprocess.check_call(["make", "-s", "-j4", "-C", EMU_DIR])
+    r = subprocess.run([sys.executable, os.path.join(EMU_DIR, "run_fuzz_search.py"), str(seed), str(n_queries), str(n_docs)], cwd=ROOT,
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]

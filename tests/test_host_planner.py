@@ -101,7 +101,10 @@ def test_plan_errors_and_fallback(small):
 
 QUERIES = ["red", "red apple", "red AND pie", "red AND pie AND cherry", "+red pie", "red -pie", "red pie -cherry -apple",
            "(red apple) AND pie", "red AND (apple OR cherry)", "NOT red", "-red", "red^3 pie", "text:pie name:pie",
-           "pie pie", "apple AND apple", "name:red AND text:red", "blue OR green OR cherry", "(red", "red:", "zzz", "zzz AND red"]
+           "pie pie", "apple AND apple", "name:red AND text:red", "blue OR green OR cherry", "(red", "red:", "zzz", "zzz AND red",
+           # a required group without a Must child: one of its Should children has to match (found by the differential fuzz:
+           # lifted as optional clauses, `red AND (-pie pie)` matched documents although the group matches nothing)
+           "red AND (-pie pie)", "red AND (-pie apple)", "+(apple cherry -green) red", "pie AND (apple cherry) AND (-blue red)"]
 FILTERS = [[], ["/namespace/x"], ["/namespace/y", "/namespace/x/organization/o1"], ["/nope"], ["*x*"], ["/namespace/y/*"]]
 
 
