@@ -297,9 +297,10 @@ struct Parser {
         }
         if (c == '[' || c == '{') throw ParseError{"range queries are not evaluated on the device", true};
         if (c == ')' || c == ']' || c == '}' || c == '^' || c == '~' || c == ':') throw ParseError{std::string("unexpected '") + c + "'"};
-        if (c == '*' && (i + 1 == s.size() || isspace((unsigned char)s[i + 1]) || s[i + 1] == ')')) {
+        if (c == '*' && (i + 1 == s.size() || isspace((unsigned char)s[i + 1]) || s[i + 1] == ')' || s[i + 1] == '^')) {
             i++;
             a.kind = Ast::ALL;
+            boost(a);  // `*^2`: a boosted AllQuery (every document scores the boost)
             return a;
         }
         if (c == '"') {
@@ -1033,7 +1034,16 @@ int32_t plan_impl(const fgh_dataset* ds, const char* query, const char* const* f
         Group fg_;
         bool any = false;
         facet_group(ds, filters, n_filters, fg_, any);
-        if (text_all) {
+        if (text_all && !blank) {
+            // `*` is a query string like any other (only query.trim().is_empty() drops the text query, :136): it parses to
+            // AllQuery and is Must-joined with the facet query, so every hit scores 1.0 (times its boost) + the facet score
+            flat.clear();
+            FlatClause ac{O_MUST, {}};
+            ac.g.all = true;
+            ac.g.all_boost = text_all_boost;
+            flat.push_back(std::move(ac));
+        }
+        if (text_all && blank) {
             // empty text query: the facet query alone (:136-138); no valid term -> AllQuery (:258-261)
             flat.clear();
             if (any) flat.push_back({O_SHOULD, fg_});

@@ -183,6 +183,10 @@ class Unsupported(Exception):
 _TOKEN = re.compile(r'\s*(\(|\)|"[^"]*"|[^\s()":^]+|\^[0-9.]+|:|")')
 
 
+class _Tok(str):
+    adj = False  # no blank space between the previous token and this one
+
+
 def _lex(q: str) -> list[str]:
     toks, pos = [], 0
     q = q.strip()
@@ -190,8 +194,16 @@ def _lex(q: str) -> list[str]:
         m = _TOKEN.match(q, pos)
         if not m:
             raise ParseError(f"cannot lex at {pos}")
-        toks.append(m.group(1))
+        tok = _Tok(m.group(1))
+        tok.adj = pos > 0 and m.start(1) == pos
         pos = m.end()
+        # AND / OR / NOT are operators only when blank space, '(' or the end of the string follows (tantivy's grammar
+        # matches "AND " / "OR "); `(w1 OR)` holds the word "or" (the analyzer lowercases it anyway)
+        if tok in ("AND", "OR", "NOT") and pos < len(q) and not q[pos].isspace() and q[pos] != "(":
+            adj = tok.adj
+            tok = _Tok(tok.lower())
+            tok.adj = adj
+        toks.append(tok)
     return toks
 
 
@@ -237,9 +249,11 @@ def parse_query(q: str):
         if any(c in t for c in "[]{}~"):
             raise Unsupported("range / fuzzy")
         if t == "*":
-            return ("all", 1.0)
+            return boost_of(("all", 1.0))
         if peek() == ":":
             take()
+            if peek() is None or not getattr(peek(), "adj", True):
+                raise ParseError("missing value after ':'")  # `field: value` is not field:value
             v = leaf()
             if v[0] != "lit":
                 raise Unsupported("field group")

@@ -1,5 +1,6 @@
 """TEST INFRASTRUCTURE ONLY: differential fuzz of the reference-facing call on a box without a GPU. Random query strings
-(bare words, field prefixes, boosts, + / -, AND / OR / AND NOT, one level of parenthesised groups), random facet filters
+(bare words, field prefixes, boosts, + / -, AND / OR / AND NOT, parenthesised groups two levels deep with boosts, `*`,
+stray punctuation and operator words that send the parser into the reference's escape-and-retry fallback), random facet filters
 and pages go through Dataset.search on tests/emu/libfugu_emu.so (C++ parser -> planner -> lowering -> the CUDA kernels
 under SIMT emulation) and through the independent Python twin (oracle/oracle_py.py: the same parse evaluated as a tree,
 no flattening). Every request the device path answers must give the twin's page (scores within 1e-5, same documents
@@ -40,6 +41,7 @@ ds.commit()
 
 def term():
     t = word()
+    if rng.random() < 0.05: t = rng.choice(["*", "W3", "w2.", "zzz", "w1,", "(w2", "w3)", "w4:", "w1-w2", '"w3"', "w5^", "AND", "OR", "NOT"])
     r = rng.random()
     if r < 0.1: t = "text:" + t
     elif r < 0.2: t = "name:" + t
@@ -49,8 +51,8 @@ def group(depth):
     n = rng.randint(1, 4)
     parts = []
     for _ in range(n):
-        if depth < 1 and rng.random() < 0.25:
-            p = "(" + group(depth + 1) + ")"
+        if depth < 2 and rng.random() < 0.3:
+            p = "(" + group(depth + 1) + ")" + (rng.choice(["", "", "^2", "^0.5"]))
         else:
             p = term()
         r = rng.random()
@@ -66,8 +68,9 @@ stats = {"ok": 0, "unsupported": 0, "invalid": 0, "both_err": 0}
 bad = 0
 for it in range(nq):
     q = group(0)
+    if rng.random() < 0.03: q = rng.choice(["", "  ", "*", "* w1", "w1 AND *"])
     fl = rng.choice([[], [], [], ["/ns/n1"], ["/ns/n2", "/kind/k0/*"], ["*x*"], ["/nope"]])
-    page, pp = rng.choice([(0, 10), (0, 20), (1, 5), (0, 100), (3, 7)])
+    page, pp = rng.choice([(0, 10), (0, 20), (1, 5), (0, 100), (3, 7), (11, 100), (0, 1)])
     try:
         want, _ = op.search(ix, q, fl, page, pp)
         werr = None

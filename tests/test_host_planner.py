@@ -104,7 +104,10 @@ QUERIES = ["red", "red apple", "red AND pie", "red AND pie AND cherry", "+red pi
            "pie pie", "apple AND apple", "name:red AND text:red", "blue OR green OR cherry", "(red", "red:", "zzz", "zzz AND red",
            # a required group without a Must child: one of its Should children has to match (found by the differential fuzz:
            # lifted as optional clauses, `red AND (-pie pie)` matched documents although the group matches nothing)
-           "red AND (-pie pie)", "red AND (-pie apple)", "+(apple cherry -green) red", "pie AND (apple cherry) AND (-blue red)"]
+           "red AND (-pie pie)", "red AND (-pie apple)", "+(apple cherry -green) red", "pie AND (apple cherry) AND (-blue red)",
+           # `*` is a query string like any other: with filters it is Must(AllQuery) AND Must(facet query), +1.0 (times its boost) on
+           # every hit (only a blank string drops the text query, search.rs:136); an operator word glued to ')' is a word
+           "*", "*^2", "red AND *^3", "(red OR) AND pie", "pie: red"]
 FILTERS = [[], ["/namespace/x"], ["/namespace/y", "/namespace/x/organization/o1"], ["/nope"], ["*x*"], ["/namespace/y/*"]]
 
 
