@@ -130,7 +130,7 @@ HIT_DT = np.dtype([("score", "<f4"), ("doc", "<u4")])
 ABI_SYMBOLS = [
     "fg_last_error", "fg_version", "fg_ctx_create", "fg_ctx_destroy", "fg_ctx_set_stream",
     "fg_ctx_synchronize", "fg_index_upload", "fg_index_release", "fg_index_with_alive", "fg_index_append", "fg_index_get_info",
-    "fg_index_term_info", "fg_search_batch", "fg_search_union_of", "fg_batch_prepare", "fg_batch_prepare_ex", "fg_batch_release",
+    "fg_index_term_info", "fg_search_batch", "fg_search_union_of", "fg_search_union_of_filtered", "fg_batch_prepare", "fg_batch_prepare_ex", "fg_batch_release",
     "fg_batch_execute", "fg_batch_submit", "fg_batch_collect", "fg_batch_get_stats", "fg_merge_topk_device", "fg_fieldnorm_to_id",
     "fg_comm_unique_id", "fg_comm_create", "fg_comm_destroy", "fg_comm_allreduce_sum_u64", "fg_comm_allreduce_sum_u32",
     "fg_batch_execute_sharded", "fg_batch_query_status", "fg_batch_submit_sharded", "fg_comm_info", "fg_comm_allgather_bytes",
@@ -167,6 +167,7 @@ def lib() -> C.CDLL:
     L.fg_index_term_info.argtypes = [vp, u32, u32, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32), C.POINTER(u64)]
     L.fg_search_batch.argtypes = [vp, C.POINTER(QueryBatch), u32, vp, vp, vp]
     L.fg_search_union_of.argtypes = [vp, C.POINTER(QueryBatch), u32, vp, C.POINTER(u32), C.POINTER(u32)]
+    L.fg_search_union_of_filtered.argtypes = [vp, C.POINTER(QueryBatch), u32, u32, vp, C.POINTER(u32), C.POINTER(u32)]
     L.fg_batch_prepare.argtypes = [vp, C.POINTER(QueryBatch), C.POINTER(vp)]
     L.fg_batch_prepare_ex.argtypes = [vp, C.POINTER(QueryBatch), u32, C.POINTER(vp)]
     L.fg_batch_release.argtypes = [vp]

@@ -1212,6 +1212,7 @@ struct fg_batch {
     uint64_t* d_sel = nullptr;     // deep-page batches (ks == 0): scratch of lead_select_kernel
     cudaStream_t exec_stream = nullptr;  // fg_batch_submit: the stream this batch runs on (null = the context's stream)
     uint32_t combine_k = 0;        // fg_search_union_of: the queries are the disjuncts of ONE query with this page limit
+    uint32_t combine_filters = 0;  // ... the last combine_filters of them are filter children (fg_search_union_of_filtered)
     uint64_t* d_comb = nullptr;    // ... and its two scratch arrays of comb_cap2 keys
     uint32_t comb_cap2 = 0;
     size_t comb_sz = 0;
@@ -2152,7 +2153,7 @@ extern "C" int32_t fg_batch_execute(fg_batch* b, uint32_t flags, uint32_t k_stri
         m.out_n = (uint32_t*)d_n_hits;
         m.out_count = (uint32_t*)d_match_count;
         m.sel = b->d_sel;
-        if (b->combine_k) launch_lead_combine(m, b->combine_k, b->d_comb, b->d_comb + b->comb_cap2, b->comb_cap2, st);
+        if (b->combine_k) launch_lead_combine(m, b->combine_k, b->d_comb, b->d_comb + b->comb_cap2, b->comb_cap2, b->combine_filters, st);
         else launch_lead_merge(m, b->ks, st);
         CU(cudaEventRecord(b->ev[2], st));
         b->n_launches = b->n_queries ? (b->n_items ? 3 : 2) : 0;
@@ -2328,9 +2329,22 @@ extern "C" int32_t fg_search_batch(fg_index* ix, const fg_query_batch* qb, uint3
 // selects the page. The disjuncts' own k is ignored.
 extern "C" int32_t fg_search_union_of(fg_index* ix, const fg_query_batch* disjuncts, uint32_t k, fg_hit* out_hits, uint32_t* out_n_hits,
                                       uint32_t* out_match_count) {
+    return fg_search_union_of_filtered(ix, disjuncts, 0, k, out_hits, out_n_hits, out_match_count);
+}
+
+// The same with FILTER children: the last n_filters queries of the batch. A document matches when at least one ordinary
+// child and every filter child match it; its score is the sum over the ordinary children plus the filter scores (tantivy:
+// Bool[Must(union of the children), Must(filter)..], src/db/search.rs:140-144 with a nested text query). Scores must not
+// be negative (the combine step tags filter entries in the sign position of the sortable score).
+extern "C" int32_t fg_search_union_of_filtered(fg_index* ix, const fg_query_batch* disjuncts, uint32_t n_filters, uint32_t k, fg_hit* out_hits,
+                                               uint32_t* out_n_hits, uint32_t* out_match_count) {
     if (!ix || !disjuncts || !out_hits || !out_n_hits) return fail(FG_ERR_INVALID, "fg_search_union_of: NULL argument");
     if (k == 0) return fail(FG_ERR_INVALID, "k == 0 (TopDocs::with_limit requires limit >= 1)");
     if (disjuncts->n_queries == 0 || disjuncts->n_queries > 64) return fail(FG_ERR_INVALID, "fg_search_union_of: 1 to 64 disjuncts");
+    if (n_filters >= disjuncts->n_queries) return fail(FG_ERR_INVALID, "fg_search_union_of_filtered: at least one child must not be a filter");
+    if (n_filters)
+        for (uint32_t i = 0; i < disjuncts->n_leaves; i++)
+            if (disjuncts->leaves[i].boost < 0.f) return fail(FG_ERR_UNSUPPORTED, "fg_search_union_of_filtered: negative boosts");
     std::vector<fg_query> qs(disjuncts->queries, disjuncts->queries + disjuncts->n_queries);
     for (fg_query& q : qs) q.k = 0x7FFFFFFFu;  // every match of every disjunct: no per-warp queue, no threshold
     fg_query_batch qb = *disjuncts;
@@ -2345,6 +2359,7 @@ extern "C" int32_t fg_search_union_of(fg_index* ix, const fg_query_batch* disjun
     while (cap2 < std::max<uint64_t>(b->partial_entries, 1)) cap2 <<= 1;
     if (cap2 > 0x40000000ull) return fail(FG_ERR_UNSUPPORTED, "fg_search_union_of: the disjuncts match too many documents");
     b->combine_k = k;
+    b->combine_filters = n_filters;
     b->comb_cap2 = (uint32_t)cap2;
     b->comb_sz = (size_t)cap2 * 16;
     CU(pool_alloc(ctx, (void**)&b->d_comb, b->comb_sz));

@@ -55,6 +55,7 @@ struct DevApi {
     FGH_DEV_FN(fg_index_term_info);
     FGH_DEV_FN(fg_search_batch);
     FGH_DEV_FN(fg_search_union_of);
+    FGH_DEV_FN(fg_search_union_of_filtered);
     FGH_DEV_FN(fg_batch_prepare_ex);
     FGH_DEV_FN(fg_batch_query_status);
     FGH_DEV_FN(fg_batch_submit);
@@ -95,6 +96,7 @@ const DevApi& dev_api() {
         FGH_DEV_BIND(fg_index_term_info);
         FGH_DEV_BIND(fg_search_batch);
         FGH_DEV_BIND(fg_search_union_of);
+        FGH_DEV_BIND(fg_search_union_of_filtered);
         FGH_DEV_BIND(fg_batch_prepare_ex);
         FGH_DEV_BIND(fg_batch_query_status);
         FGH_DEV_BIND(fg_batch_submit);
@@ -1028,9 +1030,38 @@ int32_t plan_impl(const fgh_dataset* ds, const char* query, const char* const* f
         std::string f = filters[i] ? filters[i] : "";
         if (!(!f.empty() && f.front() == '*' && f.back() == '*')) n_nonwild++;
     }
-    if (n_nonwild && !disjuncts.empty())  // Must(text_query) AND Must(facet_query): the facet group would have to score once, not once per child
-        return host_fail(FG_ERR_UNSUPPORTED, "query '%s': a nested boolean query combined with facet filters is not evaluated on the device", q.c_str());
-    if (n_nonwild) {
+    bool filter_child = false;
+    if (n_nonwild && !disjuncts.empty()) {
+        // Bool[Must(text_query = the union of the children), Must(facet_query)] (:140-144): the facet group has to hold for
+        // every hit and to score ONCE, not once per child. It becomes a FILTER child of the union (fg_search_union_of_filtered):
+        // Must(facet group) AND Must(any positive leaf of any child, boost 0) -- the second clause only bounds the child's
+        // matches by the text query's (a superset of them) instead of by the size of the namespace.
+        Group fg_;
+        bool any = false;
+        facet_group(ds, filters, n_filters, fg_, any);
+        if (!any)
+            return host_fail(FG_ERR_UNSUPPORTED, "query '%s': a nested boolean query combined with filters that hold no facet term (AllQuery) is not evaluated on the device", q.c_str());
+        FlatClause any_text{O_MUST, {}};
+        for (auto& d : disjuncts)
+            for (auto& c : d) {
+                if (c.g.all) return host_fail(FG_ERR_UNSUPPORTED, "query '%s': '*' inside a nested boolean query", q.c_str());
+                for (fg_leaf l : c.g.leaves) {
+                    if (l.boost < 0.f) return host_fail(FG_ERR_UNSUPPORTED, "query '%s': negative boosts in a nested boolean query combined with facet filters", q.c_str());
+                    if (c.occ == O_NOT || l.term_ord == FG_TERM_MISSING) continue;
+                    bool seen = false;
+                    for (const fg_leaf& x : any_text.g.leaves) seen = seen || (x.field == l.field && x.term_ord == l.term_ord);
+                    l.boost = 0.f;
+                    if (!seen) any_text.g.leaves.push_back(l);
+                }
+            }
+        for (const fg_leaf& l : fg_.leaves)
+            if (l.boost < 0.f) return host_fail(FG_ERR_UNSUPPORTED, "query '%s': negative boost", q.c_str());
+        std::vector<FlatClause> fchild;
+        fchild.push_back({O_MUST, fg_});
+        fchild.push_back(std::move(any_text));
+        disjuncts.push_back(std::move(fchild));
+        filter_child = true;
+    } else if (n_nonwild) {
         Group fg_;
         bool any = false;
         facet_group(ds, filters, n_filters, fg_, any);
@@ -1093,6 +1124,7 @@ int32_t plan_impl(const fgh_dataset* ds, const char* query, const char* const* f
                 if (c.g.all) return host_fail(FG_ERR_UNSUPPORTED, "'*' inside a nested boolean query");
                 fg_clause& oc = out->clauses[out->n_clauses++];
                 oc.occur = (c.occ == O_MUST ? FG_OCCUR_MUST : c.occ == O_NOT ? FG_OCCUR_MUST_NOT : FG_OCCUR_SHOULD) | ((uint32_t)(d + 1) << FGH_DISJUNCT_SHIFT);
+                if (filter_child && d + 1 == disjuncts.size()) oc.occur |= FGH_FILTER_CHILD;
                 oc.leaf_begin = out->n_leaves;
                 for (auto& l : c.g.leaves) {
                     if (out->n_leaves >= FGH_MAX_PLAN_LEAVES) return host_fail(FG_ERR_UNSUPPORTED, "too many leaves");
@@ -1738,9 +1770,11 @@ int32_t search_batch_impl(fgh_dataset* ds, fg_comm* comm, uint32_t n, const char
             const fgh_plan_t& P = cp.second;
             std::vector<fg_query> dq;
             std::vector<fg_clause> dc(P.clauses, P.clauses + P.n_clauses);
+            uint32_t n_filter_children = 0;
             for (uint32_t ci = 0; ci < P.n_clauses; ci++) {
                 const uint32_t d = dc[ci].occur >> FGH_DISJUNCT_SHIFT;
-                dc[ci].occur &= (1u << FGH_DISJUNCT_SHIFT) - 1u;
+                if (dc[ci].occur & FGH_FILTER_CHILD) n_filter_children = 1;  // (the last child)
+                dc[ci].occur &= FGH_FILTER_CHILD - 1u;
                 if (dq.size() < d) dq.push_back(fg_query{1u, ci, 0u});
                 dq.back().n_clauses++;
             }
@@ -1754,7 +1788,7 @@ int32_t search_batch_impl(fgh_dataset* ds, fg_comm* comm, uint32_t n, const char
             qb.leaves = P.leaves;
             std::vector<fg_hit> page(P.k);
             uint32_t n_page = 0, n_match = 0;
-            const int32_t rc = D(dev_api().fg_search_union_of(snap.get(), &qb, P.k, page.data(), &n_page, out_match_count ? &n_match : nullptr));
+            const int32_t rc = D(dev_api().fg_search_union_of_filtered(snap.get(), &qb, n_filter_children, P.k, page.data(), &n_page, out_match_count ? &n_match : nullptr));
             if (rc) {
                 if (!status) return rc;
                 status[qi] = rc;

@@ -277,7 +277,7 @@ struct LeadMergeParams {
 void launch_lead(const LeadParams& p, int ks, int n_sms, void* stream);
 void launch_lead_merge(const LeadMergeParams& p, int ks, void* stream);
 // union of the batch's queries as disjuncts of ONE query (fg_search_union_of): one output row; a, b = scratch of cap2 keys
-void launch_lead_combine(const LeadMergeParams& p, uint32_t k, uint64_t* a, uint64_t* b, uint32_t cap2, void* stream);
+void launch_lead_combine(const LeadMergeParams& p, uint32_t k, uint64_t* a, uint64_t* b, uint32_t cap2, uint32_t n_filter, void* stream);
 // merge of all-gathered per-rank lists with per-query k (word k_word of the q_words-word query records at qrec)
 void launch_merge_ranks(const void* hits, const uint32_t* n, uint32_t n_ranks, uint32_t n_queries, const void* qrec, uint32_t q_words,
                         uint32_t k_word, uint32_t k_stride, void* out_hits, uint32_t* out_n, int ks, void* stream);

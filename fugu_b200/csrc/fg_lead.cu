@@ -1017,7 +1017,13 @@ __global__ void __launch_bounds__(256) lead_select_kernel(const LeadMergeParams 
 // unbounded). One CTA: gather the m lists as (~doc, score) entries, bitonic sort (equal docs become neighbours, in a
 // value-determined order), one combined key per run of equal docs (scores summed in run order), then the ordinary
 // page selection over the combined keys. a, b: scratch of cap2 keys each (cap2 = power of two >= all matches).
-__global__ void __launch_bounds__(256) lead_combine_kernel(const LeadMergeParams p, uint32_t k, uint64_t* a, uint64_t* b, uint32_t cap2) {
+// n_filter: the LAST n_filter queries are FILTER children (tantivy: Bool[Must(the union of the other children), Must(f)..],
+// what Dataset::search builds from a nested text query and a facet query, src/db/search.rs:140-144): a document counts
+// only when an ordinary child AND every filter child hold it; the filter scores are added after the ordinary sum. Their
+// entries are tagged by clearing the top bit of sortable(score) (set for every score >= 0), which also sorts them to the
+// end of their document's run.
+__global__ void __launch_bounds__(256) lead_combine_kernel(const LeadMergeParams p, uint32_t k, uint64_t* a, uint64_t* b, uint32_t cap2,
+                                                           uint32_t n_filter) {
     __shared__ uint32_t hist[256];
     __shared__ uint64_t s_prefix;
     __shared__ uint32_t s_remaining, s_cnt, s_fill, s_runs;
@@ -1028,9 +1034,10 @@ __global__ void __launch_bounds__(256) lead_combine_kernel(const LeadMergeParams
         const LQuery q = p.queries[j];
         const uint64_t* src = p.partial + q.part_begin;
         const uint32_t cnt = min(p.qcount[j], q.part_cap), base = s_fill;
+        const uint64_t tag = j + n_filter >= p.n_queries ? ~0x80000000ull : ~0ull;
         for (uint32_t i = tid; i < cnt; i += 256u) {
             const uint64_t key = src[i];
-            if (base + i < cap2) a[base + i] = (key << 32) | (key >> 32);  // (~doc) above sortable(score)
+            if (base + i < cap2) a[base + i] = ((key << 32) | (key >> 32)) & tag;  // (~doc) above sortable(score)
         }
         __syncthreads();
         if (tid == 0) s_fill = min(base + cnt, cap2);
@@ -1058,10 +1065,17 @@ __global__ void __launch_bounds__(256) lead_combine_kernel(const LeadMergeParams
         uint64_t outk = 0;
         const uint64_t e = i < n ? a[i] : 0;
         if (e != 0 && (i == 0 || (a[i - 1] >> 32) != (e >> 32))) {
-            float sum = 0.f;
-            for (uint32_t t = i; t < n && (a[t] >> 32) == (e >> 32); t++) sum += unsortable((uint32_t)(a[t] & 0xFFFFFFFFu));
-            outk = ((uint64_t)sortable(sum) << 32) | (e >> 32);
-            atomicAdd(&s_runs, 1u);
+            float sum = 0.f, fsum = 0.f;
+            uint32_t nt = 0, nf = 0;
+            for (uint32_t t = i; t < n && (a[t] >> 32) == (e >> 32); t++) {
+                const uint32_t bits = (uint32_t)(a[t] & 0xFFFFFFFFu);
+                if (n_filter && !(bits & 0x80000000u)) fsum += unsortable(bits | 0x80000000u), nf++;
+                else sum += unsortable(bits), nt++;
+            }
+            if (n_filter == 0u || (nt && nf == n_filter)) {
+                outk = ((uint64_t)sortable(sum + fsum) << 32) | (e >> 32);
+                atomicAdd(&s_runs, 1u);
+            }
         }
         b[i] = outk;
     }
@@ -1313,8 +1327,8 @@ void launch_lead_merge(const LeadMergeParams& p, int ks, void* stream) {
     else FG_LAUNCH(lead_merge_kernel<32>, grid, 128, 0, st, p);
 }
 
-void launch_lead_combine(const LeadMergeParams& p, uint32_t k, uint64_t* a, uint64_t* b, uint32_t cap2, void* stream) {
-    FG_LAUNCH(lead_combine_kernel, 1, 256, 0, (cudaStream_t)stream, p, k, a, b, cap2);
+void launch_lead_combine(const LeadMergeParams& p, uint32_t k, uint64_t* a, uint64_t* b, uint32_t cap2, uint32_t n_filter, void* stream) {
+    FG_LAUNCH(lead_combine_kernel, 1, 256, 0, (cudaStream_t)stream, p, k, a, b, cap2, n_filter);
 }
 
 void launch_merge_ranks(const void* hits, const uint32_t* n, uint32_t n_ranks, uint32_t n_queries, const void* qrec, uint32_t q_words,

@@ -42,12 +42,13 @@ class Plan(C.Structure):
         cl = []
         for i in range(self.n_clauses):
             c = self.clauses[i]
-            cl.append((int(c.occur) & 0xFF, [(int(self.leaves[j].field), int(self.leaves[j].term_ord), float(self.leaves[j].boost))
+            cl.append((int(c.occur) & 0x7F, [(int(self.leaves[j].field), int(self.leaves[j].term_ord), float(self.leaves[j].boost))
                                              for j in range(c.leaf_begin, c.leaf_begin + c.n_leaves)]))
         d = {"k": int(self.k), "offset": int(self.offset), "is_all": bool(self.is_all),
              "used_fallback": bool(self.used_fallback), "clauses": cl}
         if self.n_disjuncts:  # nested query: which child of the top-level union each clause belongs to (1-based)
             d["disjunct_of_clause"] = [int(self.clauses[i].occur) >> 8 for i in range(self.n_clauses)]
+            d["filter_child"] = any(int(self.clauses[i].occur) & 0x80 for i in range(self.n_clauses))  # the last child (facet filters)
         return d
 
 

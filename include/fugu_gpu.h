@@ -191,6 +191,12 @@ int32_t fg_search_batch(fg_index* index, const fg_query_batch* batch, uint32_t k
  * out_match_count (may be NULL) = distinct matching documents. Blocking, host buffers. */
 int32_t fg_search_union_of(fg_index* index, const fg_query_batch* disjuncts, uint32_t k, fg_hit* out_hits,
                            uint32_t* out_n_hits, uint32_t* out_match_count);
+/* The same with FILTER children -- the last n_filters queries of `disjuncts`: a document matches when at least one
+ * ordinary child and every filter child match it, and scores the sum over the ordinary children plus the filters' scores.
+ * This is what Dataset::search builds from a nested text query and facet filters: Bool[Must(text_query), Must(facet_query)]
+ * (src/db/search.rs:140-144). Boosts must not be negative. */
+int32_t fg_search_union_of_filtered(fg_index* index, const fg_query_batch* disjuncts, uint32_t n_filters, uint32_t k,
+                                    fg_hit* out_hits, uint32_t* out_n_hits, uint32_t* out_match_count);
 
 /* ---- split-phase form (batches resident in HBM; CUDA-event timing; multi-GPU merge) --------- */
 typedef struct fg_batch fg_batch;

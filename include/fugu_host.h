@@ -113,9 +113,13 @@ typedef struct {
     uint32_t n_disjuncts;
 } fgh_plan_t;
 #define FGH_DISJUNCT_SHIFT 8
+/* A nested query combined with facet filters (Bool[Must(text_query), Must(facet_query)], src/db/search.rs:140-144): the
+ * plan's LAST child is a filter child, its clauses carry this bit in `occur` -- a document matches when an ordinary child
+ * and the filter child hold it, and scores the children's sum plus the filter's score (fg_search_union_of_filtered). */
+#define FGH_FILTER_CHILD 0x80u
 /* FG_ERR_INVALID = parse error even after the fallback (the reference returns Err -> HTTP 500);
  * FG_ERR_UNSUPPORTED = valid tantivy query the device path does not evaluate (phrase, range, fuzzy, boolean
- * trees nested deeper than a union of one-level boolean queries, nested queries combined with facet filters). */
+ * trees nested deeper than a union of one-level boolean queries). */
 int32_t fgh_plan(const fgh_dataset* ds, const char* query, const char* const* filters,
                  uint32_t n_filters, uint32_t page, uint32_t per_page, fgh_plan_t* out);
 

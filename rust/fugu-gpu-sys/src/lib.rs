@@ -106,6 +106,8 @@ extern "C" {
     // one query whose Should children are boolean queries themselves: `(a AND b) OR (c AND d)`
     pub fn fg_search_union_of(index: *mut fg_index, disjuncts: *const fg_query_batch, k: u32, out_hits: *mut fg_hit,
                               out_n_hits: *mut u32, out_match_count: *mut u32) -> i32;
+    pub fn fg_search_union_of_filtered(index: *mut fg_index, disjuncts: *const fg_query_batch, n_filters: u32, k: u32, out_hits: *mut fg_hit,
+                                       out_n_hits: *mut u32, out_match_count: *mut u32) -> i32;
     // snapshot refresh after a commit that added documents: only the new segment crosses PCIe
     pub fn fg_index_append(base: *mut fg_index, segment: *const fg_index_desc, alive_bitset: *const u32, out: *mut *mut fg_index) -> i32;
     // sharded submit (collective), communicator info, host-buffer all-gather (shared planning)

@@ -6,7 +6,7 @@ import pytest
 
 from fugu_b200 import _native as nat
 from fugu_b200 import handlers as H
-from fugu_b200.dataset import Dataset, ObjectRecord
+from fugu_b200.dataset import Dataset, ObjectRecord, all_facet_paths
 
 pytestmark = pytest.mark.gpu
 
@@ -188,6 +188,28 @@ def test_nested_boolean_queries_through_dataset_search(ctx):
             assert [g[0] for g in got] == [w[0] for w in want], (q, page, pp)
             for (_, gs), (_, ws) in zip(got, want):
                 assert abs(gs - ws) <= 1e-5 * max(abs(ws), 1e-30), (q, gs, ws)
+    # with facet filters: Bool[Must(nested text query), Must(facet query)] (src/db/search.rs:140-144) -- the facet group must
+    # hold for every hit and scores once (a filter child of the union). Expected from the Python twin's tree evaluation.
+    from oracle import oracle_py as op
+
+    ix = op.PyIndex()
+    for i in range(30):
+        r = ObjectRecord(id=f"doc{i}", text=f"alpha beta gamma{i % 3} filler{i}", metadata={"name": f"report {i}", "kind": "memo"},
+                         namespace="acme", organization=f"org{i % 2}", data_type="note")
+        ix.upsert(r.id, r.text, r.name(), all_facet_paths(r))
+    plain = ObjectRecord(id="plain", text="alpha only here", facets=["/custom/path", "nolead/slash"])
+    ix.upsert(plain.id, plain.text, plain.name(), all_facet_paths(plain))
+    for q, _ in cases:
+        for fl in (["/namespace/acme/organization/org1"], ["/namespace/acme/organization/org0", "/custom/path"], ["/nowhere"]):
+            assert main.plan(q, fl).as_dict().get("filter_child"), (q, fl)
+            for page, pp in ((0, 20), (1, 4)):
+                got = main.search(q, fl, page, pp)
+                want, n_match = op.search(ix, q, fl, page, pp)
+                assert [r.id for r in got] == [ix.ids[d] for d, _ in want], (q, fl, page, pp)
+                for r, (_, ws) in zip(got, want):
+                    assert abs(r.score - ws) <= 1e-5 * max(abs(ws), 1e-30), (q, fl, r.score, ws)
+            h, n, c, st = main.search_batch([q], [fl], 0, 20, want_counts=True)
+            assert st[0] == 0 and int(c[0]) == op.search(ix, q, fl, 0, 20)[1], (q, fl)
     # in a batch next to ordinary queries, and through the micro-batcher
     qs = ["alpha", cases[0][0], "beta AND gamma1", cases[1][0]]
     hits, nh, cnt, status = main.search_batch(QuerySet(qs, None, 0, 20), want_counts=False)

@@ -176,8 +176,9 @@ def test_fast_path_equals_general_parser(small):
 
 def test_nested_union_of_boolean_queries_plans_as_disjuncts():
     """`(a AND b) OR (c AND d)`, `a OR (b AND c)`: a union whose children are one-level boolean queries plans as
-    disjuncts (fgh_plan_t::n_disjuncts; answered by fg_search_union_of). Deeper nesting, a Must sibling of a nested
-    group, or facet filters next to it stay FG_ERR_UNSUPPORTED."""
+    disjuncts (fgh_plan_t::n_disjuncts; answered by fg_search_union_of). With facet filters the plan's last child is a
+    FILTER child: Must(facet group) AND Must(any positive leaf of the children at boost 0). Deeper nesting or a Must
+    sibling of a nested group stay FG_ERR_UNSUPPORTED."""
     from fugu_b200 import _native as nat
     from fugu_b200.dataset import Dataset, ObjectRecord
 
@@ -192,8 +193,16 @@ def test_nested_union_of_boolean_queries_plans_as_disjuncts():
     assert p["disjunct_of_clause"] == [1, 1, 2, 2] and [c[0] for c in p["clauses"]] == [S, S, M, N]
     assert "disjunct_of_clause" not in ds.plan("alpha AND beta").as_dict()
     assert "disjunct_of_clause" not in ds.plan("alpha (beta gamma)").as_dict()
+    ds.upsert([ObjectRecord(id="y", text="alpha", facets=["/namespace/x"])], commit=False)
+    p = ds.plan("(alpha AND beta) OR gamma", ["namespace/x"]).as_dict()
+    assert p["filter_child"] and p["disjunct_of_clause"] == [1, 2, 2, 3, 3]
+    assert [c[0] for c in p["clauses"]] == [S, M, M, M, M]           # gamma | alpha AND beta | facet AND any-text
+    assert [l[0] for l in p["clauses"][3][1]] == [2]                # the facet group (field 2), scored
+    # the children's positive leaves that exist in the dictionaries (gamma, alpha, beta in text; alpha in name), boost 0
+    assert len(p["clauses"][4][1]) == 4 and all(l[2] == 0.0 for l in p["clauses"][4][1])
+    assert not ds.plan("(alpha AND beta) OR gamma").as_dict()["filter_child"]
     for q, f in (("alpha OR (beta AND (gamma OR (delta AND omega)))", []), ("+alpha (beta AND gamma)", []),
-                 ("(alpha AND beta) OR gamma", ["namespace/x"])):
+                 ("(alpha^-1 AND beta) OR gamma", ["namespace/x"])):
         with pytest.raises(nat.FgError) as e:
             ds.plan(q, f)
         assert e.value.code == nat.FG_ERR_UNSUPPORTED, q
