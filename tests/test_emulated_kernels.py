@@ -108,3 +108,15 @@ def test_differential_fuzz_of_dataset_search(seed, n_queries, n_docs):
     r = subprocess.run([sys.executable, os.path.join(EMU_DIR, "run_fuzz_search.py"), str(seed), str(n_queries), str(n_docs)], cwd=ROOT,
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("seed,rounds,base_docs", [(1, 8, 400), (5, 12, 150)])
+def test_differential_fuzz_of_ingest_and_commits(seed, rounds, base_docs):
+    """Random upsert / delete / commit sequences (full upload, appended segments, delete-only refreshes, re-upload after
+    growth) on the emulated library vs the Python twin, queries checked after every commit (tests/emu/run_fuzz_ingest.py)."""
+    import sys
+
+    subprocess.check_call(["make", "-s", "-j4", "-C", EMU_DIR])
+    r = subprocess.run([sys.executable, os.path.join(EMU_DIR, "run_fuzz_ingest.py"), str(seed), str(rounds), str(base_docs)], cwd=ROOT,
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "bad 0" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
