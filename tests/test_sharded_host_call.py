@@ -36,9 +36,25 @@ def test_merge_shard_pages_equals_global_order():
     assert len(merge_shard_pages([], 0, 10)) == 0
 
 
-@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("seed,world,n_requests", [(1, 2, 120), (2, 3, 150)])
+def test_differential_fuzz_of_the_collective_call(seed, world, n_requests):
+    """CPU: random requests (words, AND / OR, boosts, nested groups, facet filters, first and deep pages) over a random
+    corpus with deleted documents cut into `world` shards -- ranks as threads, as below -- against the Python twin's
+    answer on the unsharded corpus (tests/emu/run_fuzz_sharded.py)."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.check_call(["make", "-s", "-j4", "-C", os.path.join(root, "tests", "emu")])
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "emu", "run_fuzz_sharded.py"), str(seed), str(world), str(n_requests)],
+                       cwd=root, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and " 0 bad" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+@pytest.mark.parametrize("world", [2])
 def test_collective_call_with_ranks_as_threads_emulated(world):
-    """CPU: fgh_search_batch_sharded with world_size 2 and 3 -- ranks are threads of one process over the emulated
+    """CPU: fgh_search_batch_sharded with world_size 2 -- ranks are threads of one process over the emulated
     library and an in-process NCCL stand-in (tests/emu/fake_nccl.cpp): shared planning, the fused exchange + merge,
     and the per-shard answers of deep pages and nested queries, against the unsharded dataset. In a subprocess: the
     stand-in must be mapped before any other libnccl.so.2 (torch's)."""
