@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 from fugu_b200 import _native as nat
 from tests import util
-nat.LIB_PATH = os.path.join(ROOT, "tests", "emu", "libfugu_emu.so"); util.EMULATED = True
+nat.LIB_PATH = os.environ.get("FG_EMU_LIB") or os.path.join(ROOT, "tests", "emu", "libfugu_emu.so")  # (FG_EMU_LIB: the `make asan` build); util.EMULATED = True
 from fugu_b200.dataset import Dataset, ObjectRecord
 from oracle import oracle_py as op
 seed = int(sys.argv[1]); rounds = int(sys.argv[2]); base_docs = int(sys.argv[3])

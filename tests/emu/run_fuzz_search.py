@@ -15,7 +15,7 @@ sys.path.insert(0, ROOT)
 import numpy as np
 from fugu_b200 import _native as nat
 from tests import util
-nat.LIB_PATH = os.path.join(ROOT, "tests", "emu", "libfugu_emu.so"); util.EMULATED = True
+nat.LIB_PATH = os.environ.get("FG_EMU_LIB") or os.path.join(ROOT, "tests", "emu", "libfugu_emu.so")  # (FG_EMU_LIB: the `make asan` build); util.EMULATED = True
 from fugu_b200.dataset import Dataset, ObjectRecord
 from oracle import oracle_py as op
 

@@ -20,7 +20,7 @@ from fugu_b200 import _native as nat  # noqa: E402
 from fugu_b200 import synth  # noqa: E402
 from tests import util  # noqa: E402
 
-nat.LIB_PATH = os.path.join(EMU, "libfugu_emu.so")
+nat.LIB_PATH = os.environ.get("FG_EMU_LIB") or os.path.join(EMU, "libfugu_emu.so")  # (FG_EMU_LIB: the `make asan` build)
 util.EMULATED = True
 assert "torch" not in sys.modules
 
