@@ -769,3 +769,45 @@ def test_union_of_boolean_queries(ctx):
         check_topk(g_hits, o_hits, 50, ctx=f"union-of with deletes, case {ci}")
     dead_ix.close()
     index.close()
+
+
+def test_grammar_replay_kit_through_dataset_search(ctx):
+    """The committed grammar replay kit (tests/golden/grammar_replay: what a box with `cargo` would POST to a real fugu)
+    through Dataset.upsert / delete / commit / search on the device (and, in the CPU suite, on the emulated library): every case the device path answers gives
+    the kit's page; a case the kit marks as an error (HTTP 500 in the reference) is FG_ERR_INVALID; the rest may only be
+    FG_ERR_UNSUPPORTED."""
+    import json
+    import os
+
+    from fugu_b200.dataset import Dataset, ObjectRecord
+
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "grammar_replay")
+    ds = Dataset(ctx)
+    ds.upsert([ObjectRecord(id=d["id"], text=d["text"], metadata=d["metadata"], facets=d["facets"])
+               for d in json.load(open(os.path.join(here, "ingest.json")))["data"]], commit=True)
+    for i in json.load(open(os.path.join(here, "deletes.json"))):
+        ds.delete(i, commit=False)
+    ds.commit()
+    answered = unsupported = 0
+    for ln in open(os.path.join(here, "cases.jsonl")):
+        c = json.loads(ln)
+        b = c["body"]
+        try:
+            res = ds.search(b["query"], b["filters"], b["page"]["page"], b["page"]["per_page"])
+        except nat.FgError as e:
+            if e.code == nat.FG_ERR_UNSUPPORTED:
+                unsupported += 1
+                continue
+            assert e.code == nat.FG_ERR_INVALID and "error" in c, (b, str(e))
+            continue
+        assert "error" not in c, b
+        want = c["hits"]
+        assert len(res) == len(want), b
+        for j, (r, (wid, ws)) in enumerate(zip(res, want)):
+            assert abs(r.score - ws) <= 1e-5 * max(abs(ws), 1e-30), (b, j, r.score, ws)
+            if r.id != wid:  # only inside a run of tied scores (or a tie cut by the end of the page)
+                tie = [x for x in range(len(want)) if abs(want[x][1] - ws) <= 4e-5 * abs(ws)]
+                assert r.id in [want[x][0] for x in tie] or max(tie) == len(want) - 1, (b, j, r.id, wid)
+        answered += 1
+    assert answered >= 250 and answered + unsupported >= 355, (answered, unsupported)
+    ds.close()
