@@ -374,11 +374,14 @@ class Index:
         check(lib().fg_search_batch(self.h, C.byref(batch.batch), ks, _ptr(hits), _ptr(n), _ptr(cnt)))
         return hits, n, cnt
 
-    def search_union_of(self, disjuncts: HostBatch, k: int):
-        """fg_search_union_of: the batch's queries are the Should children (boolean queries themselves) of ONE query.
-        Returns (hits[n], match_count)."""
+    def search_union_of(self, disjuncts: HostBatch, k: int, n_filters: int = 0):
+        """fg_search_union_of[_filtered]: the batch's queries are the Should children (boolean queries themselves) of ONE
+        query; the last n_filters of them are filter children. Returns (hits[n], match_count)."""
         hits = np.zeros(max(k, 1), HIT_DT)
         n, cnt = C.c_uint32(), C.c_uint32()
+        if n_filters:
+            check(lib().fg_search_union_of_filtered(self.h, C.byref(disjuncts.batch), n_filters, k, _ptr(hits), C.byref(n), C.byref(cnt)))
+            return hits[:n.value], int(cnt.value)
         check(lib().fg_search_union_of(self.h, C.byref(disjuncts.batch), k, _ptr(hits), C.byref(n), C.byref(cnt)))
         return hits[:n.value], int(cnt.value)
 

@@ -696,17 +696,26 @@ int32_t orc_search_batch(const fg_index_desc* d, const fg_query_batch* qb, uint3
 // One query whose Should children are the batch's queries (each a one-level plan): tantivy's BooleanQuery of boolean
 // queries, e.g. `(a AND b) OR (c AND d)`. complex_scorer builds each child's scorer and puts them under the buffered
 // union (A.5): a document matches when any child matches and scores the sum of the matching children.
-int32_t orc_search_union_of(const fg_index_desc* d, const fg_query_batch* disjuncts, uint32_t k, fg_hit* hits, uint32_t* n_hits,
-                            uint32_t* match_count) {
-    if (k == 0) return FG_ERR_INVALID;
+// With n_filters > 0 the LAST n_filters queries are Must siblings of that union -- Bool[Must(union), Must(f)..], what
+// Dataset::search builds from a nested text query and a facet query (/root/reference/src/db/search.rs:140-144): an
+// Intersection of the union and the filters (counterpart of fg_search_union_of_filtered).
+int32_t orc_search_union_of_filtered(const fg_index_desc* d, const fg_query_batch* disjuncts, uint32_t n_filters, uint32_t k, fg_hit* hits,
+                                     uint32_t* n_hits, uint32_t* match_count) {
+    if (k == 0 || n_filters >= disjuncts->n_queries) return FG_ERR_INVALID;
     Index ix = make_index(d);
-    std::vector<std::unique_ptr<Scorer>> kids;
+    std::vector<std::unique_ptr<Scorer>> kids, filters;
     for (uint32_t qi = 0; qi < disjuncts->n_queries; qi++) {
         BuiltQuery bq = build(ix, *disjuncts, disjuncts->queries[qi]);
         if (bq.unsupported) return FG_ERR_UNSUPPORTED;
-        kids.push_back(std::move(bq.scorer));
+        (qi + n_filters >= disjuncts->n_queries ? filters : kids).push_back(std::move(bq.scorer));
     }
     std::unique_ptr<Scorer> u = make_union(std::move(kids));
+    if (!filters.empty()) {
+        std::vector<std::unique_ptr<Scorer>> musts;
+        musts.push_back(std::move(u));
+        for (auto& f : filters) musts.push_back(std::move(f));
+        u.reset(new IntersectionScorer(std::move(musts)));
+    }
     TopN top(k);
     uint32_t cnt = 0;
     for (uint32_t doc = u->doc(); doc != TERMINATED; doc = u->advance()) {
@@ -722,6 +731,10 @@ int32_t orc_search_union_of(const fg_index_desc* d, const fg_query_batch* disjun
     *n_hits = (uint32_t)r.size();
     if (match_count) *match_count = cnt;
     return FG_OK;
+}
+int32_t orc_search_union_of(const fg_index_desc* d, const fg_query_batch* disjuncts, uint32_t k, fg_hit* hits, uint32_t* n_hits,
+                            uint32_t* match_count) {
+    return orc_search_union_of_filtered(d, disjuncts, 0, k, hits, n_hits, match_count);
 }
 
 // Block-max metadata of an index (what tantivy keeps in its skip entries): built once, released with orc_blockmax_free.

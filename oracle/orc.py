@@ -73,6 +73,8 @@ def lib():
         L.orc_algorithmic_bytes.restype = i32
         L.orc_search_union_of.argtypes = [C.POINTER(nat.IndexDesc), C.POINTER(nat.QueryBatch), u32, vp, C.POINTER(u32), C.POINTER(u32)]
         L.orc_search_union_of.restype = i32
+        L.orc_search_union_of_filtered.argtypes = [C.POINTER(nat.IndexDesc), C.POINTER(nat.QueryBatch), u32, u32, vp, C.POINTER(u32), C.POINTER(u32)]
+        L.orc_search_union_of_filtered.restype = i32
         L.orc_blockmax_build.argtypes = [C.POINTER(nat.IndexDesc), i32]
         L.orc_blockmax_build.restype = vp
         L.orc_blockmax_free.argtypes = [vp]
@@ -132,11 +134,12 @@ def algorithmic_bytes(desc: nat.HostIndexDesc, batch: nat.HostBatch, threads: in
     return b, s
 
 
-def search_union_of(desc: nat.HostIndexDesc, disjuncts: nat.HostBatch, k: int):
-    """One query whose Should children are the batch's queries (BooleanQuery of boolean queries). Returns (hits, count)."""
+def search_union_of(desc: nat.HostIndexDesc, disjuncts: nat.HostBatch, k: int, n_filters: int = 0):
+    """One query whose Should children are the batch's queries (BooleanQuery of boolean queries); the last n_filters of
+    them are Must siblings of that union (facet filters). Returns (hits, count)."""
     hits = np.zeros(max(k, 1), nat.HIT_DT)
     n, cnt = C.c_uint32(), C.c_uint32()
-    rc = lib().orc_search_union_of(C.byref(desc.desc), C.byref(disjuncts.batch), k, hits.ctypes.data, C.byref(n), C.byref(cnt))
+    rc = lib().orc_search_union_of_filtered(C.byref(desc.desc), C.byref(disjuncts.batch), n_filters, k, hits.ctypes.data, C.byref(n), C.byref(cnt))
     if rc != 0:
         raise nat.FgError(rc, "oracle")
     return hits[:n.value], int(cnt.value)

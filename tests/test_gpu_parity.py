@@ -754,6 +754,21 @@ def test_union_of_boolean_queries(ctx):
             g_hits, g_cnt = index.search_union_of(batch, k)
             assert g_cnt == o_cnt and len(g_hits) == len(o_hits), (ci, k, g_cnt, o_cnt, len(g_hits), len(o_hits))
             check_topk(g_hits, o_hits, k, ctx=f"union-of case {ci}, k = {k}")
+    # filter children (fg_search_union_of_filtered): Bool[Must(union of the children), Must(filter)..] -- a document needs
+    # an ordinary child and every filter, the filters score once. Against the oracle's Intersection(union, filters).
+    fcases = [
+        ([[(M, W(3)), (M, W(40))], [(M, W(7)), (M, W(120))], [(S, W(1))]], 1),                   # ((a AND b) OR (c AND d)) AND f
+        ([[(S, W(900))], [(M, W(1)), (M, W(2))], [(M, W(0)), (M, [(0, 900, 0.0), (0, 1, 0.0), (0, 2, 0.0)])]], 1),  # the planner's form: f AND any-text^0
+        ([[(M, W(10)), (N, W(0))], [(M, W(60)), (M, W(61))], [(S, W(5))], [(S, W(2))]], 2),       # two filters
+        ([[(M, W(2500)), (M, W(2900))], [(M, W(3)), (M, W(4))], [(S, W(2999))]], 1),              # rare filter: few or no matches
+    ]
+    for ci, (disj, nf) in enumerate(fcases):
+        batch = nat.HostBatch([{"k": 1, "clauses": cl} for cl in disj])
+        for k in (10, 100, 3000):
+            o_hits, o_cnt = orc.search_union_of(desc, batch, k, n_filters=nf)
+            g_hits, g_cnt = index.search_union_of(batch, k, n_filters=nf)
+            assert g_cnt == o_cnt and len(g_hits) == len(o_hits), (ci, k, g_cnt, o_cnt, len(g_hits), len(o_hits))
+            check_topk(g_hits, o_hits, k, ctx=f"filtered union-of case {ci}, k = {k}")
     # with deleted documents (an alive bitset on the same postings)
     rng = np.random.default_rng(11)
     alive = np.full((cfg.n_docs + 31) // 32, 0xFFFFFFFF, np.uint32)
