@@ -180,7 +180,8 @@ class Unsupported(Exception):
     pass
 
 
-_TOKEN = re.compile(r'\s*(\(|\)|"[^"]*"|[^\s()":^]+|\^[0-9.]+|:|")')
+# (a boost is `^` + a float as nom's `double` reads it: sign, digits, fraction, exponent)
+_TOKEN = re.compile(r'\s*(\(|\)|"[^"]*"|[^\s()":^]+|\^[-+]?(?:[0-9]+\.?[0-9]*|\.[0-9]+)(?:[eE][-+]?[0-9]+)?|:|")')
 
 
 class _Tok(str):

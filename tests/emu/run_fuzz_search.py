@@ -45,10 +45,10 @@ def term():
     r = rng.random()
     if r < 0.1: t = "text:" + t
     elif r < 0.2: t = "name:" + t
-    if rng.random() < 0.15: t += rng.choice(["^2", "^0.5", "^3.5"])
+    if rng.random() < 0.15: t += rng.choice(["^2", "^0.5", "^3.5", "^2", "^0.5", "^0", "^-1", "^1e3", "^.5"])
     return t
 def group(depth):
-    n = rng.randint(1, 4)
+    n = rng.randint(1, 4) if rng.random() < 0.92 else rng.randint(8, 20)  # (long ones: up to and beyond 32 leaves)
     parts = []
     for _ in range(n):
         if depth < 2 and rng.random() < 0.3:
@@ -70,7 +70,8 @@ for it in range(nq):
     q = group(0)
     if rng.random() < 0.03: q = rng.choice(["", "  ", "*", "* w1", "w1 AND *"])
     fl = rng.choice([[], [], [], ["/ns/n1"], ["/ns/n2", "/kind/k0/*"], ["*x*"], ["/nope"]])
-    page, pp = rng.choice([(0, 10), (0, 20), (1, 5), (0, 100), (3, 7), (11, 100), (0, 1)])
+    page, pp = rng.choice([(0, 10), (0, 20), (1, 5), (0, 100), (3, 7), (11, 100), (0, 1), (0, 10), (0, 20), (0, 32), (0, 33), (0, 128), (0, 129),
+                           (7, 128), (0, 300), (0, 1024), (0, 1025)])  # (the top-k queue sizes 32 / 128 / 1024 and one past each)
     try:
         want, _ = op.search(ix, q, fl, page, pp)
         werr = None
