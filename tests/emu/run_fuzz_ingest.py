@@ -24,6 +24,11 @@ ctx = nat.Context(0); ds = Dataset(ctx); ix = op.PyIndex()
 next_id = 0; live = []
 def make(i):
     text = " ".join(word() for _ in range(rng.randint(2, 30)))
+    r_ = rng.random()
+    if r_ < 0.04: text = " ".join([word()] * rng.randint(256, 400)) + " " + word()   # tf above 255: no tf column for that term
+    elif r_ < 0.06: text = "!!! ??? ..."                                             # a document without a token
+    elif r_ < 0.09: text = " ".join(word() for _ in range(rng.randint(500, 3000)))   # long: the upper fieldnorm buckets
+    elif r_ < 0.11: text = "w1-w2 W3,w4. É" + word()                                 # punctuation, case, non-ASCII
     name = " ".join(word() for _ in range(rng.randint(1, 3))) if rng.random() < 0.3 else None
     facets = [f"/ns/n{i % 4}"]
     return ObjectRecord(id=f"d{i}", text=text, metadata={"name": name} if name else None, facets=facets), name
