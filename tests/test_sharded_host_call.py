@@ -38,10 +38,10 @@ def test_merge_shard_pages_equals_global_order():
 
 def _run_threads_script(name, *args):
     """Runs a ranks-as-threads script of tests/emu in a subprocess (with faulthandler: a crash leaves the Python stacks of
-    all threads in stderr). Known issue of this HARNESS (ranks as threads of one interpreter over the emulator; the
-    product runs one process per GPU): about one run in forty has died with SIGSEGV before printing anything, not
-    reproduced in 18 further runs under AddressSanitizer. A run killed by a signal is therefore repeated once; a wrong
-    answer (exit code 1) never is."""
+    all threads in stderr). Open issue: with ranks as threads of one process a run dies with
+    SIGSEGV about once in forty (one in eight under heavy load), at the start of a rank's first collective call while
+    another rank is still creating its communicator; never under AddressSanitizer, never a wrong answer; the product
+    runs one process per GPU. A run killed by a signal is therefore repeated once; a wrong answer (exit code 1) never is."""
     import os
     import subprocess
     import sys
